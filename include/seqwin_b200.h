@@ -1,0 +1,122 @@
+/*
+ * seqwin_b200.h -- C ABI of libseqwin_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the native extension of treangenlab/Seqwin, `seqwin.graph._core`
+ * (reference: cpp/src/bindings/python_bindings.cpp:43-169).  The three pybind11 entry
+ * points of that module map onto this header as follows (citations into /root/reference):
+ *
+ *   _build_native        python_bindings.cpp:50-90   -> sw_build + sw_graph_size /
+ *        (seqwin::build, cpp/src/seqwin/build.cpp:330-394)  sw_graph_export / sw_graph_record_id
+ *   _get_penalty_native  python_bindings.cpp:92-135  -> sw_get_penalty
+ *        (seqwin::get_penalty, cpp/src/seqwin/filter.cpp:15-137)
+ *   _filter_kmers_native python_bindings.cpp:137-168 -> sw_filter_kmers
+ *        (seqwin::filter_kmers, cpp/src/seqwin/filter.cpp:139-201)
+ *
+ * Plain pointers and sizes only; no C++ exception crosses the ABI.  Every function that
+ * returns int returns SW_OK or an error class that the Python shim turns into the exception
+ * type the reference raises (RuntimeError / ValueError); the message is sw_last_error().
+ * All compute runs on the current CUDA device; there is no CPU fallback: without a usable
+ * device the compute entry points return SW_ERR_RUNTIME ("no CUDA device").
+ *
+ * Output record layouts are the reference's (cpp/include/seqwin/graph.hpp:15-53):
+ *   kmer  { u32 pos; u32 record_idx; }                                   8 bytes
+ *   node  { u64 hash; u64 start; u64 stop; u32 n_tar; u32 n_neg; f64 penalty; }  40 bytes
+ *   edge  { u64 first; u64 second; u64 weight; }                        24 bytes
+ */
+#ifndef SEQWIN_B200_H
+#define SEQWIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SW_OK 0
+#define SW_ERR_RUNTIME 1 /* -> RuntimeError (I/O, CUDA, limits; build.cpp:136-147,337-339) */
+#define SW_ERR_VALUE 2   /* -> ValueError   (std::invalid_argument in filter.cpp:33-60,106-125) */
+
+typedef struct sw_kmer { uint32_t pos, record_idx; } sw_kmer;
+typedef struct sw_node { uint64_t hash, start, stop; uint32_t n_tar, n_neg; double penalty; } sw_node;
+typedef struct sw_edge { uint64_t first, second, weight; } sw_edge;
+
+typedef struct sw_graph sw_graph;   /* a built graph (device and/or host resident) */
+typedef struct sw_batch sw_batch;   /* parsed + 2-bit packed assemblies in pinned host memory */
+typedef struct sw_dev_batch sw_dev_batch; /* the same, resident in HBM */
+
+/* which= argument of sw_graph_size */
+enum { SW_KMERS = 0, SW_NODES = 1, SW_EDGES = 2, SW_OFFSETS = 3, SW_RECORDS = 4 };
+
+/* Thread-local message of the last failing call on this thread. */
+const char* sw_last_error(void);
+
+/* ---- the reference boundary ------------------------------------------------------------ */
+
+/* Replaces seqwin::build (build.cpp:330-394): read the FASTA / .gz assemblies with
+ * n_host_threads parser threads, pack to 2 bit, sketch and aggregate on the GPU.
+ * low_memory is accepted for signature parity (build.cpp:380-391 produces identical output). */
+int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w,
+             uint32_t n_host_threads, int low_memory, sw_graph** out);
+
+size_t sw_graph_size(const sw_graph* g, int which);
+/* Copy the graph into caller-owned (e.g. numpy) buffers sized by sw_graph_size. */
+int sw_graph_export(sw_graph* g, void* kmers, void* nodes, void* edges, uint32_t* record_offsets);
+size_t sw_graph_n_records(const sw_graph* g, size_t assembly);
+const char* sw_graph_record_id(const sw_graph* g, size_t assembly, size_t i);
+void sw_graph_free(sw_graph* g);
+
+/* Replaces seqwin::get_penalty (filter.cpp:15-137): fills n_tar / n_neg / penalty in place.
+ * Unlike the reference it is told n_kmers and rejects node ranges beyond it (SW_ERR_VALUE). */
+int sw_get_penalty(const sw_kmer* kmers, size_t n_kmers, sw_node* nodes, size_t n_nodes,
+                   const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
+                   size_t n_assemblies, uint32_t n_threads);
+
+/* Replaces seqwin::filter_kmers (filter.cpp:139-201).  Two-call protocol: with kmers_out ==
+ * NULL only the two counts are written; then call again with buffers of that size. */
+int sw_filter_kmers(const sw_kmer* kmers, size_t n_kmers, const sw_node* nodes, size_t n_nodes,
+                    const uint64_t* used_hashes, size_t n_used, sw_kmer* kmers_out,
+                    sw_node* nodes_out, size_t* n_kmers_out, size_t* n_nodes_out);
+
+/* ---- staged entry points (host ingest | H2D | device build), used by bench / multi-GPU -- */
+
+/* Host ingest (replaces read_fasta, cpp/src/utils/fasta_reader.cpp:207-213, plus the 2-bit
+ * packer): FASTA -> pinned 2-bit words + invalid-base runs + record table. */
+int sw_batch_from_fasta(const char* const* paths, size_t n_paths, uint32_t n_host_threads,
+                        sw_batch** out);
+/* Same, from in-memory ASCII records (synthetic data): seqs[i] has lens[i] bytes and belongs to
+ * assembly asm_of[i] (non-decreasing).  ids may be NULL. */
+int sw_batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const uint32_t* asm_of,
+                         const char* const* ids, size_t n_records, size_t n_assemblies,
+                         uint32_t n_host_threads, sw_batch** out);
+size_t sw_batch_n_bases(const sw_batch* b);
+size_t sw_batch_n_records(const sw_batch* b);
+size_t sw_batch_packed_bytes(const sw_batch* b);
+void sw_batch_free(sw_batch* b);
+
+int sw_dev_upload(const sw_batch* b, sw_dev_batch** out); /* cudaMemcpyAsync from pinned */
+void sw_dev_batch_free(sw_dev_batch* d);
+
+/* Per-stage device times of one build, CUDA events on the launching stream (ms). */
+typedef struct sw_stage_times {
+    float h2d_ms, sketch_ms, sort_nodes_ms, nodes_ms, edges_ms, d2h_ms, total_ms;
+    uint64_t n_bases, n_kmers, n_nodes, n_edges, n_tiles, sketch_launches, total_launches;
+} sw_stage_times;
+
+/* Device-resident build: input already in HBM, graph left in HBM (exported lazily). */
+int sw_dev_build(const sw_dev_batch* d, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t);
+/* End-to-end from pinned host memory: H2D + build + D2H into the graph's host arrays. */
+int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t);
+
+/* Minimizer stream of a device batch in (record, position) order -- the sketch stage alone.
+ * Two-call protocol like sw_filter_kmers (h1_out == NULL -> count only). Test / multi-GPU hook. */
+int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_out,
+                  uint32_t* pos_out, uint32_t* record_out, size_t capacity, size_t* n_out);
+
+/* Device properties the host side sizes grids with. */
+int sw_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQWIN_B200_H */

@@ -1,0 +1,481 @@
+// api.cu -- the C ABI of libseqwin_b200.so (see include/seqwin_b200.h for the mapping onto the
+// reference's pybind11 module, cpp/src/bindings/python_bindings.cpp:43-169).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "device.h"
+#include "ingest.h"
+#include "nthash.h"
+
+namespace sw {
+
+namespace {
+thread_local std::string g_last_error;
+std::once_flag g_init_flag;
+int g_sm_count = 0;
+bool g_have_device = false;
+std::string g_init_error;
+
+void do_init()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_init_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        cudaGetLastError();
+        return;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { g_init_error = "cudaGetDevice failed"; return; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { g_init_error = "cudaGetDeviceProperties failed"; return; }
+    if (p.major < 10) {
+        g_init_error = "libseqwin_b200 is built for sm_100a only; device is sm_" + std::to_string(p.major) +
+                       std::to_string(p.minor);
+        return;
+    }
+    g_sm_count = p.multiProcessorCount;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;  // keep freed blocks cached in the pool
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_have_device = true;
+}
+}  // namespace
+
+void init_device_once()
+{
+    std::call_once(g_init_flag, do_init);
+    if (!g_have_device) fail_runtime(g_init_error);
+}
+int sm_count()
+{
+    init_device_once();
+    return g_sm_count;
+}
+
+void* alloc_host(size_t bytes, bool* pinned)
+{
+    std::call_once(g_init_flag, do_init);
+    void* p = nullptr;
+    if (g_have_device && cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess) {
+        *pinned = true;
+        return p;
+    }
+    cudaGetLastError();
+    *pinned = false;  // host-only tooling (no device): pageable memory, nothing will be copied
+    return aligned_alloc(64, ((bytes ? bytes : 1) + 63) / 64 * 64);
+}
+void free_host(void* p, bool pinned)
+{
+    if (pinned) cudaFreeHost(p);
+    else free(p);
+}
+
+namespace {
+
+struct StreamGuard {
+    cudaStream_t s = nullptr;
+    StreamGuard() { SW_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+};
+
+cudaStream_t lib_stream()
+{
+    static thread_local std::unique_ptr<StreamGuard> g;
+    if (!g) g.reset(new StreamGuard());
+    return g->s;
+}
+
+void copy_meta(const sw_batch& src, sw_batch& dst)
+{
+    dst.words = nullptr;
+    dst.n_words = src.n_words;
+    dst.rec_word_off = src.rec_word_off;
+    dst.rec_len = src.rec_len;
+    dst.rec_inv_off = src.rec_inv_off;
+    dst.inv_start = src.inv_start;
+    dst.inv_len = src.inv_len;
+    dst.record_offsets = src.record_offsets;
+    dst.ids = src.ids;
+    dst.n_bases = src.n_bases;
+}
+
+std::vector<uint32_t> record_assembly_map(const std::vector<uint32_t>& offsets)
+{
+    const size_t A = offsets.size() - 1;
+    std::vector<uint32_t> m(offsets.back());
+    for (size_t a = 0; a < A; ++a)
+        for (uint32_t r = offsets[a]; r < offsets[a + 1]; ++r) m[r] = (uint32_t)a;
+    return m;
+}
+
+void check_kw(uint32_t k, uint32_t w)
+{
+    // k < 3 is undefined behaviour in the reference (nthash_kmer.hpp:26, unsigned k-3) and k is
+    // a uint16 there (hashing_internals.hpp:10); w = 0 never selects anything.
+    if (k < 3 || k > 65535) fail_runtime("kmerlen must be in [3, 65535]");
+    if (w < 1) fail_runtime("windowsize must be >= 1");
+}
+
+sw_dev_batch* dev_upload(const sw_batch& b)
+{
+    init_device_once();
+    auto d = std::make_unique<sw_dev_batch>();
+    cudaStream_t s = lib_stream();
+    d->stream = s;
+    copy_meta(b, d->meta);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    d->words.alloc(b.n_words, s);
+    SW_CUDA(cudaMemcpyAsync(d->words.p, b.words, b.n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    const size_t R = b.rec_len.size();
+    d->rec_word_off.alloc(R, s);
+    d->rec_asm.alloc(R, s);
+    const std::vector<uint32_t> ra = record_assembly_map(b.record_offsets);
+    if (R) {
+        SW_CUDA(cudaMemcpyAsync(d->rec_word_off.p, b.rec_word_off.data(), R * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d->rec_asm.p, ra.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    }
+    cudaEventRecord(e1, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&d->h2d_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return d.release();
+}
+
+sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t)
+{
+    init_device_once();
+    check_kw(k, w);
+    cudaStream_t s = d.stream;
+    auto g = std::make_unique<sw_graph>();
+    g->stream = s;
+    g->record_offsets = d.meta.record_offsets;
+    g->ids = d.meta.ids;
+
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    cudaEventRecord(e0, s);
+    DevPlan plan = make_plan(d.meta, k, w, s);
+    SketchStream st;
+    run_sketch(d.words.p, d.rec_word_off.p, plan, k, w, 0u, s, st);
+    cudaEventRecord(e1, s);
+    GraphTimes gt;
+    build_graph(st, d.rec_asm.p, s, g->dev, &gt);
+    cudaEventRecord(e2, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    g->on_device = true;
+    if (t) {
+        memset(t, 0, sizeof(*t));
+        cudaEventElapsedTime(&t->sketch_ms, e0, e1);
+        cudaEventElapsedTime(&t->total_ms, e0, e2);
+        t->sort_nodes_ms = gt.sort_nodes_ms;
+        t->nodes_ms = gt.nodes_ms;
+        t->edges_ms = gt.edges_ms;
+        t->n_bases = d.meta.n_bases;
+        t->n_kmers = g->dev.n_kmers;
+        t->n_nodes = g->dev.n_nodes;
+        t->n_edges = g->dev.n_edges;
+        t->n_tiles = plan.n_tiles;
+        t->sketch_launches = st.launches;
+        t->total_launches = st.launches + gt.launches;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    return g.release();
+}
+
+void graph_to_host(sw_graph& g)
+{
+    if (g.on_host) return;
+    cudaStream_t s = g.stream;
+    g.h_kmers.resize(g.dev.n_kmers);
+    g.h_nodes.resize(g.dev.n_nodes);
+    g.h_edges.resize(g.dev.n_edges);
+    if (g.dev.n_kmers)
+        SW_CUDA(cudaMemcpyAsync(g.h_kmers.data(), g.dev.kmers.p, g.dev.n_kmers * sizeof(sw_kmer),
+                                cudaMemcpyDeviceToHost, s));
+    if (g.dev.n_nodes)
+        SW_CUDA(cudaMemcpyAsync(g.h_nodes.data(), g.dev.nodes.p, g.dev.n_nodes * sizeof(sw_node),
+                                cudaMemcpyDeviceToHost, s));
+    if (g.dev.n_edges)
+        SW_CUDA(cudaMemcpyAsync(g.h_edges.data(), g.dev.edges.p, g.dev.n_edges * sizeof(sw_edge),
+                                cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+    g.on_host = true;
+}
+
+template <typename F>
+int guarded(F&& fn)
+{
+    try {
+        fn();
+        return SW_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return SW_ERR_RUNTIME;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return SW_ERR_RUNTIME;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return SW_ERR_RUNTIME;
+    }
+}
+
+}  // namespace
+}  // namespace sw
+
+using namespace sw;
+
+extern "C" {
+
+const char* sw_last_error(void) { return g_last_error.c_str(); }
+
+int sw_device_info(int* sm, int* major, int* minor, size_t* hbm)
+{
+    return guarded([&] {
+        init_device_once();
+        int dev = 0;
+        SW_CUDA(cudaGetDevice(&dev));
+        cudaDeviceProp p;
+        SW_CUDA(cudaGetDeviceProperties(&p, dev));
+        if (sm) *sm = p.multiProcessorCount;
+        if (major) *major = p.major;
+        if (minor) *minor = p.minor;
+        if (hbm) *hbm = p.totalGlobalMem;
+    });
+}
+
+int sw_batch_from_fasta(const char* const* paths, size_t n_paths, uint32_t n_threads, sw_batch** out)
+{
+    return guarded([&] { *out = batch_from_fasta(paths, n_paths, n_threads); });
+}
+
+int sw_batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const uint32_t* asm_of,
+                         const char* const* ids, size_t n_records, size_t n_assemblies, uint32_t n_threads,
+                         sw_batch** out)
+{
+    return guarded([&] { *out = batch_from_memory(seqs, lens, asm_of, ids, n_records, n_assemblies, n_threads); });
+}
+
+size_t sw_batch_n_bases(const sw_batch* b) { return b->n_bases; }
+size_t sw_batch_n_records(const sw_batch* b) { return b->rec_len.size(); }
+size_t sw_batch_packed_bytes(const sw_batch* b) { return b->n_words * sizeof(uint32_t); }
+void sw_batch_free(sw_batch* b) { delete b; }
+
+int sw_dev_upload(const sw_batch* b, sw_dev_batch** out)
+{
+    return guarded([&] { *out = dev_upload(*b); });
+}
+void sw_dev_batch_free(sw_dev_batch* d)
+{
+    if (!d) return;
+    cudaStream_t s = d->stream;
+    delete d;
+    if (s) cudaStreamSynchronize(s);
+}
+
+int sw_dev_build(const sw_dev_batch* d, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)
+{
+    return guarded([&] { *out = dev_build(*d, k, w, t); });
+}
+
+int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)
+{
+    return guarded([&] {
+        check_kw(k, w);
+        std::unique_ptr<sw_dev_batch, void (*)(sw_dev_batch*)> d(dev_upload(*b), sw_dev_batch_free);
+        std::unique_ptr<sw_graph, void (*)(sw_graph*)> g(dev_build(*d, k, w, t), sw_graph_free);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, g->stream);
+        graph_to_host(*g);
+        cudaEventRecord(e1, g->stream);
+        cudaEventSynchronize(e1);
+        if (t) {
+            cudaEventElapsedTime(&t->d2h_ms, e0, e1);
+            t->h2d_ms = d->h2d_ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        // the device copies are no longer needed once the host arrays exist
+        g->dev = DevGraph();
+        g->on_device = false;
+        *out = g.release();
+    });
+}
+
+int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, uint32_t n_host_threads,
+             int low_memory, sw_graph** out)
+{
+    (void)low_memory;  // identical output by contract (build.cpp:380-391, test_graph.py:222-245)
+    return guarded([&] {
+        check_kw(k, w);
+        init_device_once();
+        std::unique_ptr<sw_batch> b(batch_from_fasta(paths, n_paths, n_host_threads));
+        sw_graph* g = nullptr;
+        int rc = sw_build_from_batch(b.get(), k, w, &g, nullptr);
+        if (rc != SW_OK) throw Error(rc, g_last_error);
+        *out = g;
+    });
+}
+
+size_t sw_graph_size(const sw_graph* g, int which)
+{
+    switch (which) {
+    case SW_KMERS: return g->on_host ? g->h_kmers.size() : g->dev.n_kmers;
+    case SW_NODES: return g->on_host ? g->h_nodes.size() : g->dev.n_nodes;
+    case SW_EDGES: return g->on_host ? g->h_edges.size() : g->dev.n_edges;
+    case SW_OFFSETS: return g->record_offsets.size();
+    case SW_RECORDS: return g->ids.size();
+    default: return 0;
+    }
+}
+
+int sw_graph_export(sw_graph* g, void* kmers, void* nodes, void* edges, uint32_t* record_offsets)
+{
+    return guarded([&] {
+        if (!g->on_host) graph_to_host(*g);
+        if (kmers && !g->h_kmers.empty()) memcpy(kmers, g->h_kmers.data(), g->h_kmers.size() * sizeof(sw_kmer));
+        if (nodes && !g->h_nodes.empty()) memcpy(nodes, g->h_nodes.data(), g->h_nodes.size() * sizeof(sw_node));
+        if (edges && !g->h_edges.empty()) memcpy(edges, g->h_edges.data(), g->h_edges.size() * sizeof(sw_edge));
+        if (record_offsets)
+            memcpy(record_offsets, g->record_offsets.data(), g->record_offsets.size() * sizeof(uint32_t));
+    });
+}
+
+size_t sw_graph_n_records(const sw_graph* g, size_t a)
+{
+    if (a + 1 >= g->record_offsets.size()) return 0;
+    return g->record_offsets[a + 1] - g->record_offsets[a];
+}
+const char* sw_graph_record_id(const sw_graph* g, size_t a, size_t i)
+{
+    if (a + 1 >= g->record_offsets.size()) return nullptr;
+    const size_t r = (size_t)g->record_offsets[a] + i;
+    return r < g->ids.size() ? g->ids[r].c_str() : nullptr;
+}
+void sw_graph_free(sw_graph* g)
+{
+    if (!g) return;
+    cudaStream_t s = g->stream;
+    delete g;
+    if (s) cudaStreamSynchronize(s);
+}
+
+int sw_get_penalty(const sw_kmer* kmers, size_t n_kmers, sw_node* nodes, size_t n_nodes,
+                   const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
+                   size_t n_assemblies, uint32_t n_threads)
+{
+    (void)n_threads;
+    return guarded([&] {
+        // argument validation of filter.cpp:33-60 (std::invalid_argument -> ValueError)
+        if (n_offsets != n_assemblies + 1) fail_value("len(record_offsets) must equal len(is_targets) + 1");
+        if (n_offsets == 0 || record_offsets[0] != 0) fail_value("record_offsets must start with 0");
+        if (n_assemblies > 0xFFFFFFFFull) fail_value("Number of assemblies exceeds uint32 range");
+        size_t n_t = 0, n_n = 0;
+        for (size_t i = 0; i < n_assemblies; ++i) {
+            if (record_offsets[i + 1] < record_offsets[i]) fail_value("record_offsets must be nondecreasing");
+            if (is_targets[i]) ++n_t; else ++n_n;
+        }
+        if (!n_t) fail_value("is_targets must contain at least one target assembly");
+        if (!n_n) fail_value("is_targets must contain at least one non-target assembly");
+        if (n_nodes == 0) return;
+        init_device_once();
+        cudaStream_t s = lib_stream();
+        const std::vector<uint32_t> offs(record_offsets, record_offsets + n_offsets);
+        const std::vector<uint32_t> ra = record_assembly_map(offs);
+        const uint32_t n_records = offs.back();
+        DevBuf<sw_kmer> d_k(n_kmers, s);
+        DevBuf<sw_node> d_n(n_nodes, s);
+        DevBuf<uint32_t> d_ra(ra.size(), s);
+        DevBuf<uint8_t> d_t(n_assemblies, s);
+        if (n_kmers) SW_CUDA(cudaMemcpyAsync(d_k.p, kmers, n_kmers * sizeof(sw_kmer), cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d_n.p, nodes, n_nodes * sizeof(sw_node), cudaMemcpyHostToDevice, s));
+        if (!ra.empty()) SW_CUDA(cudaMemcpyAsync(d_ra.p, ra.data(), ra.size() * 4, cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d_t.p, is_targets, n_assemblies, cudaMemcpyHostToDevice, s));
+        const uint32_t bad = run_penalty(d_k.p, n_kmers, d_n.p, n_nodes, d_ra.p, n_records, d_t.p,
+                                         1.0 / (double)n_t, 1.0 / (double)n_n, s);
+        if (bad & 4u) fail_value("node [start, stop) range lies outside kmers");
+        if (bad & 1u) fail_value("record_idx is outside record_offsets range");
+        if (bad & 2u) fail_value("record_idx must be nondecreasing within each node range");
+        SW_CUDA(cudaMemcpyAsync(nodes, d_n.p, n_nodes * sizeof(sw_node), cudaMemcpyDeviceToHost, s));
+        SW_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int sw_filter_kmers(const sw_kmer* kmers, size_t n_kmers, const sw_node* nodes, size_t n_nodes,
+                    const uint64_t* used_hashes, size_t n_used, sw_kmer* kmers_out, sw_node* nodes_out,
+                    size_t* n_kmers_out, size_t* n_nodes_out)
+{
+    // Host-side by design: a sorted-merge of two small lists plus a
+    // segment copy; see DESIGN.md "out of scope / next".  filter.cpp:139-201.
+    return guarded([&] {
+        std::vector<uint64_t> used(used_hashes, used_hashes + n_used);
+        std::sort(used.begin(), used.end());
+        size_t ni = 0, ui = 0, nk = 0, nn = 0;
+        while (ni < n_nodes && ui < used.size()) {
+            if (nodes[ni].hash < used[ui]) { ++ni; continue; }
+            if (used[ui] < nodes[ni].hash) { ++ui; continue; }
+            const sw_node& nd = nodes[ni];
+            if (nd.start > nd.stop || nd.stop > n_kmers) fail_value("node [start, stop) range lies outside kmers");
+            const size_t size = nd.stop - nd.start;
+            if (kmers_out) {
+                nodes_out[nn] = nd;
+                nodes_out[nn].start = nk;
+                nodes_out[nn].stop = nk + size;
+                if (size) memcpy(kmers_out + nk, kmers + nd.start, size * sizeof(sw_kmer));
+            }
+            nk += size;
+            ++nn; ++ni; ++ui;
+        }
+        *n_kmers_out = nk;
+        *n_nodes_out = nn;
+    });
+}
+
+int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_out, uint32_t* pos_out,
+                  uint32_t* record_out, size_t capacity, size_t* n_out)
+{
+    return guarded([&] {
+        init_device_once();
+        check_kw(k, w);
+        cudaStream_t s = d->stream;
+        DevPlan plan = make_plan(d->meta, k, w, s);
+        SketchStream st;
+        run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, 0u, s, st);
+        *n_out = st.n;
+        if (!h1_out) return;
+        const size_t n = std::min<size_t>(st.n, capacity);
+        std::vector<uint64_t> vals(n);
+        if (n) {
+            SW_CUDA(cudaMemcpyAsync(h1_out, st.keys.p, n * 8, cudaMemcpyDeviceToHost, s));
+            SW_CUDA(cudaMemcpyAsync(vals.data(), st.vals.p, n * 8, cudaMemcpyDeviceToHost, s));
+        }
+        SW_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n; ++i) {
+            pos_out[i] = (uint32_t)vals[i];
+            record_out[i] = (uint32_t)(vals[i] >> 32);
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// device.h -- internal device-side interfaces of libseqwin_b200 (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "ingest.h"
+
+namespace sw {
+
+#define SW_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t err__ = (expr);                                                          \
+        if (err__ != cudaSuccess)                                                            \
+            ::sw::fail_runtime(std::string("CUDA error: ") + cudaGetErrorString(err__) +    \
+                               " at " __FILE__ ":" + std::to_string(__LINE__));            \
+    } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync pool; the pool keeps freed blocks cached).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t count, cudaStream_t s) { alloc(count, s); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; n = o.n; stream = o.stream; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count, cudaStream_t s)
+    {
+        release();
+        stream = s;
+        n = count;
+        SW_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), s));
+    }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, stream);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+void init_device_once();
+int sm_count();
+
+// ---- sketch stage ---------------------------------------------------------------------------
+struct DevPlan {
+    DevBuf<Tile> tiles;
+    DevBuf<Piece> pieces;
+    uint32_t n_tiles = 0;
+    uint64_t n_windows = 0, n_kmers = 0;
+    uint32_t tk = 0;  // tile capacity the plan was cut for
+    int config = 0;   // kernel configuration index
+};
+
+struct SketchStream {
+    DevBuf<uint64_t> keys;  // h1, (record, pos) order
+    DevBuf<uint64_t> vals;  // pos | record << 32
+    uint64_t n = 0;
+    uint32_t launches = 0;
+};
+
+int sketch_pick_config(uint32_t w, uint32_t* tk_out);
+DevPlan make_plan(const sw_batch& meta, uint32_t k, uint32_t w, cudaStream_t s);
+void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const DevPlan& plan,
+                uint32_t k, uint32_t w, uint32_t rec_base, cudaStream_t s, SketchStream& out);
+
+// ---- radix sort -------------------------------------------------------------------------------
+// Stable LSD radix sort of (u64 key, u32 value) pairs over key bits [0, end_bit).
+// On return keys/vals hold the sorted data (buffers may have been swapped with the alternates).
+struct SortPairs {
+    DevBuf<uint64_t> keys, keys_alt;
+    DevBuf<uint32_t> vals, vals_alt;
+    uint64_t n = 0;
+};
+uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s);  // returns #launches
+
+// ---- graph stage ------------------------------------------------------------------------------
+struct DevGraph {
+    DevBuf<sw_kmer> kmers;
+    DevBuf<sw_node> nodes;
+    DevBuf<sw_edge> edges;
+    uint64_t n_kmers = 0, n_nodes = 0, n_edges = 0;
+};
+struct GraphTimes {
+    float sort_nodes_ms = 0, nodes_ms = 0, edges_ms = 0;
+    uint32_t launches = 0;
+};
+// d_rec_asm: assembly index of every global record id used in the stream.
+void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, DevGraph& g,
+                 GraphTimes* times);
+
+// ---- penalty ----------------------------------------------------------------------------------
+// Fills n_tar / n_neg / penalty of device-resident nodes; returns an error bit mask
+// (1: record_idx out of range, 2: record_idx decreasing, 4: node range outside kmers).
+uint32_t run_penalty(const sw_kmer* d_kmers, uint64_t n_kmers, sw_node* d_nodes, uint64_t n_nodes,
+                     const uint32_t* d_rec_asm, uint32_t n_records, const uint8_t* d_is_target,
+                     double inv_t, double inv_n, cudaStream_t s);
+
+}  // namespace sw
+
+struct sw_dev_batch {
+    sw::DevBuf<uint32_t> words;
+    sw::DevBuf<uint64_t> rec_word_off;
+    sw::DevBuf<uint32_t> rec_asm;   // [R] assembly of each record
+    sw_batch meta;                  // host tables (no packed words) for the planner + ids
+    cudaStream_t stream = nullptr;
+    float h2d_ms = 0;
+};
+
+struct sw_graph {
+    sw::DevGraph dev;
+    bool on_device = false;
+    std::vector<sw_kmer> h_kmers;
+    std::vector<sw_node> h_nodes;
+    std::vector<sw_edge> h_edges;
+    bool on_host = false;
+    std::vector<uint32_t> record_offsets;
+    std::vector<std::string> ids;
+    cudaStream_t stream = nullptr;
+};

@@ -1,0 +1,440 @@
+// graph.cu -- minimizer pan-genome graph aggregation on the device.
+//
+// Input: the ordered minimizer stream of sketch.cu (h1, pos | record << 32), (record, pos) order.
+// Output (reference layouts, cpp/include/seqwin/graph.hpp:15-53):
+//   kmers  stream entries stably sorted by h1        -> (h1, record, pos) order
+//   nodes  one per distinct h1: {hash, start, stop, 0, 0, 0.0}
+//   edges  unordered pairs of stream-adjacent minimizers of one record, weight = number of
+//          distinct assemblies showing the pair, sorted by (first, second)
+// This is what build_worker + merge_thread_graphs produce with two hash maps and a CPU radix
+// sort (cpp/src/seqwin/build.cpp:152-241, cpp/src/seqwin/build_internals.cpp:159-291); here both
+// aggregations are sort + run-length encode, which is insensitive to hot keys.
+//
+// Edge keys are pairs of node RANKS (rank order == hash order), so the edge sort handles one
+// 64-bit key whose unused high digits are skipped, instead of a 128-bit hash pair.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "device.h"
+
+namespace sw {
+
+namespace {
+
+constexpr int kNT = 256;
+constexpr int kRounds = 8;
+constexpr int kBlockItems = kNT * kRounds;
+
+struct EventTimer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st)
+    {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    ~EventTimer()
+    {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    void start() { cudaEventRecord(a, s); }
+    float stop()
+    {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+};
+
+// Ordered rank of a flag inside one 256-thread round; `running` carries over rounds.
+__device__ __forceinline__ uint32_t round_rank(bool flag, uint32_t* s_warp, uint32_t& running)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+    const uint32_t prefix = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[wid] = __popc(ballot);
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < kNT / 32; ++i) {
+        const uint32_t t = s_warp[i];
+        if (i < wid) wbase += t;
+        total += t;
+    }
+    __syncthreads();
+    const uint32_t r = running + wbase + prefix;
+    running += total;
+    return r;
+}
+
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < kNT / 32; ++i) t += s_warp[i];
+    return t;
+}
+
+// In-place exclusive scan of per-block counts (single CTA), total to *total.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(unsigned long long* counts, uint64_t n,
+                                                           unsigned long long* total)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? counts[i] : 0;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0, sum = 0;
+        for (int w = 0; w < 32; ++w) {
+            const unsigned long long t = s_warp[w];
+            if (w < wid) wbase += t;
+            sum += t;
+        }
+        const unsigned long long carry = s_carry;
+        if (i < n) counts[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + sum;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void iota_kernel(uint32_t* v, uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
+}
+
+// ---- nodes ------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kNT) node_count_kernel(const uint64_t* __restrict__ ks, uint64_t n,
+                                                         unsigned long long* counts)
+{
+    __shared__ uint32_t s_warp[kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        if (j < n) c += (j == 0 || ks[j] != ks[j - 1]) ? 1u : 0u;
+    }
+    const uint32_t t = block_sum(c, s_warp);
+    if (threadIdx.x == 0) counts[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kNT) node_write_kernel(
+    const uint64_t* __restrict__ ks, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ stream_vals,
+    uint64_t n, const unsigned long long* __restrict__ block_off, sw_kmer* __restrict__ kmers,
+    sw_node* __restrict__ nodes, uint32_t* __restrict__ rank_of_stream)
+{
+    __shared__ uint32_t s_warp[kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    const unsigned long long off = block_off[blockIdx.x];
+    uint32_t running = 0;
+#pragma unroll 1
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        const bool in = j < n;
+        uint64_t key = 0;
+        bool flag = false;
+        if (in) {
+            key = ks[j];
+            flag = (j == 0) || key != ks[j - 1];
+        }
+        const uint32_t excl = round_rank(flag, s_warp, running);
+        if (in) {
+            // node rank of element j = (#run starts up to and including j) - 1
+            const unsigned long long nr = off + excl + (flag ? 1u : 0u) - 1u;
+            const uint32_t src = idx[j];
+            const uint64_t v = stream_vals[src];
+            kmers[j] = sw_kmer{(uint32_t)v, (uint32_t)(v >> 32)};
+            rank_of_stream[src] = (uint32_t)nr;
+            if (flag) {
+                sw_node* nd = nodes + nr;
+                nd->hash = key;
+                nd->start = j;
+                nd->n_tar = 0;
+                nd->n_neg = 0;
+                nd->penalty = 0.0;
+                if (nr > 0) nodes[nr - 1].stop = j;
+            }
+            if (j == n - 1) nodes[nr].stop = n;
+        }
+    }
+}
+
+// ---- edges ------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kNT) edge_count_kernel(const uint64_t* __restrict__ stream_vals, uint64_t n,
+                                                         unsigned long long* counts)
+{
+    __shared__ uint32_t s_warp[kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t i = base + (uint64_t)r * kNT + threadIdx.x;
+        if (i + 1 < n) c += ((stream_vals[i] >> 32) == (stream_vals[i + 1] >> 32)) ? 1u : 0u;
+    }
+    const uint32_t t = block_sum(c, s_warp);
+    if (threadIdx.x == 0) counts[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kNT) edge_write_kernel(
+    const uint64_t* __restrict__ stream_vals, const uint32_t* __restrict__ rank_of_stream, uint64_t n,
+    const uint32_t* __restrict__ rec_asm, uint32_t rec_base, const unsigned long long* __restrict__ block_off,
+    uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm)
+{
+    __shared__ uint32_t s_warp[kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    const unsigned long long off = block_off[blockIdx.x];
+    uint32_t running = 0;
+#pragma unroll 1
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t i = base + (uint64_t)r * kNT + threadIdx.x;
+        bool flag = false;
+        uint32_t rec = 0;
+        if (i + 1 < n) {
+            rec = (uint32_t)(stream_vals[i] >> 32);
+            flag = rec == (uint32_t)(stream_vals[i + 1] >> 32);
+        }
+        const uint32_t excl = round_rank(flag, s_warp, running);
+        if (flag) {
+            uint32_t u = rank_of_stream[i], v = rank_of_stream[i + 1];
+            if (v < u) { const uint32_t t = u; u = v; v = t; }
+            const unsigned long long slot = off + excl;
+            ekey[slot] = ((uint64_t)u << 32) | v;
+            easm[slot] = rec_asm[rec - rec_base];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kNT) edge_final_kernel(
+    const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ easm, uint64_t n,
+    const unsigned long long* __restrict__ block_off, const sw_node* __restrict__ nodes, sw_edge* __restrict__ edges)
+{
+    __shared__ uint32_t s_warp[kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    const unsigned long long off = block_off[blockIdx.x];
+    uint32_t running = 0;
+#pragma unroll 1
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        const bool in = j < n;
+        uint64_t key = 0;
+        bool new_pair = false, new_asm = false;
+        if (in) {
+            key = ekey[j];
+            new_pair = (j == 0) || key != ekey[j - 1];
+            new_asm = new_pair || easm[j] != easm[j - 1];
+        }
+        const uint32_t excl = round_rank(new_pair, s_warp, running);
+        if (in) {
+            const unsigned long long e = off + excl + (new_pair ? 1u : 0u) - 1u;
+            if (new_pair) {
+                edges[e].first = nodes[(uint32_t)(key >> 32)].hash;
+                edges[e].second = nodes[(uint32_t)key].hash;
+            }
+            // weight was zeroed before the launch; one count per distinct assembly of the run
+            if (new_asm) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), 1ULL);
+        }
+    }
+}
+
+// also used for the edge run starts
+__global__ void __launch_bounds__(kNT) key_run_count_kernel(const uint64_t* __restrict__ ks, uint64_t n,
+                                                            unsigned long long* counts)
+{
+    __shared__ uint32_t s_warp[kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        if (j < n) c += (j == 0 || ks[j] != ks[j - 1]) ? 1u : 0u;
+    }
+    const uint32_t t = block_sum(c, s_warp);
+    if (threadIdx.x == 0) counts[blockIdx.x] = t;
+}
+
+// ---- penalty ----------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) penalty_kernel(
+    const sw_kmer* __restrict__ kmers, uint64_t n_kmers, sw_node* __restrict__ nodes, uint64_t n_nodes,
+    const uint32_t* __restrict__ rec_asm, uint32_t n_records, const uint8_t* __restrict__ is_target,
+    double inv_t, double inv_n, uint32_t* err)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < n_nodes; i += n_warps) {
+        const uint64_t start = nodes[i].start, stop = nodes[i].stop;
+        if (start == stop) {
+            if (lane == 0) { nodes[i].n_tar = 0; nodes[i].n_neg = 0; nodes[i].penalty = 1.0; }
+            continue;
+        }
+        if (start > stop || stop > n_kmers) {
+            if (lane == 0) atomicOr(err, 4u);
+            continue;
+        }
+        uint32_t nt = 0, nn = 0, bad = 0;
+        for (uint64_t j = start + lane; j < stop; j += 32) {
+            const uint32_t r = kmers[j].record_idx;
+            if (r >= n_records) { bad |= 1u; continue; }
+            bool fresh = (j == start);
+            if (!fresh) {
+                const uint32_t pr = kmers[j - 1].record_idx;
+                if (r < pr) bad |= 2u;
+                fresh = pr >= n_records || rec_asm[pr] != rec_asm[r];
+            }
+            if (fresh) {
+                if (is_target[rec_asm[r]]) ++nt; else ++nn;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            nt += __shfl_xor_sync(0xffffffffu, nt, d);
+            nn += __shfl_xor_sync(0xffffffffu, nn, d);
+            bad |= __shfl_xor_sync(0xffffffffu, bad, d);
+        }
+        if (lane == 0) {
+            if (bad) atomicOr(err, bad);
+            nodes[i].n_tar = nt;
+            nodes[i].n_neg = nn;
+            // filter.cpp:132-134 evaluated without fused multiply-add (x86-64 baseline)
+            const double ft = __dmul_rn((double)nt, inv_t);
+            const double fn = __dmul_rn((double)nn, inv_n);
+            const double a = __dsub_rn(1.0, ft);
+            nodes[i].penalty = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(fn, fn)));
+        }
+    }
+}
+
+uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlockItems - 1) / kBlockItems); }
+
+}  // namespace
+
+void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, DevGraph& g, GraphTimes* times)
+{
+    const uint64_t M = st.n;
+    g.n_kmers = M;
+    g.n_nodes = 0;
+    g.n_edges = 0;
+    GraphTimes tm;
+    EventTimer timer(s);
+    if (M == 0) {
+        g.kmers.alloc(0, s);
+        g.nodes.alloc(0, s);
+        g.edges.alloc(0, s);
+        if (times) *times = tm;
+        return;
+    }
+    if (M > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers on one device");
+
+    // -- sort (h1, stream index) ---------------------------------------------------------------
+    timer.start();
+    SortPairs sp;
+    sp.n = M;
+    sp.keys.alloc(M, s);
+    sp.vals.alloc(M, s);
+    SW_CUDA(cudaMemcpyAsync(sp.keys.p, st.keys.p, M * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    iota_kernel<<<(uint32_t)std::min<uint64_t>((M + 255) / 256, 65535), 256, 0, s>>>(sp.vals.p, M);
+    SW_CUDA(cudaGetLastError());
+    tm.launches += 1 + radix_sort_pairs(sp, 64, s);
+    tm.sort_nodes_ms = timer.stop();
+
+    // -- nodes + kmers ---------------------------------------------------------------------------
+    timer.start();
+    const uint32_t nb = blocks_for(M);
+    DevBuf<unsigned long long> counts((size_t)nb + 1, s);
+    node_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(counts.p, nb, counts.p + nb);
+    SW_CUDA(cudaGetLastError());
+    unsigned long long n_nodes = 0;
+    SW_CUDA(cudaMemcpyAsync(&n_nodes, counts.p + nb, sizeof(n_nodes), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+    g.n_nodes = n_nodes;
+    g.kmers.alloc(M, s);
+    g.nodes.alloc(n_nodes, s);
+    DevBuf<uint32_t> rank_of_stream(M, s);
+    node_write_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
+                                         rank_of_stream.p);
+    SW_CUDA(cudaGetLastError());
+    tm.launches += 3;
+    tm.nodes_ms = timer.stop();
+
+    // -- edges -----------------------------------------------------------------------------------
+    timer.start();
+    edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, counts.p);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(counts.p, nb, counts.p + nb);
+    SW_CUDA(cudaGetLastError());
+    unsigned long long n_raw = 0;
+    SW_CUDA(cudaMemcpyAsync(&n_raw, counts.p + nb, sizeof(n_raw), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+    tm.launches += 2;
+    if (n_raw == 0) {
+        g.edges.alloc(0, s);
+    } else {
+        // reuse the node sort's buffers for the (rank pair, assembly) sort
+        sp.n = n_raw;
+        edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, 0u, counts.p, sp.keys.p,
+                                             sp.vals.p);
+        SW_CUDA(cudaGetLastError());
+        tm.launches += 1 + radix_sort_pairs(sp, 64, s);
+        const uint32_t eb = blocks_for(n_raw);
+        DevBuf<unsigned long long> ecounts((size_t)eb + 1, s);
+        key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
+        scan_counts_kernel<<<1, 1024, 0, s>>>(ecounts.p, eb, ecounts.p + eb);
+        SW_CUDA(cudaGetLastError());
+        unsigned long long n_edges = 0;
+        SW_CUDA(cudaMemcpyAsync(&n_edges, ecounts.p + eb, sizeof(n_edges), cudaMemcpyDeviceToHost, s));
+        SW_CUDA(cudaStreamSynchronize(s));
+        g.n_edges = n_edges;
+        g.edges.alloc(n_edges, s);
+        SW_CUDA(cudaMemsetAsync(g.edges.p, 0, n_edges * sizeof(sw_edge), s));
+        edge_final_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_raw, ecounts.p, g.nodes.p, g.edges.p);
+        SW_CUDA(cudaGetLastError());
+        tm.launches += 3;
+    }
+    tm.edges_ms = timer.stop();
+    if (times) *times = tm;
+}
+
+uint32_t run_penalty(const sw_kmer* d_kmers, uint64_t n_kmers, sw_node* d_nodes, uint64_t n_nodes,
+                     const uint32_t* d_rec_asm, uint32_t n_records, const uint8_t* d_is_target, double inv_t,
+                     double inv_n, cudaStream_t s)
+{
+    if (n_nodes == 0) return 0;
+    DevBuf<uint32_t> err(1, s);
+    SW_CUDA(cudaMemsetAsync(err.p, 0, sizeof(uint32_t), s));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_nodes + 7) / 8, (uint64_t)sm_count() * 16);
+    penalty_kernel<<<grid, 256, 0, s>>>(d_kmers, n_kmers, d_nodes, n_nodes, d_rec_asm, n_records, d_is_target,
+                                        inv_t, inv_n, err.p);
+    SW_CUDA(cudaGetLastError());
+    uint32_t h = 0;
+    SW_CUDA(cudaMemcpyAsync(&h, err.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+    return h;
+}
+
+}  // namespace sw

@@ -1,0 +1,366 @@
+// ingest.cpp -- host side of the hot path: FASTA / .gz -> 2-bit packed pinned batch, and the
+// tile planner that cuts each record's valid-k-mer stream into CTA-sized tiles.
+//
+// Replaces (behaviourally, not textually) the reference's reader
+//   cpp/src/utils/fasta_reader.cpp:40-95   read_fasta_core  (line rules, id extraction)
+//   cpp/src/utils/fasta_reader.cpp:97-213  plain / gzip front ends (".gz" by suffix only)
+// and the per-assembly bookkeeping of build_worker (cpp/src/seqwin/build.cpp:129-147,192-193).
+#include "ingest.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <exception>
+#include <mutex>
+#include <thread>
+
+namespace sw {
+
+void* alloc_host(size_t bytes, bool* pinned);  // api.cu (cudaHostAlloc) or emul (malloc)
+void free_host(void* p, bool pinned);
+
+namespace {
+
+// byte class: 0..3 = A,C,G,T/U code; 4 = unhashable (packed as 0, recorded as invalid);
+// 5 = ASCII whitespace (dropped, fasta_reader.cpp:82-86 uses std::isspace)
+struct ByteClass {
+    uint8_t t[256];
+    ByteClass()
+    {
+        for (int i = 0; i < 256; ++i) t[i] = 4;
+        t[(int)'A'] = t[(int)'a'] = 0;
+        t[(int)'C'] = t[(int)'c'] = 1;
+        t[(int)'G'] = t[(int)'g'] = 2;
+        t[(int)'T'] = t[(int)'t'] = t[(int)'U'] = t[(int)'u'] = 3;
+        t[(int)' '] = t[(int)'\t'] = t[(int)'\n'] = t[(int)'\r'] = t[(int)'\f'] = t[(int)'\v'] = 5;
+    }
+};
+const ByteClass kClass;
+
+// One assembly, parsed and packed, before it is placed into the batch.
+struct AsmPacked {
+    std::vector<uint32_t> words;        // records laid out back to back, 4-word aligned
+    std::vector<uint64_t> rec_word_off; // local
+    std::vector<uint32_t> rec_len;
+    std::vector<uint32_t> rec_inv_cnt;
+    std::vector<uint32_t> inv_start, inv_len;
+    std::vector<std::string> ids;
+    size_t n_bases = 0;
+};
+
+// Streaming packer for one record.
+struct RecordPacker {
+    AsmPacked& a;
+    uint32_t acc = 0;
+    uint64_t cnt = 0;  // bases so far (64-bit so that > u32 records are detected, build.cpp:136)
+    uint32_t n_inv = 0;
+    bool open = false;
+
+    explicit RecordPacker(AsmPacked& a_) : a(a_) {}
+
+    void begin(std::string id)
+    {
+        a.ids.push_back(std::move(id));
+        a.rec_word_off.push_back(a.words.size());
+        acc = 0; cnt = 0; n_inv = 0; open = true;
+    }
+    inline void push_code(uint32_t c)
+    {
+        acc |= c << (2 * (cnt & 15));
+        if ((++cnt & 15) == 0) { a.words.push_back(acc); acc = 0; }
+    }
+    inline void push_invalid()
+    {
+        if (n_inv && (uint64_t)a.inv_start.back() + a.inv_len.back() == cnt) ++a.inv_len.back();
+        else { a.inv_start.push_back((uint32_t)cnt); a.inv_len.push_back(1); ++n_inv; }
+        push_code(0);
+    }
+    void append(const unsigned char* p, size_t n)
+    {
+        for (size_t i = 0; i < n; ++i) {
+            const uint8_t c = kClass.t[p[i]];
+            if (c < 4) push_code(c);
+            else if (c == 4) push_invalid();
+        }
+    }
+    void end(const std::string& path)
+    {
+        if (!open) return;
+        if (cnt > 0xFFFFFFFFull)
+            fail_runtime("Sequence length exceeds uint32 range for record " + a.ids.back() +
+                         " in assembly " + path);
+        if (cnt & 15) a.words.push_back(acc);
+        while (a.words.size() % kRecordAlignWords) a.words.push_back(0);
+        a.rec_len.push_back((uint32_t)cnt);
+        a.rec_inv_cnt.push_back(n_inv);
+        a.n_bases += cnt;
+        open = false;
+    }
+};
+
+bool ends_with(const std::string& s, const char* suf)
+{
+    size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+std::vector<char> slurp(const std::string& path)
+{
+    std::vector<char> buf;
+    if (ends_with(path, ".gz")) {
+        gzFile f = gzopen(path.c_str(), "rb");
+        if (!f) fail_runtime("Unable to open gzip FASTA: " + path);
+        gzbuffer(f, 1 << 20);
+        size_t n = 0;
+        buf.resize(1 << 22);
+        for (;;) {
+            if (buf.size() - n < (1 << 20)) buf.resize(buf.size() * 2);
+            int got = gzread(f, buf.data() + n, 1 << 20);
+            if (got < 0) {
+                int errnum = 0;
+                const char* msg = gzerror(f, &errnum);
+                std::string m = std::string("gzip read error: ") + (msg ? msg : "unknown");
+                gzclose(f);
+                fail_runtime(m);
+            }
+            if (got == 0) break;
+            n += (size_t)got;
+        }
+        gzclose(f);
+        buf.resize(n);
+    } else {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) fail_runtime("Unable to open FASTA: " + path);
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz > 0) {
+            buf.resize((size_t)sz);
+            size_t got = fread(buf.data(), 1, (size_t)sz, f);
+            buf.resize(got);
+        } else {  // unseekable / special file: stream it
+            char tmp[1 << 16];
+            size_t got;
+            while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+        }
+        fclose(f);
+    }
+    return buf;
+}
+
+// Line rules of read_fasta_core (fasta_reader.cpp:50-87): split at '\n', strip one trailing
+// '\r', skip empty / whitespace-only lines, '>' in column 0 opens a record whose id runs to the
+// first whitespace, every other line is sequence with whitespace bytes dropped.
+void parse_fasta(const std::string& path, AsmPacked& out)
+{
+    const std::vector<char> buf = slurp(path);
+    const unsigned char* p = (const unsigned char*)buf.data();
+    const size_t n = buf.size();
+    out.words.reserve(n / 16 + 64);
+    RecordPacker rp(out);
+    bool have = false;
+    size_t i = 0;
+    while (i < n) {
+        const void* nl = memchr(p + i, '\n', n - i);
+        const size_t j = nl ? (size_t)((const unsigned char*)nl - p) : n;
+        size_t end = j;
+        if (end > i && p[end - 1] == '\r') --end;
+        size_t t = i;
+        while (t < end && kClass.t[p[t]] == 5) ++t;
+        if (t < end) {  // not blank
+            if (p[i] == '>') {
+                rp.end(path);
+                size_t e = i + 1;
+                while (e < end && kClass.t[p[e]] != 5) ++e;
+                rp.begin(std::string((const char*)p + i + 1, e - (i + 1)));
+                have = true;
+            } else {
+                if (!have) fail_runtime("Invalid FASTA: sequence encountered before header");
+                rp.append(p + i, end - i);
+            }
+        }
+        i = j + 1;
+    }
+    rp.end(path);
+}
+
+template <typename F>
+void parallel_for(size_t n, uint32_t n_threads, F&& fn)
+{
+    n_threads = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_threads ? n_threads : 1, n));
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex mu;
+    auto body = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n) return;
+            try {
+                fn(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> g(mu);
+                if (!err) err = std::current_exception();
+                next.store(n);
+                return;
+            }
+        }
+    };
+    if (n_threads == 1) {
+        body();
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < n_threads; ++t) th.emplace_back(body);
+        for (auto& t : th) t.join();
+    }
+    if (err) std::rethrow_exception(err);
+}
+
+// Lay the per-assembly pieces out in one (pinned) stream and build the global tables.
+sw_batch* assemble(std::vector<AsmPacked>& parts, uint32_t n_threads)
+{
+    auto* b = new sw_batch();
+    try {
+        const size_t A = parts.size();
+        if (A > 0xFFFFFFFFull) fail_runtime("Number of input assemblies exceeds uint32 range");
+        std::vector<size_t> word_base(A + 1, 0), rec_base(A + 1, 0), inv_base(A + 1, 0);
+        for (size_t a = 0; a < A; ++a) {
+            word_base[a + 1] = word_base[a] + parts[a].words.size();
+            rec_base[a + 1] = rec_base[a] + parts[a].rec_len.size();
+            inv_base[a + 1] = inv_base[a] + parts[a].inv_start.size();
+            if (rec_base[a + 1] > 0xFFFFFFFFull)
+                fail_runtime("Total number of FASTA records exceeds uint32 range");
+        }
+        const size_t R = rec_base[A];
+        b->n_words = word_base[A] + kTailPadWords;
+        b->words = (uint32_t*)alloc_host(b->n_words * sizeof(uint32_t), &b->pinned);
+        if (!b->words) fail_runtime("host allocation of the packed batch failed");
+        memset(b->words + word_base[A], 0, kTailPadWords * sizeof(uint32_t));
+        b->rec_word_off.resize(R);
+        b->rec_len.resize(R);
+        b->rec_inv_off.assign(R + 1, 0);
+        b->inv_start.resize(inv_base[A]);
+        b->inv_len.resize(inv_base[A]);
+        b->ids.resize(R);
+        b->record_offsets.resize(A + 1);
+        for (size_t a = 0; a <= A; ++a) b->record_offsets[a] = (uint32_t)rec_base[a];
+        parallel_for(A, n_threads, [&](size_t a) {
+            AsmPacked& p = parts[a];
+            if (!p.words.empty())
+                memcpy(b->words + word_base[a], p.words.data(), p.words.size() * sizeof(uint32_t));
+            size_t iv = inv_base[a];
+            for (size_t r = 0; r < p.rec_len.size(); ++r) {
+                const size_t g = rec_base[a] + r;
+                b->rec_word_off[g] = word_base[a] + p.rec_word_off[r];
+                b->rec_len[g] = p.rec_len[r];
+                b->rec_inv_off[g] = (uint32_t)iv;
+                iv += p.rec_inv_cnt[r];
+                b->ids[g] = std::move(p.ids[r]);
+            }
+            if (!p.inv_start.empty()) {
+                memcpy(b->inv_start.data() + inv_base[a], p.inv_start.data(), p.inv_start.size() * 4);
+                memcpy(b->inv_len.data() + inv_base[a], p.inv_len.data(), p.inv_len.size() * 4);
+            }
+            std::vector<uint32_t>().swap(p.words);
+        });
+        if (inv_base[A] > 0xFFFFFFFFull) fail_runtime("too many unhashable runs");
+        b->rec_inv_off[R] = (uint32_t)inv_base[A];
+        for (size_t a = 0; a < A; ++a) b->n_bases += parts[a].n_bases;
+    } catch (...) {
+        delete b;
+        throw;
+    }
+    return b;
+}
+
+}  // namespace
+
+sw_batch* batch_from_fasta(const char* const* paths, size_t n_paths, uint32_t n_threads)
+{
+    std::vector<AsmPacked> parts(n_paths);
+    parallel_for(n_paths, n_threads, [&](size_t a) { parse_fasta(paths[a], parts[a]); });
+    return assemble(parts, n_threads);
+}
+
+sw_batch* batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const uint32_t* asm_of,
+                            const char* const* ids, size_t n_records, size_t n_assemblies,
+                            uint32_t n_threads)
+{
+    std::vector<AsmPacked> parts(n_assemblies);
+    std::vector<size_t> first(n_assemblies + 1, n_records);
+    for (size_t r = n_records; r-- > 0;) {
+        if (asm_of[r] >= n_assemblies) fail_value("asm_of out of range");
+        if (r + 1 < n_records && asm_of[r] > asm_of[r + 1]) fail_value("asm_of must be nondecreasing");
+        first[asm_of[r]] = r;
+    }
+    for (size_t a = n_assemblies; a-- > 0;)
+        if (first[a] == n_records) first[a] = first[a + 1];
+    first[n_assemblies] = n_records;
+    parallel_for(n_assemblies, n_threads, [&](size_t a) {
+        RecordPacker rp(parts[a]);
+        size_t total = 0;
+        for (size_t r = first[a]; r < first[a + 1]; ++r) total += lens[r];
+        parts[a].words.reserve(total / 16 + 8 * (first[a + 1] - first[a]));
+        for (size_t r = first[a]; r < first[a + 1]; ++r) {
+            rp.begin(ids ? std::string(ids[r]) : std::string());
+            rp.append(seqs[r], lens[r]);
+            rp.end("<memory>");
+        }
+    });
+    return assemble(parts, n_threads);
+}
+
+Plan plan_tiles(const sw_batch& b, uint32_t k, uint32_t w, uint32_t tk)
+{
+    Plan plan;
+    if (tk <= w) fail_runtime("windowsize too large for the sketch tile");
+    const uint32_t tw = tk - w;  // windows per tile (one k-mer of slack for the previous window)
+    const size_t R = b.rec_len.size();
+    for (size_t r = 0; r < R; ++r) {
+        const uint32_t L = b.rec_len[r];
+        const size_t piece_lo = plan.pieces.size();
+        uint64_t n_valid = 0;
+        // valid runs between the record's unhashable runs
+        uint32_t s = 0;
+        auto add_run = [&](uint32_t start, uint32_t stop) {
+            if (stop - start >= k) {
+                plan.pieces.push_back(Piece{(uint32_t)n_valid, start, stop - start - k + 1});
+                n_valid += stop - start - k + 1;
+            }
+        };
+        for (uint32_t iv = b.rec_inv_off[r]; iv < b.rec_inv_off[r + 1]; ++iv) {
+            add_run(s, b.inv_start[iv]);
+            s = b.inv_start[iv] + b.inv_len[iv];
+        }
+        add_run(s, L);
+        plan.n_kmers += n_valid;
+        if (plan.pieces.size() > 0xFFFFFFF0ull) fail_runtime("too many valid runs");
+        if (n_valid < w) {  // minimizer.cpp:56-58 and "fewer than w valid k-mers": nothing to emit
+            plan.pieces.resize(piece_lo);
+            continue;
+        }
+        const uint64_t n_win = n_valid - w + 1;
+        plan.n_windows += n_win;
+        size_t pc = piece_lo;
+        for (uint64_t a0 = 0; a0 < n_win; a0 += tw) {
+            const uint64_t a1 = std::min<uint64_t>(a0 + tw, n_win);
+            const uint64_t e0 = a0 ? a0 - 1 : 0;
+            const uint64_t nk = a1 + w - 1 - e0;
+            while ((uint64_t)plan.pieces[pc].kidx + plan.pieces[pc].n <= e0) ++pc;
+            size_t pe = pc;
+            while (pe + 1 < plan.pieces.size() && plan.pieces[pe + 1].kidx < e0 + nk) ++pe;
+            plan.tiles.push_back(Tile{(uint32_t)r, (uint32_t)e0, (uint32_t)nk, (uint32_t)pc,
+                                      (uint32_t)(pe - pc + 1), a0 == 0 ? 1u : 0u});
+        }
+    }
+    if (plan.tiles.size() > 0x7FFFFFFFull) fail_runtime("too many sketch tiles");
+    return plan;
+}
+
+}  // namespace sw
+
+sw_batch::~sw_batch()
+{
+    if (words) sw::free_host(words, pinned);
+}

@@ -1,0 +1,206 @@
+// radix.cu -- stable LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, one
+// read + one write of the data per digit ("onesweep": per-tile digit counts are chained
+// through a decoupled look-back so the scatter pass needs no separate per-tile scan).
+//
+// Plays the role of the reference's 16-bit-digit CPU LSD sort
+// (cpp/src/seqwin/build_internals.cpp:76-144) and, because the sort is what groups equal
+// minimizer hashes / equal edges, of its two ankerl hash maps (cpp/src/seqwin/build.cpp:66-89).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "device.h"
+
+namespace sw {
+
+namespace {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kMaxPasses = 8;
+
+constexpr unsigned long long kStAgg = 1ULL << 62;
+constexpr unsigned long long kStInc = 2ULL << 62;
+constexpr unsigned long long kStMask = (1ULL << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Digit histograms of every pass in one read of the keys.
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                         int n_passes, unsigned long long* ghist)
+{
+    __shared__ uint32_t sh[kMaxPasses][kRadix];
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        for (int p = 0; p < n_passes; ++p)
+            atomicAdd(&sh[p][(key >> (p * kRadixBits)) & (kRadix - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_passes * kRadix; i += blockDim.x) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
+    }
+}
+
+template <int NT, int ITEMS>
+__global__ void __launch_bounds__(NT) radix_onesweep_kernel(
+    const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
+    uint32_t* __restrict__ vout, uint64_t n, int shift, const unsigned long long* __restrict__ goff,
+    unsigned long long* status, unsigned int* ticket)
+{
+    constexpr int NW = NT / 32;
+    constexpr int TILE = NT * ITEMS;
+    __shared__ uint32_t whist[NW][kRadix];
+    __shared__ unsigned long long dbase[kRadix];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < NW * kRadix; i += NT) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t wbase = (uint64_t)tile * TILE + (uint64_t)wid * (32 * ITEMS);
+
+    uint64_t key[ITEMS];
+    uint32_t val[ITEMS];
+    uint32_t rank[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
+        const bool valid = idx < n;
+        key[i] = valid ? kin[idx] : ~0ULL;
+        val[i] = valid ? vin[idx] : 0u;
+    }
+
+    // warp-local stable ranking: items of one warp are ordered (item, lane)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const bool valid = wbase + (uint64_t)i * 32 + lane < n;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x1FFu);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = whist[wid][d];
+            whist[wid][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = old + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive scan over warps, then chain the tile count through the look-back
+    if (tid < kRadix) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int wv = 0; wv < NW; ++wv) {
+            const uint32_t t = whist[wv][tid];
+            whist[wv][tid] = run;
+            run += t;
+        }
+        unsigned long long before = 0;
+        unsigned long long* my = status + (uint64_t)tile * kRadix + tid;
+        if (tile == 0) {
+            st_relaxed(my, kStInc | run);
+        } else {
+            st_relaxed(my, kStAgg | run);
+            const unsigned long long* p = my - kRadix;
+            for (;;) {
+                const unsigned long long st = ld_relaxed(p);
+                if ((st >> 62) == 0) continue;
+                before += st & kStMask;
+                if ((st >> 62) == 2) break;
+                p -= kRadix;
+            }
+            st_relaxed(my, kStInc | (before + run));
+        }
+        dbase[tid] = goff[tid] + before;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const bool valid = wbase + (uint64_t)i * 32 + lane < n;
+        if (valid) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+            const unsigned long long pos = dbase[d] + whist[wid][d] + rank[i];
+            kout[pos] = key[i];
+            vout[pos] = val[i];
+        }
+    }
+}
+
+}  // namespace
+
+uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
+{
+    const uint64_t n = sp.n;
+    if (n < 2 || end_bit <= 0) return 0;
+    const int n_passes = std::min(kMaxPasses, (end_bit + kRadixBits - 1) / kRadixBits);
+    uint32_t launches = 0;
+
+    DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s);
+    SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
+    const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
+    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(sp.keys.p, n, n_passes, ghist.p);
+    SW_CUDA(cudaGetLastError());
+    ++launches;
+    std::vector<unsigned long long> hist((size_t)kMaxPasses * kRadix);
+    SW_CUDA(cudaMemcpyAsync(hist.data(), ghist.p, ghist.bytes(), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+
+    // exclusive digit offsets per pass; a pass whose keys all share one digit is a no-op
+    bool skip[kMaxPasses];
+    for (int p = 0; p < n_passes; ++p) {
+        unsigned long long run = 0, mx = 0;
+        for (int d = 0; d < kRadix; ++d) {
+            const unsigned long long c = hist[(size_t)p * kRadix + d];
+            hist[(size_t)p * kRadix + d] = run;
+            run += c;
+            mx = std::max(mx, c);
+        }
+        skip[p] = (mx == n);
+    }
+    SW_CUDA(cudaMemcpyAsync(ghist.p, hist.data(), ghist.bytes(), cudaMemcpyHostToDevice, s));
+
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    DevBuf<unsigned long long> status(n_tiles * kRadix, s);
+    DevBuf<unsigned int> ticket(1, s);
+    if (!sp.keys_alt.p || sp.keys_alt.n < n) sp.keys_alt.alloc(n, s);
+    if (!sp.vals_alt.p || sp.vals_alt.n < n) sp.vals_alt.alloc(n, s);
+
+    for (int p = 0; p < n_passes; ++p) {
+        if (skip[p]) continue;
+        SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
+        SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
+        radix_onesweep_kernel<kSortThreads, kSortItems><<<(uint32_t)n_tiles, kSortThreads, 0, s>>>(
+            sp.keys.p, sp.keys_alt.p, sp.vals.p, sp.vals_alt.p, n, p * kRadixBits,
+            ghist.p + (size_t)p * kRadix, status.p, ticket.p);
+        SW_CUDA(cudaGetLastError());
+        ++launches;
+        std::swap(sp.keys, sp.keys_alt);
+        std::swap(sp.vals, sp.vals_alt);
+    }
+    // `hist` (pageable) was the source of an async copy: make sure it was consumed
+    SW_CUDA(cudaStreamSynchronize(s));
+    return launches;
+}
+
+}  // namespace sw

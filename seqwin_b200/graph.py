@@ -1,0 +1,40 @@
+"""Host-side mirror of the reference's graph API (``src/seqwin/graph/__init__.py:40-196``).
+
+Same names, argument meaning and error behaviour, so parity tests read like the reference's
+``tests/smoke/test_graph.py``; the native module is :mod:`seqwin_b200._core`.
+"""
+from __future__ import annotations
+
+from collections.abc import Iterable
+from pathlib import Path
+
+import numpy as np
+from numpy.typing import NDArray
+
+from ._core import (EDGE_DTYPE, KMER_DTYPE, NODE_DTYPE, _build_native, _filter_kmers_native,
+                    _get_penalty_native)
+
+__all__ = ["KMER_DTYPE", "NODE_DTYPE", "EDGE_DTYPE", "KmerGraph", "_get_penalty", "_filter_kmers"]
+
+
+class KmerGraph:
+    """The minimizer graph (``graph/__init__.py:61-146``): kmers grouped and sorted by hash, nodes
+    and edges sorted by hash, ``record_offsets`` cumulative per assembly, ``record_ids`` per assembly."""
+    __slots__ = ("kmers", "nodes", "edges", "record_offsets", "record_ids")
+
+    def __init__(self, assembly_paths: Iterable[Path], kmerlen: int, windowsize: int,
+                 low_memory: bool = False, n_cpu: int = 1) -> None:
+        self.kmers, self.nodes, self.edges, self.record_offsets, self.record_ids = _build_native(
+            list(str(p) for p in assembly_paths), int(kmerlen), int(windowsize), int(n_cpu), bool(low_memory))
+
+
+def _get_penalty(kmers: NDArray[np.void], nodes: NDArray[np.void], record_offsets: NDArray[np.uint32],
+                 is_targets: Iterable[bool], n_cpu: int = 1) -> None:
+    """``graph/__init__.py:149-171``: populate n_tar / n_neg / penalty in place."""
+    _get_penalty_native(kmers, nodes, record_offsets,
+                        np.asarray(is_targets, dtype=np.bool_, order="C"), int(n_cpu))
+
+
+def _filter_kmers(kmers: NDArray[np.void], nodes: NDArray[np.void], used_hashes):
+    """``graph/__init__.py:174-196``: keep the nodes (and their k-mers) whose hash is in ``used_hashes``."""
+    return _filter_kmers_native(kmers, nodes, used_hashes)

@@ -1,0 +1,85 @@
+"""The sketch kernel's per-thread phase functions, executed serially on the host (tests/emul) and
+compared with the oracle: tiling, halos, N gaps, ties, tiny tiles.  CPU only."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+EMUL_DIR = Path(__file__).resolve().parent / "emul"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = EMUL_DIR / "libemul.so"
+    srcs = [EMUL_DIR / "emul.cpp"] + list((EMUL_DIR.parents[1] / "seqwin_b200" / "csrc").glob("*.h")) + \
+        [EMUL_DIR.parents[1] / "seqwin_b200" / "csrc" / "ingest.cpp"]
+    if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", str(so),
+                               str(EMUL_DIR / "emul.cpp"), "-lz"])
+    L = C.CDLL(str(so))
+    L.emul_sketch.restype = C.c_long
+
+    def run(seqs, k, w, nt, c1):
+        n = len(seqs)
+        arrs = [np.frombuffer(s, dtype=np.uint8) for s in seqs]
+        ptrs = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+        cap = sum(len(s) for s in seqs) + 16
+        h1, pos, rec = np.empty(cap, np.uint64), np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        nt_out = C.c_uint32()
+        m = L.emul_sketch(ptrs, C.c_void_p(lens.ctypes.data), C.c_size_t(n), C.c_uint32(k), C.c_uint32(w), nt, c1,
+                          C.c_void_p(h1.ctypes.data), C.c_void_p(pos.ctypes.data), C.c_void_p(rec.ctypes.data),
+                          C.c_size_t(cap), C.byref(nt_out))
+        assert m >= 0, f"emulator failed ({m})"
+        return h1[:m], pos[:m], rec[:m], nt_out.value
+    return run
+
+
+def _oracle_stream(seqs, k, w):
+    H, P, R = [], [], []
+    for r, s in enumerate(seqs):
+        h, p = O.minimize(s, k, w)
+        H.append(h), P.append(p), R.append(np.full(len(h), r, np.uint32))
+    return np.concatenate(H), np.concatenate(P), np.concatenate(R)
+
+
+def _seqs(rng):
+    def rand(n, p_n=0.0, low=False, alphabet=b"ACGT"):
+        a = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)].copy()
+        if p_n:
+            for s in rng.integers(0, max(1, n), max(1, int(n * p_n / 5))):
+                a[s:s + rng.integers(1, 12)] = ord("N")
+        if low:
+            a[rng.random(n) < 0.2] |= 0x20
+        return a.tobytes()
+    return [rand(int(rng.integers(1, 4000))) for _ in range(3)] + [
+        rand(3000, 0.01, True), rand(2500, alphabet=b"AC"), rand(1500, alphabet=b"A"), rand(2000, 0.05), b"", b"ACGT",
+        rand(12000), rand(40000, 0.002), b"ACGTTGCA" * 400]
+
+
+CONFIGS = [(8, 11), (32, 9), (4, 45), (128, 45), (256, 21), (256, 61)]
+KW = [(21, 200), (21, 10), (17, 10), (7, 10), (5, 3), (4, 1), (6, 7), (3, 2), (31, 50), (21, 46), (21, 45), (21, 47),
+      (9, 9), (11, 16), (15, 64), (12, 11), (33, 100), (127, 10)]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"nt{c[0]}c{c[1]}")
+def test_emulated_kernel_matches_oracle(emul, cfg):
+    nt, c1 = cfg
+    rng = np.random.default_rng(nt * 1000 + c1)
+    n_multi_tile = 0
+    for k, w in KW:
+        if nt * c1 <= w + 1:
+            continue
+        seqs = _seqs(rng)
+        eh, ep, er, n_tiles = emul(seqs, k, w, nt, c1)
+        oh, op, orr = _oracle_stream(seqs, k, w)
+        assert len(eh) == len(oh), (cfg, k, w, len(eh), len(oh))
+        assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (cfg, k, w)
+        n_multi_tile += n_tiles > len(seqs)
+    assert n_multi_tile > 0
