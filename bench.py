@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- Gbp/s sketched + graph-built on synthetic bacterial-genome sets (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--genomes G] ...
+
+One "step" = one pass of the hot path (ntHash -> window minimizers -> minimizer graph) over the
+whole synthetic batch.  Workload at N=1: BASELINE.json configs[1] -- 500 genomes x 5 Mbp (100
+targets / 400 non-targets), k=21, w=200.  Under torchrun (N>1) every rank owns one such shard
+(weak scaling) and minimizer / edge records are exchanged with NCCL all-to-all (seqwin_b200.dist).
+
+  value      device-resident: packed input already in HBM, graph left in HBM, CUDA-event timed
+  e2e        the same through the host-buffer C-ABI call (pinned 2-bit batch -> H2D -> build ->
+             D2H of kmers/nodes/edges), wall-clock around the call
+  roofline   dominant kernel (sketch): algorithmic bytes / CUDA-event kernel time vs measured HBM
+             peak, plus the INT32-pipe view that actually bounds it
+  cpu_baseline / --impl reference: the UNMODIFIED reference extension (oracle/_ref) on the box's
+             host cores over a bounded sample of the same genomes (FASTA on /dev/shm)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from seqwin_b200.synth import SynthSet, SynthSpec, write_fasta  # noqa: E402
+
+K_DEFAULT, W_DEFAULT = 21, 200
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=500, help="genomes per GPU (weak scaling)")
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--k", type=int, default=K_DEFAULT)
+    ap.add_argument("--w", type=int, default=W_DEFAULT)
+    ap.add_argument("--sample-genomes", type=int, default=0, help="genomes in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skew", action="store_true", help="config C5: near-clonal + repeats")
+    return ap.parse_args()
+
+
+def spec_for(args, world: int) -> SynthSpec:
+    n = args.genomes * world
+    return SynthSpec(n_genomes=n, n_targets=max(1, n // 5), genome_len=args.genome_len, n_contigs=50,
+                     seed=42, skew=args.skew)
+
+
+# ---- clocks ----------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- reference / CPU baseline ------------------------------------------------------------------
+def sample_indices(spec: SynthSpec, n_sample: int) -> list[int]:
+    n_sample = max(2, min(n_sample, spec.n_genomes))
+    n_t = max(1, min(spec.n_targets, n_sample // 5))
+    n_n = min(spec.n_genomes - spec.n_targets, n_sample - n_t)
+    return list(range(n_t)) + list(range(spec.n_targets, spec.n_targets + n_n))
+
+
+def write_sample(ss: SynthSet, idx: list[int]) -> tuple[Path, list[Path], np.ndarray, int]:
+    base = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
+    d = Path(tempfile.mkdtemp(prefix="seqwin_b200_sample_", dir=base))
+    paths, n_bases = [], 0
+    for g in idx:
+        p = d / f"g{g:05d}.fasta"
+        recs = ss.records(g)
+        n_bases += sum(len(s) for _, s in recs)
+        write_fasta(p, recs)
+        paths.append(p)
+    is_t = np.array([g < ss.spec.n_targets for g in idx])
+    return d, paths, is_t, n_bases
+
+
+def time_reference(paths, is_t, k, w, n_bases, steps, warmup):
+    """The reference's own CPU path: _build_native + _get_penalty_native, --threads = all cores."""
+    from oracle import oracle as O
+    ref = O.load_reference()
+    kind = "reference"
+    cores = os.cpu_count() or 1
+    if ref is None:  # oracle/_ref not present: fall back to the scalar C port of the oracle
+        ref, kind, cores = O, "port", 1
+    spaths = [str(p) for p in paths]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        kmers, nodes, edges, offsets, ids = ref._build_native(spaths, k, w, cores, False)
+        ref._get_penalty_native(kmers, nodes, offsets, np.asarray(is_t, dtype=np.bool_), cores)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = float(np.mean(times))
+    return {"value": n_bases / mean / 1e9, "unit": "Gbp/s", "cores": cores, "kind": kind,
+            "sample": f"{len(paths)} of the workload's genomes ({n_bases / 1e6:.0f} Mbp), plain FASTA on tmpfs, "
+                      f"build+get_penalty, mean of {steps} (warmup {warmup})",
+            "seconds": mean, "graph": (kmers, nodes, edges, offsets)}
+
+
+# ---- our arm -----------------------------------------------------------------------------------
+def build_batch(ss: SynthSet, genomes: range, threads: int):
+    """Generate genomes and pack them into one pinned 2-bit batch through the C ABI."""
+    from seqwin_b200 import _lib
+    L = _lib.lib()
+    arrs, lens, asm_of, ids = [], [], [], []
+    for a, g in enumerate(genomes):
+        for rid, seq in ss.records(g):
+            arrs.append(np.ascontiguousarray(seq))
+            lens.append(len(seq))
+            asm_of.append(a)
+            ids.append(rid.encode())
+    n = len(arrs)
+    ptrs = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in arrs])
+    idp = (C.c_char_p * max(1, n))(*ids)
+    lens_a = np.asarray(lens, dtype=np.uint32)
+    asm_a = np.asarray(asm_of, dtype=np.uint32)
+    b = C.c_void_p()
+    _lib.check(L.sw_batch_from_memory(ptrs, lens_a.ctypes.data, asm_a.ctypes.data, idp, n, len(genomes), threads,
+                                      C.byref(b)))
+    return b
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    k, w = args.k, args.w
+    spec = spec_for(args, world)
+    workload = (f"synthetic {spec.n_genomes} genomes x {spec.genome_len / 1e6:g} Mbp "
+                f"({spec.n_targets} targets / {spec.n_genomes - spec.n_targets} non-targets), 50 contigs each, "
+                f"k={k} w={w}" + (", skew (C5)" if args.skew else ""))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ss = SynthSet(spec)
+        n_s = args.sample_genomes or int(np.clip(os.cpu_count() or 8, 32, 96))
+        idx = sample_indices(spec, n_s)
+        d, paths, is_t, n_bases = write_sample(ss, idx)
+        try:
+            r = time_reference(paths, is_t, k, w, n_bases, args.steps, args.warmup)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+        r.pop("graph")
+        line = {"impl": "reference", "metric": "Gbp/s sketched+graph-built", "value": r["value"], "unit": "Gbp/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": workload},
+                "cpu_baseline": {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    torch.cuda.set_device(local_rank)
+    from seqwin_b200 import _lib
+    from seqwin_b200._lib import StageTimes
+    L = _lib.lib()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    threads = max(1, (os.cpu_count() or 8) // max(1, world))
+    ss = SynthSet(spec)
+    my_genomes = range(rank * args.genomes, (rank + 1) * args.genomes)
+    t0 = time.perf_counter()
+    batch = build_batch(ss, my_genomes, threads)
+    gen_s = time.perf_counter() - t0
+    n_bases_local = L.sw_batch_n_bases(batch)
+    packed_bytes = L.sw_batch_packed_bytes(batch)
+    n_records = L.sw_batch_n_records(batch)
+
+    if world > 1:
+        from seqwin_b200 import dist as swdist
+        result = swdist.bench_loop(L, batch, spec, rank, world, k, w, args.steps, args.warmup)
+    else:
+        dev = C.c_void_p()
+        _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
+        st = StageTimes()
+
+        def dev_step():
+            g = C.c_void_p()
+            _lib.check(L.sw_dev_build(dev, k, w, C.byref(g), C.byref(st)))
+            L.sw_graph_free(g)
+            return st.as_dict()
+
+        for _ in range(args.warmup):
+            dev_step()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        torch.cuda.synchronize()
+        stages = [dev_step() for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        L.sw_dev_batch_free(dev)
+
+        # end to end through the host-buffer call: pinned packed batch -> graph arrays on the host
+        def e2e_step():
+            g = C.c_void_p()
+            t0 = time.perf_counter()
+            _lib.check(L.sw_build_from_batch(batch, k, w, C.byref(g), C.byref(st)))
+            dt = time.perf_counter() - t0
+            L.sw_graph_free(g)
+            return dt, st.as_dict()
+
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        e2e_runs = [e2e_step() for _ in range(args.steps)]
+        result = {"stages": stages, "clocks": clocks, "e2e_runs": e2e_runs}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    stages = result["stages"]
+    total_ms = float(np.mean([s["total_ms"] for s in stages]))
+    sketch_ms = float(np.mean([s["sketch_kernel_ms"] for s in stages]))
+    s0 = stages[-1]
+    n_bases_total = result.get("n_bases_total", n_bases_local)
+    M, Un, Ue = s0["n_kmers"], s0["n_nodes"], s0["n_edges"]
+    value = n_bases_total / (total_ms * 1e-3) / 1e9
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    # dominant kernel = sketch: reads the 2-bit input once, writes 16 B per minimizer
+    sketch_bytes = n_bases_local / 4 + 16 * M
+    ach = sketch_bytes / (sketch_ms * 1e-3) / 1e9
+    clocks = result["clocks"]
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    int_peak = 148 * 128 * sm_mhz * 1e6  # lane-ops/s at the clock seen under load
+    int_alg = 45.0 * n_bases_local + 12.0 * M
+    roofline = {"bound": "hbm", "kernel": "sketch_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sketch_bytes, "kernel_ms": sketch_ms,
+                "note": "sketch is INT32-pipe bound (SURVEY 8d): see int_roofline",
+                "int_roofline": {"achieved_Tops": int_alg / (sketch_ms * 1e-3) / 1e12, "peak_Tops": int_peak / 1e12,
+                                 "frac": int_alg / (sketch_ms * 1e-3) / int_peak,
+                                 "model": "I_alg = 45*N + 12*M lane-ops; peak = 148 SM x 128 lanes x sm clock under load"},
+                "path": {"algorithmic_bytes": n_bases_local / 4 + 40 * M + 40 * Un + 24 * Ue, "ms": total_ms,
+                         "achieved": (n_bases_local / 4 + 40 * M + 40 * Un + 24 * Ue) / (total_ms * 1e-3) / 1e9,
+                         "stage_ms": {n: float(np.mean([s[n] for s in stages]))
+                                      for n in ("plan_ms", "sketch_kernel_ms", "reorder_ms", "sketch_ms", "sort_nodes_ms",
+                                                "nodes_ms", "edges_ms")}}}
+
+    e2e_runs = result["e2e_runs"]
+    e2e_s = float(np.mean([r[0] for r in e2e_runs]))
+    d2h = 8 * M + 40 * Un + 24 * Ue
+    e2e = {"value": n_bases_total / e2e_s / 1e9, "unit": "Gbp/s",
+           "h2d_bytes_per_step": int(packed_bytes + 12 * n_records) * world, "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_s * 1e3,
+           "stage_ms": {n: float(np.mean([r[1][n] for r in e2e_runs])) for n in ("h2d_ms", "total_ms", "d2h_ms")},
+           "what": "sw_build_from_batch: pinned 2-bit host batch -> H2D -> sketch+graph -> D2H host arrays"}
+
+    cpu_baseline = None
+    parity_sample = None
+    if not args.no_cpu_baseline and world == 1:
+        n_s = args.sample_genomes or int(np.clip(os.cpu_count() or 8, 32, 96))
+        idx = sample_indices(spec, n_s)
+        d, paths, is_t, nb = write_sample(ss, idx)
+        try:
+            r = time_reference(paths, is_t, k, w, nb, steps=1, warmup=1)
+            # the same sample through our FASTA entry point: bit-exact check + FASTA-inclusive e2e
+            from seqwin_b200.graph import KmerGraph, _get_penalty
+            t0 = time.perf_counter()
+            g = KmerGraph(paths, k, w, n_cpu=os.cpu_count() or 8)
+            nodes = g.nodes.copy()
+            _get_penalty(g.kmers, nodes, g.record_offsets, is_t)
+            ours_s = time.perf_counter() - t0
+            rk, rn, re_, ro = r.pop("graph")
+            parity_sample = bool(np.array_equal(g.kmers, rk) and np.array_equal(nodes, rn)
+                                 and np.array_equal(g.edges, re_) and np.array_equal(g.record_offsets, ro))
+            cpu_baseline = {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
+            cpu_baseline["ours_same_sample_from_fasta_gbps"] = nb / ours_s / 1e9
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+
+    line = {"metric": "Gbp/s sketched+graph-built", "value": value, "unit": "Gbp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload, "l2": "inputs larger than L2 (packed batch %.0f MB > 126 MB)" % (packed_bytes / 1e6),
+                       "timing": "CUDA events on the library stream around each step (host tile planning included)",
+                       "genomes_per_gpu": args.genomes, "gen_seconds": round(gen_s, 1)},
+            "graph": {"n_bases": int(n_bases_total), "n_kmers": int(M), "n_nodes": int(Un), "n_edges": int(Ue)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(s["total_launches"] for s in stages)),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_sample_bit_exact": parity_sample}
+    print(json.dumps(line))
+    L.sw_batch_free(batch)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,7 @@ void sw_dev_batch_free(sw_dev_batch* d);
 /* Per-stage device times of one build, CUDA events on the launching stream (ms). */
 typedef struct sw_stage_times {
     float h2d_ms, sketch_ms, sort_nodes_ms, nodes_ms, edges_ms, d2h_ms, total_ms;
+    float plan_ms, sketch_kernel_ms, reorder_ms; /* parts of sketch_ms: host tile plan + upload, kernel, reorder */
     uint64_t n_bases, n_kmers, n_nodes, n_edges, n_tiles, sketch_launches, total_launches;
 } sw_stage_times;
 

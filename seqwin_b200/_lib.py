@@ -13,7 +13,7 @@ SW_KMERS, SW_NODES, SW_EDGES, SW_OFFSETS, SW_RECORDS = range(5)
 
 class StageTimes(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "sketch_ms", "sort_nodes_ms", "nodes_ms", "edges_ms",
-                                         "d2h_ms", "total_ms")] + \
+                                         "d2h_ms", "total_ms", "plan_ms", "sketch_kernel_ms", "reorder_ms")] + \
                [(n, C.c_uint64) for n in ("n_bases", "n_kmers", "n_nodes", "n_edges", "n_tiles",
                                           "sketch_launches", "total_launches")]
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -78,6 +79,50 @@ void free_host(void* p, bool pinned)
 }
 
 namespace {
+std::mutex g_pool_mu;
+std::vector<HostBuf> g_pool_free;
+size_t g_pool_cached = 0;
+constexpr size_t kPoolMaxCached = (size_t)16 << 30;
+}  // namespace
+
+// Pinned allocations are expensive (page locking), so graph export buffers are recycled.
+HostBuf host_pool_get(size_t bytes)
+{
+    if (bytes == 0) return HostBuf{};
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pool_free.size(); ++i)
+            if (g_pool_free[i].bytes >= bytes && g_pool_free[i].bytes <= bytes * 2 + (1u << 20) &&
+                (best < 0 || g_pool_free[i].bytes < g_pool_free[best].bytes))
+                best = (int)i;
+        if (best >= 0) {
+            HostBuf b = g_pool_free[best];
+            g_pool_free.erase(g_pool_free.begin() + best);
+            g_pool_cached -= b.bytes;
+            return b;
+        }
+    }
+    HostBuf b;
+    b.bytes = bytes + bytes / 8 + 4096;
+    b.p = alloc_host(b.bytes, &b.pinned);
+    if (!b.p) fail_runtime("host allocation of graph export buffer failed");
+    return b;
+}
+void host_pool_put(HostBuf& b)
+{
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_cached + b.bytes <= kPoolMaxCached) {
+        g_pool_cached += b.bytes;
+        g_pool_free.push_back(b);
+    } else {
+        free_host(b.p, b.pinned);
+    }
+    b = HostBuf{};
+}
+
+namespace {
 
 struct StreamGuard {
     cudaStream_t s = nullptr;
@@ -140,7 +185,17 @@ sw_dev_batch* dev_upload(const sw_batch& b)
     d->rec_word_off.alloc(R, s);
     d->rec_asm.alloc(R, s);
     const std::vector<uint32_t> ra = record_assembly_map(b.record_offsets);
+    d->rec_len.alloc(R, s);
+    d->rec_inv_off.alloc(R + 1, s);
+    d->inv_start.alloc(b.inv_start.size(), s);
+    d->inv_len.alloc(b.inv_len.size(), s);
+    SW_CUDA(cudaMemcpyAsync(d->rec_inv_off.p, b.rec_inv_off.data(), (R + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (!b.inv_start.empty()) {
+        SW_CUDA(cudaMemcpyAsync(d->inv_start.p, b.inv_start.data(), b.inv_start.size() * 4, cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d->inv_len.p, b.inv_len.data(), b.inv_len.size() * 4, cudaMemcpyHostToDevice, s));
+    }
     if (R) {
+        SW_CUDA(cudaMemcpyAsync(d->rec_len.p, b.rec_len.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         SW_CUDA(cudaMemcpyAsync(d->rec_word_off.p, b.rec_word_off.data(), R * sizeof(uint64_t),
                                 cudaMemcpyHostToDevice, s));
         SW_CUDA(cudaMemcpyAsync(d->rec_asm.p, ra.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -168,7 +223,9 @@ sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_time
     cudaEventCreate(&e1);
     cudaEventCreate(&e2);
     cudaEventRecord(e0, s);
-    DevPlan plan = make_plan(d.meta, k, w, s);
+    const auto host_t0 = std::chrono::steady_clock::now();
+    DevPlan plan = make_plan(d, k, w, s);
+    const float plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     SketchStream st;
     run_sketch(d.words.p, d.rec_word_off.p, plan, k, w, 0u, s, st);
     cudaEventRecord(e1, s);
@@ -177,10 +234,16 @@ sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_time
     cudaEventRecord(e2, s);
     SW_CUDA(cudaStreamSynchronize(s));
     g->on_device = true;
+    g->n_kmers = g->dev.n_kmers;
+    g->n_nodes = g->dev.n_nodes;
+    g->n_edges = g->dev.n_edges;
     if (t) {
         memset(t, 0, sizeof(*t));
         cudaEventElapsedTime(&t->sketch_ms, e0, e1);
         cudaEventElapsedTime(&t->total_ms, e0, e2);
+        t->plan_ms = plan_ms;
+        t->sketch_kernel_ms = st.kernel_ms;
+        t->reorder_ms = st.reorder_ms;
         t->sort_nodes_ms = gt.sort_nodes_ms;
         t->nodes_ms = gt.nodes_ms;
         t->edges_ms = gt.edges_ms;
@@ -202,18 +265,15 @@ void graph_to_host(sw_graph& g)
 {
     if (g.on_host) return;
     cudaStream_t s = g.stream;
-    g.h_kmers.resize(g.dev.n_kmers);
-    g.h_nodes.resize(g.dev.n_nodes);
-    g.h_edges.resize(g.dev.n_edges);
-    if (g.dev.n_kmers)
-        SW_CUDA(cudaMemcpyAsync(g.h_kmers.data(), g.dev.kmers.p, g.dev.n_kmers * sizeof(sw_kmer),
-                                cudaMemcpyDeviceToHost, s));
-    if (g.dev.n_nodes)
-        SW_CUDA(cudaMemcpyAsync(g.h_nodes.data(), g.dev.nodes.p, g.dev.n_nodes * sizeof(sw_node),
-                                cudaMemcpyDeviceToHost, s));
-    if (g.dev.n_edges)
-        SW_CUDA(cudaMemcpyAsync(g.h_edges.data(), g.dev.edges.p, g.dev.n_edges * sizeof(sw_edge),
-                                cudaMemcpyDeviceToHost, s));
+    g.h_kmers = host_pool_get(g.n_kmers * sizeof(sw_kmer));
+    g.h_nodes = host_pool_get(g.n_nodes * sizeof(sw_node));
+    g.h_edges = host_pool_get(g.n_edges * sizeof(sw_edge));
+    if (g.n_kmers)
+        SW_CUDA(cudaMemcpyAsync(g.h_kmers.p, g.dev.kmers.p, g.n_kmers * sizeof(sw_kmer), cudaMemcpyDeviceToHost, s));
+    if (g.n_nodes)
+        SW_CUDA(cudaMemcpyAsync(g.h_nodes.p, g.dev.nodes.p, g.n_nodes * sizeof(sw_node), cudaMemcpyDeviceToHost, s));
+    if (g.n_edges)
+        SW_CUDA(cudaMemcpyAsync(g.h_edges.p, g.dev.edges.p, g.n_edges * sizeof(sw_edge), cudaMemcpyDeviceToHost, s));
     SW_CUDA(cudaStreamSynchronize(s));
     g.on_host = true;
 }
@@ -331,19 +391,19 @@ int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, u
         check_kw(k, w);
         init_device_once();
         std::unique_ptr<sw_batch> b(batch_from_fasta(paths, n_paths, n_host_threads));
-        sw_graph* g = nullptr;
-        int rc = sw_build_from_batch(b.get(), k, w, &g, nullptr);
-        if (rc != SW_OK) throw Error(rc, g_last_error);
-        *out = g;
+        std::unique_ptr<sw_dev_batch, void (*)(sw_dev_batch*)> d(dev_upload(*b), sw_dev_batch_free);
+        b.reset();
+        // the graph stays in HBM; sw_graph_export copies it straight into the caller's arrays
+        *out = dev_build(*d, k, w, nullptr);
     });
 }
 
 size_t sw_graph_size(const sw_graph* g, int which)
 {
     switch (which) {
-    case SW_KMERS: return g->on_host ? g->h_kmers.size() : g->dev.n_kmers;
-    case SW_NODES: return g->on_host ? g->h_nodes.size() : g->dev.n_nodes;
-    case SW_EDGES: return g->on_host ? g->h_edges.size() : g->dev.n_edges;
+    case SW_KMERS: return g->n_kmers;
+    case SW_NODES: return g->n_nodes;
+    case SW_EDGES: return g->n_edges;
     case SW_OFFSETS: return g->record_offsets.size();
     case SW_RECORDS: return g->ids.size();
     default: return 0;
@@ -353,10 +413,18 @@ size_t sw_graph_size(const sw_graph* g, int which)
 int sw_graph_export(sw_graph* g, void* kmers, void* nodes, void* edges, uint32_t* record_offsets)
 {
     return guarded([&] {
-        if (!g->on_host) graph_to_host(*g);
-        if (kmers && !g->h_kmers.empty()) memcpy(kmers, g->h_kmers.data(), g->h_kmers.size() * sizeof(sw_kmer));
-        if (nodes && !g->h_nodes.empty()) memcpy(nodes, g->h_nodes.data(), g->h_nodes.size() * sizeof(sw_node));
-        if (edges && !g->h_edges.empty()) memcpy(edges, g->h_edges.data(), g->h_edges.size() * sizeof(sw_edge));
+        struct Part { void* dst; const void* host; const void* dev; size_t bytes; };
+        const Part parts[3] = {
+            {kmers, g->h_kmers.p, g->dev.kmers.p, g->n_kmers * sizeof(sw_kmer)},
+            {nodes, g->h_nodes.p, g->dev.nodes.p, g->n_nodes * sizeof(sw_node)},
+            {edges, g->h_edges.p, g->dev.edges.p, g->n_edges * sizeof(sw_edge)}};
+        for (const Part& pt : parts) {
+            if (!pt.dst || !pt.bytes) continue;
+            if (g->on_host) memcpy(pt.dst, pt.host, pt.bytes);
+            else  // straight from HBM into the caller's (numpy) buffer, no intermediate copy
+                SW_CUDA(cudaMemcpyAsync(pt.dst, pt.dev, pt.bytes, cudaMemcpyDeviceToHost, g->stream));
+        }
+        if (!g->on_host) SW_CUDA(cudaStreamSynchronize(g->stream));
         if (record_offsets)
             memcpy(record_offsets, g->record_offsets.data(), g->record_offsets.size() * sizeof(uint32_t));
     });
@@ -373,6 +441,17 @@ const char* sw_graph_record_id(const sw_graph* g, size_t a, size_t i)
     const size_t r = (size_t)g->record_offsets[a] + i;
     return r < g->ids.size() ? g->ids[r].c_str() : nullptr;
 }
+}  // extern "C"
+
+sw_graph::~sw_graph()
+{
+    sw::host_pool_put(h_kmers);
+    sw::host_pool_put(h_nodes);
+    sw::host_pool_put(h_edges);
+}
+
+extern "C" {
+
 void sw_graph_free(sw_graph* g)
 {
     if (!g) return;
@@ -459,7 +538,7 @@ int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_ou
         init_device_once();
         check_kw(k, w);
         cudaStream_t s = d->stream;
-        DevPlan plan = make_plan(d->meta, k, w, s);
+        DevPlan plan = make_plan(*d, k, w, s);
         SketchStream st;
         run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, 0u, s, st);
         *n_out = st.n;

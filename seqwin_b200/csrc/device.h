@@ -9,6 +9,8 @@
 #include "common.h"
 #include "ingest.h"
 
+struct sw_dev_batch;
+
 namespace sw {
 
 #define SW_CUDA(expr)                                                                        \
@@ -52,6 +54,15 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// A (pinned) host buffer owned by the HostPool cache.
+struct HostBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool pinned = false;
+};
+HostBuf host_pool_get(size_t bytes);
+void host_pool_put(HostBuf& b);
+
 void init_device_once();
 int sm_count();
 
@@ -70,10 +81,13 @@ struct SketchStream {
     DevBuf<uint64_t> vals;  // pos | record << 32
     uint64_t n = 0;
     uint32_t launches = 0;
+    float kernel_ms = 0, reorder_ms = 0;  // CUDA-event times of the last run
 };
 
 int sketch_pick_config(uint32_t w, uint32_t* tk_out);
-DevPlan make_plan(const sw_batch& meta, uint32_t k, uint32_t w, cudaStream_t s);
+// Device-side tile planner: cuts every record's valid-k-mer stream into tiles (see ingest.h:
+// plan_tiles is the host statement of the same rule, used by the test emulator).
+DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s);
 void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const DevPlan& plan,
                 uint32_t k, uint32_t w, uint32_t rec_base, cudaStream_t s, SketchStream& out);
 
@@ -115,6 +129,9 @@ struct sw_dev_batch {
     sw::DevBuf<uint32_t> words;
     sw::DevBuf<uint64_t> rec_word_off;
     sw::DevBuf<uint32_t> rec_asm;   // [R] assembly of each record
+    sw::DevBuf<uint32_t> rec_len;      // [R] bases per record
+    sw::DevBuf<uint32_t> rec_inv_off;  // [R+1] slice of inv_* owned by each record
+    sw::DevBuf<uint32_t> inv_start, inv_len;  // unhashable runs (record-relative)
     sw_batch meta;                  // host tables (no packed words) for the planner + ids
     cudaStream_t stream = nullptr;
     float h2d_ms = 0;
@@ -123,10 +140,11 @@ struct sw_dev_batch {
 struct sw_graph {
     sw::DevGraph dev;
     bool on_device = false;
-    std::vector<sw_kmer> h_kmers;
-    std::vector<sw_node> h_nodes;
-    std::vector<sw_edge> h_edges;
+    // host copies live in pinned buffers drawn from a process-wide cache (api.cu: HostPool)
+    sw::HostBuf h_kmers, h_nodes, h_edges;
+    uint64_t n_kmers = 0, n_nodes = 0, n_edges = 0;  // sizes (valid for device and host copies)
     bool on_host = false;
+    ~sw_graph();
     std::vector<uint32_t> record_offsets;
     std::vector<std::string> ids;
     cudaStream_t stream = nullptr;

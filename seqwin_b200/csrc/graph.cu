@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "device.h"
+#include "scan.cuh"
 
 namespace sw {
 
@@ -84,41 +85,6 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp)
     return t;
 }
 
-// In-place exclusive scan of per-block counts (single CTA), total to *total.
-__global__ void __launch_bounds__(1024) scan_counts_kernel(unsigned long long* counts, uint64_t n,
-                                                           unsigned long long* total)
-{
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (uint64_t base = 0; base < n; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const unsigned long long v = i < n ? counts[i] : 0;
-        unsigned long long inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        unsigned long long wbase = 0, sum = 0;
-        for (int w = 0; w < 32; ++w) {
-            const unsigned long long t = s_warp[w];
-            if (w < wid) wbase += t;
-            sum += t;
-        }
-        const unsigned long long carry = s_carry;
-        if (i < n) counts[i] = carry + wbase + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + sum;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = s_carry;
-}
-
 __global__ void iota_kernel(uint32_t* v, uint64_t n)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -127,8 +93,9 @@ __global__ void iota_kernel(uint32_t* v, uint64_t n)
 
 // ---- nodes ------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kNT) node_count_kernel(const uint64_t* __restrict__ ks, uint64_t n,
-                                                         unsigned long long* counts)
+// run starts of a sorted key array (nodes and edges)
+__global__ void __launch_bounds__(kNT) key_run_count_kernel(const uint64_t* __restrict__ ks, uint64_t n,
+                                                            unsigned long long* counts)
 {
     __shared__ uint32_t s_warp[kNT / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
@@ -141,6 +108,7 @@ __global__ void __launch_bounds__(kNT) node_count_kernel(const uint64_t* __restr
     const uint32_t t = block_sum(c, s_warp);
     if (threadIdx.x == 0) counts[blockIdx.x] = t;
 }
+
 
 __global__ void __launch_bounds__(kNT) node_write_kernel(
     const uint64_t* __restrict__ ks, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ stream_vals,
@@ -261,22 +229,6 @@ __global__ void __launch_bounds__(kNT) edge_final_kernel(
     }
 }
 
-// also used for the edge run starts
-__global__ void __launch_bounds__(kNT) key_run_count_kernel(const uint64_t* __restrict__ ks, uint64_t n,
-                                                            unsigned long long* counts)
-{
-    __shared__ uint32_t s_warp[kNT / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
-    uint32_t c = 0;
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
-        if (j < n) c += (j == 0 || ks[j] != ks[j - 1]) ? 1u : 0u;
-    }
-    const uint32_t t = block_sum(c, s_warp);
-    if (threadIdx.x == 0) counts[blockIdx.x] = t;
-}
-
 // ---- penalty ----------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) penalty_kernel(
@@ -367,7 +319,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     timer.start();
     const uint32_t nb = blocks_for(M);
     DevBuf<unsigned long long> counts((size_t)nb + 1, s);
-    node_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
+    key_run_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
     scan_counts_kernel<<<1, 1024, 0, s>>>(counts.p, nb, counts.p + nb);
     SW_CUDA(cudaGetLastError());
     unsigned long long n_nodes = 0;

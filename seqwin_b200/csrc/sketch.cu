@@ -1,13 +1,16 @@
-// sketch.cu -- persistent sketch kernel: ntHash2 + (w,k) window minimizers + ordered emission.
+// sketch.cu -- persistent sketch kernels: ntHash2 + (w,k) window minimizers + emission.
 //
 // Replaces the reference's per-record btllib::minimize_sequence loop
 // (cpp/vendor/btllib/minimizer.cpp:53-90, called from cpp/src/seqwin/build.cpp:152).
 //
 // One CTA processes one tile (<= TK valid k-mers of one record, see sketch_tile.h) at a time and
-// loops, taking tile tickets from a global counter.  Tiles are numbered in (record, window)
-// order and tickets are handed out in that order, so a decoupled look-back over per-tile
-// minimizer counts gives every tile its slot range in the globally ordered output stream
-// without a second pass.  Output: out_key[i] = h1, out_val[i] = pos | record_idx << 32.
+// loops, taking tile tickets from a global counter.  A tile appends its minimizers (already in
+// position order) at a slot range claimed with ONE atomicAdd on a global cursor, so CTAs never
+// wait for each other; a segment-copy pass (reorder_kernel) then moves each tile's range to its
+// place in (record, window) order, which is the order the stable graph sort relies on.
+//   sketch_fast_kernel     w-1 >= C1: chunk == thread, fully unrolled, flags fused (sketch_tile.h)
+//   sketch_generic_kernel  any w: runtime chunking / direct scan for tiny windows
+// Output: out_key[i] = h1, out_val[i] = pos | record_idx << 32.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -15,26 +18,12 @@
 
 #include "device.h"
 #include "nthash.h"
+#include "scan.cuh"
 #include "sketch_tile.h"
 
 namespace sw {
 
 namespace {
-
-constexpr unsigned long long kStAgg = 1ULL << 62;
-constexpr unsigned long long kStInc = 2ULL << 62;
-constexpr unsigned long long kStMask = (1ULL << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // Exclusive block scan of one u32 per thread; *total = block sum. Contains two barriers.
 template <int NT>
@@ -61,8 +50,17 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_s
     return base + inc - v;
 }
 
+// thread 0: claim `total` output slots for this tile and record where they are
+__device__ __forceinline__ unsigned long long claim_slots(const SketchParams& P, uint32_t tile_id, uint32_t total)
+{
+    const unsigned long long slot = total ? atomicAdd(P.cursor, (unsigned long long)total) : 0ULL;
+    P.tile_count[tile_id] = total;
+    P.tile_slot[tile_id] = slot;
+    return slot;
+}
+
 template <int NT, int C1>
-__global__ void __launch_bounds__(NT) sketch_kernel(const __grid_constant__ SketchParams P)
+__global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__ SketchParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tile;
@@ -70,14 +68,47 @@ __global__ void __launch_bounds__(NT) sketch_kernel(const __grid_constant__ Sket
     __shared__ unsigned long long s_gbase;
 
     constexpr uint32_t TK = NT * C1;
-    const TileSmem S = carve_tile_smem(smem_raw, TK);
+    const TileSmem S = carve_tile_smem(smem_raw, TK, NT);
     const int tid = threadIdx.x;
-
     if (tid < 20) S.tab[tid] = P.table.e[tid];
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
-        __syncthreads();  // also orders the table / previous tile's smem reuse
+        __syncthreads();  // also: table visible / previous tile's smem reads done
+        const uint32_t tile_id = s_tile;
+        if (tile_id >= P.n_tiles) break;
+        const Tile T = P.tiles[tile_id];
+
+        fastA_hash_prefix<NT, C1>(tid, P, T, S);
+        __syncthreads();
+        FastState st;
+        fastB_windows<NT, C1>(tid, P, T, S, st);
+        __syncthreads();
+        const uint32_t cnt = fastC_finish<NT, C1>(tid, P, T, S, st);
+        uint32_t total;
+        const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
+        if (tid == 0) s_gbase = claim_slots(P, tile_id, total);
+        __syncthreads();
+        if (cnt) fastD_write<NT, C1>(tid, P, T, S, st, s_gbase + excl);
+    }
+}
+
+template <int NT, int C1>
+__global__ void __launch_bounds__(NT) sketch_generic_kernel(const __grid_constant__ SketchParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp_sums[NT / 32];
+    __shared__ unsigned long long s_gbase;
+
+    constexpr uint32_t TK = NT * C1;
+    const TileSmem S = carve_tile_smem(smem_raw, TK, TK / 9 + 2);
+    const int tid = threadIdx.x;
+    if (tid < 20) S.tab[tid] = P.table.e[tid];
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
         const uint32_t tile_id = s_tile;
         if (tile_id >= P.n_tiles) break;
         const Tile T = P.tiles[tile_id];
@@ -99,45 +130,52 @@ __global__ void __launch_bounds__(NT) sketch_kernel(const __grid_constant__ Sket
         uint32_t total;
         const uint32_t excl = block_excl_scan<NT>((uint32_t)__popcll(mask), s_warp_sums, &total);
         phase3b_stage(tid, c3, mask, excl, S);
-
-        if (tid == 0) {
-            unsigned long long before = 0;
-            if (tile_id == 0) {
-                st_status(P.tile_status, kStInc | total);
-            } else {
-                st_status(P.tile_status + tile_id, kStAgg | total);
-                uint32_t j = tile_id - 1;
-                for (;;) {
-                    const unsigned long long st = ld_status(P.tile_status + j);
-                    if ((st >> 62) == 0) { __nanosleep(40); continue; }
-                    before += st & kStMask;
-                    if ((st >> 62) == 2) break;
-                    --j;
-                }
-                st_status(P.tile_status + tile_id, kStInc | (before + total));
-            }
-            if (tile_id == P.n_tiles - 1) *P.total_out = before + total;
-            s_gbase = before;
-        }
+        if (tid == 0) s_gbase = claim_slots(P, tile_id, total);
         __syncthreads();
         const unsigned long long gbase = s_gbase;
         for (uint32_t i = tid; i < total; i += NT) phase3c_write(i, gbase, P, T, S);
-        // the barrier at the top of the loop separates these reads from the next tile's writes
+    }
+}
+
+// One warp per tile: move the tile's slot range to its place in (record, window) order.
+__global__ void __launch_bounds__(256) reorder_kernel(const uint64_t* __restrict__ ukey, const uint64_t* __restrict__ uval,
+                                                      const unsigned long long* __restrict__ tile_off,
+                                                      const unsigned long long* __restrict__ tile_slot, uint32_t n_tiles,
+                                                      unsigned long long total, uint64_t* __restrict__ okey,
+                                                      uint64_t* __restrict__ oval)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = warp; t < n_tiles; t += n_warps) {
+        const unsigned long long dst = tile_off[t];
+        const unsigned long long end = (t + 1 < n_tiles) ? tile_off[t + 1] : total;
+        const unsigned long long src = tile_slot[t];
+        const uint32_t n = (uint32_t)(end - dst);
+        for (uint32_t i = lane; i < n; i += 32) {
+            okey[dst + i] = ukey[src + i];
+            oval[dst + i] = uval[src + i];
+        }
     }
 }
 
 struct KernelConfig {
     int nt, c1;
-    void (*kernel)(const SketchParams);
+    void (*fast)(const SketchParams);
+    void (*generic)(const SketchParams);
 };
 
+#define SW_CFG(NT, C1) {NT, C1, sketch_fast_kernel<NT, C1>, sketch_generic_kernel<NT, C1>}
 const KernelConfig kConfigs[] = {
-    {128, 45, sketch_kernel<128, 45>},  // default: 3 warps per scheduler at 2 CTAs/SM
-    {256, 21, sketch_kernel<256, 21>},  // more warps, more warm-up
-    {256, 45, sketch_kernel<256, 45>},
-    {256, 61, sketch_kernel<256, 61>},  // large windows (w up to ~15k)
+    SW_CFG(128, 33),  // default: 4 CTAs/SM
+    SW_CFG(128, 45),
+    SW_CFG(256, 45),
+    SW_CFG(256, 61),  // large windows (w up to ~15k)
+    SW_CFG(128, 63),
+    SW_CFG(256, 21),
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
+constexpr int kLargeWindowConfig = 3;
 
 }  // namespace
 
@@ -146,7 +184,7 @@ int sketch_pick_config(uint32_t w, uint32_t* tk_out)
     int cfg = 0;
     if (const char* e = getenv("SEQWIN_SKETCH_CONFIG")) cfg = std::max(0, std::min(kNumConfigs - 1, atoi(e)));
     // keep the halo (w k-mers re-hashed per tile) under ~25 % of the tile
-    if ((uint64_t)w * 4 > (uint64_t)kConfigs[cfg].nt * kConfigs[cfg].c1) cfg = 3;
+    if ((uint64_t)w * 4 > (uint64_t)kConfigs[cfg].nt * kConfigs[cfg].c1) cfg = kLargeWindowConfig;
     const uint32_t tk = (uint32_t)kConfigs[cfg].nt * kConfigs[cfg].c1;
     if (w + 64 > tk)
         fail_runtime("windowsize " + std::to_string(w) + " exceeds the sketch kernel's limit of " +
@@ -155,24 +193,116 @@ int sketch_pick_config(uint32_t w, uint32_t* tk_out)
     return cfg;
 }
 
-DevPlan make_plan(const sw_batch& meta, uint32_t k, uint32_t w, cudaStream_t s)
+// ---- device-side tile planner -------------------------------------------------------------------
+// Same rule as plan_tiles() in ingest.cpp, one thread per record (records have tens of tiles).
+
+struct RecordRuns {
+    const uint32_t* rec_len;
+    const uint32_t* rec_inv_off;
+    const uint32_t* inv_start;
+    const uint32_t* inv_len;
+};
+
+// Walk the hashable runs of record r; f(kidx, pos, n) for every run with >= k bases.
+template <typename F>
+__device__ __forceinline__ uint64_t for_each_piece(const RecordRuns& rr, uint32_t r, uint32_t k, F&& f)
+{
+    const uint32_t L = rr.rec_len[r];
+    uint64_t n_valid = 0;
+    uint32_t s = 0;
+    for (uint32_t iv = rr.rec_inv_off[r]; iv <= rr.rec_inv_off[r + 1]; ++iv) {
+        const bool last = iv == rr.rec_inv_off[r + 1];
+        const uint32_t stop = last ? L : rr.inv_start[iv];
+        if (stop - s >= k) {
+            f((uint32_t)n_valid, s, stop - s - k + 1);
+            n_valid += stop - s - k + 1;
+        }
+        if (!last) s = rr.inv_start[iv] + rr.inv_len[iv];
+    }
+    return n_valid;
+}
+
+__global__ void plan_count_kernel(RecordRuns rr, uint32_t R, uint32_t k, uint32_t w, uint32_t tw,
+                                  unsigned long long* tiles_per_rec, unsigned long long* pieces_per_rec,
+                                  unsigned long long* totals)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    uint32_t n_pieces = 0;
+    const uint64_t n_valid = for_each_piece(rr, r, k, [&](uint32_t, uint32_t, uint32_t) { ++n_pieces; });
+    unsigned long long n_tiles = 0;
+    if (n_valid >= w) {
+        const uint64_t n_win = n_valid - w + 1;
+        n_tiles = (n_win + tw - 1) / tw;
+        atomicAdd(totals + 1, (unsigned long long)n_win);
+    } else {
+        n_pieces = 0;
+    }
+    if (n_valid) atomicAdd(totals, (unsigned long long)n_valid);
+    tiles_per_rec[r] = n_tiles;
+    pieces_per_rec[r] = n_pieces;
+}
+
+__global__ void plan_fill_kernel(RecordRuns rr, uint32_t R, uint32_t k, uint32_t w, uint32_t tw,
+                                 const unsigned long long* tile_off, const unsigned long long* piece_off,
+                                 unsigned long long n_tiles_total, Tile* tiles, Piece* pieces)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const unsigned long long t0 = tile_off[r];
+    const unsigned long long t1 = (r + 1 < R) ? tile_off[r + 1] : n_tiles_total;
+    if (t1 == t0) return;
+    const unsigned long long p0 = piece_off[r];
+    uint32_t np = 0;
+    const uint64_t n_valid = for_each_piece(rr, r, k, [&](uint32_t kidx, uint32_t pos, uint32_t n) {
+        pieces[p0 + np] = Piece{kidx, pos, n};
+        ++np;
+    });
+    const uint64_t n_win = n_valid - w + 1;
+    uint32_t pc = 0;
+    unsigned long long t = t0;
+    for (uint64_t a0 = 0; a0 < n_win; a0 += tw, ++t) {
+        const uint64_t a1 = a0 + tw < n_win ? a0 + tw : n_win;
+        const uint64_t e0 = a0 ? a0 - 1 : 0;
+        const uint64_t nk = a1 + w - 1 - e0;
+        while ((uint64_t)pieces[p0 + pc].kidx + pieces[p0 + pc].n <= e0) ++pc;
+        uint32_t pe = pc;
+        while (pe + 1 < np && pieces[p0 + pe + 1].kidx < e0 + nk) ++pe;
+        tiles[t] = Tile{r, (uint32_t)e0, (uint32_t)nk, (uint32_t)(p0 + pc), pe - pc + 1, a0 == 0 ? 1u : 0u};
+    }
+}
+
+DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
 {
     DevPlan dp;
     dp.config = sketch_pick_config(w, &dp.tk);
-    Plan plan = plan_tiles(meta, k, w, dp.tk);
-    dp.n_tiles = (uint32_t)plan.tiles.size();
-    dp.n_windows = plan.n_windows;
-    dp.n_kmers = plan.n_kmers;
-    dp.tiles.alloc(plan.tiles.size(), s);
-    dp.pieces.alloc(plan.pieces.size(), s);
-    if (!plan.tiles.empty())
-        SW_CUDA(cudaMemcpyAsync(dp.tiles.p, plan.tiles.data(), plan.tiles.size() * sizeof(Tile),
-                                cudaMemcpyHostToDevice, s));
-    if (!plan.pieces.empty())
-        SW_CUDA(cudaMemcpyAsync(dp.pieces.p, plan.pieces.data(), plan.pieces.size() * sizeof(Piece),
-                                cudaMemcpyHostToDevice, s));
-    // the host vectors die at return: the copies above must have consumed them
+    const uint32_t R = (uint32_t)d.meta.rec_len.size();
+    if (R == 0) return dp;
+    const uint32_t tw = dp.tk - w;
+    RecordRuns rr{d.rec_len.p, d.rec_inv_off.p, d.inv_start.p, d.inv_len.p};
+    // [0,R) tiles per record, [R] total tiles, [R+1, 2R+1) pieces per record, [2R+1] total pieces,
+    // [2R+2] valid k-mers, [2R+3] windows
+    DevBuf<unsigned long long> buf((size_t)2 * R + 4, s);
+    SW_CUDA(cudaMemsetAsync(buf.p + 2 * (size_t)R + 2, 0, 2 * sizeof(unsigned long long), s));
+    const uint32_t grid = (R + 127) / 128;
+    plan_count_kernel<<<grid, 128, 0, s>>>(rr, R, k, w, tw, buf.p, buf.p + R + 1, buf.p + 2 * (size_t)R + 2);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(buf.p, R, buf.p + R);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(buf.p + R + 1, R, buf.p + 2 * (size_t)R + 1);
+    SW_CUDA(cudaGetLastError());
+    unsigned long long h[4];
+    SW_CUDA(cudaMemcpyAsync(&h[0], buf.p + R, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaMemcpyAsync(&h[1], buf.p + 2 * (size_t)R + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     SW_CUDA(cudaStreamSynchronize(s));
+    if (h[0] > 0x7FFFFFFFull) fail_runtime("too many sketch tiles");
+    if (h[1] > 0xFFFFFFF0ull) fail_runtime("too many valid runs");
+    dp.n_tiles = (uint32_t)h[0];
+    dp.n_kmers = h[2];
+    dp.n_windows = h[3];
+    dp.tiles.alloc(h[0], s);
+    dp.pieces.alloc(h[1], s);
+    if (dp.n_tiles)
+        plan_fill_kernel<<<grid, 128, 0, s>>>(rr, R, k, w, tw, buf.p, buf.p + R + 1, h[0], dp.tiles.p, dp.pieces.p);
+    SW_CUDA(cudaGetLastError());
     return dp;
 }
 
@@ -188,23 +318,29 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     }
     const KernelConfig& kc = kConfigs[plan.config];
     const uint32_t tk = (uint32_t)kc.nt * kc.c1;
-    const size_t smem = tile_smem_bytes(tk);
-    SW_CUDA(cudaFuncSetAttribute(kc.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool fast = (w - 1 >= (uint32_t)kc.c1) && !getenv("SEQWIN_SKETCH_GENERIC");
+    auto kernel = fast ? kc.fast : kc.generic;
+    const size_t smem = tile_smem_bytes(tk, fast ? (uint32_t)kc.nt : tk / 9 + 2);
+    SW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
-    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kc.kernel, kc.nt, smem));
+    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kc.nt, smem));
     if (ctas_per_sm < 1) fail_runtime("sketch kernel does not fit on this device");
     const uint32_t grid = (uint32_t)std::min<uint64_t>(plan.n_tiles, (uint64_t)sm_count() * ctas_per_sm);
 
-    DevBuf<unsigned long long> status(plan.n_tiles, s);
-    DevBuf<unsigned long long> counters(2, s);  // [0] ticket (as u32), [1] total
+    // [0, n_tiles): per-tile counts (scanned in place into ordered offsets); then the slots
+    DevBuf<unsigned long long> tile_info((size_t)plan.n_tiles * 2, s);
+    DevBuf<unsigned long long> counters(3, s);  // [0] cursor, [1] ticket (as u32), [2] scan total
 
     // expected density 2/(w+1); leave 50 % headroom and re-run with the exact size on overflow
     uint64_t capacity = (uint64_t)((double)plan.n_kmers * 3.0 / ((double)w + 1.0)) + 4096;
     capacity = std::min<uint64_t>(capacity, plan.n_windows);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        out.keys.alloc(capacity, s);
-        out.vals.alloc(capacity, s);
-        SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
+    DevBuf<uint64_t> ukeys, uvals;
+    unsigned long long total = 0;
+    cudaEvent_t ev[4];
+    for (auto& e : ev) cudaEventCreate(&e);
+    for (int attempt = 0;; ++attempt) {
+        ukeys.alloc(capacity, s);
+        uvals.alloc(capacity, s);
         SW_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
         SketchParams P;
         P.words = d_words;
@@ -217,24 +353,44 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.c2 = choose_c2(w, (uint32_t)kc.c1);
         P.rec_base = rec_base;
         P.h1_mult = h1_multiplier(k);
-        P.out_key = out.keys.p;
-        P.out_val = out.vals.p;
+        P.out_key = ukeys.p;
+        P.out_val = uvals.p;
         P.capacity = capacity;
-        P.tile_status = status.p;
-        P.tile_counter = reinterpret_cast<unsigned int*>(counters.p);
-        P.total_out = counters.p + 1;
+        P.cursor = counters.p;
+        P.tile_count = tile_info.p;
+        P.tile_slot = tile_info.p + plan.n_tiles;
+        P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 1);
         P.table = make_roll_table(k);
-        kc.kernel<<<grid, kc.nt, smem, s>>>(P);
+        cudaEventRecord(ev[0], s);
+        kernel<<<grid, kc.nt, smem, s>>>(P);
+        cudaEventRecord(ev[1], s);
         SW_CUDA(cudaGetLastError());
         ++out.launches;
-        unsigned long long total = 0;
-        SW_CUDA(cudaMemcpyAsync(&total, counters.p + 1, sizeof(total), cudaMemcpyDeviceToHost, s));
+        SW_CUDA(cudaMemcpyAsync(&total, counters.p, sizeof(total), cudaMemcpyDeviceToHost, s));
         SW_CUDA(cudaStreamSynchronize(s));
-        out.n = total;
-        if (total <= capacity) return;
+        if (total <= capacity) break;
+        if (attempt) fail_runtime("sketch output overflow after resize");
         capacity = total;  // low-complexity input: more minimizers than the density estimate
     }
-    fail_runtime("sketch output overflow after resize");
+    out.n = total;
+    out.keys.alloc(total, s);
+    out.vals.alloc(total, s);
+    cudaEventElapsedTime(&out.kernel_ms, ev[0], ev[1]);
+    if (total == 0) {
+        for (auto& e : ev) cudaEventDestroy(e);
+        return;
+    }
+    cudaEventRecord(ev[2], s);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(tile_info.p, plan.n_tiles, counters.p + 2);
+    const uint32_t rgrid = (uint32_t)std::min<uint64_t>(((uint64_t)plan.n_tiles + 7) / 8, (uint64_t)sm_count() * 8);
+    reorder_kernel<<<rgrid, 256, 0, s>>>(ukeys.p, uvals.p, tile_info.p, tile_info.p + plan.n_tiles, plan.n_tiles,
+                                         total, out.keys.p, out.vals.p);
+    cudaEventRecord(ev[3], s);
+    SW_CUDA(cudaGetLastError());
+    out.launches += 2;
+    SW_CUDA(cudaEventSynchronize(ev[3]));
+    cudaEventElapsedTime(&out.reorder_ms, ev[2], ev[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
 }
 
 }  // namespace sw

@@ -46,9 +46,12 @@ struct SketchParams {
     uint64_t* out_key;             // [capacity] h1 of each minimizer, (record, pos) order
     uint64_t* out_val;             // [capacity] pos | record_idx << 32
     unsigned long long capacity;
-    unsigned long long* tile_status;  // decoupled look-back words, one per tile
+    // Tiles emit into [cursor, cursor + count) in completion order; tile_count / tile_slot let a
+    // segment-copy pass (sketch.cu: reorder_kernel) restore (record, window) order afterwards.
+    unsigned long long* cursor;       // next free slot of out_key / out_val
+    unsigned long long* tile_count;   // [n_tiles] minimizers emitted by each tile
+    unsigned long long* tile_slot;    // [n_tiles] first slot of each tile
     unsigned int* tile_counter;       // ticket dispenser
-    unsigned long long* total_out;    // number of minimizers produced
     RollTable table;
 };
 
@@ -58,21 +61,23 @@ struct TileSmem {
     uint64_t* h0;     // [TK]
     uint64_t* cm_h;   // [TK / 9 + 2]  chunk minima (value)
     uint16_t* cm_i;   // [TK / 9 + 2]  chunk minima (tile-local index)
-    uint16_t* amin;   // [TK] A[a]
-    uint16_t* pidx;   // [TK] in-chunk offset of the prefix argmin; reused as the emit staging list
+    uint16_t* amin;   // [TK] A[a] (fast path: only for emitting windows)
+    uint16_t* pidx;   // [TK] tile-local index of the prefix argmin of the element's chunk up to it;
+                      //      the generic path reuses it as the emit staging list
+    uint16_t* first_a;  // [TK / 9 + 2] fast path: A of each thread's first window
 };
 
-SW_HD size_t tile_smem_bytes(uint32_t tk)
+// nc = number of chunk-minimum slots: TK / 9 + 2 for the generic kernel (logical chunks of >= 9),
+// NT for the specialised kernel (chunk == thread).
+SW_HD size_t tile_smem_bytes(uint32_t tk, uint32_t nc)
 {
-    const size_t nc = tk / 9 + 2;
     size_t b = sizeof(RollEntry) * 20 + sizeof(uint64_t) * tk + sizeof(uint64_t) * nc;
-    b += sizeof(uint16_t) * (nc + 2 * (size_t)tk);
+    b += sizeof(uint16_t) * (2 * (size_t)nc + 2 * (size_t)tk);
     return (b + 15) & ~(size_t)15;
 }
 
-SW_HD TileSmem carve_tile_smem(unsigned char* base, uint32_t tk)
+SW_HD TileSmem carve_tile_smem(unsigned char* base, uint32_t tk, uint32_t nc)
 {
-    const size_t nc = tk / 9 + 2;
     TileSmem s;
     s.tab = reinterpret_cast<RollEntry*>(base);
     s.h0 = reinterpret_cast<uint64_t*>(base + sizeof(RollEntry) * 20);
@@ -80,6 +85,7 @@ SW_HD TileSmem carve_tile_smem(unsigned char* base, uint32_t tk)
     s.cm_i = reinterpret_cast<uint16_t*>(s.cm_h + nc);
     s.amin = s.cm_i + nc;
     s.pidx = s.amin + tk;
+    s.first_a = s.pidx + tk;
     return s;
 }
 
@@ -104,10 +110,13 @@ SW_HD uint32_t base_at(const uint32_t* W, uint64_t p)
 // ---- phase 1: hash --------------------------------------------------------------------------
 
 // Fast path: the whole tile lies in one run of hashable bases.  Thread hashes C1 consecutive
-// k-mers starting at record position p0: k warm-up steps, then C1-1 rolling steps.
-template <int C1>
+// k-mers starting at record position p0: k warm-up steps, then C1-1 rolling steps.  With PREFIX
+// it also tracks the running rightmost argmin of its chunk (tile-local index, base j0) into pidx
+// and returns the chunk minimum.
+template <int C1, bool PREFIX>
 SW_HD void hash_chunk_fast(const uint32_t* W, uint64_t p0, uint32_t k, const RollEntry* tab,
-                           uint64_t* h0_out)
+                           uint64_t* h0_out, uint16_t* pidx_out, uint32_t j0, uint64_t* min_h,
+                           uint32_t* min_i)
 {
     uint64_t fwd = 0, rev = 0;
     for (uint32_t i = 0; i < k; i += 16) {
@@ -117,21 +126,33 @@ SW_HD void hash_chunk_fast(const uint32_t* W, uint64_t p0, uint32_t k, const Rol
         for (int s = 0; s < 16; ++s)
             if ((uint32_t)s < m) roll_step(fwd, rev, tab[16 + ((x >> (2 * s)) & 3u)]);
     }
-    h0_out[0] = fwd + rev;
+    uint64_t bh = fwd + rev;
+    uint32_t bi = j0;
+    h0_out[0] = bh;
+    if (PREFIX) pidx_out[0] = (uint16_t)bi;
 #pragma unroll
     for (int b = 0; b < (C1 - 1 + 15) / 16; ++b) {
         const uint32_t in = fetch16(W, p0 + k + 16 * b);
         const uint32_t out = fetch16(W, p0 + 16 * b);
+        // nibble i of x / y = (out << 2 | in) of base 2i / 2i+1 of this block of 16
+        const uint32_t x = (in & 0x33333333u) | ((out & 0x33333333u) << 2);
+        const uint32_t y = ((in >> 2) & 0x33333333u) | (out & 0xCCCCCCCCu);
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
             const int n = 16 * b + s + 1;
             if (n < C1) {
-                const uint32_t idx = ((in >> (2 * s)) & 3u) | (((out >> (2 * s)) & 3u) << 2);
+                const uint32_t idx = (((s & 1) ? y : x) >> (4 * (s >> 1))) & 15u;
                 roll_step(fwd, rev, tab[idx]);
-                h0_out[n] = fwd + rev;
+                const uint64_t h = fwd + rev;
+                h0_out[n] = h;
+                if (PREFIX) {
+                    if (h <= bh) { bh = h; bi = j0 + n; }
+                    pidx_out[n] = (uint16_t)bi;
+                }
             }
         }
     }
+    if (PREFIX) { *min_h = bh; *min_i = bi; }
 }
 
 // Generic path: k-mers [j0, j1) of the tile may cross gaps between runs (pieces); every run
@@ -175,14 +196,14 @@ SW_HD void phase1_hash(int tid, const SketchParams& P, const Tile& T, const Tile
         // reads (and stores into the padded tail of h0) may run past n_kmers; the packed
         // stream has kTailPadWords of slack and window evaluation never looks there
         const uint64_t p0 = (uint64_t)pcs[0].pos + ((uint64_t)T.e0 + j0 - pcs[0].kidx);
-        hash_chunk_fast<C1>(W, p0, P.k, S.tab, S.h0 + j0);
+        hash_chunk_fast<C1, false>(W, p0, P.k, S.tab, S.h0 + j0, nullptr, j0, nullptr, nullptr);
     } else {
         const uint32_t j1 = j0 + C1 < T.n_kmers ? j0 + C1 : T.n_kmers;
         hash_range_generic(W, pcs, T.e0, j0, j1, P.k, S.tab, S.h0);
     }
 }
 
-// ---- phase 2: window minima -------------------------------------------------------------------
+// ---- phase 2 (generic, any c2 <= w-1): window minima -------------------------------------------
 
 // 2a: per logical chunk, running rightmost argmin from the chunk start (prefix) + chunk minimum.
 template <int NT>
@@ -194,15 +215,15 @@ SW_HD void phase2a_prefix(int tid, const SketchParams& P, const Tile& T, const T
         const uint32_t base = c * c2;
         const uint32_t nend = T.n_kmers - base < c2 ? T.n_kmers - base : c2;
         uint64_t bh = S.h0[base];
-        uint32_t bi = 0;
-        S.pidx[base] = 0;
+        uint32_t bi = base;
+        S.pidx[base] = (uint16_t)base;
         for (uint32_t n = 1; n < nend; ++n) {
             const uint64_t h = S.h0[base + n];
-            if (h <= bh) { bh = h; bi = n; }
+            if (h <= bh) { bh = h; bi = base + n; }
             S.pidx[base + n] = (uint16_t)bi;
         }
         S.cm_h[c] = bh;
-        S.cm_i[c] = (uint16_t)(base + bi);
+        S.cm_i[c] = (uint16_t)bi;
     }
 }
 
@@ -217,6 +238,7 @@ SW_HD void phase2b_windows(int tid, const SketchParams& P, const Tile& T, const 
         const uint32_t base = c * c2;
         // end chunk of the chunk's first window; higher windows end there or one chunk later
         const uint32_t te_lo = (base + w - 1) / c2;
+        const uint32_t e_split = (te_lo + 1) * c2;  // window ends >= e_split lie in chunk te_lo + 1
         // whole chunks strictly between c and te_lo
         bool m_lo_valid = false;
         uint64_t m_lo_h = 0;
@@ -242,15 +264,14 @@ SW_HD void phase2b_windows(int tid, const SketchParams& P, const Tile& T, const 
             if (n == c2 - 1 || h < sh) { sh = h; si = a; }
             if (a >= n_eval) continue;
             const uint32_t e = a + w - 1;
-            const uint32_t te = e / c2;
             uint64_t rh = sh;
             uint32_t ri = si;
-            if (te == te_lo) {
+            if (e < e_split) {
                 if (m_lo_valid && m_lo_h <= rh) { rh = m_lo_h; ri = m_lo_i; }
             } else {
                 if (m_hi_h <= rh) { rh = m_hi_h; ri = m_hi_i; }
             }
-            const uint32_t pe = te * c2 + S.pidx[e];
+            const uint32_t pe = S.pidx[e];
             const uint64_t ph = S.h0[pe];
             if (ph <= rh) { rh = ph; ri = pe; }
             S.amin[a] = (uint16_t)ri;
@@ -275,7 +296,7 @@ SW_HD void phase2_direct(int tid, const SketchParams& P, const Tile& T, const Ti
     }
 }
 
-// ---- phase 3: emit ----------------------------------------------------------------------------
+// ---- phase 3 (generic): emit --------------------------------------------------------------------
 
 // 3a: thread owns windows [tid*c3, (tid+1)*c3); returns the flag mask of the emitting ones.
 SW_HD uint64_t phase3a_flags(int tid, uint32_t c3, const Tile& T, uint32_t w, const TileSmem& S)
@@ -322,15 +343,178 @@ SW_HD uint32_t kmer_pos(const SketchParams& P, const Tile& T, uint32_t idx)
     return pcs[pi].pos + (uint32_t)(g - pcs[pi].kidx);
 }
 
+// write tile-local k-mer idx as a minimizer into a global slot
+SW_HD void write_minimizer(unsigned long long slot, uint32_t idx, const SketchParams& P, const Tile& T,
+                           const TileSmem& S)
+{
+    if (slot >= P.capacity) return;  // counted, not stored: the host re-runs with more room
+    P.out_key[slot] = h1_of(S.h0[idx], P.h1_mult);
+    P.out_val[slot] = (uint64_t)kmer_pos(P, T, idx) | ((uint64_t)(P.rec_base + T.rec) << 32);
+}
+
 // 3c: write staged minimizer i of the tile to its global slot.
 SW_HD void phase3c_write(uint32_t i, unsigned long long gbase, const SketchParams& P, const Tile& T,
                          const TileSmem& S)
 {
-    const unsigned long long slot = gbase + i;
-    if (slot >= P.capacity) return;  // counted, not stored: the host re-runs with more room
-    const uint32_t idx = S.pidx[i];
-    P.out_key[slot] = h1_of(S.h0[idx], P.h1_mult);
-    P.out_val[slot] = (uint64_t)kmer_pos(P, T, idx) | ((uint64_t)(P.rec_base + T.rec) << 32);
+    write_minimizer(gbase + i, S.pidx[i], P, T, S);
+}
+
+// ---- fast path: w - 1 >= C1, logical chunk == thread chunk, everything unrolled -----------------
+//
+//  A  hash own chunk + prefix argmin (fused when the tile is one run), chunk minimum
+//  --barrier--
+//  B  chunk minima of the whole chunks a window spans (two variants), suffix pass right-to-left,
+//     A[a] for own windows; window a+1 emits iff A[a+1] != A[a] -> mask bit, A kept in amin
+//  --barrier--
+//  C  the flag of the first window of the NEXT chunk (needs that thread's A), window 0, the
+//     2^64-1 exclusion; returns the number of minimizers this thread emits
+//  --block scan + one atomicAdd on the global cursor--
+//  D  write own minimizers
+struct FastState {
+    uint64_t mask;     // bit n: window j0 + n + 1 emits
+    uint32_t a_top;    // A of the thread's last window (n = C1-1)
+    uint32_t a_first;  // A of the thread's first window
+    uint32_t f0;       // thread 0 only: window 0 emits
+};
+
+template <int NT, int C1>
+SW_HD void fastA_hash_prefix(int tid, const SketchParams& P, const Tile& T, const TileSmem& S)
+{
+    const uint32_t j0 = (uint32_t)tid * C1;
+    if (j0 >= T.n_kmers) return;
+    const uint32_t* W = P.words + P.rec_word_off[T.rec];
+    const Piece* pcs = P.pieces + T.piece_lo;
+    uint64_t bh;
+    uint32_t bi;
+    if (T.n_pieces == 1) {
+        const uint64_t p0 = (uint64_t)pcs[0].pos + ((uint64_t)T.e0 + j0 - pcs[0].kidx);
+        hash_chunk_fast<C1, true>(W, p0, P.k, S.tab, S.h0 + j0, S.pidx + j0, j0, &bh, &bi);
+    } else {
+        const uint32_t j1 = j0 + C1 < T.n_kmers ? j0 + C1 : T.n_kmers;
+        hash_range_generic(W, pcs, T.e0, j0, j1, P.k, S.tab, S.h0);
+        bh = S.h0[j0];
+        bi = j0;
+        S.pidx[j0] = (uint16_t)j0;
+        for (uint32_t j = j0 + 1; j < j1; ++j) {
+            const uint64_t h = S.h0[j];
+            if (h <= bh) { bh = h; bi = j; }
+            S.pidx[j] = (uint16_t)bi;
+        }
+    }
+    S.cm_h[tid] = bh;
+    S.cm_i[tid] = (uint16_t)bi;
+}
+
+template <int NT, int C1>
+SW_HD void fastB_windows(int tid, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
+{
+    const uint32_t w = P.w;
+    const uint32_t n_eval = T.n_kmers - w + 1;
+    const uint32_t j0 = (uint32_t)tid * C1;
+    st.mask = 0;
+    st.a_top = st.a_first = 0xFFFFFFFFu;
+    st.f0 = 0;
+    if (j0 >= n_eval) return;
+    const uint32_t q = (w - 1) / C1, r = (w - 1) % C1;  // window end = chunk tid+q (+1), offset (n+r) % C1
+    // whole chunks tid+1 .. tid+q-1 (windows ending in chunk tid+q) and .. tid+q (ending in tid+q+1).
+    // Chunks past the tile only matter to windows that are not evaluated.
+    bool lo_valid = false;
+    uint64_t m_lo_h = 0;
+    uint32_t m_lo_i = 0;
+    for (uint32_t cc = (uint32_t)tid + 1; cc < (uint32_t)tid + q && cc < NT; ++cc) {
+        const uint64_t h = S.cm_h[cc];
+        if (!lo_valid || h <= m_lo_h) { m_lo_h = h; m_lo_i = S.cm_i[cc]; lo_valid = true; }
+    }
+    uint64_t m_hi_h = m_lo_h;
+    uint32_t m_hi_i = m_lo_i;
+    if ((uint32_t)tid + q < NT) {
+        const uint64_t h = S.cm_h[tid + q];
+        if (!lo_valid || h <= m_lo_h) { m_hi_h = h; m_hi_i = S.cm_i[tid + q]; }
+    }
+    uint64_t sh = 0, mask = 0;
+    uint32_t si = 0, prev_a = 0xFFFFFFFFu, a_top = 0xFFFFFFFFu;
+#pragma unroll
+    for (int n = C1 - 1; n >= 0; --n) {
+        const uint32_t a = j0 + n;
+        const uint64_t h = S.h0[a];
+        if (n == C1 - 1 || h < sh) { sh = h; si = a; }
+        if (a < n_eval) {
+            uint64_t rh = sh;
+            uint32_t ri = si;
+            if ((uint32_t)n + r >= (uint32_t)C1) {
+                if (m_hi_h <= rh) { rh = m_hi_h; ri = m_hi_i; }
+            } else {
+                if (lo_valid && m_lo_h <= rh) { rh = m_lo_h; ri = m_lo_i; }
+            }
+            const uint32_t pe = S.pidx[a + w - 1];
+            const uint64_t ph = S.h0[pe];
+            if (ph <= rh) { rh = ph; ri = pe; }
+            if (n == C1 - 1) {
+                a_top = ri;
+            } else if (a + 1 < n_eval && prev_a != ri) {
+                mask |= 1ULL << n;
+                S.amin[a + 1] = (uint16_t)prev_a;
+            }
+            prev_a = ri;
+        }
+    }
+    st.mask = mask;
+    st.a_top = a_top;
+    st.a_first = prev_a;
+    S.first_a[tid] = (uint16_t)prev_a;
+}
+
+template <int NT, int C1>
+SW_HD uint32_t fastC_finish(int tid, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
+{
+    const uint32_t n_eval = T.n_kmers - P.w + 1;
+    const uint32_t j0 = (uint32_t)tid * C1;
+    if (j0 >= n_eval) return 0;
+    uint64_t mask = st.mask;
+    const uint32_t a_b = j0 + C1;  // first window of the next chunk
+    if (a_b < n_eval) {
+        const uint32_t nxt = S.first_a[tid + 1];
+        if (nxt != st.a_top) {
+            mask |= 1ULL << (C1 - 1);
+            S.amin[a_b] = (uint16_t)nxt;
+        }
+    }
+    // minimizer.cpp:45: a selected k-mer whose h0 is 2^64-1 is never emitted
+    uint64_t it = mask;
+    while (it) {
+#if defined(__CUDA_ARCH__)
+        const int b = __ffsll((long long)it) - 1;
+#else
+        const int b = __builtin_ctzll(it);
+#endif
+        it &= it - 1;
+        if (S.h0[S.amin[j0 + b + 1]] == ~0ULL) mask &= ~(1ULL << b);
+    }
+    st.mask = mask;
+    st.f0 = (tid == 0 && T.first != 0 && S.h0[st.a_first] != ~0ULL) ? 1u : 0u;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(mask) + st.f0;
+#else
+    return (uint32_t)__builtin_popcountll(mask) + st.f0;
+#endif
+}
+
+template <int NT, int C1>
+SW_HD void fastD_write(int tid, const SketchParams& P, const Tile& T, const TileSmem& S, const FastState& st,
+                       unsigned long long slot)
+{
+    const uint32_t j0 = (uint32_t)tid * C1;
+    if (st.f0) write_minimizer(slot++, st.a_first, P, T, S);
+    uint64_t it = st.mask;
+    while (it) {
+#if defined(__CUDA_ARCH__)
+        const int b = __ffsll((long long)it) - 1;
+#else
+        const int b = __builtin_ctzll(it);
+#endif
+        it &= it - 1;
+        write_minimizer(slot++, S.amin[j0 + b + 1], P, T, S);
+    }
 }
 
 }  // namespace sw

@@ -25,7 +25,7 @@ def emul():
     L = C.CDLL(str(so))
     L.emul_sketch.restype = C.c_long
 
-    def run(seqs, k, w, nt, c1):
+    def run(seqs, k, w, nt, c1, force_generic=0):
         n = len(seqs)
         arrs = [np.frombuffer(s, dtype=np.uint8) for s in seqs]
         ptrs = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in arrs])
@@ -33,7 +33,7 @@ def emul():
         cap = sum(len(s) for s in seqs) + 16
         h1, pos, rec = np.empty(cap, np.uint64), np.empty(cap, np.uint32), np.empty(cap, np.uint32)
         nt_out = C.c_uint32()
-        m = L.emul_sketch(ptrs, C.c_void_p(lens.ctypes.data), C.c_size_t(n), C.c_uint32(k), C.c_uint32(w), nt, c1,
+        m = L.emul_sketch(ptrs, C.c_void_p(lens.ctypes.data), C.c_size_t(n), C.c_uint32(k), C.c_uint32(w), nt, c1, force_generic,
                           C.c_void_p(h1.ctypes.data), C.c_void_p(pos.ctypes.data), C.c_void_p(rec.ctypes.data),
                           C.c_size_t(cap), C.byref(nt_out))
         assert m >= 0, f"emulator failed ({m})"
@@ -63,7 +63,7 @@ def _seqs(rng):
         rand(12000), rand(40000, 0.002), b"ACGTTGCA" * 400]
 
 
-CONFIGS = [(8, 11), (32, 9), (4, 45), (128, 45), (256, 21), (256, 61)]
+CONFIGS = [(8, 11), (32, 9), (4, 45), (128, 45), (128, 33), (256, 21), (256, 61)]
 KW = [(21, 200), (21, 10), (17, 10), (7, 10), (5, 3), (4, 1), (6, 7), (3, 2), (31, 50), (21, 46), (21, 45), (21, 47),
       (9, 9), (11, 16), (15, 64), (12, 11), (33, 100), (127, 10)]
 
@@ -77,9 +77,11 @@ def test_emulated_kernel_matches_oracle(emul, cfg):
         if nt * c1 <= w + 1:
             continue
         seqs = _seqs(rng)
-        eh, ep, er, n_tiles = emul(seqs, k, w, nt, c1)
         oh, op, orr = _oracle_stream(seqs, k, w)
-        assert len(eh) == len(oh), (cfg, k, w, len(eh), len(oh))
-        assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (cfg, k, w)
+        # the specialised path (taken when w - 1 >= C1) and the generic path must both match
+        for force_generic in ((0, 1) if w - 1 >= c1 else (0,)):
+            eh, ep, er, n_tiles = emul(seqs, k, w, nt, c1, force_generic)
+            assert len(eh) == len(oh), (cfg, k, w, force_generic, len(eh), len(oh))
+            assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (cfg, k, w, force_generic)
         n_multi_tile += n_tiles > len(seqs)
     assert n_multi_tile > 0
