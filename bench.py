@@ -64,48 +64,60 @@ def spec_for(args, world: int) -> SynthSpec:
 
 # ---- clocks ----------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason sampling during the timed region (NVML, 5 ms period; the
+    nvidia-smi line of B200_PROFILING.md polls the same counters but cannot start fast enough
+    for a sub-second region)."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[int, int, int]] = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+        except Exception:
+            self._h = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self._h is None:
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thread.join()
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, _, r in self.samples))
+        sm = [s for s, _, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(m for _, m, _ in self.samples)) if sm else None,
+                "reasons": reasons, "samples": len(sm)}
 
 
 # ---- reference / CPU baseline ------------------------------------------------------------------
@@ -312,7 +324,8 @@ def main():
     e2e = {"value": n_bases_total / e2e_s / 1e9, "unit": "Gbp/s",
            "h2d_bytes_per_step": int(packed_bytes + 12 * n_records) * world, "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_s * 1e3,
-           "stage_ms": {n: float(np.mean([r[1][n] for r in e2e_runs])) for n in ("h2d_ms", "total_ms", "d2h_ms")},
+           "stage_ms": {n: float(np.mean([r[1][n] for r in e2e_runs])) for n in ("h2d_ms", "plan_ms", "sketch_kernel_ms", "reorder_ms", "sort_nodes_ms", "nodes_ms",
+                                  "edges_ms", "total_ms", "d2h_ms")},
            "what": "sw_build_from_batch: pinned 2-bit host batch -> H2D -> sketch+graph -> D2H host arrays"}
 
     cpu_baseline = None

@@ -79,6 +79,52 @@ void free_host(void* p, bool pinned)
 }
 
 namespace {
+struct Arena {
+    struct Slab { char* p; size_t bytes; };
+    std::vector<Slab> slabs;
+    size_t cur = 0, off = 0;
+    ~Arena() { for (auto& sl : slabs) cudaFree(sl.p); }
+    void* alloc(size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        while (cur < slabs.size() && off + bytes > slabs[cur].bytes) { ++cur; off = 0; }
+        if (cur == slabs.size()) {
+            Slab sl;
+            sl.bytes = std::max(bytes, (size_t)256 << 20);
+            SW_CUDA(cudaMalloc((void**)&sl.p, sl.bytes));
+            slabs.push_back(sl);
+            off = 0;
+        }
+        void* r = slabs[cur].p + off;
+        off += bytes;
+        return r;
+    }
+    void reset()
+    {
+        if (slabs.size() > 1) {  // grew during the last build: come back as one slab next time
+            size_t total = 0;
+            for (auto& sl : slabs) { total += sl.bytes; cudaFree(sl.p); }
+            slabs.clear();
+            Slab sl;
+            sl.bytes = total;
+            if (cudaMalloc((void**)&sl.p, sl.bytes) == cudaSuccess) slabs.push_back(sl);
+            else cudaGetLastError();
+        }
+        cur = 0;
+        off = 0;
+    }
+};
+Arena& tls_arena()
+{
+    static thread_local Arena a;
+    return a;
+}
+}  // namespace
+
+void* arena_alloc(size_t bytes) { return tls_arena().alloc(bytes); }
+void arena_reset() { tls_arena().reset(); }
+
+namespace {
 std::mutex g_pool_mu;
 std::vector<HostBuf> g_pool_free;
 size_t g_pool_cached = 0;
@@ -213,6 +259,7 @@ sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_time
     init_device_once();
     check_kw(k, w);
     cudaStream_t s = d.stream;
+    arena_reset();
     auto g = std::make_unique<sw_graph>();
     g->stream = s;
     g->record_offsets = d.meta.record_offsets;
@@ -480,13 +527,14 @@ int sw_get_penalty(const sw_kmer* kmers, size_t n_kmers, sw_node* nodes, size_t 
         if (n_nodes == 0) return;
         init_device_once();
         cudaStream_t s = lib_stream();
+        arena_reset();
         const std::vector<uint32_t> offs(record_offsets, record_offsets + n_offsets);
         const std::vector<uint32_t> ra = record_assembly_map(offs);
         const uint32_t n_records = offs.back();
-        DevBuf<sw_kmer> d_k(n_kmers, s);
-        DevBuf<sw_node> d_n(n_nodes, s);
-        DevBuf<uint32_t> d_ra(ra.size(), s);
-        DevBuf<uint8_t> d_t(n_assemblies, s);
+        DevBuf<sw_kmer> d_k(n_kmers, s, true);
+        DevBuf<sw_node> d_n(n_nodes, s, true);
+        DevBuf<uint32_t> d_ra(ra.size(), s, true);
+        DevBuf<uint8_t> d_t(n_assemblies, s, true);
         if (n_kmers) SW_CUDA(cudaMemcpyAsync(d_k.p, kmers, n_kmers * sizeof(sw_kmer), cudaMemcpyHostToDevice, s));
         SW_CUDA(cudaMemcpyAsync(d_n.p, nodes, n_nodes * sizeof(sw_node), cudaMemcpyHostToDevice, s));
         if (!ra.empty()) SW_CUDA(cudaMemcpyAsync(d_ra.p, ra.data(), ra.size() * 4, cudaMemcpyHostToDevice, s));
@@ -538,6 +586,7 @@ int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_ou
         init_device_once();
         check_kw(k, w);
         cudaStream_t s = d->stream;
+        arena_reset();
         DevPlan plan = make_plan(*d, k, w, s);
         SketchStream st;
         run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, 0u, s, st);

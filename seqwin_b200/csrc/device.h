@@ -21,33 +21,47 @@ namespace sw {
                                " at " __FILE__ ":" + std::to_string(__LINE__));            \
     } while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync pool; the pool keeps freed blocks cached).
+// Scratch arena: one grow-only device slab per host thread, bump-allocated and reset at the start
+// of every build, so the steady state performs no cudaMalloc / cudaFree at all.
+void* arena_alloc(size_t bytes);
+void arena_reset();
+
+// Device buffer.  Persistent buffers (graph outputs, uploaded batches) come from the stream-ordered
+// cudaMallocAsync pool; temporaries (tmp = true) come from the scratch arena and are never freed
+// individually.
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t stream = nullptr;
+    bool tmp = false;
     DevBuf() = default;
-    DevBuf(size_t count, cudaStream_t s) { alloc(count, s); }
+    DevBuf(size_t count, cudaStream_t s, bool temporary = false) { alloc(count, s, temporary); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream), tmp(o.tmp) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept
     {
-        if (this != &o) { release(); p = o.p; n = o.n; stream = o.stream; o.p = nullptr; o.n = 0; }
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; stream = o.stream; tmp = o.tmp;
+            o.p = nullptr; o.n = 0;
+        }
         return *this;
     }
     ~DevBuf() { release(); }
-    void alloc(size_t count, cudaStream_t s)
+    void alloc(size_t count, cudaStream_t s, bool temporary = false)
     {
         release();
         stream = s;
         n = count;
-        SW_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), s));
+        tmp = temporary;
+        if (tmp) p = static_cast<T*>(arena_alloc((count ? count : 1) * sizeof(T)));
+        else SW_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), s));
     }
     void release()
     {
-        if (p) cudaFreeAsync(p, stream);
+        if (p && !tmp) cudaFreeAsync(p, stream);
         p = nullptr;
         n = 0;
     }

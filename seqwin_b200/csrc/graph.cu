@@ -307,8 +307,8 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     timer.start();
     SortPairs sp;
     sp.n = M;
-    sp.keys.alloc(M, s);
-    sp.vals.alloc(M, s);
+    sp.keys.alloc(M, s, true);
+    sp.vals.alloc(M, s, true);
     SW_CUDA(cudaMemcpyAsync(sp.keys.p, st.keys.p, M * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     iota_kernel<<<(uint32_t)std::min<uint64_t>((M + 255) / 256, 65535), 256, 0, s>>>(sp.vals.p, M);
     SW_CUDA(cudaGetLastError());
@@ -318,7 +318,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     // -- nodes + kmers ---------------------------------------------------------------------------
     timer.start();
     const uint32_t nb = blocks_for(M);
-    DevBuf<unsigned long long> counts((size_t)nb + 1, s);
+    DevBuf<unsigned long long> counts((size_t)nb + 1, s, true);
     key_run_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
     scan_counts_kernel<<<1, 1024, 0, s>>>(counts.p, nb, counts.p + nb);
     SW_CUDA(cudaGetLastError());
@@ -328,7 +328,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     g.n_nodes = n_nodes;
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
-    DevBuf<uint32_t> rank_of_stream(M, s);
+    DevBuf<uint32_t> rank_of_stream(M, s, true);
     node_write_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
                                          rank_of_stream.p);
     SW_CUDA(cudaGetLastError());
@@ -354,7 +354,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
         SW_CUDA(cudaGetLastError());
         tm.launches += 1 + radix_sort_pairs(sp, 64, s);
         const uint32_t eb = blocks_for(n_raw);
-        DevBuf<unsigned long long> ecounts((size_t)eb + 1, s);
+        DevBuf<unsigned long long> ecounts((size_t)eb + 1, s, true);
         key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
         scan_counts_kernel<<<1, 1024, 0, s>>>(ecounts.p, eb, ecounts.p + eb);
         SW_CUDA(cudaGetLastError());
@@ -377,7 +377,7 @@ uint32_t run_penalty(const sw_kmer* d_kmers, uint64_t n_kmers, sw_node* d_nodes,
                      double inv_n, cudaStream_t s)
 {
     if (n_nodes == 0) return 0;
-    DevBuf<uint32_t> err(1, s);
+    DevBuf<uint32_t> err(1, s, true);
     SW_CUDA(cudaMemsetAsync(err.p, 0, sizeof(uint32_t), s));
     const uint32_t grid = (uint32_t)std::min<uint64_t>((n_nodes + 7) / 8, (uint64_t)sm_count() * 16);
     penalty_kernel<<<grid, 256, 0, s>>>(d_kmers, n_kmers, d_nodes, n_nodes, d_rec_asm, n_records, d_is_target,

@@ -156,7 +156,7 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
     const int n_passes = std::min(kMaxPasses, (end_bit + kRadixBits - 1) / kRadixBits);
     uint32_t launches = 0;
 
-    DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s);
+    DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s, true);
     SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
     const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
     radix_hist_kernel<<<hist_grid, 256, 0, s>>>(sp.keys.p, n, n_passes, ghist.p);
@@ -181,10 +181,10 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
     SW_CUDA(cudaMemcpyAsync(ghist.p, hist.data(), ghist.bytes(), cudaMemcpyHostToDevice, s));
 
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
-    DevBuf<unsigned long long> status(n_tiles * kRadix, s);
-    DevBuf<unsigned int> ticket(1, s);
-    if (!sp.keys_alt.p || sp.keys_alt.n < n) sp.keys_alt.alloc(n, s);
-    if (!sp.vals_alt.p || sp.vals_alt.n < n) sp.vals_alt.alloc(n, s);
+    DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);
+    DevBuf<unsigned int> ticket(1, s, true);
+    if (!sp.keys_alt.p || sp.keys_alt.n < n) sp.keys_alt.alloc(n, s, true);
+    if (!sp.vals_alt.p || sp.vals_alt.n < n) sp.vals_alt.alloc(n, s, true);
 
     for (int p = 0; p < n_passes; ++p) {
         if (skip[p]) continue;

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp_sums[NT / 32];
     __shared__ unsigned long long s_gbase;
+    __shared__ uint16_t s_active[NT];
 
     constexpr uint32_t TK = NT * C1;
     const TileSmem S = carve_tile_smem(smem_raw, TK, NT);
@@ -81,15 +82,22 @@ __global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__
 
         fastA_hash_prefix<NT, C1>(tid, P, T, S);
         __syncthreads();
-        FastState st;
-        fastB_windows<NT, C1>(tid, P, T, S, st);
+        fastB1_boundary<NT, C1>(tid, P, T, S);
         __syncthreads();
-        const uint32_t cnt = fastC_finish<NT, C1>(tid, P, T, S, st);
+        // compact the chunks whose windows do not all select the same k-mer
+        const bool act = fast_chunk_active<NT, C1>(tid, P, T, S);
+        uint32_t n_active;
+        const uint32_t a_slot = block_excl_scan<NT>(act ? 1u : 0u, s_warp_sums, &n_active);
+        if (act) s_active[a_slot] = (uint16_t)tid;
+        __syncthreads();
+        FastState st;
+        uint32_t cnt = 0;
+        if ((uint32_t)tid < n_active) cnt = fastB2_windows<NT, C1>(s_active[tid], P, T, S, st);
         uint32_t total;
         const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
         if (tid == 0) s_gbase = claim_slots(P, tile_id, total);
         __syncthreads();
-        if (cnt) fastD_write<NT, C1>(tid, P, T, S, st, s_gbase + excl);
+        if (cnt) fastD_write<NT, C1>(P, T, S, st, s_gbase + excl);
     }
 }
 
@@ -282,7 +290,7 @@ DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
     RecordRuns rr{d.rec_len.p, d.rec_inv_off.p, d.inv_start.p, d.inv_len.p};
     // [0,R) tiles per record, [R] total tiles, [R+1, 2R+1) pieces per record, [2R+1] total pieces,
     // [2R+2] valid k-mers, [2R+3] windows
-    DevBuf<unsigned long long> buf((size_t)2 * R + 4, s);
+    DevBuf<unsigned long long> buf((size_t)2 * R + 4, s, true);
     SW_CUDA(cudaMemsetAsync(buf.p + 2 * (size_t)R + 2, 0, 2 * sizeof(unsigned long long), s));
     const uint32_t grid = (R + 127) / 128;
     plan_count_kernel<<<grid, 128, 0, s>>>(rr, R, k, w, tw, buf.p, buf.p + R + 1, buf.p + 2 * (size_t)R + 2);
@@ -298,8 +306,8 @@ DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
     dp.n_tiles = (uint32_t)h[0];
     dp.n_kmers = h[2];
     dp.n_windows = h[3];
-    dp.tiles.alloc(h[0], s);
-    dp.pieces.alloc(h[1], s);
+    dp.tiles.alloc(h[0], s, true);
+    dp.pieces.alloc(h[1], s, true);
     if (dp.n_tiles)
         plan_fill_kernel<<<grid, 128, 0, s>>>(rr, R, k, w, tw, buf.p, buf.p + R + 1, h[0], dp.tiles.p, dp.pieces.p);
     SW_CUDA(cudaGetLastError());
@@ -312,8 +320,8 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     out.n = 0;
     out.launches = 0;
     if (plan.n_tiles == 0) {
-        out.keys.alloc(0, s);
-        out.vals.alloc(0, s);
+        out.keys.alloc(0, s, true);
+        out.vals.alloc(0, s, true);
         return;
     }
     const KernelConfig& kc = kConfigs[plan.config];
@@ -328,8 +336,8 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     const uint32_t grid = (uint32_t)std::min<uint64_t>(plan.n_tiles, (uint64_t)sm_count() * ctas_per_sm);
 
     // [0, n_tiles): per-tile counts (scanned in place into ordered offsets); then the slots
-    DevBuf<unsigned long long> tile_info((size_t)plan.n_tiles * 2, s);
-    DevBuf<unsigned long long> counters(3, s);  // [0] cursor, [1] ticket (as u32), [2] scan total
+    DevBuf<unsigned long long> tile_info((size_t)plan.n_tiles * 2, s, true);
+    DevBuf<unsigned long long> counters(3, s, true);  // [0] cursor, [1] ticket (as u32), [2] scan total
 
     // expected density 2/(w+1); leave 50 % headroom and re-run with the exact size on overflow
     uint64_t capacity = (uint64_t)((double)plan.n_kmers * 3.0 / ((double)w + 1.0)) + 4096;
@@ -339,8 +347,8 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
     for (int attempt = 0;; ++attempt) {
-        ukeys.alloc(capacity, s);
-        uvals.alloc(capacity, s);
+        ukeys.alloc(capacity, s, true);
+        uvals.alloc(capacity, s, true);
         SW_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
         SketchParams P;
         P.words = d_words;
@@ -373,8 +381,8 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         capacity = total;  // low-complexity input: more minimizers than the density estimate
     }
     out.n = total;
-    out.keys.alloc(total, s);
-    out.vals.alloc(total, s);
+    out.keys.alloc(total, s, true);
+    out.vals.alloc(total, s, true);
     cudaEventElapsedTime(&out.kernel_ms, ev[0], ev[1]);
     if (total == 0) {
         for (auto& e : ev) cudaEventDestroy(e);

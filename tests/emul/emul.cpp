@@ -66,15 +66,17 @@ static void emulate(const sw_batch& b, uint32_t k, uint32_t w, std::vector<uint6
         uint32_t total = 0;
         if (fast) {
             std::vector<FastState> st(NT);
-            std::vector<uint32_t> cnt(NT);
+            std::vector<uint32_t> cnt(NT, 0), active;
             for (int tid = 0; tid < NT; ++tid) fastA_hash_prefix<NT, C1>(tid, P, T, S);
-            for (int tid = 0; tid < NT; ++tid) fastB_windows<NT, C1>(tid, P, T, S, st[tid]);
-            for (int tid = 0; tid < NT; ++tid) cnt[tid] = fastC_finish<NT, C1>(tid, P, T, S, st[tid]);
+            for (int tid = 0; tid < NT; ++tid) fastB1_boundary<NT, C1>(tid, P, T, S);
+            for (int tid = 0; tid < NT; ++tid)
+                if (fast_chunk_active<NT, C1>(tid, P, T, S)) active.push_back((uint32_t)tid);
+            for (size_t i = 0; i < active.size(); ++i) cnt[i] = fastB2_windows<NT, C1>(active[i], P, T, S, st[i]);
             for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += cnt[tid]; }
             tile_count[t] = total;
             tile_slot[t] = cursor;
             for (int tid = 0; tid < NT; ++tid)
-                if (cnt[tid]) fastD_write<NT, C1>(tid, P, T, S, st[tid], cursor + excl[tid]);
+                if (cnt[tid]) fastD_write<NT, C1>(P, T, S, st[tid], cursor + excl[tid]);
         } else {
             for (int tid = 0; tid < NT; ++tid) phase1_hash<NT, C1>(tid, P, T, S);
             if (P.c2) {
