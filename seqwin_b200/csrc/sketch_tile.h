@@ -361,20 +361,21 @@ SW_HD void phase3c_write(uint32_t i, unsigned long long gbase, const SketchParam
 
 // ---- fast path: w - 1 >= C1, logical chunk == thread chunk, everything unrolled -----------------
 //
-//  A  hash own chunk + prefix argmin (fused when the tile is one run), chunk minimum
+//  A   hash own chunk + prefix argmin (fused when the tile is one run), chunk minimum
 //  --barrier--
-//  B  chunk minima of the whole chunks a window spans (two variants), suffix pass right-to-left,
-//     A[a] for own windows; window a+1 emits iff A[a+1] != A[a] -> mask bit, A kept in amin
-//  --barrier--
-//  C  the flag of the first window of the NEXT chunk (needs that thread's A), window 0, the
-//     2^64-1 exclusion; returns the number of minimizers this thread emits
+//  B1  A of the FIRST window of every chunk (whole chunk + whole chunks + one prefix lookup).
+//      A[] is monotone, so a chunk whose first window and the next chunk's first window select the
+//      same k-mer emits nothing: at density 2/(w+1) most chunks are skipped.
+//  --barrier + compaction of the remaining ("active") chunks--
+//  B2  one thread per active chunk: suffix pass right-to-left, A[a] for every window of the chunk;
+//      window a+1 emits iff A[a+1] != A[a]; the 2^64-1 exclusion; count
 //  --block scan + one atomicAdd on the global cursor--
-//  D  write own minimizers
+//  D   write own minimizers
 struct FastState {
-    uint64_t mask;     // bit n: window j0 + n + 1 emits
-    uint32_t a_top;    // A of the thread's last window (n = C1-1)
-    uint32_t a_first;  // A of the thread's first window
-    uint32_t f0;       // thread 0 only: window 0 emits
+    uint64_t mask;     // bit n: window c*C1 + n + 1 emits
+    uint32_t chunk;    // chunk this thread evaluated in B2
+    uint32_t a_first;  // A of the chunk's first window
+    uint32_t f0;       // chunk 0 only: window 0 emits
 };
 
 template <int NT, int C1>
@@ -405,31 +406,62 @@ SW_HD void fastA_hash_prefix(int tid, const SketchParams& P, const Tile& T, cons
     S.cm_i[tid] = (uint16_t)bi;
 }
 
+// B1: A of window tid*C1 -> first_a[tid]
 template <int NT, int C1>
-SW_HD void fastB_windows(int tid, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
+SW_HD void fastB1_boundary(int tid, const SketchParams& P, const Tile& T, const TileSmem& S)
 {
     const uint32_t w = P.w;
     const uint32_t n_eval = T.n_kmers - w + 1;
     const uint32_t j0 = (uint32_t)tid * C1;
-    st.mask = 0;
-    st.a_top = st.a_first = 0xFFFFFFFFu;
-    st.f0 = 0;
     if (j0 >= n_eval) return;
-    const uint32_t q = (w - 1) / C1, r = (w - 1) % C1;  // window end = chunk tid+q (+1), offset (n+r) % C1
-    // whole chunks tid+1 .. tid+q-1 (windows ending in chunk tid+q) and .. tid+q (ending in tid+q+1).
+    const uint32_t q = (w - 1) / C1;
+    // the window covers chunk tid entirely (w - 1 >= C1), then chunks tid+1 .. tid+q-1, then a
+    // prefix of chunk tid+q; everything to the right wins ties
+    uint64_t rh = S.cm_h[tid];
+    uint32_t ri = S.cm_i[tid];
+    for (uint32_t cc = (uint32_t)tid + 1; cc < (uint32_t)tid + q; ++cc) {
+        const uint64_t h = S.cm_h[cc];
+        if (h <= rh) { rh = h; ri = S.cm_i[cc]; }
+    }
+    const uint32_t pe = S.pidx[j0 + w - 1];
+    if (S.h0[pe] <= rh) ri = pe;
+    S.first_a[tid] = (uint16_t)ri;
+}
+
+// does chunk c need a full evaluation?
+template <int NT, int C1>
+SW_HD bool fast_chunk_active(int c, const SketchParams& P, const Tile& T, const TileSmem& S)
+{
+    const uint32_t n_eval = T.n_kmers - P.w + 1;
+    const uint32_t j0 = (uint32_t)c * C1;
+    if (j0 >= n_eval) return false;
+    if (j0 + C1 >= n_eval) return true;             // last chunk: no next boundary to compare with
+    if (c == 0 && T.first != 0) return true;         // window 0 of the record always emits
+    return S.first_a[c] != S.first_a[c + 1];
+}
+
+// B2: full evaluation of chunk c; returns the number of minimizers its windows emit
+template <int NT, int C1>
+SW_HD uint32_t fastB2_windows(uint32_t c, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
+{
+    const uint32_t w = P.w;
+    const uint32_t n_eval = T.n_kmers - w + 1;
+    const uint32_t j0 = c * C1;
+    const uint32_t q = (w - 1) / C1, r = (w - 1) % C1;  // window end = chunk c+q (+1), offset (n+r) % C1
+    // whole chunks c+1 .. c+q-1 (windows ending in chunk c+q) and .. c+q (ending in c+q+1).
     // Chunks past the tile only matter to windows that are not evaluated.
     bool lo_valid = false;
     uint64_t m_lo_h = 0;
     uint32_t m_lo_i = 0;
-    for (uint32_t cc = (uint32_t)tid + 1; cc < (uint32_t)tid + q && cc < NT; ++cc) {
+    for (uint32_t cc = c + 1; cc < c + q && cc < NT; ++cc) {
         const uint64_t h = S.cm_h[cc];
         if (!lo_valid || h <= m_lo_h) { m_lo_h = h; m_lo_i = S.cm_i[cc]; lo_valid = true; }
     }
     uint64_t m_hi_h = m_lo_h;
     uint32_t m_hi_i = m_lo_i;
-    if ((uint32_t)tid + q < NT) {
-        const uint64_t h = S.cm_h[tid + q];
-        if (!lo_valid || h <= m_lo_h) { m_hi_h = h; m_hi_i = S.cm_i[tid + q]; }
+    if (c + q < NT) {
+        const uint64_t h = S.cm_h[c + q];
+        if (!lo_valid || h <= m_lo_h) { m_hi_h = h; m_hi_i = S.cm_i[c + q]; }
     }
     uint64_t sh = 0, mask = 0;
     uint32_t si = 0, prev_a = 0xFFFFFFFFu, a_top = 0xFFFFFFFFu;
@@ -458,23 +490,11 @@ SW_HD void fastB_windows(int tid, const SketchParams& P, const Tile& T, const Ti
             prev_a = ri;
         }
     }
-    st.mask = mask;
-    st.a_top = a_top;
-    st.a_first = prev_a;
-    S.first_a[tid] = (uint16_t)prev_a;
-}
-
-template <int NT, int C1>
-SW_HD uint32_t fastC_finish(int tid, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
-{
-    const uint32_t n_eval = T.n_kmers - P.w + 1;
-    const uint32_t j0 = (uint32_t)tid * C1;
-    if (j0 >= n_eval) return 0;
-    uint64_t mask = st.mask;
-    const uint32_t a_b = j0 + C1;  // first window of the next chunk
+    // first window of the next chunk (its A is known from B1)
+    const uint32_t a_b = j0 + C1;
     if (a_b < n_eval) {
-        const uint32_t nxt = S.first_a[tid + 1];
-        if (nxt != st.a_top) {
+        const uint32_t nxt = S.first_a[c + 1];
+        if (nxt != a_top) {
             mask |= 1ULL << (C1 - 1);
             S.amin[a_b] = (uint16_t)nxt;
         }
@@ -491,7 +511,9 @@ SW_HD uint32_t fastC_finish(int tid, const SketchParams& P, const Tile& T, const
         if (S.h0[S.amin[j0 + b + 1]] == ~0ULL) mask &= ~(1ULL << b);
     }
     st.mask = mask;
-    st.f0 = (tid == 0 && T.first != 0 && S.h0[st.a_first] != ~0ULL) ? 1u : 0u;
+    st.chunk = c;
+    st.a_first = prev_a;
+    st.f0 = (c == 0 && T.first != 0 && S.h0[prev_a] != ~0ULL) ? 1u : 0u;
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__popcll(mask) + st.f0;
 #else
@@ -500,10 +522,10 @@ SW_HD uint32_t fastC_finish(int tid, const SketchParams& P, const Tile& T, const
 }
 
 template <int NT, int C1>
-SW_HD void fastD_write(int tid, const SketchParams& P, const Tile& T, const TileSmem& S, const FastState& st,
+SW_HD void fastD_write(const SketchParams& P, const Tile& T, const TileSmem& S, const FastState& st,
                        unsigned long long slot)
 {
-    const uint32_t j0 = (uint32_t)tid * C1;
+    const uint32_t j0 = st.chunk * C1;
     if (st.f0) write_minimizer(slot++, st.a_first, P, T, S);
     uint64_t it = st.mask;
     while (it) {
