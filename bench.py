@@ -243,7 +243,7 @@ def main():
 
     if world > 1:
         from seqwin_b200 import dist as swdist
-        result = swdist.bench_loop(L, batch, spec, rank, world, k, w, args.steps, args.warmup)
+        result = swdist.bench_loop(L, batch, spec, rank, world, k, w, args.steps, args.warmup, ClockSampler)
     else:
         dev = C.c_void_p()
         _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
@@ -299,12 +299,12 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     # dominant kernel = sketch: reads the 2-bit input once, writes 16 B per minimizer
-    sketch_bytes = n_bases_local / 4 + 16 * M
+    sketch_bytes = n_bases_local / 4 + 16 * s0.get("n_kmers_local", M)
     ach = sketch_bytes / (sketch_ms * 1e-3) / 1e9
     clocks = result["clocks"]
     sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     int_peak = 148 * 128 * sm_mhz * 1e6  # lane-ops/s at the clock seen under load
-    int_alg = 45.0 * n_bases_local + 12.0 * M
+    int_alg = 45.0 * n_bases_local + 12.0 * s0.get("n_kmers_local", M)
     roofline = {"bound": "hbm", "kernel": "sketch_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sketch_bytes, "kernel_ms": sketch_ms,

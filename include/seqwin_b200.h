@@ -114,6 +114,27 @@ int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** ou
 int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_out,
                   uint32_t* pos_out, uint32_t* record_out, size_t capacity, size_t* n_out);
 
+/* ---- multi-GPU building blocks (one process per GPU; seqwin_b200/dist.py drives them) --------- */
+
+/* Run every later call of this host thread on `stream` (a cudaStream_t, e.g. torch's current
+ * stream) instead of the library's own stream; NULL restores the default. */
+int sw_set_stream(void* stream);
+/* sw_dev_build with the shard's global record base: record_idx = rec_base + local record index. */
+int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_graph** out,
+                    sw_stage_times* t);
+/* Device pointers of a device-resident graph (valid until sw_graph_free). */
+int sw_graph_device_ptrs(sw_graph* g, void** kmers, void** nodes, void** edges);
+/* Cut the sorted node / k-mer / edge arrays at the n_parts+1 hash boundaries i * 2^64 / n_parts
+ * (edges by `first`); each output array has n_parts + 1 entries. */
+int sw_graph_split(sw_graph* g, uint32_t n_parts, uint64_t* node_split, uint64_t* kmer_split,
+                   uint64_t* edge_split);
+/* Merge the slices a hash-range owner received from n_src ranks (device pointers, concatenated in
+ * rank order; kmer_base[i] = first k-mer index of rank i's slice in rank i's own array). Mirrors
+ * merge_thread_graphs (cpp/src/seqwin/build_internals.cpp:295-392). */
+int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const void* recv_kmers,
+                  const uint64_t* kmer_counts, const uint64_t* kmer_base, const void* recv_edges,
+                  const uint64_t* edge_counts, uint32_t n_src, sw_graph** out, uint32_t* launches);
+
 /* Device properties the host side sizes grids with. */
 int sw_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
 

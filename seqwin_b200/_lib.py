@@ -44,6 +44,11 @@ PROTOTYPES = {
     "sw_dev_build": (_I, [_P, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_build_from_batch": (_I, [_P, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_dev_sketch": (_I, [_P, _U32, _U32, _P, _P, _P, _SZ, C.POINTER(_SZ)]),
+    "sw_set_stream": (_I, [_P]),
+    "sw_dev_build_ex": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_graph_device_ptrs": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "sw_graph_split": (_I, [_P, _U32, _P, _P, _P]),
+    "sw_dist_merge": (_I, [_P, _P, _P, _P, _P, _P, _P, _U32, C.POINTER(_P), C.POINTER(_U32)]),
     "sw_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ)]),
 }
 

@@ -176,8 +176,12 @@ struct StreamGuard {
     ~StreamGuard() { if (s) cudaStreamDestroy(s); }
 };
 
+thread_local cudaStream_t g_stream_override = nullptr;
+thread_local bool g_have_override = false;
+
 cudaStream_t lib_stream()
 {
+    if (g_have_override) return g_stream_override;
     static thread_local std::unique_ptr<StreamGuard> g;
     if (!g) g.reset(new StreamGuard());
     return g->s;
@@ -254,7 +258,7 @@ sw_dev_batch* dev_upload(const sw_batch& b)
     return d.release();
 }
 
-sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t)
+sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t, uint32_t rec_base = 0)
 {
     init_device_once();
     check_kw(k, w);
@@ -274,10 +278,10 @@ sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_time
     DevPlan plan = make_plan(d, k, w, s);
     const float plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     SketchStream st;
-    run_sketch(d.words.p, d.rec_word_off.p, plan, k, w, 0u, s, st);
+    run_sketch(d.words.p, d.rec_word_off.p, plan, k, w, rec_base, s, st);
     cudaEventRecord(e1, s);
     GraphTimes gt;
-    build_graph(st, d.rec_asm.p, s, g->dev, &gt);
+    build_graph(st, d.rec_asm.p, rec_base, s, g->dev, &gt);
     cudaEventRecord(e2, s);
     SW_CUDA(cudaStreamSynchronize(s));
     g->on_device = true;
@@ -402,6 +406,66 @@ void sw_dev_batch_free(sw_dev_batch* d)
 int sw_dev_build(const sw_dev_batch* d, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)
 {
     return guarded([&] { *out = dev_build(*d, k, w, t); });
+}
+
+int sw_set_stream(void* stream)
+{
+    g_stream_override = static_cast<cudaStream_t>(stream);
+    g_have_override = stream != nullptr;
+    return SW_OK;
+}
+
+int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_graph** out,
+                    sw_stage_times* t)
+{
+    return guarded([&] { *out = dev_build(*d, k, w, t, rec_base); });
+}
+
+int sw_graph_device_ptrs(sw_graph* g, void** kmers, void** nodes, void** edges)
+{
+    return guarded([&] {
+        if (!g->on_device) fail_runtime("graph is not device resident");
+        if (kmers) *kmers = g->dev.kmers.p;
+        if (nodes) *nodes = g->dev.nodes.p;
+        if (edges) *edges = g->dev.edges.p;
+    });
+}
+
+int sw_graph_split(sw_graph* g, uint32_t n_parts, uint64_t* node_split, uint64_t* kmer_split, uint64_t* edge_split)
+{
+    return guarded([&] {
+        if (!g->on_device) fail_runtime("graph is not device resident");
+        if (n_parts == 0) fail_value("n_parts must be >= 1");
+        std::vector<unsigned long long> h(3 * (size_t)(n_parts + 1));
+        graph_split(g->dev, n_parts, h.data(), g->stream);
+        for (uint32_t i = 0; i <= n_parts; ++i) {
+            node_split[i] = h[i];
+            kmer_split[i] = h[(n_parts + 1) + i];
+            edge_split[i] = h[2 * (size_t)(n_parts + 1) + i];
+        }
+    });
+}
+
+int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const void* recv_kmers,
+                  const uint64_t* kmer_counts, const uint64_t* kmer_base, const void* recv_edges,
+                  const uint64_t* edge_counts, uint32_t n_src, sw_graph** out, uint32_t* launches)
+{
+    return guarded([&] {
+        init_device_once();
+        cudaStream_t s = lib_stream();
+        arena_reset();
+        auto g = std::make_unique<sw_graph>();
+        g->stream = s;
+        dist_merge(static_cast<const sw_node*>(recv_nodes), node_counts, static_cast<const sw_kmer*>(recv_kmers),
+                   kmer_counts, kmer_base, static_cast<const sw_edge*>(recv_edges), edge_counts, n_src, s, g->dev,
+                   launches);
+        g->on_device = true;
+        g->n_kmers = g->dev.n_kmers;
+        g->n_nodes = g->dev.n_nodes;
+        g->n_edges = g->dev.n_edges;
+        g->record_offsets.assign(1, 0);
+        *out = g.release();
+    });
 }
 
 int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)

@@ -127,8 +127,14 @@ struct GraphTimes {
     uint32_t launches = 0;
 };
 // d_rec_asm: assembly index of every global record id used in the stream.
-void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, DevGraph& g,
+void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                  GraphTimes* times);
+
+// ---- multi-GPU merge (dist.cu) -------------------------------------------------------------------
+void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out /* 3*(P+1) */, cudaStream_t s);
+void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
+                const uint64_t* kmer_counts, const uint64_t* kmer_base, const sw_edge* recv_edges,
+                const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out, uint32_t* launches);
 
 // ---- penalty ----------------------------------------------------------------------------------
 // Fills n_tar / n_neg / penalty of device-resident nodes; returns an error bit mask

@@ -1,0 +1,273 @@
+// dist.cu -- owner-side merge of per-GPU shard graphs (multi-GPU build).
+//
+// Every rank builds the graph of its own assemblies with the single-GPU kernels.  Because an
+// assembly lives on exactly one rank, a node's k-mer list is the concatenation of the per-rank lists
+// in rank order and an edge's weight is the sum of the per-rank weights -- the same rule the reference
+// uses to merge its per-thread graphs (cpp/src/seqwin/build_internals.cpp:159-291, merge_nodes /
+// merge_kmers / merge_edges).  Ranks exchange hash-range slices of their sorted node / k-mer / edge
+// arrays (NCCL all-to-all, seqwin_b200/dist.py); this file merges what a range owner received:
+//   nodes   sort the (much shorter) node list by hash, run-length merge, segment-copy the k-mers
+//   edges   stable two-key LSD sort by (first, second), run-length merge, sum the weights
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "device.h"
+#include "scan.cuh"
+
+namespace sw {
+
+namespace {
+
+constexpr int kNT = 256;
+
+__global__ void iota32_kernel(uint32_t* v, uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
+}
+
+// concatenated received nodes -> sort key (hash) and absolute source offset of the node's k-mers
+__global__ void node_prepare_kernel(const sw_node* __restrict__ nodes, uint64_t n, const unsigned long long* __restrict__ seg,
+                                    uint32_t n_src, uint64_t* __restrict__ key, unsigned long long* __restrict__ abs_start)
+{
+    // seg layout: [0, n_src] node offsets, then n_src received-k-mer offsets, then n_src sender k-mer bases
+    const unsigned long long* node_off = seg;
+    const unsigned long long* kmer_off = seg + n_src + 1;
+    const unsigned long long* kmer_base = kmer_off + n_src;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t s = 0;
+        while (s + 1 < n_src && node_off[s + 1] <= i) ++s;
+        key[i] = nodes[i].hash;
+        abs_start[i] = kmer_off[s] + (nodes[i].start - kmer_base[s]);
+    }
+}
+
+// sorted order j -> (run start flag, k-mer count) as one packed u64: count in the low 40 bits,
+// flag in bit 40, so that ONE exclusive scan yields both the output k-mer offset and the node rank
+__global__ void node_pack_kernel(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
+                                 const sw_node* __restrict__ nodes, uint64_t n, unsigned long long* __restrict__ packed)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const sw_node nd = nodes[sidx[j]];
+        const unsigned long long flag = (j == 0 || skey[j] != skey[j - 1]) ? 1ULL : 0ULL;
+        packed[j] = (nd.stop - nd.start) | (flag << 40);
+    }
+}
+
+// one warp per received node segment: copy its k-mers to the merged position, fill merged nodes
+__global__ void node_merge_kernel(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
+                                  const sw_node* __restrict__ nodes, const unsigned long long* __restrict__ abs_start,
+                                  const unsigned long long* __restrict__ scanned, uint64_t n, unsigned long long total_packed,
+                                  const sw_kmer* __restrict__ recv_kmers, sw_kmer* __restrict__ out_kmers,
+                                  sw_node* __restrict__ out_nodes)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long mask40 = (1ULL << 40) - 1;
+    for (uint64_t j = warp; j < n; j += n_warps) {
+        const uint32_t i = sidx[j];
+        const sw_node nd = nodes[i];
+        const unsigned long long cnt = nd.stop - nd.start;
+        const unsigned long long ex = scanned[j];
+        const unsigned long long off = ex & mask40;
+        const bool flag = (j == 0) || skey[j] != skey[j - 1];
+        // node rank = (#flags up to and including j) - 1
+        const unsigned long long rank = (ex >> 40) + (flag ? 1 : 0) - 1;
+        const unsigned long long src = abs_start[i];
+        for (unsigned long long t = lane; t < cnt; t += 32) out_kmers[off + t] = recv_kmers[src + t];
+        if (lane == 0) {
+            if (flag) {
+                sw_node* o = out_nodes + rank;
+                o->hash = nd.hash;
+                o->start = off;
+                o->n_tar = 0;
+                o->n_neg = 0;
+                o->penalty = 0.0;
+                if (rank > 0) out_nodes[rank - 1].stop = off;
+            }
+            if (j == n - 1) out_nodes[rank].stop = total_packed & mask40;
+        }
+    }
+}
+
+__global__ void edge_key_kernel(const sw_edge* __restrict__ edges, const uint32_t* __restrict__ idx, uint64_t n,
+                                int which, uint64_t* __restrict__ key)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const sw_edge& e = edges[idx ? idx[j] : j];
+        key[j] = which ? e.first : e.second;
+    }
+}
+
+__global__ void edge_flag_kernel(const sw_edge* __restrict__ edges, const uint32_t* __restrict__ sidx, uint64_t n,
+                                 unsigned long long* __restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        bool f = j == 0;
+        if (!f) {
+            const sw_edge& a = edges[sidx[j]];
+            const sw_edge& b = edges[sidx[j - 1]];
+            f = a.first != b.first || a.second != b.second;
+        }
+        flags[j] = f ? 1ULL : 0ULL;
+    }
+}
+
+__global__ void edge_merge_kernel(const sw_edge* __restrict__ edges, const uint32_t* __restrict__ sidx,
+                                  const unsigned long long* __restrict__ scanned, uint64_t n, sw_edge* __restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const sw_edge e = edges[sidx[j]];
+        bool f = j == 0;
+        if (!f) {
+            const sw_edge& b = edges[sidx[j - 1]];
+            f = e.first != b.first || e.second != b.second;
+        }
+        const unsigned long long rank = scanned[j] + (f ? 1 : 0) - 1;
+        if (f) {
+            out[rank].first = e.first;
+            out[rank].second = e.second;
+        }
+        atomicAdd(reinterpret_cast<unsigned long long*>(&out[rank].weight), (unsigned long long)e.weight);
+    }
+}
+
+// lower_bound of P+1 hash boundaries in the sorted node / edge arrays
+__global__ void split_kernel(const sw_node* __restrict__ nodes, uint64_t n_nodes, uint64_t n_kmers,
+                             const sw_edge* __restrict__ edges, uint64_t n_edges, uint32_t P,
+                             unsigned long long* __restrict__ out /* 3*(P+1) */)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > P) return;
+    // boundary i = floor(i * 2^64 / P); i == P means "past the end"
+    uint64_t lo_n = 0, hi_n = n_nodes, lo_e = 0, hi_e = n_edges;
+    if (i == P) {
+        lo_n = n_nodes;
+        lo_e = n_edges;
+    } else if (i > 0) {
+        const unsigned __int128 full = (unsigned __int128)1 << 64;
+        const uint64_t b = (uint64_t)((full * i) / P);
+        while (lo_n < hi_n) {
+            const uint64_t m = (lo_n + hi_n) >> 1;
+            if (nodes[m].hash < b) lo_n = m + 1; else hi_n = m;
+        }
+        while (lo_e < hi_e) {
+            const uint64_t m = (lo_e + hi_e) >> 1;
+            if (edges[m].first < b) lo_e = m + 1; else hi_e = m;
+        }
+    }
+    out[i] = lo_n;
+    out[(P + 1) + i] = lo_n < n_nodes ? nodes[lo_n].start : n_kmers;
+    out[2 * (P + 1) + i] = lo_e;
+}
+
+uint32_t grid_for(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>((n + kNT - 1) / kNT, 1), 148 * 16); }
+
+}  // namespace
+
+void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out, cudaStream_t s)
+{
+    DevBuf<unsigned long long> d(3 * (size_t)(P + 1), s, true);
+    split_kernel<<<(P + 1 + 63) / 64, 64, 0, s>>>(g.nodes.p, g.n_nodes, g.n_kmers, g.edges.p, g.n_edges, P, d.p);
+    SW_CUDA(cudaGetLastError());
+    SW_CUDA(cudaMemcpyAsync(host_out, d.p, d.bytes(), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+}
+
+void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
+                const uint64_t* kmer_counts, const uint64_t* kmer_base, const sw_edge* recv_edges,
+                const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out, uint32_t* launches)
+{
+    uint64_t Nn = 0, Nk = 0, Ne = 0;
+    std::vector<unsigned long long> seg(3 * (size_t)n_src + 1);
+    for (uint32_t i = 0; i < n_src; ++i) {
+        seg[i] = Nn;
+        seg[n_src + 1 + i] = Nk;
+        seg[2 * n_src + 1 + i] = kmer_base[i];
+        Nn += node_counts[i];
+        Nk += kmer_counts[i];
+        Ne += edge_counts[i];
+    }
+    seg[n_src] = Nn;
+    if (Nn > 0xFFFFFFFFull || Ne > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 nodes / edges in one hash range");
+    if (Nk >= (1ULL << 40)) fail_runtime("more than 2^40 k-mers in one hash range");
+    uint32_t nl = 0;
+    out.n_kmers = Nk;
+    out.n_nodes = 0;
+    out.n_edges = 0;
+    out.kmers.alloc(Nk, s);
+
+    // ---- nodes + kmers -------------------------------------------------------------------------
+    if (Nn == 0) {
+        out.nodes.alloc(0, s);
+    } else {
+        DevBuf<unsigned long long> d_seg(seg.size(), s, true);
+        SW_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        SortPairs sp;
+        sp.n = Nn;
+        sp.keys.alloc(Nn, s, true);
+        sp.vals.alloc(Nn, s, true);
+        DevBuf<unsigned long long> abs_start(Nn, s, true);
+        node_prepare_kernel<<<grid_for(Nn), kNT, 0, s>>>(recv_nodes, Nn, d_seg.p, n_src, sp.keys.p, abs_start.p);
+        iota32_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.vals.p, Nn);
+        SW_CUDA(cudaGetLastError());
+        nl += 2 + radix_sort_pairs(sp, 64, s);
+        DevBuf<unsigned long long> packed(Nn + 1, s, true);
+        node_pack_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, Nn, packed.p);
+        exclusive_scan_u64(packed.p, Nn, packed.p + Nn, s);
+        SW_CUDA(cudaGetLastError());
+        unsigned long long total = 0;
+        SW_CUDA(cudaMemcpyAsync(&total, packed.p + Nn, sizeof(total), cudaMemcpyDeviceToHost, s));
+        SW_CUDA(cudaStreamSynchronize(s));
+        out.n_nodes = total >> 40;
+        out.nodes.alloc(out.n_nodes, s);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((Nn + 7) / 8, 148 * 16);
+        node_merge_kernel<<<grid, 256, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, abs_start.p, packed.p, Nn, total,
+                                               recv_kmers, out.kmers.p, out.nodes.p);
+        SW_CUDA(cudaGetLastError());
+        nl += 3;
+    }
+
+    // ---- edges ---------------------------------------------------------------------------------
+    if (Ne == 0) {
+        out.edges.alloc(0, s);
+    } else {
+        SortPairs sp;
+        sp.n = Ne;
+        sp.keys.alloc(Ne, s, true);
+        sp.vals.alloc(Ne, s, true);
+        // stable LSD over the 128-bit key: by `second`, then by `first`
+        edge_key_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, nullptr, Ne, 0, sp.keys.p);
+        iota32_kernel<<<grid_for(Ne), kNT, 0, s>>>(sp.vals.p, Ne);
+        SW_CUDA(cudaGetLastError());
+        nl += 2 + radix_sort_pairs(sp, 64, s);
+        edge_key_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, 1, sp.keys.p);
+        SW_CUDA(cudaGetLastError());
+        nl += 1 + radix_sort_pairs(sp, 64, s);
+        DevBuf<unsigned long long> flags(Ne + 1, s, true);
+        edge_flag_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, flags.p);
+        exclusive_scan_u64(flags.p, Ne, flags.p + Ne, s);
+        SW_CUDA(cudaGetLastError());
+        unsigned long long n_edges = 0;
+        SW_CUDA(cudaMemcpyAsync(&n_edges, flags.p + Ne, sizeof(n_edges), cudaMemcpyDeviceToHost, s));
+        SW_CUDA(cudaStreamSynchronize(s));
+        out.n_edges = n_edges;
+        out.edges.alloc(n_edges, s);
+        SW_CUDA(cudaMemsetAsync(out.edges.p, 0, n_edges * sizeof(sw_edge), s));
+        edge_merge_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, flags.p, Ne, out.edges.p);
+        SW_CUDA(cudaGetLastError());
+        nl += 3;
+    }
+    SW_CUDA(cudaStreamSynchronize(s));
+    if (launches) *launches = nl;
+}
+
+}  // namespace sw

@@ -286,7 +286,8 @@ uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlockItems - 1) / kBlo
 
 }  // namespace
 
-void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, DevGraph& g, GraphTimes* times)
+void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
+                 GraphTimes* times)
 {
     const uint64_t M = st.n;
     g.n_kmers = M;
@@ -320,7 +321,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     const uint32_t nb = blocks_for(M);
     DevBuf<unsigned long long> counts((size_t)nb + 1, s, true);
     key_run_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
-    scan_counts_kernel<<<1, 1024, 0, s>>>(counts.p, nb, counts.p + nb);
+    exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
     SW_CUDA(cudaGetLastError());
     unsigned long long n_nodes = 0;
     SW_CUDA(cudaMemcpyAsync(&n_nodes, counts.p + nb, sizeof(n_nodes), cudaMemcpyDeviceToHost, s));
@@ -338,7 +339,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     // -- edges -----------------------------------------------------------------------------------
     timer.start();
     edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, counts.p);
-    scan_counts_kernel<<<1, 1024, 0, s>>>(counts.p, nb, counts.p + nb);
+    exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
     SW_CUDA(cudaGetLastError());
     unsigned long long n_raw = 0;
     SW_CUDA(cudaMemcpyAsync(&n_raw, counts.p + nb, sizeof(n_raw), cudaMemcpyDeviceToHost, s));
@@ -349,14 +350,14 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, cudaStream_t s, De
     } else {
         // reuse the node sort's buffers for the (rank pair, assembly) sort
         sp.n = n_raw;
-        edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, 0u, counts.p, sp.keys.p,
+        edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, rec_base, counts.p, sp.keys.p,
                                              sp.vals.p);
         SW_CUDA(cudaGetLastError());
         tm.launches += 1 + radix_sort_pairs(sp, 64, s);
         const uint32_t eb = blocks_for(n_raw);
         DevBuf<unsigned long long> ecounts((size_t)eb + 1, s, true);
         key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
-        scan_counts_kernel<<<1, 1024, 0, s>>>(ecounts.p, eb, ecounts.p + eb);
+        exclusive_scan_u64(ecounts.p, eb, ecounts.p + eb, s);
         SW_CUDA(cudaGetLastError());
         unsigned long long n_edges = 0;
         SW_CUDA(cudaMemcpyAsync(&n_edges, ecounts.p + eb, sizeof(n_edges), cudaMemcpyDeviceToHost, s));

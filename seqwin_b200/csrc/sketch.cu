@@ -296,8 +296,8 @@ DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
     SW_CUDA(cudaMemsetAsync(buf.p + 2 * (size_t)R + 2, 0, 2 * sizeof(unsigned long long), s));
     const uint32_t grid = (R + 127) / 128;
     plan_count_kernel<<<grid, 128, 0, s>>>(rr, R, k, w, tw, buf.p, buf.p + R + 1, buf.p + 2 * (size_t)R + 2);
-    scan_counts_kernel<<<1, 1024, 0, s>>>(buf.p, R, buf.p + R);
-    scan_counts_kernel<<<1, 1024, 0, s>>>(buf.p + R + 1, R, buf.p + 2 * (size_t)R + 1);
+    exclusive_scan_u64(buf.p, R, buf.p + R, s);
+    exclusive_scan_u64(buf.p + R + 1, R, buf.p + 2 * (size_t)R + 1, s);
     SW_CUDA(cudaGetLastError());
     unsigned long long h[4];
     SW_CUDA(cudaMemcpyAsync(&h[0], buf.p + R, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -391,7 +391,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         return;
     }
     cudaEventRecord(ev[2], s);
-    scan_counts_kernel<<<1, 1024, 0, s>>>(tile_info.p, plan.n_tiles, counters.p + 2);
+    exclusive_scan_u64(tile_info.p, plan.n_tiles, counters.p + 2, s);
     const uint32_t rgrid = (uint32_t)std::min<uint64_t>(((uint64_t)plan.n_tiles + 7) / 8, (uint64_t)sm_count() * 8);
     reorder_kernel<<<rgrid, 256, 0, s>>>(ukeys.p, uvals.p, tile_info.p, tile_info.p + plan.n_tiles, plan.n_tiles,
                                          total, out.keys.p, out.vals.p);

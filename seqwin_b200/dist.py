@@ -1,0 +1,271 @@
+"""Multi-GPU graph build: one process per GPU, genomes sharded, hash ranges owned.
+
+    rank r:  shard of assemblies --(single-GPU kernels)--> local graph (global record indices)
+             cut the sorted node / k-mer / edge arrays at the hash boundaries i * 2^64 / P
+             all-to-all the slices (NCCL over NVLink; torch.distributed is only the plumbing)
+             merge what arrived for hash range r  (csrc/dist.cu, mirrors merge_thread_graphs,
+             cpp/src/seqwin/build_internals.cpp:295-392)
+
+An assembly lives on exactly one rank, so k-mer lists concatenate in rank order and edge weights
+add; concatenating the ranks' outputs in rank order is the reference graph.
+
+The exchange logic is backend-agnostic: :class:`CudaStages` runs the stages through the C ABI on
+device pointers; tests drive the same :func:`exchange_and_merge` over ``gloo`` with a numpy stand-in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+KMER_BYTES, NODE_BYTES, EDGE_BYTES = 8, 40, 24
+
+
+@dataclass
+class LocalGraph:
+    """A shard's graph as three flat uint8 tensors plus the hash-range cut points."""
+    kmers: torch.Tensor
+    nodes: torch.Tensor
+    edges: torch.Tensor
+    node_split: np.ndarray   # [P+1]
+    kmer_split: np.ndarray   # [P+1]
+    edge_split: np.ndarray   # [P+1]
+    handle: object = None
+
+
+def all_to_all_bytes(chunks: list[torch.Tensor], group=None) -> list[torch.Tensor]:
+    """chunks[d] (uint8, 1-D) goes to rank d; returns what every rank sent to this one."""
+    world = dist.get_world_size(group)
+    dev = chunks[0].device
+    send_counts = torch.tensor([c.numel() for c in chunks], dtype=torch.int64, device=dev)
+    recv_counts = torch.empty(world, dtype=torch.int64, device=dev)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        rc = recv_counts.tolist()
+        out = torch.empty(sum(rc), dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(out, torch.cat(chunks), output_split_sizes=rc,
+                               input_split_sizes=send_counts.tolist(), group=group)
+        return list(out.split(rc))
+    # gloo has no all_to_all: pairwise exchange through host memory (CPU tests, 1-GPU debugging)
+    rank = dist.get_rank(group)
+    gathered = [torch.empty(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, send_counts.cpu(), group=group)
+    rc = [int(gathered[s][rank]) for s in range(world)]
+    host_chunks = [c.cpu().contiguous() for c in chunks]
+    outs = [torch.empty(n, dtype=torch.uint8) for n in rc]
+    outs[rank].copy_(host_chunks[rank])
+    reqs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if host_chunks[peer].numel():
+            reqs.append(dist.isend(host_chunks[peer], peer, group=group))
+        if rc[peer]:
+            reqs.append(dist.irecv(outs[peer], peer, group=group))
+    for r in reqs:
+        r.wait()
+    return [o.to(dev) for o in outs]
+
+
+def exchange_and_merge(stages, local: LocalGraph, group=None):
+    """Send every hash range to its owner and merge what arrives. Returns stages.merge(...)."""
+    world = dist.get_world_size(group)
+    ns, ks, es = local.node_split, local.kmer_split, local.edge_split
+    node_chunks = [local.nodes[int(ns[d]) * NODE_BYTES:int(ns[d + 1]) * NODE_BYTES] for d in range(world)]
+    kmer_chunks = [local.kmers[int(ks[d]) * KMER_BYTES:int(ks[d + 1]) * KMER_BYTES] for d in range(world)]
+    edge_chunks = [local.edges[int(es[d]) * EDGE_BYTES:int(es[d + 1]) * EDGE_BYTES] for d in range(world)]
+    # the owner needs each sender's k-mer base to rebase node.start: ship it as 8 extra bytes
+    dev = local.nodes.device
+    base_chunks = [torch.tensor([int(ks[d])], dtype=torch.int64, device=dev).view(torch.uint8) for d in range(world)]
+    recv_nodes = all_to_all_bytes(node_chunks, group)
+    recv_kmers = all_to_all_bytes(kmer_chunks, group)
+    recv_edges = all_to_all_bytes(edge_chunks, group)
+    recv_base = all_to_all_bytes(base_chunks, group)
+    node_counts = np.array([t.numel() // NODE_BYTES for t in recv_nodes], dtype=np.uint64)
+    kmer_counts = np.array([t.numel() // KMER_BYTES for t in recv_kmers], dtype=np.uint64)
+    edge_counts = np.array([t.numel() // EDGE_BYTES for t in recv_edges], dtype=np.uint64)
+    kmer_base = np.array([int(t.view(torch.int64)[0]) for t in recv_base], dtype=np.uint64)
+    return stages.merge(torch.cat(recv_nodes), node_counts, torch.cat(recv_kmers), kmer_counts, kmer_base,
+                        torch.cat(recv_edges), edge_counts)
+
+
+def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
+    """(global index of this shard's first record, total records)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if dist.get_backend(group) != "nccl":
+        device = torch.device("cpu")
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_records_local], dtype=torch.int64, device=device), group=group)
+    counts = [int(c) for c in counts]
+    return sum(counts[:rank]), sum(counts)
+
+
+# ---- CUDA stages (C ABI) ------------------------------------------------------------------------
+
+class _DevView:
+    """Zero-copy uint8 view of device memory owned by libseqwin_b200 (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+def _view(ptr, nbytes: int, device) -> torch.Tensor:
+    if not nbytes or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevView(int(ptr), int(nbytes)), device=device)
+
+
+class CudaStages:
+    """The product stages: everything runs in libseqwin_b200.so on torch's current stream."""
+
+    def __init__(self, lib, device):
+        from . import _lib
+        self.L, self._lib, self.device = lib, _lib, device
+        self._lib.check(self.L.sw_set_stream(C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        self.times = None
+        self.merge_launches = 0
+
+    def local_build(self, dev_batch, k: int, w: int, rec_base: int, world: int) -> LocalGraph:
+        L, lb = self.L, self._lib
+        g = C.c_void_p()
+        self.times = lb.StageTimes()
+        lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, C.byref(g), C.byref(self.times)))
+        pk, pn, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        lb.check(L.sw_graph_device_ptrs(g, C.byref(pk), C.byref(pn), C.byref(pe)))
+        n_k, n_n, n_e = (L.sw_graph_size(g, i) for i in (lb.SW_KMERS, lb.SW_NODES, lb.SW_EDGES))
+        ns, ks, es = (np.zeros(world + 1, dtype=np.uint64) for _ in range(3))
+        lb.check(L.sw_graph_split(g, world, ns.ctypes.data, ks.ctypes.data, es.ctypes.data))
+        return LocalGraph(_view(pk.value, n_k * KMER_BYTES, self.device), _view(pn.value, n_n * NODE_BYTES, self.device),
+                          _view(pe.value, n_e * EDGE_BYTES, self.device), ns, ks, es, handle=g)
+
+    def free_local(self, local: LocalGraph) -> None:
+        if local.handle:
+            self.L.sw_graph_free(local.handle)
+            local.handle = None
+
+    def merge(self, nodes, node_counts, kmers, kmer_counts, kmer_base, edges, edge_counts):
+        L, lb = self.L, self._lib
+        torch.cuda.current_stream(self.device).synchronize()   # NCCL results visible to the library stream
+        g = C.c_void_p()
+        n_launch = C.c_uint32()
+        lb.check(L.sw_dist_merge(C.c_void_p(nodes.data_ptr()), node_counts.ctypes.data, C.c_void_p(kmers.data_ptr()),
+                                 kmer_counts.ctypes.data, kmer_base.ctypes.data, C.c_void_p(edges.data_ptr()),
+                                 edge_counts.ctypes.data, len(node_counts), C.byref(g), C.byref(n_launch)))
+        self.merge_launches = n_launch.value
+        return g
+
+
+def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None):
+    """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle."""
+    world = dist.get_world_size(group)
+    rec_base, _ = record_base(n_records_local, stages.device, group)
+    local = stages.local_build(dev_batch, k, w, rec_base, world)
+    try:
+        return exchange_and_merge(stages, local, group)
+    finally:
+        stages.free_local(local)
+
+
+def export_graph(lib, g):
+    """Host numpy copies (kmers, nodes, edges) of a device-resident graph handle."""
+    from . import _lib
+    from ._core import EDGE_DTYPE, KMER_DTYPE, NODE_DTYPE
+    kmers = np.empty(lib.sw_graph_size(g, _lib.SW_KMERS), dtype=KMER_DTYPE)
+    nodes = np.empty(lib.sw_graph_size(g, _lib.SW_NODES), dtype=NODE_DTYPE)
+    edges = np.empty(lib.sw_graph_size(g, _lib.SW_EDGES), dtype=EDGE_DTYPE)
+    _lib.check(lib.sw_graph_export(g, kmers.ctypes.data, nodes.ctypes.data, edges.ctypes.data, None))
+    return kmers, nodes, edges
+
+
+def concat_rank_graphs(parts):
+    """Concatenate per-rank (kmers, nodes, edges) in rank order into the global graph."""
+    kmers = np.concatenate([p[0] for p in parts])
+    nodes_l, off = [], 0
+    for k_, n_, _ in parts:
+        n_ = n_.copy()
+        n_["start"] += off
+        n_["stop"] += off
+        off += len(k_)
+        nodes_l.append(n_)
+    return kmers, np.concatenate(nodes_l), np.concatenate([p[2] for p in parts])
+
+
+def gather_graph(parts_local, group=None):
+    """Gather every rank's (kmers, nodes, edges) on rank 0 and concatenate (tests / small graphs)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(parts_local, gathered, dst=0, group=group)
+    return concat_rank_graphs(gathered) if rank == 0 else None
+
+
+# ---- bench driver (bench.py --gpus N under torchrun) ----------------------------------------------
+
+def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int, warmup: int, sampler_cls) -> dict:
+    from . import _lib
+    device = torch.device("cuda", torch.cuda.current_device())
+    stages = CudaStages(L, device)
+    n_records = L.sw_batch_n_records(batch)
+    n_bases_local = L.sw_batch_n_bases(batch)
+    dev = C.c_void_p()
+    _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
+
+    def step():
+        g = dist_build(stages, dev, n_records, k, w)
+        sizes = [L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES)]
+        L.sw_graph_free(g)
+        return sizes
+
+    for _ in range(warmup):
+        step()
+    sampler = sampler_cls(torch.cuda.current_device())
+    times, stage_dicts, sizes = [], [], None
+    sampler.start()
+    for _ in range(steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sizes = step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t))
+        d = stages.times.as_dict()
+        d["n_kmers_local"] = d["n_kmers"]
+        d["total_ms"] = float(t)
+        d["total_launches"] = d["total_launches"] + stages.merge_launches
+        stage_dicts.append(d)
+    clocks = sampler.stop()
+    L.sw_dev_batch_free(dev)
+
+    # end to end: pinned host batch -> H2D -> distributed build -> D2H of this rank's range
+    import time
+    e2e = []
+    for i in range(max(1, warmup // 2) + steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d2 = C.c_void_p()
+        _lib.check(L.sw_dev_upload(batch, C.byref(d2)))
+        g = dist_build(stages, d2, n_records, k, w)
+        export_graph(L, g)
+        L.sw_graph_free(g)
+        L.sw_dev_batch_free(d2)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i >= max(1, warmup // 2):
+            e2e.append((float(t), stage_dicts[-1]))
+
+    tot = torch.tensor([n_bases_local] + sizes, dtype=torch.int64, device=device)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    n_bases_total, n_k, n_n, n_e = (int(x) for x in tot)
+    for d in stage_dicts:
+        d["n_kmers"], d["n_nodes"], d["n_edges"] = n_k, n_n, n_e
+    L.sw_set_stream(None)
+    return {"stages": stage_dicts, "clocks": clocks, "e2e_runs": e2e, "n_bases_total": n_bases_total}

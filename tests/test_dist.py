@@ -1,0 +1,113 @@
+"""N>1 host-side logic over gloo (world_size 2, CPU): shard bookkeeping, hash-range cuts, the byte
+all-to-all and the rank-order concatenation of seqwin_b200.dist, with a numpy stand-in for the CUDA
+stages (the stand-in lives here, in tests/, and uses the oracle for the per-shard build)."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.helpers import assert_graph_equal
+
+
+class NumpyStages:
+    """Test double for seqwin_b200.dist.CudaStages."""
+    device = torch.device("cpu")
+
+    def local_build(self, paths, k, w, rec_base, world):
+        from oracle import oracle as O
+        from seqwin_b200.dist import LocalGraph
+        kmers, nodes, edges, offsets, ids = O._build_native(paths, k, w)
+        kmers = kmers.copy()
+        kmers["record_idx"] += np.uint32(rec_base)
+        bounds = [(i << 64) // world for i in range(world)]
+        ns = np.array([int(np.searchsorted(nodes["hash"], np.uint64(b), "left")) if b else 0 for b in bounds] + [len(nodes)],
+                      dtype=np.uint64)
+        es = np.array([int(np.searchsorted(edges["first"], np.uint64(b), "left")) if b else 0 for b in bounds] + [len(edges)],
+                      dtype=np.uint64)
+        ks = np.array([int(nodes["start"][int(i)]) if int(i) < len(nodes) else len(kmers) for i in ns], dtype=np.uint64)
+        as_t = lambda a: torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy())  # noqa: E731
+        return LocalGraph(as_t(kmers), as_t(nodes), as_t(edges), ns, ks, es)
+
+    def free_local(self, local):
+        pass
+
+    def merge(self, nodes_t, node_counts, kmers_t, kmer_counts, kmer_base, edges_t, edge_counts):
+        from oracle.oracle import EDGE_DTYPE, KMER_DTYPE, NODE_DTYPE
+        nodes = np.frombuffer(nodes_t.numpy().tobytes(), dtype=NODE_DTYPE)
+        kmers = np.frombuffer(kmers_t.numpy().tobytes(), dtype=KMER_DTYPE)
+        edges = np.frombuffer(edges_t.numpy().tobytes(), dtype=EDGE_DTYPE)
+        node_off = np.concatenate([[0], np.cumsum(node_counts)]).astype(np.int64)
+        kmer_off = np.concatenate([[0], np.cumsum(kmer_counts)]).astype(np.int64)
+        abs_start = np.empty(len(nodes), dtype=np.int64)
+        for s in range(len(node_counts)):
+            sl = slice(node_off[s], node_off[s + 1])
+            abs_start[sl] = kmer_off[s] + (nodes["start"][sl].astype(np.int64) - int(kmer_base[s]))
+        order = np.argsort(nodes["hash"], kind="stable")
+        out_k, out_n = [], []
+        for j in order:
+            cnt = int(nodes["stop"][j] - nodes["start"][j])
+            seg = kmers[abs_start[j]:abs_start[j] + cnt]
+            if out_n and out_n[-1][0] == nodes["hash"][j]:
+                out_n[-1][2] += cnt
+            else:
+                pos = sum(len(x) for x in out_k)
+                out_n.append([nodes["hash"][j], pos, pos + cnt])
+            out_k.append(seg)
+        mk = np.concatenate(out_k) if out_k else np.empty(0, KMER_DTYPE)
+        mn = np.zeros(len(out_n), dtype=NODE_DTYPE)
+        for i, (h, a, b) in enumerate(out_n):
+            mn[i] = (h, a, b, 0, 0, 0.0)
+        eo = np.lexsort((edges["second"], edges["first"]))
+        me = []
+        for j in eo:
+            if me and me[-1][0] == edges["first"][j] and me[-1][1] == edges["second"][j]:
+                me[-1][2] += int(edges["weight"][j])
+            else:
+                me.append([edges["first"][j], edges["second"][j], int(edges["weight"][j])])
+        mee = np.zeros(len(me), dtype=EDGE_DTYPE)
+        for i, (a, b, c) in enumerate(me):
+            mee[i] = (a, b, c)
+        return mk, mn, mee
+
+
+def _worker(rank, world, port, paths, k, w, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from seqwin_b200 import dist as swd
+        per = (len(paths) + world - 1) // world
+        mine = paths[rank * per:(rank + 1) * per]
+        n_rec_local = int(O._build_native(mine, k, w)[3][-1])
+        stages = NumpyStages()
+        rec_base, total = swd.record_base(n_rec_local, torch.device("cpu"))
+        local = stages.local_build(mine, k, w, rec_base, world)
+        merged = swd.exchange_and_merge(stages, local)
+        full = swd.gather_graph(merged)
+        if rank == 0:
+            np.savez(out_path, kmers=full[0], nodes=full[1], edges=full[2], total=np.array([total]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kw", [(17, 10), (21, 46)], ids=lambda kw: f"k{kw[0]}w{kw[1]}")
+def test_two_rank_exchange_matches_single_graph(synth_sets, tmp_path, kw):
+    from oracle import oracle as O
+    paths, _ = synth_sets["synth_small"]
+    paths = [str(p) for p in paths]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "merged.npz"
+    mp.spawn(_worker, args=(2, port, paths, kw[0], kw[1], str(out)), nprocs=2, join=True)
+    got = np.load(out)
+    want = O._build_native(paths, *kw)
+    assert int(got["total"][0]) == int(want[3][-1])
+    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"2 ranks {kw}")
