@@ -121,8 +121,50 @@ Arena& tls_arena()
 }
 }  // namespace
 
+namespace {
+__global__ void readback_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+struct ReadbackRing {
+    unsigned long long* host = nullptr;
+    size_t cap = 0, off = 0;
+    ~ReadbackRing() { if (host) cudaFreeHost(host); }
+    unsigned long long* take(size_t count)
+    {
+        if (!host) {
+            cap = (size_t)1 << 20;  // 8 MB of u64 slots
+            SW_CUDA(cudaHostAlloc((void**)&host, cap * sizeof(unsigned long long), cudaHostAllocMapped));
+        }
+        if (count > cap) fail_runtime("readback too large");
+        if (off + count > cap) off = 0;  // wrap: earlier slots were consumed long ago
+        unsigned long long* r = host + off;
+        off += count;
+        return r;
+    }
+};
+ReadbackRing& tls_readback()
+{
+    static thread_local ReadbackRing r;
+    return r;
+}
+}  // namespace
+
 void* arena_alloc(size_t bytes) { return tls_arena().alloc(bytes); }
 void arena_reset() { tls_arena().reset(); }
+
+const unsigned long long* readback_u64(const unsigned long long* d_src, size_t count, cudaStream_t s)
+{
+    unsigned long long* h = tls_readback().take(count ? count : 1);
+    if (count) {
+        unsigned long long* d_dst = nullptr;
+        SW_CUDA(cudaHostGetDevicePointer((void**)&d_dst, h, 0));
+        readback_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_src, d_dst, count);
+        SW_CUDA(cudaGetLastError());
+    }
+    return h;
+}
 
 namespace {
 std::mutex g_pool_mu;
@@ -187,6 +229,13 @@ cudaStream_t lib_stream()
     return g->s;
 }
 
+cudaStream_t copy_stream()
+{
+    static thread_local std::unique_ptr<StreamGuard> g;
+    if (!g) g.reset(new StreamGuard());
+    return g->s;
+}
+
 void copy_meta(const sw_batch& src, sw_batch& dst)
 {
     dst.words = nullptr;
@@ -218,6 +267,30 @@ void check_kw(uint32_t k, uint32_t w)
     if (w < 1) fail_runtime("windowsize must be >= 1");
 }
 
+// small per-record tables (everything but the packed bases)
+void upload_tables(const sw_batch& b, sw_dev_batch& d, cudaStream_t s)
+{
+    const size_t R = b.rec_len.size();
+    d.rec_word_off.alloc(R, s);
+    d.rec_asm.alloc(R, s);
+    d.rec_len.alloc(R, s);
+    d.rec_inv_off.alloc(R + 1, s);
+    d.inv_start.alloc(b.inv_start.size(), s);
+    d.inv_len.alloc(b.inv_len.size(), s);
+    const std::vector<uint32_t> ra = record_assembly_map(b.record_offsets);
+    SW_CUDA(cudaMemcpyAsync(d.rec_inv_off.p, b.rec_inv_off.data(), (R + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (!b.inv_start.empty()) {
+        SW_CUDA(cudaMemcpyAsync(d.inv_start.p, b.inv_start.data(), b.inv_start.size() * 4, cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d.inv_len.p, b.inv_len.data(), b.inv_len.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (R) {
+        SW_CUDA(cudaMemcpyAsync(d.rec_len.p, b.rec_len.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d.rec_word_off.p, b.rec_word_off.data(), R * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d.rec_asm.p, ra.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    }
+    SW_CUDA(cudaStreamSynchronize(s));  // `ra` is a pageable temporary
+}
+
 sw_dev_batch* dev_upload(const sw_batch& b)
 {
     init_device_once();
@@ -231,25 +304,7 @@ sw_dev_batch* dev_upload(const sw_batch& b)
     cudaEventRecord(e0, s);
     d->words.alloc(b.n_words, s);
     SW_CUDA(cudaMemcpyAsync(d->words.p, b.words, b.n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    const size_t R = b.rec_len.size();
-    d->rec_word_off.alloc(R, s);
-    d->rec_asm.alloc(R, s);
-    const std::vector<uint32_t> ra = record_assembly_map(b.record_offsets);
-    d->rec_len.alloc(R, s);
-    d->rec_inv_off.alloc(R + 1, s);
-    d->inv_start.alloc(b.inv_start.size(), s);
-    d->inv_len.alloc(b.inv_len.size(), s);
-    SW_CUDA(cudaMemcpyAsync(d->rec_inv_off.p, b.rec_inv_off.data(), (R + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    if (!b.inv_start.empty()) {
-        SW_CUDA(cudaMemcpyAsync(d->inv_start.p, b.inv_start.data(), b.inv_start.size() * 4, cudaMemcpyHostToDevice, s));
-        SW_CUDA(cudaMemcpyAsync(d->inv_len.p, b.inv_len.data(), b.inv_len.size() * 4, cudaMemcpyHostToDevice, s));
-    }
-    if (R) {
-        SW_CUDA(cudaMemcpyAsync(d->rec_len.p, b.rec_len.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        SW_CUDA(cudaMemcpyAsync(d->rec_word_off.p, b.rec_word_off.data(), R * sizeof(uint64_t),
-                                cudaMemcpyHostToDevice, s));
-        SW_CUDA(cudaMemcpyAsync(d->rec_asm.p, ra.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    }
+    upload_tables(b, *d, s);
     cudaEventRecord(e1, s);
     SW_CUDA(cudaStreamSynchronize(s));
     cudaEventElapsedTime(&d->h2d_ms, e0, e1);
@@ -327,6 +382,144 @@ void graph_to_host(sw_graph& g)
         SW_CUDA(cudaMemcpyAsync(g.h_edges.p, g.dev.edges.p, g.n_edges * sizeof(sw_edge), cudaMemcpyDeviceToHost, s));
     SW_CUDA(cudaStreamSynchronize(s));
     g.on_host = true;
+}
+
+// End-to-end build from a pinned host batch with the copies overlapped with the kernels:
+//   copy stream:    bases slice 0 | slice 1 | ... | slice C-1            kmers+nodes D2H
+//   compute stream: tables, plan  | sketch(slice 0) | sketch(slice 1) ... sort, nodes | edges | edges D2H
+sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_times* t, bool to_host)
+{
+    init_device_once();
+    check_kw(k, w);
+    cudaStream_t s = lib_stream(), cs = copy_stream();
+    arena_reset();
+    auto d = std::make_unique<sw_dev_batch>();
+    d->stream = s;
+    copy_meta(b, d->meta);
+    auto g = std::make_unique<sw_graph>();
+    g->stream = s;
+    g->record_offsets = b.record_offsets;
+    g->ids = b.ids;
+
+    constexpr int kMaxChunks = 8;
+    cudaEvent_t ev[kMaxChunks + 8];
+    for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDefault);
+    cudaEvent_t& e_begin = ev[kMaxChunks], &e_alloc = ev[kMaxChunks + 1], &e_h2d0 = ev[kMaxChunks + 2],
+                 &e_h2d1 = ev[kMaxChunks + 3], &e_nodes = ev[kMaxChunks + 4], &e_d2h0 = ev[kMaxChunks + 5],
+                 &e_d2h1 = ev[kMaxChunks + 6], &e_end = ev[kMaxChunks + 7];
+    struct EvGuard {
+        cudaEvent_t* e; size_t n;
+        ~EvGuard() { for (size_t i = 0; i < n; ++i) cudaEventDestroy(e[i]); }
+    } ev_guard{ev, sizeof(ev) / sizeof(ev[0])};
+
+    cudaEventRecord(e_begin, s);
+    // the small tables go first: behind the bulk copies they would wait for the whole upload
+    upload_tables(b, *d, s);
+    d->words.alloc(b.n_words, s);
+    cudaEventRecord(e_alloc, s);
+    SW_CUDA(cudaStreamWaitEvent(cs, e_alloc, 0));
+
+    // slices of whole records, roughly equal in words
+    const size_t R = b.rec_len.size();
+    std::vector<size_t> rec_cut{0};
+    const size_t data_words = b.n_words - kTailPadWords;
+    const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(kMaxChunks, data_words / (4u << 20)));  // >= 16 MB each
+    for (int c = 1; c < n_chunks; ++c) {
+        const uint64_t target = (uint64_t)data_words * c / n_chunks;
+        size_t r = std::lower_bound(b.rec_word_off.begin(), b.rec_word_off.end(), target) - b.rec_word_off.begin();
+        if (r > rec_cut.back() && r < R) rec_cut.push_back(r);
+    }
+    rec_cut.push_back(R);
+    const size_t C = rec_cut.size() - 1;
+    cudaEventRecord(e_h2d0, cs);
+    for (size_t c = 0; c < C; ++c) {
+        const size_t w0 = c == 0 ? 0 : b.rec_word_off[rec_cut[c]];
+        const size_t w1 = c + 1 == C ? b.n_words : b.rec_word_off[rec_cut[c + 1]];
+        if (w1 > w0)
+            SW_CUDA(cudaMemcpyAsync(d->words.p + w0, b.words + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+        cudaEventRecord(ev[c], cs);
+    }
+    cudaEventRecord(e_h2d1, cs);
+
+    const auto host_t0 = std::chrono::steady_clock::now();
+    DevPlan plan = make_plan(*d, k, w, s, true);
+    const float plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    std::vector<SketchChunk> chunks(C);
+    for (size_t c = 0; c < C; ++c) {
+        const uint32_t lo = plan.rec_tile_off.empty() ? 0 : (uint32_t)plan.rec_tile_off[rec_cut[c]];
+        const uint32_t hi = plan.rec_tile_off.empty() ? 0
+                            : (rec_cut[c + 1] >= R ? plan.n_tiles : (uint32_t)plan.rec_tile_off[rec_cut[c + 1]]);
+        chunks[c] = SketchChunk{lo, hi, ev[c]};
+    }
+    SketchStream st;
+    run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, 0u, s, st, &chunks);
+
+    bool d2h_started = false;
+    const std::function<void()> after_nodes = [&] {
+        if (!to_host) return;
+        g->n_kmers = g->dev.n_kmers;
+        g->n_nodes = g->dev.n_nodes;
+        g->h_kmers = host_pool_get(g->n_kmers * sizeof(sw_kmer));
+        g->h_nodes = host_pool_get(g->n_nodes * sizeof(sw_node));
+        cudaEventRecord(e_nodes, s);
+        SW_CUDA(cudaStreamWaitEvent(cs, e_nodes, 0));
+        cudaEventRecord(e_d2h0, cs);
+        if (g->n_kmers)
+            SW_CUDA(cudaMemcpyAsync(g->h_kmers.p, g->dev.kmers.p, g->n_kmers * sizeof(sw_kmer), cudaMemcpyDeviceToHost, cs));
+        if (g->n_nodes)
+            SW_CUDA(cudaMemcpyAsync(g->h_nodes.p, g->dev.nodes.p, g->n_nodes * sizeof(sw_node), cudaMemcpyDeviceToHost, cs));
+        d2h_started = true;
+    };
+    GraphTimes gt;
+    build_graph(st, d->rec_asm.p, 0u, s, g->dev, &gt, &after_nodes);
+    g->on_device = true;
+    g->n_kmers = g->dev.n_kmers;
+    g->n_nodes = g->dev.n_nodes;
+    g->n_edges = g->dev.n_edges;
+    if (to_host) {
+        if (!d2h_started) {  // empty stream: nothing was copied yet
+            g->h_kmers = host_pool_get(0);
+            g->h_nodes = host_pool_get(0);
+            cudaEventRecord(e_d2h0, cs);
+        }
+        g->h_edges = host_pool_get(g->n_edges * sizeof(sw_edge));
+        // edges follow kmers + nodes on the copy stream (one D2H engine anyway)
+        cudaEventRecord(e_nodes, s);
+        SW_CUDA(cudaStreamWaitEvent(cs, e_nodes, 0));
+        if (g->n_edges)
+            SW_CUDA(cudaMemcpyAsync(g->h_edges.p, g->dev.edges.p, g->n_edges * sizeof(sw_edge), cudaMemcpyDeviceToHost, cs));
+        cudaEventRecord(e_d2h1, cs);
+        SW_CUDA(cudaStreamWaitEvent(s, e_d2h1, 0));
+    }
+    cudaEventRecord(e_end, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    SW_CUDA(cudaStreamSynchronize(cs));
+    if (to_host) {
+        g->on_host = true;
+        g->dev = DevGraph();  // the device copies are no longer needed once the host arrays exist
+        g->on_device = false;
+    }
+    if (t) {
+        memset(t, 0, sizeof(*t));
+        cudaEventElapsedTime(&t->h2d_ms, e_h2d0, e_h2d1);
+        if (to_host) cudaEventElapsedTime(&t->d2h_ms, e_d2h0, e_d2h1);
+        cudaEventElapsedTime(&t->total_ms, e_begin, e_end);
+        t->plan_ms = plan_ms;
+        t->sketch_kernel_ms = st.kernel_ms;
+        t->reorder_ms = st.reorder_ms;
+        t->sort_nodes_ms = gt.sort_nodes_ms;
+        t->nodes_ms = gt.nodes_ms;
+        t->edges_ms = gt.edges_ms;
+        t->n_bases = b.n_bases;
+        t->n_kmers = g->n_kmers;
+        t->n_nodes = g->n_nodes;
+        t->n_edges = g->n_edges;
+        t->n_tiles = plan.n_tiles;
+        t->sketch_launches = st.launches;
+        t->total_launches = st.launches + gt.launches;
+    }
+    // d (device batch) is released here, stream-ordered after everything above
+    return g.release();
 }
 
 template <typename F>
@@ -470,28 +663,7 @@ int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const voi
 
 int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)
 {
-    return guarded([&] {
-        check_kw(k, w);
-        std::unique_ptr<sw_dev_batch, void (*)(sw_dev_batch*)> d(dev_upload(*b), sw_dev_batch_free);
-        std::unique_ptr<sw_graph, void (*)(sw_graph*)> g(dev_build(*d, k, w, t), sw_graph_free);
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0);
-        cudaEventCreate(&e1);
-        cudaEventRecord(e0, g->stream);
-        graph_to_host(*g);
-        cudaEventRecord(e1, g->stream);
-        cudaEventSynchronize(e1);
-        if (t) {
-            cudaEventElapsedTime(&t->d2h_ms, e0, e1);
-            t->h2d_ms = d->h2d_ms;
-        }
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        // the device copies are no longer needed once the host arrays exist
-        g->dev = DevGraph();
-        g->on_device = false;
-        *out = g.release();
-    });
+    return guarded([&] { *out = build_pipelined(*b, k, w, t, /*to_host=*/true); });
 }
 
 int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, uint32_t n_host_threads,
@@ -502,10 +674,8 @@ int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, u
         check_kw(k, w);
         init_device_once();
         std::unique_ptr<sw_batch> b(batch_from_fasta(paths, n_paths, n_host_threads));
-        std::unique_ptr<sw_dev_batch, void (*)(sw_dev_batch*)> d(dev_upload(*b), sw_dev_batch_free);
-        b.reset();
         // the graph stays in HBM; sw_graph_export copies it straight into the caller's arrays
-        *out = dev_build(*d, k, w, nullptr);
+        *out = build_pipelined(*b, k, w, nullptr, /*to_host=*/false);
     });
 }
 

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,12 @@ namespace sw {
 // of every build, so the steady state performs no cudaMalloc / cudaFree at all.
 void* arena_alloc(size_t bytes);
 void arena_reset();
+
+// Small device -> host readbacks (counts, histograms) go through a pinned, device-mapped buffer
+// written by a tiny kernel instead of cudaMemcpyAsync: a copy-engine transfer would queue behind
+// the bulk graph export that the end-to-end path overlaps with the kernels.  The returned host
+// pointer is valid once `s` has been synchronized and until the next arena_reset().
+const unsigned long long* readback_u64(const unsigned long long* d_src, size_t count, cudaStream_t s);
 
 // Device buffer.  Persistent buffers (graph outputs, uploaded batches) come from the stream-ordered
 // cudaMallocAsync pool; temporaries (tmp = true) come from the scratch arena and are never freed
@@ -86,6 +93,7 @@ struct DevPlan {
     DevBuf<Piece> pieces;
     uint32_t n_tiles = 0;
     uint64_t n_windows = 0, n_kmers = 0;
+    std::vector<unsigned long long> rec_tile_off;  // [R+1] first tile of each record (host, optional)
     uint32_t tk = 0;  // tile capacity the plan was cut for
     int config = 0;   // kernel configuration index
 };
@@ -101,9 +109,15 @@ struct SketchStream {
 int sketch_pick_config(uint32_t w, uint32_t* tk_out);
 // Device-side tile planner: cuts every record's valid-k-mer stream into tiles (see ingest.h:
 // plan_tiles is the host statement of the same rule, used by the test emulator).
-DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s);
+DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s, bool want_rec_tile_off = false);
+// A slice of tiles whose packed bases arrive with their own H2D copy (pipelined upload).
+struct SketchChunk {
+    uint32_t tile_lo, tile_hi;
+    cudaEvent_t ready;  // recorded on the copy stream after the slice's bases landed (may be null)
+};
 void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const DevPlan& plan,
-                uint32_t k, uint32_t w, uint32_t rec_base, cudaStream_t s, SketchStream& out);
+                uint32_t k, uint32_t w, uint32_t rec_base, cudaStream_t s, SketchStream& out,
+                const std::vector<SketchChunk>* chunks = nullptr);
 
 // ---- radix sort -------------------------------------------------------------------------------
 // Stable LSD radix sort of (u64 key, u32 value) pairs over key bits [0, end_bit).
@@ -127,8 +141,10 @@ struct GraphTimes {
     uint32_t launches = 0;
 };
 // d_rec_asm: assembly index of every global record id used in the stream.
+// after_nodes (optional) is called once kmers + nodes are final and enqueued on s, before the edge
+// stage starts: the end-to-end path uses it to begin their D2H copies on a second stream.
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
-                 GraphTimes* times);
+                 GraphTimes* times, const std::function<void()>* after_nodes = nullptr);
 
 // ---- multi-GPU merge (dist.cu) -------------------------------------------------------------------
 void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out /* 3*(P+1) */, cudaStream_t s);

@@ -178,8 +178,9 @@ void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out, cu
     DevBuf<unsigned long long> d(3 * (size_t)(P + 1), s, true);
     split_kernel<<<(P + 1 + 63) / 64, 64, 0, s>>>(g.nodes.p, g.n_nodes, g.n_kmers, g.edges.p, g.n_edges, P, d.p);
     SW_CUDA(cudaGetLastError());
-    SW_CUDA(cudaMemcpyAsync(host_out, d.p, d.bytes(), cudaMemcpyDeviceToHost, s));
+    const unsigned long long* h = readback_u64(d.p, d.n, s);
     SW_CUDA(cudaStreamSynchronize(s));
+    std::copy(h, h + d.n, host_out);
 }
 
 void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
@@ -224,9 +225,9 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         node_pack_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, Nn, packed.p);
         exclusive_scan_u64(packed.p, Nn, packed.p + Nn, s);
         SW_CUDA(cudaGetLastError());
-        unsigned long long total = 0;
-        SW_CUDA(cudaMemcpyAsync(&total, packed.p + Nn, sizeof(total), cudaMemcpyDeviceToHost, s));
+        const unsigned long long* total_p = readback_u64(packed.p + Nn, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long total = *total_p;
         out.n_nodes = total >> 40;
         out.nodes.alloc(out.n_nodes, s);
         const uint32_t grid = (uint32_t)std::min<uint64_t>((Nn + 7) / 8, 148 * 16);
@@ -256,9 +257,9 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         edge_flag_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, flags.p);
         exclusive_scan_u64(flags.p, Ne, flags.p + Ne, s);
         SW_CUDA(cudaGetLastError());
-        unsigned long long n_edges = 0;
-        SW_CUDA(cudaMemcpyAsync(&n_edges, flags.p + Ne, sizeof(n_edges), cudaMemcpyDeviceToHost, s));
+        const unsigned long long* n_edges_p = readback_u64(flags.p + Ne, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long n_edges = *n_edges_p;
         out.n_edges = n_edges;
         out.edges.alloc(n_edges, s);
         SW_CUDA(cudaMemsetAsync(out.edges.p, 0, n_edges * sizeof(sw_edge), s));

@@ -287,7 +287,7 @@ uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlockItems - 1) / kBlo
 }  // namespace
 
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
-                 GraphTimes* times)
+                 GraphTimes* times, const std::function<void()>* after_nodes)
 {
     const uint64_t M = st.n;
     g.n_kmers = M;
@@ -323,9 +323,9 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     key_run_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
     exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
     SW_CUDA(cudaGetLastError());
-    unsigned long long n_nodes = 0;
-    SW_CUDA(cudaMemcpyAsync(&n_nodes, counts.p + nb, sizeof(n_nodes), cudaMemcpyDeviceToHost, s));
+    const unsigned long long* n_nodes_p = readback_u64(counts.p + nb, 1, s);
     SW_CUDA(cudaStreamSynchronize(s));
+    const unsigned long long n_nodes = *n_nodes_p;
     g.n_nodes = n_nodes;
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
@@ -334,6 +334,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
                                          rank_of_stream.p);
     SW_CUDA(cudaGetLastError());
     tm.launches += 3;
+    if (after_nodes) (*after_nodes)();
     tm.nodes_ms = timer.stop();
 
     // -- edges -----------------------------------------------------------------------------------
@@ -341,9 +342,9 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, counts.p);
     exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
     SW_CUDA(cudaGetLastError());
-    unsigned long long n_raw = 0;
-    SW_CUDA(cudaMemcpyAsync(&n_raw, counts.p + nb, sizeof(n_raw), cudaMemcpyDeviceToHost, s));
+    const unsigned long long* n_raw_p = readback_u64(counts.p + nb, 1, s);
     SW_CUDA(cudaStreamSynchronize(s));
+    const unsigned long long n_raw = *n_raw_p;
     tm.launches += 2;
     if (n_raw == 0) {
         g.edges.alloc(0, s);
@@ -359,9 +360,9 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
         exclusive_scan_u64(ecounts.p, eb, ecounts.p + eb, s);
         SW_CUDA(cudaGetLastError());
-        unsigned long long n_edges = 0;
-        SW_CUDA(cudaMemcpyAsync(&n_edges, ecounts.p + eb, sizeof(n_edges), cudaMemcpyDeviceToHost, s));
+        const unsigned long long* n_edges_p = readback_u64(ecounts.p + eb, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long n_edges = *n_edges_p;
         g.n_edges = n_edges;
         g.edges.alloc(n_edges, s);
         SW_CUDA(cudaMemsetAsync(g.edges.p, 0, n_edges * sizeof(sw_edge), s));
@@ -378,16 +379,16 @@ uint32_t run_penalty(const sw_kmer* d_kmers, uint64_t n_kmers, sw_node* d_nodes,
                      double inv_n, cudaStream_t s)
 {
     if (n_nodes == 0) return 0;
-    DevBuf<uint32_t> err(1, s, true);
-    SW_CUDA(cudaMemsetAsync(err.p, 0, sizeof(uint32_t), s));
+    DevBuf<unsigned long long> err64(1, s, true);
+    SW_CUDA(cudaMemsetAsync(err64.p, 0, sizeof(unsigned long long), s));
+    uint32_t* err_p = reinterpret_cast<uint32_t*>(err64.p);
     const uint32_t grid = (uint32_t)std::min<uint64_t>((n_nodes + 7) / 8, (uint64_t)sm_count() * 16);
     penalty_kernel<<<grid, 256, 0, s>>>(d_kmers, n_kmers, d_nodes, n_nodes, d_rec_asm, n_records, d_is_target,
-                                        inv_t, inv_n, err.p);
+                                        inv_t, inv_n, err_p);
     SW_CUDA(cudaGetLastError());
-    uint32_t h = 0;
-    SW_CUDA(cudaMemcpyAsync(&h, err.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    const unsigned long long* h = readback_u64(err64.p, 1, s);
     SW_CUDA(cudaStreamSynchronize(s));
-    return h;
+    return (uint32_t)*h;
 }
 
 }  // namespace sw

@@ -57,6 +57,35 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restr
     }
 }
 
+// Per pass (one CTA each): exclusive scan of the 256 bin counts in place; out[pass] = largest bin.
+__global__ void __launch_bounds__(kRadix) radix_offsets_kernel(unsigned long long* ghist, unsigned long long* max_bin)
+{
+    __shared__ unsigned long long s_warp[kRadix / 32];
+    __shared__ unsigned long long s_max[kRadix / 32];
+    unsigned long long* h = ghist + (size_t)blockIdx.x * kRadix;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long c = h[threadIdx.x];
+    unsigned long long inc = c, mx = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+        const unsigned long long m = __shfl_xor_sync(0xffffffffu, mx, d);
+        mx = m > mx ? m : mx;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    if (lane == 0) s_max[wid] = mx;
+    __syncthreads();
+    unsigned long long base = 0, gmx = 0;
+#pragma unroll
+    for (int i = 0; i < kRadix / 32; ++i) {
+        if (i < wid) base += s_warp[i];
+        gmx = s_max[i] > gmx ? s_max[i] : gmx;
+    }
+    h[threadIdx.x] = base + inc - c;
+    if (threadIdx.x == 0) max_bin[blockIdx.x] = gmx;
+}
+
 template <int NT, int ITEMS>
 __global__ void __launch_bounds__(NT) radix_onesweep_kernel(
     const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
@@ -162,23 +191,16 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
     radix_hist_kernel<<<hist_grid, 256, 0, s>>>(sp.keys.p, n, n_passes, ghist.p);
     SW_CUDA(cudaGetLastError());
     ++launches;
-    std::vector<unsigned long long> hist((size_t)kMaxPasses * kRadix);
-    SW_CUDA(cudaMemcpyAsync(hist.data(), ghist.p, ghist.bytes(), cudaMemcpyDeviceToHost, s));
+    // exclusive digit offsets per pass, computed in place on the device; a pass whose keys all share
+    // one digit is a no-op and is skipped (needs only the per-pass maximum on the host)
+    DevBuf<unsigned long long> max_bin(kMaxPasses, s, true);
+    radix_offsets_kernel<<<n_passes, kRadix, 0, s>>>(ghist.p, max_bin.p);
+    SW_CUDA(cudaGetLastError());
+    ++launches;
+    const unsigned long long* h_max = readback_u64(max_bin.p, n_passes, s);
     SW_CUDA(cudaStreamSynchronize(s));
-
-    // exclusive digit offsets per pass; a pass whose keys all share one digit is a no-op
     bool skip[kMaxPasses];
-    for (int p = 0; p < n_passes; ++p) {
-        unsigned long long run = 0, mx = 0;
-        for (int d = 0; d < kRadix; ++d) {
-            const unsigned long long c = hist[(size_t)p * kRadix + d];
-            hist[(size_t)p * kRadix + d] = run;
-            run += c;
-            mx = std::max(mx, c);
-        }
-        skip[p] = (mx == n);
-    }
-    SW_CUDA(cudaMemcpyAsync(ghist.p, hist.data(), ghist.bytes(), cudaMemcpyHostToDevice, s));
+    for (int p = 0; p < n_passes; ++p) skip[p] = (h_max[p] == n);
 
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
     DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);
@@ -198,8 +220,6 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
         std::swap(sp.keys, sp.keys_alt);
         std::swap(sp.vals, sp.vals_alt);
     }
-    // `hist` (pageable) was the source of an async copy: make sure it was consumed
-    SW_CUDA(cudaStreamSynchronize(s));
     return launches;
 }
 

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
         __syncthreads();  // also: table visible / previous tile's smem reads done
-        const uint32_t tile_id = s_tile;
+        const uint32_t tile_id = P.tile_lo + s_tile;
         if (tile_id >= P.n_tiles) break;
         const Tile T = P.tiles[tile_id];
 
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(NT) sketch_generic_kernel(const __grid_constan
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
         __syncthreads();
-        const uint32_t tile_id = s_tile;
+        const uint32_t tile_id = P.tile_lo + s_tile;
         if (tile_id >= P.n_tiles) break;
         const Tile T = P.tiles[tile_id];
 
@@ -282,7 +282,7 @@ __global__ void plan_fill_kernel(RecordRuns rr, uint32_t R, uint32_t k, uint32_t
     }
 }
 
-DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
+DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s, bool want_rec_tile_off)
 {
     DevPlan dp;
     dp.config = sketch_pick_config(w, &dp.tk);
@@ -299,10 +299,12 @@ DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
     exclusive_scan_u64(buf.p, R, buf.p + R, s);
     exclusive_scan_u64(buf.p + R + 1, R, buf.p + 2 * (size_t)R + 1, s);
     SW_CUDA(cudaGetLastError());
-    unsigned long long h[4];
-    SW_CUDA(cudaMemcpyAsync(&h[0], buf.p + R, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    SW_CUDA(cudaMemcpyAsync(&h[1], buf.p + 2 * (size_t)R + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    const unsigned long long* hb = readback_u64(buf.p, want_rec_tile_off ? (size_t)2 * R + 4 : 0, s);
+    const unsigned long long* h0p = readback_u64(buf.p + R, 1, s);
+    const unsigned long long* h1p = readback_u64(buf.p + 2 * (size_t)R + 1, 3, s);
     SW_CUDA(cudaStreamSynchronize(s));
+    const unsigned long long h[4] = {h0p[0], h1p[0], h1p[1], h1p[2]};
+    if (want_rec_tile_off) dp.rec_tile_off.assign(hb, hb + R + 1);
     if (h[0] > 0x7FFFFFFFull) fail_runtime("too many sketch tiles");
     if (h[1] > 0xFFFFFFF0ull) fail_runtime("too many valid runs");
     dp.n_tiles = (uint32_t)h[0];
@@ -317,7 +319,8 @@ DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s)
 }
 
 void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const DevPlan& plan,
-                uint32_t k, uint32_t w, uint32_t rec_base, cudaStream_t s, SketchStream& out)
+                uint32_t k, uint32_t w, uint32_t rec_base, cudaStream_t s, SketchStream& out,
+                const std::vector<SketchChunk>* chunks)
 {
     out.n = 0;
     out.launches = 0;
@@ -339,7 +342,9 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
 
     // [0, n_tiles): per-tile counts (scanned in place into ordered offsets); then the slots
     DevBuf<unsigned long long> tile_info((size_t)plan.n_tiles * 2, s, true);
-    DevBuf<unsigned long long> counters(3, s, true);  // [0] cursor, [1] ticket (as u32), [2] scan total
+    // [0] cursor, [1] scan total, [2..] one ticket counter (as u32) per launch
+    const size_t n_launch = chunks && !chunks->empty() ? chunks->size() : 1;
+    DevBuf<unsigned long long> counters(2 + n_launch, s, true);
 
     // expected density 2/(w+1); leave 50 % headroom and re-run with the exact size on overflow
     uint64_t capacity = (uint64_t)((double)plan.n_kmers * 3.0 / ((double)w + 1.0)) + 4096;
@@ -369,15 +374,28 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.cursor = counters.p;
         P.tile_count = tile_info.p;
         P.tile_slot = tile_info.p + plan.n_tiles;
-        P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 1);
         P.table = make_roll_table(k);
         cudaEventRecord(ev[0], s);
-        kernel<<<grid, kc.nt, smem, s>>>(P);
+        for (size_t c = 0; c < n_launch; ++c) {
+            P.tile_lo = 0;
+            if (chunks && !chunks->empty()) {
+                // tiles of one uploaded slice of the packed stream: wait for its H2D copy only
+                const SketchChunk& ch = (*chunks)[c];
+                if (ch.tile_hi <= ch.tile_lo) continue;
+                if (ch.ready && attempt == 0) SW_CUDA(cudaStreamWaitEvent(s, ch.ready, 0));
+                P.tile_lo = ch.tile_lo;
+                P.n_tiles = ch.tile_hi;
+            }
+            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 2 + c);
+            const uint32_t g = (uint32_t)std::min<uint64_t>(P.n_tiles - P.tile_lo, grid);
+            kernel<<<g, kc.nt, smem, s>>>(P);
+            SW_CUDA(cudaGetLastError());
+            ++out.launches;
+        }
         cudaEventRecord(ev[1], s);
-        SW_CUDA(cudaGetLastError());
-        ++out.launches;
-        SW_CUDA(cudaMemcpyAsync(&total, counters.p, sizeof(total), cudaMemcpyDeviceToHost, s));
+        const unsigned long long* tp = readback_u64(counters.p, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
+        total = *tp;
         if (total <= capacity) break;
         if (attempt) fail_runtime("sketch output overflow after resize");
         capacity = total;  // low-complexity input: more minimizers than the density estimate
@@ -391,7 +409,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         return;
     }
     cudaEventRecord(ev[2], s);
-    exclusive_scan_u64(tile_info.p, plan.n_tiles, counters.p + 2, s);
+    exclusive_scan_u64(tile_info.p, plan.n_tiles, counters.p + 1, s);
     const uint32_t rgrid = (uint32_t)std::min<uint64_t>(((uint64_t)plan.n_tiles + 7) / 8, (uint64_t)sm_count() * 8);
     reorder_kernel<<<rgrid, 256, 0, s>>>(ukeys.p, uvals.p, tile_info.p, tile_info.p + plan.n_tiles, plan.n_tiles,
                                          total, out.keys.p, out.vals.p);

@@ -39,6 +39,7 @@ struct SketchParams {
     const uint64_t* rec_word_off;  // [R] first word of each record
     const Tile* tiles;
     const Piece* pieces;
+    uint32_t tile_lo;              // this launch handles tiles [tile_lo, n_tiles)
     uint32_t n_tiles;
     uint32_t k, w, c2;
     uint32_t rec_base;             // global index of batch record 0
