@@ -5,6 +5,7 @@
 // Plays the role of the reference's 16-bit-digit CPU LSD sort
 // (cpp/src/seqwin/build_internals.cpp:76-144) and, because the sort is what groups equal
 // minimizer hashes / equal edges, of its two ankerl hash maps (cpp/src/seqwin/build.cpp:66-89).
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -21,6 +22,9 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;
 constexpr int kMaxPasses = 8;
+#ifndef SW_SORT_MINB
+#define SW_SORT_MINB 3
+#endif
 
 constexpr unsigned long long kStAgg = 1ULL << 62;
 constexpr unsigned long long kStInc = 2ULL << 62;
@@ -87,15 +91,20 @@ __global__ void __launch_bounds__(kRadix) radix_offsets_kernel(unsigned long lon
 }
 
 template <int NT, int ITEMS>
-__global__ void __launch_bounds__(NT) radix_onesweep_kernel(
+__global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
     uint32_t* __restrict__ vout, uint64_t n, int shift, const unsigned long long* __restrict__ goff,
     unsigned long long* status, unsigned int* ticket)
 {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * ITEMS;
-    __shared__ uint32_t whist[NW][kRadix];
-    __shared__ unsigned long long dbase[kRadix];
+    static_assert(ITEMS % 4 == 0 && NT >= kRadix, "one thread per digit");
+    __shared__ uint32_t whist[NW][kRadix];       // per-warp digit counts -> per-warp offsets inside the tile
+    __shared__ unsigned long long dbase[kRadix];  // global slot of tile-sorted position 0 of each digit run
+    extern __shared__ __align__(16) unsigned char radix_smem[];
+    uint64_t* s_buf = reinterpret_cast<uint64_t*>(radix_smem);            // [TILE] tile-sorted staging (keys, then values)
+    uint32_t* s_vin = reinterpret_cast<uint32_t*>(radix_smem + (size_t)TILE * 8);  // [TILE] prefetched input values
+    __shared__ uint32_t s_scan[NW];
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -103,18 +112,26 @@ __global__ void __launch_bounds__(NT) radix_onesweep_kernel(
     for (int i = tid; i < NW * kRadix; i += NT) (&whist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t wbase = (uint64_t)tile * TILE + (uint64_t)wid * (32 * ITEMS);
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const uint64_t wbase = tile_base + (uint64_t)wid * (32 * ITEMS);
+    const uint32_t n_valid = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
 
     uint64_t key[ITEMS];
-    uint32_t val[ITEMS];
     uint32_t rank[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
-        const bool valid = idx < n;
-        key[i] = valid ? kin[idx] : ~0ULL;
-        val[i] = valid ? vin[idx] : 0u;
+        key[i] = idx < n ? kin[idx] : ~0ULL;
     }
+    // the values are not needed before the keys have been written out: fetch them into shared
+    // memory asynchronously (cp.async), each thread into its own slots
+    uint32_t* my_vin = s_vin + wid * (32 * ITEMS) + lane;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
+        if (idx < n) __pipeline_memcpy_async(my_vin + i * 32, vin + idx, 4);
+    }
+    __pipeline_commit();
 
     // warp-local stable ranking: items of one warp are ordered (item, lane)
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -135,22 +152,54 @@ __global__ void __launch_bounds__(NT) radix_onesweep_kernel(
     }
     __syncthreads();
 
-    // per digit: exclusive scan over warps, then chain the tile count through the look-back
+    // per digit: exclusive scan over warps; exclusive scan over digits gives the digit's first
+    // tile-sorted position; the tile's count is chained through the decoupled look-back
+    uint32_t run = 0;
     if (tid < kRadix) {
-        uint32_t run = 0;
 #pragma unroll
         for (int wv = 0; wv < NW; ++wv) {
             const uint32_t t = whist[wv][tid];
             whist[wv][tid] = run;
             run += t;
         }
+    }
+    uint32_t inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_scan[wid] = inc;
+    __syncthreads();
+    uint32_t digit_first = inc - run;
+#pragma unroll
+    for (int i = 0; i < NW; ++i)
+        if (i < wid) digit_first += s_scan[i];
+    unsigned long long* my_status = status + (uint64_t)tile * kRadix + tid;
+    if (tid < kRadix) {
+        // publish the tile's digit count right away; the look-back itself runs after the keys have
+        // been staged, when the predecessors have most likely published theirs
+        st_relaxed(my_status, (tile == 0 ? kStInc : kStAgg) | run);
+#pragma unroll
+        for (int wv = 0; wv < NW; ++wv) whist[wv][tid] += digit_first;  // now: tile-sorted position
+    }
+    __syncthreads();
+
+    // keys: registers -> tile-sorted shared memory -> coalesced runs in global memory
+    // (rank[] becomes the item's tile-sorted position)
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const bool valid = wbase + (uint64_t)i * 32 + lane < n;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+        if (valid) {
+            rank[i] += whist[wid][d];
+            s_buf[rank[i]] = key[i];
+        }
+    }
+    if (tid < kRadix) {
         unsigned long long before = 0;
-        unsigned long long* my = status + (uint64_t)tile * kRadix + tid;
-        if (tile == 0) {
-            st_relaxed(my, kStInc | run);
-        } else {
-            st_relaxed(my, kStAgg | run);
-            const unsigned long long* p = my - kRadix;
+        if (tile != 0) {
+            const unsigned long long* p = my_status - kRadix;
             for (;;) {
                 const unsigned long long st = ld_relaxed(p);
                 if ((st >> 62) == 0) continue;
@@ -158,21 +207,37 @@ __global__ void __launch_bounds__(NT) radix_onesweep_kernel(
                 if ((st >> 62) == 2) break;
                 p -= kRadix;
             }
-            st_relaxed(my, kStInc | (before + run));
+            st_relaxed(my_status, kStInc | (before + run));
         }
-        dbase[tid] = goff[tid] + before;
+        dbase[tid] = goff[tid] + before - digit_first;
     }
     __syncthreads();
-
+    uint32_t dig[ITEMS / 4];  // digits of the tile-sorted items this thread writes, 4 per register
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const bool valid = wbase + (uint64_t)i * 32 + lane < n;
-        if (valid) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
-            const unsigned long long pos = dbase[d] + whist[wid][d] + rank[i];
-            kout[pos] = key[i];
-            vout[pos] = val[i];
+        const uint32_t p = (uint32_t)i * NT + tid;
+        if ((i & 3) == 0) dig[i >> 2] = 0;
+        if (p < n_valid) {
+            const uint64_t k2 = s_buf[p];
+            const uint32_t d = (uint32_t)(k2 >> shift) & (kRadix - 1);
+            dig[i >> 2] |= d << (8 * (i & 3));
+            kout[dbase[d] + p] = k2;
         }
+    }
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    // values take the same route through the (re-used) staging buffer
+    uint32_t* s_val = reinterpret_cast<uint32_t*>(s_buf);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
+        if (idx < n) s_val[rank[i]] = my_vin[i * 32];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t p = (uint32_t)i * NT + tid;
+        if (p < n_valid) vout[dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_val[p];
     }
 }
 
@@ -208,11 +273,14 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
     if (!sp.keys_alt.p || sp.keys_alt.n < n) sp.keys_alt.alloc(n, s, true);
     if (!sp.vals_alt.p || sp.vals_alt.n < n) sp.vals_alt.alloc(n, s, true);
 
+    constexpr size_t kSortSmem = (size_t)kSortTile * 12;
+    SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
     for (int p = 0; p < n_passes; ++p) {
         if (skip[p]) continue;
         SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
         SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
-        radix_onesweep_kernel<kSortThreads, kSortItems><<<(uint32_t)n_tiles, kSortThreads, 0, s>>>(
+        radix_onesweep_kernel<kSortThreads, kSortItems><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
             sp.keys.p, sp.keys_alt.p, sp.vals.p, sp.vals_alt.p, n, p * kRadixBits,
             ghist.p + (size_t)p * kRadix, status.p, ticket.p);
         SW_CUDA(cudaGetLastError());
