@@ -314,6 +314,8 @@ def main():
                                  "model": "I_alg = 45*N + 12*M lane-ops; peak = 148 SM x 128 lanes x sm clock under load"},
                 "path": {"algorithmic_bytes": n_bases_local / 4 + 40 * M + 40 * Un + 24 * Ue, "ms": total_ms,
                          "achieved": (n_bases_local / 4 + 40 * M + 40 * Un + 24 * Ue) / (total_ms * 1e-3) / 1e9,
+                         "dist_ms": {n: float(np.mean([s[n] for s in stages])) for n in
+                                     ("phase_local_ms", "phase_exchange_merge_ms", "phase_merge_ms") if n in stages[0]},
                          "stage_ms": {n: float(np.mean([s[n] for s in stages]))
                                       for n in ("plan_ms", "sketch_kernel_ms", "reorder_ms", "sketch_ms", "sort_nodes_ms",
                                                 "nodes_ms", "edges_ms")}}}

@@ -122,6 +122,11 @@ int sw_set_stream(void* stream);
 /* sw_dev_build with the shard's global record base: record_idx = rec_base + local record index. */
 int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_graph** out,
                     sw_stage_times* t);
+/* sw_build_from_batch with a record base; to_host = 0 leaves the graph in HBM (copies overlapped). */
+int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t rec_base, int to_host,
+                           sw_graph** out, sw_stage_times* t);
+/* Bring a device-resident graph into (pooled, pinned) host memory; sw_graph_export then memcpy's. */
+int sw_graph_fetch(sw_graph* g);
 /* Device pointers of a device-resident graph (valid until sw_graph_free). */
 int sw_graph_device_ptrs(sw_graph* g, void** kmers, void** nodes, void** edges);
 /* Cut the sorted node / k-mer / edge arrays at the n_parts+1 hash boundaries i * 2^64 / n_parts

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "sw_dev_sketch": (_I, [_P, _U32, _U32, _P, _P, _P, _SZ, C.POINTER(_SZ)]),
     "sw_set_stream": (_I, [_P]),
     "sw_dev_build_ex": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_build_from_batch_ex": (_I, [_P, _U32, _U32, _U32, _I, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_graph_fetch": (_I, [_P]),
     "sw_graph_device_ptrs": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sw_graph_split": (_I, [_P, _U32, _P, _P, _P]),
     "sw_dist_merge": (_I, [_P, _P, _P, _P, _P, _P, _P, _U32, C.POINTER(_P), C.POINTER(_U32)]),

@@ -387,7 +387,7 @@ void graph_to_host(sw_graph& g)
 // End-to-end build from a pinned host batch with the copies overlapped with the kernels:
 //   copy stream:    bases slice 0 | slice 1 | ... | slice C-1            kmers+nodes D2H
 //   compute stream: tables, plan  | sketch(slice 0) | sketch(slice 1) ... sort, nodes | edges | edges D2H
-sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_times* t, bool to_host)
+sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_times* t, bool to_host, uint32_t rec_base = 0)
 {
     init_device_once();
     check_kw(k, w);
@@ -452,7 +452,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
         chunks[c] = SketchChunk{lo, hi, ev[c]};
     }
     SketchStream st;
-    run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, 0u, s, st, &chunks);
+    run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, rec_base, s, st, &chunks);
 
     bool d2h_started = false;
     const std::function<void()> after_nodes = [&] {
@@ -471,7 +471,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
         d2h_started = true;
     };
     GraphTimes gt;
-    build_graph(st, d->rec_asm.p, 0u, s, g->dev, &gt, &after_nodes);
+    build_graph(st, d->rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes);
     g->on_device = true;
     g->n_kmers = g->dev.n_kmers;
     g->n_nodes = g->dev.n_nodes;
@@ -664,6 +664,22 @@ int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const voi
 int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)
 {
     return guarded([&] { *out = build_pipelined(*b, k, w, t, /*to_host=*/true); });
+}
+
+int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t rec_base, int to_host, sw_graph** out,
+                           sw_stage_times* t)
+{
+    return guarded([&] { *out = build_pipelined(*b, k, w, t, to_host != 0, rec_base); });
+}
+
+int sw_graph_fetch(sw_graph* g)
+{
+    return guarded([&] {
+        if (!g->on_host) {
+            if (!g->on_device) fail_runtime("graph holds no data");
+            graph_to_host(*g);
+        }
+    });
 }
 
 int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, uint32_t n_host_threads,

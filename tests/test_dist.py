@@ -26,9 +26,10 @@ class NumpyStages:
         kmers = kmers.copy()
         kmers["record_idx"] += np.uint32(rec_base)
         bounds = [(i << 64) // world for i in range(world)]
+        ebounds = [int((1.0 - (1.0 - i / world) ** 0.5) * 2.0 ** 64) for i in range(world)]   # balanced for min(u, v)
         ns = np.array([int(np.searchsorted(nodes["hash"], np.uint64(b), "left")) if b else 0 for b in bounds] + [len(nodes)],
                       dtype=np.uint64)
-        es = np.array([int(np.searchsorted(edges["first"], np.uint64(b), "left")) if b else 0 for b in bounds] + [len(edges)],
+        es = np.array([int(np.searchsorted(edges["first"], np.uint64(b), "left")) if b else 0 for b in ebounds] + [len(edges)],
                       dtype=np.uint64)
         ks = np.array([int(nodes["start"][int(i)]) if int(i) < len(nodes) else len(kmers) for i in ns], dtype=np.uint64)
         as_t = lambda a: torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy())  # noqa: E731
