@@ -15,6 +15,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 
 #include "device.h"
 #include "nthash.h"
@@ -165,6 +168,26 @@ __global__ void __launch_bounds__(256) reorder_kernel(const uint64_t* __restrict
             oval[dst + i] = uval[src + i];
         }
     }
+}
+
+// the k-independent 4-base seed tables, uploaded once per process / device
+const TetraTable* device_tetra_table(cudaStream_t s)
+{
+    static std::mutex mu;
+    static std::map<int, TetraTable*> per_device;
+    int dev = 0;
+    SW_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = per_device.find(dev);
+    if (it != per_device.end()) return it->second;
+    auto host = std::make_unique<TetraTable>();
+    make_tetra_table(*host);
+    TetraTable* d = nullptr;
+    SW_CUDA(cudaMalloc((void**)&d, sizeof(TetraTable)));
+    SW_CUDA(cudaMemcpyAsync(d, host.get(), sizeof(TetraTable), cudaMemcpyHostToDevice, s));
+    SW_CUDA(cudaStreamSynchronize(s));
+    per_device[dev] = d;
+    return d;
 }
 
 struct KernelConfig {
@@ -375,6 +398,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.tile_count = tile_info.p;
         P.tile_slot = tile_info.p + plan.n_tiles;
         P.table = make_roll_table(k);
+        P.tetra = device_tetra_table(s);
         cudaEventRecord(ev[0], s);
         for (size_t c = 0; c < n_launch; ++c) {
             P.tile_lo = 0;

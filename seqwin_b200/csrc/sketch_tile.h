@@ -53,6 +53,7 @@ struct SketchParams {
     unsigned long long* tile_count;   // [n_tiles] minimizers emitted by each tile
     unsigned long long* tile_slot;    // [n_tiles] first slot of each tile
     unsigned int* tile_counter;       // ticket dispenser
+    const TetraTable* tetra;          // 4-base warm-up tables (device global)
     RollTable table;
 };
 
@@ -114,19 +115,53 @@ SW_HD uint32_t base_at(const uint32_t* W, uint64_t p)
 // k-mers starting at record position p0: k warm-up steps, then C1-1 rolling steps.  With PREFIX
 // it also tracks the running rightmost argmin of its chunk (tile-local index, base j0) into pidx
 // and returns the chunk minimum.
+SW_HD uint64_t tetra_load(const uint64_t* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const unsigned long long*>(p));
+#else
+    return *p;
+#endif
+}
+
+// fwd / rev hash of the k-mer at record position p0, four bases per table step (TetraTable).
+SW_HD void seed_kmer(const uint32_t* W, uint64_t p0, uint32_t k, const RollEntry* tab, const TetraTable* tt,
+                     uint64_t* fwd_out, uint64_t* rev_out)
+{
+    const uint32_t G = k >> 2, rem = k & 3;
+    uint64_t fwd = 0, rev = 0;
+    for (uint32_t m = 0; 4 * m < G; ++m) {
+        const uint32_t x = fetch16(W, p0 + 16 * m);
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b)
+            if (4 * m + b < G) fwd = srol4(fwd) ^ tetra_load(&tt->fwd4[(x >> (8 * b)) & 255u]);
+    }
+    if (rem) {
+        const uint32_t x = fetch16(W, p0 + 4 * (uint64_t)G);
+        for (uint32_t j = 0; j < rem; ++j) fwd = srol1(fwd) ^ tab[16 + ((x >> (2 * j)) & 3u)].f;
+        for (uint32_t j = rem; j-- > 0;) rev = srol1(rev) ^ tab[16 + (3u - ((x >> (2 * j)) & 3u))].f;
+    }
+    for (uint32_t m = (G + 3) / 4; m-- > 0;) {
+        const uint32_t x = fetch16(W, p0 + 16 * m);
+#pragma unroll
+        for (uint32_t b = 4; b-- > 0;)
+            if (4 * m + b < G) rev = srol4(rev) ^ tetra_load(&tt->rev4[(x >> (8 * b)) & 255u]);
+    }
+    *fwd_out = fwd;
+    *rev_out = rev;
+}
+
+// Fast path: the whole tile lies in one run of hashable bases.  Thread hashes C1 consecutive
+// k-mers starting at record position p0: a table-driven seed of the first k-mer, then C1-1 rolling
+// steps.  With PREFIX it also tracks the running rightmost argmin of its chunk (tile-local index,
+// base j0) into pidx and returns the chunk minimum.
 template <int C1, bool PREFIX>
-SW_HD void hash_chunk_fast(const uint32_t* W, uint64_t p0, uint32_t k, const RollEntry* tab,
+SW_HD void hash_chunk_fast(const uint32_t* W, uint64_t p0, uint32_t k, const RollEntry* tab, const TetraTable* tt,
                            uint64_t* h0_out, uint16_t* pidx_out, uint32_t j0, uint64_t* min_h,
                            uint32_t* min_i)
 {
-    uint64_t fwd = 0, rev = 0;
-    for (uint32_t i = 0; i < k; i += 16) {
-        const uint32_t x = fetch16(W, p0 + i);
-        const uint32_t m = k - i;
-#pragma unroll
-        for (int s = 0; s < 16; ++s)
-            if ((uint32_t)s < m) roll_step(fwd, rev, tab[16 + ((x >> (2 * s)) & 3u)]);
-    }
+    uint64_t fwd, rev;
+    seed_kmer(W, p0, k, tab, tt, &fwd, &rev);
     uint64_t bh = fwd + rev;
     uint32_t bi = j0;
     h0_out[0] = bh;
@@ -147,7 +182,7 @@ SW_HD void hash_chunk_fast(const uint32_t* W, uint64_t p0, uint32_t k, const Rol
                 const uint64_t h = fwd + rev;
                 h0_out[n] = h;
                 if (PREFIX) {
-                    if (h <= bh) { bh = h; bi = j0 + n; }
+                    take_if_le(h, j0 + n, bh, bi);
                     pidx_out[n] = (uint16_t)bi;
                 }
             }
@@ -197,7 +232,7 @@ SW_HD void phase1_hash(int tid, const SketchParams& P, const Tile& T, const Tile
         // reads (and stores into the padded tail of h0) may run past n_kmers; the packed
         // stream has kTailPadWords of slack and window evaluation never looks there
         const uint64_t p0 = (uint64_t)pcs[0].pos + ((uint64_t)T.e0 + j0 - pcs[0].kidx);
-        hash_chunk_fast<C1, false>(W, p0, P.k, S.tab, S.h0 + j0, nullptr, j0, nullptr, nullptr);
+        hash_chunk_fast<C1, false>(W, p0, P.k, S.tab, P.tetra, S.h0 + j0, nullptr, j0, nullptr, nullptr);
     } else {
         const uint32_t j1 = j0 + C1 < T.n_kmers ? j0 + C1 : T.n_kmers;
         hash_range_generic(W, pcs, T.e0, j0, j1, P.k, S.tab, S.h0);
@@ -390,7 +425,7 @@ SW_HD void fastA_hash_prefix(int tid, const SketchParams& P, const Tile& T, cons
     uint32_t bi;
     if (T.n_pieces == 1) {
         const uint64_t p0 = (uint64_t)pcs[0].pos + ((uint64_t)T.e0 + j0 - pcs[0].kidx);
-        hash_chunk_fast<C1, true>(W, p0, P.k, S.tab, S.h0 + j0, S.pidx + j0, j0, &bh, &bi);
+        hash_chunk_fast<C1, true>(W, p0, P.k, S.tab, P.tetra, S.h0 + j0, S.pidx + j0, j0, &bh, &bi);
     } else {
         const uint32_t j1 = j0 + C1 < T.n_kmers ? j0 + C1 : T.n_kmers;
         hash_range_generic(W, pcs, T.e0, j0, j1, P.k, S.tab, S.h0);

@@ -45,6 +45,9 @@ static void emulate(const sw_batch& b, uint32_t k, uint32_t w, std::vector<uint6
     P.rec_base = 0;
     P.h1_mult = h1_multiplier(k);
     P.table = make_roll_table(k);
+    static TetraTable tetra;
+    make_tetra_table(tetra);
+    P.tetra = &tetra;
     std::vector<uint64_t> ukeys(plan.n_windows, 0), uvals(plan.n_windows, 0);
     std::vector<unsigned long long> tile_count(P.n_tiles, 0), tile_slot(P.n_tiles, 0);
     P.out_key = ukeys.data();
