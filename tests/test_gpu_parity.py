@@ -205,6 +205,23 @@ def test_sketch_stream_matches_oracle(kw):
     assert np.array_equal(rec, orr) and np.array_equal(pos, op) and np.array_equal(h1, oh)
 
 
+def test_low_complexity_overflows_the_density_estimate():
+    """Homopolymer / short-period input emits a minimizer for (almost) every window, far above the
+    2/(w+1) density the output buffer is sized for: the sketch must re-run with the exact size."""
+    rng = np.random.default_rng(5)
+    rand = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 50_000)].tobytes()
+    seqs = [b"A" * 400_000 + rand + b"AC" * 150_000, rand + b"T" * 250_000]
+    for k, w in [(21, 200), (15, 33)]:
+        h1, pos, rec = _dev_sketch(seqs, k, w)
+        H, P, R = [], [], []
+        for r, s in enumerate(seqs):
+            h, p = O.minimize(s, k, w)
+            H.append(h), P.append(p), R.append(np.full(len(h), r, np.uint32))
+        assert len(h1) == sum(len(x) for x in H) > 700_000
+        assert np.array_equal(h1, np.concatenate(H)) and np.array_equal(pos, np.concatenate(P))
+        assert np.array_equal(rec, np.concatenate(R))
+
+
 def test_window_too_large_fails_loudly():
     with pytest.raises(RuntimeError, match="windowsize"):
         _dev_sketch([b"ACGT" * 100], 21, 40_000)
