@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <unordered_map>
 
 #include "device.h"
 #include "ingest.h"
@@ -60,7 +61,8 @@ int sm_count()
     return g_sm_count;
 }
 
-void* alloc_host(size_t bytes, bool* pinned)
+namespace {
+void* raw_alloc_host(size_t bytes, bool* pinned)
 {
     std::call_once(g_init_flag, do_init);
     void* p = nullptr;
@@ -72,10 +74,37 @@ void* alloc_host(size_t bytes, bool* pinned)
     *pinned = false;  // host-only tooling (no device): pageable memory, nothing will be copied
     return aligned_alloc(64, ((bytes ? bytes : 1) + 63) / 64 * 64);
 }
-void free_host(void* p, bool pinned)
+void raw_free_host(void* p, bool pinned)
 {
     if (pinned) cudaFreeHost(p);
     else free(p);
+}
+std::mutex g_batch_mu;
+std::unordered_map<void*, HostBuf> g_batch_bufs;  // packed batches drawn from the pinned pool
+}  // namespace
+
+// Packed batches (ingest.cpp) live in recycled pinned buffers too: page-locking hundreds of MB per
+// call would cost more than parsing the FASTA.
+void* alloc_host(size_t bytes, bool* pinned)
+{
+    HostBuf b = host_pool_get(bytes ? bytes : 1);
+    *pinned = b.pinned;
+    std::lock_guard<std::mutex> lk(g_batch_mu);
+    g_batch_bufs[b.p] = b;
+    return b.p;
+}
+void free_host(void* p, bool pinned)
+{
+    (void)pinned;
+    HostBuf b;
+    {
+        std::lock_guard<std::mutex> lk(g_batch_mu);
+        auto it = g_batch_bufs.find(p);
+        if (it == g_batch_bufs.end()) return;
+        b = it->second;
+        g_batch_bufs.erase(it);
+    }
+    host_pool_put(b);
 }
 
 namespace {
@@ -193,7 +222,7 @@ HostBuf host_pool_get(size_t bytes)
     }
     HostBuf b;
     b.bytes = bytes + bytes / 8 + 4096;
-    b.p = alloc_host(b.bytes, &b.pinned);
+    b.p = raw_alloc_host(b.bytes, &b.pinned);
     if (!b.p) fail_runtime("host allocation of graph export buffer failed");
     return b;
 }
@@ -205,7 +234,7 @@ void host_pool_put(HostBuf& b)
         g_pool_cached += b.bytes;
         g_pool_free.push_back(b);
     } else {
-        free_host(b.p, b.pinned);
+        raw_free_host(b.p, b.pinned);
     }
     b = HostBuf{};
 }

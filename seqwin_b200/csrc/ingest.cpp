@@ -8,11 +8,15 @@
 #include "ingest.h"
 
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <exception>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -50,10 +54,33 @@ struct AsmPacked {
     size_t n_bases = 0;
 };
 
+#if defined(__x86_64__)
+// 16 ASCII bases -> one packed word, or false if any byte is not A/C/G/T/U (either case).
+// code = ((c >> 1) ^ (c >> 2)) & 3 maps A,C,G,T/U (and lower case) to 0,1,2,3.
+__attribute__((target("ssse3"))) inline bool pack16_ssse3(const unsigned char* p, uint32_t* word)
+{
+    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+    const __m128i lc = _mm_or_si128(v, _mm_set1_epi8(0x20));
+    __m128i ok = _mm_or_si128(_mm_cmpeq_epi8(lc, _mm_set1_epi8('a')), _mm_cmpeq_epi8(lc, _mm_set1_epi8('c')));
+    ok = _mm_or_si128(ok, _mm_cmpeq_epi8(lc, _mm_set1_epi8('g')));
+    ok = _mm_or_si128(ok, _mm_cmpeq_epi8(lc, _mm_set1_epi8('t')));
+    ok = _mm_or_si128(ok, _mm_cmpeq_epi8(lc, _mm_set1_epi8('u')));
+    if (_mm_movemask_epi8(ok) != 0xFFFF) return false;
+    const __m128i code = _mm_and_si128(_mm_xor_si128(_mm_srli_epi16(v, 1), _mm_srli_epi16(v, 2)), _mm_set1_epi8(3));
+    const __m128i t = _mm_maddubs_epi16(code, _mm_set1_epi16(0x0401));   // 2 bases per 16-bit lane
+    const __m128i u = _mm_madd_epi16(t, _mm_set1_epi32(0x00100001));     // 4 bases per 32-bit lane
+    const __m128i g = _mm_shuffle_epi8(u, _mm_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
+    *word = (uint32_t)_mm_cvtsi128_si32(g);
+    return true;
+}
+const bool kHaveSsse3 = __builtin_cpu_supports("ssse3");
+#endif
+
 // Streaming packer for one record.
 struct RecordPacker {
     AsmPacked& a;
-    uint32_t acc = 0;
+    uint64_t acc = 0;   // pending bases, `fill` of them (2 bits each)
+    uint32_t fill = 0;
     uint64_t cnt = 0;  // bases so far (64-bit so that > u32 records are detected, build.cpp:136)
     uint32_t n_inv = 0;
     bool open = false;
@@ -64,12 +91,20 @@ struct RecordPacker {
     {
         a.ids.push_back(std::move(id));
         a.rec_word_off.push_back(a.words.size());
-        acc = 0; cnt = 0; n_inv = 0; open = true;
+        acc = 0; fill = 0; cnt = 0; n_inv = 0; open = true;
     }
     inline void push_code(uint32_t c)
     {
-        acc |= c << (2 * (cnt & 15));
-        if ((++cnt & 15) == 0) { a.words.push_back(acc); acc = 0; }
+        acc |= (uint64_t)c << (2 * fill);
+        ++cnt;
+        if (++fill == 16) { a.words.push_back((uint32_t)acc); acc = 0; fill = 0; }
+    }
+    inline void push_word16(uint32_t w16)  // 16 hashable bases at once
+    {
+        acc |= (uint64_t)w16 << (2 * fill);
+        a.words.push_back((uint32_t)acc);
+        acc >>= 32;
+        cnt += 16;
     }
     inline void push_invalid()
     {
@@ -77,7 +112,7 @@ struct RecordPacker {
         else { a.inv_start.push_back((uint32_t)cnt); a.inv_len.push_back(1); ++n_inv; }
         push_code(0);
     }
-    void append(const unsigned char* p, size_t n)
+    inline void append_bytes(const unsigned char* p, size_t n)
     {
         for (size_t i = 0; i < n; ++i) {
             const uint8_t c = kClass.t[p[i]];
@@ -85,13 +120,27 @@ struct RecordPacker {
             else if (c == 4) push_invalid();
         }
     }
+    void append(const unsigned char* p, size_t n)
+    {
+        size_t i = 0;
+#if defined(__x86_64__)
+        if (kHaveSsse3) {
+            for (; i + 16 <= n; i += 16) {
+                uint32_t w16;
+                if (pack16_ssse3(p + i, &w16)) push_word16(w16);
+                else append_bytes(p + i, 16);
+            }
+        }
+#endif
+        append_bytes(p + i, n - i);
+    }
     void end(const std::string& path)
     {
         if (!open) return;
         if (cnt > 0xFFFFFFFFull)
             fail_runtime("Sequence length exceeds uint32 range for record " + a.ids.back() +
                          " in assembly " + path);
-        if (cnt & 15) a.words.push_back(acc);
+        if (fill) a.words.push_back((uint32_t)acc);
         while (a.words.size() % kRecordAlignWords) a.words.push_back(0);
         a.rec_len.push_back((uint32_t)cnt);
         a.rec_inv_cnt.push_back(n_inv);
@@ -106,18 +155,31 @@ bool ends_with(const std::string& s, const char* suf)
     return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
 }
 
-std::vector<char> slurp(const std::string& path)
+// Whole file in memory (uninitialised buffer: no zero fill before the read).
+struct FileBuf {
+    std::unique_ptr<char[]> p;
+    size_t n = 0, cap = 0;
+    void reserve(size_t c)
+    {
+        if (c <= cap) return;
+        std::unique_ptr<char[]> q(new char[c]);
+        if (n) memcpy(q.get(), p.get(), n);
+        p = std::move(q);
+        cap = c;
+    }
+};
+
+FileBuf slurp(const std::string& path)
 {
-    std::vector<char> buf;
+    FileBuf buf;
     if (ends_with(path, ".gz")) {
         gzFile f = gzopen(path.c_str(), "rb");
         if (!f) fail_runtime("Unable to open gzip FASTA: " + path);
         gzbuffer(f, 1 << 20);
-        size_t n = 0;
-        buf.resize(1 << 22);
+        buf.reserve(1 << 22);
         for (;;) {
-            if (buf.size() - n < (1 << 20)) buf.resize(buf.size() * 2);
-            int got = gzread(f, buf.data() + n, 1 << 20);
+            if (buf.cap - buf.n < (1 << 20)) buf.reserve(buf.cap * 2);
+            int got = gzread(f, buf.p.get() + buf.n, 1 << 20);
             if (got < 0) {
                 int errnum = 0;
                 const char* msg = gzerror(f, &errnum);
@@ -126,24 +188,21 @@ std::vector<char> slurp(const std::string& path)
                 fail_runtime(m);
             }
             if (got == 0) break;
-            n += (size_t)got;
+            buf.n += (size_t)got;
         }
         gzclose(f);
-        buf.resize(n);
     } else {
         FILE* f = fopen(path.c_str(), "rb");
         if (!f) fail_runtime("Unable to open FASTA: " + path);
         fseek(f, 0, SEEK_END);
-        long sz = ftell(f);
+        const long sz = ftell(f);
         fseek(f, 0, SEEK_SET);
-        if (sz > 0) {
-            buf.resize((size_t)sz);
-            size_t got = fread(buf.data(), 1, (size_t)sz, f);
-            buf.resize(got);
-        } else {  // unseekable / special file: stream it
-            char tmp[1 << 16];
-            size_t got;
-            while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+        buf.reserve(sz > 0 ? (size_t)sz + 1 : (size_t)1 << 16);
+        for (;;) {  // also copes with special files whose size is unknown
+            if (buf.cap == buf.n) buf.reserve(buf.cap * 2);
+            const size_t got = fread(buf.p.get() + buf.n, 1, buf.cap - buf.n, f);
+            if (got == 0) break;
+            buf.n += got;
         }
         fclose(f);
     }
@@ -155,9 +214,9 @@ std::vector<char> slurp(const std::string& path)
 // first whitespace, every other line is sequence with whitespace bytes dropped.
 void parse_fasta(const std::string& path, AsmPacked& out)
 {
-    const std::vector<char> buf = slurp(path);
-    const unsigned char* p = (const unsigned char*)buf.data();
-    const size_t n = buf.size();
+    const FileBuf buf = slurp(path);
+    const unsigned char* p = (const unsigned char*)buf.p.get();
+    const size_t n = buf.n;
     out.words.reserve(n / 16 + 64);
     RecordPacker rp(out);
     bool have = false;
