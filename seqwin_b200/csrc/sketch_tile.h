@@ -476,10 +476,16 @@ SW_HD bool fast_chunk_active(int c, const SketchParams& P, const Tile& T, const 
     return S.first_a[c] != S.first_a[c + 1];
 }
 
-// B2: full evaluation of chunk c; returns the number of minimizers its windows emit
-template <int NT, int C1>
-SW_HD uint32_t fastB2_windows(uint32_t c, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
+// B2: evaluation of the windows n in [sub*SUBW, (sub+1)*SUBW) of active chunk c, right to left;
+// returns the number of minimizers they emit.  An active chunk is split over NSUB threads so that
+// the whole CTA (not one or two warps) works through the few active chunks; each thread first scans
+// the part of the chunk to its right for the suffix minimum and evaluates the window just above its
+// range (whose selection it needs to decide whether its own top window emits).
+template <int NT, int C1, int NSUB>
+SW_HD uint32_t fastB2_windows(uint32_t c, uint32_t sub, const SketchParams& P, const Tile& T, const TileSmem& S,
+                              FastState& st)
 {
+    constexpr int SUBW = (C1 + NSUB - 1) / NSUB;
     const uint32_t w = P.w;
     const uint32_t n_eval = T.n_kmers - w + 1;
     const uint32_t j0 = c * C1;
@@ -499,40 +505,50 @@ SW_HD uint32_t fastB2_windows(uint32_t c, const SketchParams& P, const Tile& T, 
         const uint64_t h = S.cm_h[c + q];
         if (!lo_valid || h <= m_lo_h) { m_hi_h = h; m_hi_i = S.cm_i[c + q]; }
     }
-    uint64_t sh = 0, mask = 0;
-    uint32_t si = 0, prev_a = 0xFFFFFFFFu, a_top = 0xFFFFFFFFu;
-#pragma unroll
-    for (int n = C1 - 1; n >= 0; --n) {
-        const uint32_t a = j0 + n;
-        const uint64_t h = S.h0[a];
-        if (n == C1 - 1 || h < sh) { sh = h; si = a; }
-        if (a < n_eval) {
-            uint64_t rh = sh;
-            uint32_t ri = si;
-            if ((uint32_t)n + r >= (uint32_t)C1) {
-                if (m_hi_h <= rh) { rh = m_hi_h; ri = m_hi_i; }
-            } else {
-                if (lo_valid && m_lo_h <= rh) { rh = m_lo_h; ri = m_lo_i; }
-            }
-            const uint32_t pe = S.pidx[a + w - 1];
-            const uint64_t ph = S.h0[pe];
-            if (ph <= rh) { rh = ph; ri = pe; }
-            if (n == C1 - 1) {
-                a_top = ri;
-            } else if (a + 1 < n_eval && prev_a != ri) {
-                mask |= 1ULL << n;
-                S.amin[a + 1] = (uint16_t)prev_a;
-            }
-            prev_a = ri;
+    // rightmost minimum of window j0 + n given the suffix minimum (sh, si) of the chunk from n on
+    auto eval = [&](uint32_t n, uint64_t sh, uint32_t si) -> uint32_t {
+        uint64_t rh = sh;
+        uint32_t ri = si;
+        if (n + r >= (uint32_t)C1) {
+            if (m_hi_h <= rh) { rh = m_hi_h; ri = m_hi_i; }
+        } else {
+            if (lo_valid && m_lo_h <= rh) { rh = m_lo_h; ri = m_lo_i; }
         }
+        const uint32_t pe = S.pidx[j0 + n + w - 1];
+        const uint64_t ph = S.h0[pe];
+        if (ph <= rh) { rh = ph; ri = pe; }
+        return ri;
+    };
+    const uint32_t n_lo = sub * SUBW;
+    const uint32_t n_top = n_lo + SUBW < (uint32_t)C1 ? n_lo + SUBW : (uint32_t)C1;  // one past this thread's range
+    uint64_t sh = 0, mask = 0;
+    uint32_t si = 0, prev_a = 0xFFFFFFFFu;
+    bool have_suffix = false;
+    // suffix minimum of the chunk to the right of the range; strict '<' keeps the right-hand element
+    for (uint32_t n = C1; n-- > n_top;) {
+        const uint64_t h = S.h0[j0 + n];
+        if (!have_suffix || h < sh) { sh = h; si = j0 + n; have_suffix = true; }
     }
-    // first window of the next chunk (its A is known from B1)
-    const uint32_t a_b = j0 + C1;
-    if (a_b < n_eval) {
-        const uint32_t nxt = S.first_a[c + 1];
-        if (nxt != a_top) {
-            mask |= 1ULL << (C1 - 1);
-            S.amin[a_b] = (uint16_t)nxt;
+    if (n_top < (uint32_t)C1) {
+        if (j0 + n_top < n_eval) prev_a = eval(n_top, sh, si);           // window just above the range
+    } else if (j0 + C1 < n_eval) {
+        prev_a = S.first_a[c + 1];                                        // next chunk's first window (B1)
+    }
+#pragma unroll
+    for (int i = SUBW - 1; i >= 0; --i) {
+        const uint32_t n = n_lo + (uint32_t)i;
+        if (n < n_top) {
+            const uint32_t a = j0 + n;
+            const uint64_t h = S.h0[a];
+            if (!have_suffix || h < sh) { sh = h; si = a; have_suffix = true; }
+            if (a < n_eval) {
+                const uint32_t ri = eval(n, sh, si);
+                if (a + 1 < n_eval && prev_a != ri) {   // window a + 1 selects a new k-mer
+                    mask |= 1ULL << n;
+                    S.amin[a + 1] = (uint16_t)prev_a;
+                }
+                prev_a = ri;
+            }
         }
     }
     // minimizer.cpp:45: a selected k-mer whose h0 is 2^64-1 is never emitted
@@ -549,7 +565,7 @@ SW_HD uint32_t fastB2_windows(uint32_t c, const SketchParams& P, const Tile& T, 
     st.mask = mask;
     st.chunk = c;
     st.a_first = prev_a;
-    st.f0 = (c == 0 && T.first != 0 && S.h0[prev_a] != ~0ULL) ? 1u : 0u;
+    st.f0 = (c == 0 && sub == 0 && T.first != 0 && S.h0[prev_a] != ~0ULL) ? 1u : 0u;
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__popcll(mask) + st.f0;
 #else
