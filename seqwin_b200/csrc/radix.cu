@@ -90,61 +90,53 @@ __global__ void __launch_bounds__(kRadix) radix_offsets_kernel(unsigned long lon
     if (threadIdx.x == 0) max_bin[blockIdx.x] = gmx;
 }
 
+// Shared state of one onesweep CTA.
 template <int NT, int ITEMS>
-__global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
-    const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
-    uint32_t* __restrict__ vout, uint64_t n, int shift, const unsigned long long* __restrict__ goff,
-    unsigned long long* status, unsigned int* ticket)
+struct OnesweepSmem {
+    uint32_t whist[NT / 32][kRadix];    // per-warp digit counts -> tile-sorted position of the warp's first item
+    unsigned long long dbase[kRadix];    // global slot of tile-sorted position 0, per digit
+    uint32_t scan[NT / 32];
+    uint32_t tile;
+};
+
+// One tile of one pass.  FULL = the tile holds NT * ITEMS items (no bounds checks).
+template <int NT, int ITEMS, bool FULL>
+__device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint64_t* s_buf, uint32_t* s_vin,
+                                              const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
+                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+                                              uint32_t n_valid, uint32_t tile, int shift,
+                                              const unsigned long long* __restrict__ goff, unsigned long long* status)
 {
     constexpr int NW = NT / 32;
-    constexpr int TILE = NT * ITEMS;
-    static_assert(ITEMS % 4 == 0 && NT >= kRadix, "one thread per digit");
-    __shared__ uint32_t whist[NW][kRadix];       // per-warp digit counts -> per-warp offsets inside the tile
-    __shared__ unsigned long long dbase[kRadix];  // global slot of tile-sorted position 0 of each digit run
-    extern __shared__ __align__(16) unsigned char radix_smem[];
-    uint64_t* s_buf = reinterpret_cast<uint64_t*>(radix_smem);            // [TILE] tile-sorted staging (keys, then values)
-    uint32_t* s_vin = reinterpret_cast<uint32_t*>(radix_smem + (size_t)TILE * 8);  // [TILE] prefetched input values
-    __shared__ uint32_t s_scan[NW];
-    __shared__ uint32_t s_tile;
-
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < NW * kRadix; i += NT) (&whist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t tile_base = (uint64_t)tile * TILE;
-    const uint64_t wbase = tile_base + (uint64_t)wid * (32 * ITEMS);
-    const uint32_t n_valid = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
+    const uint32_t wofs = (uint32_t)wid * (32 * ITEMS) + lane;  // this thread's first item inside the tile
+    const uint64_t* kin_t = kin + wofs;                         // (kin / vin already point at the tile)
+    const uint32_t* vin_t = vin + wofs;
 
     uint64_t key[ITEMS];
     uint32_t rank[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
-        key[i] = idx < n ? kin[idx] : ~0ULL;
-    }
+    for (int i = 0; i < ITEMS; ++i) key[i] = (FULL || wofs + i * 32 < n_valid) ? kin_t[i * 32] : ~0ULL;
     // the values are not needed before the keys have been written out: fetch them into shared
     // memory asynchronously (cp.async), each thread into its own slots
-    uint32_t* my_vin = s_vin + wid * (32 * ITEMS) + lane;
+    uint32_t* my_vin = s_vin + wofs;
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
-        if (idx < n) __pipeline_memcpy_async(my_vin + i * 32, vin + idx, 4);
-    }
+    for (int i = 0; i < ITEMS; ++i)
+        if (FULL || wofs + i * 32 < n_valid) __pipeline_memcpy_async(my_vin + i * 32, vin_t + i * 32, 4);
     __pipeline_commit();
 
     // warp-local stable ranking: items of one warp are ordered (item, lane)
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const bool valid = wbase + (uint64_t)i * 32 + lane < n;
+        const bool valid = FULL || wofs + i * 32 < n_valid;
         const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x1FFu);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader && valid) {
-            old = whist[wid][d];
-            whist[wid][d] = old + __popc(peers);
+            old = sm.whist[wid][d];
+            sm.whist[wid][d] = old + __popc(peers);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[i] = old + __popc(peers & lt_mask);
@@ -158,8 +150,8 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     if (tid < kRadix) {
 #pragma unroll
         for (int wv = 0; wv < NW; ++wv) {
-            const uint32_t t = whist[wv][tid];
-            whist[wv][tid] = run;
+            const uint32_t t = sm.whist[wv][tid];
+            sm.whist[wv][tid] = run;
             run += t;
         }
     }
@@ -169,19 +161,19 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
     }
-    if (lane == 31) s_scan[wid] = inc;
+    if (lane == 31) sm.scan[wid] = inc;
     __syncthreads();
     uint32_t digit_first = inc - run;
 #pragma unroll
     for (int i = 0; i < NW; ++i)
-        if (i < wid) digit_first += s_scan[i];
+        if (i < wid) digit_first += sm.scan[i];
     unsigned long long* my_status = status + (uint64_t)tile * kRadix + tid;
     if (tid < kRadix) {
         // publish the tile's digit count right away; the look-back itself runs after the keys have
         // been staged, when the predecessors have most likely published theirs
         st_relaxed(my_status, (tile == 0 ? kStInc : kStAgg) | run);
 #pragma unroll
-        for (int wv = 0; wv < NW; ++wv) whist[wv][tid] += digit_first;  // now: tile-sorted position
+        for (int wv = 0; wv < NW; ++wv) sm.whist[wv][tid] += digit_first;  // now: tile-sorted position
     }
     __syncthreads();
 
@@ -189,10 +181,9 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     // (rank[] becomes the item's tile-sorted position)
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const bool valid = wbase + (uint64_t)i * 32 + lane < n;
-        const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
-        if (valid) {
-            rank[i] += whist[wid][d];
+        if (FULL || wofs + i * 32 < n_valid) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+            rank[i] += sm.whist[wid][d];
             s_buf[rank[i]] = key[i];
         }
     }
@@ -209,7 +200,7 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
             }
             st_relaxed(my_status, kStInc | (before + run));
         }
-        dbase[tid] = goff[tid] + before - digit_first;
+        sm.dbase[tid] = goff[tid] + before - digit_first;
     }
     __syncthreads();
     uint32_t dig[ITEMS / 4];  // digits of the tile-sorted items this thread writes, 4 per register
@@ -217,11 +208,11 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     for (int i = 0; i < ITEMS; ++i) {
         const uint32_t p = (uint32_t)i * NT + tid;
         if ((i & 3) == 0) dig[i >> 2] = 0;
-        if (p < n_valid) {
+        if (FULL || p < n_valid) {
             const uint64_t k2 = s_buf[p];
             const uint32_t d = (uint32_t)(k2 >> shift) & (kRadix - 1);
             dig[i >> 2] |= d << (8 * (i & 3));
-            kout[dbase[d] + p] = k2;
+            kout[sm.dbase[d] + p] = k2;
         }
     }
     __pipeline_wait_prior(0);
@@ -229,16 +220,43 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     // values take the same route through the (re-used) staging buffer
     uint32_t* s_val = reinterpret_cast<uint32_t*>(s_buf);
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
-        if (idx < n) s_val[rank[i]] = my_vin[i * 32];
-    }
+    for (int i = 0; i < ITEMS; ++i)
+        if (FULL || wofs + i * 32 < n_valid) s_val[rank[i]] = my_vin[i * 32];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const uint32_t p = (uint32_t)i * NT + tid;
-        if (p < n_valid) vout[dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_val[p];
+        if (FULL || p < n_valid) vout[sm.dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_val[p];
     }
+}
+
+template <int NT, int ITEMS>
+__global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
+    const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
+    uint32_t* __restrict__ vout, uint64_t n, int shift, const unsigned long long* __restrict__ goff,
+    unsigned long long* status, unsigned int* ticket)
+{
+    constexpr int NW = NT / 32;
+    constexpr int TILE = NT * ITEMS;
+    static_assert(ITEMS % 4 == 0 && NT >= kRadix, "one thread per digit");
+    __shared__ OnesweepSmem<NT, ITEMS> sm;
+    extern __shared__ __align__(16) unsigned char radix_smem[];
+    uint64_t* s_buf = reinterpret_cast<uint64_t*>(radix_smem);                     // [TILE] tile-sorted staging
+    uint32_t* s_vin = reinterpret_cast<uint32_t*>(radix_smem + (size_t)TILE * 8);  // [TILE] prefetched values
+
+    const int tid = threadIdx.x;
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < NW * kRadix; i += NT) (&sm.whist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const uint32_t n_valid = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
+    if (n_valid == (uint32_t)TILE)
+        onesweep_tile<NT, ITEMS, true>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
+                                       shift, goff, status);
+    else
+        onesweep_tile<NT, ITEMS, false>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
+                                        shift, goff, status);
 }
 
 }  // namespace
