@@ -72,6 +72,36 @@ __device__ __forceinline__ uint32_t round_rank(bool flag, uint32_t* s_warp, uint
     return r;
 }
 
+// Ordered ranks of kRounds flags per thread (item r of thread t is element r * kNT + t of the
+// block) with ONE barrier: ballots of all rounds first, then every thread sums the (round, warp)
+// counts that precede it.  rank[r] = number of set flags before the item in block order.
+__device__ __forceinline__ void block_ranks(const bool (&flag)[kRounds], uint32_t (&rank)[kRounds],
+                                            uint32_t (*s_cnt)[kNT / 32])
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t prefix[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint32_t ballot = __ballot_sync(0xffffffffu, flag[r]);
+        prefix[r] = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[r][wid] = __popc(ballot);
+    }
+    __syncthreads();
+    uint32_t running = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < kNT / 32; ++i) {
+            const uint32_t t = s_cnt[r][i];
+            if (i < wid) before += t;
+            total += t;
+        }
+        rank[r] = running + before + prefix[r];
+        running += total;
+    }
+}
+
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -115,31 +145,37 @@ __global__ void __launch_bounds__(kNT) node_write_kernel(
     uint64_t n, const unsigned long long* __restrict__ block_off, sw_kmer* __restrict__ kmers,
     sw_node* __restrict__ nodes, uint32_t* __restrict__ rank_of_stream)
 {
-    __shared__ uint32_t s_warp[kNT / 32];
+    __shared__ uint32_t s_cnt[kRounds][kNT / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
     const unsigned long long off = block_off[blockIdx.x];
-    uint32_t running = 0;
-#pragma unroll 1
+    // all loads of the block's items are issued before anything depends on them
+    uint64_t key[kRounds], val[kRounds];
+    uint32_t src[kRounds], rank[kRounds];
+    bool flag[kRounds];
+#pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
-        const bool in = j < n;
-        uint64_t key = 0;
-        bool flag = false;
-        if (in) {
-            key = ks[j];
-            flag = (j == 0) || key != ks[j - 1];
-        }
-        const uint32_t excl = round_rank(flag, s_warp, running);
-        if (in) {
+        key[r] = j < n ? ks[j] : 0;
+        src[r] = j < n ? idx[j] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        val[r] = j < n ? stream_vals[src[r]] : 0;
+        flag[r] = j < n && (j == 0 || key[r] != ks[j - 1]);
+    }
+    block_ranks(flag, rank, s_cnt);
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        if (j < n) {
             // node rank of element j = (#run starts up to and including j) - 1
-            const unsigned long long nr = off + excl + (flag ? 1u : 0u) - 1u;
-            const uint32_t src = idx[j];
-            const uint64_t v = stream_vals[src];
-            kmers[j] = sw_kmer{(uint32_t)v, (uint32_t)(v >> 32)};
-            rank_of_stream[src] = (uint32_t)nr;
-            if (flag) {
+            const unsigned long long nr = off + rank[r] + (flag[r] ? 1u : 0u) - 1u;
+            kmers[j] = sw_kmer{(uint32_t)val[r], (uint32_t)(val[r] >> 32)};
+            rank_of_stream[src[r]] = (uint32_t)nr;
+            if (flag[r]) {
                 sw_node* nd = nodes + nr;
-                nd->hash = key;
+                nd->hash = key[r];
                 nd->start = j;
                 nd->n_tar = 0;
                 nd->n_neg = 0;
@@ -173,26 +209,31 @@ __global__ void __launch_bounds__(kNT) edge_write_kernel(
     const uint32_t* __restrict__ rec_asm, uint32_t rec_base, const unsigned long long* __restrict__ block_off,
     uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm)
 {
-    __shared__ uint32_t s_warp[kNT / 32];
+    __shared__ uint32_t s_cnt[kRounds][kNT / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
     const unsigned long long off = block_off[blockIdx.x];
-    uint32_t running = 0;
-#pragma unroll 1
+    bool flag[kRounds];
+    uint32_t rec[kRounds], rank[kRounds];
+#pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t i = base + (uint64_t)r * kNT + threadIdx.x;
-        bool flag = false;
-        uint32_t rec = 0;
+        flag[r] = false;
+        rec[r] = 0;
         if (i + 1 < n) {
-            rec = (uint32_t)(stream_vals[i] >> 32);
-            flag = rec == (uint32_t)(stream_vals[i + 1] >> 32);
+            rec[r] = (uint32_t)(stream_vals[i] >> 32);
+            flag[r] = rec[r] == (uint32_t)(stream_vals[i + 1] >> 32);
         }
-        const uint32_t excl = round_rank(flag, s_warp, running);
-        if (flag) {
+    }
+    block_ranks(flag, rank, s_cnt);
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t i = base + (uint64_t)r * kNT + threadIdx.x;
+        if (flag[r]) {
             uint32_t u = rank_of_stream[i], v = rank_of_stream[i + 1];
             if (v < u) { const uint32_t t = u; u = v; v = t; }
-            const unsigned long long slot = off + excl;
+            const unsigned long long slot = off + rank[r];
             ekey[slot] = ((uint64_t)u << 32) | v;
-            easm[slot] = rec_asm[rec - rec_base];
+            easm[slot] = rec_asm[rec[r] - rec_base];
         }
     }
 }
@@ -201,30 +242,35 @@ __global__ void __launch_bounds__(kNT) edge_final_kernel(
     const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ easm, uint64_t n,
     const unsigned long long* __restrict__ block_off, const sw_node* __restrict__ nodes, sw_edge* __restrict__ edges)
 {
-    __shared__ uint32_t s_warp[kNT / 32];
+    __shared__ uint32_t s_cnt[kRounds][kNT / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
     const unsigned long long off = block_off[blockIdx.x];
-    uint32_t running = 0;
-#pragma unroll 1
+    uint64_t key[kRounds];
+    bool new_pair[kRounds], new_asm[kRounds];
+    uint32_t rank[kRounds];
+#pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
-        const bool in = j < n;
-        uint64_t key = 0;
-        bool new_pair = false, new_asm = false;
-        if (in) {
-            key = ekey[j];
-            new_pair = (j == 0) || key != ekey[j - 1];
-            new_asm = new_pair || easm[j] != easm[j - 1];
+        key[r] = 0;
+        new_pair[r] = new_asm[r] = false;
+        if (j < n) {
+            key[r] = ekey[j];
+            new_pair[r] = (j == 0) || key[r] != ekey[j - 1];
+            new_asm[r] = new_pair[r] || easm[j] != easm[j - 1];
         }
-        const uint32_t excl = round_rank(new_pair, s_warp, running);
-        if (in) {
-            const unsigned long long e = off + excl + (new_pair ? 1u : 0u) - 1u;
-            if (new_pair) {
-                edges[e].first = nodes[(uint32_t)(key >> 32)].hash;
-                edges[e].second = nodes[(uint32_t)key].hash;
+    }
+    block_ranks(new_pair, rank, s_cnt);
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        if (j < n) {
+            const unsigned long long e = off + rank[r] + (new_pair[r] ? 1u : 0u) - 1u;
+            if (new_pair[r]) {
+                edges[e].first = nodes[(uint32_t)(key[r] >> 32)].hash;
+                edges[e].second = nodes[(uint32_t)key[r]].hash;
             }
             // weight was zeroed before the launch; one count per distinct assembly of the run
-            if (new_asm) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), 1ULL);
+            if (new_asm[r]) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), 1ULL);
         }
     }
 }

@@ -208,10 +208,10 @@ const KernelConfig kConfigs[] = {
     SW_CFG(128, 45),
     SW_CFG(256, 45),
     SW_CFG(256, 61),  // large windows (w up to ~15k)
-    SW_CFG(256, 17),
-    SW_CFG(128, 17),
+    SW_CFG(128, 27),
+    SW_CFG(128, 21),
     SW_CFG(256, 33),
-    SW_CFG(256, 25),
+    SW_CFG(96, 33),
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 constexpr int kLargeWindowConfig = 3;
