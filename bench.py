@@ -305,10 +305,18 @@ def main():
     sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     int_peak = 148 * 128 * sm_mhz * 1e6  # lane-ops/s at the clock seen under load
     int_alg = 45.0 * n_bases_local + 12.0 * s0.get("n_kmers_local", M)
-    roofline = {"bound": "hbm", "kernel": "sketch_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture, scaled by the
+    # algorithmic bytes when the workload differs from the captured one
+    traffic = None
+    tp = ROOT / "profiles" / "r1_sketch_traffic.json"
+    if tp.exists():
+        tj = json.loads(tp.read_text())
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * sketch_bytes / tj["algorithmic_bytes"]
+    roofline = {"bound": "hbm", "kernel": "sketch_fast_kernel<128,33>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sketch_bytes, "kernel_ms": sketch_ms,
-                "note": "sketch is INT32-pipe bound (SURVEY 8d): see int_roofline",
+                "note": "the sketch kernel is bound by the INT32 ALU pipe, not HBM (SURVEY 8d; ncu: ALU pipe 66 % busy, "
+                        "DRAM 1.4 %): see int_roofline and path",
                 "int_roofline": {"achieved_Tops": int_alg / (sketch_ms * 1e-3) / 1e12, "peak_Tops": int_peak / 1e12,
                                  "frac": int_alg / (sketch_ms * 1e-3) / int_peak,
                                  "model": "I_alg = 45*N + 12*M lane-ops; peak = 148 SM x 128 lanes x sm clock under load"},
