@@ -24,6 +24,91 @@ namespace sw {
 namespace {
 
 constexpr int kNT = 256;
+constexpr int kMergeVT = 8;  // outputs per thread in the merge kernel
+
+// ---- pairwise merge of sorted runs (merge path) ------------------------------------------------
+// Each rank's slice arrives sorted, so the owner merges P sorted runs in ceil(log2 P) rounds of
+// pairwise merges instead of re-sorting: one read + one write of the data per round.
+
+struct KeyIdx {
+    uint64_t key;  // node hash
+    uint64_t idx;  // index into the concatenated received nodes
+};
+struct LessKey {
+    __device__ __forceinline__ bool operator()(const KeyIdx& a, const KeyIdx& b) const { return a.key < b.key; }
+};
+struct LessEdge {
+    __device__ __forceinline__ bool operator()(const sw_edge& a, const sw_edge& b) const
+    {
+        return a.first < b.first || (a.first == b.first && a.second < b.second);
+    }
+};
+
+// number of elements taken from A among the first `diag` outputs of merge(A, B); ties take A first,
+// which keeps equal keys in source-rank order
+template <typename T, typename Less>
+__device__ __forceinline__ uint64_t merge_path(const T* __restrict__ A, uint64_t na, const T* __restrict__ B,
+                                               uint64_t nb, uint64_t diag, Less less)
+{
+    uint64_t lo = diag > nb ? diag - nb : 0, hi = diag < na ? diag : na;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (!less(B[diag - 1 - mid], A[mid])) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <typename T, typename Less>
+__global__ void __launch_bounds__(kNT) merge_pair_kernel(const T* __restrict__ A, uint64_t na, const T* __restrict__ B,
+                                                         uint64_t nb, T* __restrict__ out)
+{
+    Less less;
+    const uint64_t n = na + nb;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kMergeVT;
+    if (i0 >= n) return;
+    uint64_t a = merge_path(A, na, B, nb, i0, less);
+    uint64_t b = i0 - a;
+#pragma unroll
+    for (int t = 0; t < kMergeVT; ++t) {
+        if (i0 + t >= n) break;
+        const bool take_a = b >= nb || (a < na && !less(B[b], A[a]));
+        out[i0 + t] = take_a ? A[a] : B[b];
+        if (take_a) ++a; else ++b;
+    }
+}
+
+// Merge the runs [seg[i], seg[i+1]) of `src` pairwise until one run is left.  buf0 / buf1 are
+// scratch of the same total size; returns the buffer holding the result.
+template <typename T, typename Less>
+const T* merge_runs(const T* src, std::vector<unsigned long long> seg, T* buf0, T* buf1, cudaStream_t s, uint32_t* launches)
+{
+    const T* cur = src;
+    T* dst = buf0;
+    while (seg.size() > 2) {
+        std::vector<unsigned long long> next{seg.front()};
+        for (size_t i = 0; i + 1 < seg.size(); i += 2) {
+            const unsigned long long a0 = seg[i], a1 = seg[i + 1];
+            const unsigned long long b1 = i + 2 < seg.size() ? seg[i + 2] : a1;
+            const uint64_t na = a1 - a0, nb = b1 - a1, n = na + nb;
+            if (n) {
+                if (nb == 0 || na == 0) {
+                    SW_CUDA(cudaMemcpyAsync(dst + a0, cur + a0, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+                } else {
+                    const uint64_t threads = (n + kMergeVT - 1) / kMergeVT;
+                    merge_pair_kernel<T, Less><<<(uint32_t)((threads + kNT - 1) / kNT), kNT, 0, s>>>(cur + a0, na, cur + a1, nb,
+                                                                                                 dst + a0);
+                    SW_CUDA(cudaGetLastError());
+                    ++*launches;
+                }
+            }
+            next.push_back(b1);
+        }
+        seg.swap(next);
+        cur = dst;
+        dst = (dst == buf0) ? buf1 : buf0;
+    }
+    return cur;
+}
 
 __global__ void iota32_kernel(uint32_t* v, uint64_t n)
 {
@@ -31,9 +116,10 @@ __global__ void iota32_kernel(uint32_t* v, uint64_t n)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
 }
 
-// concatenated received nodes -> sort key (hash) and absolute source offset of the node's k-mers
+// concatenated received nodes -> (hash, index) merge records and the absolute source offset of each
+// node's k-mers
 __global__ void node_prepare_kernel(const sw_node* __restrict__ nodes, uint64_t n, const unsigned long long* __restrict__ seg,
-                                    uint32_t n_src, uint64_t* __restrict__ key, unsigned long long* __restrict__ abs_start)
+                                    uint32_t n_src, KeyIdx* __restrict__ rec, unsigned long long* __restrict__ abs_start)
 {
     // seg layout: [0, n_src] node offsets, then n_src received-k-mer offsets, then n_src sender k-mer bases
     const unsigned long long* node_off = seg;
@@ -43,28 +129,28 @@ __global__ void node_prepare_kernel(const sw_node* __restrict__ nodes, uint64_t 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t s = 0;
         while (s + 1 < n_src && node_off[s + 1] <= i) ++s;
-        key[i] = nodes[i].hash;
+        rec[i] = KeyIdx{nodes[i].hash, i};
         abs_start[i] = kmer_off[s] + (nodes[i].start - kmer_base[s]);
     }
 }
 
 // sorted order j -> (run start flag, k-mer count) as one packed u64: count in the low 40 bits,
 // flag in bit 40, so that ONE exclusive scan yields both the output k-mer offset and the node rank
-__global__ void node_pack_kernel(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
-                                 const sw_node* __restrict__ nodes, uint64_t n, unsigned long long* __restrict__ packed)
+__global__ void node_pack_kernel(const KeyIdx* __restrict__ sorted, const sw_node* __restrict__ nodes, uint64_t n,
+                                 unsigned long long* __restrict__ packed)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const sw_node nd = nodes[sidx[j]];
-        const unsigned long long flag = (j == 0 || skey[j] != skey[j - 1]) ? 1ULL : 0ULL;
+        const sw_node nd = nodes[sorted[j].idx];
+        const unsigned long long flag = (j == 0 || sorted[j].key != sorted[j - 1].key) ? 1ULL : 0ULL;
         packed[j] = (nd.stop - nd.start) | (flag << 40);
     }
 }
 
 // 8 lanes per received node segment (segments hold a handful of k-mers): copy its k-mers to the
 // merged position, fill merged nodes
-__global__ void node_merge_kernel(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
-                                  const sw_node* __restrict__ nodes, const unsigned long long* __restrict__ abs_start,
+__global__ void node_merge_kernel(const KeyIdx* __restrict__ sorted, const sw_node* __restrict__ nodes,
+                                  const unsigned long long* __restrict__ abs_start,
                                   const unsigned long long* __restrict__ scanned, uint64_t n, unsigned long long total_packed,
                                   const sw_kmer* __restrict__ recv_kmers, sw_kmer* __restrict__ out_kmers,
                                   sw_node* __restrict__ out_nodes)
@@ -75,12 +161,12 @@ __global__ void node_merge_kernel(const uint64_t* __restrict__ skey, const uint3
     const uint64_t n_grp = ((uint64_t)gridDim.x * blockDim.x) / G;
     const unsigned long long mask40 = (1ULL << 40) - 1;
     for (uint64_t j = grp; j < n; j += n_grp) {
-        const uint32_t i = sidx[j];
+        const uint64_t i = sorted[j].idx;
         const sw_node nd = nodes[i];
         const unsigned long long cnt = nd.stop - nd.start;
         const unsigned long long ex = scanned[j];
         const unsigned long long off = ex & mask40;
-        const bool flag = (j == 0) || skey[j] != skey[j - 1];
+        const bool flag = (j == 0) || sorted[j].key != sorted[j - 1].key;
         // node rank = (#flags up to and including j) - 1
         const unsigned long long rank = (ex >> 40) + (flag ? 1 : 0) - 1;
         const unsigned long long src = abs_start[i];
@@ -100,42 +186,22 @@ __global__ void node_merge_kernel(const uint64_t* __restrict__ skey, const uint3
     }
 }
 
-__global__ void edge_key_kernel(const sw_edge* __restrict__ edges, const uint32_t* __restrict__ idx, uint64_t n,
-                                int which, uint64_t* __restrict__ key)
+__global__ void edge_flag_kernel(const sw_edge* __restrict__ sorted, uint64_t n, unsigned long long* __restrict__ flags)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const sw_edge& e = edges[idx ? idx[j] : j];
-        key[j] = which ? e.first : e.second;
-    }
-}
-
-__global__ void edge_flag_kernel(const sw_edge* __restrict__ edges, const uint32_t* __restrict__ sidx, uint64_t n,
-                                 unsigned long long* __restrict__ flags)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        bool f = j == 0;
-        if (!f) {
-            const sw_edge& a = edges[sidx[j]];
-            const sw_edge& b = edges[sidx[j - 1]];
-            f = a.first != b.first || a.second != b.second;
-        }
+        const bool f = j == 0 || sorted[j].first != sorted[j - 1].first || sorted[j].second != sorted[j - 1].second;
         flags[j] = f ? 1ULL : 0ULL;
     }
 }
 
-__global__ void edge_merge_kernel(const sw_edge* __restrict__ edges, const uint32_t* __restrict__ sidx,
-                                  const unsigned long long* __restrict__ scanned, uint64_t n, sw_edge* __restrict__ out)
+__global__ void edge_merge_kernel(const sw_edge* __restrict__ sorted, const unsigned long long* __restrict__ scanned,
+                                  uint64_t n, sw_edge* __restrict__ out)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const sw_edge e = edges[sidx[j]];
-        bool f = j == 0;
-        if (!f) {
-            const sw_edge& b = edges[sidx[j - 1]];
-            f = e.first != b.first || e.second != b.second;
-        }
+        const sw_edge e = sorted[j];
+        const bool f = j == 0 || e.first != sorted[j - 1].first || e.second != sorted[j - 1].second;
         const unsigned long long rank = scanned[j] + (f ? 1 : 0) - 1;
         if (f) {
             out[rank].first = e.first;
@@ -216,7 +282,6 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         Ne += edge_counts[i];
     }
     seg[n_src] = Nn;
-    if (Nn > 0xFFFFFFFFull || Ne > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 nodes / edges in one hash range");
     if (Nk >= (1ULL << 40)) fail_runtime("more than 2^40 k-mers in one hash range");
     uint32_t nl = 0;
     const bool prof = getenv("SEQWIN_DIST_PROFILE") != nullptr;
@@ -235,19 +300,18 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
     } else {
         DevBuf<unsigned long long> d_seg(seg.size(), s, true);
         SW_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
-        SortPairs sp;
-        sp.n = Nn;
-        sp.keys.alloc(Nn, s, true);
-        sp.vals.alloc(Nn, s, true);
+        DevBuf<KeyIdx> rec0(Nn, s, true), rec1(Nn, s, true), rec2(Nn, s, true);
         DevBuf<unsigned long long> abs_start(Nn, s, true);
-        node_prepare_kernel<<<grid_for(Nn), kNT, 0, s>>>(recv_nodes, Nn, d_seg.p, n_src, sp.keys.p, abs_start.p);
-        iota32_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.vals.p, Nn);
+        node_prepare_kernel<<<grid_for(Nn), kNT, 0, s>>>(recv_nodes, Nn, d_seg.p, n_src, rec0.p, abs_start.p);
         SW_CUDA(cudaGetLastError());
-        nl += 2 + radix_sort_pairs(sp, 64, s);
+        ++nl;
+        // every rank's slice is sorted by hash: merge the runs (ties keep source-rank order)
+        const std::vector<unsigned long long> node_seg(seg.begin(), seg.begin() + n_src + 1);
+        const KeyIdx* sorted = merge_runs<KeyIdx, LessKey>(rec0.p, node_seg, rec1.p, rec2.p, s, &nl);
         mark(1);
         DevBuf<unsigned long long> packed(Nn + 1, s, true);
-        node_pack_kernel<<<grid_for(Nn), kNT, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, Nn, packed.p);
-        exclusive_scan_u64(packed.p, Nn, packed.p + Nn, s);
+        node_pack_kernel<<<grid_for(Nn), kNT, 0, s>>>(sorted, recv_nodes, Nn, packed.p);
+        nl += exclusive_scan_u64(packed.p, Nn, packed.p + Nn, s);
         SW_CUDA(cudaGetLastError());
         const unsigned long long* total_p = readback_u64(packed.p + Nn, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
@@ -255,10 +319,10 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         out.n_nodes = total >> 40;
         out.nodes.alloc(out.n_nodes, s);
         const uint32_t grid = (uint32_t)std::min<uint64_t>((Nn + 31) / 32, 148 * 32);
-        node_merge_kernel<<<grid, 256, 0, s>>>(sp.keys.p, sp.vals.p, recv_nodes, abs_start.p, packed.p, Nn, total,
-                                               recv_kmers, out.kmers.p, out.nodes.p);
+        node_merge_kernel<<<grid, 256, 0, s>>>(sorted, recv_nodes, abs_start.p, packed.p, Nn, total, recv_kmers,
+                                               out.kmers.p, out.nodes.p);
         SW_CUDA(cudaGetLastError());
-        nl += 3;
+        nl += 2;
     }
 
     mark(2);
@@ -266,22 +330,15 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
     if (Ne == 0) {
         out.edges.alloc(0, s);
     } else {
-        SortPairs sp;
-        sp.n = Ne;
-        sp.keys.alloc(Ne, s, true);
-        sp.vals.alloc(Ne, s, true);
-        // stable LSD over the 128-bit key: by `second`, then by `first`
-        edge_key_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, nullptr, Ne, 0, sp.keys.p);
-        iota32_kernel<<<grid_for(Ne), kNT, 0, s>>>(sp.vals.p, Ne);
-        SW_CUDA(cudaGetLastError());
-        nl += 2 + radix_sort_pairs(sp, 64, s);
-        edge_key_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, 1, sp.keys.p);
-        SW_CUDA(cudaGetLastError());
-        nl += 1 + radix_sort_pairs(sp, 64, s);
+        // every rank's slice is sorted by (first, second): merge the runs, then sum equal pairs
+        std::vector<unsigned long long> edge_seg(n_src + 1, 0);
+        for (uint32_t i = 0; i < n_src; ++i) edge_seg[i + 1] = edge_seg[i] + edge_counts[i];
+        DevBuf<sw_edge> e0(Ne, s, true), e1(Ne, s, true);
+        const sw_edge* sorted = merge_runs<sw_edge, LessEdge>(recv_edges, edge_seg, e0.p, e1.p, s, &nl);
         mark(3);
         DevBuf<unsigned long long> flags(Ne + 1, s, true);
-        edge_flag_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, Ne, flags.p);
-        exclusive_scan_u64(flags.p, Ne, flags.p + Ne, s);
+        edge_flag_kernel<<<grid_for(Ne), kNT, 0, s>>>(sorted, Ne, flags.p);
+        nl += exclusive_scan_u64(flags.p, Ne, flags.p + Ne, s);
         SW_CUDA(cudaGetLastError());
         const unsigned long long* n_edges_p = readback_u64(flags.p + Ne, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
@@ -289,9 +346,9 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         out.n_edges = n_edges;
         out.edges.alloc(n_edges, s);
         SW_CUDA(cudaMemsetAsync(out.edges.p, 0, n_edges * sizeof(sw_edge), s));
-        edge_merge_kernel<<<grid_for(Ne), kNT, 0, s>>>(recv_edges, sp.vals.p, flags.p, Ne, out.edges.p);
+        edge_merge_kernel<<<grid_for(Ne), kNT, 0, s>>>(sorted, flags.p, Ne, out.edges.p);
         SW_CUDA(cudaGetLastError());
-        nl += 3;
+        nl += 2;
     }
     mark(4);
     SW_CUDA(cudaStreamSynchronize(s));

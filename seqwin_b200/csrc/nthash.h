@@ -73,7 +73,7 @@ SW_HD uint64_t srol4(uint64_t x)
 SW_HD void take_if_le(uint64_t h, uint32_t i, uint64_t& best, uint32_t& best_i)
 {
 #if defined(__CUDA_ARCH__)
-    asm("{\n\t.reg .pred p;\n\tsetp.le.u64 p, %2, %0;\n\tselp.b64 %0, %2, %0, p;\n\tselp.b32 %1, %3, %1, p;\n\t}"
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.u64 p, %2, %0;\n\tselp.b64 %0, %0, %2, p;\n\tselp.b32 %1, %1, %3, p;\n\t}"
         : "+l"(best), "+r"(best_i)
         : "l"(h), "r"(i));
 #else
