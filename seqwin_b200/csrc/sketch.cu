@@ -95,13 +95,7 @@ __global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__
         __syncthreads();
         FastState st;
         uint32_t cnt = 0;
-        constexpr int kSub = 3;  // threads per active chunk when they all fit in the CTA
-        if (n_active * kSub <= (uint32_t)NT) {
-            if ((uint32_t)tid < n_active * kSub)
-                cnt = fastB2_windows<NT, C1, kSub>(s_active[tid / kSub], (uint32_t)tid % kSub, P, T, S, st);
-        } else if ((uint32_t)tid < n_active) {
-            cnt = fastB2_windows<NT, C1, 1>(s_active[tid], 0u, P, T, S, st);
-        }
+        if ((uint32_t)tid < n_active) cnt = fastB2_windows<NT, C1>(s_active[tid], P, T, S, st);
         uint32_t total;
         const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
         if (tid == 0) s_gbase = claim_slots(P, tile_id, total);

@@ -476,16 +476,18 @@ SW_HD bool fast_chunk_active(int c, const SketchParams& P, const Tile& T, const 
     return S.first_a[c] != S.first_a[c + 1];
 }
 
-// B2: evaluation of the windows n in [sub*SUBW, (sub+1)*SUBW) of active chunk c, right to left;
-// returns the number of minimizers they emit.  An active chunk is split over NSUB threads so that
-// the whole CTA (not one or two warps) works through the few active chunks; each thread first scans
-// the part of the chunk to its right for the suffix minimum and evaluates the window just above its
-// range (whose selection it needs to decide whether its own top window emits).
-template <int NT, int C1, int NSUB>
-SW_HD uint32_t fastB2_windows(uint32_t c, uint32_t sub, const SketchParams& P, const Tile& T, const TileSmem& S,
-                              FastState& st)
+// B2: one thread per active chunk.  The selected position A(n) of window c*C1 + n is monotone in n,
+// A(0) is known from B1 and so is A(C1) (the next chunk's first window), so the windows where the
+// selection changes are found by bisection instead of evaluating all C1 windows:
+//   1. one right-to-left pass stores the suffix argmin of the chunk from every offset (in amin[])
+//   2. repeat: binary-search the smallest n > lo with A(n) != A(lo)  (about log2(C1) window
+//      evaluations per emitted minimizer; each evaluation is three lookups, see fastB1_boundary)
+// Emitted selections are appended to amin[c*C1 ...] (slots the search has already passed) and their
+// window offsets are the set bits of st.mask.  Returns the number of minimizers emitted by windows
+// c*C1+1 .. (c+1)*C1, plus window 0 for chunk 0 of a record's first tile.
+template <int NT, int C1>
+SW_HD uint32_t fastB2_windows(uint32_t c, const SketchParams& P, const Tile& T, const TileSmem& S, FastState& st)
 {
-    constexpr int SUBW = (C1 + NSUB - 1) / NSUB;
     const uint32_t w = P.w;
     const uint32_t n_eval = T.n_kmers - w + 1;
     const uint32_t j0 = c * C1;
@@ -505,10 +507,23 @@ SW_HD uint32_t fastB2_windows(uint32_t c, uint32_t sub, const SketchParams& P, c
         const uint64_t h = S.cm_h[c + q];
         if (!lo_valid || h <= m_lo_h) { m_hi_h = h; m_hi_i = S.cm_i[c + q]; }
     }
-    // rightmost minimum of window j0 + n given the suffix minimum (sh, si) of the chunk from n on
-    auto eval = [&](uint32_t n, uint64_t sh, uint32_t si) -> uint32_t {
-        uint64_t rh = sh;
-        uint32_t ri = si;
+    // 1. suffix argmin from every offset of the chunk; strict '<' keeps the right-hand element on ties.
+    //    (the chunk is complete: its first window is evaluated and spans more than C1 k-mers)
+    {
+        uint64_t sh = S.h0[j0 + C1 - 1];
+        uint32_t si = j0 + C1 - 1;
+        S.amin[j0 + C1 - 1] = (uint16_t)si;
+#pragma unroll 4
+        for (int n = C1 - 2; n >= 0; --n) {
+            const uint64_t h = S.h0[j0 + n];
+            if (h < sh) { sh = h; si = j0 + n; }
+            S.amin[j0 + n] = (uint16_t)si;
+        }
+    }
+    // rightmost minimum of window j0 + n (0 <= n < C1, j0 + n < n_eval)
+    auto eval = [&](uint32_t n, uint64_t* out_h) -> uint32_t {
+        uint32_t ri = S.amin[j0 + n];
+        uint64_t rh = S.h0[ri];
         if (n + r >= (uint32_t)C1) {
             if (m_hi_h <= rh) { rh = m_hi_h; ri = m_hi_i; }
         } else {
@@ -517,60 +532,51 @@ SW_HD uint32_t fastB2_windows(uint32_t c, uint32_t sub, const SketchParams& P, c
         const uint32_t pe = S.pidx[j0 + n + w - 1];
         const uint64_t ph = S.h0[pe];
         if (ph <= rh) { rh = ph; ri = pe; }
+        *out_h = rh;
         return ri;
     };
-    const uint32_t n_lo = sub * SUBW;
-    const uint32_t n_top = n_lo + SUBW < (uint32_t)C1 ? n_lo + SUBW : (uint32_t)C1;  // one past this thread's range
-    uint64_t sh = 0, mask = 0;
-    uint32_t si = 0, prev_a = 0xFFFFFFFFu;
-    bool have_suffix = false;
-    // suffix minimum of the chunk to the right of the range; strict '<' keeps the right-hand element
-    for (uint32_t n = C1; n-- > n_top;) {
-        const uint64_t h = S.h0[j0 + n];
-        if (!have_suffix || h < sh) { sh = h; si = j0 + n; have_suffix = true; }
+    // right end of the search: the next chunk's first window if it is evaluated, else the last
+    // evaluated window of this chunk
+    uint32_t a_lo = S.first_a[c];
+    uint32_t hi_end, a_end;
+    uint64_t h_end = 0;
+    bool end_is_next = false;
+    if (j0 + C1 < n_eval) {
+        hi_end = C1;
+        a_end = S.first_a[c + 1];
+        end_is_next = true;
+    } else {
+        hi_end = n_eval - 1 - j0;
+        a_end = hi_end ? eval(hi_end, &h_end) : a_lo;
     }
-    if (n_top < (uint32_t)C1) {
-        if (j0 + n_top < n_eval) prev_a = eval(n_top, sh, si);           // window just above the range
-    } else if (j0 + C1 < n_eval) {
-        prev_a = S.first_a[c + 1];                                        // next chunk's first window (B1)
-    }
-#pragma unroll
-    for (int i = SUBW - 1; i >= 0; --i) {
-        const uint32_t n = n_lo + (uint32_t)i;
-        if (n < n_top) {
-            const uint32_t a = j0 + n;
-            const uint64_t h = S.h0[a];
-            if (!have_suffix || h < sh) { sh = h; si = a; have_suffix = true; }
-            if (a < n_eval) {
-                const uint32_t ri = eval(n, sh, si);
-                if (a + 1 < n_eval && prev_a != ri) {   // window a + 1 selects a new k-mer
-                    mask |= 1ULL << n;
-                    S.amin[a + 1] = (uint16_t)prev_a;
-                }
-                prev_a = ri;
-            }
+    st.chunk = c;
+    st.a_first = a_lo;
+    st.f0 = (c == 0 && T.first != 0 && S.h0[a_lo] != ~0ULL) ? 1u : 0u;
+    uint64_t mask = 0;
+    uint32_t n_out = 0, lo = 0;
+    // 2. next change point after lo, until the selection at the right end is reached
+    while (a_lo != a_end) {
+        uint32_t l = lo, rr = hi_end, a_r = a_end;
+        uint64_t h_r = h_end;
+        bool r_is_end = true;
+        while (rr - l > 1) {
+            const uint32_t m = (l + rr) >> 1;
+            uint64_t hm;
+            const uint32_t a_m = eval(m, &hm);
+            if (a_m != a_lo) { rr = m; a_r = a_m; h_r = hm; r_is_end = false; } else { l = m; }
         }
-    }
-    // minimizer.cpp:45: a selected k-mer whose h0 is 2^64-1 is never emitted
-    uint64_t it = mask;
-    while (it) {
-#if defined(__CUDA_ARCH__)
-        const int b = __ffsll((long long)it) - 1;
-#else
-        const int b = __builtin_ctzll(it);
-#endif
-        it &= it - 1;
-        if (S.h0[S.amin[j0 + b + 1]] == ~0ULL) mask &= ~(1ULL << b);
+        if (r_is_end && end_is_next) h_r = S.h0[a_r];
+        // window j0 + rr selects a new k-mer; minimizer.cpp:45: never emit one whose h0 is 2^64-1
+        if (h_r != ~0ULL) {
+            mask |= 1ULL << (rr - 1);
+            S.amin[j0 + n_out] = (uint16_t)a_r;   // slot n_out < rr: the search never looks there again
+            ++n_out;
+        }
+        lo = rr;
+        a_lo = a_r;
     }
     st.mask = mask;
-    st.chunk = c;
-    st.a_first = prev_a;
-    st.f0 = (c == 0 && sub == 0 && T.first != 0 && S.h0[prev_a] != ~0ULL) ? 1u : 0u;
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)__popcll(mask) + st.f0;
-#else
-    return (uint32_t)__builtin_popcountll(mask) + st.f0;
-#endif
+    return n_out + st.f0;
 }
 
 template <int NT, int C1>
@@ -579,16 +585,12 @@ SW_HD void fastD_write(const SketchParams& P, const Tile& T, const TileSmem& S, 
 {
     const uint32_t j0 = st.chunk * C1;
     if (st.f0) write_minimizer(slot++, st.a_first, P, T, S);
-    uint64_t it = st.mask;
-    while (it) {
 #if defined(__CUDA_ARCH__)
-        const int b = __ffsll((long long)it) - 1;
+    const uint32_t n_out = (uint32_t)__popcll(st.mask);
 #else
-        const int b = __builtin_ctzll(it);
+    const uint32_t n_out = (uint32_t)__builtin_popcountll(st.mask);
 #endif
-        it &= it - 1;
-        write_minimizer(slot++, S.amin[j0 + b + 1], P, T, S);
-    }
+    for (uint32_t i = 0; i < n_out; ++i) write_minimizer(slot++, S.amin[j0 + i], P, T, S);
 }
 
 }  // namespace sw

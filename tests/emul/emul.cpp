@@ -74,13 +74,7 @@ static void emulate(const sw_batch& b, uint32_t k, uint32_t w, std::vector<uint6
             for (int tid = 0; tid < NT; ++tid) fastB1_boundary<NT, C1>(tid, P, T, S);
             for (int tid = 0; tid < NT; ++tid)
                 if (fast_chunk_active<NT, C1>(tid, P, T, S)) active.push_back((uint32_t)tid);
-            constexpr int kSub = 3;
-            if (active.size() * kSub <= (size_t)NT) {
-                for (size_t i = 0; i < active.size() * kSub; ++i)
-                    cnt[i] = fastB2_windows<NT, C1, kSub>(active[i / kSub], (uint32_t)(i % kSub), P, T, S, st[i]);
-            } else {
-                for (size_t i = 0; i < active.size(); ++i) cnt[i] = fastB2_windows<NT, C1, 1>(active[i], 0u, P, T, S, st[i]);
-            }
+            for (size_t i = 0; i < active.size(); ++i) cnt[i] = fastB2_windows<NT, C1>(active[i], P, T, S, st[i]);
             for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += cnt[tid]; }
             tile_count[t] = total;
             tile_slot[t] = cursor;
