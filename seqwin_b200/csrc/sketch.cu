@@ -198,14 +198,14 @@ struct KernelConfig {
 
 #define SW_CFG(NT, C1) {NT, C1, sketch_fast_kernel<NT, C1>, sketch_generic_kernel<NT, C1>}
 const KernelConfig kConfigs[] = {
-    SW_CFG(128, 33),  // default: 4 CTAs/SM
-    SW_CFG(128, 45),
+    SW_CFG(128, 27),  // default: 5 CTAs/SM (20 warps); measured best of the sweep in profiles/
+    SW_CFG(128, 33),
     SW_CFG(256, 45),
     SW_CFG(256, 61),  // large windows (w up to ~15k)
-    SW_CFG(128, 27),
+    SW_CFG(128, 45),
     SW_CFG(128, 21),
-    SW_CFG(256, 33),
-    SW_CFG(96, 33),
+    SW_CFG(128, 23),
+    SW_CFG(64, 33),
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 constexpr int kLargeWindowConfig = 3;

@@ -132,6 +132,7 @@ long emul_sketch(const uint8_t* const* seqs, const uint32_t* lens, size_t n_reco
         else if (nt == 4 && c1 == 45) sw::emulate<4, 45>(*b, k, w, keys, vals, n_tiles_out, force_generic);
         else if (nt == 128 && c1 == 33) sw::emulate<128, 33>(*b, k, w, keys, vals, n_tiles_out, force_generic);
         else if (nt == 256 && c1 == 17) sw::emulate<256, 17>(*b, k, w, keys, vals, n_tiles_out, force_generic);
+        else if (nt == 128 && c1 == 27) sw::emulate<128, 27>(*b, k, w, keys, vals, n_tiles_out, force_generic);
         else if (nt == 32 && c1 == 9) sw::emulate<32, 9>(*b, k, w, keys, vals, n_tiles_out, force_generic);
         else { delete b; return -2; }
         delete b;

@@ -63,7 +63,7 @@ def _seqs(rng):
         rand(12000), rand(40000, 0.002), b"ACGTTGCA" * 400]
 
 
-CONFIGS = [(8, 11), (32, 9), (4, 45), (128, 45), (128, 33), (256, 17), (256, 21), (256, 61)]
+CONFIGS = [(8, 11), (32, 9), (4, 45), (128, 45), (128, 27), (128, 33), (256, 17), (256, 21), (256, 61)]
 KW = [(21, 200), (21, 10), (17, 10), (7, 10), (5, 3), (4, 1), (6, 7), (3, 2), (31, 50), (21, 46), (21, 45), (21, 47),
       (9, 9), (11, 16), (15, 64), (12, 11), (33, 100), (127, 10)]
 
