@@ -159,14 +159,30 @@ __global__ void readback_kernel(const unsigned long long* __restrict__ src, unsi
 struct ReadbackRing {
     unsigned long long* host = nullptr;
     size_t cap = 0, off = 0;
-    ~ReadbackRing() { if (host) cudaFreeHost(host); }
+    std::vector<unsigned long long*> retired;  // outgrown buffers, kept until the next build starts
+    ~ReadbackRing()
+    {
+        if (host) cudaFreeHost(host);
+        for (auto* p : retired) cudaFreeHost(p);
+    }
+    void release_retired()
+    {
+        for (auto* p : retired) cudaFreeHost(p);
+        retired.clear();
+    }
     unsigned long long* take(size_t count)
     {
-        if (!host) {
-            cap = (size_t)1 << 20;  // 8 MB of u64 slots
-            SW_CUDA(cudaHostAlloc((void**)&host, cap * sizeof(unsigned long long), cudaHostAllocMapped));
+        if (!host || count > cap / 2) {  // first use, or a request the ring cannot hold comfortably
+            size_t ncap = (size_t)1 << 20;  // 8 MB of u64 slots
+            while (ncap / 4 < count) ncap *= 2;
+            if (ncap > cap) {
+                if (host) retired.push_back(host);  // earlier slots may still be read after the next sync
+                host = nullptr;
+                SW_CUDA(cudaHostAlloc((void**)&host, ncap * sizeof(unsigned long long), cudaHostAllocMapped));
+                cap = ncap;
+                off = 0;
+            }
         }
-        if (count > cap) fail_runtime("readback too large");
         if (off + count > cap) off = 0;  // wrap: earlier slots were consumed long ago
         unsigned long long* r = host + off;
         off += count;
@@ -181,7 +197,11 @@ ReadbackRing& tls_readback()
 }  // namespace
 
 void* arena_alloc(size_t bytes) { return tls_arena().alloc(bytes); }
-void arena_reset() { tls_arena().reset(); }
+void arena_reset()
+{
+    tls_arena().reset();
+    tls_readback().release_retired();
+}
 
 const unsigned long long* readback_u64(const unsigned long long* d_src, size_t count, cudaStream_t s)
 {
