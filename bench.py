@@ -8,7 +8,8 @@ whole synthetic batch.  Workload at N=1: BASELINE.json configs[1] -- 500 genomes
 targets / 400 non-targets), k=21, w=200.  Under torchrun (N>1) every rank owns one such shard
 (weak scaling) and minimizer / edge records are exchanged with NCCL all-to-all (seqwin_b200.dist).
 
-  value      device-resident: packed input already in HBM, graph left in HBM, CUDA-event timed
+  value      device-resident: packed input already in HBM, graph (build + get_penalty scoring) left in
+             HBM, CUDA-event timed
   e2e        the same through the host-buffer C-ABI call (pinned 2-bit batch -> H2D -> build ->
              D2H of kmers/nodes/edges), wall-clock around the call
   roofline   dominant kernel (sketch): algorithmic bytes / CUDA-event kernel time vs measured HBM
@@ -248,12 +249,20 @@ def main():
         dev = C.c_void_p()
         _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
         st = StageTimes()
+        is_t = np.ascontiguousarray(ss.is_targets[my_genomes.start:my_genomes.stop], dtype=np.bool_)
+        pen_ms = C.c_float()
 
         def dev_step():
+            # build + scoring, like the reference arm (_build_native + _get_penalty_native)
             g = C.c_void_p()
             _lib.check(L.sw_dev_build(dev, k, w, C.byref(g), C.byref(st)))
+            _lib.check(L.sw_graph_penalty(g, None, 0, is_t.ctypes.data, len(is_t), C.byref(pen_ms)))
             L.sw_graph_free(g)
-            return st.as_dict()
+            d = st.as_dict()
+            d["penalty_ms"] = pen_ms.value
+            d["total_ms"] += pen_ms.value
+            d["total_launches"] += 1
+            return d
 
         for _ in range(args.warmup):
             dev_step()
@@ -269,7 +278,7 @@ def main():
         def e2e_step():
             g = C.c_void_p()
             t0 = time.perf_counter()
-            _lib.check(L.sw_build_from_batch(batch, k, w, C.byref(g), C.byref(st)))
+            _lib.check(L.sw_build_from_batch_scored(batch, k, w, is_t.ctypes.data, len(is_t), C.byref(g), C.byref(st)))
             dt = time.perf_counter() - t0
             L.sw_graph_free(g)
             return dt, st.as_dict()
@@ -326,7 +335,7 @@ def main():
                                      ("phase_local_ms", "phase_exchange_merge_ms", "phase_merge_ms") if n in stages[0]},
                          "stage_ms": {n: float(np.mean([s[n] for s in stages]))
                                       for n in ("plan_ms", "sketch_kernel_ms", "reorder_ms", "sketch_ms", "sort_nodes_ms",
-                                                "nodes_ms", "edges_ms")}}}
+                                                "nodes_ms", "edges_ms", "penalty_ms") if n in stages[0]}}}
 
     e2e_runs = result["e2e_runs"]
     e2e_s = float(np.mean([r[0] for r in e2e_runs]))
@@ -335,8 +344,9 @@ def main():
            "h2d_bytes_per_step": int(packed_bytes + 12 * n_records) * world, "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_s * 1e3,
            "stage_ms": {n: float(np.mean([r[1][n] for r in e2e_runs])) for n in ("h2d_ms", "plan_ms", "sketch_kernel_ms", "reorder_ms", "sort_nodes_ms", "nodes_ms",
-                                  "edges_ms", "total_ms", "d2h_ms")},
-           "what": "sw_build_from_batch: pinned 2-bit host batch -> H2D -> sketch+graph -> D2H host arrays"}
+                                  "penalty_ms", "edges_ms", "total_ms", "d2h_ms")},
+           "what": "sw_build_from_batch_scored: pinned 2-bit host batch -> H2D -> sketch + graph + get_penalty -> "
+                   "D2H host arrays (copies overlapped with the kernels)"}
 
     cpu_baseline = None
     parity_sample = None

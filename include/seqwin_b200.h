@@ -92,6 +92,8 @@ int sw_batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const
 size_t sw_batch_n_bases(const sw_batch* b);
 size_t sw_batch_n_records(const sw_batch* b);
 size_t sw_batch_packed_bytes(const sw_batch* b);
+/* cumulative records per assembly, n = assemblies + 1 entries */
+int sw_batch_record_offsets(const sw_batch* b, int64_t* out, size_t n);
 void sw_batch_free(sw_batch* b);
 
 int sw_dev_upload(const sw_batch* b, sw_dev_batch** out); /* cudaMemcpyAsync from pinned */
@@ -101,6 +103,7 @@ void sw_dev_batch_free(sw_dev_batch* d);
 typedef struct sw_stage_times {
     float h2d_ms, sketch_ms, sort_nodes_ms, nodes_ms, edges_ms, d2h_ms, total_ms;
     float plan_ms, sketch_kernel_ms, reorder_ms; /* parts of sketch_ms: host tile plan + upload, kernel, reorder */
+    float penalty_ms;                            /* scoring kernel, when the call includes it */
     uint64_t n_bases, n_kmers, n_nodes, n_edges, n_tiles, sketch_launches, total_launches;
 } sw_stage_times;
 
@@ -108,6 +111,15 @@ typedef struct sw_stage_times {
 int sw_dev_build(const sw_dev_batch* d, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t);
 /* End-to-end from pinned host memory: H2D + build + D2H into the graph's host arrays. */
 int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t);
+
+/* Build + score in one call: get_penalty (filter.cpp:15-137) runs on the device-resident kmers / nodes
+ * before they are exported, so the host receives nodes with n_tar / n_neg / penalty filled in. */
+int sw_build_from_batch_scored(const sw_batch* b, uint32_t k, uint32_t w, const uint8_t* is_targets,
+                               size_t n_assemblies, sw_graph** out, sw_stage_times* t);
+/* get_penalty on a device-resident graph (record_offsets == NULL: the graph's own offsets; pass the
+ * global offsets for a multi-GPU hash-range graph). kernel_ms may be NULL. */
+int sw_graph_penalty(sw_graph* g, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
+                     size_t n_assemblies, float* kernel_ms);
 
 /* Minimizer stream of a device batch in (record, position) order -- the sketch stage alone.
  * Two-call protocol like sw_filter_kmers (h1_out == NULL -> count only). Test / multi-GPU hook. */

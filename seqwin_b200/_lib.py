@@ -13,7 +13,7 @@ SW_KMERS, SW_NODES, SW_EDGES, SW_OFFSETS, SW_RECORDS = range(5)
 
 class StageTimes(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "sketch_ms", "sort_nodes_ms", "nodes_ms", "edges_ms",
-                                         "d2h_ms", "total_ms", "plan_ms", "sketch_kernel_ms", "reorder_ms")] + \
+                                         "d2h_ms", "total_ms", "plan_ms", "sketch_kernel_ms", "reorder_ms", "penalty_ms")] + \
                [(n, C.c_uint64) for n in ("n_bases", "n_kmers", "n_nodes", "n_edges", "n_tiles",
                                           "sketch_launches", "total_launches")]
 
@@ -38,11 +38,14 @@ PROTOTYPES = {
     "sw_batch_n_bases": (_SZ, [_P]),
     "sw_batch_n_records": (_SZ, [_P]),
     "sw_batch_packed_bytes": (_SZ, [_P]),
+    "sw_batch_record_offsets": (_I, [_P, _P, _SZ]),
     "sw_batch_free": (None, [_P]),
     "sw_dev_upload": (_I, [_P, C.POINTER(_P)]),
     "sw_dev_batch_free": (None, [_P]),
     "sw_dev_build": (_I, [_P, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_build_from_batch": (_I, [_P, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_build_from_batch_scored": (_I, [_P, _U32, _U32, _P, _SZ, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_graph_penalty": (_I, [_P, _P, _SZ, _P, _SZ, C.POINTER(C.c_float)]),
     "sw_dev_sketch": (_I, [_P, _U32, _U32, _P, _P, _P, _SZ, C.POINTER(_SZ)]),
     "sw_set_stream": (_I, [_P]),
     "sw_dev_build_ex": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),

@@ -433,10 +433,49 @@ void graph_to_host(sw_graph& g)
     g.on_host = true;
 }
 
+// n_tar / n_neg / penalty of a device-resident graph (validation of filter.cpp:33-60 included).
+// Returns the kernel's CUDA-event time in ms.
+float penalty_on_device(DevGraph& dg, const std::vector<uint32_t>& offsets, const uint8_t* is_targets,
+                        size_t n_assemblies, cudaStream_t s)
+{
+    if (offsets.size() != n_assemblies + 1) fail_value("len(record_offsets) must equal len(is_targets) + 1");
+    if (offsets.empty() || offsets[0] != 0) fail_value("record_offsets must start with 0");
+    size_t n_t = 0, n_n = 0;
+    for (size_t i = 0; i < n_assemblies; ++i) {
+        if (offsets[i + 1] < offsets[i]) fail_value("record_offsets must be nondecreasing");
+        if (is_targets[i]) ++n_t; else ++n_n;
+    }
+    if (!n_t) fail_value("is_targets must contain at least one target assembly");
+    if (!n_n) fail_value("is_targets must contain at least one non-target assembly");
+    if (dg.n_nodes == 0) return 0.f;
+    const std::vector<uint32_t> ra = record_assembly_map(offsets);
+    DevBuf<uint32_t> d_ra(ra.size(), s, true);
+    DevBuf<uint8_t> d_t(n_assemblies, s, true);
+    if (!ra.empty()) SW_CUDA(cudaMemcpyAsync(d_ra.p, ra.data(), ra.size() * 4, cudaMemcpyHostToDevice, s));
+    SW_CUDA(cudaMemcpyAsync(d_t.p, is_targets, n_assemblies, cudaMemcpyHostToDevice, s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    const uint32_t bad = run_penalty(dg.kmers.p, dg.n_kmers, dg.nodes.p, dg.n_nodes, d_ra.p, offsets.back(), d_t.p,
+                                     1.0 / (double)n_t, 1.0 / (double)n_n, s);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (bad & 4u) fail_value("node [start, stop) range lies outside kmers");
+    if (bad & 1u) fail_value("record_idx is outside record_offsets range");
+    if (bad & 2u) fail_value("record_idx must be nondecreasing within each node range");
+    return ms;
+}
+
 // End-to-end build from a pinned host batch with the copies overlapped with the kernels:
 //   copy stream:    bases slice 0 | slice 1 | ... | slice C-1            kmers+nodes D2H
 //   compute stream: tables, plan  | sketch(slice 0) | sketch(slice 1) ... sort, nodes | edges | edges D2H
-sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_times* t, bool to_host, uint32_t rec_base = 0)
+sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_times* t, bool to_host, uint32_t rec_base = 0,
+                          const uint8_t* is_targets = nullptr, size_t n_assemblies = 0)
 {
     init_device_once();
     check_kw(k, w);
@@ -504,7 +543,10 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, rec_base, s, st, &chunks);
 
     bool d2h_started = false;
+    float penalty_ms = 0;
     const std::function<void()> after_nodes = [&] {
+        // scoring (get_penalty) runs on the device-resident kmers + nodes before they are exported
+        if (is_targets) penalty_ms = penalty_on_device(g->dev, b.record_offsets, is_targets, n_assemblies, s);
         if (!to_host) return;
         g->n_kmers = g->dev.n_kmers;
         g->n_nodes = g->dev.n_nodes;
@@ -554,6 +596,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
         if (to_host) cudaEventElapsedTime(&t->d2h_ms, e_d2h0, e_d2h1);
         cudaEventElapsedTime(&t->total_ms, e_begin, e_end);
         t->plan_ms = plan_ms;
+        t->penalty_ms = penalty_ms;
         t->sketch_kernel_ms = st.kernel_ms;
         t->reorder_ms = st.reorder_ms;
         t->sort_nodes_ms = gt.sort_nodes_ms;
@@ -631,6 +674,13 @@ int sw_batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const
 size_t sw_batch_n_bases(const sw_batch* b) { return b->n_bases; }
 size_t sw_batch_n_records(const sw_batch* b) { return b->rec_len.size(); }
 size_t sw_batch_packed_bytes(const sw_batch* b) { return b->n_words * sizeof(uint32_t); }
+int sw_batch_record_offsets(const sw_batch* b, int64_t* out, size_t n)
+{
+    return guarded([&] {
+        if (n != b->record_offsets.size()) fail_value("record_offsets size mismatch");
+        for (size_t i = 0; i < n; ++i) out[i] = b->record_offsets[i];
+    });
+}
 void sw_batch_free(sw_batch* b) { delete b; }
 
 int sw_dev_upload(const sw_batch* b, sw_dev_batch** out)
@@ -719,6 +769,25 @@ int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t r
                            sw_stage_times* t)
 {
     return guarded([&] { *out = build_pipelined(*b, k, w, t, to_host != 0, rec_base); });
+}
+
+int sw_build_from_batch_scored(const sw_batch* b, uint32_t k, uint32_t w, const uint8_t* is_targets, size_t n_assemblies,
+                               sw_graph** out, sw_stage_times* t)
+{
+    return guarded([&] { *out = build_pipelined(*b, k, w, t, /*to_host=*/true, 0u, is_targets, n_assemblies); });
+}
+
+int sw_graph_penalty(sw_graph* g, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
+                     size_t n_assemblies, float* kernel_ms)
+{
+    return guarded([&] {
+        if (!g->on_device) fail_runtime("graph is not device resident");
+        const std::vector<uint32_t> offs = record_offsets ? std::vector<uint32_t>(record_offsets, record_offsets + n_offsets)
+                                                          : g->record_offsets;
+        const float ms = penalty_on_device(g->dev, offs, is_targets, n_assemblies, g->stream);
+        if (kernel_ms) *kernel_ms = ms;
+        g->on_host = false;  // any earlier host copy of the nodes is stale now
+    });
 }
 
 int sw_graph_fetch(sw_graph* g)

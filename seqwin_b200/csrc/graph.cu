@@ -277,53 +277,63 @@ __global__ void __launch_bounds__(kNT) edge_final_kernel(
 
 // ---- penalty ----------------------------------------------------------------------------------
 
+// kLanes lanes per node: a node holds a handful of k-mers on average (M / U_n), hot nodes loop.
+template <int kLanes>
 __global__ void __launch_bounds__(256) penalty_kernel(
     const sw_kmer* __restrict__ kmers, uint64_t n_kmers, sw_node* __restrict__ nodes, uint64_t n_nodes,
     const uint32_t* __restrict__ rec_asm, uint32_t n_records, const uint8_t* __restrict__ is_target,
     double inv_t, double inv_n, uint32_t* err)
 {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t i = warp; i < n_nodes; i += n_warps) {
-        const uint64_t start = nodes[i].start, stop = nodes[i].stop;
-        if (start == stop) {
-            if (lane == 0) { nodes[i].n_tar = 0; nodes[i].n_neg = 0; nodes[i].penalty = 1.0; }
-            continue;
-        }
-        if (start > stop || stop > n_kmers) {
-            if (lane == 0) atomicOr(err, 4u);
-            continue;
-        }
+    const int lane = threadIdx.x & (kLanes - 1);
+    const uint64_t grp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    const uint64_t n_grp = ((uint64_t)gridDim.x * blockDim.x) / kLanes;
+    // every group of a warp runs the same number of iterations, so the shuffles below stay convergent
+    const uint64_t n_iter = (n_nodes + n_grp - 1) / n_grp;
+    for (uint64_t it = 0; it < n_iter; ++it) {
+        const uint64_t i = grp + it * n_grp;
+        const bool live = i < n_nodes;
+        uint64_t start = 0, stop = 0;
+        if (live) { start = nodes[i].start; stop = nodes[i].stop; }
+        const bool range_bad = live && (start > stop || stop > n_kmers);
         uint32_t nt = 0, nn = 0, bad = 0;
-        for (uint64_t j = start + lane; j < stop; j += 32) {
-            const uint32_t r = kmers[j].record_idx;
-            if (r >= n_records) { bad |= 1u; continue; }
-            bool fresh = (j == start);
-            if (!fresh) {
-                const uint32_t pr = kmers[j - 1].record_idx;
-                if (r < pr) bad |= 2u;
-                fresh = pr >= n_records || rec_asm[pr] != rec_asm[r];
-            }
-            if (fresh) {
-                if (is_target[rec_asm[r]]) ++nt; else ++nn;
+        if (live && !range_bad) {
+            for (uint64_t j = start + lane; j < stop; j += kLanes) {
+                const uint32_t r = kmers[j].record_idx;
+                if (r >= n_records) { bad |= 1u; continue; }
+                bool fresh = (j == start);
+                if (!fresh) {
+                    const uint32_t pr = kmers[j - 1].record_idx;
+                    if (r < pr) bad |= 2u;
+                    fresh = pr >= n_records || rec_asm[pr] != rec_asm[r];
+                }
+                if (fresh) {
+                    if (is_target[rec_asm[r]]) ++nt; else ++nn;
+                }
             }
         }
 #pragma unroll
-        for (int d = 16; d; d >>= 1) {
+        for (int d = kLanes / 2; d; d >>= 1) {
             nt += __shfl_xor_sync(0xffffffffu, nt, d);
             nn += __shfl_xor_sync(0xffffffffu, nn, d);
             bad |= __shfl_xor_sync(0xffffffffu, bad, d);
         }
-        if (lane == 0) {
-            if (bad) atomicOr(err, bad);
-            nodes[i].n_tar = nt;
-            nodes[i].n_neg = nn;
-            // filter.cpp:132-134 evaluated without fused multiply-add (x86-64 baseline)
-            const double ft = __dmul_rn((double)nt, inv_t);
-            const double fn = __dmul_rn((double)nn, inv_n);
-            const double a = __dsub_rn(1.0, ft);
-            nodes[i].penalty = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(fn, fn)));
+        if (lane == 0 && live) {
+            if (range_bad) {
+                atomicOr(err, 4u);
+            } else if (start == stop) {
+                nodes[i].n_tar = 0;
+                nodes[i].n_neg = 0;
+                nodes[i].penalty = 1.0;
+            } else {
+                if (bad) atomicOr(err, bad);
+                nodes[i].n_tar = nt;
+                nodes[i].n_neg = nn;
+                // filter.cpp:132-134 evaluated without fused multiply-add (x86-64 baseline)
+                const double ft = __dmul_rn((double)nt, inv_t);
+                const double fn = __dmul_rn((double)nn, inv_n);
+                const double a = __dsub_rn(1.0, ft);
+                nodes[i].penalty = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(fn, fn)));
+            }
         }
     }
 }
@@ -428,8 +438,9 @@ uint32_t run_penalty(const sw_kmer* d_kmers, uint64_t n_kmers, sw_node* d_nodes,
     DevBuf<unsigned long long> err64(1, s, true);
     SW_CUDA(cudaMemsetAsync(err64.p, 0, sizeof(unsigned long long), s));
     uint32_t* err_p = reinterpret_cast<uint32_t*>(err64.p);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_nodes + 7) / 8, (uint64_t)sm_count() * 16);
-    penalty_kernel<<<grid, 256, 0, s>>>(d_kmers, n_kmers, d_nodes, n_nodes, d_rec_asm, n_records, d_is_target,
+    constexpr int kLanes = 8;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_nodes * kLanes + 255) / 256, (uint64_t)sm_count() * 16);
+    penalty_kernel<kLanes><<<grid, 256, 0, s>>>(d_kmers, n_kmers, d_nodes, n_nodes, d_rec_asm, n_records, d_is_target,
                                         inv_t, inv_n, err_p);
     SW_CUDA(cudaGetLastError());
     const unsigned long long* h = readback_u64(err64.p, 1, s);

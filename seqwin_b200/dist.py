@@ -256,9 +256,25 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
 
     rec_base, _ = record_base(n_records, device)   # shard bookkeeping is input metadata, not per-step work
+    # global record offsets / classes for the scoring of every rank's hash range (input metadata too)
+    n_asm_local = spec.n_genomes // world
+    local_off = np.empty(n_asm_local + 1, dtype=np.int64)
+    _lib.check(L.sw_batch_record_offsets(batch, local_off.ctypes.data, n_asm_local + 1))
+    gathered = [torch.empty(n_asm_local + 1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(local_off).to(device))
+    glob, base = [0], 0
+    for t in gathered:
+        o = t.cpu().numpy()
+        glob.extend((base + o[1:]).tolist())
+        base += int(o[-1])
+    global_off = np.asarray(glob, dtype=np.uint32)
+    is_t = np.ascontiguousarray(np.arange(spec.n_genomes) < spec.n_targets, dtype=np.bool_)
+    pen_ms = C.c_float()
 
     def step():
         g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base)
+        _lib.check(L.sw_graph_penalty(g, global_off.ctypes.data, len(global_off), is_t.ctypes.data, len(is_t),
+                                      C.byref(pen_ms)))
         sizes = [L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES)]
         L.sw_graph_free(g)
         return sizes
@@ -300,6 +316,8 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch)
+        _lib.check(L.sw_graph_penalty(g, global_off.ctypes.data, len(global_off), is_t.ctypes.data, len(is_t),
+                                      C.byref(pen_ms)))
         _lib.check(L.sw_graph_fetch(g))     # this rank's hash range -> pinned host memory
         L.sw_graph_free(g)
         torch.cuda.synchronize()

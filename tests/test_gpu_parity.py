@@ -148,6 +148,45 @@ def test_get_penalty_device_side_validation():
         _get_penalty(desc, nodes.copy(), offsets, is_t)
 
 
+def test_scored_build_entry_points(edge_paths):
+    """Build + get_penalty in one call (device-resident scoring) == reference build then get_penalty."""
+    L = _lib.lib()
+    paths, is_t = edge_paths
+    is_t = np.ascontiguousarray(is_t, dtype=np.bool_)
+    arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    for k, w in [(17, 10), (21, 200), (31, 50)]:
+        want = np.load(GOLDEN_ARRAYS / f"edge_{k}_{w}.npz", allow_pickle=False)
+        b, d, g = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(L.sw_batch_from_fasta(arr, len(paths), 2, C.byref(b)))
+        try:
+            # end-to-end entry: pinned host batch -> scored graph in host memory
+            _lib.check(L.sw_build_from_batch_scored(b, k, w, is_t.ctypes.data, len(is_t), C.byref(g), None))
+            from seqwin_b200.dist import export_graph
+            kmers, nodes, edges = export_graph(L, g)
+            L.sw_graph_free(g)
+            assert np.array_equal(kmers, want["kmers"]) and np.array_equal(edges, want["edges"])
+            assert np.array_equal(nodes, want["nodes_penalty"])
+            # device-resident entry: build, then score in place on the device
+            _lib.check(L.sw_dev_upload(b, C.byref(d)))
+            g = C.c_void_p()
+            _lib.check(L.sw_dev_build(d, k, w, C.byref(g), None))
+            _lib.check(L.sw_graph_penalty(g, None, 0, is_t.ctypes.data, len(is_t), None))
+            kmers, nodes, edges = export_graph(L, g)
+            L.sw_graph_free(g)
+            L.sw_dev_batch_free(d)
+            assert np.array_equal(nodes, want["nodes_penalty"]) and np.array_equal(kmers, want["kmers"])
+        finally:
+            L.sw_batch_free(b)
+    with pytest.raises(ValueError):
+        b = C.c_void_p()
+        _lib.check(L.sw_batch_from_fasta(arr, len(paths), 2, C.byref(b)))
+        try:
+            all_t = np.ones(len(paths), dtype=np.bool_)
+            _lib.check(L.sw_build_from_batch_scored(b, 17, 10, all_t.ctypes.data, len(all_t), C.byref(g), None))
+        finally:
+            L.sw_batch_free(b)
+
+
 def test_filter_kmers_on_built_graph(fixture_paths):
     kmers, nodes, _, offsets, _ = _build(fixture_paths, 17, 10)
     used = frozenset(nodes["hash"][::3])
