@@ -7,6 +7,8 @@
 // and the per-assembly bookkeeping of build_worker (cpp/src/seqwin/build.cpp:129-147,192-193).
 #include "ingest.h"
 
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -155,16 +157,29 @@ bool ends_with(const std::string& s, const char* suf)
     return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
 }
 
-// Whole file in memory (uninitialised buffer: no zero fill before the read).
+// Whole file in memory: plain files are mapped (no copy through the page cache), gzip streams are
+// inflated into an uninitialised heap buffer.
 struct FileBuf {
     std::unique_ptr<char[]> p;
+    const char* data = nullptr;
     size_t n = 0, cap = 0;
+    void* map = nullptr;
+    size_t map_len = 0;
+    FileBuf() = default;
+    FileBuf(FileBuf&& o) noexcept : p(std::move(o.p)), data(o.data), n(o.n), cap(o.cap), map(o.map), map_len(o.map_len)
+    {
+        o.map = nullptr;
+        o.data = nullptr;
+    }
+    FileBuf(const FileBuf&) = delete;
+    ~FileBuf() { if (map) munmap(map, map_len); }
     void reserve(size_t c)
     {
         if (c <= cap) return;
         std::unique_ptr<char[]> q(new char[c]);
         if (n) memcpy(q.get(), p.get(), n);
         p = std::move(q);
+        data = p.get();
         cap = c;
     }
 };
@@ -194,6 +209,21 @@ FileBuf slurp(const std::string& path)
     } else {
         FILE* f = fopen(path.c_str(), "rb");
         if (!f) fail_runtime("Unable to open FASTA: " + path);
+        {
+            struct stat sb;
+            if (fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+                void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fileno(f), 0);
+                if (m != MAP_FAILED) {
+                    madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+                    buf.map = m;
+                    buf.map_len = (size_t)sb.st_size;
+                    buf.data = static_cast<const char*>(m);
+                    buf.n = (size_t)sb.st_size;
+                    fclose(f);
+                    return buf;
+                }
+            }
+        }
         fseek(f, 0, SEEK_END);
         const long sz = ftell(f);
         fseek(f, 0, SEEK_SET);
@@ -215,7 +245,7 @@ FileBuf slurp(const std::string& path)
 void parse_fasta(const std::string& path, AsmPacked& out)
 {
     const FileBuf buf = slurp(path);
-    const unsigned char* p = (const unsigned char*)buf.p.get();
+    const unsigned char* p = (const unsigned char*)buf.data;
     const size_t n = buf.n;
     out.words.reserve(n / 16 + 64);
     RecordPacker rp(out);
