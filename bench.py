@@ -358,11 +358,12 @@ def main():
             r = time_reference(paths, is_t, k, w, nb, steps=1, warmup=1)
             # the same sample through our FASTA entry point: bit-exact check + FASTA-inclusive e2e
             from seqwin_b200.graph import KmerGraph, _get_penalty
-            t0 = time.perf_counter()
-            g = KmerGraph(paths, k, w, n_cpu=os.cpu_count() or 8)
-            nodes = g.nodes.copy()
-            _get_penalty(g.kmers, nodes, g.record_offsets, is_t)
-            ours_s = time.perf_counter() - t0
+            for _ in range(2):   # like the reference arm: one warm-up pass, one timed pass
+                t0 = time.perf_counter()
+                g = KmerGraph(paths, k, w, n_cpu=os.cpu_count() or 8)
+                nodes = g.nodes.copy()
+                _get_penalty(g.kmers, nodes, g.record_offsets, is_t)
+                ours_s = time.perf_counter() - t0
             rk, rn, re_, ro = r.pop("graph")
             parity_sample = bool(np.array_equal(g.kmers, rk) and np.array_equal(nodes, rn)
                                  and np.array_equal(g.edges, re_) and np.array_equal(g.record_offsets, ro))
