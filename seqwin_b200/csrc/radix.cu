@@ -105,7 +105,8 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
                                               const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
                                               const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                               uint32_t n_valid, uint32_t tile, int shift,
-                                              const unsigned long long* __restrict__ goff, unsigned long long* status)
+                                              const unsigned long long* __restrict__ goff, unsigned long long* status,
+                                              uint32_t n_tiles)
 {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -167,6 +168,8 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
     for (int i = 0; i < NW; ++i)
         if (i < wid) digit_first += sm.scan[i];
+    // tile-major layout: a tile's 256 words share no sector with another tile's (no false sharing
+    // between the CTA that publishes and the CTAs that poll)
     unsigned long long* my_status = status + (uint64_t)tile * kRadix + tid;
     if (tid < kRadix) {
         // publish the tile's digit count right away; the look-back itself runs after the keys have
@@ -190,13 +193,22 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
     if (tid < kRadix) {
         unsigned long long before = 0;
         if (tile != 0) {
-            const unsigned long long* p = my_status - kRadix;
-            for (;;) {
-                const unsigned long long st = ld_relaxed(p);
-                if ((st >> 62) == 0) continue;
-                before += st & kStMask;
-                if ((st >> 62) == 2) break;
-                p -= kRadix;
+            // walk the predecessors kLook at a time: the loads of one batch are independent
+            constexpr int kLook = 8;
+            long long p = (long long)tile - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long st[kLook];
+#pragma unroll
+                for (int q = 0; q < kLook; ++q) st[q] = (p - q >= 0) ? ld_relaxed(my_status - (long long)(tile - (p - q)) * kRadix) : kStInc;
+#pragma unroll
+                for (int q = 0; q < kLook; ++q) {
+                    if (done) break;
+                    if ((st[q] >> 62) == 0) break;   // not published yet: re-read from here
+                    before += st[q] & kStMask;
+                    --p;
+                    if ((st[q] >> 62) == 2) done = true;
+                }
             }
             st_relaxed(my_status, kStInc | (before + run));
         }
@@ -253,10 +265,10 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     const uint32_t n_valid = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
     if (n_valid == (uint32_t)TILE)
         onesweep_tile<NT, ITEMS, true>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
-                                       shift, goff, status);
+                                       shift, goff, status, gridDim.x);
     else
         onesweep_tile<NT, ITEMS, false>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
-                                        shift, goff, status);
+                                        shift, goff, status, gridDim.x);
 }
 
 }  // namespace
