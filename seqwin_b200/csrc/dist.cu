@@ -110,12 +110,6 @@ const T* merge_runs(const T* src, std::vector<unsigned long long> seg, T* buf0, 
     return cur;
 }
 
-__global__ void iota32_kernel(uint32_t* v, uint64_t n)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
-}
-
 // concatenated received nodes -> (hash, index) merge records and the absolute source offset of each
 // node's k-mers
 __global__ void node_prepare_kernel(const sw_node* __restrict__ nodes, uint64_t n, const unsigned long long* __restrict__ seg,

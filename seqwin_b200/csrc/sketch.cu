@@ -376,6 +376,10 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     unsigned long long total = 0;
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); }
+    } ev_guard{ev};
     for (int attempt = 0;; ++attempt) {
         ukeys.alloc(capacity, s, true);
         uvals.alloc(capacity, s, true);
@@ -428,10 +432,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     out.keys.alloc(total, s, true);
     out.vals.alloc(total, s, true);
     cudaEventElapsedTime(&out.kernel_ms, ev[0], ev[1]);
-    if (total == 0) {
-        for (auto& e : ev) cudaEventDestroy(e);
-        return;
-    }
+    if (total == 0) return;
     cudaEventRecord(ev[2], s);
     exclusive_scan_u64(tile_info.p, plan.n_tiles, counters.p + 1, s);
     const uint32_t rgrid = (uint32_t)std::min<uint64_t>(((uint64_t)plan.n_tiles + 7) / 8, (uint64_t)sm_count() * 8);
@@ -442,7 +443,6 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     out.launches += 2;
     SW_CUDA(cudaEventSynchronize(ev[3]));
     cudaEventElapsedTime(&out.reorder_ms, ev[2], ev[3]);
-    for (auto& e : ev) cudaEventDestroy(e);
 }
 
 }  // namespace sw
