@@ -141,10 +141,20 @@ int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t r
 int sw_graph_fetch(sw_graph* g);
 /* Device pointers of a device-resident graph (valid until sw_graph_free). */
 int sw_graph_device_ptrs(sw_graph* g, void** kmers, void** nodes, void** edges);
-/* Cut the sorted node / k-mer / edge arrays at the n_parts+1 hash boundaries i * 2^64 / n_parts
- * (edges by `first`); each output array has n_parts + 1 entries. */
+/* Cut the sorted node / k-mer / edge arrays at the n_parts+1 hash-range boundaries (nodes and
+ * k-mers at i * 2^64 / n_parts, edges by `first` at the matching quantiles); each output array has
+ * n_parts + 1 entries and may be NULL when that cut is not wanted. */
 int sw_graph_split(sw_graph* g, uint32_t n_parts, uint64_t* node_split, uint64_t* kmer_split,
                    uint64_t* edge_split);
+/* Host callback fired by the next builds (sw_dev_build*, sw_build_from_batch_ex) once the k-mer and
+ * node arrays of `g` are final on the device while the edge stage is still to run: a multi-GPU
+ * caller cuts them (sw_graph_split with edge_split = NULL) and starts their exchange from here, so
+ * that the transfer overlaps the edge stage -- the role the per-thread hand-off to
+ * merge_thread_graphs plays in the reference (cpp/src/seqwin/build.cpp:352-378).  Inside the
+ * callback only sw_graph_size / sw_graph_device_ptrs / sw_graph_split may be called on `g`.
+ * fn = NULL clears the hook.  The hook is process-wide: one builder thread per process. */
+typedef void (*sw_nodes_ready_fn)(void* user, sw_graph* g);
+int sw_set_nodes_ready(sw_nodes_ready_fn fn, void* user);
 /* Merge the slices a hash-range owner received from n_src ranks (device pointers, concatenated in
  * rank order; kmer_base[i] = first k-mer index of rank i's slice in rank i's own array). Mirrors
  * merge_thread_graphs (cpp/src/seqwin/build_internals.cpp:295-392). */

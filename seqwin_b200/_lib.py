@@ -23,6 +23,7 @@ class StageTimes(C.Structure):
 
 # every symbol include/seqwin_b200.h declares: (restype, argtypes)
 _P, _SZ, _U32, _I = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
+NODES_READY_FN = C.CFUNCTYPE(None, _P, _P)   # sw_nodes_ready_fn(user, graph)
 PROTOTYPES = {
     "sw_last_error": (C.c_char_p, []),
     "sw_build": (_I, [C.POINTER(C.c_char_p), _SZ, _U32, _U32, _U32, _I, C.POINTER(_P)]),
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "sw_graph_fetch": (_I, [_P]),
     "sw_graph_device_ptrs": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sw_graph_split": (_I, [_P, _U32, _P, _P, _P]),
+    "sw_set_nodes_ready": (_I, [NODES_READY_FN, _P]),
     "sw_dist_merge": (_I, [_P, _P, _P, _P, _P, _P, _P, _U32, C.POINTER(_P), C.POINTER(_U32)]),
     "sw_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ)]),
 }

@@ -362,6 +362,21 @@ sw_dev_batch* dev_upload(const sw_batch& b)
     return d.release();
 }
 
+// Optional host callback fired once kmers + nodes are final on the device (multi-GPU builds start
+// their node / k-mer exchange from it while the edge stage is still running).
+sw_nodes_ready_fn g_nodes_ready = nullptr;
+void* g_nodes_ready_user = nullptr;
+
+void fire_nodes_ready(sw_graph* g)
+{
+    if (!g_nodes_ready) return;
+    g->on_device = true;
+    g->n_kmers = g->dev.n_kmers;
+    g->n_nodes = g->dev.n_nodes;
+    g->n_edges = 0;
+    g_nodes_ready(g_nodes_ready_user, g);
+}
+
 sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t, uint32_t rec_base = 0)
 {
     init_device_once();
@@ -385,7 +400,8 @@ sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_time
     run_sketch(d.words.p, d.rec_word_off.p, plan, k, w, rec_base, s, st);
     cudaEventRecord(e1, s);
     GraphTimes gt;
-    build_graph(st, d.rec_asm.p, rec_base, s, g->dev, &gt);
+    const std::function<void()> after_nodes = [&] { fire_nodes_ready(g.get()); };
+    build_graph(st, d.rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes);
     cudaEventRecord(e2, s);
     SW_CUDA(cudaStreamSynchronize(s));
     g->on_device = true;
@@ -547,6 +563,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     const std::function<void()> after_nodes = [&] {
         // scoring (get_penalty) runs on the device-resident kmers + nodes before they are exported
         if (is_targets) penalty_ms = penalty_on_device(g->dev, b.record_offsets, is_targets, n_assemblies, s);
+        fire_nodes_ready(g.get());
         if (!to_host) return;
         g->n_kmers = g->dev.n_kmers;
         g->n_nodes = g->dev.n_nodes;
@@ -731,11 +748,18 @@ int sw_graph_split(sw_graph* g, uint32_t n_parts, uint64_t* node_split, uint64_t
         std::vector<unsigned long long> h(3 * (size_t)(n_parts + 1));
         graph_split(g->dev, n_parts, h.data(), g->stream);
         for (uint32_t i = 0; i <= n_parts; ++i) {
-            node_split[i] = h[i];
-            kmer_split[i] = h[(n_parts + 1) + i];
-            edge_split[i] = h[2 * (size_t)(n_parts + 1) + i];
+            if (node_split) node_split[i] = h[i];
+            if (kmer_split) kmer_split[i] = h[(n_parts + 1) + i];
+            if (edge_split) edge_split[i] = h[2 * (size_t)(n_parts + 1) + i];
         }
     });
+}
+
+int sw_set_nodes_ready(sw_nodes_ready_fn fn, void* user)
+{
+    g_nodes_ready = fn;
+    g_nodes_ready_user = user;
+    return SW_OK;
 }
 
 int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const void* recv_kmers,

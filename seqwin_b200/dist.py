@@ -34,6 +34,7 @@ class LocalGraph:
     kmer_split: np.ndarray   # [P+1]
     edge_split: np.ndarray   # [P+1]
     handle: object = None
+    early: object = None     # node / k-mer exchange already in flight (exchange_nodes result)
 
 
 def all_to_all_bytes(chunks: list[torch.Tensor], group=None) -> list[torch.Tensor]:
@@ -70,14 +71,15 @@ def all_to_all_bytes(chunks: list[torch.Tensor], group=None) -> list[torch.Tenso
     return [o.to(dev) for o in outs]
 
 
-def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], item_bytes: list[int], group=None):
+def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], item_bytes: list[int], group=None,
+                      async_op: bool = False):
     """Several byte tensors, each already laid out as P consecutive destination slices
     (splits[t][d] .. splits[t][d+1], in items).  One count exchange for all of them, then one
     all_to_all_single per tensor straight out of / into contiguous buffers (no concatenation).
-    Returns (received tensors, received item counts per source [T, P])."""
+    Returns (received tensors, received item counts per source [T, P], pending work handles);
+    with async_op (NCCL only) the data transfers are left in flight on NCCL's stream."""
     world = dist.get_world_size(group)
     dev = tensors[0].device
-    T = len(tensors)
     send_items = np.stack([np.diff(sp.astype(np.int64)) for sp in splits])          # [T, P]
     if dist.get_backend(group) != "nccl":
         outs, counts = [], []
@@ -86,35 +88,45 @@ def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], ite
             rc = all_to_all_bytes(chunks, group)
             outs.append(torch.cat(rc))
             counts.append([c.numel() // ib for c in rc])
-        return outs, np.array(counts, dtype=np.uint64)
+        return outs, np.array(counts, dtype=np.uint64), []
     send_t = torch.from_numpy(np.ascontiguousarray(send_items.T)).to(dev)            # [P, T]: row d goes to rank d
     recv_t = torch.empty_like(send_t)
     dist.all_to_all_single(recv_t, send_t, group=group)
     recv_items = recv_t.cpu().numpy().T                                              # [T, P]
-    outs = []
+    outs, works = [], []
     for i, (t, sp, ib) in enumerate(zip(tensors, splits, item_bytes)):
         out = torch.empty(int(recv_items[i].sum()) * ib, dtype=torch.uint8, device=dev)
         src = t[int(sp[0]) * ib:int(sp[-1]) * ib]
-        dist.all_to_all_single(out, src, output_split_sizes=(recv_items[i] * ib).tolist(),
-                               input_split_sizes=(send_items[i] * ib).tolist(), group=group)
+        wk = dist.all_to_all_single(out, src, output_split_sizes=(recv_items[i] * ib).tolist(),
+                                    input_split_sizes=(send_items[i] * ib).tolist(), group=group, async_op=async_op)
+        if async_op:
+            works.append(wk)
         outs.append(out)
-    return outs, recv_items.astype(np.uint64)
+    return outs, recv_items.astype(np.uint64), works
 
 
-def exchange_and_merge(stages, local: LocalGraph, group=None):
-    """Send every hash range to its owner and merge what arrives. Returns stages.merge(...)."""
+def exchange_nodes(nodes, kmers, node_split, kmer_split, group=None, async_op=False):
+    """First half of the exchange: node and k-mer slices (plus each sender's k-mer base, which the
+    owner needs to rebase node.start: one extra 8-byte item per destination)."""
     world = dist.get_world_size(group)
-    dev = local.nodes.device
-    # the owner needs each sender's k-mer base to rebase node.start: ship it as one extra 8-byte item
-    bases = torch.from_numpy(local.kmer_split[:world].astype(np.int64)).to(dev).view(torch.uint8)
+    bases = torch.from_numpy(kmer_split[:world].astype(np.int64)).to(nodes.device).view(torch.uint8)
     base_split = np.arange(world + 1, dtype=np.uint64)
-    (recv_nodes, recv_kmers, recv_edges, recv_base), counts = all_to_all_slices(
-        [local.nodes, local.kmers, local.edges, bases],
-        [local.node_split, local.kmer_split, local.edge_split, base_split],
-        [NODE_BYTES, KMER_BYTES, EDGE_BYTES, 8], group)
+    return all_to_all_slices([nodes, kmers, bases], [node_split, kmer_split, base_split],
+                             [NODE_BYTES, KMER_BYTES, 8], group, async_op)
+
+
+def exchange_and_merge(stages, local: LocalGraph, group=None, early=None):
+    """Send every hash range to its owner and merge what arrives. Returns stages.merge(...).
+    `early` is the result of an exchange_nodes() already started while the edge stage was running."""
+    if early is None:
+        early = exchange_nodes(local.nodes, local.kmers, local.node_split, local.kmer_split, group)
+    (recv_nodes, recv_kmers, recv_base), counts, works = early
+    (recv_edges,), ecounts, _ = all_to_all_slices([local.edges], [local.edge_split], [EDGE_BYTES], group)
+    for wk in works:
+        wk.wait()
     kmer_base = recv_base.view(torch.int64).cpu().numpy().astype(np.uint64)
     return stages.merge(recv_nodes, np.ascontiguousarray(counts[0]), recv_kmers, np.ascontiguousarray(counts[1]),
-                        kmer_base, recv_edges, np.ascontiguousarray(counts[2]))
+                        kmer_base, recv_edges, np.ascontiguousarray(ecounts[0]))
 
 
 def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
@@ -156,21 +168,50 @@ class CudaStages:
         self.phase_events = None
         self.merge_ms = 0.0
 
-    def local_build(self, dev_batch, k: int, w: int, rec_base: int, world: int, host_batch=None) -> LocalGraph:
+    def local_build(self, dev_batch, k: int, w: int, rec_base: int, world: int, host_batch=None,
+                    on_nodes=None) -> LocalGraph:
+        """Single-GPU kernels on this rank's shard.  on_nodes(nodes, kmers, node_split, kmer_split), if
+        given, is called from inside the build as soon as nodes + k-mers are final on the device (the
+        edge stage follows); its return value lands in LocalGraph.early."""
         L, lb = self.L, self._lib
         g = C.c_void_p()
         self.times = lb.StageTimes()
-        if host_batch is not None:   # end-to-end: the H2D copy is sliced and overlapped with the sketch
-            lb.check(L.sw_build_from_batch_ex(host_batch, k, w, rec_base, 0, C.byref(g), C.byref(self.times)))
-        else:
-            lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, C.byref(g), C.byref(self.times)))
-        pk, pn, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        lb.check(L.sw_graph_device_ptrs(g, C.byref(pk), C.byref(pn), C.byref(pe)))
-        n_k, n_n, n_e = (L.sw_graph_size(g, i) for i in (lb.SW_KMERS, lb.SW_NODES, lb.SW_EDGES))
-        ns, ks, es = (np.zeros(world + 1, dtype=np.uint64) for _ in range(3))
-        lb.check(L.sw_graph_split(g, world, ns.ctypes.data, ks.ctypes.data, es.ctypes.data))
-        return LocalGraph(_view(pk.value, n_k * KMER_BYTES, self.device), _view(pn.value, n_n * NODE_BYTES, self.device),
-                          _view(pe.value, n_e * EDGE_BYTES, self.device), ns, ks, es, handle=g)
+        early, failure = [], []
+
+        def cuts(gh, want_edges: bool):
+            pk, pn, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            lb.check(L.sw_graph_device_ptrs(gh, C.byref(pk), C.byref(pn), C.byref(pe)))
+            n_k, n_n, n_e = (L.sw_graph_size(gh, i) for i in (lb.SW_KMERS, lb.SW_NODES, lb.SW_EDGES))
+            ns, ks, es = (np.zeros(world + 1, dtype=np.uint64) for _ in range(3))
+            lb.check(L.sw_graph_split(gh, world, ns.ctypes.data, ks.ctypes.data, es.ctypes.data if want_edges else None))
+            return (_view(pk.value, n_k * KMER_BYTES, self.device), _view(pn.value, n_n * NODE_BYTES, self.device),
+                    _view(pe.value, n_e * EDGE_BYTES, self.device), ns, ks, es)
+
+        def hook(_user, gh):
+            try:   # an exception must not unwind through the C frames
+                kmers, nodes, _, ns, ks, _ = cuts(C.c_void_p(gh), want_edges=False)
+                early.append(on_nodes(nodes, kmers, ns, ks))
+            except BaseException as exc:   # noqa: BLE001 - re-raised below
+                failure.append(exc)
+
+        cb = lb.NODES_READY_FN(hook)
+        if on_nodes is not None:
+            lb.check(L.sw_set_nodes_ready(cb, None))
+        try:
+            if host_batch is not None:   # end-to-end: the H2D copy is sliced and overlapped with the sketch
+                lb.check(L.sw_build_from_batch_ex(host_batch, k, w, rec_base, 0, C.byref(g), C.byref(self.times)))
+            else:
+                lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, C.byref(g), C.byref(self.times)))
+        finally:
+            if on_nodes is not None:
+                L.sw_set_nodes_ready(lb.NODES_READY_FN(0), None)
+        if failure:
+            L.sw_graph_free(g)
+            raise failure[0]
+        kmers, nodes, edges, ns, ks, es = cuts(g, want_edges=True)
+        local = LocalGraph(kmers, nodes, edges, ns, ks, es, handle=g)
+        local.early = early[0] if early else None
+        return local
 
     def free_local(self, local: LocalGraph) -> None:
         if local.handle:
@@ -194,17 +235,25 @@ class CudaStages:
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
-               host_batch=None):
+               host_batch=None, overlap: bool = True):
     """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle."""
     world = dist.get_world_size(group)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
-    local = stages.local_build(dev_batch, k, w, rec_base, world, host_batch=host_batch)
+    # the node / k-mer slices leave as soon as they are final; over NCCL the transfer stays in flight
+    # while the edge stage runs (gloo exchanges synchronously inside the hook: same code path, no overlap)
+    on_nodes = None
+    if overlap:
+        nccl = dist.get_backend(group) == "nccl"
+
+        def on_nodes(nodes, kmers, node_split, kmer_split):
+            return exchange_nodes(nodes, kmers, node_split, kmer_split, group, async_op=nccl)
+    local = stages.local_build(dev_batch, k, w, rec_base, world, host_batch=host_batch, on_nodes=on_nodes)
     ev[1].record()
     try:
-        g = exchange_and_merge(stages, local, group)
+        g = exchange_and_merge(stages, local, group, early=local.early)
     finally:
         stages.free_local(local)
     ev[2].record()
@@ -271,8 +320,11 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     is_t = np.ascontiguousarray(np.arange(spec.n_genomes) < spec.n_targets, dtype=np.bool_)
     pen_ms = C.c_float()
 
+    import os
+    overlap = os.environ.get("SEQWIN_DIST_OVERLAP", "1") != "0"   # A/B switch for profiles/
+
     def step():
-        g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base)
+        g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, overlap=overlap)
         _lib.check(L.sw_graph_penalty(g, global_off.ctypes.data, len(global_off), is_t.ctypes.data, len(is_t),
                                       C.byref(pen_ms)))
         sizes = [L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES)]
@@ -315,7 +367,7 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch)
+        g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch, overlap=overlap)
         _lib.check(L.sw_graph_penalty(g, global_off.ctypes.data, len(global_off), is_t.ctypes.data, len(is_t),
                                       C.byref(pen_ms)))
         _lib.check(L.sw_graph_fetch(g))     # this rank's hash range -> pinned host memory

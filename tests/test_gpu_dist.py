@@ -19,7 +19,7 @@ from tests.helpers import assert_graph_equal, check_graph_invariants
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, paths, k, w, out_path, use_nccl):
+def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev_index = rank if use_nccl else 0
@@ -40,7 +40,7 @@ def _worker(rank, world, port, paths, k, w, out_path, use_nccl):
         b, d = C.c_void_p(), C.c_void_p()
         _lib.check(L.sw_batch_from_fasta(arr, len(mine), 2, C.byref(b)))
         _lib.check(L.sw_dev_upload(b, C.byref(d)))
-        g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w)
+        g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap)
         parts = swd.export_graph(L, g)
         L.sw_graph_free(g)
         L.sw_dev_batch_free(d)
@@ -68,3 +68,35 @@ def test_multi_rank_build_matches_oracle(synth_sets, tmp_path, kw, world):
     want = O._build_native(paths, *kw)
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"{world} ranks {kw}")
     check_graph_invariants(got["kmers"], got["nodes"], got["edges"], want[3])
+
+
+def test_multi_rank_build_without_overlap(synth_sets, tmp_path):
+    """overlap=False: the whole exchange after the local build (the path the CPU gloo tests model)."""
+    from oracle import oracle as O
+    world, kw = 2, (21, 200)
+    use_nccl = torch.cuda.device_count() >= world
+    paths = [str(p) for p in synth_sets["synth_medium"][0]]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "merged.npz"
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, False), nprocs=world, join=True)
+    got = np.load(out)
+    want = O._build_native(paths, *kw)
+    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, "2 ranks, no overlap")
+
+
+def test_more_ranks_than_assemblies(synth_sets, tmp_path):
+    """A rank with an empty shard never reaches the nodes-ready hook and must still join every collective."""
+    from oracle import oracle as O
+    world, kw = 3, (21, 50)
+    use_nccl = torch.cuda.device_count() >= world
+    paths = [str(p) for p in synth_sets["synth_medium"][0]][:2]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "merged.npz"
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl), nprocs=world, join=True)
+    got = np.load(out)
+    want = O._build_native(paths, *kw)
+    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, "3 ranks, 2 assemblies")
