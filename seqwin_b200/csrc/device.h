@@ -95,7 +95,8 @@ struct DevPlan {
     uint64_t n_windows = 0, n_kmers = 0;
     std::vector<unsigned long long> rec_tile_off;  // [R+1] first tile of each record (host, optional)
     uint32_t tk = 0;  // tile capacity the plan was cut for
-    int config = 0;   // kernel configuration index
+    int config = 0;   // dense kernel configuration index
+    bool sparse = false;  // sparse kernel first, the dense configuration only for the tiles it hands over
 };
 
 struct SketchStream {
@@ -106,7 +107,7 @@ struct SketchStream {
     float kernel_ms = 0, reorder_ms = 0;  // CUDA-event times of the last run
 };
 
-int sketch_pick_config(uint32_t w, uint32_t* tk_out);
+int sketch_pick_config(uint32_t w, uint32_t* tk_out, bool* sparse_out);
 // Device-side tile planner: cuts every record's valid-k-mer stream into tiles (see ingest.h:
 // plan_tiles is the host statement of the same rule, used by the test emulator).
 DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s, bool want_rec_tile_off = false);

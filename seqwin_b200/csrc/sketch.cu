@@ -62,6 +62,19 @@ __device__ __forceinline__ unsigned long long claim_slots(const SketchParams& P,
     return slot;
 }
 
+// ticket -> tile: a contiguous range of the plan, or (dense kernels finishing what the sparse kernel
+// handed over) an explicit list whose length is only known on the device
+__device__ __forceinline__ bool next_tile(const SketchParams& P, uint32_t ticket, uint32_t* tile_id)
+{
+    if (P.tile_list) {
+        if (ticket >= *P.tile_list_n) return false;
+        *tile_id = P.tile_list[ticket];
+        return true;
+    }
+    *tile_id = P.tile_lo + ticket;
+    return *tile_id < P.n_tiles;
+}
+
 template <int NT, int C1>
 __global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__ SketchParams P)
 {
@@ -79,8 +92,8 @@ __global__ void __launch_bounds__(NT) sketch_fast_kernel(const __grid_constant__
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
         __syncthreads();  // also: table visible / previous tile's smem reads done
-        const uint32_t tile_id = P.tile_lo + s_tile;
-        if (tile_id >= P.n_tiles) break;
+        uint32_t tile_id;
+        if (!next_tile(P, s_tile, &tile_id)) break;
         const Tile T = P.tiles[tile_id];
 
         fastA_hash_prefix<NT, C1>(tid, P, T, S);
@@ -120,8 +133,8 @@ __global__ void __launch_bounds__(NT) sketch_generic_kernel(const __grid_constan
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
         __syncthreads();
-        const uint32_t tile_id = P.tile_lo + s_tile;
-        if (tile_id >= P.n_tiles) break;
+        uint32_t tile_id;
+        if (!next_tile(P, s_tile, &tile_id)) break;
         const Tile T = P.tiles[tile_id];
 
         phase1_hash<NT, C1>(tid, P, T, S);
@@ -145,6 +158,57 @@ __global__ void __launch_bounds__(NT) sketch_generic_kernel(const __grid_constan
         __syncthreads();
         const unsigned long long gbase = s_gbase;
         for (uint32_t i = tid; i < total; i += NT) phase3c_write(i, gbase, P, T, S);
+    }
+}
+
+// Sparse path (sketch_tile.h): candidates only, no per-k-mer shared memory.
+template <int NT, int C1, int CAP>
+__global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant__ SketchParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp_sums[NT / 32];
+    __shared__ unsigned long long s_gbase;
+
+    const SparseSmem S = carve_sparse_smem(smem_raw, NT, CAP);
+    const int tid = threadIdx.x;
+    if (tid < 20) S.tab[tid] = P.table.e[tid];
+    constexpr uint32_t MC = NT * kSparsePerThread;
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
+        __syncthreads();  // also: table visible / previous tile's smem reads done
+        uint32_t tile_id;
+        if (!next_tile(P, s_tile, &tile_id)) break;
+        const Tile T = P.tiles[tile_id];
+
+        uint64_t mask = 0;
+        bool ok = T.n_pieces == 1;
+        if (ok) ok = sparseA_hash<NT, C1, CAP>(tid, P, T, S, &mask);
+        bool hand_over = __syncthreads_or(!ok) != 0;
+        uint32_t m = 0, off = 0;
+        if (!hand_over) {
+            off = block_excl_scan<NT>(popcount64(mask), s_warp_sums, &m);
+            hand_over = m == 0 || m > MC;
+        }
+        uint32_t flags = 0, cnt = 0;
+        const uint32_t per = (m + NT - 1) / NT;
+        if (!hand_over) {
+            sparseC_compact<NT, C1>(tid, mask, off, m, S);
+            __syncthreads();
+            bool bad;
+            cnt = sparseS_select<NT>(tid, m, per, P, T, S, &flags, &bad);
+            hand_over = __syncthreads_or(bad) != 0;
+        }
+        if (hand_over) {   // uniform: a dense kernel recomputes the tile
+            if (tid == 0) P.fallback_tiles[atomicAdd(P.fallback_count, 1u)] = tile_id;
+            continue;
+        }
+        uint32_t total;
+        const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
+        if (tid == 0) s_gbase = claim_slots(P, tile_id, total);
+        __syncthreads();
+        if (cnt) sparseD_write<NT>(tid, per, flags, s_gbase + excl, P, T, S);
     }
 }
 
@@ -206,14 +270,28 @@ const KernelConfig kConfigs[] = {
     SW_CFG(128, 21),
     SW_CFG(128, 23),
     SW_CFG(64, 33),
+    SW_CFG(256, 33),  // holds the sparse kernel's 8192-k-mer tiles
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 constexpr int kLargeWindowConfig = 3;
+constexpr int kSparseDenseConfig = 8;
+// the sparse kernel: 128 threads x 64 k-mers, 24 private candidate slots per thread
+constexpr int kSparseNT = 128, kSparseC1 = 64, kSparseCap = 24;
+constexpr uint32_t kSparseTK = kSparseNT * kSparseC1;
 
 }  // namespace
 
-int sketch_pick_config(uint32_t w, uint32_t* tk_out)
+int sketch_pick_config(uint32_t w, uint32_t* tk_out, bool* sparse_out)
 {
+    *sparse_out = false;
+    // large windows: the sparse kernel (SEQWIN_SKETCH_DENSE=1 keeps every tile on the dense kernels)
+    if (w >= kSparseMinW && (uint64_t)w * 4 <= kSparseTK && !getenv("SEQWIN_SKETCH_DENSE") &&
+        !getenv("SEQWIN_SKETCH_CONFIG") && !getenv("SEQWIN_SKETCH_GENERIC")) {
+        static_assert(kSparseTK <= 256 * 33, "the hand-over configuration must hold a sparse tile");
+        *sparse_out = true;
+        *tk_out = kSparseTK;
+        return kSparseDenseConfig;
+    }
     int cfg = 0;
     if (const char* e = getenv("SEQWIN_SKETCH_CONFIG")) cfg = std::max(0, std::min(kNumConfigs - 1, atoi(e)));
     // keep the halo (w k-mers re-hashed per tile) under ~25 % of the tile
@@ -308,7 +386,7 @@ __global__ void plan_fill_kernel(RecordRuns rr, uint32_t R, uint32_t k, uint32_t
 DevPlan make_plan(const sw_dev_batch& d, uint32_t k, uint32_t w, cudaStream_t s, bool want_rec_tile_off)
 {
     DevPlan dp;
-    dp.config = sketch_pick_config(w, &dp.tk);
+    dp.config = sketch_pick_config(w, &dp.tk, &dp.sparse);
     const uint32_t R = (uint32_t)d.meta.rec_len.size();
     if (R == 0) return dp;
     const uint32_t tw = dp.tk - w;
@@ -353,21 +431,37 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         return;
     }
     const KernelConfig& kc = kConfigs[plan.config];
-    const uint32_t tk = (uint32_t)kc.nt * kc.c1;
     const bool fast = (w - 1 >= (uint32_t)kc.c1) && !getenv("SEQWIN_SKETCH_GENERIC");
-    auto kernel = fast ? kc.fast : kc.generic;
-    const size_t smem = tile_smem_bytes(tk, fast ? (uint32_t)kc.nt : tk / 9 + 2);
-    SW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ctas_per_sm = 0;
-    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kc.nt, smem));
-    if (ctas_per_sm < 1) fail_runtime("sketch kernel does not fit on this device");
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(plan.n_tiles, (uint64_t)sm_count() * ctas_per_sm);
+    auto dense_kernel = fast ? kc.fast : kc.generic;
+    const size_t dense_smem = tile_smem_bytes((uint32_t)kc.nt * kc.c1, fast ? (uint32_t)kc.nt : (uint32_t)kc.nt * kc.c1 / 9 + 2);
+    SW_CUDA(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
+    int dense_ctas = 0;
+    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dense_ctas, dense_kernel, kc.nt, dense_smem));
+    if (dense_ctas < 1) fail_runtime("sketch kernel does not fit on this device");
+    const uint32_t dense_grid = (uint32_t)std::min<uint64_t>(plan.n_tiles, (uint64_t)sm_count() * dense_ctas);
+    // first pass: the sparse kernel when the plan was cut for it, else the dense kernel itself
+    auto kernel = dense_kernel;
+    size_t smem = dense_smem;
+    int nt = kc.nt;
+    uint32_t grid = dense_grid;
+    if (plan.sparse) {
+        kernel = sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap>;
+        smem = sparse_smem_bytes(kSparseNT, kSparseCap);
+        nt = kSparseNT;
+        SW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int ctas = 0;
+        SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, nt, smem));
+        if (ctas < 1) fail_runtime("sketch kernel does not fit on this device");
+        grid = (uint32_t)std::min<uint64_t>(plan.n_tiles, (uint64_t)sm_count() * ctas);
+    }
+    DevBuf<uint32_t> fallback_tiles(plan.sparse ? plan.n_tiles : 0, s, true);
 
     // [0, n_tiles): per-tile counts (scanned in place into ordered offsets); then the slots
     DevBuf<unsigned long long> tile_info((size_t)plan.n_tiles * 2, s, true);
-    // [0] cursor, [1] scan total, [2..] one ticket counter (as u32) per launch
+    // [0] cursor, [1] scan total, [2] handed-over tiles | their ticket counter << 32,
+    // [3..] one ticket counter (as u32) per launch
     const size_t n_launch = chunks && !chunks->empty() ? chunks->size() : 1;
-    DevBuf<unsigned long long> counters(2 + n_launch, s, true);
+    DevBuf<unsigned long long> counters(3 + n_launch, s, true);
 
     // expected density 2/(w+1); leave 50 % headroom and re-run with the exact size on overflow
     uint64_t capacity = (uint64_t)((double)plan.n_kmers * 3.0 / ((double)w + 1.0)) + 4096;
@@ -403,6 +497,11 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.tile_slot = tile_info.p + plan.n_tiles;
         P.table = make_roll_table(k);
         P.tetra = device_tetra_table(s);
+        P.cand_hi = sparse_cand_hi(w);
+        P.fallback_count = reinterpret_cast<unsigned int*>(counters.p + 2);
+        P.fallback_tiles = fallback_tiles.p;
+        P.tile_list = nullptr;
+        P.tile_list_n = nullptr;
         cudaEventRecord(ev[0], s);
         for (size_t c = 0; c < n_launch; ++c) {
             P.tile_lo = 0;
@@ -414,9 +513,20 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
                 P.tile_lo = ch.tile_lo;
                 P.n_tiles = ch.tile_hi;
             }
-            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 2 + c);
+            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 3 + c);
             const uint32_t g = (uint32_t)std::min<uint64_t>(P.n_tiles - P.tile_lo, grid);
-            kernel<<<g, kc.nt, smem, s>>>(P);
+            kernel<<<g, nt, smem, s>>>(P);
+            SW_CUDA(cudaGetLastError());
+            ++out.launches;
+        }
+        if (plan.sparse) {
+            // the tiles the sparse kernel handed over (few; the count stays on the device)
+            P.tile_lo = 0;
+            P.n_tiles = plan.n_tiles;
+            P.tile_list = fallback_tiles.p;
+            P.tile_list_n = P.fallback_count;
+            P.tile_counter = P.fallback_count + 1;
+            dense_kernel<<<dense_grid, kc.nt, dense_smem, s>>>(P);
             SW_CUDA(cudaGetLastError());
             ++out.launches;
         }

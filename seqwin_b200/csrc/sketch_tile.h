@@ -53,6 +53,12 @@ struct SketchParams {
     unsigned long long* tile_count;   // [n_tiles] minimizers emitted by each tile
     unsigned long long* tile_slot;    // [n_tiles] first slot of each tile
     unsigned int* tile_counter;       // ticket dispenser
+    // sparse path (below): candidate threshold and the list of tiles it hands to the dense kernels
+    uint32_t cand_hi;                 // candidates are k-mers with (h0 >> 32) < cand_hi
+    unsigned int* fallback_count;     // sparse kernel: number of tiles appended to fallback_tiles
+    uint32_t* fallback_tiles;         // [n_tiles]
+    const uint32_t* tile_list;        // dense kernels: if set, ticket i handles tile tile_list[i] ...
+    const unsigned int* tile_list_n;  // ... for i < *tile_list_n
     const TetraTable* tetra;          // 4-base warm-up tables (device global)
     RollTable table;
 };
@@ -591,6 +597,239 @@ SW_HD void fastD_write(const SketchParams& P, const Tile& T, const TileSmem& S, 
     const uint32_t n_out = (uint32_t)__builtin_popcountll(st.mask);
 #endif
     for (uint32_t i = 0; i < n_out; ++i) write_minimizer(slot++, S.amin[j0 + i], P, T, S);
+}
+
+// ---- sparse path: large windows, one run of hashable bases per tile ---------------------------------
+//
+// A k-mer p of the tile is selected by some window (minimizer.cpp:69-87, rightmost minimum) iff a
+// window of w k-mers fits between its nearest strictly smaller k-mer on the left (L) and its nearest
+// smaller-or-equal k-mer on the right (R): R - L - 1 >= w.  It is then the selection of exactly the
+// windows [max(L + 1, p - w + 1), min(p, R - w)], and selections are monotone in the window index,
+// so "emit when the selection changes" (minimizer.cpp:41-47) = every such p once, in position order.
+//
+// Only small hashes can be selected: if every window holds at least one CANDIDATE, a k-mer with
+// (h0 >> 32) < cand_hi, then every selection is a candidate and L / R need only be looked for among
+// candidates.  cand_hi keeps about 16 candidates per window, so each thread
+//   A  hashes C1 consecutive k-mers and appends the few candidates to a private list  (no h0 array)
+//   C  the lists are compacted into one position-ordered array per tile
+//   S  one thread per candidate scans its neighbours (at most those within w positions) for L and R
+//   D  selected candidates are written out
+// Tiles the argument does not cover -- a window without candidate (low-complexity sequence), a
+// private list that overflows, a tile that crosses a gap -- are appended to fallback_tiles and
+// recomputed by the dense kernels above.  Both paths are exact; the split only decides who does it.
+struct SparseSmem {
+    RollEntry* tab;   // [20]
+    uint64_t* list;   // [CAP][NT] slot-major private candidate lists (h0)
+    uint64_t* key;    // [MC + 2]  dense candidates: tile-local index << 32 | h0 >> 32; [0], [m + 1] sentinels
+    uint32_t* lo;     // [MC + 2]  low word of h0
+};
+
+constexpr uint32_t kSparsePerThread = 8;   // dense capacity MC = NT * kSparsePerThread
+constexpr uint32_t kSparseCheck = 8;       // a private list is checked for room every 8 steps
+constexpr uint32_t kSparseMinW = 96;       // below this the dense kernels are used for every tile
+constexpr double kSparseCandPerWindow = 16.0;
+
+SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
+{
+    const size_t mc = (size_t)nt * kSparsePerThread + 2;
+    return sizeof(RollEntry) * 20 + sizeof(uint64_t) * (size_t)cap * nt + sizeof(uint64_t) * mc +
+           ((sizeof(uint32_t) * mc + 15) & ~(size_t)15);
+}
+
+SW_HD SparseSmem carve_sparse_smem(unsigned char* base, uint32_t nt, uint32_t cap)
+{
+    const size_t mc = (size_t)nt * kSparsePerThread + 2;
+    SparseSmem s;
+    s.tab = reinterpret_cast<RollEntry*>(base);
+    s.list = reinterpret_cast<uint64_t*>(base + sizeof(RollEntry) * 20);
+    s.key = s.list + (size_t)cap * nt;
+    s.lo = reinterpret_cast<uint32_t*>(s.key + mc);
+    return s;
+}
+
+// (h0 >> 32) threshold that leaves about kSparseCandPerWindow candidates in a window of w k-mers
+inline uint32_t sparse_cand_hi(uint32_t w)
+{
+    const double f = kSparseCandPerWindow / (double)w;
+    return f >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(f * 4294967296.0);
+}
+
+// A: hash the thread's C1 k-mers; candidates go to list[slot * NT + tid] in position order and set
+// their bit in *mask.  Returns false when the private list would overflow (tile -> dense path).
+template <int NT, int C1, int CAP>
+SW_HD bool sparseA_hash(int tid, const SketchParams& P, const Tile& T, const SparseSmem& S, uint64_t* mask_out)
+{
+    static_assert(C1 <= 64 && CAP > (int)kSparseCheck, "mask is 64 bits; the list needs room for one check interval");
+    *mask_out = 0;
+    const uint32_t j0 = (uint32_t)tid * C1;
+    if (j0 >= T.n_kmers) return true;
+    const uint32_t* W = P.words + P.rec_word_off[T.rec];
+    const Piece pc = P.pieces[T.piece_lo];
+    // reads may run past the tile's last k-mer (kTailPadWords of slack); those steps are masked off below
+    const uint64_t p0 = (uint64_t)pc.pos + ((uint64_t)T.e0 + j0 - pc.kidx);
+    uint64_t fwd, rev;
+    seed_kmer(W, p0, P.k, S.tab, P.tetra, &fwd, &rev);
+    uint64_t* slot = S.list + tid;
+    uint64_t* const slot_limit = slot + (size_t)(CAP - (int)kSparseCheck) * NT;   // room for one more interval
+    uint32_t thr = P.cand_hi;
+    uint32_t m_lo = 0, m_hi = 0;
+    bool ok = true;
+    {
+        const uint64_t h = fwd + rev;
+        if ((uint32_t)(h >> 32) < thr) { *slot = h; slot += NT; m_lo |= 1u; }
+    }
+#pragma unroll
+    for (int b = 0; b < (C1 - 1 + 15) / 16; ++b) {
+        const uint32_t in = fetch16(W, p0 + P.k + 16 * b);
+        const uint32_t out = fetch16(W, p0 + 16 * b);
+        const uint32_t x = (in & 0x33333333u) | ((out & 0x33333333u) << 2);
+        const uint32_t y = ((in >> 2) & 0x33333333u) | (out & 0xCCCCCCCCu);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int n = 16 * b + s + 1;
+            if (n < C1) {
+                if (n % (int)kSparseCheck == 0 && n > CAP - (int)kSparseCheck) {
+                    if (slot > slot_limit) { ok = false; thr = 0; }   // stop recording: the tile is recomputed
+                }
+                const uint32_t idx = (((s & 1) ? y : x) >> (4 * (s >> 1))) & 15u;
+                roll_step(fwd, rev, S.tab[idx]);
+                const uint64_t h = fwd + rev;
+                if ((uint32_t)(h >> 32) < thr) {
+                    *slot = h;
+                    slot += NT;
+                    if (n < 32) m_lo |= 1u << (n & 31); else m_hi |= 1u << (n & 31);
+                }
+            }
+        }
+    }
+    uint64_t mask = ((uint64_t)m_hi << 32) | m_lo;
+    const uint32_t lim = T.n_kmers - j0;   // k-mers of this chunk that exist
+    if (lim < (uint32_t)C1) mask &= (1ULL << lim) - 1;
+    *mask_out = mask;
+    return ok;
+}
+
+SW_HD uint32_t popcount64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(x);
+#else
+    return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+
+SW_HD uint32_t ctz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffsll((long long)x) - 1);
+#else
+    return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+
+// C: copy the thread's candidates to dense slots [1 + off, ...); thread 0 writes the sentinels
+// (h0 word 0 stops every scan; they are recognised by their index).
+template <int NT, int C1>
+SW_HD void sparseC_compact(int tid, uint64_t mask, uint32_t off, uint32_t m, const SparseSmem& S)
+{
+    const uint32_t j0 = (uint32_t)tid * C1;
+    uint32_t s = 0;
+    while (mask) {
+        const uint32_t b = ctz64(mask);
+        mask &= mask - 1;
+        const uint64_t h = S.list[(size_t)s * NT + tid];
+        S.key[1 + off + s] = ((uint64_t)(j0 + b) << 32) | (h >> 32);
+        S.lo[1 + off + s] = (uint32_t)h;
+        ++s;
+    }
+    if (tid == 0) {
+        S.key[0] = 0;
+        S.lo[0] = 0;
+        S.key[m + 1] = 0;
+        S.lo[m + 1] = 0;
+    }
+}
+
+// S: thread owns dense candidates [1 + tid * per, 1 + (tid + 1) * per) of m.  Returns the number
+// selected (bit i of *flags: candidate 1 + tid * per + i); *bad is set if some window of the tile
+// holds no candidate.
+template <int NT>
+SW_HD uint32_t sparseS_select(int tid, uint32_t m, uint32_t per, const SketchParams& P, const Tile& T,
+                              const SparseSmem& S, uint32_t* flags, bool* bad)
+{
+    const int32_t w = (int32_t)P.w, n = (int32_t)T.n_kmers;
+    uint32_t f = 0, cnt = 0;
+    *bad = false;
+    for (uint32_t i = 0; i < per; ++i) {
+        const uint32_t j = 1 + (uint32_t)tid * per + i;
+        if (j > m) break;
+        const uint64_t kj = S.key[j];
+        const int32_t p = (int32_t)(kj >> 32);
+        const uint32_t hh = (uint32_t)kj, hl = S.lo[j];
+        // coverage: no stretch of w k-mers without candidate before this one / after the last one
+        const int32_t prev = j == 1 ? -1 : (int32_t)(S.key[j - 1] >> 32);
+        if (p - prev > w || (j == m && n - p > w)) *bad = true;
+        // nearest strictly smaller candidate on the left, looked for down to position p - w + 1
+        int32_t L;
+        {
+            const int32_t reach = p - w;   // a candidate at or before it cannot matter
+            uint32_t q = j - 1;
+            for (;;) {
+                const uint64_t kq = S.key[q];
+                const int32_t pq = (int32_t)(kq >> 32);
+                if ((uint32_t)kq <= hh || pq <= reach) {
+                    if (q == 0) { L = -1; break; }
+                    if (pq <= reach || (uint32_t)kq < hh || S.lo[q] < hl) { L = pq; break; }
+                }
+                --q;
+            }
+        }
+        // nearest smaller-or-equal candidate on the right, looked for up to position p + w - 1
+        int32_t R;
+        {
+            const int32_t reach = p + w;
+            uint32_t q = j + 1;
+            for (;;) {
+                const uint64_t kq = S.key[q];
+                const int32_t pq = (int32_t)(kq >> 32);
+                if ((uint32_t)kq <= hh || pq >= reach) {
+                    if (q == m + 1) { R = n; break; }
+                    if (pq >= reach || (uint32_t)kq < hh || S.lo[q] <= hl) { R = pq; break; }
+                }
+                ++q;
+            }
+        }
+        const int32_t i_lo = L + 1 > p - w + 1 ? L + 1 : p - w + 1;
+        const int32_t i_hi = p < R - w ? p : R - w;
+        // window 0 of a tile that is not the record's first only provides the previous selection
+        if (i_lo <= i_hi && (T.first != 0 || i_lo >= 1)) {
+            f |= 1u << i;
+            ++cnt;
+        }
+    }
+    *flags = f;
+    return cnt;
+}
+
+// D: write the thread's selected candidates to consecutive global slots.
+template <int NT>
+SW_HD void sparseD_write(int tid, uint32_t per, uint32_t flags, unsigned long long slot, const SketchParams& P,
+                         const Tile& T, const SparseSmem& S)
+{
+    const Piece pc = P.pieces[T.piece_lo];
+    while (flags) {
+        const uint32_t i = ctz64(flags);
+        flags &= flags - 1;
+        const uint32_t j = 1 + (uint32_t)tid * per + i;
+        const uint64_t kj = S.key[j];
+        const uint64_t h = (kj << 32) | S.lo[j];
+        if (slot < P.capacity) {
+            P.out_key[slot] = h1_of(h, P.h1_mult);
+            const uint32_t pos = pc.pos + (uint32_t)((uint64_t)T.e0 + (uint32_t)(kj >> 32) - pc.kidx);
+            P.out_val[slot] = (uint64_t)pos | ((uint64_t)(P.rec_base + T.rec) << 32);
+        }
+        ++slot;
+    }
 }
 
 }  // namespace sw

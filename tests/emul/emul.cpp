@@ -21,17 +21,14 @@ void* alloc_host(size_t bytes, bool* pinned)
 }
 void free_host(void* p, bool) { free(p); }
 
-template <int NT, int C1>
-static void emulate(const sw_batch& b, uint32_t k, uint32_t w, std::vector<uint64_t>& keys,
-                    std::vector<uint64_t>& vals, uint32_t* n_tiles_out, int force_generic)
+struct EmulOut {
+    std::vector<uint64_t> ukeys, uvals;
+    std::vector<unsigned long long> tile_count, tile_slot;
+    unsigned long long cursor = 0;
+};
+
+static SketchParams make_params(const sw_batch& b, const Plan& plan, uint32_t k, uint32_t w, uint32_t c1, EmulOut& o)
 {
-    constexpr uint32_t TK = NT * C1;
-    Plan plan = plan_tiles(b, k, w, TK);
-    *n_tiles_out = (uint32_t)plan.tiles.size();
-    const bool fast = (w - 1 >= (uint32_t)C1) && !force_generic;
-    const uint32_t nc = fast ? (uint32_t)NT : TK / 9 + 2;
-    std::vector<unsigned char> smem(tile_smem_bytes(TK, nc) + 64);
-    TileSmem S = carve_tile_smem(smem.data(), TK, nc);
     SketchParams P;
     memset(&P, 0, sizeof P);
     P.words = b.words;
@@ -41,76 +38,165 @@ static void emulate(const sw_batch& b, uint32_t k, uint32_t w, std::vector<uint6
     P.n_tiles = (uint32_t)plan.tiles.size();
     P.k = k;
     P.w = w;
-    P.c2 = choose_c2(w, C1);
+    P.c2 = choose_c2(w, c1);
     P.rec_base = 0;
     P.h1_mult = h1_multiplier(k);
     P.table = make_roll_table(k);
     static TetraTable tetra;
     make_tetra_table(tetra);
     P.tetra = &tetra;
-    std::vector<uint64_t> ukeys(plan.n_windows, 0), uvals(plan.n_windows, 0);
-    std::vector<unsigned long long> tile_count(P.n_tiles, 0), tile_slot(P.n_tiles, 0);
-    P.out_key = ukeys.data();
-    P.out_val = uvals.data();
+    o.ukeys.assign(plan.n_windows, 0);
+    o.uvals.assign(plan.n_windows, 0);
+    o.tile_count.assign(P.n_tiles, 0);
+    o.tile_slot.assign(P.n_tiles, 0);
+    P.out_key = o.ukeys.data();
+    P.out_val = o.uvals.data();
     P.capacity = plan.n_windows;
-    unsigned long long cursor = 0;
-    // tiles complete in arbitrary order on the device: emulate a scrambled completion order
-    std::vector<uint32_t> order(P.n_tiles);
-    for (uint32_t t = 0; t < P.n_tiles; ++t) order[t] = t;
-    for (uint32_t t = 0; t + 1 < P.n_tiles; t += 2) std::swap(order[t], order[t + 1]);
+    return P;
+}
+
+// tiles complete in arbitrary order on the device: emulate a scrambled completion order
+static std::vector<uint32_t> scrambled_order(uint32_t n)
+{
+    std::vector<uint32_t> order(n);
+    for (uint32_t t = 0; t < n; ++t) order[t] = t;
+    for (uint32_t t = 0; t + 1 < n; t += 2) std::swap(order[t], order[t + 1]);
     std::reverse(order.begin(), order.end());
-    for (uint32_t oi = 0; oi < P.n_tiles; ++oi) {
-        const uint32_t t = order[oi];
-        // poison shared memory between tiles so that reads of stale data show up as mismatches
+    return order;
+}
+
+// reorder_kernel: exclusive scan of the counts in tile order, then segment copy
+static void reorder(const EmulOut& o, std::vector<uint64_t>& keys, std::vector<uint64_t>& vals)
+{
+    keys.assign(o.cursor, 0);
+    vals.assign(o.cursor, 0);
+    unsigned long long off = 0;
+    for (size_t t = 0; t < o.tile_count.size(); ++t) {
+        for (unsigned long long i = 0; i < o.tile_count[t]; ++i) {
+            keys[off + i] = o.ukeys[o.tile_slot[t] + i];
+            vals[off + i] = o.uvals[o.tile_slot[t] + i];
+        }
+        off += o.tile_count[t];
+    }
+}
+
+// one tile through the dense kernels' phases (sketch_fast_kernel / sketch_generic_kernel)
+template <int NT, int C1>
+static void dense_tile(const SketchParams& P, uint32_t t, bool fast, EmulOut& o)
+{
+    constexpr uint32_t TK = NT * C1;
+    const uint32_t w = P.w;
+    const uint32_t nc = fast ? (uint32_t)NT : TK / 9 + 2;
+    std::vector<unsigned char> smem(tile_smem_bytes(TK, nc) + 64);
+    TileSmem S = carve_tile_smem(smem.data(), TK, nc);
+    // poison shared memory between tiles so that reads of stale data show up as mismatches
+    memset(smem.data(), 0xA5, smem.size());
+    for (int i = 0; i < 20; ++i) S.tab[i] = P.table.e[i];
+    const Tile T = P.tiles[t];
+    std::vector<uint32_t> excl(NT);
+    uint32_t total = 0;
+    if (fast) {
+        std::vector<FastState> st(NT);
+        std::vector<uint32_t> cnt(NT, 0), active;
+        for (int tid = 0; tid < NT; ++tid) fastA_hash_prefix<NT, C1>(tid, P, T, S);
+        for (int tid = 0; tid < NT; ++tid) fastB1_boundary<NT, C1>(tid, P, T, S);
+        for (int tid = 0; tid < NT; ++tid)
+            if (fast_chunk_active<NT, C1>(tid, P, T, S)) active.push_back((uint32_t)tid);
+        for (size_t i = 0; i < active.size(); ++i) cnt[i] = fastB2_windows<NT, C1>(active[i], P, T, S, st[i]);
+        for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += cnt[tid]; }
+        o.tile_count[t] = total;
+        o.tile_slot[t] = o.cursor;
+        for (int tid = 0; tid < NT; ++tid)
+            if (cnt[tid]) fastD_write<NT, C1>(P, T, S, st[tid], o.cursor + excl[tid]);
+    } else {
+        for (int tid = 0; tid < NT; ++tid) phase1_hash<NT, C1>(tid, P, T, S);
+        if (P.c2) {
+            for (int tid = 0; tid < NT; ++tid) phase2a_prefix<NT>(tid, P, T, S);
+            for (int tid = 0; tid < NT; ++tid) phase2b_windows<NT>(tid, P, T, S);
+        } else {
+            for (int tid = 0; tid < NT; ++tid) phase2_direct<NT>(tid, P, T, S);
+        }
+        const uint32_t n_eval = T.n_kmers - w + 1;
+        const uint32_t c3 = (n_eval + NT - 1) / NT;
+        std::vector<uint64_t> masks(NT);
+        for (int tid = 0; tid < NT; ++tid) masks[tid] = phase3a_flags(tid, c3, T, w, S);
+        for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += (uint32_t)__builtin_popcountll(masks[tid]); }
+        for (int tid = 0; tid < NT; ++tid) phase3b_stage(tid, c3, masks[tid], excl[tid], S);
+        o.tile_count[t] = total;
+        o.tile_slot[t] = o.cursor;
+        for (uint32_t i = 0; i < total; ++i) phase3c_write(i, o.cursor, P, T, S);
+    }
+    o.cursor += total;
+}
+
+template <int NT, int C1>
+static void emulate(const sw_batch& b, uint32_t k, uint32_t w, std::vector<uint64_t>& keys,
+                    std::vector<uint64_t>& vals, uint32_t* n_tiles_out, int force_generic)
+{
+    constexpr uint32_t TK = NT * C1;
+    Plan plan = plan_tiles(b, k, w, TK);
+    *n_tiles_out = (uint32_t)plan.tiles.size();
+    const bool fast = (w - 1 >= (uint32_t)C1) && !force_generic;
+    EmulOut o;
+    const SketchParams P = make_params(b, plan, k, w, C1, o);
+    for (uint32_t t : scrambled_order(P.n_tiles)) dense_tile<NT, C1>(P, t, fast, o);
+    reorder(o, keys, vals);
+}
+
+// sketch_sparse_kernel<NT, C1, CAP>, with sketch_fast/generic_kernel<FNT, FC1> for the tiles it hands over
+template <int NT, int C1, int CAP, int FNT, int FC1>
+static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double cand_per_window, std::vector<uint64_t>& keys,
+                           std::vector<uint64_t>& vals, uint32_t* n_tiles_out, uint32_t* n_fallback_out)
+{
+    constexpr uint32_t TK = NT * C1;
+    static_assert(FNT * FC1 >= NT * C1, "the hand-over configuration must hold a sparse tile");
+    Plan plan = plan_tiles(b, k, w, TK);
+    *n_tiles_out = (uint32_t)plan.tiles.size();
+    EmulOut o;
+    SketchParams P = make_params(b, plan, k, w, FC1, o);
+    const double f = cand_per_window / (double)w;
+    P.cand_hi = cand_per_window <= 0 ? sparse_cand_hi(w) : (f >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(f * 4294967296.0));
+    constexpr uint32_t MC = NT * kSparsePerThread;
+    std::vector<unsigned char> smem(sparse_smem_bytes(NT, CAP) + 64);
+    SparseSmem S = carve_sparse_smem(smem.data(), NT, CAP);
+    std::vector<uint32_t> fallback;
+    for (uint32_t t : scrambled_order(P.n_tiles)) {
         memset(smem.data(), 0xA5, smem.size());
         for (int i = 0; i < 20; ++i) S.tab[i] = P.table.e[i];
-        const Tile T = plan.tiles[t];
-        std::vector<uint32_t> excl(NT);
-        uint32_t total = 0;
-        if (fast) {
-            std::vector<FastState> st(NT);
-            std::vector<uint32_t> cnt(NT, 0), active;
-            for (int tid = 0; tid < NT; ++tid) fastA_hash_prefix<NT, C1>(tid, P, T, S);
-            for (int tid = 0; tid < NT; ++tid) fastB1_boundary<NT, C1>(tid, P, T, S);
+        const Tile T = P.tiles[t];
+        std::vector<uint64_t> mask(NT, 0);
+        bool hand_over = T.n_pieces != 1;
+        if (!hand_over)
             for (int tid = 0; tid < NT; ++tid)
-                if (fast_chunk_active<NT, C1>(tid, P, T, S)) active.push_back((uint32_t)tid);
-            for (size_t i = 0; i < active.size(); ++i) cnt[i] = fastB2_windows<NT, C1>(active[i], P, T, S, st[i]);
-            for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += cnt[tid]; }
-            tile_count[t] = total;
-            tile_slot[t] = cursor;
-            for (int tid = 0; tid < NT; ++tid)
-                if (cnt[tid]) fastD_write<NT, C1>(P, T, S, st[tid], cursor + excl[tid]);
-        } else {
-            for (int tid = 0; tid < NT; ++tid) phase1_hash<NT, C1>(tid, P, T, S);
-            if (P.c2) {
-                for (int tid = 0; tid < NT; ++tid) phase2a_prefix<NT>(tid, P, T, S);
-                for (int tid = 0; tid < NT; ++tid) phase2b_windows<NT>(tid, P, T, S);
-            } else {
-                for (int tid = 0; tid < NT; ++tid) phase2_direct<NT>(tid, P, T, S);
+                if (!sparseA_hash<NT, C1, CAP>(tid, P, T, S, &mask[tid])) hand_over = true;
+        std::vector<uint32_t> off(NT, 0), flags(NT, 0), cnt(NT, 0), excl(NT, 0);
+        uint32_t m = 0;
+        if (!hand_over) {
+            for (int tid = 0; tid < NT; ++tid) { off[tid] = m; m += (uint32_t)__builtin_popcountll(mask[tid]); }
+            hand_over = m == 0 || m > MC;
+        }
+        const uint32_t per = (m + NT - 1) / NT;
+        if (!hand_over) {
+            for (int tid = 0; tid < NT; ++tid) sparseC_compact<NT, C1>(tid, mask[tid], off[tid], m, S);
+            for (int tid = 0; tid < NT; ++tid) {
+                bool bad;
+                cnt[tid] = sparseS_select<NT>(tid, m, per, P, T, S, &flags[tid], &bad);
+                if (bad) hand_over = true;
             }
-            const uint32_t n_eval = T.n_kmers - w + 1;
-            const uint32_t c3 = (n_eval + NT - 1) / NT;
-            std::vector<uint64_t> masks(NT);
-            for (int tid = 0; tid < NT; ++tid) masks[tid] = phase3a_flags(tid, c3, T, w, S);
-            for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += (uint32_t)__builtin_popcountll(masks[tid]); }
-            for (int tid = 0; tid < NT; ++tid) phase3b_stage(tid, c3, masks[tid], excl[tid], S);
-            tile_count[t] = total;
-            tile_slot[t] = cursor;
-            for (uint32_t i = 0; i < total; ++i) phase3c_write(i, cursor, P, T, S);
         }
-        cursor += total;
+        if (hand_over) { fallback.push_back(t); continue; }
+        uint32_t total = 0;
+        for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += cnt[tid]; }
+        o.tile_count[t] = total;
+        o.tile_slot[t] = o.cursor;
+        for (int tid = 0; tid < NT; ++tid)
+            if (cnt[tid]) sparseD_write<NT>(tid, per, flags[tid], o.cursor + excl[tid], P, T, S);
+        o.cursor += total;
     }
-    // reorder_kernel: exclusive scan of the counts in tile order, then segment copy
-    keys.assign(cursor, 0);
-    vals.assign(cursor, 0);
-    unsigned long long off = 0;
-    for (uint32_t t = 0; t < P.n_tiles; ++t) {
-        for (unsigned long long i = 0; i < tile_count[t]; ++i) {
-            keys[off + i] = ukeys[tile_slot[t] + i];
-            vals[off + i] = uvals[tile_slot[t] + i];
-        }
-        off += tile_count[t];
-    }
+    *n_fallback_out = (uint32_t)fallback.size();
+    const bool fast = w - 1 >= (uint32_t)FC1;
+    for (uint32_t t : fallback) dense_tile<FNT, FC1>(P, t, fast, o);
+    reorder(o, keys, vals);
 }
 }  // namespace sw
 
@@ -144,6 +230,37 @@ long emul_sketch(const uint8_t* const* seqs, const uint32_t* lens, size_t n_reco
         return (long)keys.size();
     } catch (const std::exception& e) {
         fprintf(stderr, "emul_sketch: %s\n", e.what());
+        return -1;
+    }
+}
+
+// sparse kernel + dense hand-over; cand_per_window <= 0 uses the library's threshold
+long emul_sketch_sparse(const uint8_t* const* seqs, const uint32_t* lens, size_t n_records, uint32_t k, uint32_t w,
+                        int nt, int c1, double cand_per_window, uint64_t* h1_out, uint32_t* pos_out, uint32_t* rec_out,
+                        size_t cap, uint32_t* n_tiles_out, uint32_t* n_fallback_out)
+{
+    try {
+        std::vector<uint32_t> asm_of(n_records, 0);
+        sw_batch* b = sw::batch_from_memory(seqs, lens, asm_of.data(), nullptr, n_records, 1, 1);
+        std::vector<uint64_t> keys, vals;
+        if (nt == 128 && c1 == 64)
+            sw::emulate_sparse<128, 64, 24, 256, 33>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
+        else if (nt == 8 && c1 == 64)
+            sw::emulate_sparse<8, 64, 24, 16, 33>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
+        else if (nt == 16 && c1 == 32)
+            sw::emulate_sparse<16, 32, 12, 32, 17>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
+        else if (nt == 4 && c1 == 48)
+            sw::emulate_sparse<4, 48, 16, 8, 25>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
+        else { delete b; return -2; }
+        delete b;
+        for (size_t i = 0; i < keys.size() && i < cap; ++i) {
+            h1_out[i] = keys[i];
+            pos_out[i] = (uint32_t)vals[i];
+            rec_out[i] = (uint32_t)(vals[i] >> 32);
+        }
+        return (long)keys.size();
+    } catch (const std::exception& e) {
+        fprintf(stderr, "emul_sketch_sparse: %s\n", e.what());
         return -1;
     }
 }

@@ -24,6 +24,7 @@ def emul():
                                str(EMUL_DIR / "emul.cpp"), "-lz"])
     L = C.CDLL(str(so))
     L.emul_sketch.restype = C.c_long
+    L.emul_sketch_sparse.restype = C.c_long
 
     def run(seqs, k, w, nt, c1, force_generic=0):
         n = len(seqs)
@@ -38,6 +39,21 @@ def emul():
                           C.c_size_t(cap), C.byref(nt_out))
         assert m >= 0, f"emulator failed ({m})"
         return h1[:m], pos[:m], rec[:m], nt_out.value
+
+    def run_sparse(seqs, k, w, nt, c1, cand_per_window=0.0):
+        n = len(seqs)
+        arrs = [np.frombuffer(s, dtype=np.uint8) for s in seqs]
+        ptrs = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+        cap = sum(len(s) for s in seqs) + 16
+        h1, pos, rec = np.empty(cap, np.uint64), np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        nt_out, nf_out = C.c_uint32(), C.c_uint32()
+        m = L.emul_sketch_sparse(ptrs, C.c_void_p(lens.ctypes.data), C.c_size_t(n), C.c_uint32(k), C.c_uint32(w), nt, c1,
+                                 C.c_double(cand_per_window), C.c_void_p(h1.ctypes.data), C.c_void_p(pos.ctypes.data),
+                                 C.c_void_p(rec.ctypes.data), C.c_size_t(cap), C.byref(nt_out), C.byref(nf_out))
+        assert m >= 0, f"emulator failed ({m})"
+        return h1[:m], pos[:m], rec[:m], nt_out.value, nf_out.value
+    run.sparse = run_sparse
     return run
 
 
@@ -85,3 +101,43 @@ def test_emulated_kernel_matches_oracle(emul, cfg):
             assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (cfg, k, w, force_generic)
         n_multi_tile += n_tiles > len(seqs)
     assert n_multi_tile > 0
+
+
+SPARSE_CONFIGS = [(128, 64), (8, 64), (16, 32), (4, 48)]
+SPARSE_KW = [(21, 200), (21, 96), (31, 150), (15, 128), (17, 333), (7, 100), (21, 120)]
+
+
+@pytest.mark.parametrize("cfg", SPARSE_CONFIGS, ids=lambda c: f"nt{c[0]}c{c[1]}")
+def test_emulated_sparse_kernel_matches_oracle(emul, cfg):
+    """sketch_sparse_kernel's phases (candidate lists, neighbour scans) plus the dense hand-over.
+    Thresholds from 'a few candidates per window' (most tiles handed over for lack of coverage) to
+    'every k-mer is a candidate' (private lists overflow) must all give the oracle's stream."""
+    nt, c1 = cfg
+    rng = np.random.default_rng(nt * 77 + c1)
+    n_sparse_tiles = n_fallback_tiles = 0
+    for k, w in SPARSE_KW:
+        if nt * c1 < 4 * w // 3:
+            continue
+        seqs = _seqs(rng) + [b"ACGTTGCA" * 40 + bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 6000)) + b"AC" * 900]
+        oh, op, orr = _oracle_stream(seqs, k, w)
+        for cpw in (0.0, 3.0, 8.0, 40.0, 1e9):
+            eh, ep, er, n_tiles, n_fb = emul.sparse(seqs, k, w, nt, c1, cpw)
+            assert len(eh) == len(oh), (cfg, k, w, cpw, len(eh), len(oh))
+            assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (cfg, k, w, cpw)
+            n_sparse_tiles += n_tiles - n_fb
+            n_fallback_tiles += n_fb
+    assert n_sparse_tiles > 0 and n_fallback_tiles > 0
+
+
+def test_sparse_tie_rule_on_repeats(emul):
+    """Equal hashes inside one window (tandem repeats longer than w): the rightmost minimum wins and
+    the left / right scans must treat ties asymmetrically."""
+    rng = np.random.default_rng(5)
+    unit = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 37))
+    seqs = [unit * 300, (unit + b"A") * 250, bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 500)) + unit * 200]
+    for k, w in ((11, 100), (21, 200), (15, 120)):
+        oh, op, orr = _oracle_stream(seqs, k, w)
+        for cpw in (0.0, 1e9):
+            for nt, c1 in ((8, 64), (128, 64)):
+                eh, ep, er, _, _ = emul.sparse(seqs, k, w, nt, c1, cpw)
+                assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (k, w, cpw, nt)
