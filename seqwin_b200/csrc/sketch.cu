@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
     const SparseSmem S = carve_sparse_smem(smem_raw, NT, CAP);
     const int tid = threadIdx.x;
     if (tid < 20) S.tab[tid] = P.table.e[tid];
-    constexpr uint32_t MC = NT * kSparsePerThread;
+    constexpr uint32_t MC = NT * kSparsePerThread, MA = NT * kSparseSmallPerThread;
+    static_assert(NT * CAP < 65536, "candidate counts are scanned as 16-bit halves");
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
@@ -186,24 +187,32 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
         bool ok = T.n_pieces == 1;
         if (ok) ok = sparseA_hash<NT, C1, CAP>(tid, P, T, S, &mask);
         bool hand_over = __syncthreads_or(!ok) != 0;
-        uint32_t m = 0, off = 0;
+        uint32_t m = 0, ma = 0, off = 0, aoff = 0;
         if (!hand_over) {
-            off = block_excl_scan<NT>(popcount64(mask), s_warp_sums, &m);
-            hand_over = m == 0 || m > MC;
+            // one scan for both arrays: all candidates in the low half, the small ones in the high half
+            const uint32_t cnt_all = popcount64(mask);
+            uint32_t tot;
+            const uint32_t ex = block_excl_scan<NT>(cnt_all | (sparse_count_small<NT>(tid, cnt_all, P, S) << 16),
+                                                    s_warp_sums, &tot);
+            m = tot & 0xFFFFu, ma = tot >> 16, off = ex & 0xFFFFu, aoff = ex >> 16;
+            hand_over = m == 0 || m > MC || ma > MA;
         }
-        uint32_t flags = 0, cnt = 0;
+        uint32_t flags = 0;
         const uint32_t per = (m + NT - 1) / NT;
         if (!hand_over) {
-            sparseC_compact<NT, C1>(tid, mask, off, m, S);
+            sparseC_compact<NT, C1>(tid, mask, off, aoff, m, ma, P, T, S);
             __syncthreads();
             bool bad;
-            cnt = sparseS_select<NT>(tid, m, per, P, T, S, &flags, &bad);
+            flags = sparseS_main<NT>(tid, m, per, P, T, S, &bad);
+            sparseS_small<NT>(tid, ma, P, T, S);
             hand_over = __syncthreads_or(bad) != 0;
         }
         if (hand_over) {   // uniform: a dense kernel recomputes the tile
             if (tid == 0) P.fallback_tiles[atomicAdd(P.fallback_count, 1u)] = tile_id;
             continue;
         }
+        flags = sparse_merge_flags(tid, m, per, flags, S);
+        const uint32_t cnt = (uint32_t)__popc(flags);
         uint32_t total;
         const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
         if (tid == 0) s_gbase = claim_slots(P, tile_id, total);
@@ -497,7 +506,8 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.tile_slot = tile_info.p + plan.n_tiles;
         P.table = make_roll_table(k);
         P.tetra = device_tetra_table(s);
-        P.cand_hi = sparse_cand_hi(w);
+        P.cand_hi = sparse_threshold(w, kSparseCandPerWindow);
+        P.cand_hi_a = sparse_threshold(w, kSparseSmallPerWindow);
         P.fallback_count = reinterpret_cast<unsigned int*>(counters.p + 2);
         P.fallback_tiles = fallback_tiles.p;
         P.tile_list = nullptr;

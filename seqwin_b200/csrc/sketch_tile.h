@@ -55,6 +55,7 @@ struct SketchParams {
     unsigned int* tile_counter;       // ticket dispenser
     // sparse path (below): candidate threshold and the list of tiles it hands to the dense kernels
     uint32_t cand_hi;                 // candidates are k-mers with (h0 >> 32) < cand_hi
+    uint32_t cand_hi_a;               // ... and the "small" ones those below cand_hi_a
     unsigned int* fallback_count;     // sparse kernel: number of tiles appended to fallback_tiles
     uint32_t* fallback_tiles;         // [n_tiles]
     const uint32_t* tile_list;        // dense kernels: if set, ticket i handles tile tile_list[i] ...
@@ -609,48 +610,63 @@ SW_HD void fastD_write(const SketchParams& P, const Tile& T, const TileSmem& S, 
 //
 // Only small hashes can be selected: if every window holds at least one CANDIDATE, a k-mer with
 // (h0 >> 32) < cand_hi, then every selection is a candidate and L / R need only be looked for among
-// candidates.  cand_hi keeps about 16 candidates per window, so each thread
+// candidates.  cand_hi keeps about kSparseCandPerWindow candidates per window, so each thread
 //   A  hashes C1 consecutive k-mers and appends the few candidates to a private list  (no h0 array)
-//   C  the lists are compacted into one position-ordered array per tile
-//   S  one thread per candidate scans its neighbours (at most those within w positions) for L and R
+//   C  the lists are compacted into one position-ordered array per tile, plus a second array with
+//      only the SMALL candidates ((h0 >> 32) < cand_hi_a, about kSparseSmallPerWindow per window)
+//   S  one thread per candidate walks outwards until it meets L and R (or has gone w positions).
+//      A small candidate can only be stopped by small ones, so it walks the short array; the others
+//      meet something smaller after a step or two.  The two kinds run in separate passes so that the
+//      lanes of a warp do similar amounts of work.
 //   D  selected candidates are written out
 // Tiles the argument does not cover -- a window without candidate (low-complexity sequence), a
-// private list that overflows, a tile that crosses a gap -- are appended to fallback_tiles and
-// recomputed by the dense kernels above.  Both paths are exact; the split only decides who does it.
+// list that overflows, a tile that crosses a gap -- are appended to fallback_tiles and recomputed
+// by the dense kernels above.  Both paths are exact; the split only decides who does the work.
 struct SparseSmem {
-    RollEntry* tab;   // [20]
-    uint64_t* list;   // [CAP][NT] slot-major private candidate lists (h0)
-    uint64_t* key;    // [MC + 2]  dense candidates: tile-local index << 32 | h0 >> 32; [0], [m + 1] sentinels
-    uint32_t* lo;     // [MC + 2]  low word of h0
+    RollEntry* tab;    // [20]
+    uint64_t* list;    // [CAP][NT] slot-major private candidate lists (h0)
+    uint64_t* key;     // [MC + 2]  all candidates: tile-local index << 32 | h0 >> 32; [0], [m + 1] sentinels
+    uint64_t* akey;    // [MA + 2]  small candidates, same encoding and sentinels
+    uint32_t* lo;      // [MC + 2]  low word of h0
+    uint32_t* alo;     // [MA + 2]
+    uint32_t* selbits; // [MC / 32 + 2] bit j: candidate j is selected (written by the small pass)
+    uint16_t* aj;      // [MA + 2]  index of the small candidate in key[]
 };
 
-constexpr uint32_t kSparsePerThread = 8;   // dense capacity MC = NT * kSparsePerThread
+constexpr uint32_t kSparsePerThread = 8;   // capacity of key[]:  MC = NT * 8
+constexpr uint32_t kSparseSmallPerThread = 4;   // capacity of akey[]: MA = NT * 4
 constexpr uint32_t kSparseCheck = 8;       // a private list is checked for room every 8 steps
 constexpr uint32_t kSparseMinW = 96;       // below this the dense kernels are used for every tile
-constexpr double kSparseCandPerWindow = 16.0;
+constexpr double kSparseCandPerWindow = 12.0;
+constexpr double kSparseSmallPerWindow = 4.0;
 
 SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
 {
-    const size_t mc = (size_t)nt * kSparsePerThread + 2;
-    return sizeof(RollEntry) * 20 + sizeof(uint64_t) * (size_t)cap * nt + sizeof(uint64_t) * mc +
-           ((sizeof(uint32_t) * mc + 15) & ~(size_t)15);
+    const size_t mc = (size_t)nt * kSparsePerThread + 2, ma = (size_t)nt * kSparseSmallPerThread + 2;
+    size_t b = sizeof(RollEntry) * 20 + sizeof(uint64_t) * ((size_t)cap * nt + mc + ma);
+    b += sizeof(uint32_t) * (mc + ma + mc / 32 + 2) + sizeof(uint16_t) * ma;
+    return (b + 15) & ~(size_t)15;
 }
 
 SW_HD SparseSmem carve_sparse_smem(unsigned char* base, uint32_t nt, uint32_t cap)
 {
-    const size_t mc = (size_t)nt * kSparsePerThread + 2;
+    const size_t mc = (size_t)nt * kSparsePerThread + 2, ma = (size_t)nt * kSparseSmallPerThread + 2;
     SparseSmem s;
     s.tab = reinterpret_cast<RollEntry*>(base);
     s.list = reinterpret_cast<uint64_t*>(base + sizeof(RollEntry) * 20);
     s.key = s.list + (size_t)cap * nt;
-    s.lo = reinterpret_cast<uint32_t*>(s.key + mc);
+    s.akey = s.key + mc;
+    s.lo = reinterpret_cast<uint32_t*>(s.akey + ma);
+    s.alo = s.lo + mc;
+    s.selbits = s.alo + ma;
+    s.aj = reinterpret_cast<uint16_t*>(s.selbits + mc / 32 + 2);
     return s;
 }
 
-// (h0 >> 32) threshold that leaves about kSparseCandPerWindow candidates in a window of w k-mers
-inline uint32_t sparse_cand_hi(uint32_t w)
+// (h0 >> 32) threshold that leaves about `per_window` candidates in a window of w k-mers
+inline uint32_t sparse_threshold(uint32_t w, double per_window)
 {
-    const double f = kSparseCandPerWindow / (double)w;
+    const double f = per_window / (double)w;
     return f >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(f * 4294967296.0);
 }
 
@@ -727,88 +743,152 @@ SW_HD uint32_t ctz64(uint64_t x)
 #endif
 }
 
-// C: copy the thread's candidates to dense slots [1 + off, ...); thread 0 writes the sentinels
-// (h0 word 0 stops every scan; they are recognised by their index).
+// how many of the thread's `cnt` listed candidates are small
+template <int NT>
+SW_HD uint32_t sparse_count_small(int tid, uint32_t cnt, const SketchParams& P, const SparseSmem& S)
+{
+    uint32_t c = 0;
+    for (uint32_t s = 0; s < cnt; ++s) c += (uint32_t)(S.list[(size_t)s * NT + tid] >> 32) < P.cand_hi_a ? 1u : 0u;
+    return c;
+}
+
+// C: copy the thread's candidates to key[1 + off ...] (and the small ones to akey[1 + aoff ...]);
+// the first threads write the sentinels (h0 word 0 stops every walk, position -1 / n_kmers is the
+// bound it then reports) and clear the selection bits.
 template <int NT, int C1>
-SW_HD void sparseC_compact(int tid, uint64_t mask, uint32_t off, uint32_t m, const SparseSmem& S)
+SW_HD void sparseC_compact(int tid, uint64_t mask, uint32_t off, uint32_t aoff, uint32_t m, uint32_t ma,
+                           const SketchParams& P, const Tile& T, const SparseSmem& S)
 {
     const uint32_t j0 = (uint32_t)tid * C1;
-    uint32_t s = 0;
+    uint32_t s = 0, sa = 0;
     while (mask) {
         const uint32_t b = ctz64(mask);
         mask &= mask - 1;
         const uint64_t h = S.list[(size_t)s * NT + tid];
-        S.key[1 + off + s] = ((uint64_t)(j0 + b) << 32) | (h >> 32);
-        S.lo[1 + off + s] = (uint32_t)h;
+        const uint64_t key = ((uint64_t)(j0 + b) << 32) | (h >> 32);
+        const uint32_t j = 1 + off + s;
+        S.key[j] = key;
+        S.lo[j] = (uint32_t)h;
+        if ((uint32_t)(h >> 32) < P.cand_hi_a) {
+            const uint32_t a = 1 + aoff + sa;
+            S.akey[a] = key;
+            S.alo[a] = (uint32_t)h;
+            S.aj[a] = (uint16_t)j;
+            ++sa;
+        }
         ++s;
     }
     if (tid == 0) {
-        S.key[0] = 0;
-        S.lo[0] = 0;
-        S.key[m + 1] = 0;
-        S.lo[m + 1] = 0;
+        const uint64_t left = 0xFFFFFFFFull << 32, right = (uint64_t)T.n_kmers << 32;
+        S.key[0] = left;
+        S.key[m + 1] = right;
+        S.akey[0] = left;
+        S.akey[ma + 1] = right;
+        S.lo[0] = S.lo[m + 1] = S.alo[0] = S.alo[ma + 1] = 0;
+    }
+    for (uint32_t i = (uint32_t)tid; i < (uint32_t)NT * kSparsePerThread / 32 + 2; i += NT) S.selbits[i] = 0;
+}
+
+// Walk left from entry j of a candidate array to the nearest strictly smaller h0, giving up once w
+// positions away; returns its position (-1 from the sentinel; anything <= p - w means "none in reach").
+SW_HD int32_t sparse_walk_left(const uint64_t* key, const uint32_t* lo, uint32_t j, int32_t p, uint32_t hh,
+                               uint32_t hl, int32_t w)
+{
+    const int32_t reach = p - w;
+    uint32_t q = j - 1;
+    for (;;) {
+        const uint64_t kq = key[q];
+        const int32_t pq = (int32_t)(kq >> 32);
+        if ((uint32_t)kq <= hh || pq <= reach) {
+            // equal high words are rare: only then the low words (and the sentinel's index) matter
+            if ((uint32_t)kq < hh || pq <= reach || q == 0 || lo[q] < hl) return pq;
+        }
+        --q;
     }
 }
 
-// S: thread owns dense candidates [1 + tid * per, 1 + (tid + 1) * per) of m.  Returns the number
-// selected (bit i of *flags: candidate 1 + tid * per + i); *bad is set if some window of the tile
-// holds no candidate.
+// Walk right to the nearest smaller-or-equal h0 (ties: the right-hand k-mer wins, minimizer.cpp:75).
+SW_HD int32_t sparse_walk_right(const uint64_t* key, const uint32_t* lo, uint32_t j, uint32_t last, int32_t p,
+                                uint32_t hh, uint32_t hl, int32_t w)
+{
+    const int32_t reach = p + w;
+    uint32_t q = j + 1;
+    for (;;) {
+        const uint64_t kq = key[q];
+        const int32_t pq = (int32_t)(kq >> 32);
+        if ((uint32_t)kq <= hh || pq >= reach) {
+            if ((uint32_t)kq < hh || pq >= reach || q == last || lo[q] <= hl) return pq;
+        }
+        ++q;
+    }
+}
+
+// is the k-mer at p, boxed in by L and R, the selection of a window this tile emits for?
+SW_HD bool sparse_selected(int32_t p, int32_t L, int32_t R, int32_t w, const Tile& T)
+{
+    const int32_t i_lo = L + 1 > p - w + 1 ? L + 1 : p - w + 1;
+    const int32_t i_hi = p < R - w ? p : R - w;
+    // window 0 of a tile that is not the record's first only provides the previous selection
+    return i_lo <= i_hi && (T.first != 0 || i_lo >= 1);
+}
+
+// S (small pass): thread handles small candidates 1 + tid, 1 + tid + NT, ... of ma, walking akey[].
 template <int NT>
-SW_HD uint32_t sparseS_select(int tid, uint32_t m, uint32_t per, const SketchParams& P, const Tile& T,
-                              const SparseSmem& S, uint32_t* flags, bool* bad)
+SW_HD void sparseS_small(int tid, uint32_t ma, const SketchParams& P, const Tile& T, const SparseSmem& S)
+{
+    const int32_t w = (int32_t)P.w;
+    for (uint32_t a = 1 + (uint32_t)tid; a <= ma; a += NT) {
+        const uint64_t ka = S.akey[a];
+        const int32_t p = (int32_t)(ka >> 32);
+        const uint32_t hh = (uint32_t)ka, hl = S.alo[a];
+        const int32_t L = sparse_walk_left(S.akey, S.alo, a, p, hh, hl, w);
+        const int32_t R = sparse_walk_right(S.akey, S.alo, a, ma + 1, p, hh, hl, w);
+        if (sparse_selected(p, L, R, w, T)) {
+            const uint32_t j = S.aj[a];
+#if defined(__CUDA_ARCH__)
+            atomicOr(&S.selbits[j >> 5], 1u << (j & 31));
+#else
+            S.selbits[j >> 5] |= 1u << (j & 31);
+#endif
+        }
+    }
+}
+
+// S (main pass): thread owns candidates [1 + tid * per, 1 + (tid + 1) * per) of m; the small ones
+// are skipped.  Returns the selection flags of its other candidates (bit i: candidate
+// 1 + tid * per + i); *bad is set if some window of the tile holds no candidate.
+template <int NT>
+SW_HD uint32_t sparseS_main(int tid, uint32_t m, uint32_t per, const SketchParams& P, const Tile& T,
+                            const SparseSmem& S, bool* bad)
 {
     const int32_t w = (int32_t)P.w, n = (int32_t)T.n_kmers;
-    uint32_t f = 0, cnt = 0;
+    uint32_t f = 0;
     *bad = false;
     for (uint32_t i = 0; i < per; ++i) {
         const uint32_t j = 1 + (uint32_t)tid * per + i;
         if (j > m) break;
         const uint64_t kj = S.key[j];
         const int32_t p = (int32_t)(kj >> 32);
-        const uint32_t hh = (uint32_t)kj, hl = S.lo[j];
+        const uint32_t hh = (uint32_t)kj;
         // coverage: no stretch of w k-mers without candidate before this one / after the last one
-        const int32_t prev = j == 1 ? -1 : (int32_t)(S.key[j - 1] >> 32);
+        const int32_t prev = (int32_t)(S.key[j - 1] >> 32);
         if (p - prev > w || (j == m && n - p > w)) *bad = true;
-        // nearest strictly smaller candidate on the left, looked for down to position p - w + 1
-        int32_t L;
-        {
-            const int32_t reach = p - w;   // a candidate at or before it cannot matter
-            uint32_t q = j - 1;
-            for (;;) {
-                const uint64_t kq = S.key[q];
-                const int32_t pq = (int32_t)(kq >> 32);
-                if ((uint32_t)kq <= hh || pq <= reach) {
-                    if (q == 0) { L = -1; break; }
-                    if (pq <= reach || (uint32_t)kq < hh || S.lo[q] < hl) { L = pq; break; }
-                }
-                --q;
-            }
-        }
-        // nearest smaller-or-equal candidate on the right, looked for up to position p + w - 1
-        int32_t R;
-        {
-            const int32_t reach = p + w;
-            uint32_t q = j + 1;
-            for (;;) {
-                const uint64_t kq = S.key[q];
-                const int32_t pq = (int32_t)(kq >> 32);
-                if ((uint32_t)kq <= hh || pq >= reach) {
-                    if (q == m + 1) { R = n; break; }
-                    if (pq >= reach || (uint32_t)kq < hh || S.lo[q] <= hl) { R = pq; break; }
-                }
-                ++q;
-            }
-        }
-        const int32_t i_lo = L + 1 > p - w + 1 ? L + 1 : p - w + 1;
-        const int32_t i_hi = p < R - w ? p : R - w;
-        // window 0 of a tile that is not the record's first only provides the previous selection
-        if (i_lo <= i_hi && (T.first != 0 || i_lo >= 1)) {
-            f |= 1u << i;
-            ++cnt;
-        }
+        if (hh < P.cand_hi_a) continue;
+        const uint32_t hl = S.lo[j];
+        const int32_t L = sparse_walk_left(S.key, S.lo, j, p, hh, hl, w);
+        const int32_t R = sparse_walk_right(S.key, S.lo, j, m + 1, p, hh, hl, w);
+        if (sparse_selected(p, L, R, w, T)) f |= 1u << i;
     }
-    *flags = f;
-    return cnt;
+    return f;
+}
+
+// after both passes: add the small candidates' selection bits to the thread's flags
+SW_HD uint32_t sparse_merge_flags(int tid, uint32_t m, uint32_t per, uint32_t flags, const SparseSmem& S)
+{
+    const uint32_t j0 = 1 + (uint32_t)tid * per;
+    if (j0 > m || per == 0) return flags;
+    const uint64_t two = (uint64_t)S.selbits[j0 >> 5] | ((uint64_t)S.selbits[(j0 >> 5) + 1] << 32);
+    return flags | ((uint32_t)(two >> (j0 & 31)) & ((1u << per) - 1u));
 }
 
 // D: write the thread's selected candidates to consecutive global slots.

@@ -154,9 +154,10 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
     *n_tiles_out = (uint32_t)plan.tiles.size();
     EmulOut o;
     SketchParams P = make_params(b, plan, k, w, FC1, o);
-    const double f = cand_per_window / (double)w;
-    P.cand_hi = cand_per_window <= 0 ? sparse_cand_hi(w) : (f >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(f * 4294967296.0));
-    constexpr uint32_t MC = NT * kSparsePerThread;
+    // cand_per_window <= 0: the library's thresholds; else that many candidates, a third of them small
+    P.cand_hi = sparse_threshold(w, cand_per_window <= 0 ? kSparseCandPerWindow : cand_per_window);
+    P.cand_hi_a = sparse_threshold(w, cand_per_window <= 0 ? kSparseSmallPerWindow : cand_per_window / 3.0);
+    constexpr uint32_t MC = NT * kSparsePerThread, MA = NT * kSparseSmallPerThread;
     std::vector<unsigned char> smem(sparse_smem_bytes(NT, CAP) + 64);
     SparseSmem S = carve_sparse_smem(smem.data(), NT, CAP);
     std::vector<uint32_t> fallback;
@@ -169,28 +170,39 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
         if (!hand_over)
             for (int tid = 0; tid < NT; ++tid)
                 if (!sparseA_hash<NT, C1, CAP>(tid, P, T, S, &mask[tid])) hand_over = true;
-        std::vector<uint32_t> off(NT, 0), flags(NT, 0), cnt(NT, 0), excl(NT, 0);
-        uint32_t m = 0;
+        std::vector<uint32_t> off(NT, 0), aoff(NT, 0), flags(NT, 0), excl(NT, 0);
+        uint32_t m = 0, ma = 0;
         if (!hand_over) {
-            for (int tid = 0; tid < NT; ++tid) { off[tid] = m; m += (uint32_t)__builtin_popcountll(mask[tid]); }
-            hand_over = m == 0 || m > MC;
+            for (int tid = 0; tid < NT; ++tid) {
+                const uint32_t c = (uint32_t)__builtin_popcountll(mask[tid]);
+                off[tid] = m;
+                aoff[tid] = ma;
+                m += c;
+                ma += sparse_count_small<NT>(tid, c, P, S);
+            }
+            hand_over = m == 0 || m > MC || ma > MA;
         }
         const uint32_t per = (m + NT - 1) / NT;
         if (!hand_over) {
-            for (int tid = 0; tid < NT; ++tid) sparseC_compact<NT, C1>(tid, mask[tid], off[tid], m, S);
+            for (int tid = 0; tid < NT; ++tid) sparseC_compact<NT, C1>(tid, mask[tid], off[tid], aoff[tid], m, ma, P, T, S);
             for (int tid = 0; tid < NT; ++tid) {
                 bool bad;
-                cnt[tid] = sparseS_select<NT>(tid, m, per, P, T, S, &flags[tid], &bad);
+                flags[tid] = sparseS_main<NT>(tid, m, per, P, T, S, &bad);
+                sparseS_small<NT>(tid, ma, P, T, S);
                 if (bad) hand_over = true;
             }
         }
         if (hand_over) { fallback.push_back(t); continue; }
         uint32_t total = 0;
-        for (int tid = 0; tid < NT; ++tid) { excl[tid] = total; total += cnt[tid]; }
+        for (int tid = 0; tid < NT; ++tid) {
+            flags[tid] = sparse_merge_flags(tid, m, per, flags[tid], S);
+            excl[tid] = total;
+            total += (uint32_t)__builtin_popcount(flags[tid]);
+        }
         o.tile_count[t] = total;
         o.tile_slot[t] = o.cursor;
         for (int tid = 0; tid < NT; ++tid)
-            if (cnt[tid]) sparseD_write<NT>(tid, per, flags[tid], o.cursor + excl[tid], P, T, S);
+            if (flags[tid]) sparseD_write<NT>(tid, per, flags[tid], o.cursor + excl[tid], P, T, S);
         o.cursor += total;
     }
     *n_fallback_out = (uint32_t)fallback.size();
