@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
     const SparseSmem S = carve_sparse_smem(smem_raw, NT, CAP);
     const int tid = threadIdx.x;
     if (tid < 20) S.tab[tid] = P.table.e[tid];
-    constexpr uint32_t MC = NT * kSparsePerThread, MA = NT * kSparseSmallPerThread;
+    constexpr uint32_t MC = sparse_mc(NT), MA = sparse_ma(NT);
     static_assert(NT * CAP < 65536, "candidate counts are scanned as 16-bit halves");
 
     for (;;) {
@@ -284,8 +284,8 @@ const KernelConfig kConfigs[] = {
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 constexpr int kLargeWindowConfig = 3;
 constexpr int kSparseDenseConfig = 8;
-// the sparse kernel: 128 threads x 64 k-mers, 24 private candidate slots per thread
-constexpr int kSparseNT = 128, kSparseC1 = 64, kSparseCap = 24;
+// the sparse kernel: 128 threads x 64 k-mers, 20 private candidate slots per thread
+constexpr int kSparseNT = 128, kSparseC1 = 64, kSparseCap = 20;
 constexpr uint32_t kSparseTK = kSparseNT * kSparseC1;
 
 }  // namespace
@@ -506,8 +506,12 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.tile_slot = tile_info.p + plan.n_tiles;
         P.table = make_roll_table(k);
         P.tetra = device_tetra_table(s);
-        P.cand_hi = sparse_threshold(w, kSparseCandPerWindow);
-        P.cand_hi_a = sparse_threshold(w, kSparseSmallPerWindow);
+        {   // SEQWIN_SPARSE_CPW / SEQWIN_SPARSE_SMALL: tuning overrides (any value gives the same output)
+            const char* e1 = getenv("SEQWIN_SPARSE_CPW");
+            const char* e2 = getenv("SEQWIN_SPARSE_SMALL");
+            P.cand_hi = sparse_threshold(w, e1 ? atof(e1) : kSparseCandPerWindow);
+            P.cand_hi_a = sparse_threshold(w, e2 ? atof(e2) : kSparseSmallPerWindow);
+        }
         P.fallback_count = reinterpret_cast<unsigned int*>(counters.p + 2);
         P.fallback_tiles = fallback_tiles.p;
         P.tile_list = nullptr;

@@ -633,16 +633,18 @@ struct SparseSmem {
     uint16_t* aj;      // [MA + 2]  index of the small candidate in key[]
 };
 
-constexpr uint32_t kSparsePerThread = 8;   // capacity of key[]:  MC = NT * 8
-constexpr uint32_t kSparseSmallPerThread = 4;   // capacity of akey[]: MA = NT * 4
+// capacities of key[] / akey[] for NT threads: the means are 64 * NT * 11 / w and 64 * NT * 4 / w
+// (3.5 and 1.3 per thread at w = 200, falling with w); shared memory per CTA decides the occupancy
+SW_HD constexpr uint32_t sparse_mc(uint32_t nt) { return nt * 5; }
+SW_HD constexpr uint32_t sparse_ma(uint32_t nt) { return nt * 7 / 4; }
 constexpr uint32_t kSparseCheck = 8;       // a private list is checked for room every 8 steps
 constexpr uint32_t kSparseMinW = 96;       // below this the dense kernels are used for every tile
-constexpr double kSparseCandPerWindow = 12.0;
+constexpr double kSparseCandPerWindow = 11.0;
 constexpr double kSparseSmallPerWindow = 4.0;
 
 SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
 {
-    const size_t mc = (size_t)nt * kSparsePerThread + 2, ma = (size_t)nt * kSparseSmallPerThread + 2;
+    const size_t mc = (size_t)sparse_mc(nt) + 2, ma = (size_t)sparse_ma(nt) + 2;
     size_t b = sizeof(RollEntry) * 20 + sizeof(uint64_t) * ((size_t)cap * nt + mc + ma);
     b += sizeof(uint32_t) * (mc + ma + mc / 32 + 2) + sizeof(uint16_t) * ma;
     return (b + 15) & ~(size_t)15;
@@ -650,7 +652,7 @@ SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
 
 SW_HD SparseSmem carve_sparse_smem(unsigned char* base, uint32_t nt, uint32_t cap)
 {
-    const size_t mc = (size_t)nt * kSparsePerThread + 2, ma = (size_t)nt * kSparseSmallPerThread + 2;
+    const size_t mc = (size_t)sparse_mc(nt) + 2, ma = (size_t)sparse_ma(nt) + 2;
     SparseSmem s;
     s.tab = reinterpret_cast<RollEntry*>(base);
     s.list = reinterpret_cast<uint64_t*>(base + sizeof(RollEntry) * 20);
@@ -685,14 +687,23 @@ SW_HD bool sparseA_hash(int tid, const SketchParams& P, const Tile& T, const Spa
     const uint64_t p0 = (uint64_t)pc.pos + ((uint64_t)T.e0 + j0 - pc.kidx);
     uint64_t fwd, rev;
     seed_kmer(W, p0, P.k, S.tab, P.tetra, &fwd, &rev);
+    // private list cursor: a 32-bit shared-memory address on the device (one predicated add per
+    // candidate instead of 64-bit pointer arithmetic), a plain pointer in the host emulator
+#if defined(__CUDA_ARCH__)
+    uint32_t slot = (uint32_t)__cvta_generic_to_shared(S.list + tid);
+    const uint32_t slot_limit = slot + (uint32_t)((CAP - (int)kSparseCheck) * NT * sizeof(uint64_t));
+#define SW_LIST_PUSH(h) do { asm volatile("st.shared.u64 [%0], %1;" :: "r"(slot), "l"(h) : "memory"); slot += NT * 8; } while (0)
+#else
     uint64_t* slot = S.list + tid;
     uint64_t* const slot_limit = slot + (size_t)(CAP - (int)kSparseCheck) * NT;   // room for one more interval
+#define SW_LIST_PUSH(h) do { *slot = (h); slot += NT; } while (0)
+#endif
     uint32_t thr = P.cand_hi;
     uint32_t m_lo = 0, m_hi = 0;
     bool ok = true;
     {
         const uint64_t h = fwd + rev;
-        if ((uint32_t)(h >> 32) < thr) { *slot = h; slot += NT; m_lo |= 1u; }
+        if ((uint32_t)(h >> 32) < thr) { SW_LIST_PUSH(h); m_lo |= 1u; }
     }
 #pragma unroll
     for (int b = 0; b < (C1 - 1 + 15) / 16; ++b) {
@@ -711,13 +722,13 @@ SW_HD bool sparseA_hash(int tid, const SketchParams& P, const Tile& T, const Spa
                 roll_step(fwd, rev, S.tab[idx]);
                 const uint64_t h = fwd + rev;
                 if ((uint32_t)(h >> 32) < thr) {
-                    *slot = h;
-                    slot += NT;
+                    SW_LIST_PUSH(h);
                     if (n < 32) m_lo |= 1u << (n & 31); else m_hi |= 1u << (n & 31);
                 }
             }
         }
     }
+#undef SW_LIST_PUSH
     uint64_t mask = ((uint64_t)m_hi << 32) | m_lo;
     const uint32_t lim = T.n_kmers - j0;   // k-mers of this chunk that exist
     if (lim < (uint32_t)C1) mask &= (1ULL << lim) - 1;
@@ -786,7 +797,7 @@ SW_HD void sparseC_compact(int tid, uint64_t mask, uint32_t off, uint32_t aoff, 
         S.akey[ma + 1] = right;
         S.lo[0] = S.lo[m + 1] = S.alo[0] = S.alo[ma + 1] = 0;
     }
-    for (uint32_t i = (uint32_t)tid; i < (uint32_t)NT * kSparsePerThread / 32 + 2; i += NT) S.selbits[i] = 0;
+    for (uint32_t i = (uint32_t)tid; i < sparse_mc(NT) / 32 + 2; i += NT) S.selbits[i] = 0;
 }
 
 // Walk left from entry j of a candidate array to the nearest strictly smaller h0, giving up once w

@@ -157,7 +157,7 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
     // cand_per_window <= 0: the library's thresholds; else that many candidates, a third of them small
     P.cand_hi = sparse_threshold(w, cand_per_window <= 0 ? kSparseCandPerWindow : cand_per_window);
     P.cand_hi_a = sparse_threshold(w, cand_per_window <= 0 ? kSparseSmallPerWindow : cand_per_window / 3.0);
-    constexpr uint32_t MC = NT * kSparsePerThread, MA = NT * kSparseSmallPerThread;
+    constexpr uint32_t MC = sparse_mc(NT), MA = sparse_ma(NT);
     std::vector<unsigned char> smem(sparse_smem_bytes(NT, CAP) + 64);
     SparseSmem S = carve_sparse_smem(smem.data(), NT, CAP);
     std::vector<uint32_t> fallback;
@@ -256,7 +256,7 @@ long emul_sketch_sparse(const uint8_t* const* seqs, const uint32_t* lens, size_t
         sw_batch* b = sw::batch_from_memory(seqs, lens, asm_of.data(), nullptr, n_records, 1, 1);
         std::vector<uint64_t> keys, vals;
         if (nt == 128 && c1 == 64)
-            sw::emulate_sparse<128, 64, 24, 256, 33>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
+            sw::emulate_sparse<128, 64, 20, 256, 33>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
         else if (nt == 8 && c1 == 64)
             sw::emulate_sparse<8, 64, 24, 16, 33>(*b, k, w, cand_per_window, keys, vals, n_tiles_out, n_fallback_out);
         else if (nt == 16 && c1 == 32)
