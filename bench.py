@@ -316,16 +316,19 @@ def main():
     int_alg = 45.0 * n_bases_local + 12.0 * s0.get("n_kmers_local", M)
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture, scaled by the
     # algorithmic bytes when the workload differs from the captured one
-    traffic = None
+    traffic, kernel_name, alu_pct = None, "sketch_sparse_kernel<128,64,20>", 73
     tp = ROOT / "profiles" / "r1_sketch_traffic.json"
     if tp.exists():
         tj = json.loads(tp.read_text())
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * sketch_bytes / tj["algorithmic_bytes"]
-    roofline = {"bound": "hbm", "kernel": "sketch_fast_kernel<128,33>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+        kernel_name, alu_pct = tj.get("kernel", kernel_name), tj.get("alu_pipe_pct", alu_pct)
+    if k != K_DEFAULT or w != W_DEFAULT or os.environ.get("SEQWIN_SKETCH_DENSE"):
+        kernel_name = "sketch kernel selected for this (k, w)"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sketch_bytes, "kernel_ms": sketch_ms,
-                "note": "the sketch kernel is bound by the INT32 ALU pipe, not HBM (SURVEY 8d; ncu: ALU pipe 66 % busy, "
-                        "DRAM 1.4 %): see int_roofline and path",
+                "note": f"the sketch kernel is bound by the INT32 ALU pipe, not HBM (SURVEY 8d; ncu: ALU pipe {alu_pct:g} % busy, "
+                        "DRAM < 3 %): see int_roofline and path",
                 "int_roofline": {"achieved_Tops": int_alg / (sketch_ms * 1e-3) / 1e12, "peak_Tops": int_peak / 1e12,
                                  "frac": int_alg / (sketch_ms * 1e-3) / int_peak,
                                  "model": "I_alg = 45*N + 12*M lane-ops; peak = 148 SM x 128 lanes x sm clock under load"},

@@ -615,9 +615,10 @@ SW_HD void fastD_write(const SketchParams& P, const Tile& T, const TileSmem& S, 
 //   C  the lists are compacted into one position-ordered array per tile, plus a second array with
 //      only the SMALL candidates ((h0 >> 32) < cand_hi_a, about kSparseSmallPerWindow per window)
 //   S  one thread per candidate walks outwards until it meets L and R (or has gone w positions).
-//      A small candidate can only be stopped by small ones, so it walks the short array; the others
-//      meet something smaller after a step or two.  The two kinds run in separate passes so that the
-//      lanes of a warp do similar amounts of work.
+//      A small candidate can only be stopped by small ones, so it walks the short array.  Any other
+//      candidate first looks at the small ones next to it: they are all smaller, so unless w k-mers
+//      fit between them it is done without walking.  The two kinds run in separate passes so that
+//      the lanes of a warp do similar amounts of work.
 //   D  selected candidates are written out
 // Tiles the argument does not cover -- a window without candidate (low-complexity sequence), a
 // list that overflows, a tile that crosses a gap -- are appended to fallback_tiles and recomputed
@@ -628,9 +629,9 @@ struct SparseSmem {
     uint64_t* key;     // [MC + 2]  all candidates: tile-local index << 32 | h0 >> 32; [0], [m + 1] sentinels
     uint64_t* akey;    // [MA + 2]  small candidates, same encoding and sentinels
     uint32_t* lo;      // [MC + 2]  low word of h0
-    uint32_t* alo;     // [MA + 2]
     uint32_t* selbits; // [MC / 32 + 2] bit j: candidate j is selected (written by the small pass)
     uint16_t* aj;      // [MA + 2]  index of the small candidate in key[]
+    uint16_t* na;      // [MC + 2]  number of small candidates among key[1 .. j]
 };
 
 // capacities of key[] / akey[] for NT threads: the means are 64 * NT * 11 / w and 64 * NT * 4 / w
@@ -646,7 +647,7 @@ SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
 {
     const size_t mc = (size_t)sparse_mc(nt) + 2, ma = (size_t)sparse_ma(nt) + 2;
     size_t b = sizeof(RollEntry) * 20 + sizeof(uint64_t) * ((size_t)cap * nt + mc + ma);
-    b += sizeof(uint32_t) * (mc + ma + mc / 32 + 2) + sizeof(uint16_t) * ma;
+    b += sizeof(uint32_t) * (mc + mc / 32 + 2) + sizeof(uint16_t) * (ma + mc);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -659,9 +660,9 @@ SW_HD SparseSmem carve_sparse_smem(unsigned char* base, uint32_t nt, uint32_t ca
     s.key = s.list + (size_t)cap * nt;
     s.akey = s.key + mc;
     s.lo = reinterpret_cast<uint32_t*>(s.akey + ma);
-    s.alo = s.lo + mc;
-    s.selbits = s.alo + ma;
+    s.selbits = s.lo + mc;
     s.aj = reinterpret_cast<uint16_t*>(s.selbits + mc / 32 + 2);
+    s.na = s.aj + ma;
     return s;
 }
 
@@ -783,10 +784,10 @@ SW_HD void sparseC_compact(int tid, uint64_t mask, uint32_t off, uint32_t aoff, 
         if ((uint32_t)(h >> 32) < P.cand_hi_a) {
             const uint32_t a = 1 + aoff + sa;
             S.akey[a] = key;
-            S.alo[a] = (uint32_t)h;
             S.aj[a] = (uint16_t)j;
             ++sa;
         }
+        S.na[j] = (uint16_t)(aoff + sa);
         ++s;
     }
     if (tid == 0) {
@@ -795,16 +796,20 @@ SW_HD void sparseC_compact(int tid, uint64_t mask, uint32_t off, uint32_t aoff, 
         S.key[m + 1] = right;
         S.akey[0] = left;
         S.akey[ma + 1] = right;
-        S.lo[0] = S.lo[m + 1] = S.alo[0] = S.alo[ma + 1] = 0;
+        S.lo[0] = S.lo[m + 1] = 0;
+        S.aj[0] = 0;
+        S.aj[ma + 1] = (uint16_t)(m + 1);
     }
     for (uint32_t i = (uint32_t)tid; i < sparse_mc(NT) / 32 + 2; i += NT) S.selbits[i] = 0;
 }
 
 // Walk left from entry j of a candidate array to the nearest strictly smaller h0, giving up once w
 // positions away; returns its position (-1 from the sentinel; anything <= p - w means "none in reach").
-SW_HD int32_t sparse_walk_left(const uint64_t* key, const uint32_t* lo, uint32_t j, int32_t p, uint32_t hh,
-                               uint32_t hl, int32_t w)
+// SMALL: the array is akey[], whose low words are found through aj[].
+template <bool SMALL>
+SW_HD int32_t sparse_walk_left(const SparseSmem& S, uint32_t j, int32_t p, uint32_t hh, uint32_t hl, int32_t w)
 {
+    const uint64_t* key = SMALL ? S.akey : S.key;
     const int32_t reach = p - w;
     uint32_t q = j - 1;
     for (;;) {
@@ -812,23 +817,25 @@ SW_HD int32_t sparse_walk_left(const uint64_t* key, const uint32_t* lo, uint32_t
         const int32_t pq = (int32_t)(kq >> 32);
         if ((uint32_t)kq <= hh || pq <= reach) {
             // equal high words are rare: only then the low words (and the sentinel's index) matter
-            if ((uint32_t)kq < hh || pq <= reach || q == 0 || lo[q] < hl) return pq;
+            if ((uint32_t)kq < hh || pq <= reach || q == 0 || S.lo[SMALL ? S.aj[q] : q] < hl) return pq;
         }
         --q;
     }
 }
 
 // Walk right to the nearest smaller-or-equal h0 (ties: the right-hand k-mer wins, minimizer.cpp:75).
-SW_HD int32_t sparse_walk_right(const uint64_t* key, const uint32_t* lo, uint32_t j, uint32_t last, int32_t p,
-                                uint32_t hh, uint32_t hl, int32_t w)
+template <bool SMALL>
+SW_HD int32_t sparse_walk_right(const SparseSmem& S, uint32_t j, uint32_t last, int32_t p, uint32_t hh, uint32_t hl,
+                                int32_t w)
 {
+    const uint64_t* key = SMALL ? S.akey : S.key;
     const int32_t reach = p + w;
     uint32_t q = j + 1;
     for (;;) {
         const uint64_t kq = key[q];
         const int32_t pq = (int32_t)(kq >> 32);
         if ((uint32_t)kq <= hh || pq >= reach) {
-            if ((uint32_t)kq < hh || pq >= reach || q == last || lo[q] <= hl) return pq;
+            if ((uint32_t)kq < hh || pq >= reach || q == last || S.lo[SMALL ? S.aj[q] : q] <= hl) return pq;
         }
         ++q;
     }
@@ -851,11 +858,11 @@ SW_HD void sparseS_small(int tid, uint32_t ma, const SketchParams& P, const Tile
     for (uint32_t a = 1 + (uint32_t)tid; a <= ma; a += NT) {
         const uint64_t ka = S.akey[a];
         const int32_t p = (int32_t)(ka >> 32);
-        const uint32_t hh = (uint32_t)ka, hl = S.alo[a];
-        const int32_t L = sparse_walk_left(S.akey, S.alo, a, p, hh, hl, w);
-        const int32_t R = sparse_walk_right(S.akey, S.alo, a, ma + 1, p, hh, hl, w);
+        const uint32_t j = S.aj[a];
+        const uint32_t hh = (uint32_t)ka, hl = S.lo[j];
+        const int32_t L = sparse_walk_left<true>(S, a, p, hh, hl, w);
+        const int32_t R = sparse_walk_right<true>(S, a, ma + 1, p, hh, hl, w);
         if (sparse_selected(p, L, R, w, T)) {
-            const uint32_t j = S.aj[a];
 #if defined(__CUDA_ARCH__)
             atomicOr(&S.selbits[j >> 5], 1u << (j & 31));
 #else
@@ -885,9 +892,13 @@ SW_HD uint32_t sparseS_main(int tid, uint32_t m, uint32_t per, const SketchParam
         const int32_t prev = (int32_t)(S.key[j - 1] >> 32);
         if (p - prev > w || (j == m && n - p > w)) *bad = true;
         if (hh < P.cand_hi_a) continue;
+        // every small candidate is smaller: unless w k-mers fit between the nearest ones on either
+        // side (about one window in fifty has no small candidate), this one is never selected
+        const uint32_t a = S.na[j];
+        if ((int32_t)(S.akey[a + 1] >> 32) - (int32_t)(S.akey[a] >> 32) - 1 < w) continue;
         const uint32_t hl = S.lo[j];
-        const int32_t L = sparse_walk_left(S.key, S.lo, j, p, hh, hl, w);
-        const int32_t R = sparse_walk_right(S.key, S.lo, j, m + 1, p, hh, hl, w);
+        const int32_t L = sparse_walk_left<false>(S, j, p, hh, hl, w);
+        const int32_t R = sparse_walk_right<false>(S, j, m + 1, p, hh, hl, w);
         if (sparse_selected(p, L, R, w, T)) f |= 1u << i;
     }
     return f;
