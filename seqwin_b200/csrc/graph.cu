@@ -155,13 +155,14 @@ __global__ void __launch_bounds__(kNT) node_write_kernel(
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
-        key[r] = j < n ? ks[j] : 0;
-        src[r] = j < n ? idx[j] : 0;
+        key[r] = j < n ? __ldcs(ks + j) : 0;
+        src[r] = j < n ? __ldcs(idx + j) : 0;
     }
+    // everything but rank_of_stream is touched once: streaming hints keep the scattered array in L2
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
-        val[r] = j < n ? stream_vals[src[r]] : 0;
+        val[r] = j < n ? __ldcs(stream_vals + src[r]) : 0;
         flag[r] = j < n && (j == 0 || key[r] != ks[j - 1]);
     }
     block_ranks(flag, rank, s_cnt);
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kNT) node_write_kernel(
         if (j < n) {
             // node rank of element j = (#run starts up to and including j) - 1
             const unsigned long long nr = off + rank[r] + (flag[r] ? 1u : 0u) - 1u;
-            kmers[j] = sw_kmer{(uint32_t)val[r], (uint32_t)(val[r] >> 32)};
+            __stcs(reinterpret_cast<unsigned long long*>(kmers + j), (unsigned long long)val[r]);
             rank_of_stream[src[r]] = (uint32_t)nr;
             if (flag[r]) {
                 sw_node* nd = nodes + nr;

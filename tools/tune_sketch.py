@@ -50,10 +50,11 @@ def main():
             g, t = C.c_void_p(), _lib.StageTimes()
             _lib.check(L.sw_dev_build(dev, a.k, a.w, C.byref(g), C.byref(t)))
             L.sw_graph_free(g)
-            rows.append((t.sketch_kernel_ms, t.total_ms, t.n_kmers))
+            rows.append((t.sketch_kernel_ms, t.total_ms, t.n_kmers, t.sort_nodes_ms, t.nodes_ms, t.edges_ms))
         rows = rows[1:]
-        print(f"{s or '(default)':50s} sketch_kernel {np.mean([r[0] for r in rows]):7.3f} ms  total {np.mean([r[1] for r in rows]):7.3f} ms"
-              f"  minimizers {rows[0][2]}", flush=True)
+        m = [float(np.mean([r[i] for r in rows])) for i in range(6)]
+        print(f"{s or '(default)':50s} sketch_kernel {m[0]:7.3f} ms  total {m[1]:7.3f} ms  sort_nodes {m[3]:6.3f}  nodes {m[4]:6.3f}"
+              f"  edges {m[5]:6.3f}  minimizers {rows[0][2]}", flush=True)
 
 
 if __name__ == "__main__":
