@@ -506,11 +506,11 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     g->ids = b.ids;
 
     constexpr int kMaxChunks = 8;
-    cudaEvent_t ev[kMaxChunks + 8];
+    cudaEvent_t ev[kMaxChunks + 9];
     for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDefault);
     cudaEvent_t& e_begin = ev[kMaxChunks], &e_alloc = ev[kMaxChunks + 1], &e_h2d0 = ev[kMaxChunks + 2],
                  &e_h2d1 = ev[kMaxChunks + 3], &e_nodes = ev[kMaxChunks + 4], &e_d2h0 = ev[kMaxChunks + 5],
-                 &e_d2h1 = ev[kMaxChunks + 6], &e_end = ev[kMaxChunks + 7];
+                 &e_d2h1 = ev[kMaxChunks + 6], &e_end = ev[kMaxChunks + 7], &e_kmers = ev[kMaxChunks + 8];
     struct EvGuard {
         cudaEvent_t* e; size_t n;
         ~EvGuard() { for (size_t i = 0; i < n; ++i) cudaEventDestroy(e[i]); }
@@ -561,22 +561,32 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     bool d2h_started = false;
     float penalty_ms = 0;
     const std::function<void()> after_nodes = [&] {
-        // scoring (get_penalty) runs on the device-resident kmers + nodes before they are exported
-        if (is_targets) penalty_ms = penalty_on_device(g->dev, b.record_offsets, is_targets, n_assemblies, s);
+        if (to_host) {
+            // the k-mer array is final: its copy starts now and runs under the scoring kernel
+            g->n_kmers = g->dev.n_kmers;
+            g->n_nodes = g->dev.n_nodes;
+            g->h_kmers = host_pool_get(g->n_kmers * sizeof(sw_kmer));
+            g->h_nodes = host_pool_get(g->n_nodes * sizeof(sw_node));
+            cudaEventRecord(e_kmers, s);
+            SW_CUDA(cudaStreamWaitEvent(cs, e_kmers, 0));
+            cudaEventRecord(e_d2h0, cs);
+            if (g->n_kmers)
+                SW_CUDA(cudaMemcpyAsync(g->h_kmers.p, g->dev.kmers.p, g->n_kmers * sizeof(sw_kmer), cudaMemcpyDeviceToHost, cs));
+            d2h_started = true;
+        }
+        // scoring (get_penalty) fills n_tar / n_neg / penalty of the device-resident nodes before they are exported
+        try {
+            if (is_targets) penalty_ms = penalty_on_device(g->dev, b.record_offsets, is_targets, n_assemblies, s);
+        } catch (...) {
+            cudaStreamSynchronize(cs);   // the k-mer copy must not outlive the buffers the unwinding frees
+            throw;
+        }
         fire_nodes_ready(g.get());
         if (!to_host) return;
-        g->n_kmers = g->dev.n_kmers;
-        g->n_nodes = g->dev.n_nodes;
-        g->h_kmers = host_pool_get(g->n_kmers * sizeof(sw_kmer));
-        g->h_nodes = host_pool_get(g->n_nodes * sizeof(sw_node));
         cudaEventRecord(e_nodes, s);
         SW_CUDA(cudaStreamWaitEvent(cs, e_nodes, 0));
-        cudaEventRecord(e_d2h0, cs);
-        if (g->n_kmers)
-            SW_CUDA(cudaMemcpyAsync(g->h_kmers.p, g->dev.kmers.p, g->n_kmers * sizeof(sw_kmer), cudaMemcpyDeviceToHost, cs));
         if (g->n_nodes)
             SW_CUDA(cudaMemcpyAsync(g->h_nodes.p, g->dev.nodes.p, g->n_nodes * sizeof(sw_node), cudaMemcpyDeviceToHost, cs));
-        d2h_started = true;
     };
     GraphTimes gt;
     build_graph(st, d->rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes);
