@@ -128,7 +128,8 @@ struct SortPairs {
     DevBuf<uint32_t> vals, vals_alt;
     uint64_t n = 0;
 };
-uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s);  // returns #launches
+// stable LSD sort of sp on key bits [begin_bit, end_bit) (begin_bit a multiple of 8); returns #launches
+uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s, int begin_bit = 0);
 
 // ---- graph stage ------------------------------------------------------------------------------
 struct DevGraph {

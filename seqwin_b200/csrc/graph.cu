@@ -188,6 +188,100 @@ __global__ void __launch_bounds__(kNT) node_write_kernel(
     }
 }
 
+// ---- node sort on the high word of h1 + tie fix-up ----------------------------------------------
+// h1 is a 64-bit mix, so sorting on its high 32 bits (4 radix passes instead of 8) already separates
+// almost every pair of nodes: with U_n distinct hashes about U_n^2 / 2^33 pairs share a high word.
+// Those few groups are found and stably re-sorted on the full key afterwards, which makes the result
+// identical to the 64-bit sort.
+
+constexpr uint32_t kTieListCap = 1u << 20;   // boundaries recorded; more -> the caller sorts all 64 bits
+constexpr uint32_t kTieMaxGroup = 1u << 14;  // largest group re-sorted in place (rank counting, O(G^2 / 32))
+
+// j with equal high words but different keys at j-1, j
+__global__ void __launch_bounds__(256) tie_detect_kernel(const uint64_t* __restrict__ ks, uint64_t n, int shift,
+                                                         uint32_t* __restrict__ list, unsigned int* counters)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; j < n; j += stride) {
+        const uint64_t a = ks[j - 1], b = ks[j];
+        if ((a >> shift) == (b >> shift) && a != b) {
+            const unsigned int c = atomicAdd(counters, 1u);
+            if (c < kTieListCap) list[c] = (uint32_t)j;
+        }
+    }
+}
+
+// One warp per recorded boundary: find the group of equal high words around it.  Only the leftmost
+// boundary of a group keeps it (groups[e] = [g0, g1), else an empty range).  A separate launch does
+// the re-sorting, so no warp ever looks at a group while another one rewrites it.
+__global__ void __launch_bounds__(256) tie_group_kernel(const uint64_t* __restrict__ ks, uint64_t n, int shift,
+                                                        const uint32_t* __restrict__ list, uint2* __restrict__ groups,
+                                                        unsigned int* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_list = min(counters[0], kTieListCap);
+    for (uint32_t e = warp; e < n_list; e += n_warps) {
+        const long long j = list[e];
+        const uint64_t hi = ks[j] >> shift, ref = ks[j - 1];
+        long long g0 = j;
+        bool earlier = false;   // another boundary lies to the left: that one owns the group
+        for (;;) {
+            const long long q = g0 - 1 - lane;
+            const uint64_t kq = q >= 0 ? ks[q] : 0;
+            const bool in = q >= 0 && (kq >> shift) == hi;
+            const unsigned out_mask = __ballot_sync(0xffffffffu, !in);
+            const unsigned below = out_mask ? ((1u << (__ffs(out_mask) - 1)) - 1u) : 0xffffffffu;  // lanes still in the group
+            if (__ballot_sync(0xffffffffu, in && kq != ref) & below) earlier = true;
+            if (out_mask) { g0 -= __ffs(out_mask) - 1; break; }
+            g0 -= 32;
+        }
+        long long g1 = j;
+        if (!earlier) {
+            for (;;) {
+                const long long q = g1 + lane;
+                const bool in = q < (long long)n && (ks[q] >> shift) == hi;
+                const unsigned out_mask = __ballot_sync(0xffffffffu, !in);
+                if (out_mask) { g1 += __ffs(out_mask) - 1; break; }
+                g1 += 32;
+            }
+            if (g1 - g0 > (long long)kTieMaxGroup) {
+                if (lane == 0) counters[1] = 1u;
+                earlier = true;
+            }
+        }
+        if (lane == 0) groups[e] = earlier ? make_uint2(0u, 0u) : make_uint2((uint32_t)g0, (uint32_t)g1);
+    }
+}
+
+// One warp per group: stable re-sort by (key, original order) through the scratch arrays.
+__global__ void __launch_bounds__(256) tie_sort_kernel(uint64_t* ks, uint32_t* vs, uint64_t* ks_tmp, uint32_t* vs_tmp,
+                                                       const uint2* __restrict__ groups, const unsigned int* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_list = min(counters[0], kTieListCap);
+    for (uint32_t e = warp; e < n_list; e += n_warps) {
+        const uint32_t g0 = groups[e].x, g1 = groups[e].y;
+        for (uint32_t i = g0 + lane; i < g1; i += 32) {
+            const uint64_t ki = ks[i];
+            uint32_t r = 0;
+            for (uint32_t t = g0; t < g1; ++t) {
+                const uint64_t kt = ks[t];
+                r += (kt < ki || (kt == ki && t < i)) ? 1u : 0u;
+            }
+            ks_tmp[g0 + r] = ki;
+            vs_tmp[g0 + r] = vs[i];
+        }
+        __syncwarp();
+        for (uint32_t i = g0 + lane; i < g1; i += 32) {
+            ks[i] = ks_tmp[i];
+            vs[i] = vs_tmp[i];
+        }
+        __syncwarp();
+    }
+}
+
 // ---- edges ------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kNT) edge_count_kernel(const uint64_t* __restrict__ stream_vals, uint64_t n,
@@ -361,28 +455,53 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     }
     if (M > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers on one device");
 
-    // -- sort (h1, stream index) ---------------------------------------------------------------
-    timer.start();
+    // -- sort (h1, stream index): high word in 4 passes + tie fix-up (all 64 bits if that gives up) --
     SortPairs sp;
-    sp.n = M;
-    sp.keys.alloc(M, s, true);
-    sp.vals.alloc(M, s, true);
-    SW_CUDA(cudaMemcpyAsync(sp.keys.p, st.keys.p, M * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
-    iota_kernel<<<(uint32_t)std::min<uint64_t>((M + 255) / 256, 65535), 256, 0, s>>>(sp.vals.p, M);
-    SW_CUDA(cudaGetLastError());
-    tm.launches += 1 + radix_sort_pairs(sp, 64, s);
-    tm.sort_nodes_ms = timer.stop();
-
-    // -- nodes + kmers ---------------------------------------------------------------------------
-    timer.start();
     const uint32_t nb = blocks_for(M);
     DevBuf<unsigned long long> counts((size_t)nb + 1, s, true);
-    key_run_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
-    exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
-    SW_CUDA(cudaGetLastError());
-    const unsigned long long* n_nodes_p = readback_u64(counts.p + nb, 1, s);
-    SW_CUDA(cudaStreamSynchronize(s));
-    const unsigned long long n_nodes = *n_nodes_p;
+    DevBuf<uint32_t> tie_list(kTieListCap, s, true);
+    DevBuf<uint2> tie_groups(kTieListCap, s, true);
+    DevBuf<unsigned long long> tie_counters(1, s, true);   // low word: boundaries found, high word: group too large
+    unsigned long long n_nodes = 0;
+    // SEQWIN_SORT_BEGIN_BIT (0, 8, .. 56; default 32): first key bit the radix passes look at; 0 sorts
+    // all 64 bits, larger values leave more to the fix-up (tests use them to exercise it)
+    int begin_bit = 32;
+    if (const char* e = getenv("SEQWIN_SORT_BEGIN_BIT")) begin_bit = std::max(0, std::min(56, atoi(e) & ~7));
+    for (bool full = begin_bit == 0;; full = true) {
+        timer.start();
+        sp.n = M;
+        sp.keys.alloc(M, s, true);
+        sp.vals.alloc(M, s, true);
+        SW_CUDA(cudaMemcpyAsync(sp.keys.p, st.keys.p, M * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        iota_kernel<<<(uint32_t)std::min<uint64_t>((M + 255) / 256, 65535), 256, 0, s>>>(sp.vals.p, M);
+        SW_CUDA(cudaGetLastError());
+        SW_CUDA(cudaMemsetAsync(tie_counters.p, 0, sizeof(unsigned long long), s));
+        if (full) {
+            tm.launches += 1 + radix_sort_pairs(sp, 64, s);
+        } else {
+            tm.launches += 4 + radix_sort_pairs(sp, 64, s, begin_bit);
+            unsigned int* tc = reinterpret_cast<unsigned int*>(tie_counters.p);
+            tie_detect_kernel<<<(uint32_t)sm_count() * 8, 256, 0, s>>>(sp.keys.p, M, begin_bit, tie_list.p, tc);
+            tie_group_kernel<<<(uint32_t)sm_count() * 2, 256, 0, s>>>(sp.keys.p, M, begin_bit, tie_list.p, tie_groups.p, tc);
+            tie_sort_kernel<<<(uint32_t)sm_count() * 2, 256, 0, s>>>(sp.keys.p, sp.vals.p, sp.keys_alt.p, sp.vals_alt.p,
+                                                                     tie_groups.p, tc);
+            SW_CUDA(cudaGetLastError());
+        }
+        tm.sort_nodes_ms += timer.stop();
+
+        // -- nodes + kmers -----------------------------------------------------------------------
+        timer.start();
+        key_run_count_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, M, counts.p);
+        exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
+        SW_CUDA(cudaGetLastError());
+        const unsigned long long* n_nodes_p = readback_u64(counts.p + nb, 1, s);
+        const unsigned long long* tie_p = readback_u64(tie_counters.p, 1, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        n_nodes = *n_nodes_p;
+        const unsigned long long tie = *tie_p;
+        if (full || ((uint32_t)tie <= kTieListCap && (tie >> 32) == 0)) break;
+        tm.nodes_ms += timer.stop();   // too many / too large groups of equal high words: sort everything
+    }
     g.n_nodes = n_nodes;
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
@@ -392,7 +511,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     SW_CUDA(cudaGetLastError());
     tm.launches += 3;
     if (after_nodes) (*after_nodes)();
-    tm.nodes_ms = timer.stop();
+    tm.nodes_ms += timer.stop();
 
     // -- edges -----------------------------------------------------------------------------------
     timer.start();

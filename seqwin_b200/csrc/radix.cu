@@ -43,7 +43,7 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
 
 // Digit histograms of every pass in one read of the keys.
 __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                         int n_passes, unsigned long long* ghist)
+                                                         int first_pass, int n_passes, unsigned long long* ghist)
 {
     __shared__ uint32_t sh[kMaxPasses][kRadix];
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
@@ -51,11 +51,11 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restr
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t key = keys[i];
-        for (int p = 0; p < n_passes; ++p)
+        for (int p = first_pass; p < n_passes; ++p)
             atomicAdd(&sh[p][(key >> (p * kRadixBits)) & (kRadix - 1)], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_passes * kRadix; i += blockDim.x) {
+    for (int i = first_pass * kRadix + threadIdx.x; i < n_passes * kRadix; i += blockDim.x) {
         const uint32_t c = (&sh[0][0])[i];
         if (c) atomicAdd(&ghist[i], (unsigned long long)c);
     }
@@ -273,17 +273,18 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
 
 }  // namespace
 
-uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
+uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s, int begin_bit)
 {
     const uint64_t n = sp.n;
-    if (n < 2 || end_bit <= 0) return 0;
+    if (n < 2 || end_bit <= begin_bit) return 0;
     const int n_passes = std::min(kMaxPasses, (end_bit + kRadixBits - 1) / kRadixBits);
+    const int first_pass = begin_bit / kRadixBits;   // stable LSD passes over digits [first_pass, n_passes)
     uint32_t launches = 0;
 
     DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s, true);
     SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
     const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
-    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(sp.keys.p, n, n_passes, ghist.p);
+    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(sp.keys.p, n, first_pass, n_passes, ghist.p);
     SW_CUDA(cudaGetLastError());
     ++launches;
     // exclusive digit offsets per pass, computed in place on the device; a pass whose keys all share
@@ -295,7 +296,7 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s)
     const unsigned long long* h_max = readback_u64(max_bin.p, n_passes, s);
     SW_CUDA(cudaStreamSynchronize(s));
     bool skip[kMaxPasses];
-    for (int p = 0; p < n_passes; ++p) skip[p] = (h_max[p] == n);
+    for (int p = 0; p < n_passes; ++p) skip[p] = p < first_pass || (h_max[p] == n);
 
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
     DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);

@@ -264,3 +264,23 @@ def test_low_complexity_overflows_the_density_estimate():
 def test_window_too_large_fails_loudly():
     with pytest.raises(RuntimeError, match="windowsize"):
         _dev_sketch([b"ACGT" * 100], 21, 40_000)
+
+
+@pytest.mark.parametrize("begin_bit", [0, 40, 48, 56])
+def test_node_sort_tie_fixup(begin_bit, synth_sets, digests, fixture_paths, expected_graph, monkeypatch):
+    """The node sort looks at the high word of h1 only (4 radix passes) and re-sorts the rare groups of
+    equal high words afterwards.  Starting the passes at bit 40 / 48 / 56 makes such groups common
+    (and, on the larger set, too big for the fix-up, which then falls back to the 64-bit sort);
+    bit 0 is the plain 64-bit sort.  The graphs must not change."""
+    monkeypatch.setenv("SEQWIN_SORT_BEGIN_BIT", str(begin_bit))
+    kmers, nodes, edges, offsets, _ = _build(fixture_paths, 17, 10, n_cpu=1)
+    np.testing.assert_array_equal(kmers, expected_graph["kmers"])
+    np.testing.assert_array_equal(edges, expected_graph["edges"])
+    for f in ("hash", "start", "stop"):
+        np.testing.assert_array_equal(nodes[f], expected_graph["nodes"][f])
+    for case in ("synth_small", "synth_medium", "synth_skew"):
+        paths, is_t = synth_sets[case]
+        for kw in GOLDEN_KW[:3]:
+            d = digests[case][f"{kw[0]},{kw[1]}"]
+            got = _build(paths, *kw, n_cpu=4)
+            assert_matches_digest(got, d, f"{case} {kw} begin_bit={begin_bit}")
