@@ -14,6 +14,8 @@
 // 64-bit key whose unused high digits are skipped, instead of a 128-bit hash pair.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include <algorithm>
 
 #include "device.h"
@@ -282,6 +284,39 @@ __global__ void __launch_bounds__(256) tie_sort_kernel(uint64_t* ks, uint32_t* v
     }
 }
 
+// Enqueue a stable sort of sp on key bits [full_begin_bit, 64): either all of those passes, or only
+// the passes from begin_bit up followed by the tie fix-up.  The caller reads `counters` back at its
+// next synchronisation point and, if gave_up(), refills sp and calls again with full = true.
+struct TieFix {
+    DevBuf<uint32_t> list;
+    DevBuf<uint2> groups;
+    DevBuf<unsigned long long> counters;   // low word: boundaries found, high word: a group was too large
+    explicit TieFix(cudaStream_t s) : list(kTieListCap, s, true), groups(kTieListCap, s, true), counters(1, s, true) {}
+
+    uint32_t sort(SortPairs& sp, int begin_bit, int full_begin_bit, bool full, cudaStream_t s)
+    {
+        SW_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long), s));
+        if (full || begin_bit <= full_begin_bit) return radix_sort_pairs(sp, 64, s, full_begin_bit);
+        const uint32_t launches = radix_sort_pairs(sp, 64, s, begin_bit);
+        unsigned int* tc = reinterpret_cast<unsigned int*>(counters.p);
+        tie_detect_kernel<<<(uint32_t)sm_count() * 8, 256, 0, s>>>(sp.keys.p, sp.n, begin_bit, list.p, tc);
+        tie_group_kernel<<<(uint32_t)sm_count() * 2, 256, 0, s>>>(sp.keys.p, sp.n, begin_bit, list.p, groups.p, tc);
+        tie_sort_kernel<<<(uint32_t)sm_count() * 2, 256, 0, s>>>(sp.keys.p, sp.vals.p, sp.keys_alt.p, sp.vals_alt.p,
+                                                                 groups.p, tc);
+        SW_CUDA(cudaGetLastError());
+        return launches + 3;
+    }
+    static bool gave_up(unsigned long long c) { return (uint32_t)c > kTieListCap || (c >> 32) != 0; }
+};
+
+// first key bit the reduced sorts look at (SEQWIN_SORT_BEGIN_BIT = 0, 8, .. 56; default 32).  0 sorts
+// every significant bit; larger values leave more to the fix-up (tests use them to exercise it).
+int sort_begin_bit()
+{
+    if (const char* e = getenv("SEQWIN_SORT_BEGIN_BIT")) return std::max(0, std::min(56, atoi(e) & ~7));
+    return 32;
+}
+
 // ---- edges ------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kNT) edge_count_kernel(const uint64_t* __restrict__ stream_vals, uint64_t n,
@@ -302,7 +337,7 @@ __global__ void __launch_bounds__(kNT) edge_count_kernel(const uint64_t* __restr
 __global__ void __launch_bounds__(kNT) edge_write_kernel(
     const uint64_t* __restrict__ stream_vals, const uint32_t* __restrict__ rank_of_stream, uint64_t n,
     const uint32_t* __restrict__ rec_asm, uint32_t rec_base, const unsigned long long* __restrict__ block_off,
-    uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm)
+    int rank_bits, uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm)
 {
     __shared__ uint32_t s_cnt[kRounds][kNT / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
@@ -327,7 +362,8 @@ __global__ void __launch_bounds__(kNT) edge_write_kernel(
             uint32_t u = rank_of_stream[i], v = rank_of_stream[i + 1];
             if (v < u) { const uint32_t t = u; u = v; v = t; }
             const unsigned long long slot = off + rank[r];
-            ekey[slot] = ((uint64_t)u << 32) | v;
+            // (u, v) left-aligned: u in the top rank_bits bits, v right below (sorts like u << 32 | v)
+            ekey[slot] = ((uint64_t)u << (64 - rank_bits)) | ((uint64_t)v << (64 - 2 * rank_bits));
             easm[slot] = rec_asm[rec[r] - rec_base];
         }
     }
@@ -335,7 +371,8 @@ __global__ void __launch_bounds__(kNT) edge_write_kernel(
 
 __global__ void __launch_bounds__(kNT) edge_final_kernel(
     const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ easm, uint64_t n,
-    const unsigned long long* __restrict__ block_off, const sw_node* __restrict__ nodes, sw_edge* __restrict__ edges)
+    const unsigned long long* __restrict__ block_off, int rank_bits, const sw_node* __restrict__ nodes,
+    sw_edge* __restrict__ edges)
 {
     __shared__ uint32_t s_cnt[kRounds][kNT / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
@@ -361,8 +398,8 @@ __global__ void __launch_bounds__(kNT) edge_final_kernel(
         if (j < n) {
             const unsigned long long e = off + rank[r] + (new_pair[r] ? 1u : 0u) - 1u;
             if (new_pair[r]) {
-                edges[e].first = nodes[(uint32_t)(key[r] >> 32)].hash;
-                edges[e].second = nodes[(uint32_t)key[r]].hash;
+                edges[e].first = nodes[key[r] >> (64 - rank_bits)].hash;
+                edges[e].second = nodes[(key[r] >> (64 - 2 * rank_bits)) & ((1ull << rank_bits) - 1)].hash;
             }
             // weight was zeroed before the launch; one count per distinct assembly of the run
             if (new_asm[r]) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), 1ULL);
@@ -459,14 +496,9 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     SortPairs sp;
     const uint32_t nb = blocks_for(M);
     DevBuf<unsigned long long> counts((size_t)nb + 1, s, true);
-    DevBuf<uint32_t> tie_list(kTieListCap, s, true);
-    DevBuf<uint2> tie_groups(kTieListCap, s, true);
-    DevBuf<unsigned long long> tie_counters(1, s, true);   // low word: boundaries found, high word: group too large
+    TieFix tie(s);
+    const int begin_bit = sort_begin_bit();
     unsigned long long n_nodes = 0;
-    // SEQWIN_SORT_BEGIN_BIT (0, 8, .. 56; default 32): first key bit the radix passes look at; 0 sorts
-    // all 64 bits, larger values leave more to the fix-up (tests use them to exercise it)
-    int begin_bit = 32;
-    if (const char* e = getenv("SEQWIN_SORT_BEGIN_BIT")) begin_bit = std::max(0, std::min(56, atoi(e) & ~7));
     for (bool full = begin_bit == 0;; full = true) {
         timer.start();
         sp.n = M;
@@ -475,18 +507,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         SW_CUDA(cudaMemcpyAsync(sp.keys.p, st.keys.p, M * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
         iota_kernel<<<(uint32_t)std::min<uint64_t>((M + 255) / 256, 65535), 256, 0, s>>>(sp.vals.p, M);
         SW_CUDA(cudaGetLastError());
-        SW_CUDA(cudaMemsetAsync(tie_counters.p, 0, sizeof(unsigned long long), s));
-        if (full) {
-            tm.launches += 1 + radix_sort_pairs(sp, 64, s);
-        } else {
-            tm.launches += 4 + radix_sort_pairs(sp, 64, s, begin_bit);
-            unsigned int* tc = reinterpret_cast<unsigned int*>(tie_counters.p);
-            tie_detect_kernel<<<(uint32_t)sm_count() * 8, 256, 0, s>>>(sp.keys.p, M, begin_bit, tie_list.p, tc);
-            tie_group_kernel<<<(uint32_t)sm_count() * 2, 256, 0, s>>>(sp.keys.p, M, begin_bit, tie_list.p, tie_groups.p, tc);
-            tie_sort_kernel<<<(uint32_t)sm_count() * 2, 256, 0, s>>>(sp.keys.p, sp.vals.p, sp.keys_alt.p, sp.vals_alt.p,
-                                                                     tie_groups.p, tc);
-            SW_CUDA(cudaGetLastError());
-        }
+        tm.launches += 1 + tie.sort(sp, begin_bit, 0, full, s);
         tm.sort_nodes_ms += timer.stop();
 
         // -- nodes + kmers -----------------------------------------------------------------------
@@ -495,11 +516,11 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
         SW_CUDA(cudaGetLastError());
         const unsigned long long* n_nodes_p = readback_u64(counts.p + nb, 1, s);
-        const unsigned long long* tie_p = readback_u64(tie_counters.p, 1, s);
+        const unsigned long long* tie_p = readback_u64(tie.counters.p, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
         n_nodes = *n_nodes_p;
-        const unsigned long long tie = *tie_p;
-        if (full || ((uint32_t)tie <= kTieListCap && (tie >> 32) == 0)) break;
+        if (getenv("SEQWIN_DEBUG_TIE")) fprintf(stderr, "[tie] nodes: M %llu boundaries %u too_large %u\n", (unsigned long long)M, (unsigned)*tie_p, (unsigned)(*tie_p >> 32));
+        if (full || !TieFix::gave_up(*tie_p)) break;
         tm.nodes_ms += timer.stop();   // too many / too large groups of equal high words: sort everything
     }
     g.n_nodes = n_nodes;
@@ -525,24 +546,39 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     if (n_raw == 0) {
         g.edges.alloc(0, s);
     } else {
-        // reuse the node sort's buffers for the (rank pair, assembly) sort
-        sp.n = n_raw;
-        edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, rec_base, counts.p, sp.keys.p,
-                                             sp.vals.p);
-        SW_CUDA(cudaGetLastError());
-        tm.launches += 1 + radix_sort_pairs(sp, 64, s);
+        // reuse the node sort's buffers for the (rank pair, assembly) sort.  The key holds the two
+        // ranks left-aligned (2 * rank_bits significant bits); the radix passes look at its high word
+        // and the tie fix-up finishes the few pairs that agree there.
+        int rank_bits = 1;
+        while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
+        const int full_begin_bit = (64 - 2 * rank_bits) & ~7;
+        // first + 16 bits of second: pairs that still agree there are rare enough for the fix-up (with
+        // only the high word, 10 bits of `second` at 4 M nodes, the C2 workload leaves 228 k boundaries)
+        const int edge_begin_bit = getenv("SEQWIN_SORT_BEGIN_BIT") ? begin_bit
+                                                                    : std::min(begin_bit, std::max(0, 64 - rank_bits - 16) & ~7);
         const uint32_t eb = blocks_for(n_raw);
         DevBuf<unsigned long long> ecounts((size_t)eb + 1, s, true);
-        key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
-        exclusive_scan_u64(ecounts.p, eb, ecounts.p + eb, s);
-        SW_CUDA(cudaGetLastError());
-        const unsigned long long* n_edges_p = readback_u64(ecounts.p + eb, 1, s);
-        SW_CUDA(cudaStreamSynchronize(s));
-        const unsigned long long n_edges = *n_edges_p;
+        unsigned long long n_edges = 0;
+        for (bool full = edge_begin_bit <= full_begin_bit;; full = true) {
+            sp.n = n_raw;
+            edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, rec_base, counts.p, rank_bits,
+                                                 sp.keys.p, sp.vals.p);
+            SW_CUDA(cudaGetLastError());
+            tm.launches += 1 + tie.sort(sp, edge_begin_bit, full_begin_bit, full, s);
+            key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
+            exclusive_scan_u64(ecounts.p, eb, ecounts.p + eb, s);
+            SW_CUDA(cudaGetLastError());
+            const unsigned long long* n_edges_p = readback_u64(ecounts.p + eb, 1, s);
+            const unsigned long long* tie_p = readback_u64(tie.counters.p, 1, s);
+            SW_CUDA(cudaStreamSynchronize(s));
+            n_edges = *n_edges_p;
+            if (getenv("SEQWIN_DEBUG_TIE")) fprintf(stderr, "[tie] edges: n_raw %llu boundaries %u too_large %u rank_bits %d\n", n_raw, (unsigned)*tie_p, (unsigned)(*tie_p >> 32), rank_bits);
+            if (full || !TieFix::gave_up(*tie_p)) break;
+        }
         g.n_edges = n_edges;
         g.edges.alloc(n_edges, s);
         SW_CUDA(cudaMemsetAsync(g.edges.p, 0, n_edges * sizeof(sw_edge), s));
-        edge_final_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_raw, ecounts.p, g.nodes.p, g.edges.p);
+        edge_final_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_raw, ecounts.p, rank_bits, g.nodes.p, g.edges.p);
         SW_CUDA(cudaGetLastError());
         tm.launches += 3;
     }
