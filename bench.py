@@ -250,19 +250,13 @@ def main():
         _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
         st = StageTimes()
         is_t = np.ascontiguousarray(ss.is_targets[my_genomes.start:my_genomes.stop], dtype=np.bool_)
-        pen_ms = C.c_float()
-
         def dev_step():
-            # build + scoring, like the reference arm (_build_native + _get_penalty_native)
+            # build + scoring, like the reference arm (_build_native + _get_penalty_native); the classes are
+            # known up front, so the scoring is fused into the node stage (sw_dev_build_scored)
             g = C.c_void_p()
-            _lib.check(L.sw_dev_build(dev, k, w, C.byref(g), C.byref(st)))
-            _lib.check(L.sw_graph_penalty(g, None, 0, is_t.ctypes.data, len(is_t), C.byref(pen_ms)))
+            _lib.check(L.sw_dev_build_scored(dev, k, w, is_t.ctypes.data, len(is_t), C.byref(g), C.byref(st)))
             L.sw_graph_free(g)
-            d = st.as_dict()
-            d["penalty_ms"] = pen_ms.value
-            d["total_ms"] += pen_ms.value
-            d["total_launches"] += 1
-            return d
+            return st.as_dict()
 
         for _ in range(args.warmup):
             dev_step()

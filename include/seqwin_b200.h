@@ -112,10 +112,16 @@ int sw_dev_build(const sw_dev_batch* d, uint32_t k, uint32_t w, sw_graph** out, 
 /* End-to-end from pinned host memory: H2D + build + D2H into the graph's host arrays. */
 int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t);
 
-/* Build + score in one call: get_penalty (filter.cpp:15-137) runs on the device-resident kmers / nodes
- * before they are exported, so the host receives nodes with n_tar / n_neg / penalty filled in. */
+/* Build + score in one call: the classes of the batch's assemblies are known up front, so get_penalty
+ * (filter.cpp:15-137) is fused into the node stage -- n_tar / n_neg are counted while the nodes are
+ * written, the penalty follows in one pass -- and the nodes come back with the three fields filled in.
+ * is_targets has one byte per assembly of the batch and needs at least one target and one non-target
+ * (SW_ERR_VALUE otherwise, as in filter.cpp:33-60). */
 int sw_build_from_batch_scored(const sw_batch* b, uint32_t k, uint32_t w, const uint8_t* is_targets,
                                size_t n_assemblies, sw_graph** out, sw_stage_times* t);
+/* The same on a device-resident batch; the graph stays in HBM. */
+int sw_dev_build_scored(const sw_dev_batch* d, uint32_t k, uint32_t w, const uint8_t* is_targets, size_t n_assemblies,
+                        sw_graph** out, sw_stage_times* t);
 /* get_penalty on a device-resident graph (record_offsets == NULL: the graph's own offsets; pass the
  * global offsets for a multi-GPU hash-range graph). kernel_ms may be NULL. */
 int sw_graph_penalty(sw_graph* g, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "sw_dev_build": (_I, [_P, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_build_from_batch": (_I, [_P, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_build_from_batch_scored": (_I, [_P, _U32, _U32, _P, _SZ, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_dev_build_scored": (_I, [_P, _U32, _U32, _P, _SZ, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_graph_penalty": (_I, [_P, _P, _SZ, _P, _SZ, C.POINTER(C.c_float)]),
     "sw_dev_sketch": (_I, [_P, _U32, _U32, _P, _P, _P, _SZ, C.POINTER(_SZ)]),
     "sw_set_stream": (_I, [_P]),

@@ -377,12 +377,33 @@ void fire_nodes_ready(sw_graph* g)
     g_nodes_ready(g_nodes_ready_user, g);
 }
 
-sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t, uint32_t rec_base = 0)
+// Classes of the batch's assemblies for a build that scores its nodes on the way (ScoreArgs): the
+// checks of filter.cpp:33-60 that concern is_targets, then the flags go to the device.
+struct ScoreUpload {
+    DevBuf<uint8_t> d_t;
+    ScoreArgs args{};
+    ScoreUpload(const uint8_t* is_targets, size_t n_assemblies, size_t n_batch_assemblies, cudaStream_t s)
+    {
+        if (n_assemblies != n_batch_assemblies) fail_value("len(is_targets) must equal the number of assemblies");
+        size_t n_t = 0;
+        for (size_t i = 0; i < n_assemblies; ++i) n_t += is_targets[i] ? 1 : 0;
+        if (!n_t) fail_value("is_targets must contain at least one target assembly");
+        if (n_t == n_assemblies) fail_value("is_targets must contain at least one non-target assembly");
+        d_t.alloc(n_assemblies, s, true);
+        SW_CUDA(cudaMemcpyAsync(d_t.p, is_targets, n_assemblies, cudaMemcpyHostToDevice, s));
+        args = ScoreArgs{d_t.p, 1.0 / (double)n_t, 1.0 / (double)(n_assemblies - n_t)};
+    }
+};
+
+sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t, uint32_t rec_base = 0,
+                    const uint8_t* is_targets = nullptr, size_t n_assemblies = 0)
 {
     init_device_once();
     check_kw(k, w);
     cudaStream_t s = d.stream;
     arena_reset();
+    std::unique_ptr<ScoreUpload> score;
+    if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, d.meta.record_offsets.size() - 1, s);
     auto g = std::make_unique<sw_graph>();
     g->stream = s;
     g->record_offsets = d.meta.record_offsets;
@@ -401,7 +422,7 @@ sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_time
     cudaEventRecord(e1, s);
     GraphTimes gt;
     const std::function<void()> after_nodes = [&] { fire_nodes_ready(g.get()); };
-    build_graph(st, d.rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes);
+    build_graph(st, d.rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes, score ? &score->args : nullptr);
     cudaEventRecord(e2, s);
     SW_CUDA(cudaStreamSynchronize(s));
     g->on_device = true;
@@ -559,10 +580,12 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, rec_base, s, st, &chunks);
 
     bool d2h_started = false;
-    float penalty_ms = 0;
+    const float penalty_ms = 0;   // scoring is part of the node stage
+    std::unique_ptr<ScoreUpload> score;
+    if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, b.record_offsets.size() - 1, s);
     const std::function<void()> after_nodes = [&] {
         if (to_host) {
-            // the k-mer array is final: its copy starts now and runs under the scoring kernel
+            // kmers + nodes are final (scored in the node stage when the classes were given)
             g->n_kmers = g->dev.n_kmers;
             g->n_nodes = g->dev.n_nodes;
             g->h_kmers = host_pool_get(g->n_kmers * sizeof(sw_kmer));
@@ -574,13 +597,6 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
                 SW_CUDA(cudaMemcpyAsync(g->h_kmers.p, g->dev.kmers.p, g->n_kmers * sizeof(sw_kmer), cudaMemcpyDeviceToHost, cs));
             d2h_started = true;
         }
-        // scoring (get_penalty) fills n_tar / n_neg / penalty of the device-resident nodes before they are exported
-        try {
-            if (is_targets) penalty_ms = penalty_on_device(g->dev, b.record_offsets, is_targets, n_assemblies, s);
-        } catch (...) {
-            cudaStreamSynchronize(cs);   // the k-mer copy must not outlive the buffers the unwinding frees
-            throw;
-        }
         fire_nodes_ready(g.get());
         if (!to_host) return;
         cudaEventRecord(e_nodes, s);
@@ -589,7 +605,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
             SW_CUDA(cudaMemcpyAsync(g->h_nodes.p, g->dev.nodes.p, g->n_nodes * sizeof(sw_node), cudaMemcpyDeviceToHost, cs));
     };
     GraphTimes gt;
-    build_graph(st, d->rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes);
+    build_graph(st, d->rec_asm.p, rec_base, s, g->dev, &gt, &after_nodes, score ? &score->args : nullptr);
     g->on_device = true;
     g->n_kmers = g->dev.n_kmers;
     g->n_nodes = g->dev.n_nodes;
@@ -725,6 +741,15 @@ void sw_dev_batch_free(sw_dev_batch* d)
 int sw_dev_build(const sw_dev_batch* d, uint32_t k, uint32_t w, sw_graph** out, sw_stage_times* t)
 {
     return guarded([&] { *out = dev_build(*d, k, w, t); });
+}
+
+int sw_dev_build_scored(const sw_dev_batch* d, uint32_t k, uint32_t w, const uint8_t* is_targets, size_t n_assemblies,
+                        sw_graph** out, sw_stage_times* t)
+{
+    return guarded([&] {
+        if (!is_targets) fail_value("is_targets is required");
+        *out = dev_build(*d, k, w, t, 0u, is_targets, n_assemblies);
+    });
 }
 
 int sw_set_stream(void* stream)

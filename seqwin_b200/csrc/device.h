@@ -145,8 +145,16 @@ struct GraphTimes {
 // d_rec_asm: assembly index of every global record id used in the stream.
 // after_nodes (optional) is called once kmers + nodes are final and enqueued on s, before the edge
 // stage starts: the end-to-end path uses it to begin their D2H copies on a second stream.
+// score (optional): the classes of the assemblies are known at build time, so n_tar / n_neg are
+// counted while the nodes are written and the penalty follows in one pass over the nodes
+// (get_penalty, cpp/src/seqwin/filter.cpp:15-137, fused into the build).
+struct ScoreArgs {
+    const uint8_t* d_is_target;   // [n_assemblies], indexed by the values of d_rec_asm
+    double inv_t, inv_n;          // 1 / #targets, 1 / #non-targets
+};
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
-                 GraphTimes* times, const std::function<void()>* after_nodes = nullptr);
+                 GraphTimes* times, const std::function<void()>* after_nodes = nullptr,
+                 const ScoreArgs* score = nullptr);
 
 // ---- multi-GPU merge (dist.cu) -------------------------------------------------------------------
 void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out /* 3*(P+1) */, cudaStream_t s);

@@ -142,12 +142,18 @@ __global__ void __launch_bounds__(kNT) key_run_count_kernel(const uint64_t* __re
 }
 
 
+// SCORE: also count, per node, the distinct target / non-target assemblies among its k-mers (they
+// are sorted by record, hence by assembly, inside a node): a warp-segmented sum over the node rank,
+// one 64-bit atomic per (warp, node) on the adjacent {n_tar, n_neg} fields, which the host zeroed.
+template <bool SCORE>
 __global__ void __launch_bounds__(kNT) node_write_kernel(
     const uint64_t* __restrict__ ks, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ stream_vals,
     uint64_t n, const unsigned long long* __restrict__ block_off, sw_kmer* __restrict__ kmers,
-    sw_node* __restrict__ nodes, uint32_t* __restrict__ rank_of_stream)
+    sw_node* __restrict__ nodes, uint64_t* __restrict__ node_hash, uint32_t* __restrict__ rank_of_stream,
+    const uint32_t* __restrict__ rec_asm, uint32_t rec_base, const uint8_t* __restrict__ is_target)
 {
     __shared__ uint32_t s_cnt[kRounds][kNT / 32];
+    __shared__ uint32_t s_asm[SCORE ? kBlockItems : 1];
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
     const unsigned long long off = block_off[blockIdx.x];
     // all loads of the block's items are issued before anything depends on them
@@ -167,27 +173,72 @@ __global__ void __launch_bounds__(kNT) node_write_kernel(
         val[r] = j < n ? __ldcs(stream_vals + src[r]) : 0;
         flag[r] = j < n && (j == 0 || key[r] != ks[j - 1]);
     }
-    block_ranks(flag, rank, s_cnt);
+    if (SCORE) {
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+            s_asm[r * kNT + threadIdx.x] = j < n ? rec_asm[(uint32_t)(val[r] >> 32) - rec_base] : 0u;
+        }
+    }
+    block_ranks(flag, rank, s_cnt);   // contains the barrier that publishes s_asm
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        unsigned long long nr = ~0ull;
         if (j < n) {
             // node rank of element j = (#run starts up to and including j) - 1
-            const unsigned long long nr = off + rank[r] + (flag[r] ? 1u : 0u) - 1u;
+            nr = off + rank[r] + (flag[r] ? 1u : 0u) - 1u;
             __stcs(reinterpret_cast<unsigned long long*>(kmers + j), (unsigned long long)val[r]);
             rank_of_stream[src[r]] = (uint32_t)nr;
             if (flag[r]) {
                 sw_node* nd = nodes + nr;
                 nd->hash = key[r];
+                node_hash[nr] = key[r];   // compact copy: the edge stage gathers hashes by rank (8 B, not a 40 B stride)
                 nd->start = j;
-                nd->n_tar = 0;
-                nd->n_neg = 0;
-                nd->penalty = 0.0;
+                if (!SCORE) {
+                    nd->n_tar = 0;
+                    nd->n_neg = 0;
+                    nd->penalty = 0.0;
+                }
                 if (nr > 0) nodes[nr - 1].stop = j;
             }
             if (j == n - 1) nodes[nr].stop = n;
         }
+        if (SCORE) {
+            unsigned long long v = 0;
+            if (j < n) {
+                const uint32_t li = (uint32_t)r * kNT + threadIdx.x, a = s_asm[li];
+                bool fresh = flag[r];
+                if (!fresh) {
+                    // previous element in sorted order: one slot back, or the previous block's last element
+                    const uint32_t pa = li ? s_asm[li - 1] : rec_asm[(uint32_t)(stream_vals[idx[j - 1]] >> 32) - rec_base];
+                    fresh = pa != a;
+                }
+                if (fresh) v = is_target[a] ? 1ull : (1ull << 32);
+            }
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long k2 = __shfl_up_sync(0xffffffffu, nr, d), v2 = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d && k2 == nr) v += v2;
+            }
+            const unsigned long long next = __shfl_down_sync(0xffffffffu, nr, 1);
+            if (j < n && v && (lane == 31 || next != nr))
+                atomicAdd(reinterpret_cast<unsigned long long*>(&nodes[nr].n_tar), v);
+        }
     }
+}
+
+// penalty from the finished counts (filter.cpp:132-134), evaluated without fused multiply-add
+__global__ void __launch_bounds__(256) penalty_finish_kernel(sw_node* __restrict__ nodes, uint64_t n_nodes, double inv_t,
+                                                             double inv_n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const double ft = __dmul_rn((double)nodes[i].n_tar, inv_t);
+    const double fn = __dmul_rn((double)nodes[i].n_neg, inv_n);
+    const double a = __dsub_rn(1.0, ft);
+    nodes[i].penalty = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(fn, fn)));
 }
 
 // ---- node sort on the high word of h1 + tie fix-up ----------------------------------------------
@@ -371,7 +422,7 @@ __global__ void __launch_bounds__(kNT) edge_write_kernel(
 
 __global__ void __launch_bounds__(kNT) edge_final_kernel(
     const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ easm, uint64_t n,
-    const unsigned long long* __restrict__ block_off, int rank_bits, const sw_node* __restrict__ nodes,
+    const unsigned long long* __restrict__ block_off, int rank_bits, const uint64_t* __restrict__ node_hash,
     sw_edge* __restrict__ edges)
 {
     __shared__ uint32_t s_cnt[kRounds][kNT / 32];
@@ -398,8 +449,8 @@ __global__ void __launch_bounds__(kNT) edge_final_kernel(
         if (j < n) {
             const unsigned long long e = off + rank[r] + (new_pair[r] ? 1u : 0u) - 1u;
             if (new_pair[r]) {
-                edges[e].first = nodes[key[r] >> (64 - rank_bits)].hash;
-                edges[e].second = nodes[(key[r] >> (64 - 2 * rank_bits)) & ((1ull << rank_bits) - 1)].hash;
+                edges[e].first = node_hash[key[r] >> (64 - rank_bits)];
+                edges[e].second = node_hash[(key[r] >> (64 - 2 * rank_bits)) & ((1ull << rank_bits) - 1)];
             }
             // weight was zeroed before the launch; one count per distinct assembly of the run
             if (new_asm[r]) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), 1ULL);
@@ -475,7 +526,7 @@ uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlockItems - 1) / kBlo
 }  // namespace
 
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
-                 GraphTimes* times, const std::function<void()>* after_nodes)
+                 GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
 {
     const uint64_t M = st.n;
     g.n_kmers = M;
@@ -527,8 +578,18 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
     DevBuf<uint32_t> rank_of_stream(M, s, true);
-    node_write_kernel<<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
-                                         rank_of_stream.p);
+    DevBuf<uint64_t> node_hash(n_nodes, s, true);
+    if (score) {
+        SW_CUDA(cudaMemsetAsync(g.nodes.p, 0, n_nodes * sizeof(sw_node), s));
+        node_write_kernel<true><<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
+                                                   node_hash.p, rank_of_stream.p, d_rec_asm, rec_base, score->d_is_target);
+        penalty_finish_kernel<<<(uint32_t)((n_nodes + 255) / 256), 256, 0, s>>>(g.nodes.p, n_nodes, score->inv_t,
+                                                                                score->inv_n);
+        ++tm.launches;
+    } else {
+        node_write_kernel<false><<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
+                                                    node_hash.p, rank_of_stream.p, nullptr, 0u, nullptr);
+    }
     SW_CUDA(cudaGetLastError());
     tm.launches += 3;
     if (after_nodes) (*after_nodes)();
@@ -578,7 +639,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         g.n_edges = n_edges;
         g.edges.alloc(n_edges, s);
         SW_CUDA(cudaMemsetAsync(g.edges.p, 0, n_edges * sizeof(sw_edge), s));
-        edge_final_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_raw, ecounts.p, rank_bits, g.nodes.p, g.edges.p);
+        edge_final_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_raw, ecounts.p, rank_bits, node_hash.p, g.edges.p);
         SW_CUDA(cudaGetLastError());
         tm.launches += 3;
     }

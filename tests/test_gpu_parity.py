@@ -173,8 +173,15 @@ def test_scored_build_entry_points(edge_paths):
             _lib.check(L.sw_graph_penalty(g, None, 0, is_t.ctypes.data, len(is_t), None))
             kmers, nodes, edges = export_graph(L, g)
             L.sw_graph_free(g)
+            assert np.array_equal(nodes, want["nodes_penalty"]) and np.array_equal(kmers, want["kmers"])
+            # device-resident entry with the classes known up front: scoring fused into the node stage
+            g = C.c_void_p()
+            _lib.check(L.sw_dev_build_scored(d, k, w, is_t.ctypes.data, len(is_t), C.byref(g), None))
+            kmers, nodes, edges = export_graph(L, g)
+            L.sw_graph_free(g)
             L.sw_dev_batch_free(d)
             assert np.array_equal(nodes, want["nodes_penalty"]) and np.array_equal(kmers, want["kmers"])
+            assert np.array_equal(edges, want["edges"])
         finally:
             L.sw_batch_free(b)
     with pytest.raises(ValueError):
@@ -183,6 +190,13 @@ def test_scored_build_entry_points(edge_paths):
         try:
             all_t = np.ones(len(paths), dtype=np.bool_)
             _lib.check(L.sw_build_from_batch_scored(b, 17, 10, all_t.ctypes.data, len(all_t), C.byref(g), None))
+        finally:
+            L.sw_batch_free(b)
+    with pytest.raises(ValueError):   # one flag per assembly of the batch
+        b = C.c_void_p()
+        _lib.check(L.sw_batch_from_fasta(arr, len(paths), 2, C.byref(b)))
+        try:
+            _lib.check(L.sw_build_from_batch_scored(b, 17, 10, is_t.ctypes.data, len(is_t) - 1, C.byref(g), None))
         finally:
             L.sw_batch_free(b)
 
