@@ -509,8 +509,8 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         {   // SEQWIN_SPARSE_CPW / SEQWIN_SPARSE_SMALL: tuning overrides (any value gives the same output)
             const char* e1 = getenv("SEQWIN_SPARSE_CPW");
             const char* e2 = getenv("SEQWIN_SPARSE_SMALL");
-            P.cand_hi = sparse_threshold(w, e1 ? atof(e1) : kSparseCandPerWindow);
-            P.cand_hi_a = sparse_threshold(w, e2 ? atof(e2) : kSparseSmallPerWindow);
+            P.cand_hi = sparse_threshold(w, e1 ? atof(e1) : sparse_cand_per_window(w));
+            P.cand_hi_a = sparse_threshold(w, e2 ? atof(e2) : sparse_small_per_window(w));
         }
         P.fallback_count = reinterpret_cast<unsigned int*>(counters.p + 2);
         P.fallback_tiles = fallback_tiles.p;

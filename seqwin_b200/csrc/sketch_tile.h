@@ -610,10 +610,10 @@ SW_HD void fastD_write(const SketchParams& P, const Tile& T, const TileSmem& S, 
 //
 // Only small hashes can be selected: if every window holds at least one CANDIDATE, a k-mer with
 // (h0 >> 32) < cand_hi, then every selection is a candidate and L / R need only be looked for among
-// candidates.  cand_hi keeps about kSparseCandPerWindow candidates per window, so each thread
+// candidates.  cand_hi keeps about 11 candidates per window (sparse_cand_per_window), so each thread
 //   A  hashes C1 consecutive k-mers and appends the few candidates to a private list  (no h0 array)
 //   C  the lists are compacted into one position-ordered array per tile, plus a second array with
-//      only the SMALL candidates ((h0 >> 32) < cand_hi_a, about kSparseSmallPerWindow per window)
+//      only the SMALL candidates ((h0 >> 32) < cand_hi_a, about 4 per window)
 //   S  one thread per candidate walks outwards until it meets L and R (or has gone w positions).
 //      A small candidate can only be stopped by small ones, so it walks the short array.  Any other
 //      candidate first looks at the small ones next to it: they are all smaller, so unless w k-mers
@@ -639,9 +639,12 @@ struct SparseSmem {
 SW_HD constexpr uint32_t sparse_mc(uint32_t nt) { return nt * 5; }
 SW_HD constexpr uint32_t sparse_ma(uint32_t nt) { return nt * 7 / 4; }
 constexpr uint32_t kSparseCheck = 8;       // a private list is checked for room every 8 steps
-constexpr uint32_t kSparseMinW = 96;       // below this the dense kernels are used for every tile
-constexpr double kSparseCandPerWindow = 11.0;
-constexpr double kSparseSmallPerWindow = 4.0;
+constexpr uint32_t kSparseMinW = 144;      // below this the dense kernels are used for every tile
+// Candidates / small candidates per window.  At most one k-mer in 16 may be a candidate (the lists and
+// arrays are sized for that), so narrow windows get fewer per window and hand over more tiles for
+// lack of coverage: e^-9 per candidate at w = 144 (6 % of the tiles), e^-11 from w = 176 on (0.7 %).
+inline double sparse_cand_per_window(uint32_t w) { return w >= 176 ? 11.0 : (double)w / 16.0; }
+inline double sparse_small_per_window(uint32_t w) { return sparse_cand_per_window(w) * 4.0 / 11.0; }
 
 SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
 {

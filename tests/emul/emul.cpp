@@ -155,8 +155,8 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
     EmulOut o;
     SketchParams P = make_params(b, plan, k, w, FC1, o);
     // cand_per_window <= 0: the library's thresholds; else that many candidates, a third of them small
-    P.cand_hi = sparse_threshold(w, cand_per_window <= 0 ? kSparseCandPerWindow : cand_per_window);
-    P.cand_hi_a = sparse_threshold(w, cand_per_window <= 0 ? kSparseSmallPerWindow : cand_per_window / 3.0);
+    P.cand_hi = sparse_threshold(w, cand_per_window <= 0 ? sparse_cand_per_window(w) : cand_per_window);
+    P.cand_hi_a = sparse_threshold(w, cand_per_window <= 0 ? sparse_small_per_window(w) : cand_per_window / 3.0);
     constexpr uint32_t MC = sparse_mc(NT), MA = sparse_ma(NT);
     std::vector<unsigned char> smem(sparse_smem_bytes(NT, CAP) + 64);
     SparseSmem S = carve_sparse_smem(smem.data(), NT, CAP);
