@@ -233,7 +233,8 @@ def _dev_sketch(seqs, k, w):
 
 
 @pytest.mark.parametrize("kw", [(21, 200), (21, 10), (5, 3), (4, 1), (31, 50), (21, 46), (9, 9), (15, 64), (33, 1000),
-                                (21, 3000), (255, 40)], ids=lambda kw: f"k{kw[0]}w{kw[1]}")
+                                (21, 3000), (255, 40), (21, 144), (15, 150), (31, 175), (21, 2048), (17, 143), (64, 500),
+                                (3, 200)], ids=lambda kw: f"k{kw[0]}w{kw[1]}")
 def test_sketch_stream_matches_oracle(kw):
     """Ordered minimizer stream of the sketch kernel vs btllib semantics (minimizer.cpp:53-90)."""
     k, w = kw
