@@ -168,6 +168,23 @@ int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const voi
                   const uint64_t* kmer_counts, const uint64_t* kmer_base, const void* recv_edges,
                   const uint64_t* edge_counts, uint32_t n_src, sw_graph** out, uint32_t* launches);
 
+/* ---- first consumers of the graph, on the device-resident arrays ------------ */
+/* Edge-weight filter + isolated-node removal, the array part of _filter_edges_and_nodes
+ * (src/seqwin/kmers.py:132-162): keeps edges with weight > weight_th and the nodes that are an
+ * endpoint of a kept edge; order and all fields unchanged (node ranges still refer to the k-mer array).
+ * In place on a device-resident graph ... */
+int sw_graph_filter_edges(sw_graph* g, uint64_t weight_th);
+/* ... or from / to host arrays (nodes_out / edges_out sized like the inputs; the counts come back).
+ * SW_ERR_VALUE if an edge endpoint is not a node hash. */
+int sw_filter_edges_and_nodes(const sw_node* nodes, size_t n_nodes, const sw_edge* edges, size_t n_edges,
+                              uint64_t weight_th, sw_node* nodes_out, sw_edge* edges_out, size_t* n_nodes_out,
+                              size_t* n_edges_out);
+/* filter_kmers (cpp/src/seqwin/filter.cpp:139-201) in place on a device-resident graph: keeps the
+ * nodes whose hash is in used_hashes (any order, duplicates allowed), compacts their k-mers and
+ * rewrites start / stop; edges untouched.  Saves the D2H / H2D round trip of the k-mer array between
+ * build, scoring and filtering. */
+int sw_graph_filter_kmers(sw_graph* g, const uint64_t* used_hashes, size_t n_used);
+
 /* Device properties the host side sizes grids with. */
 int sw_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
 

@@ -129,6 +129,16 @@ def _filter_kmers_native(kmers, nodes, used_hashes):
     return ko, no
 
 
+def filter_edges_and_nodes(nodes, edges, edge_weight_th):
+    """Array part of the reference's `_filter_edges_and_nodes` (src/seqwin/kmers.py:147-162), restated:
+    edges with weight > uintp(th), then the nodes found by searchsorted for the unique endpoints.
+    Pinned against the reference's own function by tests/golden/arrays/filter_*.npz."""
+    th = np.uint64(edge_weight_th)   # kmers.py:151 -- np.uintp(edge_weight_th): truncation
+    kept = edges[edges["weight"] > th]
+    ends = np.unique(np.concatenate([kept["first"], kept["second"]]))
+    return nodes[np.searchsorted(nodes["hash"], ends)], kept
+
+
 def load_reference():
     """The UNMODIFIED reference extension compiled into oracle/_ref (None if not built)."""
     ref_dir = HERE / "_ref"

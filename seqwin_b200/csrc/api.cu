@@ -1006,6 +1006,69 @@ int sw_filter_kmers(const sw_kmer* kmers, size_t n_kmers, const sw_node* nodes, 
     });
 }
 
+namespace {
+// a device-resident graph is about to change: drop any host copy of it
+void invalidate_host_copy(sw_graph* g)
+{
+    if (!g->on_device) fail_runtime("graph is not device resident");
+    host_pool_put(g->h_kmers);
+    host_pool_put(g->h_nodes);
+    host_pool_put(g->h_edges);
+    g->on_host = false;
+}
+void sync_sizes(sw_graph* g)
+{
+    g->n_kmers = g->dev.n_kmers;
+    g->n_nodes = g->dev.n_nodes;
+    g->n_edges = g->dev.n_edges;
+}
+}  // namespace
+
+int sw_graph_filter_edges(sw_graph* g, uint64_t weight_th)
+{
+    return guarded([&] {
+        invalidate_host_copy(g);
+        arena_reset();
+        graph_filter_edges(g->dev, weight_th, g->stream);
+        sync_sizes(g);
+    });
+}
+
+int sw_graph_filter_kmers(sw_graph* g, const uint64_t* used_hashes, size_t n_used)
+{
+    return guarded([&] {
+        invalidate_host_copy(g);
+        arena_reset();
+        graph_filter_kmers(g->dev, used_hashes, n_used, g->stream);
+        sync_sizes(g);
+    });
+}
+
+int sw_filter_edges_and_nodes(const sw_node* nodes, size_t n_nodes, const sw_edge* edges, size_t n_edges,
+                              uint64_t weight_th, sw_node* nodes_out, sw_edge* edges_out, size_t* n_nodes_out,
+                              size_t* n_edges_out)
+{
+    return guarded([&] {
+        init_device_once();
+        cudaStream_t s = lib_stream();
+        arena_reset();
+        DevGraph g;
+        g.nodes.alloc(n_nodes, s);
+        g.edges.alloc(n_edges, s);
+        g.kmers.alloc(0, s);
+        g.n_nodes = n_nodes;
+        g.n_edges = n_edges;
+        if (n_nodes) SW_CUDA(cudaMemcpyAsync(g.nodes.p, nodes, n_nodes * sizeof(sw_node), cudaMemcpyHostToDevice, s));
+        if (n_edges) SW_CUDA(cudaMemcpyAsync(g.edges.p, edges, n_edges * sizeof(sw_edge), cudaMemcpyHostToDevice, s));
+        graph_filter_edges(g, weight_th, s);
+        if (g.n_nodes) SW_CUDA(cudaMemcpyAsync(nodes_out, g.nodes.p, g.n_nodes * sizeof(sw_node), cudaMemcpyDeviceToHost, s));
+        if (g.n_edges) SW_CUDA(cudaMemcpyAsync(edges_out, g.edges.p, g.n_edges * sizeof(sw_edge), cudaMemcpyDeviceToHost, s));
+        SW_CUDA(cudaStreamSynchronize(s));
+        *n_nodes_out = g.n_nodes;
+        *n_edges_out = g.n_edges;
+    });
+}
+
 int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_out, uint32_t* pos_out,
                   uint32_t* record_out, size_t capacity, size_t* n_out)
 {

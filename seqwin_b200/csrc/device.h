@@ -156,6 +156,12 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
                  GraphTimes* times, const std::function<void()>* after_nodes = nullptr,
                  const ScoreArgs* score = nullptr);
 
+// ---- consumers of a device-resident graph (filter.cu), in place on g ---------------------------------
+// edges with weight > weight_th and the nodes that keep an edge (kmers.py:132-162); k-mers untouched
+void graph_filter_edges(DevGraph& g, uint64_t weight_th, cudaStream_t s);
+// nodes whose hash is in used_hashes (host array, any order), their k-mers compacted (filter.cpp:139-201)
+void graph_filter_kmers(DevGraph& g, const uint64_t* used_hashes, size_t n_used, cudaStream_t s);
+
 // ---- multi-GPU merge (dist.cu) -------------------------------------------------------------------
 void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out /* 3*(P+1) */, cudaStream_t s);
 void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,

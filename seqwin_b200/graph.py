@@ -14,7 +14,8 @@ from numpy.typing import NDArray
 from ._core import (EDGE_DTYPE, KMER_DTYPE, NODE_DTYPE, _build_native, _filter_kmers_native,
                     _get_penalty_native)
 
-__all__ = ["KMER_DTYPE", "NODE_DTYPE", "EDGE_DTYPE", "KmerGraph", "_get_penalty", "_filter_kmers"]
+__all__ = ["KMER_DTYPE", "NODE_DTYPE", "EDGE_DTYPE", "KmerGraph", "_get_penalty", "_filter_kmers",
+           "_filter_edges_and_nodes"]
 
 
 class KmerGraph:
@@ -38,3 +39,22 @@ def _get_penalty(kmers: NDArray[np.void], nodes: NDArray[np.void], record_offset
 def _filter_kmers(kmers: NDArray[np.void], nodes: NDArray[np.void], used_hashes):
     """``graph/__init__.py:174-196``: keep the nodes (and their k-mers) whose hash is in ``used_hashes``."""
     return _filter_kmers_native(kmers, nodes, used_hashes)
+
+
+def _filter_edges_and_nodes(nodes: NDArray[np.void], edges: NDArray[np.void], edge_weight_th: float):
+    """Array part of ``kmers.py:132-162``: remove edges with ``weight <= uintp(edge_weight_th)`` and the
+    nodes left without an edge.  Returns ``(nodes, edges)``; the caller builds the networkx graph from
+    them as the reference does (``kmers.py:164-171``).  Runs on the GPU (``sw_filter_edges_and_nodes``)."""
+    import ctypes as C
+
+    from . import _lib
+    if nodes.dtype != NODE_DTYPE or edges.dtype != EDGE_DTYPE:
+        raise TypeError("nodes / edges must have the graph dtypes")
+    nodes = np.ascontiguousarray(nodes)
+    edges = np.ascontiguousarray(edges)
+    nodes_out, edges_out = np.empty_like(nodes), np.empty_like(edges)
+    nn, ne = C.c_size_t(), C.c_size_t()
+    _lib.check(_lib.lib().sw_filter_edges_and_nodes(
+        nodes.ctypes.data, len(nodes), edges.ctypes.data, len(edges), C.c_uint64(int(np.uint64(edge_weight_th))),
+        nodes_out.ctypes.data, edges_out.ctypes.data, C.byref(nn), C.byref(ne)))
+    return nodes_out[:nn.value].copy(), edges_out[:ne.value].copy()

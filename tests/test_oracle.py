@@ -103,3 +103,16 @@ def test_penalty_known_answers():
     nodes = np.array([(10, 0, 2, 0, 0, 0.0)], dtype=N)
     O._get_penalty_native(kmers, nodes, np.array([0, 1, 1, 1, 2], dtype=np.uint32), np.array([True, False, True, False]))
     assert (nodes[0]["n_tar"], nodes[0]["n_neg"]) == (1, 1) and nodes[0]["penalty"] == np.sqrt(0.5)
+
+
+@pytest.mark.parametrize("name", ["fixtures_17_10", "edge_17_10", "edge_21_200", "fixtures_31_50"])
+def test_filter_edges_and_nodes_restatement_matches_reference(name):
+    """oracle.filter_edges_and_nodes vs the reference's own _filter_edges_and_nodes
+    (kmers.py:132-173; vectors written by tests/golden/make_filter_golden.py)."""
+    arrays = GOLDEN_ARRAYS
+    a = np.load(arrays / f"{name}.npz", allow_pickle=False)
+    want = np.load(arrays / f"filter_{name}.npz", allow_pickle=False)
+    for th in (0.0, 0.9, 1.0, 2.0, 3.5, 1e9):
+        tag = str(th).replace(".", "p").replace("+", "")
+        n2, e2 = O.filter_edges_and_nodes(a["nodes_penalty"], a["edges"], th)
+        assert np.array_equal(n2, want[f"nodes_{tag}"]) and np.array_equal(e2, want[f"edges_{tag}"]), (name, th)
