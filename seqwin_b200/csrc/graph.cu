@@ -76,9 +76,10 @@ __device__ __forceinline__ uint32_t round_rank(bool flag, uint32_t* s_warp, uint
 
 // Ordered ranks of kRounds flags per thread (item r of thread t is element r * kNT + t of the
 // block) with ONE barrier: ballots of all rounds first, then every thread sums the (round, warp)
-// counts that precede it.  rank[r] = number of set flags before the item in block order.
-__device__ __forceinline__ void block_ranks(const bool (&flag)[kRounds], uint32_t (&rank)[kRounds],
-                                            uint32_t (*s_cnt)[kNT / 32])
+// counts that precede it.  rank[r] = number of set flags before the item in block order; returns the
+// block's total.
+__device__ __forceinline__ uint32_t block_ranks(const bool (&flag)[kRounds], uint32_t (&rank)[kRounds],
+                                                uint32_t (*s_cnt)[kNT / 32])
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t prefix[kRounds];
@@ -102,6 +103,7 @@ __device__ __forceinline__ void block_ranks(const bool (&flag)[kRounds], uint32_
         rank[r] = running + before + prefix[r];
         running += total;
     }
+    return running;   // set flags in the whole block
 }
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp)
@@ -420,17 +422,24 @@ __global__ void __launch_bounds__(kNT) edge_write_kernel(
     }
 }
 
+// Run-length encode the sorted (pair, assembly) records: one edge per distinct pair, weight = number
+// of distinct assemblies in its run.  Runs inside a block get their weight with one plain store (the
+// difference of two prefix counts held in shared memory); only the run a block ends with -- it may
+// continue in the next block -- and the tail of a run inherited from the previous block use an
+// atomic add on the weight, which the host zeroed.
 __global__ void __launch_bounds__(kNT) edge_final_kernel(
     const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ easm, uint64_t n,
     const unsigned long long* __restrict__ block_off, int rank_bits, const uint64_t* __restrict__ node_hash,
     sw_edge* __restrict__ edges)
 {
     __shared__ uint32_t s_cnt[kRounds][kNT / 32];
+    __shared__ uint32_t s_cnt2[kRounds][kNT / 32];
+    __shared__ uint32_t s_start[kBlockItems + 1];   // fresh assemblies before each run start of the block
     const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
     const unsigned long long off = block_off[blockIdx.x];
     uint64_t key[kRounds];
     bool new_pair[kRounds], new_asm[kRounds];
-    uint32_t rank[kRounds];
+    uint32_t rank[kRounds], arank[kRounds];
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
@@ -442,20 +451,27 @@ __global__ void __launch_bounds__(kNT) edge_final_kernel(
             new_asm[r] = new_pair[r] || easm[j] != easm[j - 1];
         }
     }
-    block_ranks(new_pair, rank, s_cnt);
+    const uint32_t n_runs = block_ranks(new_pair, rank, s_cnt);
+    const uint32_t n_fresh = block_ranks(new_asm, arank, s_cnt2);
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r)
+        if (new_pair[r]) s_start[rank[r]] = arank[r];
+    if (threadIdx.x == 0) s_start[n_runs] = n_fresh;
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
-        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
-        if (j < n) {
-            const unsigned long long e = off + rank[r] + (new_pair[r] ? 1u : 0u) - 1u;
-            if (new_pair[r]) {
-                edges[e].first = node_hash[key[r] >> (64 - rank_bits)];
-                edges[e].second = node_hash[(key[r] >> (64 - 2 * rank_bits)) & ((1ull << rank_bits) - 1)];
-            }
-            // weight was zeroed before the launch; one count per distinct assembly of the run
-            if (new_asm[r]) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), 1ULL);
+        if (new_pair[r]) {
+            const unsigned long long e = off + rank[r];
+            edges[e].first = node_hash[key[r] >> (64 - rank_bits)];
+            edges[e].second = node_hash[(key[r] >> (64 - 2 * rank_bits)) & ((1ull << rank_bits) - 1)];
+            const unsigned long long wgt = s_start[rank[r] + 1] - arank[r];
+            if (rank[r] + 1 == n_runs) atomicAdd(reinterpret_cast<unsigned long long*>(&edges[e].weight), wgt);
+            else edges[e].weight = wgt;
         }
     }
+    // records before the block's first run start continue the previous block's last run
+    if (threadIdx.x == 0 && s_start[0] != 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&edges[off - 1].weight), (unsigned long long)s_start[0]);
 }
 
 // ---- penalty ----------------------------------------------------------------------------------
