@@ -141,3 +141,31 @@ def test_sparse_tie_rule_on_repeats(emul):
             for nt, c1 in ((8, 64), (128, 64)):
                 eh, ep, er, _, _ = emul.sparse(seqs, k, w, nt, c1, cpw)
                 assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (k, w, cpw, nt)
+
+
+def test_sparse_kernel_property_random_parameters(emul):
+    """Random (k, w, candidate density, sequence composition) draws: the sparse phases + hand-over must
+    reproduce the oracle for every draw (seeded, so failures reproduce)."""
+    rng = np.random.default_rng(20261017)
+    alphabets = [b"ACGT", b"ACGT", b"ACGTN", b"AC", b"ACGTacgt", b"AAAAAAAC"]
+    for trial in range(40):
+        k = int(rng.integers(3, 40))
+        w = int(rng.integers(64, 420))
+        nt, c1 = [(8, 64), (16, 32), (4, 48)][trial % 3]
+        if nt * c1 < 4 * w // 3:
+            nt, c1 = 8, 64
+        cpw = float(rng.choice([0.0, 2.0, 6.0, 11.0, 25.0, 1e9]))
+        seqs = []
+        for _ in range(int(rng.integers(1, 5))):
+            alpha = np.frombuffer(alphabets[int(rng.integers(0, len(alphabets)))], dtype=np.uint8)
+            n = int(rng.integers(1, 6000))
+            s = alpha[rng.integers(0, len(alpha), n)].copy()
+            if rng.random() < 0.4 and n > 300:      # a tandem repeat longer than the window
+                unit = s[:int(rng.integers(1, 60))]
+                rep = np.tile(unit, 1 + (w + 80) // len(unit))
+                at = int(rng.integers(0, n - 1))
+                s = np.concatenate([s[:at], rep, s[at:]])
+            seqs.append(s.tobytes())
+        oh, op, orr = _oracle_stream(seqs, k, w)
+        eh, ep, er, _, _ = emul.sparse(seqs, k, w, nt, c1, cpw)
+        assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (trial, k, w, nt, c1, cpw)
