@@ -137,12 +137,19 @@ int sw_dev_sketch(const sw_dev_batch* d, uint32_t k, uint32_t w, uint64_t* h1_ou
 /* Run every later call of this host thread on `stream` (a cudaStream_t, e.g. torch's current
  * stream) instead of the library's own stream; NULL restores the default. */
 int sw_set_stream(void* stream);
-/* sw_dev_build with the shard's global record base: record_idx = rec_base + local record index. */
-int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_graph** out,
-                    sw_stage_times* t);
+/* One rank's shard of a multi-GPU build: sw_dev_build with the shard's global record base
+ * (record_idx = rec_base + local record index).  With is_targets (one byte per assembly of the shard,
+ * any mix of classes; NULL = no scoring) the shard's nodes come with n_tar / n_neg counted; an assembly
+ * lives on one rank, so sw_dist_merge adds the shards' counts and sw_graph_finish_penalty turns the
+ * sums into penalties -- get_penalty (filter.cpp:15-137) without a pass over the merged k-mers. */
+int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, const uint8_t* is_targets,
+                    size_t n_assemblies, sw_graph** out, sw_stage_times* t);
 /* sw_build_from_batch with a record base; to_host = 0 leaves the graph in HBM (copies overlapped). */
 int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t rec_base, int to_host,
-                           sw_graph** out, sw_stage_times* t);
+                           const uint8_t* is_targets, size_t n_assemblies, sw_graph** out, sw_stage_times* t);
+/* penalty = sqrt((1 - n_tar / n_targets)^2 + (n_neg / n_non_targets)^2) for every node of a
+ * device-resident graph whose counts are already in place. */
+int sw_graph_finish_penalty(sw_graph* g, uint64_t n_targets, uint64_t n_non_targets);
 /* Bring a device-resident graph into (pooled, pinned) host memory; sw_graph_export then memcpy's. */
 int sw_graph_fetch(sw_graph* g);
 /* Device pointers of a device-resident graph (valid until sw_graph_free). */

@@ -50,8 +50,9 @@ PROTOTYPES = {
     "sw_graph_penalty": (_I, [_P, _P, _SZ, _P, _SZ, C.POINTER(C.c_float)]),
     "sw_dev_sketch": (_I, [_P, _U32, _U32, _P, _P, _P, _SZ, C.POINTER(_SZ)]),
     "sw_set_stream": (_I, [_P]),
-    "sw_dev_build_ex": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
-    "sw_build_from_batch_ex": (_I, [_P, _U32, _U32, _U32, _I, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_dev_build_ex": (_I, [_P, _U32, _U32, _U32, _P, _SZ, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_build_from_batch_ex": (_I, [_P, _U32, _U32, _U32, _I, _P, _SZ, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_graph_finish_penalty": (_I, [_P, C.c_uint64, C.c_uint64]),
     "sw_graph_fetch": (_I, [_P]),
     "sw_graph_device_ptrs": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sw_graph_split": (_I, [_P, _U32, _P, _P, _P]),

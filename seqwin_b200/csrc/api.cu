@@ -382,28 +382,33 @@ void fire_nodes_ready(sw_graph* g)
 struct ScoreUpload {
     DevBuf<uint8_t> d_t;
     ScoreArgs args{};
-    ScoreUpload(const uint8_t* is_targets, size_t n_assemblies, size_t n_batch_assemblies, cudaStream_t s)
+    // shard: one rank's part of a multi-GPU build -- any mix of classes, counts only
+    ScoreUpload(const uint8_t* is_targets, size_t n_assemblies, size_t n_batch_assemblies, cudaStream_t s,
+                bool shard = false)
     {
         if (n_assemblies != n_batch_assemblies) fail_value("len(is_targets) must equal the number of assemblies");
         size_t n_t = 0;
         for (size_t i = 0; i < n_assemblies; ++i) n_t += is_targets[i] ? 1 : 0;
-        if (!n_t) fail_value("is_targets must contain at least one target assembly");
-        if (n_t == n_assemblies) fail_value("is_targets must contain at least one non-target assembly");
+        if (!shard) {
+            if (!n_t) fail_value("is_targets must contain at least one target assembly");
+            if (n_t == n_assemblies) fail_value("is_targets must contain at least one non-target assembly");
+        }
         d_t.alloc(n_assemblies, s, true);
-        SW_CUDA(cudaMemcpyAsync(d_t.p, is_targets, n_assemblies, cudaMemcpyHostToDevice, s));
-        args = ScoreArgs{d_t.p, 1.0 / (double)n_t, 1.0 / (double)(n_assemblies - n_t)};
+        if (n_assemblies) SW_CUDA(cudaMemcpyAsync(d_t.p, is_targets, n_assemblies, cudaMemcpyHostToDevice, s));
+        args = ScoreArgs{d_t.p, n_t ? 1.0 / (double)n_t : 0.0, n_assemblies > n_t ? 1.0 / (double)(n_assemblies - n_t) : 0.0,
+                         shard};
     }
 };
 
 sw_graph* dev_build(const sw_dev_batch& d, uint32_t k, uint32_t w, sw_stage_times* t, uint32_t rec_base = 0,
-                    const uint8_t* is_targets = nullptr, size_t n_assemblies = 0)
+                    const uint8_t* is_targets = nullptr, size_t n_assemblies = 0, bool shard = false)
 {
     init_device_once();
     check_kw(k, w);
     cudaStream_t s = d.stream;
     arena_reset();
     std::unique_ptr<ScoreUpload> score;
-    if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, d.meta.record_offsets.size() - 1, s);
+    if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, d.meta.record_offsets.size() - 1, s, shard);
     auto g = std::make_unique<sw_graph>();
     g->stream = s;
     g->record_offsets = d.meta.record_offsets;
@@ -512,7 +517,7 @@ float penalty_on_device(DevGraph& dg, const std::vector<uint32_t>& offsets, cons
 //   copy stream:    bases slice 0 | slice 1 | ... | slice C-1            kmers+nodes D2H
 //   compute stream: tables, plan  | sketch(slice 0) | sketch(slice 1) ... sort, nodes | edges | edges D2H
 sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_times* t, bool to_host, uint32_t rec_base = 0,
-                          const uint8_t* is_targets = nullptr, size_t n_assemblies = 0)
+                          const uint8_t* is_targets = nullptr, size_t n_assemblies = 0, bool shard = false)
 {
     init_device_once();
     check_kw(k, w);
@@ -582,7 +587,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     bool d2h_started = false;
     const float penalty_ms = 0;   // scoring is part of the node stage
     std::unique_ptr<ScoreUpload> score;
-    if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, b.record_offsets.size() - 1, s);
+    if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, b.record_offsets.size() - 1, s, shard);
     const std::function<void()> after_nodes = [&] {
         if (to_host) {
             // kmers + nodes are final (scored in the node stage when the classes were given)
@@ -759,10 +764,25 @@ int sw_set_stream(void* stream)
     return SW_OK;
 }
 
-int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_graph** out,
-                    sw_stage_times* t)
+int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, const uint8_t* is_targets,
+                    size_t n_assemblies, sw_graph** out, sw_stage_times* t)
 {
-    return guarded([&] { *out = dev_build(*d, k, w, t, rec_base); });
+    return guarded([&] { *out = dev_build(*d, k, w, t, rec_base, is_targets, n_assemblies, /*shard=*/true); });
+}
+
+int sw_graph_finish_penalty(sw_graph* g, uint64_t n_targets, uint64_t n_non_targets)
+{
+    return guarded([&] {
+        if (!g->on_device) fail_runtime("graph is not device resident");
+        if (!n_targets) fail_value("is_targets must contain at least one target assembly");
+        if (!n_non_targets) fail_value("is_targets must contain at least one non-target assembly");
+        host_pool_put(g->h_kmers);
+        host_pool_put(g->h_nodes);
+        host_pool_put(g->h_edges);
+        g->on_host = false;
+        finish_penalty(g->dev.nodes.p, g->dev.n_nodes, 1.0 / (double)n_targets, 1.0 / (double)n_non_targets, g->stream);
+        SW_CUDA(cudaStreamSynchronize(g->stream));
+    });
 }
 
 int sw_graph_device_ptrs(sw_graph* g, void** kmers, void** nodes, void** edges)
@@ -824,10 +844,12 @@ int sw_build_from_batch(const sw_batch* b, uint32_t k, uint32_t w, sw_graph** ou
     return guarded([&] { *out = build_pipelined(*b, k, w, t, /*to_host=*/true); });
 }
 
-int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t rec_base, int to_host, sw_graph** out,
-                           sw_stage_times* t)
+int sw_build_from_batch_ex(const sw_batch* b, uint32_t k, uint32_t w, uint32_t rec_base, int to_host,
+                           const uint8_t* is_targets, size_t n_assemblies, sw_graph** out, sw_stage_times* t)
 {
-    return guarded([&] { *out = build_pipelined(*b, k, w, t, to_host != 0, rec_base); });
+    return guarded([&] {
+        *out = build_pipelined(*b, k, w, t, to_host != 0, rec_base, is_targets, n_assemblies, /*shard=*/true);
+    });
 }
 
 int sw_build_from_batch_scored(const sw_batch* b, uint32_t k, uint32_t w, const uint8_t* is_targets, size_t n_assemblies,

@@ -151,7 +151,10 @@ struct GraphTimes {
 struct ScoreArgs {
     const uint8_t* d_is_target;   // [n_assemblies], indexed by the values of d_rec_asm
     double inv_t, inv_n;          // 1 / #targets, 1 / #non-targets
+    bool counts_only = false;     // a shard of a multi-GPU build: n_tar / n_neg only, the penalty follows the merge
 };
+// penalty of every node from its n_tar / n_neg (filter.cpp:132-134)
+void finish_penalty(sw_node* d_nodes, uint64_t n_nodes, double inv_t, double inv_n, cudaStream_t s);
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                  GraphTimes* times, const std::function<void()>* after_nodes = nullptr,
                  const ScoreArgs* score = nullptr);

@@ -170,11 +170,12 @@ __global__ void node_merge_kernel(const KeyIdx* __restrict__ sorted, const sw_no
                 sw_node* o = out_nodes + rank;
                 o->hash = nd.hash;
                 o->start = off;
-                o->n_tar = 0;
-                o->n_neg = 0;
-                o->penalty = 0.0;
                 if (rank > 0) out_nodes[rank - 1].stop = off;
             }
+            // an assembly lives on one rank, so the shards' distinct-assembly counts add up (the host
+            // zeroed the merged nodes; shards that were not scored carry zeros)
+            const unsigned long long c = (unsigned long long)nd.n_tar | ((unsigned long long)nd.n_neg << 32);
+            if (c) atomicAdd(reinterpret_cast<unsigned long long*>(&out_nodes[rank].n_tar), c);
             if (j == n - 1) out_nodes[rank].stop = total_packed & mask40;
         }
     }
@@ -312,6 +313,7 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         const unsigned long long total = *total_p;
         out.n_nodes = total >> 40;
         out.nodes.alloc(out.n_nodes, s);
+        SW_CUDA(cudaMemsetAsync(out.nodes.p, 0, out.n_nodes * sizeof(sw_node), s));
         const uint32_t grid = (uint32_t)std::min<uint64_t>((Nn + 31) / 32, 148 * 32);
         node_merge_kernel<<<grid, 256, 0, s>>>(sorted, recv_nodes, abs_start.p, packed.p, Nn, total, recv_kmers,
                                                out.kmers.p, out.nodes.p);

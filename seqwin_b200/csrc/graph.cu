@@ -599,9 +599,10 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         SW_CUDA(cudaMemsetAsync(g.nodes.p, 0, n_nodes * sizeof(sw_node), s));
         node_write_kernel<true><<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
                                                    node_hash.p, rank_of_stream.p, d_rec_asm, rec_base, score->d_is_target);
-        penalty_finish_kernel<<<(uint32_t)((n_nodes + 255) / 256), 256, 0, s>>>(g.nodes.p, n_nodes, score->inv_t,
-                                                                                score->inv_n);
-        ++tm.launches;
+        if (!score->counts_only) {
+            finish_penalty(g.nodes.p, n_nodes, score->inv_t, score->inv_n, s);
+            ++tm.launches;
+        }
     } else {
         node_write_kernel<false><<<nb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, st.vals.p, M, counts.p, g.kmers.p, g.nodes.p,
                                                     node_hash.p, rank_of_stream.p, nullptr, 0u, nullptr);
@@ -661,6 +662,13 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     }
     tm.edges_ms = timer.stop();
     if (times) *times = tm;
+}
+
+void finish_penalty(sw_node* d_nodes, uint64_t n_nodes, double inv_t, double inv_n, cudaStream_t s)
+{
+    if (n_nodes == 0) return;
+    penalty_finish_kernel<<<(uint32_t)((n_nodes + 255) / 256), 256, 0, s>>>(d_nodes, n_nodes, inv_t, inv_n);
+    SW_CUDA(cudaGetLastError());
 }
 
 uint32_t run_penalty(const sw_kmer* d_kmers, uint64_t n_kmers, sw_node* d_nodes, uint64_t n_nodes,

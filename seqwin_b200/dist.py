@@ -169,10 +169,11 @@ class CudaStages:
         self.merge_ms = 0.0
 
     def local_build(self, dev_batch, k: int, w: int, rec_base: int, world: int, host_batch=None,
-                    on_nodes=None) -> LocalGraph:
+                    on_nodes=None, is_targets=None) -> LocalGraph:
         """Single-GPU kernels on this rank's shard.  on_nodes(nodes, kmers, node_split, kmer_split), if
         given, is called from inside the build as soon as nodes + k-mers are final on the device (the
-        edge stage follows); its return value lands in LocalGraph.early."""
+        edge stage follows); its return value lands in LocalGraph.early.  is_targets (classes of this
+        shard's assemblies) makes the shard's nodes carry their n_tar / n_neg counts."""
         L, lb = self.L, self._lib
         g = C.c_void_p()
         self.times = lb.StageTimes()
@@ -198,10 +199,13 @@ class CudaStages:
         if on_nodes is not None:
             lb.check(L.sw_set_nodes_ready(cb, None))
         try:
+            t_ptr = is_targets.ctypes.data if is_targets is not None else None
+            t_len = len(is_targets) if is_targets is not None else 0
             if host_batch is not None:   # end-to-end: the H2D copy is sliced and overlapped with the sketch
-                lb.check(L.sw_build_from_batch_ex(host_batch, k, w, rec_base, 0, C.byref(g), C.byref(self.times)))
+                lb.check(L.sw_build_from_batch_ex(host_batch, k, w, rec_base, 0, t_ptr, t_len, C.byref(g),
+                                                  C.byref(self.times)))
             else:
-                lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, C.byref(g), C.byref(self.times)))
+                lb.check(L.sw_dev_build_ex(dev_batch, k, w, rec_base, t_ptr, t_len, C.byref(g), C.byref(self.times)))
         finally:
             if on_nodes is not None:
                 L.sw_set_nodes_ready(lb.NODES_READY_FN(0), None)
@@ -235,8 +239,11 @@ class CudaStages:
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
-               host_batch=None, overlap: bool = True):
-    """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle."""
+               host_batch=None, overlap: bool = True, is_targets=None, class_totals=None):
+    """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle.
+    With is_targets (bool array, the classes of THIS rank's assemblies) the graph comes back scored:
+    every shard counts its own assemblies, the merge adds the counts, and the penalty is finished with
+    class_totals = (targets, non-targets) over all ranks (all-reduced here when not given)."""
     world = dist.get_world_size(group)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
@@ -250,12 +257,22 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
 
         def on_nodes(nodes, kmers, node_split, kmer_split):
             return exchange_nodes(nodes, kmers, node_split, kmer_split, group, async_op=nccl)
-    local = stages.local_build(dev_batch, k, w, rec_base, world, host_batch=host_batch, on_nodes=on_nodes)
+    if is_targets is not None:
+        is_targets = np.ascontiguousarray(is_targets, dtype=np.bool_)
+        if class_totals is None:
+            dev_t = stages.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            tot = torch.tensor([int(is_targets.sum()), int(len(is_targets) - is_targets.sum())], dtype=torch.int64, device=dev_t)
+            dist.all_reduce(tot, group=group)
+            class_totals = (int(tot[0]), int(tot[1]))
+    local = stages.local_build(dev_batch, k, w, rec_base, world, host_batch=host_batch, on_nodes=on_nodes,
+                               is_targets=is_targets)
     ev[1].record()
     try:
         g = exchange_and_merge(stages, local, group, early=local.early)
     finally:
         stages.free_local(local)
+    if is_targets is not None:
+        stages._lib.check(stages.L.sw_graph_finish_penalty(g, C.c_uint64(class_totals[0]), C.c_uint64(class_totals[1])))
     ev[2].record()
     stages.phase_events = ev
     return g
@@ -305,28 +322,20 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     _lib.check(L.sw_dev_upload(batch, C.byref(dev)))
 
     rec_base, _ = record_base(n_records, device)   # shard bookkeeping is input metadata, not per-step work
-    # global record offsets / classes for the scoring of every rank's hash range (input metadata too)
+    # classes of the assemblies (input metadata): this rank's slice and the two class sizes
     n_asm_local = spec.n_genomes // world
-    local_off = np.empty(n_asm_local + 1, dtype=np.int64)
-    _lib.check(L.sw_batch_record_offsets(batch, local_off.ctypes.data, n_asm_local + 1))
-    gathered = [torch.empty(n_asm_local + 1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(gathered, torch.from_numpy(local_off).to(device))
-    glob, base = [0], 0
-    for t in gathered:
-        o = t.cpu().numpy()
-        glob.extend((base + o[1:]).tolist())
-        base += int(o[-1])
-    global_off = np.asarray(glob, dtype=np.uint32)
     is_t = np.ascontiguousarray(np.arange(spec.n_genomes) < spec.n_targets, dtype=np.bool_)
-    pen_ms = C.c_float()
 
     import os
     overlap = os.environ.get("SEQWIN_DIST_OVERLAP", "1") != "0"   # A/B switch for profiles/
 
+    is_t_local = np.ascontiguousarray(is_t[rank * n_asm_local:(rank + 1) * n_asm_local])
+    totals = (int(is_t.sum()), int(len(is_t) - is_t.sum()))   # class sizes are input metadata too
+
     def step():
-        g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, overlap=overlap)
-        _lib.check(L.sw_graph_penalty(g, global_off.ctypes.data, len(global_off), is_t.ctypes.data, len(is_t),
-                                      C.byref(pen_ms)))
+        # build + scoring: every shard counts its assemblies, the merge adds, the penalty is finished last
+        g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, overlap=overlap, is_targets=is_t_local,
+                       class_totals=totals)
         sizes = [L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES)]
         L.sw_graph_free(g)
         return sizes
@@ -367,9 +376,8 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch, overlap=overlap)
-        _lib.check(L.sw_graph_penalty(g, global_off.ctypes.data, len(global_off), is_t.ctypes.data, len(is_t),
-                                      C.byref(pen_ms)))
+        g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch, overlap=overlap,
+                       is_targets=is_t_local, class_totals=totals)
         _lib.check(L.sw_graph_fetch(g))     # this rank's hash range -> pinned host memory
         L.sw_graph_free(g)
         torch.cuda.synchronize()

@@ -19,7 +19,7 @@ from tests.helpers import assert_graph_equal, check_graph_invariants
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True):
+def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is_targets=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev_index = rank if use_nccl else 0
@@ -40,7 +40,8 @@ def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True):
         b, d = C.c_void_p(), C.c_void_p()
         _lib.check(L.sw_batch_from_fasta(arr, len(mine), 2, C.byref(b)))
         _lib.check(L.sw_dev_upload(b, C.byref(d)))
-        g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap)
+        mine_t = None if is_targets is None else np.asarray(is_targets[rank * per:(rank + 1) * per], dtype=np.bool_)
+        g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t)
         parts = swd.export_graph(L, g)
         L.sw_graph_free(g)
         L.sw_dev_batch_free(d)
@@ -100,3 +101,26 @@ def test_more_ranks_than_assemblies(synth_sets, tmp_path):
     got = np.load(out)
     want = O._build_native(paths, *kw)
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, "3 ranks, 2 assemblies")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_scored_build(synth_sets, tmp_path, world):
+    """Scoring across ranks: every shard counts its own assemblies (targets first, so some shards hold
+    one class only), the merge adds the counts, the penalty is finished with the global class sizes.
+    Must equal build + get_penalty of the oracle on all assemblies."""
+    from oracle import oracle as O
+    kw = (21, 200)
+    use_nccl = torch.cuda.device_count() >= world
+    paths, is_t = synth_sets["synth_medium"]
+    paths = [str(p) for p in paths]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "merged.npz"
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, True, list(map(bool, is_t))),
+             nprocs=world, join=True)
+    got = np.load(out)
+    kmers, nodes, edges, offsets, _ = O._build_native(paths, *kw)
+    O._get_penalty_native(kmers, nodes, offsets, np.asarray(is_t, dtype=np.bool_))
+    assert np.array_equal(got["kmers"], kmers) and np.array_equal(got["edges"], edges)
+    assert np.array_equal(got["nodes"], nodes), "scored nodes differ"
