@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 #include "device.h"
@@ -889,8 +890,10 @@ int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, u
         check_kw(k, w);
         init_device_once();
         std::unique_ptr<sw_batch> b(batch_from_fasta(paths, n_paths, n_host_threads));
-        // the graph stays in HBM; sw_graph_export copies it straight into the caller's arrays
-        *out = build_pipelined(*b, k, w, nullptr, /*to_host=*/false);
+        // the arrays land in pinned host memory while the edge stage still runs; sw_graph_export then
+        // copies them into the caller's (numpy) arrays with several threads, because first-touch page
+        // faults of a fresh destination, not bandwidth, bound a single-threaded copy
+        *out = build_pipelined(*b, k, w, nullptr, /*to_host=*/true);
     });
 }
 
@@ -906,6 +909,27 @@ size_t sw_graph_size(const sw_graph* g, int which)
     }
 }
 
+namespace {
+// memcpy into memory that has probably never been touched (a fresh numpy array): split across threads
+void parallel_memcpy(void* dst, const void* src, size_t bytes)
+{
+    constexpr size_t kChunk = (size_t)4 << 20;
+    const size_t n_thr = std::min<size_t>({(size_t)8, std::max<size_t>(1, std::thread::hardware_concurrency()), bytes / kChunk});
+    if (n_thr <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / n_thr) + 4095) & ~(size_t)4095;
+    for (size_t t = 0; t < n_thr; ++t) {
+        const size_t lo = t * per, hi = std::min(bytes, lo + per);
+        if (lo >= hi) break;
+        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+    }
+    for (auto& t : th) t.join();
+}
+}  // namespace
+
 int sw_graph_export(sw_graph* g, void* kmers, void* nodes, void* edges, uint32_t* record_offsets)
 {
     return guarded([&] {
@@ -916,7 +940,7 @@ int sw_graph_export(sw_graph* g, void* kmers, void* nodes, void* edges, uint32_t
             {edges, g->h_edges.p, g->dev.edges.p, g->n_edges * sizeof(sw_edge)}};
         for (const Part& pt : parts) {
             if (!pt.dst || !pt.bytes) continue;
-            if (g->on_host) memcpy(pt.dst, pt.host, pt.bytes);
+            if (g->on_host) parallel_memcpy(pt.dst, pt.host, pt.bytes);
             else  // straight from HBM into the caller's (numpy) buffer, no intermediate copy
                 SW_CUDA(cudaMemcpyAsync(pt.dst, pt.dev, pt.bytes, cudaMemcpyDeviceToHost, g->stream));
         }
