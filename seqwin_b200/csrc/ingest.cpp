@@ -76,6 +76,27 @@ __attribute__((target("ssse3"))) inline bool pack16_ssse3(const unsigned char* p
     return true;
 }
 const bool kHaveSsse3 = __builtin_cpu_supports("ssse3");
+
+// 32 ASCII bases -> two packed words (as one u64), or false if any byte is not A/C/G/T/U.
+__attribute__((target("avx2"))) inline bool pack32_avx2(const unsigned char* p, uint64_t* out)
+{
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+    const __m256i lc = _mm256_or_si256(v, _mm256_set1_epi8(0x20));
+    __m256i ok = _mm256_or_si256(_mm256_cmpeq_epi8(lc, _mm256_set1_epi8('a')), _mm256_cmpeq_epi8(lc, _mm256_set1_epi8('c')));
+    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(lc, _mm256_set1_epi8('g')));
+    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(lc, _mm256_set1_epi8('t')));
+    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(lc, _mm256_set1_epi8('u')));
+    if ((uint32_t)_mm256_movemask_epi8(ok) != 0xFFFFFFFFu) return false;
+    const __m256i code = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2)), _mm256_set1_epi8(3));
+    const __m256i t = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401));   // 2 bases per 16-bit lane
+    const __m256i u = _mm256_madd_epi16(t, _mm256_set1_epi32(0x00100001));     // 4 bases per 32-bit lane
+    const __m256i sel = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                         0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i g = _mm256_shuffle_epi8(u, sel);                             // 16 bases in the low word of each half
+    *out = (uint64_t)(uint32_t)_mm256_extract_epi32(g, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(g, 4) << 32);
+    return true;
+}
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
 #endif
 
 // Streaming packer for one record.
@@ -108,6 +129,15 @@ struct RecordPacker {
         acc >>= 32;
         cnt += 16;
     }
+    inline void push_word32(uint64_t w32)  // 32 hashable bases at once
+    {
+        const uint32_t s = 2 * fill;
+        const uint64_t x = acc | (w32 << s);
+        a.words.push_back((uint32_t)x);
+        a.words.push_back((uint32_t)(x >> 32));
+        acc = s ? (w32 >> (64 - s)) : 0;
+        cnt += 32;
+    }
     inline void push_invalid()
     {
         if (n_inv && (uint64_t)a.inv_start.back() + a.inv_len.back() == cnt) ++a.inv_len.back();
@@ -126,6 +156,13 @@ struct RecordPacker {
     {
         size_t i = 0;
 #if defined(__x86_64__)
+        if (kHaveAvx2) {
+            for (; i + 32 <= n; i += 32) {
+                uint64_t w32;
+                if (pack32_avx2(p + i, &w32)) push_word32(w32);
+                else append_bytes(p + i, 32);
+            }
+        }
         if (kHaveSsse3) {
             for (; i + 16 <= n; i += 16) {
                 uint32_t w16;
