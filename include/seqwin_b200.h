@@ -170,10 +170,14 @@ typedef void (*sw_nodes_ready_fn)(void* user, sw_graph* g);
 int sw_set_nodes_ready(sw_nodes_ready_fn fn, void* user);
 /* Merge the slices a hash-range owner received from n_src ranks (device pointers, concatenated in
  * rank order; kmer_base[i] = first k-mer index of rank i's slice in rank i's own array). Mirrors
- * merge_thread_graphs (cpp/src/seqwin/build_internals.cpp:295-392). */
+ * merge_thread_graphs (cpp/src/seqwin/build_internals.cpp:295-392); n_tar / n_neg of equal nodes add up.
+ * recv_edges == NULL merges nodes + k-mers only and leaves the edges to sw_dist_merge_edges, so that
+ * the edge slices can still be in flight while the nodes are merged. */
 int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const void* recv_kmers,
                   const uint64_t* kmer_counts, const uint64_t* kmer_base, const void* recv_edges,
                   const uint64_t* edge_counts, uint32_t n_src, sw_graph** out, uint32_t* launches);
+int sw_dist_merge_edges(sw_graph* g, const void* recv_edges, const uint64_t* edge_counts, uint32_t n_src,
+                        uint32_t* launches);
 
 /* ---- first consumers of the graph, on the device-resident arrays ------------ */
 /* Edge-weight filter + isolated-node removal, the array part of _filter_edges_and_nodes

@@ -828,15 +828,35 @@ int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const voi
         arena_reset();
         auto g = std::make_unique<sw_graph>();
         g->stream = s;
-        dist_merge(static_cast<const sw_node*>(recv_nodes), node_counts, static_cast<const sw_kmer*>(recv_kmers),
-                   kmer_counts, kmer_base, static_cast<const sw_edge*>(recv_edges), edge_counts, n_src, s, g->dev,
-                   launches);
+        uint32_t nl = 0;
+        dist_merge_nodes(static_cast<const sw_node*>(recv_nodes), node_counts, static_cast<const sw_kmer*>(recv_kmers),
+                         kmer_counts, kmer_base, n_src, s, g->dev, &nl);
+        if (recv_edges) {
+            arena_reset();
+            dist_merge_edges(static_cast<const sw_edge*>(recv_edges), edge_counts, n_src, s, g->dev, &nl);
+        } else {   // no edges, or sw_dist_merge_edges follows
+            g->dev.edges.alloc(0, s);
+            g->dev.n_edges = 0;
+        }
+        if (launches) *launches = nl;
         g->on_device = true;
         g->n_kmers = g->dev.n_kmers;
         g->n_nodes = g->dev.n_nodes;
         g->n_edges = g->dev.n_edges;
         g->record_offsets.assign(1, 0);
         *out = g.release();
+    });
+}
+
+int sw_dist_merge_edges(sw_graph* g, const void* recv_edges, const uint64_t* edge_counts, uint32_t n_src, uint32_t* launches)
+{
+    return guarded([&] {
+        if (!g->on_device) fail_runtime("graph is not device resident");
+        arena_reset();
+        uint32_t nl = 0;
+        dist_merge_edges(static_cast<const sw_edge*>(recv_edges), edge_counts, n_src, g->stream, g->dev, &nl);
+        g->n_edges = g->dev.n_edges;
+        if (launches) *launches = nl;
     });
 }
 

@@ -167,9 +167,12 @@ void graph_filter_kmers(DevGraph& g, const uint64_t* used_hashes, size_t n_used,
 
 // ---- multi-GPU merge (dist.cu) -------------------------------------------------------------------
 void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out /* 3*(P+1) */, cudaStream_t s);
-void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
-                const uint64_t* kmer_counts, const uint64_t* kmer_base, const sw_edge* recv_edges,
-                const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out, uint32_t* launches);
+// the two halves of the owner-side merge: nodes + k-mers (their slices arrive first), then edges
+void dist_merge_nodes(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
+                      const uint64_t* kmer_counts, const uint64_t* kmer_base, uint32_t n_src, cudaStream_t s, DevGraph& out,
+                      uint32_t* launches);
+void dist_merge_edges(const sw_edge* recv_edges, const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out,
+                      uint32_t* launches);
 
 // ---- penalty ----------------------------------------------------------------------------------
 // Fills n_tar / n_neg / penalty of device-resident nodes; returns an error bit mask

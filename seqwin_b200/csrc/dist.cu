@@ -262,11 +262,11 @@ void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out, cu
     std::copy(h, h + d.n, host_out);
 }
 
-void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
-                const uint64_t* kmer_counts, const uint64_t* kmer_base, const sw_edge* recv_edges,
-                const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out, uint32_t* launches)
+void dist_merge_nodes(const sw_node* recv_nodes, const uint64_t* node_counts, const sw_kmer* recv_kmers,
+                      const uint64_t* kmer_counts, const uint64_t* kmer_base, uint32_t n_src, cudaStream_t s, DevGraph& out,
+                      uint32_t* launches)
 {
-    uint64_t Nn = 0, Nk = 0, Ne = 0;
+    uint64_t Nn = 0, Nk = 0;
     std::vector<unsigned long long> seg(3 * (size_t)n_src + 1);
     for (uint32_t i = 0; i < n_src; ++i) {
         seg[i] = Nn;
@@ -274,24 +274,21 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         seg[2 * n_src + 1 + i] = kmer_base[i];
         Nn += node_counts[i];
         Nk += kmer_counts[i];
-        Ne += edge_counts[i];
     }
     seg[n_src] = Nn;
     if (Nk >= (1ULL << 40)) fail_runtime("more than 2^40 k-mers in one hash range");
     uint32_t nl = 0;
     const bool prof = getenv("SEQWIN_DIST_PROFILE") != nullptr;
-    cudaEvent_t pe[6];
+    cudaEvent_t pe[3];
     if (prof) for (auto& e : pe) cudaEventCreate(&e);
     auto mark = [&](int i) { if (prof) cudaEventRecord(pe[i], s); };
     mark(0);
     out.n_kmers = Nk;
     out.n_nodes = 0;
-    out.n_edges = 0;
     out.kmers.alloc(Nk, s);
-
-    // ---- nodes + kmers -------------------------------------------------------------------------
     if (Nn == 0) {
         out.nodes.alloc(0, s);
+        mark(1);
     } else {
         DevBuf<unsigned long long> d_seg(seg.size(), s, true);
         SW_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
@@ -320,18 +317,41 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         SW_CUDA(cudaGetLastError());
         nl += 2;
     }
-
     mark(2);
-    // ---- edges ---------------------------------------------------------------------------------
+    SW_CUDA(cudaStreamSynchronize(s));
+    if (prof) {
+        float a, b;
+        cudaEventElapsedTime(&a, pe[0], pe[1]);
+        cudaEventElapsedTime(&b, pe[1], pe[2]);
+        fprintf(stderr, "[dist_merge] Nn=%llu Nk=%llu  node_sort %.2f  node_merge %.2f ms\n", (unsigned long long)Nn,
+                (unsigned long long)Nk, a, b);
+        for (auto& e : pe) cudaEventDestroy(e);
+    }
+    if (launches) *launches += nl;
+}
+
+void dist_merge_edges(const sw_edge* recv_edges, const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out,
+                      uint32_t* launches)
+{
+    uint64_t Ne = 0;
+    for (uint32_t i = 0; i < n_src; ++i) Ne += edge_counts[i];
+    uint32_t nl = 0;
+    const bool prof = getenv("SEQWIN_DIST_PROFILE") != nullptr;
+    cudaEvent_t pe[3];
+    if (prof) for (auto& e : pe) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (prof) cudaEventRecord(pe[i], s); };
+    mark(0);
+    out.n_edges = 0;
     if (Ne == 0) {
         out.edges.alloc(0, s);
+        mark(1);
     } else {
         // every rank's slice is sorted by (first, second): merge the runs, then sum equal pairs
         std::vector<unsigned long long> edge_seg(n_src + 1, 0);
         for (uint32_t i = 0; i < n_src; ++i) edge_seg[i + 1] = edge_seg[i] + edge_counts[i];
         DevBuf<sw_edge> e0(Ne, s, true), e1(Ne, s, true);
         const sw_edge* sorted = merge_runs<sw_edge, LessEdge>(recv_edges, edge_seg, e0.p, e1.p, s, &nl);
-        mark(3);
+        mark(1);
         DevBuf<unsigned long long> flags(Ne + 1, s, true);
         edge_flag_kernel<<<grid_for(Ne), kNT, 0, s>>>(sorted, Ne, flags.p);
         nl += exclusive_scan_u64(flags.p, Ne, flags.p + Ne, s);
@@ -346,19 +366,16 @@ void dist_merge(const sw_node* recv_nodes, const uint64_t* node_counts, const sw
         SW_CUDA(cudaGetLastError());
         nl += 2;
     }
-    mark(4);
+    mark(2);
     SW_CUDA(cudaStreamSynchronize(s));
     if (prof) {
-        float a, b, c, d;
+        float a, b;
         cudaEventElapsedTime(&a, pe[0], pe[1]);
         cudaEventElapsedTime(&b, pe[1], pe[2]);
-        cudaEventElapsedTime(&c, pe[2], pe[3]);
-        cudaEventElapsedTime(&d, pe[3], pe[4]);
-        fprintf(stderr, "[dist_merge] Nn=%llu Nk=%llu Ne=%llu  node_sort %.2f  node_merge %.2f  edge_sort %.2f  edge_merge %.2f ms\n",
-                (unsigned long long)Nn, (unsigned long long)Nk, (unsigned long long)Ne, a, b, c, d);
+        fprintf(stderr, "[dist_merge] Ne=%llu  edge_sort %.2f  edge_merge %.2f ms\n", (unsigned long long)Ne, a, b);
         for (auto& e : pe) cudaEventDestroy(e);
     }
-    if (launches) *launches = nl;
+    if (launches) *launches += nl;
 }
 
 }  // namespace sw

@@ -116,17 +116,27 @@ def exchange_nodes(nodes, kmers, node_split, kmer_split, group=None, async_op=Fa
 
 
 def exchange_and_merge(stages, local: LocalGraph, group=None, early=None):
-    """Send every hash range to its owner and merge what arrives. Returns stages.merge(...).
-    `early` is the result of an exchange_nodes() already started while the edge stage was running."""
+    """Send every hash range to its owner and merge what arrives; returns the merged graph.
+    `early` is the result of an exchange_nodes() already started while the edge stage was running.
+    Stages that can merge in two halves (CudaStages) merge nodes + k-mers while the edge slices are
+    still on the wire."""
     if early is None:
         early = exchange_nodes(local.nodes, local.kmers, local.node_split, local.kmer_split, group)
     (recv_nodes, recv_kmers, recv_base), counts, works = early
-    (recv_edges,), ecounts, _ = all_to_all_slices([local.edges], [local.edge_split], [EDGE_BYTES], group)
+    two_halves = hasattr(stages, "merge_nodes") and dist.get_backend(group) == "nccl"
+    (recv_edges,), ecounts, eworks = all_to_all_slices([local.edges], [local.edge_split], [EDGE_BYTES], group,
+                                                       async_op=two_halves)
     for wk in works:
         wk.wait()
     kmer_base = recv_base.view(torch.int64).cpu().numpy().astype(np.uint64)
-    return stages.merge(recv_nodes, np.ascontiguousarray(counts[0]), recv_kmers, np.ascontiguousarray(counts[1]),
-                        kmer_base, recv_edges, np.ascontiguousarray(ecounts[0]))
+    node_args = (recv_nodes, np.ascontiguousarray(counts[0]), recv_kmers, np.ascontiguousarray(counts[1]), kmer_base)
+    if not two_halves:
+        return stages.merge(*node_args, recv_edges, np.ascontiguousarray(ecounts[0]))
+    g = stages.merge_nodes(*node_args)
+    for wk in eworks:
+        wk.wait()
+    stages.merge_edges(g, recv_edges, np.ascontiguousarray(ecounts[0]))
+    return g
 
 
 def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
@@ -223,19 +233,33 @@ class CudaStages:
             local.handle = None
 
     def merge(self, nodes, node_counts, kmers, kmer_counts, kmer_base, edges, edge_counts):
+        g = self.merge_nodes(nodes, node_counts, kmers, kmer_counts, kmer_base)
+        self.merge_edges(g, edges, edge_counts)
+        return g
+
+    def merge_nodes(self, nodes, node_counts, kmers, kmer_counts, kmer_base):
         L, lb = self.L, self._lib
-        torch.cuda.current_stream(self.device).synchronize()   # NCCL results visible to the library stream
+        torch.cuda.current_stream(self.device).synchronize()   # received slices visible to the library stream
         g = C.c_void_p()
         n_launch = C.c_uint32()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0.record()
         self._merge_events = (m0, m1)
         lb.check(L.sw_dist_merge(C.c_void_p(nodes.data_ptr()), node_counts.ctypes.data, C.c_void_p(kmers.data_ptr()),
-                                 kmer_counts.ctypes.data, kmer_base.ctypes.data, C.c_void_p(edges.data_ptr()),
-                                 edge_counts.ctypes.data, len(node_counts), C.byref(g), C.byref(n_launch)))
+                                 kmer_counts.ctypes.data, kmer_base.ctypes.data, None, None, len(node_counts),
+                                 C.byref(g), C.byref(n_launch)))
         self.merge_launches = n_launch.value
         m1.record()
         return g
+
+    def merge_edges(self, g, edges, edge_counts):
+        L, lb = self.L, self._lib
+        torch.cuda.current_stream(self.device).synchronize()
+        n_launch = C.c_uint32()
+        lb.check(L.sw_dist_merge_edges(g, C.c_void_p(edges.data_ptr()), edge_counts.ctypes.data, len(edge_counts),
+                                       C.byref(n_launch)))
+        self.merge_launches += n_launch.value
+        self._merge_events[1].record()
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
