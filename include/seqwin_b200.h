@@ -196,6 +196,12 @@ int sw_filter_edges_and_nodes(const sw_node* nodes, size_t n_nodes, const sw_edg
  * build, scoring and filtering. */
 int sw_graph_filter_kmers(sw_graph* g, const uint64_t* used_hashes, size_t n_used);
 
+/* the reductions behind the automatic penalty threshold (src/seqwin/kmers.py:424-429,
+ * the branch without Mash) on a scored device-resident graph: sums = {sum n_tar, sum n_tar^2,
+ * sum n_tar * n_neg} over the nodes, exact integers.  With T targets and N non-targets:
+ * e_absence_tar = 1 - sums[1] / (T * sums[0]), e_presence_neg = sums[2] / (N * sums[0]). */
+int sw_graph_count_sums(sw_graph* g, uint64_t sums[3]);
+
 /* Device properties the host side sizes grids with. */
 int sw_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
 

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "sw_filter_edges_and_nodes": (_I, [_P, _SZ, _P, _SZ, C.c_uint64, _P, _P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sw_graph_filter_kmers": (_I, [_P, _P, _SZ]),
     "sw_dist_merge_edges": (_I, [_P, _P, _P, _U32, C.POINTER(_U32)]),
+    "sw_graph_count_sums": (_I, [_P, _P]),
     "sw_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ)]),
 }
 

@@ -1110,6 +1110,17 @@ int sw_graph_filter_kmers(sw_graph* g, const uint64_t* used_hashes, size_t n_use
     });
 }
 
+int sw_graph_count_sums(sw_graph* g, uint64_t sums[3])
+{
+    return guarded([&] {
+        if (!g->on_device) fail_runtime("graph is not device resident");
+        arena_reset();
+        unsigned long long out[3];
+        graph_count_sums(g->dev, out, g->stream);
+        for (int i = 0; i < 3; ++i) sums[i] = out[i];
+    });
+}
+
 int sw_filter_edges_and_nodes(const sw_node* nodes, size_t n_nodes, const sw_edge* edges, size_t n_edges,
                               uint64_t weight_th, sw_node* nodes_out, sw_edge* edges_out, size_t* n_nodes_out,
                               size_t* n_edges_out)

@@ -164,6 +164,8 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
 void graph_filter_edges(DevGraph& g, uint64_t weight_th, cudaStream_t s);
 // nodes whose hash is in used_hashes (host array, any order), their k-mers compacted (filter.cpp:139-201)
 void graph_filter_kmers(DevGraph& g, const uint64_t* used_hashes, size_t n_used, cudaStream_t s);
+// out = {sum n_tar, sum n_tar^2, sum n_tar * n_neg} over the nodes (kmers.py:424-429)
+void graph_count_sums(const DevGraph& g, unsigned long long out[3], cudaStream_t s);
 
 // ---- multi-GPU merge (dist.cu) -------------------------------------------------------------------
 void graph_split(const DevGraph& g, uint32_t P, unsigned long long* host_out /* 3*(P+1) */, cudaStream_t s);

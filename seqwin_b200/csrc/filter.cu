@@ -6,7 +6,11 @@
 //   graph_filter_kmers   keep the nodes whose hash is in a given set, compact their k-mers and
 //                        rewrite start / stop (cpp/src/seqwin/filter.cpp:139-201, filter_kmers)
 //
-// Both are stream compactions: flag, exclusive scan, ordered copy.  Node and edge order and every
+//   graph_count_sums     the three integer sums behind the automatic penalty threshold
+//                        (src/seqwin/kmers.py:424-429: expected k-mer absence in targets / presence in
+//                        non-targets, weighted by n_tar)
+//
+// The filters are stream compactions: flag, exclusive scan, ordered copy.  Node and edge order and every
 // field that is not a k-mer range stay as they were.
 #include <cuda_runtime.h>
 
@@ -137,6 +141,35 @@ __global__ void __launch_bounds__(kFT) kmer_gather_kernel(const sw_node* __restr
     }
 }
 
+// sums[0..2] += sum n_tar, sum n_tar^2, sum n_tar * n_neg over the nodes
+__global__ void __launch_bounds__(kFT) count_sums_kernel(const sw_node* __restrict__ nodes, uint64_t n,
+                                                         unsigned long long* __restrict__ sums)
+{
+    __shared__ unsigned long long s_part[3][kFT / 32];
+    unsigned long long a = 0, b = 0, c = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long t = nodes[i].n_tar, g = nodes[i].n_neg;
+        a += t;
+        b += t * t;
+        c += t * g;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        b += __shfl_xor_sync(0xffffffffu, b, d);
+        c += __shfl_xor_sync(0xffffffffu, c, d);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_part[0][wid] = a; s_part[1][wid] = b; s_part[2][wid] = c; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+        for (int i = 0; i < kFT / 32; ++i) t += s_part[threadIdx.x][i];
+        atomicAdd(&sums[threadIdx.x], t);
+    }
+}
+
 unsigned long long read_total(const unsigned long long* d, cudaStream_t s)
 {
     const unsigned long long* h = readback_u64(d, 1, s);
@@ -192,6 +225,19 @@ void graph_filter_edges(DevGraph& g, uint64_t weight_th, cudaStream_t s)
     g.nodes = std::move(nodes_new);
     g.n_edges = n_keep;
     g.n_nodes = n_nodes_keep;
+}
+
+void graph_count_sums(const DevGraph& g, unsigned long long out[3], cudaStream_t s)
+{
+    DevBuf<unsigned long long> sums(3, s, true);
+    SW_CUDA(cudaMemsetAsync(sums.p, 0, sums.bytes(), s));
+    if (g.n_nodes) count_sums_kernel<<<grid_of(g.n_nodes), kFT, 0, s>>>(g.nodes.p, g.n_nodes, sums.p);
+    SW_CUDA(cudaGetLastError());
+    const unsigned long long* h = readback_u64(sums.p, 3, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    out[0] = h[0];
+    out[1] = h[1];
+    out[2] = h[2];
 }
 
 void graph_filter_kmers(DevGraph& g, const uint64_t* h_used, size_t n_used, cudaStream_t s)

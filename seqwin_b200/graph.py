@@ -15,7 +15,7 @@ from ._core import (EDGE_DTYPE, KMER_DTYPE, NODE_DTYPE, _build_native, _filter_k
                     _get_penalty_native)
 
 __all__ = ["KMER_DTYPE", "NODE_DTYPE", "EDGE_DTYPE", "KmerGraph", "_get_penalty", "_filter_kmers",
-           "_filter_edges_and_nodes"]
+           "_filter_edges_and_nodes", "penalty_threshold", "save_graph"]
 
 
 class KmerGraph:
@@ -58,3 +58,26 @@ def _filter_edges_and_nodes(nodes: NDArray[np.void], edges: NDArray[np.void], ed
         nodes.ctypes.data, len(nodes), edges.ctypes.data, len(edges), C.c_uint64(int(np.uint64(edge_weight_th))),
         nodes_out.ctypes.data, edges_out.ctypes.data, C.byref(nn), C.byref(ne)))
     return nodes_out[:nn.value].copy(), edges_out[:ne.value].copy()
+
+
+def penalty_threshold(count_sums, n_tar: int, n_neg: int, stringency: int = 5, penalty_th_cap: float = 0.2):
+    """Automatic penalty threshold of ``kmers.py:424-440`` (the branch without Mash) from the three
+    integer sums ``(sum n_tar, sum n_tar^2, sum n_tar * n_neg)`` over the scored nodes --
+    ``sw_graph_count_sums`` on a device-resident graph, or ``count_sums(nodes)`` for a numpy array.
+    Returns ``(penalty_th, e_absence_tar, e_presence_neg)``."""
+    s_t, s_tt, s_tn = (int(x) for x in count_sums)
+    e_absence_tar = 1.0 - s_tt / (n_tar * s_t)
+    e_presence_neg = s_tn / (n_neg * s_t)
+    penalty_th = (1 - stringency / 10) * (e_absence_tar * e_presence_neg) ** 0.5
+    return min(penalty_th, penalty_th_cap), e_absence_tar, e_presence_neg
+
+
+def count_sums(nodes: NDArray[np.void]):
+    """The sums of :func:`penalty_threshold` for a host array (exact integer arithmetic)."""
+    t = nodes["n_tar"].astype(np.uint64)
+    return int(t.sum()), int((t * t).sum()), int((t * nodes["n_neg"].astype(np.uint64)).sum())
+
+
+def save_graph(path, kmers, nodes, edges, record_offsets) -> None:
+    """``graph.npz`` exactly as ``core.py:134-145`` writes it."""
+    np.savez(path, allow_pickle=False, kmers=kmers, nodes=nodes, edges=edges, record_offsets=record_offsets)

@@ -117,3 +117,43 @@ def test_filter_on_full_size_graph_properties():
         if d:
             L.sw_dev_batch_free(d)
         L.sw_batch_free(batch)
+
+
+def test_penalty_threshold_statistics(synth_sets, tmp_path):
+    """the threshold statistics of kmers.py:424-440 from the device-resident nodes
+    (exact integer sums) vs the reference's float formula on the host arrays (rtol 1e-12: the
+    reference sums float products, the sums here are exact), and the graph.npz writer round trip."""
+    from seqwin_b200.graph import count_sums, penalty_threshold, save_graph
+    L = _lib.lib()
+    paths, is_t = synth_sets["synth_medium"]
+    is_t = np.ascontiguousarray(is_t, dtype=np.bool_)
+    n_tar, n_neg = int(is_t.sum()), int(len(is_t) - is_t.sum())
+    arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    b, d, g = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _lib.check(L.sw_batch_from_fasta(arr, len(paths), 2, C.byref(b)))
+    try:
+        _lib.check(L.sw_dev_upload(b, C.byref(d)))
+        _lib.check(L.sw_dev_build_scored(d, 21, 50, is_t.ctypes.data, len(is_t), C.byref(g), None))
+        sums = np.zeros(3, dtype=np.uint64)
+        _lib.check(L.sw_graph_count_sums(g, sums.ctypes.data))
+        kmers, nodes, edges = export_graph(L, g)
+        assert tuple(int(x) for x in sums) == count_sums(nodes)
+        # the reference's arithmetic (kmers.py:424-436)
+        frac_tar = nodes["n_tar"] / n_tar
+        e_abs = 1 - np.sum(frac_tar * nodes["n_tar"]) / np.sum(nodes["n_tar"])
+        frac_neg = nodes["n_neg"] / n_neg
+        e_pre = np.sum(frac_neg * nodes["n_tar"]) / np.sum(nodes["n_tar"])
+        th_ref = min((1 - 5 / 10) * (e_abs * e_pre) ** 0.5, 0.2)
+        th, a, p = penalty_threshold(sums, n_tar, n_neg)
+        assert abs(a - e_abs) <= 1e-12 and abs(p - e_pre) <= 1e-12 and abs(th - th_ref) <= 1e-12
+        offs = np.zeros(len(paths) + 1, dtype=np.uint32)
+        save_graph(tmp_path / "graph.npz", kmers, nodes, edges, offs)
+        back = np.load(tmp_path / "graph.npz", allow_pickle=False)
+        assert np.array_equal(back["nodes"], nodes) and np.array_equal(back["kmers"], kmers)
+        assert np.array_equal(back["edges"], edges) and back["nodes"].dtype == nodes.dtype
+    finally:
+        if g:
+            L.sw_graph_free(g)
+        if d:
+            L.sw_dev_batch_free(d)
+        L.sw_batch_free(b)
