@@ -43,6 +43,14 @@ struct EventTimer {
         cudaEventDestroy(b);
     }
     void start() { cudaEventRecord(a, s); }
+    void mark() { cudaEventRecord(b, s); }   // end of the interval, read later with read()
+    float read()
+    {
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
     float stop()
     {
         cudaEventRecord(b, s);
@@ -559,9 +567,18 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     }
     if (M > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers on one device");
 
+    // The number of adjacent-pair records only depends on the stream, so it is counted now and read
+    // at the node stage's synchronisation point: the edge stage can then start without one of its own.
+    const uint32_t nb = blocks_for(M);
+    DevBuf<unsigned long long> ecnt((size_t)nb + 1, s, true);
+    edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, ecnt.p);
+    exclusive_scan_u64(ecnt.p, nb, ecnt.p + nb, s);
+    SW_CUDA(cudaGetLastError());
+    const unsigned long long* n_raw_p = readback_u64(ecnt.p + nb, 1, s);
+    tm.launches += 2;
+
     // -- sort (h1, stream index): high word in 4 passes + tie fix-up (all 64 bits if that gives up) --
     SortPairs sp;
-    const uint32_t nb = blocks_for(M);
     DevBuf<unsigned long long> counts((size_t)nb + 1, s, true);
     TieFix tie(s);
     const int begin_bit = sort_begin_bit();
@@ -609,26 +626,31 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     }
     SW_CUDA(cudaGetLastError());
     tm.launches += 3;
-    if (after_nodes) (*after_nodes)();
-    tm.nodes_ms += timer.stop();
+    timer.mark();
 
     // -- edges -----------------------------------------------------------------------------------
-    timer.start();
-    edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, counts.p);
-    exclusive_scan_u64(counts.p, nb, counts.p + nb, s);
-    SW_CUDA(cudaGetLastError());
-    const unsigned long long* n_raw_p = readback_u64(counts.p + nb, 1, s);
-    SW_CUDA(cudaStreamSynchronize(s));
-    const unsigned long long n_raw = *n_raw_p;
-    tm.launches += 2;
+    // The first kernel of the edge stage is enqueued before the nodes-ready hook runs, so that the GPU
+    // has work while a multi-GPU caller cuts and ships the node arrays from the host.
+    EventTimer etimer(s);
+    etimer.start();
+    const unsigned long long n_raw = *n_raw_p;   // valid since the node stage's synchronisation
+    int rank_bits = 1;
+    while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
+    if (n_raw) {
+        sp.n = n_raw;
+        edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, rec_base, ecnt.p, rank_bits,
+                                             sp.keys.p, sp.vals.p);
+        SW_CUDA(cudaGetLastError());
+        ++tm.launches;
+    }
+    if (after_nodes) (*after_nodes)();
+    tm.nodes_ms += timer.read();
     if (n_raw == 0) {
         g.edges.alloc(0, s);
     } else {
         // reuse the node sort's buffers for the (rank pair, assembly) sort.  The key holds the two
         // ranks left-aligned (2 * rank_bits significant bits); the radix passes look at its high word
         // and the tie fix-up finishes the few pairs that agree there.
-        int rank_bits = 1;
-        while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
         const int full_begin_bit = (64 - 2 * rank_bits) & ~7;
         // first + 16 bits of second: pairs that still agree there are rare enough for the fix-up (with
         // only the high word, 10 bits of `second` at 4 M nodes, the C2 workload leaves 228 k boundaries)
@@ -637,12 +659,16 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         const uint32_t eb = blocks_for(n_raw);
         DevBuf<unsigned long long> ecounts((size_t)eb + 1, s, true);
         unsigned long long n_edges = 0;
-        for (bool full = edge_begin_bit <= full_begin_bit;; full = true) {
+        bool refill = false;
+        for (bool full = edge_begin_bit <= full_begin_bit;; full = true, refill = true) {
             sp.n = n_raw;
-            edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, rec_base, counts.p, rank_bits,
-                                                 sp.keys.p, sp.vals.p);
-            SW_CUDA(cudaGetLastError());
-            tm.launches += 1 + tie.sort(sp, edge_begin_bit, full_begin_bit, full, s);
+            if (refill) {   // the fix-up gave up: write the records again and sort every significant bit
+                edge_write_kernel<<<nb, kNT, 0, s>>>(st.vals.p, rank_of_stream.p, M, d_rec_asm, rec_base, ecnt.p, rank_bits,
+                                                     sp.keys.p, sp.vals.p);
+                SW_CUDA(cudaGetLastError());
+                ++tm.launches;
+            }
+            tm.launches += tie.sort(sp, edge_begin_bit, full_begin_bit, full, s);
             key_run_count_kernel<<<eb, kNT, 0, s>>>(sp.keys.p, n_raw, ecounts.p);
             exclusive_scan_u64(ecounts.p, eb, ecounts.p + eb, s);
             SW_CUDA(cudaGetLastError());
@@ -660,7 +686,7 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
         SW_CUDA(cudaGetLastError());
         tm.launches += 3;
     }
-    tm.edges_ms = timer.stop();
+    tm.edges_ms = etimer.stop();
     if (times) *times = tm;
 }
 
