@@ -72,12 +72,14 @@ def all_to_all_bytes(chunks: list[torch.Tensor], group=None) -> list[torch.Tenso
 
 
 def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], item_bytes: list[int], group=None,
-                      async_op: bool = False):
+                      async_op: bool = False, extra: np.ndarray | None = None):
     """Several byte tensors, each already laid out as P consecutive destination slices
     (splits[t][d] .. splits[t][d+1], in items).  One count exchange for all of them, then one
     all_to_all_single per tensor straight out of / into contiguous buffers (no concatenation).
-    Returns (received tensors, received item counts per source [T, P], pending work handles);
-    with async_op (NCCL only) the data transfers are left in flight on NCCL's stream."""
+    `extra` ([P] int64, one value per destination) rides on the count exchange.
+    Returns (received tensors, received item counts per source [T, P], pending work handles,
+    received extra values [P] or None); with async_op (NCCL only) the data transfers are left in
+    flight on NCCL's stream."""
     world = dist.get_world_size(group)
     dev = tensors[0].device
     send_items = np.stack([np.diff(sp.astype(np.int64)) for sp in splits])          # [T, P]
@@ -88,11 +90,19 @@ def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], ite
             rc = all_to_all_bytes(chunks, group)
             outs.append(torch.cat(rc))
             counts.append([c.numel() // ib for c in rc])
-        return outs, np.array(counts, dtype=np.uint64), []
-    send_t = torch.from_numpy(np.ascontiguousarray(send_items.T)).to(dev)            # [P, T]: row d goes to rank d
+        recv_extra = None
+        if extra is not None:
+            ex = torch.from_numpy(np.ascontiguousarray(extra, dtype=np.int64)).to(dev).view(torch.uint8)
+            rc = all_to_all_bytes([ex[8 * d:8 * d + 8] for d in range(world)], group)
+            recv_extra = torch.cat(rc).view(torch.int64).cpu().numpy()
+        return outs, np.array(counts, dtype=np.uint64), [], recv_extra
+    rows = [send_items] if extra is None else [send_items, np.asarray(extra, dtype=np.int64)[None, :]]
+    send_t = torch.from_numpy(np.ascontiguousarray(np.concatenate(rows).T)).to(dev)  # [P, T(+1)]: row d goes to rank d
     recv_t = torch.empty_like(send_t)
     dist.all_to_all_single(recv_t, send_t, group=group)
-    recv_items = recv_t.cpu().numpy().T                                              # [T, P]
+    recv_all = recv_t.cpu().numpy().T                                                # [T(+1), P]
+    recv_items = recv_all[:len(tensors)]
+    recv_extra = recv_all[len(tensors)].copy() if extra is not None else None
     outs, works = [], []
     for i, (t, sp, ib) in enumerate(zip(tensors, splits, item_bytes)):
         out = torch.empty(int(recv_items[i].sum()) * ib, dtype=torch.uint8, device=dev)
@@ -102,17 +112,18 @@ def all_to_all_slices(tensors: list[torch.Tensor], splits: list[np.ndarray], ite
         if async_op:
             works.append(wk)
         outs.append(out)
-    return outs, recv_items.astype(np.uint64), works
+    return outs, recv_items.astype(np.uint64), works, recv_extra
 
 
 def exchange_nodes(nodes, kmers, node_split, kmer_split, group=None, async_op=False):
-    """First half of the exchange: node and k-mer slices (plus each sender's k-mer base, which the
-    owner needs to rebase node.start: one extra 8-byte item per destination)."""
+    """First half of the exchange: node and k-mer slices.  The owner also needs each sender's k-mer
+    base to rebase node.start: one value per destination, carried by the count exchange.
+    Returns ((recv_nodes, recv_kmers, recv_kmer_base), counts, works)."""
     world = dist.get_world_size(group)
-    bases = torch.from_numpy(kmer_split[:world].astype(np.int64)).to(nodes.device).view(torch.uint8)
-    base_split = np.arange(world + 1, dtype=np.uint64)
-    return all_to_all_slices([nodes, kmers, bases], [node_split, kmer_split, base_split],
-                             [NODE_BYTES, KMER_BYTES, 8], group, async_op)
+    (recv_nodes, recv_kmers), counts, works, recv_base = all_to_all_slices(
+        [nodes, kmers], [node_split, kmer_split], [NODE_BYTES, KMER_BYTES], group, async_op,
+        extra=kmer_split[:world].astype(np.int64))
+    return (recv_nodes, recv_kmers, recv_base.astype(np.uint64)), counts, works
 
 
 def exchange_and_merge(stages, local: LocalGraph, group=None, early=None):
@@ -124,11 +135,11 @@ def exchange_and_merge(stages, local: LocalGraph, group=None, early=None):
         early = exchange_nodes(local.nodes, local.kmers, local.node_split, local.kmer_split, group)
     (recv_nodes, recv_kmers, recv_base), counts, works = early
     two_halves = hasattr(stages, "merge_nodes") and dist.get_backend(group) == "nccl"
-    (recv_edges,), ecounts, eworks = all_to_all_slices([local.edges], [local.edge_split], [EDGE_BYTES], group,
-                                                       async_op=two_halves)
+    (recv_edges,), ecounts, eworks, _ = all_to_all_slices([local.edges], [local.edge_split], [EDGE_BYTES], group,
+                                                          async_op=two_halves)
     for wk in works:
         wk.wait()
-    kmer_base = recv_base.view(torch.int64).cpu().numpy().astype(np.uint64)
+    kmer_base = np.ascontiguousarray(recv_base, dtype=np.uint64)
     node_args = (recv_nodes, np.ascontiguousarray(counts[0]), recv_kmers, np.ascontiguousarray(counts[1]), kmer_base)
     if not two_halves:
         return stages.merge(*node_args, recv_edges, np.ascontiguousarray(ecounts[0]))
