@@ -276,4 +276,27 @@ long emul_sketch_sparse(const uint8_t* const* seqs, const uint32_t* lens, size_t
         return -1;
     }
 }
+
+// the same from FASTA / .gz files through the host ingest (parse_fasta + packer), one assembly per file
+long emul_sketch_files(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, int sparse, uint64_t* h1_out,
+                       uint32_t* pos_out, uint32_t* rec_out, size_t cap)
+{
+    try {
+        sw_batch* b = sw::batch_from_fasta(paths, n_paths, 2);
+        std::vector<uint64_t> keys, vals;
+        uint32_t n_tiles = 0, n_fb = 0;
+        if (sparse) sw::emulate_sparse<8, 64, 24, 16, 33>(*b, k, w, 0.0, keys, vals, &n_tiles, &n_fb);
+        else sw::emulate<32, 9>(*b, k, w, keys, vals, &n_tiles, 0);
+        delete b;
+        for (size_t i = 0; i < keys.size() && i < cap; ++i) {
+            h1_out[i] = keys[i];
+            pos_out[i] = (uint32_t)vals[i];
+            rec_out[i] = (uint32_t)(vals[i] >> 32);
+        }
+        return (long)keys.size();
+    } catch (const std::exception& e) {
+        fprintf(stderr, "emul_sketch_files: %s\n", e.what());
+        return -1;
+    }
+}
 }

@@ -25,6 +25,7 @@ def emul():
     L = C.CDLL(str(so))
     L.emul_sketch.restype = C.c_long
     L.emul_sketch_sparse.restype = C.c_long
+    L.emul_sketch_files.restype = C.c_long
 
     def run(seqs, k, w, nt, c1, force_generic=0):
         n = len(seqs)
@@ -53,7 +54,17 @@ def emul():
                                  C.c_void_p(rec.ctypes.data), C.c_size_t(cap), C.byref(nt_out), C.byref(nf_out))
         assert m >= 0, f"emulator failed ({m})"
         return h1[:m], pos[:m], rec[:m], nt_out.value, nf_out.value
+    def run_files(paths, k, w, sparse):
+        arr = (C.c_char_p * max(1, len(paths)))(*[str(p).encode() for p in paths])
+        cap = 4_000_000
+        h1, pos, rec = np.empty(cap, np.uint64), np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        m = L.emul_sketch_files(arr, C.c_size_t(len(paths)), C.c_uint32(k), C.c_uint32(w), int(sparse),
+                                C.c_void_p(h1.ctypes.data), C.c_void_p(pos.ctypes.data), C.c_void_p(rec.ctypes.data),
+                                C.c_size_t(cap))
+        assert 0 <= m <= cap, f"emulator failed ({m})"
+        return h1[:m], pos[:m], rec[:m]
     run.sparse = run_sparse
+    run.files = run_files
     return run
 
 
@@ -169,3 +180,21 @@ def test_sparse_kernel_property_random_parameters(emul):
         oh, op, orr = _oracle_stream(seqs, k, w)
         eh, ep, er, _, _ = emul.sparse(seqs, k, w, nt, c1, cpw)
         assert np.array_equal(eh, oh) and np.array_equal(ep, op) and np.array_equal(er, orr), (trial, k, w, nt, c1, cpw)
+
+
+@pytest.mark.parametrize("kw", [(17, 10), (21, 200), (5, 3)], ids=lambda kw: f"k{kw[0]}w{kw[1]}")
+def test_fasta_ingest_then_emulated_sketch_matches_oracle(emul, kw, fixture_paths, edge_paths):
+    """FASTA / .gz files -> host parser + 2-bit packer (csrc/ingest.cpp) -> emulated sketch kernels, against
+    the oracle's graph built from the same files: the parser's line rules (blank lines, CR LF, inner
+    whitespace, IUPAC codes, lower case, empty records, gzip) checked without a GPU."""
+    k, w = kw
+    for paths in (fixture_paths, edge_paths[0]):
+        paths = [str(p) for p in paths]
+        kmers, nodes, _, _, _ = O._build_native(paths, k, w)
+        hashes = np.repeat(nodes["hash"], (nodes["stop"] - nodes["start"]).astype(np.int64))
+        order = np.lexsort((kmers["pos"], kmers["record_idx"]))
+        want = (hashes[order], kmers["pos"][order], kmers["record_idx"][order])
+        for sparse in ((0, 1) if w >= 96 else (0,)):
+            h1, pos, rec = emul.files(paths, k, w, sparse)
+            assert len(h1) == len(want[0]), (kw, sparse, len(h1), len(want[0]))
+            assert np.array_equal(h1, want[0]) and np.array_equal(pos, want[1]) and np.array_equal(rec, want[2]), (kw, sparse)
