@@ -152,6 +152,35 @@ struct RecordPacker {
             else if (c == 4) push_invalid();
         }
     }
+    // n bytes that are expected to be bases only (a full-width sequence line): packs them block by
+    // block and returns n, or stops before the first block that holds anything else and returns how
+    // many bytes it consumed (the caller goes on with the general path from there)
+    size_t append_bases(const unsigned char* p, size_t n)
+    {
+        size_t i = 0;
+#if defined(__x86_64__)
+        if (kHaveAvx2) {
+            for (; i + 32 <= n; i += 32) {
+                uint64_t w32;
+                if (!pack32_avx2(p + i, &w32)) return i;
+                push_word32(w32);
+            }
+        }
+        if (kHaveSsse3) {
+            for (; i + 16 <= n; i += 16) {
+                uint32_t w16;
+                if (!pack16_ssse3(p + i, &w16)) return i;
+                push_word16(w16);
+            }
+        }
+#endif
+        for (; i < n; ++i) {
+            const uint8_t c = kClass.t[p[i]];
+            if (c >= 4) return i;
+            push_code(c);
+        }
+        return n;
+    }
     void append(const unsigned char* p, size_t n)
     {
         size_t i = 0;
@@ -288,7 +317,29 @@ void parse_fasta(const std::string& path, AsmPacked& out)
     RecordPacker rp(out);
     bool have = false;
     size_t i = 0;
+    size_t width = 0;   // length of the previous sequence line: FASTA files keep one width per record
     while (i < n) {
+        // Fast path: the line is as long as the one before, ends where predicted and holds bases only
+        // (so no newline hides inside it).  Anything else falls through to the general rules below,
+        // from the first byte the fast path did not take.
+        if (have && width && p[i] != '>' && i + width < n &&
+            (p[i + width] == '\n' || (p[i + width] == '\r' && i + width + 1 < n && p[i + width + 1] == '\n'))) {
+            const size_t took = rp.append_bases(p + i, width);
+            if (took == width) {
+                i += width + (p[i + width] == '\n' ? 1 : 2);
+                continue;
+            }
+            if (took) {   // the rest of this line, by the general rules (it cannot be a header: not column 0)
+                const size_t q = i + took;
+                const void* nl = memchr(p + q, '\n', n - q);
+                const size_t j = nl ? (size_t)((const unsigned char*)nl - p) : n;
+                size_t end = j;
+                if (end > q && p[end - 1] == '\r') --end;
+                rp.append(p + q, end - q);
+                i = j + 1;
+                continue;
+            }
+        }
         const void* nl = memchr(p + i, '\n', n - i);
         const size_t j = nl ? (size_t)((const unsigned char*)nl - p) : n;
         size_t end = j;
@@ -302,9 +353,11 @@ void parse_fasta(const std::string& path, AsmPacked& out)
                 while (e < end && kClass.t[p[e]] != 5) ++e;
                 rp.begin(std::string((const char*)p + i + 1, e - (i + 1)));
                 have = true;
+                width = 0;
             } else {
                 if (!have) fail_runtime("Invalid FASTA: sequence encountered before header");
                 rp.append(p + i, end - i);
+                width = end - i;
             }
         }
         i = j + 1;

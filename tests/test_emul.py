@@ -198,3 +198,50 @@ def test_fasta_ingest_then_emulated_sketch_matches_oracle(emul, kw, fixture_path
             h1, pos, rec = emul.files(paths, k, w, sparse)
             assert len(h1) == len(want[0]), (kw, sparse, len(h1), len(want[0]))
             assert np.array_equal(h1, want[0]) and np.array_equal(pos, want[1]) and np.array_equal(rec, want[2]), (kw, sparse)
+
+
+def test_fasta_parser_line_width_fast_path(emul, tmp_path):
+    """The parser predicts where a sequence line ends from the width of the previous one.  Files built
+    to defeat the prediction -- CR LF, widths that change, short last lines, blank lines, an N inside a
+    full-width line, leading blanks, a header right after a short line -- must still give the oracle's
+    minimizers."""
+    rng = np.random.default_rng(3)
+
+    def seq(n, p_n=0.0):
+        a = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+        if p_n:
+            a[rng.random(n) < p_n] = ord("N")
+        return a.tobytes().decode()
+
+    files = []
+
+    def write(name, recs, width, eol="\n", lower=False, blank=False):
+        p = tmp_path / name
+        with open(p, "w", newline="") as f:
+            for rid, s in recs:
+                f.write(f">{rid} desc{eol}")
+                s = s.lower() if lower else s
+                for i in range(0, len(s), width):
+                    f.write(s[i:i + width] + eol)
+                    if blank and i % (7 * width) == 0:
+                        f.write(eol)
+        files.append(str(p))
+
+    write("a.fa", [("r1", seq(5000)), ("r2", seq(3333, 0.01))], 80)
+    write("b.fa", [("r1", seq(4000)), ("r2", seq(1000))], 60, eol="\r\n")
+    write("c.fa", [("r1", seq(2500, 0.002))], 70, lower=True, blank=True)
+    write("d.fa", [("r1", seq(100)), ("r2", seq(81)), ("r3", seq(80)), ("r4", seq(79)), ("r5", "")], 80)
+    write("e.fa", [("r1", seq(6000))], 33)
+    s1 = seq(80)
+    with open(tmp_path / "f.fa", "w") as f:
+        f.write(">x\n" + s1 + "\n" + s1[:40] + "N" + s1[41:] + "\n" + seq(30) + "\n>y\n" + seq(80) + "\n" + seq(80) + "\n"
+                + "   " + seq(77) + "\n" + seq(80))   # no newline at the end of the file
+    files.append(str(tmp_path / "f.fa"))
+    for k, w in ((5, 3), (17, 10), (21, 50)):
+        kmers, nodes, _, _, _ = O._build_native(files, k, w)
+        hashes = np.repeat(nodes["hash"], (nodes["stop"] - nodes["start"]).astype(np.int64))
+        order = np.lexsort((kmers["pos"], kmers["record_idx"]))
+        h1, pos, rec = emul.files(files, k, w, 0)
+        assert len(h1) == len(order), (k, w, len(h1), len(order))
+        assert np.array_equal(h1, hashes[order]) and np.array_equal(pos, kmers["pos"][order]), (k, w)
+        assert np.array_equal(rec, kmers["record_idx"][order]), (k, w)
