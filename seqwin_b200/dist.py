@@ -263,6 +263,10 @@ class CudaStages:
         m1.record()
         return g
 
+    def finish_penalty(self, g, class_totals) -> None:
+        """penalty of the merged nodes from their summed n_tar / n_neg and the global class sizes"""
+        self._lib.check(self.L.sw_graph_finish_penalty(g, C.c_uint64(class_totals[0]), C.c_uint64(class_totals[1])))
+
     def merge_edges(self, g, edges, edge_counts):
         L, lb = self.L, self._lib
         torch.cuda.current_stream(self.device).synchronize()
@@ -282,8 +286,10 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
     world = dist.get_world_size(group)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    ev[0].record()
+    timed = torch.device(stages.device).type == "cuda"   # phase events for bench.py (the CPU stand-in has none)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
+    if timed:
+        ev[0].record()
     # the node / k-mer slices leave as soon as they are final; over NCCL the transfer stays in flight
     # while the edge stage runs (gloo exchanges synchronously inside the hook: same code path, no overlap)
     on_nodes = None
@@ -301,14 +307,16 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
             class_totals = (int(tot[0]), int(tot[1]))
     local = stages.local_build(dev_batch, k, w, rec_base, world, host_batch=host_batch, on_nodes=on_nodes,
                                is_targets=is_targets)
-    ev[1].record()
+    if timed:
+        ev[1].record()
     try:
         g = exchange_and_merge(stages, local, group, early=local.early)
     finally:
         stages.free_local(local)
     if is_targets is not None:
-        stages._lib.check(stages.L.sw_graph_finish_penalty(g, C.c_uint64(class_totals[0]), C.c_uint64(class_totals[1])))
-    ev[2].record()
+        stages.finish_penalty(g, class_totals)
+    if timed:
+        ev[2].record()
     stages.phase_events = ev
     return g
 

@@ -19,11 +19,18 @@ class NumpyStages:
     """Test double for seqwin_b200.dist.CudaStages."""
     device = torch.device("cpu")
 
-    def local_build(self, paths, k, w, rec_base, world):
+    def local_build(self, paths, k, w, rec_base, world, host_batch=None, on_nodes=None, is_targets=None):
         from oracle import oracle as O
         from seqwin_b200.dist import LocalGraph
         kmers, nodes, edges, offsets, ids = O._build_native(paths, k, w)
         kmers = kmers.copy()
+        if is_targets is not None:   # shard counts: distinct assemblies of this shard per node, by class
+            asm_of = np.repeat(np.arange(len(offsets) - 1), np.diff(offsets.astype(np.int64)))
+            nodes = nodes.copy()
+            for i in range(len(nodes)):
+                a = np.unique(asm_of[kmers["record_idx"][int(nodes["start"][i]):int(nodes["stop"][i])]])
+                nodes["n_tar"][i] = int(np.count_nonzero(is_targets[a]))
+                nodes["n_neg"][i] = len(a) - int(nodes["n_tar"][i])
         kmers["record_idx"] += np.uint32(rec_base)
         bounds = [(i << 64) // world for i in range(world)]
         ebounds = [int((1.0 - (1.0 - i / world) ** 0.5) * 2.0 ** 64) for i in range(world)]   # balanced for min(u, v)
@@ -33,7 +40,10 @@ class NumpyStages:
                       dtype=np.uint64)
         ks = np.array([int(nodes["start"][int(i)]) if int(i) < len(nodes) else len(kmers) for i in ns], dtype=np.uint64)
         as_t = lambda a: torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy())  # noqa: E731
-        return LocalGraph(as_t(kmers), as_t(nodes), as_t(edges), ns, ks, es)
+        local = LocalGraph(as_t(kmers), as_t(nodes), as_t(edges), ns, ks, es)
+        if on_nodes is not None:   # the nodes-ready hook of the CUDA build
+            local.early = on_nodes(local.nodes, local.kmers, ns, ks)
+        return local
 
     def free_local(self, local):
         pass
@@ -56,14 +66,16 @@ class NumpyStages:
             seg = kmers[abs_start[j]:abs_start[j] + cnt]
             if out_n and out_n[-1][0] == nodes["hash"][j]:
                 out_n[-1][2] += cnt
+                out_n[-1][3] += int(nodes["n_tar"][j])   # an assembly lives on one rank: counts add
+                out_n[-1][4] += int(nodes["n_neg"][j])
             else:
                 pos = sum(len(x) for x in out_k)
-                out_n.append([nodes["hash"][j], pos, pos + cnt])
+                out_n.append([nodes["hash"][j], pos, pos + cnt, int(nodes["n_tar"][j]), int(nodes["n_neg"][j])])
             out_k.append(seg)
         mk = np.concatenate(out_k) if out_k else np.empty(0, KMER_DTYPE)
         mn = np.zeros(len(out_n), dtype=NODE_DTYPE)
-        for i, (h, a, b) in enumerate(out_n):
-            mn[i] = (h, a, b, 0, 0, 0.0)
+        for i, (h, a, b, nt, nn) in enumerate(out_n):
+            mn[i] = (h, a, b, nt, nn, 0.0)
         eo = np.lexsort((edges["second"], edges["first"]))
         me = []
         for j in eo:
@@ -75,6 +87,33 @@ class NumpyStages:
         for i, (a, b, c) in enumerate(me):
             mee[i] = (a, b, c)
         return mk, mn, mee
+
+
+    def finish_penalty(self, g, class_totals):
+        nodes = g[1]
+        ft = nodes["n_tar"] * (1.0 / class_totals[0])
+        fn = nodes["n_neg"] * (1.0 / class_totals[1])
+        nodes["penalty"] = np.sqrt((1.0 - ft) * (1.0 - ft) + fn * fn)
+
+
+def _scored_worker(rank, world, port, paths, is_t, k, w, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from seqwin_b200 import dist as swd
+        per = (len(paths) + world - 1) // world
+        mine = paths[rank * per:(rank + 1) * per]
+        mine_t = np.asarray(is_t[rank * per:(rank + 1) * per], dtype=np.bool_)
+        n_rec_local = int(O._build_native(mine, k, w)[3][-1])
+        # dist_build end to end (hook, class totals by all-reduce, merge, finish) with the numpy stand-in
+        merged = swd.dist_build(NumpyStages(), mine, n_rec_local, k, w, is_targets=mine_t)
+        full = swd.gather_graph(merged)
+        if rank == 0:
+            np.savez(out_path, kmers=full[0], nodes=full[1], edges=full[2])
+    finally:
+        dist.destroy_process_group()
 
 
 def _worker(rank, world, port, paths, k, w, out_path):
@@ -112,3 +151,24 @@ def test_two_rank_exchange_matches_single_graph(synth_sets, tmp_path, kw):
     want = O._build_native(paths, *kw)
     assert int(got["total"][0]) == int(want[3][-1])
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"2 ranks {kw}")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dist_build_scored_flow_over_gloo(synth_sets, tmp_path, world):
+    """seqwin_b200.dist.dist_build with scoring, host logic only: shards that hold one class only,
+    class totals by all-reduce, counts summed in the merge, penalty finished last == the oracle's
+    build + get_penalty on all assemblies."""
+    from oracle import oracle as O
+    k, w = 17, 10
+    paths, is_t = synth_sets["synth_small"]
+    paths = [str(p) for p in paths]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "merged.npz"
+    mp.spawn(_scored_worker, args=(world, port, paths, list(map(bool, is_t)), k, w, str(out)), nprocs=world, join=True)
+    got = np.load(out)
+    kmers, nodes, edges, offsets, _ = O._build_native(paths, k, w)
+    O._get_penalty_native(kmers, nodes, offsets, np.asarray(is_t, dtype=np.bool_))
+    assert np.array_equal(got["kmers"], kmers) and np.array_equal(got["edges"], edges)
+    assert np.array_equal(got["nodes"], nodes)
