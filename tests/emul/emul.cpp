@@ -160,6 +160,16 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
     constexpr uint32_t MC = sparse_mc(NT), MA = sparse_ma(NT);
     std::vector<unsigned char> smem(sparse_smem_bytes(NT, CAP) + 64);
     SparseSmem S = carve_sparse_smem(smem.data(), NT, CAP);
+#ifdef EMUL_SPLIT_SMEM
+    // manual check (g++ -DEMUL_SPLIT_SMEM -fsanitize=address): every shared array in its own heap
+    // block of exactly its size, so that AddressSanitizer sees an overrun from one array into the next
+    const size_t mc = sparse_mc(NT) + 2, ma = sparse_ma(NT) + 2;
+    std::vector<RollEntry> v_tab(20);
+    std::vector<uint64_t> v_list((size_t)CAP * NT), v_key(mc), v_akey(ma);
+    std::vector<uint32_t> v_lo(mc), v_sel(mc / 32 + 2);
+    std::vector<uint16_t> v_aj(ma), v_na(mc);
+    S = SparseSmem{v_tab.data(), v_list.data(), v_key.data(), v_akey.data(), v_lo.data(), v_sel.data(), v_aj.data(), v_na.data()};
+#endif
     std::vector<uint32_t> fallback;
     for (uint32_t t : scrambled_order(P.n_tiles)) {
         memset(smem.data(), 0xA5, smem.size());
