@@ -89,6 +89,12 @@ static void dense_tile(const SketchParams& P, uint32_t t, bool fast, EmulOut& o)
     const uint32_t nc = fast ? (uint32_t)NT : TK / 9 + 2;
     std::vector<unsigned char> smem(tile_smem_bytes(TK, nc) + 64);
     TileSmem S = carve_tile_smem(smem.data(), TK, nc);
+#ifdef EMUL_SPLIT_SMEM
+    std::vector<RollEntry> v_tab(20);
+    std::vector<uint64_t> v_h0(TK, 0xA5A5A5A5A5A5A5A5ull), v_cmh(nc);
+    std::vector<uint16_t> v_cmi(nc), v_amin(TK), v_pidx(TK), v_first(nc);
+    S = TileSmem{v_tab.data(), v_h0.data(), v_cmh.data(), v_cmi.data(), v_amin.data(), v_pidx.data(), v_first.data()};
+#endif
     // poison shared memory between tiles so that reads of stale data show up as mismatches
     memset(smem.data(), 0xA5, smem.size());
     for (int i = 0; i < 20; ++i) S.tab[i] = P.table.e[i];
