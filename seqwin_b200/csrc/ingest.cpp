@@ -16,6 +16,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <memory>
@@ -458,8 +461,17 @@ sw_batch* assemble(std::vector<AsmPacked>& parts, uint32_t n_threads)
 sw_batch* batch_from_fasta(const char* const* paths, size_t n_paths, uint32_t n_threads)
 {
     std::vector<AsmPacked> parts(n_paths);
+    const auto t0 = std::chrono::steady_clock::now();
     parallel_for(n_paths, n_threads, [&](size_t a) { parse_fasta(paths[a], parts[a]); });
-    return assemble(parts, n_threads);
+    const auto t1 = std::chrono::steady_clock::now();
+    sw_batch* b = assemble(parts, n_threads);
+    if (getenv("SEQWIN_INGEST_PROFILE")) {   // where the host side of a build from FASTA spends its time
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ingest] %zu files, %u threads: parse + pack %.1f ms, assemble into the pinned batch %.1f ms\n",
+                n_paths, n_threads, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
+    return b;
 }
 
 sw_batch* batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const uint32_t* asm_of,
