@@ -89,6 +89,10 @@ int sw_batch_from_fasta(const char* const* paths, size_t n_paths, uint32_t n_hos
 int sw_batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const uint32_t* asm_of,
                          const char* const* ids, size_t n_records, size_t n_assemblies,
                          uint32_t n_host_threads, sw_batch** out);
+/* One batch out of several (assemblies of parts[0] first, then parts[1], ...): lets a caller that
+ * produces its input piecewise build a large batch without holding more than one piece unpacked.
+ * The parts stay valid and are still the caller's to free. */
+int sw_batch_concat(const sw_batch* const* parts, size_t n_parts, sw_batch** out);
 size_t sw_batch_n_bases(const sw_batch* b);
 size_t sw_batch_n_records(const sw_batch* b);
 size_t sw_batch_packed_bytes(const sw_batch* b);

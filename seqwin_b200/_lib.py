@@ -36,6 +36,7 @@ PROTOTYPES = {
     "sw_filter_kmers": (_I, [_P, _SZ, _P, _SZ, _P, _SZ, _P, _P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sw_batch_from_fasta": (_I, [C.POINTER(C.c_char_p), _SZ, _U32, C.POINTER(_P)]),
     "sw_batch_from_memory": (_I, [C.POINTER(_P), _P, _P, C.POINTER(C.c_char_p), _SZ, _SZ, _U32, C.POINTER(_P)]),
+    "sw_batch_concat": (_I, [C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "sw_batch_n_bases": (_SZ, [_P]),
     "sw_batch_n_records": (_SZ, [_P]),
     "sw_batch_packed_bytes": (_SZ, [_P]),

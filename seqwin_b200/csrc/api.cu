@@ -720,6 +720,11 @@ int sw_batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const
     return guarded([&] { *out = batch_from_memory(seqs, lens, asm_of, ids, n_records, n_assemblies, n_threads); });
 }
 
+int sw_batch_concat(const sw_batch* const* parts, size_t n_parts, sw_batch** out)
+{
+    return guarded([&] { *out = batch_concat(parts, n_parts); });
+}
+
 size_t sw_batch_n_bases(const sw_batch* b) { return b->n_bases; }
 size_t sw_batch_n_records(const sw_batch* b) { return b->rec_len.size(); }
 size_t sw_batch_packed_bytes(const sw_batch* b) { return b->n_words * sizeof(uint32_t); }

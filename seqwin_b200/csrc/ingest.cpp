@@ -502,6 +502,61 @@ sw_batch* batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, co
     return assemble(parts, n_threads);
 }
 
+// Concatenate packed batches (assemblies of part 0 first): the way a caller that produces its input
+// piecewise (synthetic sets, streamed downloads) builds one large batch without ever holding the
+// unpacked bases of more than one piece.
+sw_batch* batch_concat(const sw_batch* const* parts, size_t n_parts)
+{
+    auto* b = new sw_batch();
+    try {
+        size_t words = 0, R = 0, A = 0, I = 0;
+        for (size_t p = 0; p < n_parts; ++p) {
+            words += parts[p]->n_words - kTailPadWords;
+            R += parts[p]->rec_len.size();
+            A += parts[p]->record_offsets.size() - 1;
+            I += parts[p]->inv_start.size();
+        }
+        if (R > 0xFFFFFFFFull) fail_runtime("Total number of FASTA records exceeds uint32 range");
+        if (A > 0xFFFFFFFFull) fail_runtime("Number of input assemblies exceeds uint32 range");
+        if (I > 0xFFFFFFFFull) fail_runtime("too many unhashable runs");
+        b->n_words = words + kTailPadWords;
+        b->words = (uint32_t*)alloc_host(b->n_words * sizeof(uint32_t), &b->pinned);
+        if (!b->words) fail_runtime("host allocation of the packed batch failed");
+        memset(b->words + words, 0, kTailPadWords * sizeof(uint32_t));
+        b->rec_word_off.reserve(R);
+        b->rec_len.reserve(R);
+        b->rec_inv_off.reserve(R + 1);
+        b->inv_start.reserve(I);
+        b->inv_len.reserve(I);
+        b->ids.reserve(R);
+        b->record_offsets.reserve(A + 1);
+        b->record_offsets.push_back(0);
+        size_t w0 = 0;
+        for (size_t p = 0; p < n_parts; ++p) {
+            const sw_batch& s = *parts[p];
+            const size_t nw = s.n_words - kTailPadWords;
+            if (nw) memcpy(b->words + w0, s.words, nw * sizeof(uint32_t));
+            const uint32_t r0 = (uint32_t)b->rec_len.size(), i0 = (uint32_t)b->inv_start.size();
+            for (size_t r = 0; r < s.rec_len.size(); ++r) {
+                b->rec_word_off.push_back(w0 + s.rec_word_off[r]);
+                b->rec_len.push_back(s.rec_len[r]);
+                b->rec_inv_off.push_back(i0 + s.rec_inv_off[r]);
+            }
+            b->inv_start.insert(b->inv_start.end(), s.inv_start.begin(), s.inv_start.end());
+            b->inv_len.insert(b->inv_len.end(), s.inv_len.begin(), s.inv_len.end());
+            b->ids.insert(b->ids.end(), s.ids.begin(), s.ids.end());
+            for (size_t a = 1; a < s.record_offsets.size(); ++a) b->record_offsets.push_back(r0 + s.record_offsets[a]);
+            b->n_bases += s.n_bases;
+            w0 += nw;
+        }
+        b->rec_inv_off.push_back((uint32_t)b->inv_start.size());
+    } catch (...) {
+        delete b;
+        throw;
+    }
+    return b;
+}
+
 Plan plan_tiles(const sw_batch& b, uint32_t k, uint32_t w, uint32_t tk)
 {
     Plan plan;

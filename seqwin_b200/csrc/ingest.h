@@ -27,6 +27,7 @@ sw_batch* batch_from_fasta(const char* const* paths, size_t n_paths, uint32_t n_
 sw_batch* batch_from_memory(const uint8_t* const* seqs, const uint32_t* lens, const uint32_t* asm_of,
                             const char* const* ids, size_t n_records, size_t n_assemblies,
                             uint32_t n_threads);
+sw_batch* batch_concat(const sw_batch* const* parts, size_t n_parts);
 
 struct Plan {
     std::vector<Piece> pieces;
