@@ -169,7 +169,8 @@ int sw_graph_split(sw_graph* g, uint32_t n_parts, uint64_t* node_split, uint64_t
  * that the transfer overlaps the edge stage -- the role the per-thread hand-off to
  * merge_thread_graphs plays in the reference (cpp/src/seqwin/build.cpp:352-378).  Inside the
  * callback only sw_graph_size / sw_graph_device_ptrs / sw_graph_split may be called on `g`.
- * fn = NULL clears the hook.  The hook is process-wide: one builder thread per process. */
+ * fn = NULL clears the hook.  The hook is per host thread (like sw_set_stream): it fires for builds
+ * started by the thread that set it. */
 typedef void (*sw_nodes_ready_fn)(void* user, sw_graph* g);
 int sw_set_nodes_ready(sw_nodes_ready_fn fn, void* user);
 /* Merge the slices a hash-range owner received from n_src ranks (device pointers, concatenated in
@@ -205,6 +206,10 @@ int sw_graph_filter_kmers(sw_graph* g, const uint64_t* used_hashes, size_t n_use
  * sum n_tar * n_neg} over the nodes, exact integers.  With T targets and N non-targets:
  * e_absence_tar = 1 - sums[1] / (T * sums[0]), e_presence_neg = sums[2] / (N * sums[0]). */
 int sw_graph_count_sums(sw_graph* g, uint64_t sums[3]);
+
+/* Measured peak of the INT32 ALU pipe, the roofline that bounds the sketch kernels: lane-operations per
+ * second of dependent-chain LOP3, SHF, IADD and of their 1:1:1 mix (CUDA-event timed, ~10 ms). */
+int sw_measure_int_peak(double lane_ops_per_s[4]);
 
 /* Device properties the host side sizes grids with. */
 int sw_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);

@@ -365,8 +365,9 @@ sw_dev_batch* dev_upload(const sw_batch& b)
 
 // Optional host callback fired once kmers + nodes are final on the device (multi-GPU builds start
 // their node / k-mer exchange from it while the edge stage is still running).
-sw_nodes_ready_fn g_nodes_ready = nullptr;
-void* g_nodes_ready_user = nullptr;
+// Thread-local like the stream override and the arena: the hook belongs to the builder thread that set it.
+thread_local sw_nodes_ready_fn g_nodes_ready = nullptr;
+thread_local void* g_nodes_ready_user = nullptr;
 
 void fire_nodes_ready(sw_graph* g)
 {
@@ -542,6 +543,19 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
         cudaEvent_t* e; size_t n;
         ~EvGuard() { for (size_t i = 0; i < n; ++i) cudaEventDestroy(e[i]); }
     } ev_guard{ev, sizeof(ev) / sizeof(ev[0])};
+    // An exception after copies were enqueued must not hand pinned destinations back to the pool (or
+    // free device sources) while the copy engine still uses them: drain both streams before `g`, `d`
+    // and the events unwind (declared last, destroyed first).
+    struct DrainOnUnwind {
+        cudaStream_t a, b;
+        bool armed = true;
+        ~DrainOnUnwind()
+        {
+            if (!armed) return;
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+        }
+    } drain{cs, s};
 
     cudaEventRecord(e_begin, s);
     // the small tables go first: behind the bulk copies they would wait for the whole upload
@@ -634,6 +648,7 @@ sw_graph* build_pipelined(const sw_batch& b, uint32_t k, uint32_t w, sw_stage_ti
     cudaEventRecord(e_end, s);
     SW_CUDA(cudaStreamSynchronize(s));
     SW_CUDA(cudaStreamSynchronize(cs));
+    drain.armed = false;
     if (to_host) {
         g->on_host = true;
         g->dev = DevGraph();  // the device copies are no longer needed once the host arrays exist
@@ -705,6 +720,15 @@ int sw_device_info(int* sm, int* major, int* minor, size_t* hbm)
         if (major) *major = p.major;
         if (minor) *minor = p.minor;
         if (hbm) *hbm = p.totalGlobalMem;
+    });
+}
+
+int sw_measure_int_peak(double lane_ops_per_s[4])
+{
+    return guarded([&] {
+        init_device_once();
+        arena_reset();
+        measure_int_peak(lane_ops_per_s, lib_stream());
     });
 }
 
@@ -893,7 +917,11 @@ int sw_graph_penalty(sw_graph* g, const uint32_t* record_offsets, size_t n_offse
                                                           : g->record_offsets;
         const float ms = penalty_on_device(g->dev, offs, is_targets, n_assemblies, g->stream);
         if (kernel_ms) *kernel_ms = ms;
-        g->on_host = false;  // any earlier host copy of the nodes is stale now
+        // any earlier host copy of the nodes is stale now: back to the pool with its buffers
+        host_pool_put(g->h_kmers);
+        host_pool_put(g->h_nodes);
+        host_pool_put(g->h_edges);
+        g->on_host = false;
     });
 }
 

@@ -176,6 +176,10 @@ void dist_merge_nodes(const sw_node* recv_nodes, const uint64_t* node_counts, co
 void dist_merge_edges(const sw_edge* recv_edges, const uint64_t* edge_counts, uint32_t n_src, cudaStream_t s, DevGraph& out,
                       uint32_t* launches);
 
+// ---- diagnostics (diag.cu) -----------------------------------------------------------------------
+// lane-operations per second of dependent LOP3 / SHF / IADD chains and of their 1:1:1 mix
+void measure_int_peak(double out[4], cudaStream_t s);
+
 // ---- penalty ----------------------------------------------------------------------------------
 // Fills n_tar / n_neg / penalty of device-resident nodes; returns an error bit mask
 // (1: record_idx out of range, 2: record_idx decreasing, 4: node range outside kmers).

@@ -278,11 +278,13 @@ class CudaStages:
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
-               host_batch=None, overlap: bool = True, is_targets=None, class_totals=None):
+               host_batch=None, overlap: bool = True, is_targets=None, class_totals=None, inspect=None):
     """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle.
     With is_targets (bool array, the classes of THIS rank's assemblies) the graph comes back scored:
     every shard counts its own assemblies, the merge adds the counts, and the penalty is finished with
-    class_totals = (targets, non-targets) over all ranks (all-reduced here when not given)."""
+    class_totals = (targets, non-targets) over all ranks (all-reduced here when not given).
+    inspect(local, merged_handle), if given, runs after the merge while the shard's own graph is still alive
+    (verification hooks of bench.py)."""
     world = dist.get_world_size(group)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
@@ -311,8 +313,22 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
         ev[1].record()
     try:
         g = exchange_and_merge(stages, local, group, early=local.early)
-    finally:
+    except BaseException:
+        # slices of the local graph may still be on the wire (async all_to_all started from the hook):
+        # let them land before the buffers they read go back to the allocator
+        if local.early is not None:
+            for wk in local.early[2]:
+                try:
+                    wk.wait()
+                except Exception:   # noqa: BLE001 - the original error is the one to report
+                    pass
+        if timed:
+            torch.cuda.synchronize()
         stages.free_local(local)
+        raise
+    if inspect is not None:
+        inspect(local, g)
+    stages.free_local(local)
     if is_targets is not None:
         stages.finish_penalty(g, class_totals)
     if timed:
@@ -353,9 +369,114 @@ def gather_graph(parts_local, group=None):
     return concat_rank_graphs(gathered) if rank == 0 else None
 
 
+# ---- verification helpers (bench.py, tests): torch is the checker here, not the product -------------
+
+_C1, _C2 = -7046029254386353131, -4417276706812531889   # odd 64-bit constants (as signed)
+_MIN64 = -(1 << 63)
+
+
+def _mix(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    x = a * _C1 + b
+    x = x ^ (x >> 29)
+    return x * _C2
+
+
+def _as_i64(t: torch.Tensor, cols: int) -> torch.Tensor:
+    v = t.view(torch.int64)
+    return v.view(-1, cols) if cols > 1 else v
+
+
+def graph_checksums(kmers_u8: torch.Tensor, nodes_u8: torch.Tensor, edges_u8: torch.Tensor) -> dict:
+    """Order-independent checksums and ordering properties of a (shard or merged) graph held as flat byte
+    tensors on the device: the multiset of (node hash, record, pos) and of (first, second) x weight must
+    survive the exchange + merge; the arrays must come out sorted and tiled."""
+    out = {}
+    k = _as_i64(kmers_u8, 1)
+    n = _as_i64(nodes_u8, 5)
+    e = _as_i64(edges_u8, 3)
+    out["n_kmers"], out["n_nodes"], out["n_edges"] = int(k.numel()), int(n.shape[0]), int(e.shape[0])
+    if n.shape[0]:
+        h, start, stop = n[:, 0], n[:, 1], n[:, 2]
+        cnt = stop - start
+        per_kmer_hash = torch.repeat_interleave(h, cnt)
+        out["kmer_sum"] = int(_mix(per_kmer_hash, k).sum()) if per_kmer_hash.numel() == k.numel() else None
+        hs = h ^ _MIN64
+        out["nodes_sorted"] = bool((hs[1:] > hs[:-1]).all())
+        out["nodes_tile"] = bool(start[0] == 0 and stop[-1] == k.numel() and (start[1:] == stop[:-1]).all() and (cnt > 0).all())
+        brk = torch.zeros(k.numel(), dtype=torch.bool, device=k.device)
+        brk[start] = True
+        out["kmers_sorted_in_node"] = bool(((k[1:] > k[:-1]) | brk[1:]).all())
+        cls = n[:, 3]                       # n_tar (low 32 bits) | n_neg (high 32 bits)
+        out["n_tar_sum"] = int((cls & 0xFFFFFFFF).sum())
+        out["n_neg_sum"] = int(((cls >> 32) & 0xFFFFFFFF).sum())
+        out["first_hash"], out["last_hash"] = int(h[0]) & (2**64 - 1), int(h[-1]) & (2**64 - 1)
+    else:
+        out.update({"kmer_sum": 0, "nodes_sorted": True, "nodes_tile": k.numel() == 0, "kmers_sorted_in_node": True,
+                    "n_tar_sum": 0, "n_neg_sum": 0, "first_hash": None, "last_hash": None})
+    if e.shape[0]:
+        f, s2, wgt = e[:, 0], e[:, 1], e[:, 2]
+        out["edge_sum"] = int((_mix(f, s2) * wgt).sum())
+        fs, ss = f ^ _MIN64, s2 ^ _MIN64
+        out["edges_sorted"] = bool(((fs[1:] > fs[:-1]) | ((fs[1:] == fs[:-1]) & (ss[1:] > ss[:-1]))).all() and (fs <= ss).all())
+        out["weight_sum"] = int(wgt.sum())
+    else:
+        out.update({"edge_sum": 0, "edges_sorted": True, "weight_sum": 0})
+    return out
+
+
+def _wrap64(x: int) -> int:
+    return x & (2**64 - 1)
+
+
+def full_size_checks(stages: "CudaStages", dev, n_records: int, k: int, w: int, rec_base: int, is_t_local, totals) -> dict:
+    """One more full-size distributed step with the checksums of every shard's own graph (before the
+    exchange) and of every rank's merged hash range (after it), summed over the ranks."""
+    from . import _lib
+    L = stages.L
+    world, rank = dist.get_world_size(), dist.get_rank()
+    device = stages.device
+    got = {}
+
+    def inspect(local, g):
+        got["local"] = graph_checksums(local.kmers, local.nodes, local.edges)
+        pk, pn, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(L.sw_graph_device_ptrs(g, C.byref(pk), C.byref(pn), C.byref(pe)))
+        n_k, n_n, n_e = (L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES))
+        got["merged"] = graph_checksums(_view(pk.value, n_k * KMER_BYTES, device), _view(pn.value, n_n * NODE_BYTES, device),
+                                        _view(pe.value, n_e * EDGE_BYTES, device))
+
+    g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, is_targets=is_t_local, class_totals=totals,
+                   inspect=inspect)
+    L.sw_graph_free(g)
+    every = [None] * world
+    dist.all_gather_object(every, got)
+    if rank != 0:
+        return {}
+    loc, mer = [x["local"] for x in every], [x["merged"] for x in every]
+    tot = lambda rows, key: _wrap64(sum(r[key] for r in rows))   # noqa: E731
+    res = {
+        "kmers_conserved": sum(r["n_kmers"] for r in loc) == sum(r["n_kmers"] for r in mer),
+        "kmer_multiset_conserved": all(r["kmer_sum"] is not None for r in loc + mer) and tot(loc, "kmer_sum") == tot(mer, "kmer_sum"),
+        "edge_weight_multiset_conserved": tot(loc, "edge_sum") == tot(mer, "edge_sum") and
+                                          sum(r["weight_sum"] for r in loc) == sum(r["weight_sum"] for r in mer),
+        "class_counts_conserved": sum(r["n_tar_sum"] for r in loc) == sum(r["n_tar_sum"] for r in mer) and
+                                  sum(r["n_neg_sum"] for r in loc) == sum(r["n_neg_sum"] for r in mer),
+        "sorted_and_tiled_on_every_rank": all(r["nodes_sorted"] and r["nodes_tile"] and r["kmers_sorted_in_node"] and r["edges_sorted"]
+                                              for r in mer),
+        "rank_ranges_ascending": all(a["last_hash"] is None or b["first_hash"] is None or a["last_hash"] < b["first_hash"]
+                                     for a, b in zip(mer[:-1], mer[1:])),
+        "n_kmers": sum(r["n_kmers"] for r in mer), "n_nodes": sum(r["n_nodes"] for r in mer), "n_edges": sum(r["n_edges"] for r in mer),
+    }
+    res["all_ok"] = all(v for k2, v in res.items() if not k2.startswith("n_"))
+    return res
+
+
 # ---- bench driver (bench.py --gpus N under torchrun) ----------------------------------------------
 
 def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int, warmup: int, sampler_cls) -> dict:
+    import os
+    import time
+
     from . import _lib
     device = torch.device("cuda", torch.cuda.current_device())
     stages = CudaStages(L, device)
@@ -368,10 +489,7 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     # classes of the assemblies (input metadata): this rank's slice and the two class sizes
     n_asm_local = spec.n_genomes // world
     is_t = np.ascontiguousarray(np.arange(spec.n_genomes) < spec.n_targets, dtype=np.bool_)
-
-    import os
     overlap = os.environ.get("SEQWIN_DIST_OVERLAP", "1") != "0"   # A/B switch for profiles/
-
     is_t_local = np.ascontiguousarray(is_t[rank * n_asm_local:(rank + 1) * n_asm_local])
     totals = (int(is_t.sum()), int(len(is_t) - is_t.sum()))   # class sizes are input metadata too
 
@@ -400,7 +518,7 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         times.append(float(t))
         d = stages.times.as_dict()
-        d["n_kmers_local"] = d["n_kmers"]
+        d["n_kmers_local"], d["n_nodes_local"], d["n_edges_local"] = d["n_kmers"], d["n_nodes"], d["n_edges"]
         d["local_build_ms"] = d["total_ms"]
         d["total_ms"] = float(t)
         d["total_launches"] = d["total_launches"] + stages.merge_launches
@@ -410,10 +528,24 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         d["phase_merge_ms"] = stages._merge_events[0].elapsed_time(stages._merge_events[1])
         stage_dicts.append(d)
     clocks = sampler.stop()
+
+    # the same shard without the exchange: what one GPU does on its own with this much input (the
+    # equal-work reference point for the scaling figures; scored like the distributed step)
+    st = _lib.StageTimes()
+    single = []
+    for i in range(1 + min(steps, 5)):
+        g = C.c_void_p()
+        _lib.check(L.sw_dev_build_ex(dev, k, w, rec_base, is_t_local.ctypes.data, len(is_t_local), C.byref(g), C.byref(st)))
+        L.sw_graph_free(g)
+        if i:
+            single.append(st.total_ms)
+    sg = torch.tensor([float(np.mean(single))], device=device)
+    dist.all_reduce(sg, op=dist.ReduceOp.MAX)
+
+    checks = full_size_checks(stages, dev, n_records, k, w, rec_base, is_t_local, totals)
     L.sw_dev_batch_free(dev)
 
     # end to end: pinned host batch -> H2D -> distributed build -> D2H of this rank's range
-    import time
     e2e = []
     for i in range(max(1, warmup // 2) + steps):
         dist.barrier()
@@ -421,13 +553,19 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         t0 = time.perf_counter()
         g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch, overlap=overlap,
                        is_targets=is_t_local, class_totals=totals)
+        t1 = time.perf_counter()
         _lib.check(L.sw_graph_fetch(g))     # this rank's hash range -> pinned host memory
+        t2 = time.perf_counter()
         L.sw_graph_free(g)
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if i >= max(1, warmup // 2):
-            e2e.append((float(t), stage_dicts[-1]))
+            d = stages.times.as_dict()    # this step's own local-build stages (H2D included)
+            d["local_build_ms"] = d["total_ms"]
+            d["total_ms"] = float(t) * 1e3
+            d["fetch_ms"] = (t2 - t1) * 1e3
+            e2e.append((float(t), d))
 
     tot = torch.tensor([n_bases_local] + sizes, dtype=torch.int64, device=device)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -435,4 +573,96 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     for d in stage_dicts:
         d["n_kmers"], d["n_nodes"], d["n_edges"] = n_k, n_n, n_e
     L.sw_set_stream(None)
-    return {"stages": stage_dicts, "clocks": clocks, "e2e_runs": e2e, "n_bases_total": n_bases_total}
+    return {"stages": stage_dicts, "clocks": clocks, "e2e_runs": e2e, "n_bases_total": n_bases_total,
+            "single_gpu": {"ms_per_step": float(sg), "gbp_s_per_gpu": n_bases_local / (float(sg) * 1e-3) / 1e9,
+                           "what": "the same shard built and scored by one GPU without the exchange (slowest rank)"},
+            "full_size_checks": checks}
+
+
+def bench_parity(L, parity_batch, ss, rank: int, world: int, per_gpu: int, per_rank: int, k: int, w: int, bench) -> dict | None:
+    """Bit-exactness of the NCCL path on hardware: the first `per_rank` genomes of every shard go through
+    the same distributed build (local build, all-to-all of hash ranges, owner-side merge, scoring); rank 0
+    runs the unmodified reference on the same genomes from FASTA and compares every rank's piece of every
+    array.  Rank 0 also builds the subset on its own GPU from the FASTA files (single-GPU == multi-GPU)."""
+    import hashlib
+    import shutil
+    import time
+
+    from . import _lib
+    from ._core import NODE_DTYPE
+    device = torch.device("cuda", torch.cuda.current_device())
+    stages = CudaStages(L, device)
+    per_rank = min(per_rank, per_gpu)
+    mine = list(range(rank * per_gpu, rank * per_gpu + per_rank))
+    is_t_local = np.ascontiguousarray(ss.is_targets[mine], dtype=np.bool_)
+    n_records = L.sw_batch_n_records(parity_batch)
+    dev = C.c_void_p()
+    _lib.check(L.sw_dev_upload(parity_batch, C.byref(dev)))
+    g = dist_build(stages, dev, n_records, k, w, is_targets=is_t_local)
+    kmers, nodes, edges = export_graph(L, g)
+    L.sw_graph_free(g)
+    L.sw_dev_batch_free(dev)
+    L.sw_set_stream(None)
+    counts = [None] * world
+    dist.all_gather_object(counts, (len(kmers), len(nodes), len(edges)))
+    kbase = sum(c[0] for c in counts[:rank])
+    nodes["start"] += np.uintp(kbase)
+    nodes["stop"] += np.uintp(kbase)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).data).hexdigest()   # noqa: E731
+    digests = [None] * world
+    dist.all_gather_object(digests, (sha(kmers), sha(nodes), sha(edges)))
+
+    # FASTA of the subset: every rank writes its own genomes into one tmpfs directory
+    box = [str(bench.shm_dir("seqwin_b200_parity_"))] if rank == 0 else [None]
+    dist.broadcast_object_list(box, src=0)
+    from pathlib import Path
+    d = Path(box[0])
+    nb_local = bench.write_genomes(ss, mine, d, 4)
+    nb = torch.tensor([nb_local], dtype=torch.int64, device=device)
+    dist.all_reduce(nb)
+    dist.barrier()
+    res = None
+    if rank == 0:
+        try:
+            subset = [g2 for r in range(world) for g2 in range(r * per_gpu, r * per_gpu + per_rank)]
+            paths = [bench.fasta_path(d, g2) for g2 in subset]
+            is_t = np.ascontiguousarray(ss.is_targets[subset], dtype=np.bool_)
+            ref = bench.run_reference(paths, is_t, k, w, steps=1, warmup=0, keep_graph=True)
+            rk, rn, re_, ro = ref["graph"]
+            ok, ko, no, eo = True, 0, 0, 0
+            pieces = []
+            for r in range(world):
+                ck, cn, ce = counts[r]
+                same = (sha(rk[ko:ko + ck]), sha(rn[no:no + cn]), sha(re_[eo:eo + ce])) == tuple(digests[r])
+                pieces.append(bool(same))
+                ok = ok and same
+                ko, no, eo = ko + ck, no + cn, eo + ce
+            ok = ok and (ko, no, eo) == (len(rk), len(rn), len(re_))
+            # the same FASTA files through the drop-in entry point on one GPU
+            from .graph import KmerGraph, _get_penalty
+            t0 = time.perf_counter()
+            og = KmerGraph(paths, k, w, n_cpu=os_cpu_count())
+            _get_penalty(og.kmers, og.nodes, og.record_offsets, is_t)
+            ours_s = time.perf_counter() - t0
+            single_ok = bool(np.array_equal(og.kmers, rk) and np.array_equal(og.nodes, rn) and np.array_equal(og.edges, re_)
+                             and np.array_equal(og.record_offsets, ro))
+            res = {"bit_exact": bool(ok and single_ok), "nccl_pieces_match_reference": pieces,
+                   "single_gpu_from_fasta_matches_reference": single_ok, "against": ref["kind"],
+                   "what": f"{len(subset)} genomes ({int(nb) / 1e6:.0f} Mbp; the first {per_rank} of every shard) through the same "
+                           f"{world}-rank NCCL exchange + merge + scoring; every rank's slice of kmers / nodes / edges compared by "
+                           "SHA-256 with the reference's arrays built from FASTA",
+                   "graph": {"n_kmers": len(rk), "n_nodes": len(rn), "n_edges": len(re_)},
+                   "sha256": {"kmers": sha(rk), "nodes": sha(rn), "edges": sha(re_)},
+                   "cpu_baseline": {"value": int(nb) / ref["seconds"] / 1e9, "unit": "Gbp/s", "cores": ref["cores"], "kind": ref["kind"],
+                                    "sample": f"{len(subset)} of the workload's genomes ({int(nb) / 1e6:.0f} Mbp), plain FASTA on tmpfs, "
+                                              "build + get_penalty, one pass",
+                                    "ours_same_input_from_fasta_gbps": int(nb) / ours_s / 1e9}}
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    dist.barrier()
+    return res
+
+
+def os_cpu_count() -> int:
+    import os
+    return os.cpu_count() or 8

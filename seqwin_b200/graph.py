@@ -66,8 +66,12 @@ def penalty_threshold(count_sums, n_tar: int, n_neg: int, stringency: int = 5, p
     ``sw_graph_count_sums`` on a device-resident graph, or ``count_sums(nodes)`` for a numpy array.
     Returns ``(penalty_th, e_absence_tar, e_presence_neg)``."""
     s_t, s_tt, s_tn = (int(x) for x in count_sums)
-    e_absence_tar = 1.0 - s_tt / (n_tar * s_t)
-    e_presence_neg = s_tn / (n_neg * s_t)
+    # The reference evaluates np.sum(frac * n_tar) / np.sum(n_tar) in float64; the exact integer sums used
+    # here agree with it to the last few ulps (not bit for bit).  Empty denominators give nan / inf like
+    # numpy does there (with a warning), not an exception.
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e_absence_tar = float(1.0 - np.float64(s_tt) / np.float64(n_tar * s_t))
+        e_presence_neg = float(np.float64(s_tn) / np.float64(n_neg * s_t))
     penalty_th = (1 - stringency / 10) * (e_absence_tar * e_presence_neg) ** 0.5
     return min(penalty_th, penalty_th_cap), e_absence_tar, e_presence_neg
 

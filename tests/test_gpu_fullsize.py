@@ -86,3 +86,39 @@ def test_full_size_properties():
     assert np.array_equal(nodes["penalty"], np.sqrt((1.0 - ft) * (1.0 - ft) + fn * fn))
     # every edge endpoint is a node and weights count assemblies
     assert edges["weight"].max() <= 500
+
+
+def test_full_size_matches_reference(tmp_path_factory):
+    """The whole C2 workload (500 genomes, 2.5 Gbp) as FASTA files: the drop-in entry points
+    (KmerGraph + _get_penalty on the GPU) against the UNMODIFIED reference extension (oracle/_ref, all host
+    cores) -- kmers, scored nodes, edges and record offsets compared bit for bit, as the reference's own
+    tests/smoke/test_outputs.py:22-58 compares its graph.npz."""
+    import os
+    import shutil
+
+    import bench
+    from seqwin_b200.graph import KmerGraph, _get_penalty
+
+    ref = O.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref (the compiled reference) is not present")
+    spec = SynthSpec(n_genomes=500, n_targets=100, genome_len=5_000_000, n_contigs=50, seed=42)
+    ss = SynthSet(spec)
+    d = bench.shm_dir("seqwin_b200_fullsize_")
+    try:
+        n_bases = bench.write_genomes(ss, range(spec.n_genomes), d, 8)
+        assert n_bases == spec.n_genomes * spec.genome_len
+        paths = [str(bench.fasta_path(d, g)) for g in range(spec.n_genomes)]
+        is_t = np.ascontiguousarray(ss.is_targets, dtype=np.bool_)
+        cores = os.cpu_count() or 8
+        g = KmerGraph(paths, K, W, n_cpu=cores)
+        _get_penalty(g.kmers, g.nodes, g.record_offsets, is_t)
+        rk, rn, re_, ro, rids = ref._build_native(paths, K, W, cores, False)
+        ref._get_penalty_native(rk, rn, ro, is_t, cores)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    assert len(rk) > 24_000_000
+    assert np.array_equal(g.record_offsets, ro) and g.record_ids == rids
+    for name, ours, theirs in (("kmers", g.kmers, rk), ("nodes", g.nodes, rn), ("edges", g.edges, re_)):
+        assert ours.dtype == theirs.dtype and ours.shape == theirs.shape, name
+        assert digest(ours) == digest(theirs), f"{name} differ from the reference at full size"

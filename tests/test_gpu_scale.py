@@ -51,3 +51,31 @@ def test_properties_and_idempotence(big_set):
     assert np.array_equal(c.nodes["hash"], a.nodes["hash"])
     assert np.array_equal(c.edges, a.edges)
     assert np.array_equal(c.nodes["stop"] - c.nodes["start"], a.nodes["stop"] - a.nodes["start"])
+
+
+def test_chunked_batch_equals_whole_batch():
+    """bench.build_batch packs the synthetic genomes chunk by chunk and concatenates the packed pieces
+    (sw_batch_concat); the graph must be the one of the batch packed in one go."""
+    import ctypes as C
+
+    import bench
+    from seqwin_b200 import _lib
+    from seqwin_b200.dist import export_graph
+    from seqwin_b200.synth import SynthSet
+    from tests.helpers import digest
+    L = _lib.lib()
+    spec = SynthSpec(n_genomes=11, n_targets=3, genome_len=200_000, n_contigs=6, seed=17, n_runs_every=4)
+    ss = SynthSet(spec)
+    out = []
+    for chunk in (3, 100):
+        b = bench.build_batch(ss, range(spec.n_genomes), 4, chunk=chunk)
+        g = C.c_void_p()
+        _lib.check(L.sw_build_from_batch(b, 21, 50, C.byref(g), None))
+        out.append([digest(a) for a in export_graph(L, g)])
+        L.sw_graph_free(g)
+        L.sw_batch_free(b)
+    whole, first = bench.build_batch(ss, range(spec.n_genomes), 4, chunk=4, keep_first=True)
+    assert L.sw_batch_n_records(first) == 4 * 6 and L.sw_batch_n_records(whole) == 11 * 6
+    L.sw_batch_free(whole)
+    L.sw_batch_free(first)
+    assert out[0] == out[1]

@@ -137,3 +137,25 @@ def test_kw_limits(have_gpu, fixture_paths):
     for k, w in [(2, 10), (70000, 10), (17, 0)]:
         with pytest.raises(RuntimeError):
             KmerGraph(fixture_paths, k, w)
+
+
+def test_batch_concat_tables(edge_paths, fixture_paths):
+    """sw_batch_concat: the concatenation of two packed batches has the tables of the batch parsed in one go."""
+    L = _lib.lib()
+    paths = [str(p) for p in edge_paths[0]] + [str(p) for p in fixture_paths]
+    whole = _batch_from_fasta(paths)
+    a, b = _batch_from_fasta(paths[:4]), _batch_from_fasta(paths[4:])
+    cat = C.c_void_p()
+    arr = (C.c_void_p * 2)(a.value, b.value)
+    _lib.check(L.sw_batch_concat(arr, 2, C.byref(cat)))
+    try:
+        for fn in (L.sw_batch_n_bases, L.sw_batch_n_records, L.sw_batch_packed_bytes):
+            assert fn(cat) == fn(whole)
+        n = len(paths) + 1
+        o1, o2 = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        _lib.check(L.sw_batch_record_offsets(cat, o1.ctypes.data, n))
+        _lib.check(L.sw_batch_record_offsets(whole, o2.ctypes.data, n))
+        assert np.array_equal(o1, o2)
+    finally:
+        for x in (whole, a, b, cat):
+            L.sw_batch_free(x)
