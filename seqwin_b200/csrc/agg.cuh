@@ -1,0 +1,506 @@
+// agg.cuh -- bucketed group-by: the aggregation kernels of the graph stage.
+//
+// The minimizer stream (h1, pos | record << 32) and the adjacent-pair records (rank pair, assembly) are
+// both aggregated the same way: a STABLE partition on the top P bits of the key (radix.cu, 1-3 passes)
+// leaves every bucket holding a few hundred items in input order; one CTA then groups a bucket by key in
+// shared memory -- an open-addressing table of its distinct keys -- and
+//
+//   group_count_kernel   counts the items of every distinct key and writes the bucket's distinct keys in
+//                        ascending order (rank by counting) next to their sizes,
+//   group_place_kernel   after an exclusive scan of the per-bucket distinct counts: moves every item to its
+//                        final place -- group offset + stable rank inside the group, so a node's k-mers stay
+//                        in (record, pos) order and an edge's records in assembly order --, counts the
+//                        distinct assemblies of every group (by class for nodes: get_penalty,
+//                        cpp/src/seqwin/filter.cpp:92-136; once for edges: the edge weight,
+//                        cpp/src/seqwin/build.cpp:177-189) and writes the nodes / edges.
+//
+// This is what build_worker + merge_thread_graphs do with two hash maps and a CPU radix sort
+// (cpp/src/seqwin/build.cpp:152-241, build_internals.cpp:159-291); the data is touched twice after the
+// partition instead of once per radix digit.  A bucket never holds more distinct NODE keys than the table
+// takes (P is chosen from the item count and h1 is a 64-bit mix); an EDGE bucket can -- a hub node with
+// thousands of distinct neighbours -- and is then marked and handed to the sort-based path (graph.cu).
+//
+// The file compiles under nvcc and, through tests/emul/cuda_emul.h, as plain C++ (CPU tests).
+#pragma once
+
+#include <cstdint>
+
+#include "common.h"
+
+namespace sw {
+namespace agg {
+
+constexpr int kNT = 256;
+constexpr int kNW = kNT / 32;
+constexpr int kSlotBits = 10;
+constexpr int kSlots = 1 << kSlotBits;      // open-addressing table of one bucket's distinct keys
+constexpr int kMaxDistinct = 768;            // distinct keys a bucket may hold (table load <= 0.75)
+constexpr int kItems = 8;                    // items per thread and placement chunk
+constexpr int kChunk = kNT * kItems;
+static_assert(kMaxDistinct == 3 * kNT, "group_place_kernel scans 3 groups per thread");
+constexpr unsigned long long kEmptyKey = ~0ull;   // in-bucket keys have their top P >= 1 bits cleared
+constexpr uint32_t kOverflow = 0xFFFFFFFFu;       // bucket_d value of a bucket left to the sort-based path
+
+// start[b] = first item whose key >> shift is >= b, for b in [0, n_buckets]  (keys ascending in those bits)
+__global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift,
+                                                            uint64_t n_buckets, uint32_t* __restrict__ start)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += stride) {
+        const uint64_t lo = j ? (keys[j - 1] >> shift) + 1 : 0;
+        const uint64_t hi = j < n ? (keys[j] >> shift) : n_buckets;
+        for (uint64_t b = lo; b <= hi; ++b) start[b] = (uint32_t)j;
+    }
+}
+
+__device__ __forceinline__ uint32_t first_slot(uint64_t kb, int hshift) { return (uint32_t)(kb >> hshift) & (kSlots - 1); }
+
+// ---- pass 1: distinct keys of every bucket, ascending, with their sizes ---------------------------------
+// grp_keys / grp_cnt are indexed like the items: bucket b owns [start[b], start[b] + D_b) of them.
+__global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ start,
+                                                          int key_bits, uint32_t max_distinct, uint64_t* __restrict__ grp_keys,
+                                                          uint32_t* __restrict__ grp_cnt, uint32_t* __restrict__ bucket_d)
+{
+    __shared__ unsigned long long t_key[kSlots];
+    __shared__ uint32_t t_cnt[kSlots];
+    __shared__ unsigned long long dk[kMaxDistinct];
+    __shared__ uint32_t dc[kMaxDistinct];
+    __shared__ uint32_t s_n, s_m;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x;
+    const uint32_t bs = start[b], n = start[b + 1] - bs;
+    if (n == 0) {
+        if (tid == 0) bucket_d[b] = 0;
+        return;
+    }
+    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) {
+        t_key[s] = kEmptyKey;
+        t_cnt[s] = 0;
+    }
+    if (tid == 0) { s_n = 0; s_m = 0; }
+    __syncthreads();
+    const uint64_t lowmask = (1ull << key_bits) - 1;
+    const int hshift = key_bits > kSlotBits ? key_bits - kSlotBits : 0;
+    for (uint32_t i = tid; i < n; i += kNT) {
+        const unsigned long long kb = keys[bs + i] & lowmask;
+        uint32_t s = first_slot(kb, hshift);
+        for (int probes = 0;; ++probes) {
+            if (probes == kSlots || *(volatile uint32_t*)&s_n > max_distinct) {   // table (about to be) full: the bucket goes to the other path
+                atomicAdd(&s_n, (uint32_t)kSlots);
+                break;
+            }
+            const unsigned long long prev = atomicCAS(&t_key[s], kEmptyKey, kb);
+            if (prev == kEmptyKey) atomicAdd(&s_n, 1u);
+            if (prev == kEmptyKey || prev == kb) {
+                atomicAdd(&t_cnt[s], 1u);
+                break;
+            }
+            s = (s + 1) & (kSlots - 1);
+        }
+    }
+    __syncthreads();
+    const uint32_t D = s_n;
+    if (D > max_distinct) {
+        if (tid == 0) bucket_d[b] = kOverflow;
+        return;
+    }
+    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) {
+        if (t_key[s] != kEmptyKey) {
+            const uint32_t i = atomicAdd(&s_m, 1u);
+            dk[i] = t_key[s];
+            dc[i] = t_cnt[s];
+        }
+    }
+    __syncthreads();
+    const uint64_t prefix = key_bits < 64 ? (uint64_t)b << key_bits : 0;
+    for (uint32_t i = tid; i < D; i += kNT) {
+        const unsigned long long k = dk[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < D; ++j) r += dk[j] < k ? 1u : 0u;
+        grp_keys[bs + r] = k | prefix;
+        grp_cnt[bs + r] = dc[i];
+    }
+    if (tid == 0) bucket_d[b] = D;
+}
+
+// bucket_d -> 64-bit counts for the scans: distinct keys of the buckets grouped here (0 for the others), and
+// the item counts of the buckets that were not (tot[0] += such buckets, tot[1] += their items)
+__global__ void __launch_bounds__(256) bucket_counts_kernel(const uint32_t* __restrict__ bucket_d, const uint32_t* __restrict__ start,
+                                                            uint64_t n_buckets, unsigned long long* __restrict__ d64,
+                                                            unsigned long long* __restrict__ ovf_items64, unsigned long long* tot)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += stride) {
+        const uint32_t d = bucket_d[b];
+        const bool ovf = d == kOverflow;
+        d64[b] = ovf ? 0ull : (unsigned long long)d;
+        if (ovf_items64) ovf_items64[b] = ovf ? (unsigned long long)(start[b + 1] - start[b]) : 0ull;
+        if (ovf) {
+            atomicAdd(&tot[0], 1ull);
+            atomicAdd(&tot[1], (unsigned long long)(start[b + 1] - start[b]));
+        }
+    }
+}
+
+// ---- pass 2: placement, distinct-assembly counts, output ---------------------------------------------------
+struct NodeOut {
+    static constexpr bool kNodes = true;
+    using Val = unsigned long long;                 // pos | record << 32 == sw_kmer
+    const Val* vals;                                // partitioned like the keys
+    Val* placed;                                    // kmers (final order)
+    sw_node* nodes;
+    uint64_t* node_hash;                            // compact copy of nodes[].hash for the edge stage
+    const uint32_t* rec_asm;                        // [records] assembly of a record   (scoring only)
+    uint32_t rec_base;
+    const uint8_t* is_target;                       // [assemblies]                      (scoring only)
+    double inv_t, inv_n;
+    int counts_only;                                // a shard of a multi-GPU build: penalty left at 0
+};
+struct EdgeOut {
+    static constexpr bool kNodes = false;
+    using Val = uint32_t;                           // assembly of the adjacent-pair record
+    const Val* vals;
+    Val* placed;                                    // scratch, same size as the records
+    sw_edge* edges;
+    const uint64_t* node_hash;
+    int rank_bits;                                  // key = first << (64 - rank_bits) | second << (64 - 2 rank_bits)
+};
+
+struct PlaceArgs {
+    const uint64_t* keys;                // partitioned keys
+    const uint32_t* start;               // bucket bounds
+    int key_bits;                        // 64 - P
+    const uint64_t* grp_keys;            // from group_count_kernel
+    const uint32_t* grp_cnt;
+    const uint32_t* bucket_d;
+    const unsigned long long* grp_base;  // exclusive scan of the distinct counts: first output group of a bucket
+};
+
+__device__ __forceinline__ uint32_t assembly_of(const NodeOut& o, unsigned long long v)
+{
+    return o.rec_asm[(uint32_t)(v >> 32) - o.rec_base];
+}
+__device__ __forceinline__ uint32_t assembly_of(const EdgeOut&, uint32_t v) { return v; }
+__device__ __forceinline__ bool is_class_a(const NodeOut& o, uint32_t as) { return o.is_target[as] != 0; }
+__device__ __forceinline__ bool is_class_a(const EdgeOut&, uint32_t) { return true; }
+
+// smallest P >= 1 with n / 2^P <= per_bucket
+inline int partition_bits(uint64_t n, uint32_t per_bucket)
+{
+    int p = 1;
+    while (p < 40 && (n >> p) > per_bucket) ++p;
+    return p;
+}
+
+__device__ __forceinline__ void write_group(const NodeOut& no, unsigned long long key, unsigned long long idx, uint64_t start,
+                                            uint64_t stop, uint32_t ca, uint32_t cb, bool counted)
+{
+    sw_node nd;
+    nd.hash = key;
+    nd.start = start;
+    nd.stop = stop;
+    nd.n_tar = ca;
+    nd.n_neg = cb;
+    nd.penalty = 0.0;
+    if (counted && !no.counts_only) {
+        // filter.cpp:132-134 evaluated without fused multiply-add (x86-64 baseline)
+        const double ft = __dmul_rn((double)nd.n_tar, no.inv_t);
+        const double fn = __dmul_rn((double)nd.n_neg, no.inv_n);
+        const double d1 = __dsub_rn(1.0, ft);
+        nd.penalty = __dsqrt_rn(__dadd_rn(__dmul_rn(d1, d1), __dmul_rn(fn, fn)));
+    }
+    no.nodes[idx] = nd;
+    no.node_hash[idx] = key;
+}
+__device__ __forceinline__ void write_group(const EdgeOut& eo, unsigned long long key, unsigned long long idx, uint64_t, uint64_t,
+                                            uint32_t ca, uint32_t, bool)
+{
+    sw_edge e;
+    e.first = eo.node_hash[key >> (64 - eo.rank_bits)];
+    e.second = eo.node_hash[(key >> (64 - 2 * eo.rank_bits)) & ((1ull << eo.rank_bits) - 1)];
+    e.weight = ca;
+    eo.edges[idx] = e;
+}
+
+template <class Out, bool COUNT>
+__global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
+{
+    __shared__ unsigned long long t_key[kSlots];
+    __shared__ uint16_t t_rank[kSlots];
+    __shared__ uint32_t goff[kMaxDistinct + 1];     // first item of every group, relative to the bucket
+    __shared__ uint32_t cursor[kMaxDistinct];       // items of the group placed by earlier chunks
+    __shared__ uint32_t cbase[kMaxDistinct];        // cursor at the start of the current chunk
+    __shared__ uint16_t whist[kNW][kMaxDistinct];   // per chunk: items of the group held by each warp -> exclusive over warps
+    __shared__ uint32_t c_a[kMaxDistinct], c_b[kMaxDistinct];
+    __shared__ uint32_t s_warp[kNW];
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t bs = a.start[b], n = a.start[b + 1] - bs;
+    const uint32_t D = a.bucket_d[b];
+    if (n == 0 || D == kOverflow) return;
+    const unsigned long long base = a.grp_base[b];
+    const uint64_t lowmask = (1ull << a.key_bits) - 1;
+    const int hshift = a.key_bits > kSlotBits ? a.key_bits - kSlotBits : 0;
+
+    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) t_key[s] = kEmptyKey;
+    __syncthreads();
+    // table: key -> rank (keys are distinct); group sizes -> exclusive scan
+    uint32_t cnt[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const uint32_t r = tid * 3 + q;     // 3 consecutive groups per thread: kMaxDistinct = 3 * kNT
+        cnt[q] = 0;
+        if (r < D) {
+            const unsigned long long kb = a.grp_keys[bs + r] & lowmask;
+            uint32_t s = first_slot(kb, hshift);
+            while (atomicCAS(&t_key[s], kEmptyKey, kb) != kEmptyKey) s = (s + 1) & (kSlots - 1);
+            t_rank[s] = (uint16_t)r;
+            cnt[q] = a.grp_cnt[bs + r];
+        }
+    }
+    {
+        const uint32_t sum3 = cnt[0] + cnt[1] + cnt[2];
+        uint32_t inc = sum3;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t run = inc - sum3;
+#pragma unroll
+        for (int w = 0; w < kNW; ++w)
+            if ((uint32_t)w < wid) run += s_warp[w];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const uint32_t r = tid * 3 + q;
+            if (r < D) {
+                goff[r] = run;
+                cursor[r] = run;
+                c_a[r] = 0;
+                c_b[r] = 0;
+            }
+            run += cnt[q];
+        }
+        if (tid == 0) goff[D] = n;
+    }
+    __syncthreads();
+
+    // placement, one chunk of kChunk items at a time; inside a chunk warp w owns a contiguous piece
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t c0 = 0; c0 < n; c0 += kChunk) {
+        const uint32_t nc = n - c0 < (uint32_t)kChunk ? n - c0 : (uint32_t)kChunk;
+        const uint32_t per_warp = (((nc + kNW - 1) / kNW) + 31u) & ~31u;
+        const uint32_t w_lo = wid * per_warp;
+        const uint32_t w_hi = w_lo + per_warp < nc ? w_lo + per_warp : nc;
+        for (uint32_t r = lane; r < D; r += 32) whist[wid][r] = 0;
+        __syncwarp();
+        uint32_t rk[kItems], lr[kItems];
+#pragma unroll
+        for (int q = 0; q < kItems; ++q) {
+            rk[q] = 0xFFFFFFFFu;
+            lr[q] = 0;
+            if ((uint32_t)q * 32 < per_warp) {    // warp-uniform
+                const uint32_t i = w_lo + q * 32 + lane;
+                if (i < w_hi) {
+                    const unsigned long long kb = a.keys[bs + c0 + i] & lowmask;
+                    uint32_t s = first_slot(kb, hshift);
+                    while (t_key[s] != kb) s = (s + 1) & (kSlots - 1);
+                    rk[q] = t_rank[s];
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, rk[q]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if ((int)lane == leader && rk[q] != 0xFFFFFFFFu) {
+                    old = whist[wid][rk[q]];
+                    whist[wid][rk[q]] = (uint16_t)(old + __popc(peers));
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                lr[q] = old + __popc(peers & lt_mask);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = tid; r < D; r += kNT) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < kNW; ++w) {
+                const uint32_t t = whist[w][r];
+                whist[w][r] = (uint16_t)run;
+                run += t;
+            }
+            cbase[r] = cursor[r];
+            cursor[r] += run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kItems; ++q) {
+            if (rk[q] != 0xFFFFFFFFu) {
+                const uint32_t i = w_lo + q * 32 + lane;
+                const uint32_t pos = cbase[rk[q]] + whist[wid][rk[q]] + lr[q];
+                o.placed[bs + pos] = o.vals[bs + c0 + i];
+            }
+        }
+        __syncthreads();
+    }
+
+    // distinct assemblies per group: the items of a group are in input order, hence sorted by assembly
+    if (COUNT) {
+        const uint32_t n_up = (n + 31u) & ~31u;
+        for (uint32_t j0 = wid * 32; j0 < n_up; j0 += kNT) {
+            const uint32_t j = j0 + lane;
+            const bool valid = j < n;
+            uint32_t as = 0xFFFFFFFFu, r = 0xFFFFFFFFu;
+            if (valid) {
+                as = assembly_of(o, o.placed[bs + j]);
+                uint32_t lo = 0, hi = D;      // largest r with goff[r] <= j
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (goff[mid] <= j) lo = mid; else hi = mid;
+                }
+                r = lo;
+            }
+            uint32_t prev = __shfl_up_sync(0xffffffffu, as, 1);
+            if (lane == 0) prev = (valid && j > 0) ? assembly_of(o, o.placed[bs + j - 1]) : 0xFFFFFFFFu;
+            const bool fresh = valid && (j == goff[r] || as != prev);
+            const bool cls_a = fresh ? is_class_a(o, as) : true;
+            const uint32_t peers = __match_any_sync(0xffffffffu, r);
+            const uint32_t fa = __ballot_sync(0xffffffffu, fresh && cls_a) & peers;
+            const uint32_t fb = __ballot_sync(0xffffffffu, fresh && !cls_a) & peers;
+            if (valid && (int)lane == __ffs(peers) - 1) {
+                if (fa) atomicAdd(&c_a[r], (uint32_t)__popc(fa));
+                if (fb) atomicAdd(&c_b[r], (uint32_t)__popc(fb));
+            }
+        }
+        __syncthreads();
+    }
+
+    for (uint32_t r = tid; r < D; r += kNT) write_group(o, a.grp_keys[bs + r], base + r, (uint64_t)bs + goff[r], (uint64_t)bs + goff[r + 1],
+                                                       COUNT ? c_a[r] : 0u, COUNT ? c_b[r] : 0u, COUNT);
+}
+// ---- adjacent-pair records with node ranks looked up through a bucket table ----------------------------------
+
+// rank of hash h among the sorted node hashes: ftable[h >> fshift] = first node of that fine bucket
+__device__ __forceinline__ uint32_t rank_of_hash(uint64_t h, const uint64_t* __restrict__ node_hash,
+                                                 const uint32_t* __restrict__ ftable, int fshift)
+{
+    uint32_t i = ftable[h >> fshift];
+    while (node_hash[i] != h) ++i;
+    return i;
+}
+
+constexpr int kEmitItems = kNT * 8;
+
+// One record per pair of stream-adjacent minimizers of one record: key = (min rank, max rank) left-aligned,
+// value = assembly.  block_off[blockIdx.x] = records emitted by earlier blocks (edge_count_kernel + scan).
+__global__ void __launch_bounds__(kNT) edge_emit_kernel(const uint64_t* __restrict__ stream_keys, const uint64_t* __restrict__ stream_vals,
+                                                        uint64_t n, const uint64_t* __restrict__ node_hash,
+                                                        const uint32_t* __restrict__ ftable, int fshift,
+                                                        const uint32_t* __restrict__ rec_asm, uint32_t rec_base,
+                                                        const unsigned long long* __restrict__ block_off, int rank_bits,
+                                                        uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm)
+{
+    __shared__ uint32_t s_rank[kEmitItems + 1];
+    __shared__ uint32_t s_cnt[8][kNW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kEmitItems;
+    for (uint32_t t = tid; t <= (uint32_t)kEmitItems; t += kNT) {
+        const uint64_t i = base + t;
+        if (i < n) s_rank[t] = rank_of_hash(stream_keys[i], node_hash, ftable, fshift);
+    }
+    bool flag[8];
+    uint32_t rec[8], prefix[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint64_t i = base + (uint64_t)r * kNT + tid;
+        flag[r] = false;
+        rec[r] = 0;
+        if (i + 1 < n) {
+            rec[r] = (uint32_t)(stream_vals[i] >> 32);
+            flag[r] = rec[r] == (uint32_t)(stream_vals[i + 1] >> 32);
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, flag[r]);
+        prefix[r] = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[r][wid] = __popc(ballot);
+    }
+    __syncthreads();
+    unsigned long long running = block_off[blockIdx.x];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kNW; ++w) {
+            const uint32_t t = s_cnt[r][w];
+            if ((uint32_t)w < wid) before += t;
+            total += t;
+        }
+        if (flag[r]) {
+            const uint32_t t = (uint32_t)r * kNT + tid;
+            uint32_t u = s_rank[t], v = s_rank[t + 1];
+            if (v < u) { const uint32_t x = u; u = v; v = x; }
+            const unsigned long long slot = running + before + prefix[r];
+            ekey[slot] = ((uint64_t)u << (64 - rank_bits)) | ((uint64_t)v << (64 - 2 * rank_bits));
+            easm[slot] = rec_asm[rec[r] - rec_base];
+        }
+        running += total;
+    }
+}
+
+// ---- buckets left to the sort-based path (edge hubs) -----------------------------------------------------------
+
+// copy the items of those buckets, bucket after bucket, into side arrays (side_off = exclusive scan of their sizes)
+template <typename V>
+__global__ void __launch_bounds__(kNT) overflow_gather_kernel(const uint64_t* __restrict__ keys, const V* __restrict__ vals,
+                                                              const uint32_t* __restrict__ start, const uint32_t* __restrict__ bucket_d,
+                                                              const unsigned long long* __restrict__ side_off,
+                                                              uint64_t* __restrict__ side_keys, V* __restrict__ side_vals)
+{
+    const uint32_t b = blockIdx.x;
+    if (bucket_d[b] != kOverflow) return;
+    const uint32_t bs = start[b], n = start[b + 1] - bs;
+    const unsigned long long so = side_off[b];
+    for (uint32_t i = threadIdx.x; i < n; i += kNT) {
+        side_keys[so + i] = keys[bs + i];
+        side_vals[so + i] = vals[bs + i];
+    }
+}
+
+// distinct keys (runs of the sorted side array) of every such bucket
+__global__ void __launch_bounds__(kNT) overflow_count_kernel(const uint64_t* __restrict__ side_keys, const uint32_t* __restrict__ start,
+                                                             const uint32_t* __restrict__ bucket_d,
+                                                             const unsigned long long* __restrict__ side_off,
+                                                             unsigned long long* __restrict__ d64, unsigned long long* __restrict__ ovf_d64)
+{
+    __shared__ uint32_t s_sum;
+    const uint32_t b = blockIdx.x;
+    if (bucket_d[b] != kOverflow) {
+        if (threadIdx.x == 0) ovf_d64[b] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const uint32_t n = start[b + 1] - start[b];
+    const unsigned long long so = side_off[b];
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += kNT) c += (i == 0 || side_keys[so + i] != side_keys[so + i - 1]) ? 1u : 0u;
+    if (c) atomicAdd(&s_sum, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        d64[b] = s_sum;
+        ovf_d64[b] = s_sum;
+    }
+}
+
+// their finished edges (side_edges, in key order) go to their place among the others
+__global__ void __launch_bounds__(kNT) overflow_copy_kernel(const sw_edge* __restrict__ side_edges, const uint32_t* __restrict__ bucket_d,
+                                                            const unsigned long long* __restrict__ grp_base,
+                                                            const unsigned long long* __restrict__ ovf_base,
+                                                            sw_edge* __restrict__ edges)
+{
+    const uint32_t b = blockIdx.x;
+    if (bucket_d[b] != kOverflow) return;
+    const unsigned long long n = grp_base[b + 1] - grp_base[b];
+    for (unsigned long long i = threadIdx.x; i < n; i += kNT) edges[grp_base[b] + i] = side_edges[ovf_base[b] + i];
+}
+
+}  // namespace agg
+}  // namespace sw

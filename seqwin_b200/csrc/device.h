@@ -131,6 +131,14 @@ struct SortPairs {
 // stable LSD sort of sp on key bits [begin_bit, end_bit) (begin_bit a multiple of 8); returns #launches
 uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s, int begin_bit = 0);
 
+// Stable partition of (keys, vals) on the top `top_bits` bits of the key (1 <= top_bits <= 64): ceil(top_bits / 8)
+// onesweep passes, lowest digit first.  The input is read only; the passes ping-pong between (ka, va) and
+// (kb, vb) (each n entries) and *out_k / *out_v point at whichever holds the result.  V = uint32_t or
+// unsigned long long.  Returns the number of kernels launched (one host synchronisation inside).
+template <typename V>
+uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, int top_bits, uint64_t* ka, V* va, uint64_t* kb,
+                             V* vb, cudaStream_t s, const uint64_t** out_k, const V** out_v);
+
 // ---- graph stage ------------------------------------------------------------------------------
 struct DevGraph {
     DevBuf<sw_kmer> kmers;

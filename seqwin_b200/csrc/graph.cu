@@ -18,6 +18,10 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+#include <cstring>
+
+#include "agg.cuh"
 #include "device.h"
 #include "scan.cuh"
 
@@ -547,10 +551,233 @@ __global__ void __launch_bounds__(256) penalty_kernel(
 
 uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlockItems - 1) / kBlockItems); }
 
+uint32_t env_u32(const char* name, uint32_t dflt)
+{
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long v = atol(e);
+    return v > 0 ? (uint32_t)v : dflt;
+}
+
+uint32_t stride_grid(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>((n + 255) / 256, 1), (uint64_t)sm_count() * 16); }
+
+void build_graph_legacy(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
+                        GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score);
+
+// Bucketed aggregation (agg.cuh): stable partition on the top bits of the key, then one CTA per bucket groups
+// by key in shared memory.  Returns false -- nothing of `g` touched -- if a NODE bucket holds more distinct
+// hashes than its table takes (not expected: the bucket count follows the item count and h1 is a 64-bit mix);
+// the caller then runs the sort-based path.
+bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
+                          GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
+{
+    using namespace agg;
+    const uint64_t M = st.n;
+    GraphTimes tm;
+    EventTimer timer(s);
+    timer.start();
+    // adjacent-pair records per block of the stream (read at the node stage's synchronisation point)
+    const uint32_t nb = blocks_for(M);
+    DevBuf<unsigned long long> ecnt((size_t)nb + 1, s, true);
+    edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, ecnt.p);
+    exclusive_scan_u64(ecnt.p, nb, ecnt.p + nb, s);
+    SW_CUDA(cudaGetLastError());
+    const unsigned long long* n_raw_p = readback_u64(ecnt.p + nb, 1, s);
+    tm.launches += 2;
+
+    // scratch: four arrays of M 64-bit words, carved again for the edge stage
+    DevBuf<uint64_t> w0(M, s, true), w1(M, s, true), w2(M, s, true), w3(M, s, true);
+
+    // -- nodes: partition (h1, kmer) on the top P bits, distinct hashes per bucket ----------------------------
+    const int P = partition_bits(M, env_u32("SEQWIN_AGG_NODE_BUCKET", 512));
+    const int key_bits = 64 - P;
+    const uint64_t n_buckets = 1ull << P;
+    const uint64_t* pk = nullptr;
+    const unsigned long long* pv = nullptr;
+    tm.launches += radix_partition_top<unsigned long long>(st.keys.p, reinterpret_cast<const unsigned long long*>(st.vals.p), M, P,
+                                                           w0.p, reinterpret_cast<unsigned long long*>(w2.p), w1.p,
+                                                           reinterpret_cast<unsigned long long*>(w3.p), s, &pk, &pv);
+    uint64_t* grp_keys = pk == w0.p ? w1.p : w0.p;     // the ping-pong pair that does not hold the result is free
+    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(pk == w0.p ? w3.p : w2.p);
+    DevBuf<uint32_t> start(n_buckets + 1, s, true), bucket_d(n_buckets, s, true);
+    DevBuf<unsigned long long> d64(n_buckets + 1, s, true), tot(3, s, true);
+    bucket_bounds_kernel<<<stride_grid(M + 1), 256, 0, s>>>(pk, M, key_bits, n_buckets, start.p);
+    group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(pk, start.p, key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
+                                                           bucket_d.p);
+    SW_CUDA(cudaMemsetAsync(tot.p, 0, 3 * sizeof(unsigned long long), s));
+    SW_CUDA(cudaMemsetAsync(d64.p + n_buckets, 0, sizeof(unsigned long long), s));
+    bucket_counts_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_d.p, start.p, n_buckets, d64.p, nullptr, tot.p);
+    tm.launches += 3 + exclusive_scan_u64(d64.p, n_buckets + 1, tot.p + 2, s);
+    SW_CUDA(cudaGetLastError());
+    const unsigned long long* tot_p = readback_u64(tot.p, 3, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    tm.sort_nodes_ms = timer.stop();
+    if (tot_p[0] != 0) return false;
+    const unsigned long long n_nodes = tot_p[2];
+    const unsigned long long n_raw = *n_raw_p;
+
+    // -- nodes + kmers (+ scoring) -----------------------------------------------------------------------------
+    timer.start();
+    g.n_kmers = M;
+    g.n_nodes = n_nodes;
+    g.kmers.alloc(M, s);
+    g.nodes.alloc(n_nodes, s);
+    DevBuf<uint64_t> node_hash(n_nodes, s, true);
+    const PlaceArgs pa{pk, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
+    NodeOut no{};
+    no.vals = pv;
+    no.placed = reinterpret_cast<unsigned long long*>(g.kmers.p);
+    no.nodes = g.nodes.p;
+    no.node_hash = node_hash.p;
+    no.rec_asm = d_rec_asm;
+    no.rec_base = rec_base;
+    if (score) {
+        no.is_target = score->d_is_target;
+        no.inv_t = score->inv_t;
+        no.inv_n = score->inv_n;
+        no.counts_only = score->counts_only ? 1 : 0;
+        group_place_kernel<NodeOut, true><<<(uint32_t)n_buckets, kNT, 0, s>>>(pa, no);
+    } else {
+        group_place_kernel<NodeOut, false><<<(uint32_t)n_buckets, kNT, 0, s>>>(pa, no);
+    }
+    SW_CUDA(cudaGetLastError());
+    ++tm.launches;
+    timer.mark();
+
+    // -- edges ---------------------------------------------------------------------------------------------------
+    EventTimer etimer(s);
+    etimer.start();
+    int rank_bits = 1;
+    while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
+    // edge-stage views of the scratch (n_raw < M): raw records, two ping-pong pairs, placed assemblies
+    uint64_t* ekey0 = w0.p;
+    uint64_t* eka = w1.p;
+    uint64_t* ekb = w2.p;
+    uint32_t* easm0 = reinterpret_cast<uint32_t*>(w3.p);
+    uint32_t* eva = easm0 + M;
+    DevBuf<uint32_t> evb, placed;
+    if (n_raw) {
+        // ranks are looked up: fine bucket table over the sorted node hashes (about one node per bucket)
+        int fbits = 1;
+        while (fbits < 28 && (1ull << fbits) < n_nodes) ++fbits;
+        DevBuf<uint32_t> ftable((1ull << fbits) + 1, s, true);
+        bucket_bounds_kernel<<<stride_grid(n_nodes + 1), 256, 0, s>>>(node_hash.p, n_nodes, 64 - fbits, 1ull << fbits, ftable.p);
+        edge_emit_kernel<<<nb, kNT, 0, s>>>(st.keys.p, st.vals.p, M, node_hash.p, ftable.p, 64 - fbits, d_rec_asm, rec_base, ecnt.p,
+                                            rank_bits, ekey0, easm0);
+        SW_CUDA(cudaGetLastError());
+        tm.launches += 2;
+    }
+    if (after_nodes) (*after_nodes)();
+    tm.nodes_ms = timer.read();
+    if (n_raw == 0) {
+        g.n_edges = 0;
+        g.edges.alloc(0, s);
+    } else {
+        evb.alloc(M, s, true);
+        placed.alloc(M, s, true);
+        const int Pe = std::min(partition_bits(n_raw, env_u32("SEQWIN_AGG_EDGE_BUCKET", 256)), 2 * rank_bits);
+        const int ekey_bits = 64 - Pe;
+        const uint64_t neb = 1ull << Pe;
+        const uint64_t* pek = nullptr;
+        const uint32_t* pev = nullptr;
+        tm.launches += radix_partition_top<uint32_t>(ekey0, easm0, n_raw, Pe, eka, eva, ekb, evb.p, s, &pek, &pev);
+        uint64_t* egrp_keys = pek == eka ? ekb : eka;
+        uint32_t* egrp_cnt = pek == eka ? evb.p : eva;
+        DevBuf<uint32_t> estart(neb + 1, s, true), ebucket_d(neb, s, true);
+        DevBuf<unsigned long long> ed64(neb + 1, s, true), ebase(neb + 1, s, true), ovf_items(neb + 1, s, true), etot(4, s, true);
+        bucket_bounds_kernel<<<stride_grid(n_raw + 1), 256, 0, s>>>(pek, n_raw, ekey_bits, neb, estart.p);
+        group_count_kernel<<<(uint32_t)neb, kNT, 0, s>>>(pek, estart.p, ekey_bits,
+                                                         std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", kMaxDistinct), kMaxDistinct),
+                                                         egrp_keys, egrp_cnt, ebucket_d.p);
+        SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
+        SW_CUDA(cudaMemsetAsync(ed64.p + neb, 0, sizeof(unsigned long long), s));
+        SW_CUDA(cudaMemsetAsync(ovf_items.p + neb, 0, sizeof(unsigned long long), s));
+        bucket_counts_kernel<<<stride_grid(neb), 256, 0, s>>>(ebucket_d.p, estart.p, neb, ed64.p, ovf_items.p, etot.p);
+        SW_CUDA(cudaMemcpyAsync(ebase.p, ed64.p, (neb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        tm.launches += 3 + exclusive_scan_u64(ebase.p, neb + 1, etot.p + 2, s);
+        SW_CUDA(cudaGetLastError());
+        const unsigned long long* etot_p = readback_u64(etot.p, 4, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        unsigned long long n_edges = etot_p[2];
+        const unsigned long long n_ovf = etot_p[0], n_side = etot_p[1];
+        if (getenv("SEQWIN_DEBUG_AGG"))
+            fprintf(stderr, "[agg] M %llu P %d nodes %llu | pairs %llu Pe %d edges %llu, %llu buckets (%llu records) to the sort path\n",
+                    (unsigned long long)M, P, n_nodes, n_raw, Pe, n_edges, n_ovf, n_side);
+        DevBuf<sw_edge> side_edges;
+        DevBuf<unsigned long long> ovf_d64;
+        if (n_ovf) {
+            // buckets with more distinct pairs than a table takes (hub nodes): their records are sorted on the
+            // whole key and run-length encoded, as the sort-based path does for everything
+            exclusive_scan_u64(ovf_items.p, neb + 1, etot.p + 3, s);     // -> first side slot of every such bucket
+            SortPairs sp;
+            sp.n = n_side;
+            sp.keys.alloc(n_side, s, true);
+            sp.vals.alloc(n_side, s, true);
+            overflow_gather_kernel<uint32_t><<<(uint32_t)neb, kNT, 0, s>>>(pek, pev, estart.p, ebucket_d.p, ovf_items.p, sp.keys.p,
+                                                                           sp.vals.p);
+            SW_CUDA(cudaGetLastError());
+            tm.launches += 2 + radix_sort_pairs(sp, 64, s, (64 - 2 * rank_bits) & ~7);
+            ovf_d64.alloc(neb + 1, s, true);
+            SW_CUDA(cudaMemsetAsync(ovf_d64.p + neb, 0, sizeof(unsigned long long), s));
+            overflow_count_kernel<<<(uint32_t)neb, kNT, 0, s>>>(sp.keys.p, estart.p, ebucket_d.p, ovf_items.p, ed64.p, ovf_d64.p);
+            exclusive_scan_u64(ovf_d64.p, neb + 1, etot.p + 3, s);
+            SW_CUDA(cudaMemcpyAsync(ebase.p, ed64.p, (neb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+            exclusive_scan_u64(ebase.p, neb + 1, etot.p + 2, s);
+            const uint32_t sb = blocks_for(n_side);
+            DevBuf<unsigned long long> scounts((size_t)sb + 1, s, true);
+            key_run_count_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, n_side, scounts.p);
+            exclusive_scan_u64(scounts.p, sb, scounts.p + sb, s);
+            SW_CUDA(cudaGetLastError());
+            const unsigned long long* e2 = readback_u64(etot.p, 4, s);
+            SW_CUDA(cudaStreamSynchronize(s));
+            n_edges = e2[2];
+            const unsigned long long n_side_edges = e2[3];
+            side_edges.alloc(n_side_edges, s, true);
+            SW_CUDA(cudaMemsetAsync(side_edges.p, 0, n_side_edges * sizeof(sw_edge), s));
+            edge_final_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_side, scounts.p, rank_bits, node_hash.p, side_edges.p);
+            SW_CUDA(cudaGetLastError());
+            tm.launches += 8;
+        }
+        g.n_edges = n_edges;
+        g.edges.alloc(n_edges, s);
+        const PlaceArgs epa{pek, estart.p, ekey_bits, egrp_keys, egrp_cnt, ebucket_d.p, ebase.p};
+        EdgeOut eo{};
+        eo.vals = pev;
+        eo.placed = placed.p;
+        eo.edges = g.edges.p;
+        eo.node_hash = node_hash.p;
+        eo.rank_bits = rank_bits;
+        group_place_kernel<EdgeOut, true><<<(uint32_t)neb, kNT, 0, s>>>(epa, eo);
+        ++tm.launches;
+        if (n_ovf) {
+            overflow_copy_kernel<<<(uint32_t)neb, kNT, 0, s>>>(side_edges.p, ebucket_d.p, ebase.p, ovf_d64.p, g.edges.p);
+            ++tm.launches;
+        }
+        SW_CUDA(cudaGetLastError());
+    }
+    tm.edges_ms = etimer.stop();
+    if (times) *times = tm;
+    return true;
+}
+
 }  // namespace
 
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                  GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
+{
+    const char* mode = getenv("SEQWIN_AGG");
+    const bool legacy = mode && !strcmp(mode, "legacy");
+    if (!legacy && st.n != 0 && st.n <= 0xFFFFFFFFull) {
+        if (build_graph_bucketed(st, d_rec_asm, rec_base, s, g, times, after_nodes, score)) return;
+        if (getenv("SEQWIN_DEBUG_AGG")) fprintf(stderr, "[agg] a node bucket overflowed: sort-based path\n");
+    }
+    build_graph_legacy(st, d_rec_asm, rec_base, s, g, times, after_nodes, score);
+}
+
+namespace {
+
+void build_graph_legacy(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
+                        GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
 {
     const uint64_t M = st.n;
     g.n_kmers = M;
@@ -689,6 +916,8 @@ void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base,
     tm.edges_ms = etimer.stop();
     if (times) *times = tm;
 }
+
+}  // namespace
 
 void finish_penalty(sw_node* d_nodes, uint64_t n_nodes, double inv_t, double inv_n, cudaStream_t s)
 {

@@ -26,6 +26,13 @@ constexpr int kMaxPasses = 8;
 #define SW_SORT_MINB 3
 #endif
 
+// digit positions of the passes of one sort, lowest digit first
+struct RadixPasses {
+    int n;
+    int shift[kMaxPasses];
+    int bits[kMaxPasses];
+};
+
 constexpr unsigned long long kStAgg = 1ULL << 62;
 constexpr unsigned long long kStInc = 2ULL << 62;
 constexpr unsigned long long kStMask = (1ULL << 62) - 1;
@@ -43,7 +50,7 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
 
 // Digit histograms of every pass in one read of the keys.
 __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                         int first_pass, int n_passes, unsigned long long* ghist)
+                                                         RadixPasses ps, unsigned long long* ghist)
 {
     __shared__ uint32_t sh[kMaxPasses][kRadix];
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
@@ -51,11 +58,11 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restr
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t key = keys[i];
-        for (int p = first_pass; p < n_passes; ++p)
-            atomicAdd(&sh[p][(key >> (p * kRadixBits)) & (kRadix - 1)], 1u);
+        for (int p = 0; p < ps.n; ++p)
+            atomicAdd(&sh[p][(key >> ps.shift[p]) & ((1u << ps.bits[p]) - 1u)], 1u);
     }
     __syncthreads();
-    for (int i = first_pass * kRadix + threadIdx.x; i < n_passes * kRadix; i += blockDim.x) {
+    for (int i = threadIdx.x; i < ps.n * kRadix; i += blockDim.x) {
         const uint32_t c = (&sh[0][0])[i];
         if (c) atomicAdd(&ghist[i], (unsigned long long)c);
     }
@@ -100,11 +107,11 @@ struct OnesweepSmem {
 };
 
 // One tile of one pass.  FULL = the tile holds NT * ITEMS items (no bounds checks).
-template <int NT, int ITEMS, bool FULL>
-__device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint64_t* s_buf, uint32_t* s_vin,
+template <int NT, int ITEMS, bool FULL, typename V>
+__device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint64_t* s_buf, V* s_vin,
                                               const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
-                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
-                                              uint32_t n_valid, uint32_t tile, int shift,
+                                              const V* __restrict__ vin, V* __restrict__ vout,
+                                              uint32_t n_valid, uint32_t tile, int shift, uint32_t dmask,
                                               const unsigned long long* __restrict__ goff, unsigned long long* status,
                                               uint32_t n_tiles)
 {
@@ -112,7 +119,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t wofs = (uint32_t)wid * (32 * ITEMS) + lane;  // this thread's first item inside the tile
     const uint64_t* kin_t = kin + wofs;                         // (kin / vin already point at the tile)
-    const uint32_t* vin_t = vin + wofs;
+    const V* vin_t = vin + wofs;
 
     uint64_t key[ITEMS];
     uint32_t rank[ITEMS];
@@ -120,10 +127,10 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
     for (int i = 0; i < ITEMS; ++i) key[i] = (FULL || wofs + i * 32 < n_valid) ? kin_t[i * 32] : ~0ULL;
     // the values are not needed before the keys have been written out: fetch them into shared
     // memory asynchronously (cp.async), each thread into its own slots
-    uint32_t* my_vin = s_vin + wofs;
+    V* my_vin = s_vin + wofs;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)
-        if (FULL || wofs + i * 32 < n_valid) __pipeline_memcpy_async(my_vin + i * 32, vin_t + i * 32, 4);
+        if (FULL || wofs + i * 32 < n_valid) __pipeline_memcpy_async(my_vin + i * 32, vin_t + i * 32, sizeof(V));
     __pipeline_commit();
 
     // warp-local stable ranking: items of one warp are ordered (item, lane)
@@ -131,7 +138,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const bool valid = FULL || wofs + i * 32 < n_valid;
-        const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+        const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x1FFu);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -185,7 +192,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         if (FULL || wofs + i * 32 < n_valid) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+            const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
             rank[i] += sm.whist[wid][d];
             s_buf[rank[i]] = key[i];
         }
@@ -222,7 +229,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
         if ((i & 3) == 0) dig[i >> 2] = 0;
         if (FULL || p < n_valid) {
             const uint64_t k2 = s_buf[p];
-            const uint32_t d = (uint32_t)(k2 >> shift) & (kRadix - 1);
+            const uint32_t d = (uint32_t)(k2 >> shift) & dmask;
             dig[i >> 2] |= d << (8 * (i & 3));
             kout[sm.dbase[d] + p] = k2;
         }
@@ -230,7 +237,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
     __pipeline_wait_prior(0);
     __syncthreads();
     // values take the same route through the (re-used) staging buffer
-    uint32_t* s_val = reinterpret_cast<uint32_t*>(s_buf);
+    V* s_val = reinterpret_cast<V*>(s_buf);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)
         if (FULL || wofs + i * 32 < n_valid) s_val[rank[i]] = my_vin[i * 32];
@@ -242,10 +249,10 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
     }
 }
 
-template <int NT, int ITEMS>
+template <int NT, int ITEMS, typename V>
 __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
-    const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
-    uint32_t* __restrict__ vout, uint64_t n, int shift, const unsigned long long* __restrict__ goff,
+    const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const V* __restrict__ vin,
+    V* __restrict__ vout, uint64_t n, int shift, uint32_t dmask, const unsigned long long* __restrict__ goff,
     unsigned long long* status, unsigned int* ticket)
 {
     constexpr int NW = NT / 32;
@@ -253,8 +260,8 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     static_assert(ITEMS % 4 == 0 && NT >= kRadix, "one thread per digit");
     __shared__ OnesweepSmem<NT, ITEMS> sm;
     extern __shared__ __align__(16) unsigned char radix_smem[];
-    uint64_t* s_buf = reinterpret_cast<uint64_t*>(radix_smem);                     // [TILE] tile-sorted staging
-    uint32_t* s_vin = reinterpret_cast<uint32_t*>(radix_smem + (size_t)TILE * 8);  // [TILE] prefetched values
+    uint64_t* s_buf = reinterpret_cast<uint64_t*>(radix_smem);              // [TILE] tile-sorted staging
+    V* s_vin = reinterpret_cast<V*>(radix_smem + (size_t)TILE * 8);         // [TILE] prefetched values
 
     const int tid = threadIdx.x;
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
@@ -264,11 +271,61 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     const uint64_t tile_base = (uint64_t)tile * TILE;
     const uint32_t n_valid = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
     if (n_valid == (uint32_t)TILE)
-        onesweep_tile<NT, ITEMS, true>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
-                                       shift, goff, status, gridDim.x);
+        onesweep_tile<NT, ITEMS, true, V>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
+                                          shift, dmask, goff, status, gridDim.x);
     else
-        onesweep_tile<NT, ITEMS, false>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
-                                        shift, goff, status, gridDim.x);
+        onesweep_tile<NT, ITEMS, false, V>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
+                                           shift, dmask, goff, status, gridDim.x);
+}
+
+// The passes of `ps` over (kin, vin): pass 0 reads the input (left untouched), the others ping-pong between
+// (ka, va) and (kb, vb).  Returns 0 / 1: the result is in (ka, va) / (kb, vb); -1: no pass ran (the input IS the
+// result).  Passes whose keys all share one digit are skipped.
+template <typename V>
+int run_passes(const uint64_t* kin, const V* vin, uint64_t n, const RadixPasses& ps, uint64_t* ka, V* va, uint64_t* kb,
+               V* vb, cudaStream_t s, uint32_t* launches_out)
+{
+    uint32_t launches = 0;
+    DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s, true);
+    SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
+    const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
+    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(kin, n, ps, ghist.p);
+    SW_CUDA(cudaGetLastError());
+    ++launches;
+    // exclusive digit offsets per pass, computed in place on the device; a pass whose keys all share
+    // one digit is a no-op and is skipped (needs only the per-pass maximum on the host)
+    DevBuf<unsigned long long> max_bin(kMaxPasses, s, true);
+    radix_offsets_kernel<<<ps.n, kRadix, 0, s>>>(ghist.p, max_bin.p);
+    SW_CUDA(cudaGetLastError());
+    ++launches;
+    const unsigned long long* h_max = readback_u64(max_bin.p, ps.n, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);
+    DevBuf<unsigned int> ticket(1, s, true);
+    constexpr size_t kSortSmem = (size_t)kSortTile * (8 + sizeof(V));
+    SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems, V>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    int where = -1;
+    const uint64_t* ksrc = kin;
+    const V* vsrc = vin;
+    for (int p = 0; p < ps.n; ++p) {
+        if (h_max[p] == n) continue;
+        uint64_t* kdst = where == 0 ? kb : ka;
+        V* vdst = where == 0 ? vb : va;
+        SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
+        SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
+        radix_onesweep_kernel<kSortThreads, kSortItems, V><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
+            ksrc, kdst, vsrc, vdst, n, ps.shift[p], (1u << ps.bits[p]) - 1u, ghist.p + (size_t)p * kRadix, status.p, ticket.p);
+        SW_CUDA(cudaGetLastError());
+        ++launches;
+        where = where == 0 ? 1 : 0;
+        ksrc = kdst;
+        vsrc = vdst;
+    }
+    if (launches_out) *launches_out += launches;
+    return where;
 }
 
 }  // namespace
@@ -278,48 +335,51 @@ uint32_t radix_sort_pairs(SortPairs& sp, int end_bit, cudaStream_t s, int begin_
     const uint64_t n = sp.n;
     if (n < 2 || end_bit <= begin_bit) return 0;
     const int n_passes = std::min(kMaxPasses, (end_bit + kRadixBits - 1) / kRadixBits);
-    const int first_pass = begin_bit / kRadixBits;   // stable LSD passes over digits [first_pass, n_passes)
-    uint32_t launches = 0;
-
-    DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s, true);
-    SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
-    const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
-    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(sp.keys.p, n, first_pass, n_passes, ghist.p);
-    SW_CUDA(cudaGetLastError());
-    ++launches;
-    // exclusive digit offsets per pass, computed in place on the device; a pass whose keys all share
-    // one digit is a no-op and is skipped (needs only the per-pass maximum on the host)
-    DevBuf<unsigned long long> max_bin(kMaxPasses, s, true);
-    radix_offsets_kernel<<<n_passes, kRadix, 0, s>>>(ghist.p, max_bin.p);
-    SW_CUDA(cudaGetLastError());
-    ++launches;
-    const unsigned long long* h_max = readback_u64(max_bin.p, n_passes, s);
-    SW_CUDA(cudaStreamSynchronize(s));
-    bool skip[kMaxPasses];
-    for (int p = 0; p < n_passes; ++p) skip[p] = p < first_pass || (h_max[p] == n);
-
-    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
-    DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);
-    DevBuf<unsigned int> ticket(1, s, true);
+    RadixPasses ps{};
+    for (int p = begin_bit / kRadixBits; p < n_passes; ++p) {   // stable LSD passes over digits [first_pass, n_passes)
+        ps.shift[ps.n] = p * kRadixBits;
+        ps.bits[ps.n] = kRadixBits;
+        ++ps.n;
+    }
     if (!sp.keys_alt.p || sp.keys_alt.n < n) sp.keys_alt.alloc(n, s, true);
     if (!sp.vals_alt.p || sp.vals_alt.n < n) sp.vals_alt.alloc(n, s, true);
-
-    constexpr size_t kSortSmem = (size_t)kSortTile * 12;
-    SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
-    for (int p = 0; p < n_passes; ++p) {
-        if (skip[p]) continue;
-        SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
-        SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
-        radix_onesweep_kernel<kSortThreads, kSortItems><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
-            sp.keys.p, sp.keys_alt.p, sp.vals.p, sp.vals_alt.p, n, p * kRadixBits,
-            ghist.p + (size_t)p * kRadix, status.p, ticket.p);
-        SW_CUDA(cudaGetLastError());
-        ++launches;
+    // in place from the caller's point of view: the first pass reads (keys, vals) and writes the alternates
+    uint32_t launches = 0;
+    const int where = run_passes<uint32_t>(sp.keys.p, sp.vals.p, n, ps, sp.keys_alt.p, sp.vals_alt.p, sp.keys.p, sp.vals.p, s,
+                                           &launches);
+    if (where == 0) {
         std::swap(sp.keys, sp.keys_alt);
         std::swap(sp.vals, sp.vals_alt);
     }
     return launches;
 }
+
+// Stable partition of (keys, vals) on the top `top_bits` bits of the key: ceil(top_bits / 8) onesweep passes,
+// the lowest (and narrowest) digit first.  The input arrays are read only; out_k / out_v point at the result.
+template <typename V>
+uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, int top_bits, uint64_t* ka, V* va, uint64_t* kb,
+                             V* vb, cudaStream_t s, const uint64_t** out_k, const V** out_v)
+{
+    RadixPasses ps{};
+    const int np = (top_bits + kRadixBits - 1) / kRadixBits;
+    int lo = 64 - top_bits;
+    for (int p = 0; p < np; ++p) {
+        const int bits = p == 0 ? top_bits - kRadixBits * (np - 1) : kRadixBits;
+        ps.shift[ps.n] = lo;
+        ps.bits[ps.n] = bits;
+        ++ps.n;
+        lo += bits;
+    }
+    uint32_t launches = 0;
+    const int where = n ? run_passes<V>(keys, vals, n, ps, ka, va, kb, vb, s, &launches) : -1;
+    *out_k = where < 0 ? keys : (where == 0 ? ka : kb);
+    *out_v = where < 0 ? vals : (where == 0 ? va : vb);
+    return launches;
+}
+template uint32_t radix_partition_top<uint32_t>(const uint64_t*, const uint32_t*, uint64_t, int, uint64_t*, uint32_t*, uint64_t*,
+                                                uint32_t*, cudaStream_t, const uint64_t**, const uint32_t**);
+template uint32_t radix_partition_top<unsigned long long>(const uint64_t*, const unsigned long long*, uint64_t, int, uint64_t*,
+                                                          unsigned long long*, uint64_t*, unsigned long long*, cudaStream_t,
+                                                          const uint64_t**, const unsigned long long**);
 
 }  // namespace sw

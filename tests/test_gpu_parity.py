@@ -281,8 +281,56 @@ def test_window_too_large_fails_loudly():
         _dev_sketch([b"ACGT" * 100], 21, 40_000)
 
 
+AGG_MODES = {
+    "legacy": {"SEQWIN_AGG": "legacy"},                               # sort + run-length path (round 1)
+    "edge-overflow": {"SEQWIN_AGG_EDGE_DISTINCT": "6"},               # most edge buckets take the side (sort) path
+    "tiny-buckets": {"SEQWIN_AGG_NODE_BUCKET": "12", "SEQWIN_AGG_EDGE_BUCKET": "5"},   # 2-3 partition passes, tiny groups
+    "one-bucket-pair": {"SEQWIN_AGG_NODE_BUCKET": "700", "SEQWIN_AGG_EDGE_BUCKET": "700", "SEQWIN_AGG_EDGE_DISTINCT": "700"},
+}
+
+
+@pytest.mark.parametrize("mode", sorted(AGG_MODES))
+def test_aggregation_paths_agree(mode, synth_sets, digests, fixture_paths, expected_graph, edge_paths, monkeypatch):
+    """The bucketed aggregation (csrc/agg.cuh) under settings that force its less common branches -- edge
+    buckets handed to the sort path, several partition passes with a few items per bucket, a node bucket that
+    overflows and sends the whole build to the sort-based path -- and the sort-based path itself: the graphs
+    (build and scored build) must not change."""
+    for k_, v_ in AGG_MODES[mode].items():
+        monkeypatch.setenv(k_, v_)
+    kmers, nodes, edges, offsets, _ = _build(fixture_paths, 17, 10, n_cpu=1)
+    np.testing.assert_array_equal(kmers, expected_graph["kmers"])
+    np.testing.assert_array_equal(edges, expected_graph["edges"])
+    for f in ("hash", "start", "stop"):
+        np.testing.assert_array_equal(nodes[f], expected_graph["nodes"][f])
+    for case in ("synth_small", "synth_medium", "synth_skew"):
+        paths, is_t = synth_sets[case]
+        for kw in GOLDEN_KW[:4]:
+            d = digests[case][f"{kw[0]},{kw[1]}"]
+            got = _build(paths, *kw, n_cpu=4)
+            assert_matches_digest(got, d, f"{case} {kw} {mode}")
+            nodes2 = got[1].copy()
+            _get_penalty(got[0], nodes2, got[3], is_t)
+            assert digest(nodes2) == d["nodes_penalty"], f"{case} {kw} {mode} penalty"
+    # scored build entry point (scoring fused into the placement kernel)
+    L = _lib.lib()
+    paths, is_t = edge_paths
+    arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    b, g = C.c_void_p(), C.c_void_p()
+    _lib.check(L.sw_batch_from_fasta(arr, len(paths), 2, C.byref(b)))
+    t8 = np.ascontiguousarray(is_t, dtype=np.bool_)
+    _lib.check(L.sw_build_from_batch_scored(b, 21, 46, t8.ctypes.data, len(t8), C.byref(g), None))
+    from seqwin_b200.dist import export_graph
+    gk, gn, ge = export_graph(L, g)
+    L.sw_graph_free(g)
+    L.sw_batch_free(b)
+    want = np.load(GOLDEN_ARRAYS / "edge_21_46.npz", allow_pickle=False)
+    assert np.array_equal(gk, want["kmers"]) and np.array_equal(ge, want["edges"])
+    assert np.array_equal(gn, want["nodes_penalty"])
+
+
 @pytest.mark.parametrize("begin_bit", [0, 40, 48, 56])
 def test_node_sort_tie_fixup(begin_bit, synth_sets, digests, fixture_paths, expected_graph, monkeypatch):
+    monkeypatch.setenv("SEQWIN_AGG", "legacy")
     """The node sort looks at the high word of h1 only (4 radix passes) and re-sorts the rare groups of
     equal high words afterwards.  Starting the passes at bit 40 / 48 / 56 makes such groups common
     (and, on the larger set, too big for the fix-up, which then falls back to the 64-bit sort);
