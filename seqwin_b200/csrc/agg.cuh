@@ -41,6 +41,14 @@ static_assert(kMaxDistinct == 3 * kNT, "group_place_kernel scans 3 groups per th
 constexpr unsigned long long kEmptyKey = ~0ull;   // in-bucket keys have their top P >= 1 bits cleared
 constexpr uint32_t kOverflow = 0xFFFFFFFFu;       // bucket_d value of a bucket left to the sort-based path
 
+// smallest P >= 1 with n / 2^P <= per_bucket
+inline int partition_bits(uint64_t n, uint32_t per_bucket)
+{
+    int p = 1;
+    while (p < 40 && (n >> p) > per_bucket) ++p;
+    return p;
+}
+
 // start[b] = first item whose key >> shift is >= b, for b in [0, n_buckets]  (keys ascending in those bits)
 __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift,
                                                             uint64_t n_buckets, uint32_t* __restrict__ start)
@@ -54,6 +62,53 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __re
 }
 
 __device__ __forceinline__ uint32_t first_slot(uint64_t kb, int hshift) { return (uint32_t)(kb >> hshift) & (kSlots - 1); }
+
+// ---- how many items per distinct key?  (sizes the buckets) ----------------------------------------------------
+// A hash-range sample: every item whose mixed key has its top `sbits` bits zero -- i.e. ALL occurrences of
+// about 1 in 2^sbits distinct keys -- is counted (out[0]) and inserted into a small global set (out[1] =
+// distinct keys inserted).  out[0] / out[1] estimates items per distinct key without bias.
+constexpr int kSampleSetBits = 17;
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 31;
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 29;
+    return x;
+}
+__global__ void __launch_bounds__(256) distinct_sample_kernel(const uint64_t* __restrict__ keys, uint64_t n, int sbits,
+                                                              unsigned long long* __restrict__ set, unsigned long long* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long k = keys[i];
+        const unsigned long long m = mix64(k);
+        if (sbits && (m >> (64 - sbits)) != 0) continue;
+        atomicAdd(&out[0], 1ull);
+        uint32_t s = (uint32_t)(m >> 8) & ((1u << kSampleSetBits) - 1);
+        const unsigned long long tag = k == kEmptyKey ? k - 1 : k;   // the empty marker cannot be stored (off by one key at most)
+        for (int probes = 0; probes < 4096; ++probes) {
+            const unsigned long long prev = atomicCAS(&set[s], kEmptyKey, tag);
+            if (prev == kEmptyKey) atomicAdd(&out[1], 1ull);
+            if (prev == kEmptyKey || prev == tag) break;
+            s = (s + 1) & ((1u << kSampleSetBits) - 1);
+        }
+    }
+}
+// sample 1 key in 2^sbits so that about 2^15 items are looked at
+inline int sample_bits(uint64_t n)
+{
+    int b = 0;
+    while (b < 40 && (n >> b) > (1ull << 15)) ++b;
+    return b;
+}
+// bucket bits from the estimate: `distinct_target` distinct keys per bucket on average, at most max_items items
+inline int partition_bits_for(uint64_t n, double items_per_key, double distinct_target, uint32_t max_items)
+{
+    double per_bucket = distinct_target * (items_per_key < 1.0 ? 1.0 : items_per_key);
+    if (per_bucket > (double)max_items) per_bucket = (double)max_items;
+    if (per_bucket < 64.0) per_bucket = 64.0;
+    return partition_bits(n, (uint32_t)per_bucket);
+}
 
 // ---- pass 1: distinct keys of every bucket, ascending, with their sizes ---------------------------------
 // grp_keys / grp_cnt are indexed like the items: bucket b owns [start[b], start[b] + D_b) of them.
@@ -80,21 +135,28 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
     __syncthreads();
     const uint64_t lowmask = (1ull << key_bits) - 1;
     const int hshift = key_bits > kSlotBits ? key_bits - kSlotBits : 0;
-    for (uint32_t i = tid; i < n; i += kNT) {
-        const unsigned long long kb = keys[bs + i] & lowmask;
-        uint32_t s = first_slot(kb, hshift);
-        for (int probes = 0;; ++probes) {
-            if (probes == kSlots || *(volatile uint32_t*)&s_n > max_distinct) {   // table (about to be) full: the bucket goes to the other path
-                atomicAdd(&s_n, (uint32_t)kSlots);
-                break;
+    for (uint32_t i0 = tid; i0 < n; i0 += 4 * kNT) {
+        unsigned long long kq[4];   // four independent loads in flight per thread
+#pragma unroll
+        for (int q = 0; q < 4; ++q) kq[q] = i0 + q * kNT < n ? keys[bs + i0 + q * kNT] : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q * kNT >= n) break;
+            const unsigned long long kb = kq[q] & lowmask;
+            uint32_t s = first_slot(kb, hshift);
+            for (int probes = 0;; ++probes) {
+                if (probes == kSlots || *(volatile uint32_t*)&s_n > max_distinct) {   // table (about to be) full: the other path takes the bucket
+                    atomicAdd(&s_n, (uint32_t)kSlots);
+                    break;
+                }
+                const unsigned long long prev = atomicCAS(&t_key[s], kEmptyKey, kb);
+                if (prev == kEmptyKey) atomicAdd(&s_n, 1u);
+                if (prev == kEmptyKey || prev == kb) {
+                    atomicAdd(&t_cnt[s], 1u);
+                    break;
+                }
+                s = (s + 1) & (kSlots - 1);
             }
-            const unsigned long long prev = atomicCAS(&t_key[s], kEmptyKey, kb);
-            if (prev == kEmptyKey) atomicAdd(&s_n, 1u);
-            if (prev == kEmptyKey || prev == kb) {
-                atomicAdd(&t_cnt[s], 1u);
-                break;
-            }
-            s = (s + 1) & (kSlots - 1);
         }
     }
     __syncthreads();
@@ -147,6 +209,7 @@ struct NodeOut {
     using Val = unsigned long long;                 // pos | record << 32 == sw_kmer
     const Val* vals;                                // partitioned like the keys
     Val* placed;                                    // kmers (final order)
+    uint32_t* placed_asm;                           // [items] assembly of every placed k-mer (scoring only)
     sw_node* nodes;
     uint64_t* node_hash;                            // compact copy of nodes[].hash for the edge stage
     const uint32_t* rec_asm;                        // [records] assembly of a record   (scoring only)
@@ -159,7 +222,8 @@ struct EdgeOut {
     static constexpr bool kNodes = false;
     using Val = uint32_t;                           // assembly of the adjacent-pair record
     const Val* vals;
-    Val* placed;                                    // scratch, same size as the records
+    Val* placed;                                    // unused: the placed assemblies are the values
+    uint32_t* placed_asm;                           // [records] assemblies in final order
     sw_edge* edges;
     const uint64_t* node_hash;
     int rank_bits;                                  // key = first << (64 - rank_bits) | second << (64 - 2 rank_bits)
@@ -175,21 +239,23 @@ struct PlaceArgs {
     const unsigned long long* grp_base;  // exclusive scan of the distinct counts: first output group of a bucket
 };
 
-__device__ __forceinline__ uint32_t assembly_of(const NodeOut& o, unsigned long long v)
+// what placement writes for one item: nodes -- the k-mer, and its assembly when the groups are counted;
+// edges -- the assembly only
+template <bool COUNT>
+__device__ __forceinline__ void place_item(const NodeOut& o, uint64_t dst, unsigned long long v)
 {
-    return o.rec_asm[(uint32_t)(v >> 32) - o.rec_base];
+    o.placed[dst] = v;
+    if (COUNT) o.placed_asm[dst] = o.rec_asm[(uint32_t)(v >> 32) - o.rec_base];
 }
-__device__ __forceinline__ uint32_t assembly_of(const EdgeOut&, uint32_t v) { return v; }
+template <bool COUNT>
+__device__ __forceinline__ void place_item(const EdgeOut& o, uint64_t dst, uint32_t v)
+{
+    o.placed_asm[dst] = v;
+}
 __device__ __forceinline__ bool is_class_a(const NodeOut& o, uint32_t as) { return o.is_target[as] != 0; }
 __device__ __forceinline__ bool is_class_a(const EdgeOut&, uint32_t) { return true; }
 
-// smallest P >= 1 with n / 2^P <= per_bucket
-inline int partition_bits(uint64_t n, uint32_t per_bucket)
-{
-    int p = 1;
-    while (p < 40 && (n >> p) > per_bucket) ++p;
-    return p;
-}
+
 
 __device__ __forceinline__ void write_group(const NodeOut& no, unsigned long long key, unsigned long long idx, uint64_t start,
                                             uint64_t stop, uint32_t ca, uint32_t cb, bool counted)
@@ -295,6 +361,12 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
         for (uint32_t r = lane; r < D; r += 32) whist[wid][r] = 0;
         __syncwarp();
         uint32_t rk[kItems], lr[kItems];
+        unsigned long long kq[kItems];
+#pragma unroll
+        for (int q = 0; q < kItems; ++q) {   // all key loads of the chunk in flight before the first is used
+            const uint32_t i = w_lo + q * 32 + lane;
+            kq[q] = ((uint32_t)q * 32 < per_warp && i < w_hi) ? a.keys[bs + c0 + i] : 0;
+        }
 #pragma unroll
         for (int q = 0; q < kItems; ++q) {
             rk[q] = 0xFFFFFFFFu;
@@ -302,7 +374,7 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
             if ((uint32_t)q * 32 < per_warp) {    // warp-uniform
                 const uint32_t i = w_lo + q * 32 + lane;
                 if (i < w_hi) {
-                    const unsigned long long kb = a.keys[bs + c0 + i] & lowmask;
+                    const unsigned long long kb = kq[q] & lowmask;
                     uint32_t s = first_slot(kb, hshift);
                     while (t_key[s] != kb) s = (s + 1) & (kSlots - 1);
                     rk[q] = t_rank[s];
@@ -319,6 +391,10 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
                 __syncwarp();
             }
         }
+        typename Out::Val vq[kItems];
+#pragma unroll
+        for (int q = 0; q < kItems; ++q)   // the values are not needed before the ranks are final: load them now
+            if (rk[q] != 0xFFFFFFFFu) vq[q] = o.vals[bs + c0 + w_lo + q * 32 + lane];
         __syncthreads();
         for (uint32_t r = tid; r < D; r += kNT) {
             uint32_t run = 0;
@@ -335,9 +411,8 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
 #pragma unroll
         for (int q = 0; q < kItems; ++q) {
             if (rk[q] != 0xFFFFFFFFu) {
-                const uint32_t i = w_lo + q * 32 + lane;
                 const uint32_t pos = cbase[rk[q]] + whist[wid][rk[q]] + lr[q];
-                o.placed[bs + pos] = o.vals[bs + c0 + i];
+                place_item<COUNT>(o, (uint64_t)bs + pos, vq[q]);
             }
         }
         __syncthreads();
@@ -351,7 +426,7 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
             const bool valid = j < n;
             uint32_t as = 0xFFFFFFFFu, r = 0xFFFFFFFFu;
             if (valid) {
-                as = assembly_of(o, o.placed[bs + j]);
+                as = o.placed_asm[bs + j];
                 uint32_t lo = 0, hi = D;      // largest r with goff[r] <= j
                 while (hi - lo > 1) {
                     const uint32_t mid = (lo + hi) >> 1;
@@ -360,7 +435,7 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
                 r = lo;
             }
             uint32_t prev = __shfl_up_sync(0xffffffffu, as, 1);
-            if (lane == 0) prev = (valid && j > 0) ? assembly_of(o, o.placed[bs + j - 1]) : 0xFFFFFFFFu;
+            if (lane == 0) prev = (valid && j > 0) ? o.placed_asm[bs + j - 1] : 0xFFFFFFFFu;
             const bool fresh = valid && (j == goff[r] || as != prev);
             const bool cls_a = fresh ? is_class_a(o, as) : true;
             const uint32_t peers = __match_any_sync(0xffffffffu, r);

@@ -564,6 +564,18 @@ uint32_t stride_grid(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<
 void build_graph_legacy(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                         GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score);
 
+// items per distinct key of keys[0..n), from a hash-range sample (agg.cuh); one host synchronisation
+double estimate_items_per_key(const uint64_t* keys, uint64_t n, unsigned long long* set, unsigned long long* out, cudaStream_t s)
+{
+    SW_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(unsigned long long) << agg::kSampleSetBits, s));
+    SW_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), s));
+    agg::distinct_sample_kernel<<<stride_grid(n), 256, 0, s>>>(keys, n, agg::sample_bits(n), set, out);
+    SW_CUDA(cudaGetLastError());
+    const unsigned long long* h = readback_u64(out, 2, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    return h[1] ? (double)h[0] / (double)h[1] : 1.0;
+}
+
 // Bucketed aggregation (agg.cuh): stable partition on the top bits of the key, then one CTA per bucket groups
 // by key in shared memory.  Returns false -- nothing of `g` touched -- if a NODE bucket holds more distinct
 // hashes than its table takes (not expected: the bucket count follows the item count and h1 is a 64-bit mix);
@@ -589,7 +601,13 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     DevBuf<uint64_t> w0(M, s, true), w1(M, s, true), w2(M, s, true), w3(M, s, true);
 
     // -- nodes: partition (h1, kmer) on the top P bits, distinct hashes per bucket ----------------------------
-    const int P = partition_bits(M, env_u32("SEQWIN_AGG_NODE_BUCKET", 512));
+    // bucket size: about 400 distinct hashes each, which takes an estimate of the k-mers per distinct hash
+    DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
+    const double per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
+    tm.launches += 1;
+    const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
+    const int P = fixed_nb ? partition_bits(M, fixed_nb)
+                           : partition_bits_for(M, per_node, 400.0, env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
     const int key_bits = 64 - P;
     const uint64_t n_buckets = 1ull << P;
     const uint64_t* pk = nullptr;
@@ -623,10 +641,12 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
     DevBuf<uint64_t> node_hash(n_nodes, s, true);
+    DevBuf<uint32_t> node_asm(score ? M : 0, s, true);
     const PlaceArgs pa{pk, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
     NodeOut no{};
     no.vals = pv;
     no.placed = reinterpret_cast<unsigned long long*>(g.kmers.p);
+    no.placed_asm = node_asm.p;
     no.nodes = g.nodes.p;
     no.node_hash = node_hash.p;
     no.rec_asm = d_rec_asm;
@@ -675,7 +695,13 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     } else {
         evb.alloc(M, s, true);
         placed.alloc(M, s, true);
-        const int Pe = std::min(partition_bits(n_raw, env_u32("SEQWIN_AGG_EDGE_BUCKET", 256)), 2 * rank_bits);
+        // records per distinct pair -> about 192 distinct pairs per bucket (min(u, v) makes the low buckets twice as full)
+        const double per_edge = estimate_items_per_key(ekey0, n_raw, sample_set.p, sample_out.p, s);
+        tm.launches += 1;
+        const uint32_t fixed_eb = env_u32("SEQWIN_AGG_EDGE_BUCKET", 0);
+        const int Pe = std::min(fixed_eb ? partition_bits(n_raw, fixed_eb)
+                                         : partition_bits_for(n_raw, per_edge, 192.0, env_u32("SEQWIN_AGG_MAX_ITEMS", 4096)),
+                                2 * rank_bits);
         const int ekey_bits = 64 - Pe;
         const uint64_t neb = 1ull << Pe;
         const uint64_t* pek = nullptr;
@@ -701,8 +727,8 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         unsigned long long n_edges = etot_p[2];
         const unsigned long long n_ovf = etot_p[0], n_side = etot_p[1];
         if (getenv("SEQWIN_DEBUG_AGG"))
-            fprintf(stderr, "[agg] M %llu P %d nodes %llu | pairs %llu Pe %d edges %llu, %llu buckets (%llu records) to the sort path\n",
-                    (unsigned long long)M, P, n_nodes, n_raw, Pe, n_edges, n_ovf, n_side);
+            fprintf(stderr, "[agg] M %llu (%.2f per node) P %d nodes %llu | pairs %llu (%.2f per edge) Pe %d edges %llu, %llu buckets (%llu records) to the sort path\n",
+                    (unsigned long long)M, per_node, P, n_nodes, n_raw, per_edge, Pe, n_edges, n_ovf, n_side);
         DevBuf<sw_edge> side_edges;
         DevBuf<unsigned long long> ovf_d64;
         if (n_ovf) {
@@ -743,7 +769,8 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         const PlaceArgs epa{pek, estart.p, ekey_bits, egrp_keys, egrp_cnt, ebucket_d.p, ebase.p};
         EdgeOut eo{};
         eo.vals = pev;
-        eo.placed = placed.p;
+        eo.placed = nullptr;
+        eo.placed_asm = placed.p;
         eo.edges = g.edges.p;
         eo.node_hash = node_hash.p;
         eo.rank_bits = rank_bits;

@@ -38,6 +38,14 @@ std::vector<unsigned long long> exclusive_scan(const std::vector<unsigned long l
 
 }  // namespace
 
+// the hash-range sample behind the bucket sizing: returns items per distinct key as the device estimates it
+extern "C" double agg_emul_estimate(const uint64_t* keys, uint64_t n, int sbits)
+{
+    std::vector<unsigned long long> set(1ull << kSampleSetBits, kEmptyKey), out(2, 0);
+    cuemu::launch(dim3(4), dim3(256), [&] { distinct_sample_kernel(keys, n, sbits, set.data(), out.data()); });
+    return out[1] ? (double)out[0] / (double)out[1] : 1.0;
+}
+
 extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream_vals, uint64_t M, const uint32_t* rec_asm,
                              uint32_t rec_base, const uint8_t* is_target, int score, uint32_t n_targets, uint32_t n_non_targets,
                              uint32_t per_bucket_nodes, uint32_t per_bucket_edges, uint32_t max_distinct_edges, sw_kmer* kmers_out,
@@ -70,6 +78,8 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     NodeOut no{};
     no.vals = vals.data();
     no.placed = reinterpret_cast<unsigned long long*>(kmers_out);
+    std::vector<uint32_t> node_asm(M);
+    no.placed_asm = node_asm.data();
     no.nodes = nodes_out;
     no.node_hash = node_hash.data();
     no.rec_asm = rec_asm;
@@ -149,7 +159,8 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     PlaceArgs epa{ekey.data(), estart.data(), ekey_bits, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data(), egrp_base.data()};
     EdgeOut eo{};
     eo.vals = easm.data();
-    eo.placed = placed.data();
+    eo.placed = nullptr;
+    eo.placed_asm = placed.data();
     eo.edges = edges_out;
     eo.node_hash = node_hash.data();
     eo.rank_bits = rank_bits;

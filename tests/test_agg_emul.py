@@ -27,6 +27,7 @@ def agg():
                                "-shared", "-o", str(so), str(EMUL_DIR / "agg_emul.cpp")])
     L = C.CDLL(str(so))
     L.agg_emul_run.restype = C.c_long
+    L.agg_emul_estimate.restype = C.c_double
     return L
 
 
@@ -143,3 +144,15 @@ def test_emulated_hot_key_spans_chunks(agg):
     pairs, wgt = np.unique(trip[:, :2], axis=0, return_counts=True)
     assert np.array_equal(edges["first"], uk[pairs[:, 0]]) and np.array_equal(edges["second"], uk[pairs[:, 1]])
     assert np.array_equal(edges["weight"], wgt.astype(np.uint64))
+
+
+def test_emulated_distinct_estimate(agg):
+    """The hash-range sample that sizes the buckets: items per distinct key, sampled 1 key in 2^sbits."""
+    rng = np.random.default_rng(3)
+    uniq = rng.integers(0, 2**63, 40_000, dtype=np.uint64)
+    keys = np.ascontiguousarray(np.concatenate([np.repeat(uniq[:10_000], 9), uniq[10_000:]]))   # 120k items, 40k keys: 3.0
+    rng.shuffle(keys)
+    exact = agg.agg_emul_estimate(C.c_void_p(keys.ctypes.data), C.c_uint64(len(keys)), C.c_int(0))
+    assert abs(exact - 3.0) < 1e-9
+    est = agg.agg_emul_estimate(C.c_void_p(keys.ctypes.data), C.c_uint64(len(keys)), C.c_int(3))
+    assert abs(est - 3.0) < 0.3
