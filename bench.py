@@ -475,6 +475,9 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(s["total_launches"] for s in stages)),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity_sample_bit_exact": None if parity is None else bool(parity["bit_exact"]), "parity": parity}
+    ms = (C.c_uint64 * 4)()
+    _lib.check(L.sw_mem_stats(ms))
+    line["device_memory_gb"] = {"scratch_arena_high": ms[0] / 1e9, "pool_used_high": ms[1] / 1e9, "in_use_now": ms[3] / 1e9}
     if "single_gpu" in result:
         line["single_gpu_same_shard"] = result["single_gpu"]
     if "full_size_checks" in result:

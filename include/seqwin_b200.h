@@ -207,6 +207,11 @@ int sw_graph_filter_kmers(sw_graph* g, const uint64_t* used_hashes, size_t n_use
  * e_absence_tar = 1 - sums[1] / (T * sums[0]), e_presence_neg = sums[2] / (N * sums[0]). */
 int sw_graph_count_sums(sw_graph* g, uint64_t sums[3]);
 
+/* Device memory of this process: out[0] = scratch arena of the calling thread (high-water: it only grows),
+ * out[1] / out[2] = used / reserved high-water marks of the stream-ordered pool (batches, graphs),
+ * out[3] = bytes in use on the device right now (all processes). */
+int sw_mem_stats(uint64_t out[4]);
+
 /* Measured peak of the INT32 ALU pipe, the roofline that bounds the sketch kernels: lane-operations per
  * second of dependent-chain LOP3, SHF, IADD and of their 1:1:1 mix (CUDA-event timed, ~10 ms). */
 int sw_measure_int_peak(double lane_ops_per_s[4]);

@@ -61,7 +61,12 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __re
     }
 }
 
-__device__ __forceinline__ uint32_t first_slot(uint64_t kb, int hshift) { return (uint32_t)(kb >> hshift) & (kSlots - 1); }
+// Table slot of an in-bucket key.  Multiplicative hashing: node keys are uniform in every bit, but the edge
+// keys of one bucket share most of `first` -- a hub node's pairs differ only further down, in `second`.
+__device__ __forceinline__ uint32_t first_slot(uint64_t kb, int)
+{
+    return (uint32_t)((kb * 0x9E3779B97F4A7C15ull) >> (64 - kSlotBits));
+}
 
 // ---- how many items per distinct key?  (sizes the buckets) ----------------------------------------------------
 // A hash-range sample: every item whose mixed key has its top `sbits` bits zero -- i.e. ALL occurrences of

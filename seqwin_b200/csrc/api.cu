@@ -121,7 +121,18 @@ struct Arena {
         if (cur == slabs.size()) {
             Slab sl;
             sl.bytes = std::max(bytes, (size_t)256 << 20);
-            SW_CUDA(cudaMalloc((void**)&sl.p, sl.bytes));
+            cudaError_t err = cudaMalloc((void**)&sl.p, sl.bytes);
+            if (err == cudaErrorMemoryAllocation) {
+                // the stream-ordered pool keeps what earlier (larger) builds freed: give that back and retry
+                cudaGetLastError();
+                cudaDeviceSynchronize();
+                int dev = 0;
+                cudaMemPool_t pool;
+                if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                    cudaMemPoolTrimTo(pool, 0);
+                err = cudaMalloc((void**)&sl.p, sl.bytes);
+            }
+            SW_CUDA(err);
             slabs.push_back(sl);
             off = 0;
         }
@@ -197,7 +208,19 @@ ReadbackRing& tls_readback()
 }
 }  // namespace
 
+size_t arena_bytes()
+{
+    size_t t = 0;
+    for (auto& sl : tls_arena().slabs) t += sl.bytes;
+    return t;
+}
 void* arena_alloc(size_t bytes) { return tls_arena().alloc(bytes); }
+ArenaMark arena_mark() { return ArenaMark{tls_arena().cur, tls_arena().off}; }
+void arena_release(const ArenaMark& m)
+{
+    tls_arena().cur = m.slab;
+    tls_arena().off = m.off;
+}
 void arena_reset()
 {
     tls_arena().reset();
@@ -720,6 +743,26 @@ int sw_device_info(int* sm, int* major, int* minor, size_t* hbm)
         if (major) *major = p.major;
         if (minor) *minor = p.minor;
         if (hbm) *hbm = p.totalGlobalMem;
+    });
+}
+
+int sw_mem_stats(uint64_t out[4])
+{
+    return guarded([&] {
+        init_device_once();
+        int dev = 0;
+        SW_CUDA(cudaGetDevice(&dev));
+        out[0] = arena_bytes();
+        out[1] = out[2] = 0;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t v = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &v) == cudaSuccess) out[1] = v;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &v) == cudaSuccess) out[2] = v;
+        }
+        size_t fr = 0, tot = 0;
+        SW_CUDA(cudaMemGetInfo(&fr, &tot));
+        out[3] = tot - fr;
     });
 }
 

@@ -26,6 +26,11 @@ namespace sw {
 // of every build, so the steady state performs no cudaMalloc / cudaFree at all.
 void* arena_alloc(size_t bytes);
 void arena_reset();
+// Stack discipline inside one build: everything allocated after arena_mark() is handed back by
+// arena_release(mark) (stream order keeps a later owner of the bytes behind the kernels of the earlier one).
+struct ArenaMark { size_t slab, off; };
+ArenaMark arena_mark();
+void arena_release(const ArenaMark& m);
 
 // Small device -> host readbacks (counts, histograms) go through a pinned, device-mapped buffer
 // written by a tiny kernel instead of cudaMemcpyAsync: a copy-engine transfer would queue behind

@@ -641,6 +641,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
     DevBuf<uint64_t> node_hash(n_nodes, s, true);
+    const ArenaMark node_mark = arena_mark();   // what follows is dead once the placement kernel has run
     DevBuf<uint32_t> node_asm(score ? M : 0, s, true);
     const PlaceArgs pa{pk, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
     NodeOut no{};
@@ -663,6 +664,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     SW_CUDA(cudaGetLastError());
     ++tm.launches;
     timer.mark();
+    arena_release(node_mark);
 
     // -- edges ---------------------------------------------------------------------------------------------------
     EventTimer etimer(s);

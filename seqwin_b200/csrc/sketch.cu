@@ -475,7 +475,11 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     // expected density 2/(w+1); leave 50 % headroom and re-run with the exact size on overflow
     uint64_t capacity = (uint64_t)((double)plan.n_kmers * 3.0 / ((double)w + 1.0)) + 4096;
     capacity = std::min<uint64_t>(capacity, plan.n_windows);
+    // The ordered stream is allocated first, with the capacity of the unordered one, so that the unordered
+    // buffers (dead after the reorder) sit on top of the scratch arena and can be handed back.
     DevBuf<uint64_t> ukeys, uvals;
+    const ArenaMark stream_mark = arena_mark();
+    ArenaMark unordered_mark = stream_mark;
     unsigned long long total = 0;
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
@@ -484,6 +488,10 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); }
     } ev_guard{ev};
     for (int attempt = 0;; ++attempt) {
+        arena_release(stream_mark);
+        out.keys.alloc(capacity, s, true);
+        out.vals.alloc(capacity, s, true);
+        unordered_mark = arena_mark();
         ukeys.alloc(capacity, s, true);
         uvals.alloc(capacity, s, true);
         SW_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
@@ -553,10 +561,11 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         capacity = total;  // low-complexity input: more minimizers than the density estimate
     }
     out.n = total;
-    out.keys.alloc(total, s, true);
-    out.vals.alloc(total, s, true);
     cudaEventElapsedTime(&out.kernel_ms, ev[0], ev[1]);
-    if (total == 0) return;
+    if (total == 0) {
+        arena_release(unordered_mark);
+        return;
+    }
     cudaEventRecord(ev[2], s);
     exclusive_scan_u64(tile_info.p, plan.n_tiles, counters.p + 1, s);
     const uint32_t rgrid = (uint32_t)std::min<uint64_t>(((uint64_t)plan.n_tiles + 7) / 8, (uint64_t)sm_count() * 8);
@@ -567,6 +576,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     out.launches += 2;
     SW_CUDA(cudaEventSynchronize(ev[3]));
     cudaEventElapsedTime(&out.reorder_ms, ev[2], ev[3]);
+    arena_release(unordered_mark);   // the reorder has finished: the unordered buffers go back to the arena
 }
 
 }  // namespace sw

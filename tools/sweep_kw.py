@@ -75,6 +75,9 @@ def main():
                          "path": {"algorithmic_bytes": path_bytes, "achieved_gbs": path_bytes / (m["total_ms"] * 1e-3) / 1e9,
                                   "hbm_frac": path_bytes / (m["total_ms"] * 1e-3) / 1e9 / hbm_peak},
                          "hbm_peak_gbs": hbm_peak})
+            ms = (C.c_uint64 * 4)()
+            _lib.check(L.sw_mem_stats(ms))
+            line["device_memory_gb"] = {"scratch_arena": ms[0] / 1e9, "pool_used_high": ms[1] / 1e9, "in_use_now": ms[3] / 1e9}
         except Exception as exc:  # noqa: BLE001 - a config that does not fit is a result, not a crash
             line["error"] = f"{type(exc).__name__}: {exc}"
         print(json.dumps(line), flush=True)
