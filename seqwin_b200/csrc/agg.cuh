@@ -32,12 +32,12 @@ namespace agg {
 
 constexpr int kNT = 256;
 constexpr int kNW = kNT / 32;
-constexpr int kSlotBits = 10;
+constexpr int kSlotBits = 11;
 constexpr int kSlots = 1 << kSlotBits;      // open-addressing table of one bucket's distinct keys
-constexpr int kMaxDistinct = 768;            // distinct keys a bucket may hold (table load <= 0.75)
+constexpr int kMaxDistinct = 1024;           // distinct keys a bucket may hold (table load <= 0.5: linear probing stays short)
 constexpr int kItems = 8;                    // items per thread and placement chunk
 constexpr int kChunk = kNT * kItems;
-static_assert(kMaxDistinct == 3 * kNT, "group_place_kernel scans 3 groups per thread");
+static_assert(kMaxDistinct == 4 * kNT, "group_place_kernel scans 4 groups per thread");
 constexpr unsigned long long kEmptyKey = ~0ull;   // in-bucket keys have their top P >= 1 bits cleared
 constexpr uint32_t kOverflow = 0xFFFFFFFFu;       // bucket_d value of a bucket left to the sort-based path
 
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __re
 
 // Table slot of an in-bucket key.  Multiplicative hashing: node keys are uniform in every bit, but the edge
 // keys of one bucket share most of `first` -- a hub node's pairs differ only further down, in `second`.
-__device__ __forceinline__ uint32_t first_slot(uint64_t kb, int)
+__device__ __forceinline__ uint32_t first_slot(uint64_t kb, int = 0)
 {
     return (uint32_t)((kb * 0x9E3779B97F4A7C15ull) >> (64 - kSlotBits));
 }
@@ -117,14 +117,37 @@ inline int partition_bits_for(uint64_t n, double items_per_key, double distinct_
 
 // ---- pass 1: distinct keys of every bucket, ascending, with their sizes ---------------------------------
 // grp_keys / grp_cnt are indexed like the items: bucket b owns [start[b], start[b] + D_b) of them.
+// item_rank[i] = rank of item i's key among the distinct keys of its bucket (what pass 2 groups by).
+
+// slot of key kb in the table, inserting it if absent; kSlots if the table is full
+__device__ __forceinline__ uint32_t table_upsert(unsigned long long* t_key, unsigned long long kb, bool* inserted)
+{
+    uint32_t s = first_slot(kb, 0);
+    *inserted = false;
+    for (int probes = 0; probes < kSlots; ++probes) {
+        unsigned long long cur = t_key[s];
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(&t_key[s], kEmptyKey, kb);
+            if (cur == kEmptyKey) {
+                *inserted = true;
+                return s;
+            }
+        }
+        if (cur == kb) return s;
+        s = (s + 1) & (kSlots - 1);
+    }
+    return (uint32_t)kSlots;
+}
+
 __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ start,
                                                           int key_bits, uint32_t max_distinct, uint64_t* __restrict__ grp_keys,
-                                                          uint32_t* __restrict__ grp_cnt, uint32_t* __restrict__ bucket_d)
+                                                          uint32_t* __restrict__ grp_cnt, uint32_t* __restrict__ bucket_d,
+                                                          uint16_t* __restrict__ item_rank)
 {
     __shared__ unsigned long long t_key[kSlots];
-    __shared__ uint32_t t_cnt[kSlots];
+    __shared__ uint32_t t_cnt[kSlots];              // items per slot; afterwards: rank of the slot's key
     __shared__ unsigned long long dk[kMaxDistinct];
-    __shared__ uint32_t dc[kMaxDistinct];
+    __shared__ uint16_t dslot[kMaxDistinct];
     __shared__ uint32_t s_n, s_m;
     const uint32_t b = blockIdx.x, tid = threadIdx.x;
     const uint32_t bs = start[b], n = start[b + 1] - bs;
@@ -139,7 +162,6 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
     if (tid == 0) { s_n = 0; s_m = 0; }
     __syncthreads();
     const uint64_t lowmask = (1ull << key_bits) - 1;
-    const int hshift = key_bits > kSlotBits ? key_bits - kSlotBits : 0;
     for (uint32_t i0 = tid; i0 < n; i0 += 4 * kNT) {
         unsigned long long kq[4];   // four independent loads in flight per thread
 #pragma unroll
@@ -147,21 +169,15 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (i0 + q * kNT >= n) break;
-            const unsigned long long kb = kq[q] & lowmask;
-            uint32_t s = first_slot(kb, hshift);
-            for (int probes = 0;; ++probes) {
-                if (probes == kSlots || *(volatile uint32_t*)&s_n > max_distinct) {   // table (about to be) full: the other path takes the bucket
-                    atomicAdd(&s_n, (uint32_t)kSlots);
-                    break;
-                }
-                const unsigned long long prev = atomicCAS(&t_key[s], kEmptyKey, kb);
-                if (prev == kEmptyKey) atomicAdd(&s_n, 1u);
-                if (prev == kEmptyKey || prev == kb) {
-                    atomicAdd(&t_cnt[s], 1u);
-                    break;
-                }
-                s = (s + 1) & (kSlots - 1);
+            if (*(volatile uint32_t*)&s_n > max_distinct) break;   // more distinct keys than allowed: the other path takes the bucket
+            bool inserted;
+            const uint32_t s = table_upsert(t_key, kq[q] & lowmask, &inserted);
+            if (s == (uint32_t)kSlots) {
+                atomicAdd(&s_n, (uint32_t)kSlots);
+                break;
             }
+            if (inserted) atomicAdd(&s_n, 1u);
+            atomicAdd(&t_cnt[s], 1u);
         }
     }
     __syncthreads();
@@ -174,19 +190,36 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
         if (t_key[s] != kEmptyKey) {
             const uint32_t i = atomicAdd(&s_m, 1u);
             dk[i] = t_key[s];
-            dc[i] = t_cnt[s];
+            dslot[i] = (uint16_t)s;
         }
     }
     __syncthreads();
-    const uint64_t prefix = key_bits < 64 ? (uint64_t)b << key_bits : 0;
+    const uint64_t prefix = (uint64_t)b << key_bits;
     for (uint32_t i = tid; i < D; i += kNT) {
         const unsigned long long k = dk[i];
         uint32_t r = 0;
         for (uint32_t j = 0; j < D; ++j) r += dk[j] < k ? 1u : 0u;
+        const uint32_t sl = dslot[i];
         grp_keys[bs + r] = k | prefix;
-        grp_cnt[bs + r] = dc[i];
+        grp_cnt[bs + r] = t_cnt[sl];
+        t_cnt[sl] = r;          // only this thread touches the slot: its count has just been read
     }
     if (tid == 0) bucket_d[b] = D;
+    __syncthreads();
+    // every item's rank: second look at the (cached) keys
+    for (uint32_t i0 = tid; i0 < n; i0 += 4 * kNT) {
+        unsigned long long kq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) kq[q] = i0 + q * kNT < n ? keys[bs + i0 + q * kNT] : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q * kNT >= n) break;
+            const unsigned long long kb = kq[q] & lowmask;
+            uint32_t s = first_slot(kb, 0);
+            while (t_key[s] != kb) s = (s + 1) & (kSlots - 1);
+            item_rank[bs + i0 + q * kNT] = (uint16_t)t_cnt[s];
+        }
+    }
 }
 
 // bucket_d -> 64-bit counts for the scans: distinct keys of the buckets grouped here (0 for the others), and
@@ -235,7 +268,7 @@ struct EdgeOut {
 };
 
 struct PlaceArgs {
-    const uint64_t* keys;                // partitioned keys
+    const uint16_t* item_rank;           // rank of every item's key inside its bucket (group_count_kernel)
     const uint32_t* start;               // bucket bounds
     int key_bits;                        // 64 - P
     const uint64_t* grp_keys;            // from group_count_kernel
@@ -293,10 +326,8 @@ __device__ __forceinline__ void write_group(const EdgeOut& eo, unsigned long lon
 }
 
 template <class Out, bool COUNT>
-__global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
+__global__ void __launch_bounds__(kNT, 4) group_place_kernel(PlaceArgs a, Out o)
 {
-    __shared__ unsigned long long t_key[kSlots];
-    __shared__ uint16_t t_rank[kSlots];
     __shared__ uint32_t goff[kMaxDistinct + 1];     // first item of every group, relative to the bucket
     __shared__ uint32_t cursor[kMaxDistinct];       // items of the group placed by earlier chunks
     __shared__ uint32_t cbase[kMaxDistinct];        // cursor at the start of the current chunk
@@ -308,28 +339,18 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
     const uint32_t D = a.bucket_d[b];
     if (n == 0 || D == kOverflow) return;
     const unsigned long long base = a.grp_base[b];
-    const uint64_t lowmask = (1ull << a.key_bits) - 1;
-    const int hshift = a.key_bits > kSlotBits ? a.key_bits - kSlotBits : 0;
 
-    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) t_key[s] = kEmptyKey;
-    __syncthreads();
-    // table: key -> rank (keys are distinct); group sizes -> exclusive scan
-    uint32_t cnt[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const uint32_t r = tid * 3 + q;     // 3 consecutive groups per thread: kMaxDistinct = 3 * kNT
-        cnt[q] = 0;
-        if (r < D) {
-            const unsigned long long kb = a.grp_keys[bs + r] & lowmask;
-            uint32_t s = first_slot(kb, hshift);
-            while (atomicCAS(&t_key[s], kEmptyKey, kb) != kEmptyKey) s = (s + 1) & (kSlots - 1);
-            t_rank[s] = (uint16_t)r;
-            cnt[q] = a.grp_cnt[bs + r];
-        }
-    }
+    // group sizes -> exclusive scan (4 consecutive groups per thread)
     {
-        const uint32_t sum3 = cnt[0] + cnt[1] + cnt[2];
-        uint32_t inc = sum3;
+        uint32_t cnt[4];
+        uint32_t sum4 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t r = tid * 4 + q;
+            cnt[q] = r < D ? a.grp_cnt[bs + r] : 0u;
+            sum4 += cnt[q];
+        }
+        uint32_t inc = sum4;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -337,13 +358,13 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
         }
         if (lane == 31) s_warp[wid] = inc;
         __syncthreads();
-        uint32_t run = inc - sum3;
+        uint32_t run = inc - sum4;
 #pragma unroll
         for (int w = 0; w < kNW; ++w)
             if ((uint32_t)w < wid) run += s_warp[w];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const uint32_t r = tid * 3 + q;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t r = tid * 4 + q;
             if (r < D) {
                 goff[r] = run;
                 cursor[r] = run;
@@ -366,40 +387,32 @@ __global__ void __launch_bounds__(kNT) group_place_kernel(PlaceArgs a, Out o)
         for (uint32_t r = lane; r < D; r += 32) whist[wid][r] = 0;
         __syncwarp();
         uint32_t rk[kItems], lr[kItems];
-        unsigned long long kq[kItems];
-#pragma unroll
-        for (int q = 0; q < kItems; ++q) {   // all key loads of the chunk in flight before the first is used
-            const uint32_t i = w_lo + q * 32 + lane;
-            kq[q] = ((uint32_t)q * 32 < per_warp && i < w_hi) ? a.keys[bs + c0 + i] : 0;
-        }
-#pragma unroll
-        for (int q = 0; q < kItems; ++q) {
-            rk[q] = 0xFFFFFFFFu;
-            lr[q] = 0;
-            if ((uint32_t)q * 32 < per_warp) {    // warp-uniform
-                const uint32_t i = w_lo + q * 32 + lane;
-                if (i < w_hi) {
-                    const unsigned long long kb = kq[q] & lowmask;
-                    uint32_t s = first_slot(kb, hshift);
-                    while (t_key[s] != kb) s = (s + 1) & (kSlots - 1);
-                    rk[q] = t_rank[s];
-                }
-                const uint32_t peers = __match_any_sync(0xffffffffu, rk[q]);
-                const int leader = __ffs(peers) - 1;
-                uint32_t old = 0;
-                if ((int)lane == leader && rk[q] != 0xFFFFFFFFu) {
-                    old = whist[wid][rk[q]];
-                    whist[wid][rk[q]] = (uint16_t)(old + __popc(peers));
-                }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                lr[q] = old + __popc(peers & lt_mask);
-                __syncwarp();
-            }
-        }
         typename Out::Val vq[kItems];
 #pragma unroll
-        for (int q = 0; q < kItems; ++q)   // the values are not needed before the ranks are final: load them now
-            if (rk[q] != 0xFFFFFFFFu) vq[q] = o.vals[bs + c0 + w_lo + q * 32 + lane];
+        for (int q = 0; q < kItems; ++q) {   // all loads of the chunk in flight before the first is used
+            const uint32_t i = w_lo + q * 32 + lane;
+            const bool have = (uint32_t)q * 32 < per_warp && i < w_hi;
+            rk[q] = have ? (uint32_t)a.item_rank[bs + c0 + i] : 0xFFFFFFFFu;
+            if (have) vq[q] = o.vals[bs + c0 + i];
+        }
+        if (w_lo < nc) {   // warp-uniform: warps beyond the chunk's last item have nothing to rank
+#pragma unroll
+            for (int q = 0; q < kItems; ++q) {
+                lr[q] = 0;
+                if ((uint32_t)q * 32 < w_hi - w_lo) {    // warp-uniform
+                    const uint32_t peers = __match_any_sync(0xffffffffu, rk[q]);
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if ((int)lane == leader && rk[q] != 0xFFFFFFFFu) {
+                        old = whist[wid][rk[q]];
+                        whist[wid][rk[q]] = (uint16_t)(old + __popc(peers));
+                    }
+                    old = __shfl_sync(0xffffffffu, old, leader);
+                    lr[q] = old + __popc(peers & lt_mask);
+                    __syncwarp();
+                }
+            }
+        }
         __syncthreads();
         for (uint32_t r = tid; r < D; r += kNT) {
             uint32_t run = 0;

@@ -599,6 +599,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
 
     // scratch: four arrays of M 64-bit words, carved again for the edge stage
     DevBuf<uint64_t> w0(M, s, true), w1(M, s, true), w2(M, s, true), w3(M, s, true);
+    DevBuf<uint16_t> item_rank(M, s, true);   // rank of every item's key inside its bucket (nodes, then edges)
 
     // -- nodes: partition (h1, kmer) on the top P bits, distinct hashes per bucket ----------------------------
     // bucket size: about 400 distinct hashes each, which takes an estimate of the k-mers per distinct hash
@@ -621,7 +622,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     DevBuf<unsigned long long> d64(n_buckets + 1, s, true), tot(3, s, true);
     bucket_bounds_kernel<<<stride_grid(M + 1), 256, 0, s>>>(pk, M, key_bits, n_buckets, start.p);
     group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(pk, start.p, key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
-                                                           bucket_d.p);
+                                                           bucket_d.p, item_rank.p);
     SW_CUDA(cudaMemsetAsync(tot.p, 0, 3 * sizeof(unsigned long long), s));
     SW_CUDA(cudaMemsetAsync(d64.p + n_buckets, 0, sizeof(unsigned long long), s));
     bucket_counts_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_d.p, start.p, n_buckets, d64.p, nullptr, tot.p);
@@ -643,7 +644,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     DevBuf<uint64_t> node_hash(n_nodes, s, true);
     const ArenaMark node_mark = arena_mark();   // what follows is dead once the placement kernel has run
     DevBuf<uint32_t> node_asm(score ? M : 0, s, true);
-    const PlaceArgs pa{pk, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
+    const PlaceArgs pa{item_rank.p, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
     NodeOut no{};
     no.vals = pv;
     no.placed = reinterpret_cast<unsigned long long*>(g.kmers.p);
@@ -716,7 +717,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         bucket_bounds_kernel<<<stride_grid(n_raw + 1), 256, 0, s>>>(pek, n_raw, ekey_bits, neb, estart.p);
         group_count_kernel<<<(uint32_t)neb, kNT, 0, s>>>(pek, estart.p, ekey_bits,
                                                          std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", kMaxDistinct), kMaxDistinct),
-                                                         egrp_keys, egrp_cnt, ebucket_d.p);
+                                                         egrp_keys, egrp_cnt, ebucket_d.p, item_rank.p);
         SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
         SW_CUDA(cudaMemsetAsync(ed64.p + neb, 0, sizeof(unsigned long long), s));
         SW_CUDA(cudaMemsetAsync(ovf_items.p + neb, 0, sizeof(unsigned long long), s));
@@ -768,7 +769,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         }
         g.n_edges = n_edges;
         g.edges.alloc(n_edges, s);
-        const PlaceArgs epa{pek, estart.p, ekey_bits, egrp_keys, egrp_cnt, ebucket_d.p, ebase.p};
+        const PlaceArgs epa{item_rank.p, estart.p, ekey_bits, egrp_keys, egrp_cnt, ebucket_d.p, ebase.p};
         EdgeOut eo{};
         eo.vals = pev;
         eo.placed = nullptr;

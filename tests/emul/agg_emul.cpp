@@ -65,8 +65,10 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     cuemu::launch(dim3(3), dim3(256), [&] { bucket_bounds_kernel(keys.data(), M, key_bits, nb, start.data()); });
     std::vector<uint64_t> grp_keys(M);
     std::vector<uint32_t> grp_cnt(M);
+    std::vector<uint16_t> item_rank(M, 0xEEEE);
     cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] {
-        group_count_kernel(keys.data(), start.data(), key_bits, (uint32_t)kMaxDistinct, grp_keys.data(), grp_cnt.data(), bucket_d.data());
+        group_count_kernel(keys.data(), start.data(), key_bits, (uint32_t)kMaxDistinct, grp_keys.data(), grp_cnt.data(), bucket_d.data(),
+                           item_rank.data());
     });
     std::vector<unsigned long long> d64(nb), tot(2, 0);
     cuemu::launch(dim3(2), dim3(256), [&] { bucket_counts_kernel(bucket_d.data(), start.data(), nb, d64.data(), nullptr, tot.data()); });
@@ -74,7 +76,7 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     std::vector<unsigned long long> grp_base = exclusive_scan(d64);
     const uint64_t U = grp_base[nb];
     std::vector<uint64_t> node_hash(U);
-    PlaceArgs pa{keys.data(), start.data(), key_bits, grp_keys.data(), grp_cnt.data(), bucket_d.data(), grp_base.data()};
+    PlaceArgs pa{item_rank.data(), start.data(), key_bits, grp_keys.data(), grp_cnt.data(), bucket_d.data(), grp_base.data()};
     NodeOut no{};
     no.vals = vals.data();
     no.placed = reinterpret_cast<unsigned long long*>(kmers_out);
@@ -120,8 +122,10 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     cuemu::launch(dim3(3), dim3(256), [&] { bucket_bounds_kernel(ekey.data(), E, ekey_bits, neb, estart.data()); });
     std::vector<uint64_t> egrp_keys(E);
     std::vector<uint32_t> egrp_cnt(E), placed(E);
+    std::vector<uint16_t> eitem_rank(E, 0xEEEE);
     cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
-        group_count_kernel(ekey.data(), estart.data(), ekey_bits, max_distinct_edges, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data());
+        group_count_kernel(ekey.data(), estart.data(), ekey_bits, max_distinct_edges, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data(),
+                           eitem_rank.data());
     });
     std::vector<unsigned long long> ed64(neb), ovf_items(neb), etot(2, 0);
     cuemu::launch(dim3(2), dim3(256), [&] { bucket_counts_kernel(ebucket_d.data(), estart.data(), neb, ed64.data(), ovf_items.data(), etot.data()); });
@@ -156,7 +160,7 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     }
     std::vector<unsigned long long> egrp_base = exclusive_scan(ed64);
     const uint64_t UE = egrp_base[neb];
-    PlaceArgs epa{ekey.data(), estart.data(), ekey_bits, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data(), egrp_base.data()};
+    PlaceArgs epa{eitem_rank.data(), estart.data(), ekey_bits, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data(), egrp_base.data()};
     EdgeOut eo{};
     eo.vals = easm.data();
     eo.placed = nullptr;

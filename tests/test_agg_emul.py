@@ -46,7 +46,7 @@ def _stream(spec: SynthSpec, k: int, w: int):
             np.asarray(rec_asm, dtype=np.uint32), ss.is_targets)
 
 
-def _run(L, keys, vals, rec_asm, is_t, score, per_nodes, per_edges, max_distinct_edges=768):
+def _run(L, keys, vals, rec_asm, is_t, score, per_nodes, per_edges, max_distinct_edges=1024):
     M = len(keys)
     kmers = np.zeros(M, O.KMER_DTYPE)
     nodes = np.zeros(M, O.NODE_DTYPE)
@@ -78,7 +78,7 @@ def test_emulated_aggregation_matches_oracle(agg, tmp_path, name, per_bucket):
     O._get_penalty_native(want_k, want_n, offsets, is_t)
     keys, vals, rec_asm, is_t2 = _stream(spec, k, w)
     assert len(keys) == len(want_k)
-    if per_bucket[0] >= 3000 and len(np.unique(keys)) > 768 * 2:
+    if per_bucket[0] >= 3000 and len(np.unique(keys)) > 1024 * 2:
         pytest.skip("more distinct nodes than two buckets hold")
     kmers, nodes, edges, _ = _run(agg, keys, vals, rec_asm, is_t2, True, *per_bucket)
     assert np.array_equal(kmers, want_k)
