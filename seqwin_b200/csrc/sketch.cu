@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp_sums[NT / 32];
     __shared__ unsigned long long s_gbase;
+    __shared__ GapList s_gaps;
 
     const SparseSmem S = carve_sparse_smem(smem_raw, NT, CAP);
     const int tid = threadIdx.x;
@@ -177,7 +178,10 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
     static_assert(NT * CAP < 65536, "candidate counts are scanned as 16-bit halves");
 
     for (;;) {
-        if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
+        if (tid == 0) {
+            s_tile = atomicAdd(P.tile_counter, 1u);
+            s_gaps.n = 0;
+        }
         __syncthreads();  // also: table visible / previous tile's smem reads done
         uint32_t tile_id;
         if (!next_tile(P, s_tile, &tile_id)) break;
@@ -203,21 +207,41 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
             sparseC_compact<NT, C1>(tid, mask, off, aoff, m, ma, P, T, S);
             __syncthreads();
             bool bad;
-            flags = sparseS_main<NT>(tid, m, per, P, T, S, &bad);
+            flags = sparseS_main<NT>(tid, m, per, P, T, S, &s_gaps, &bad);
             sparseS_small<NT>(tid, ma, P, T, S);
             hand_over = __syncthreads_or(bad) != 0;
+            if (!hand_over && s_gaps.n != 0) {
+                // stretches of more than w k-mers without a candidate (low-complexity sequence): their windows
+                // are evaluated directly, in the shared memory of the private lists
+                if (tid == 0) sparseG_sort(&s_gaps);
+                __syncthreads();
+                const uint32_t n_gaps = s_gaps.n;
+                for (uint32_t gi = 0; gi < n_gaps; ++gi) {
+                    sparseG_hash<NT>(tid, gi, s_gaps, P, T, S);
+                    __syncthreads();
+                    sparseG_windows<NT>(tid, gi, s_gaps, P, S);
+                    __syncthreads();
+                    if (tid == 0) sparseG_emit(gi, &s_gaps, P, T, S);
+                    __syncthreads();
+                }
+                hand_over = s_gaps.overflow != 0;
+            }
         }
         if (hand_over) {   // uniform: a dense kernel recomputes the tile
             if (tid == 0) P.fallback_tiles[atomicAdd(P.fallback_count, 1u)] = tile_id;
             continue;
         }
         flags = sparse_merge_flags(tid, m, per, flags, S);
-        const uint32_t cnt = (uint32_t)__popc(flags);
+        const uint32_t n_gaps = s_gaps.n;
+        const uint32_t cnt = (uint32_t)__popc(flags) + (n_gaps ? sparse_gap_count(tid, m, per, s_gaps) : 0u);
         uint32_t total;
         const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
         if (tid == 0) s_gbase = claim_slots(P, tile_id, total);
         __syncthreads();
-        if (cnt) sparseD_write<NT>(tid, per, flags, s_gbase + excl, P, T, S);
+        if (cnt) {
+            if (n_gaps) sparseD_write_gaps<NT>(tid, m, per, flags, s_gbase + excl, s_gaps, P, T, S);
+            else sparseD_write<NT>(tid, per, flags, s_gbase + excl, P, T, S);
+        }
     }
 }
 

@@ -646,10 +646,30 @@ constexpr uint32_t kSparseMinW = 144;      // below this the dense kernels are u
 inline double sparse_cand_per_window(uint32_t w) { return w >= 176 ? 11.0 : (double)w / 16.0; }
 inline double sparse_small_per_window(uint32_t w) { return sparse_cand_per_window(w) * 4.0 / 11.0; }
 
+// Windows without any candidate (low-complexity stretches) are settled in place: the k-mers between the
+// two candidates around such a stretch are hashed again into a workspace that overlays the private lists
+// (dead after the compaction) and their windows are evaluated directly.
+constexpr uint32_t kGapMax = 8;         // stretches per tile handled in place
+constexpr uint32_t kGapLenMax = 1024;   // k-mers per stretch
+constexpr uint32_t kGapEmitMax = 192;   // minimizers they may add per tile
+struct GapList {
+    uint32_t n;                   // stretches registered by the selection pass
+    uint32_t overflow;            // more minimizers than kGapEmitMax
+    int32_t a[kGapMax];           // tile-local index of the candidate before the stretch (-1: none)
+    int32_t b[kGapMax];           // ... and after it (n_kmers: none)
+    uint16_t owner[kGapMax];      // index in key[] of the candidate after it (m + 1: none)
+    uint16_t e0[kGapMax + 1];     // first entry of the stretch in the emit arrays
+};
+SW_HD constexpr size_t sparse_gap_ws_words() { return kGapLenMax + kGapLenMax / 4 + kGapEmitMax + kGapEmitMax / 4; }
+SW_HD constexpr size_t sparse_list_words(uint32_t nt, uint32_t cap)
+{
+    return (size_t)cap * nt > sparse_gap_ws_words() ? (size_t)cap * nt : sparse_gap_ws_words();
+}
+
 SW_HD size_t sparse_smem_bytes(uint32_t nt, uint32_t cap)
 {
     const size_t mc = (size_t)sparse_mc(nt) + 2, ma = (size_t)sparse_ma(nt) + 2;
-    size_t b = sizeof(RollEntry) * 20 + sizeof(uint64_t) * ((size_t)cap * nt + mc + ma);
+    size_t b = sizeof(RollEntry) * 20 + sizeof(uint64_t) * (sparse_list_words(nt, cap) + mc + ma);
     b += sizeof(uint32_t) * (mc + mc / 32 + 2) + sizeof(uint16_t) * (ma + mc);
     return (b + 15) & ~(size_t)15;
 }
@@ -660,7 +680,7 @@ SW_HD SparseSmem carve_sparse_smem(unsigned char* base, uint32_t nt, uint32_t ca
     SparseSmem s;
     s.tab = reinterpret_cast<RollEntry*>(base);
     s.list = reinterpret_cast<uint64_t*>(base + sizeof(RollEntry) * 20);
-    s.key = s.list + (size_t)cap * nt;
+    s.key = s.list + sparse_list_words(nt, cap);
     s.akey = s.key + mc;
     s.lo = reinterpret_cast<uint32_t*>(s.akey + ma);
     s.selbits = s.lo + mc;
@@ -878,9 +898,23 @@ SW_HD void sparseS_small(int tid, uint32_t ma, const SketchParams& P, const Tile
 // S (main pass): thread owns candidates [1 + tid * per, 1 + (tid + 1) * per) of m; the small ones
 // are skipped.  Returns the selection flags of its other candidates (bit i: candidate
 // 1 + tid * per + i); *bad is set if some window of the tile holds no candidate.
+SW_HD void gap_register(GapList* G, int32_t a, int32_t b, uint32_t owner, bool* bad)
+{
+    if ((uint32_t)(b - a - 1) > kGapLenMax) { *bad = true; return; }
+#if defined(__CUDA_ARCH__)
+    const uint32_t i = atomicAdd(&G->n, 1u);
+#else
+    const uint32_t i = G->n++;
+#endif
+    if (i >= kGapMax) { *bad = true; return; }
+    G->a[i] = a;
+    G->b[i] = b;
+    G->owner[i] = (uint16_t)owner;
+}
+
 template <int NT>
 SW_HD uint32_t sparseS_main(int tid, uint32_t m, uint32_t per, const SketchParams& P, const Tile& T,
-                            const SparseSmem& S, bool* bad)
+                            const SparseSmem& S, GapList* G, bool* bad)
 {
     const int32_t w = (int32_t)P.w, n = (int32_t)T.n_kmers;
     uint32_t f = 0;
@@ -893,7 +927,8 @@ SW_HD uint32_t sparseS_main(int tid, uint32_t m, uint32_t per, const SketchParam
         const uint32_t hh = (uint32_t)kj;
         // coverage: no stretch of w k-mers without candidate before this one / after the last one
         const int32_t prev = (int32_t)(S.key[j - 1] >> 32);
-        if (p - prev > w || (j == m && n - p > w)) *bad = true;
+        if (p - prev > w) gap_register(G, prev, p, j, bad);
+        if (j == m && n - p > w) gap_register(G, p, n, m + 1, bad);
         if (hh < P.cand_hi_a) continue;
         // every small candidate is smaller: unless w k-mers fit between the nearest ones on either
         // side (about one window in fifty has no small candidate), this one is never selected
@@ -934,6 +969,151 @@ SW_HD void sparseD_write(int tid, uint32_t per, uint32_t flags, unsigned long lo
             P.out_val[slot] = (uint64_t)pos | ((uint64_t)(P.rec_base + T.rec) << 32);
         }
         ++slot;
+    }
+}
+
+// ---- stretches without a candidate ---------------------------------------------------------------------
+struct GapWs {
+    uint64_t* h;      // [kGapLenMax] h0 of the stretch's k-mers
+    uint16_t* sel;    // [kGapLenMax] selection of every window of the stretch (index into h)
+    uint64_t* eh;     // [kGapEmitMax] h0 of the minimizers to add
+    uint16_t* ep;     // [kGapEmitMax] their tile-local k-mer index
+};
+SW_HD GapWs gap_workspace(const SparseSmem& S)
+{
+    GapWs g;
+    g.h = S.list;
+    g.sel = reinterpret_cast<uint16_t*>(S.list + kGapLenMax);
+    g.eh = S.list + kGapLenMax + kGapLenMax / 4;
+    g.ep = reinterpret_cast<uint16_t*>(g.eh + kGapEmitMax);
+    return g;
+}
+
+// one thread: order the stretches by position (they were registered in any order)
+SW_HD void sparseG_sort(GapList* G)
+{
+    for (uint32_t i = 1; i < G->n; ++i)
+        for (uint32_t j = i; j > 0 && G->a[j] < G->a[j - 1]; --j) {
+            const int32_t ta = G->a[j], tb = G->b[j];
+            const uint16_t to = G->owner[j];
+            G->a[j] = G->a[j - 1]; G->b[j] = G->b[j - 1]; G->owner[j] = G->owner[j - 1];
+            G->a[j - 1] = ta; G->b[j - 1] = tb; G->owner[j - 1] = to;
+        }
+    G->e0[0] = 0;
+    G->overflow = 0;
+}
+
+// thread t hashes k-mers [16 t, 16 t + 16), [16 (t + NT), ...) ... of stretch gi (one seed, then rolling steps)
+template <int NT>
+SW_HD void sparseG_hash(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const Tile& T, const SparseSmem& S)
+{
+    const GapWs ws = gap_workspace(S);
+    const uint32_t g = (uint32_t)(G.b[gi] - G.a[gi] - 1);
+    const uint32_t* W = P.words + P.rec_word_off[T.rec];
+    const Piece pc = P.pieces[T.piece_lo];
+    for (uint32_t q0 = (uint32_t)tid * 16; q0 < g; q0 += NT * 16) {
+        const uint32_t q1 = q0 + 16 < g ? q0 + 16 : g;
+        uint64_t p = (uint64_t)pc.pos + ((uint64_t)T.e0 + (uint32_t)(G.a[gi] + 1) + q0 - pc.kidx);
+        uint64_t fwd, rev;
+        seed_kmer(W, p, P.k, S.tab, P.tetra, &fwd, &rev);
+        ws.h[q0] = fwd + rev;
+        for (uint32_t q = q0 + 1; q < q1; ++q, ++p) {
+            roll_step(fwd, rev, S.tab[(base_at(W, p) << 2) | base_at(W, p + P.k)]);
+            ws.h[q] = fwd + rev;
+        }
+    }
+}
+
+// thread t evaluates windows t, t + NT, ... of the stretch: rightmost minimum of w consecutive k-mers
+template <int NT>
+SW_HD void sparseG_windows(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const SparseSmem& S)
+{
+    const GapWs ws = gap_workspace(S);
+    const uint32_t g = (uint32_t)(G.b[gi] - G.a[gi] - 1), nw = g - P.w + 1;
+    for (uint32_t i = (uint32_t)tid; i < nw; i += NT) {
+        uint64_t best = ws.h[i];
+        uint32_t arg = i;
+        for (uint32_t x = 1; x < P.w; ++x) {
+            const uint64_t h = ws.h[i + x];
+            if (h <= best) { best = h; arg = i + x; }
+        }
+        ws.sel[i] = (uint16_t)arg;
+    }
+}
+
+// one thread: the windows' selections, each once, in position order (minimizer.cpp:41-47)
+SW_HD void sparseG_emit(uint32_t gi, GapList* G, const SketchParams& P, const Tile& T, const SparseSmem& S)
+{
+    const GapWs ws = gap_workspace(S);
+    const int32_t a = G->a[gi];
+    const uint32_t g = (uint32_t)(G->b[gi] - a - 1), nw = g - P.w + 1;
+    uint32_t e = G->e0[gi];
+    for (uint32_t i = 0; i < nw; ++i) {
+        const uint32_t sel = ws.sel[i];
+        // the window before the stretch's first one selected the candidate at a; window 0 of a tile that
+        // is not the record's first only provides the previous selection
+        const bool emit = i == 0 ? (a >= 0 || T.first != 0) : sel != ws.sel[i - 1];
+        if (!emit || ws.h[sel] == ~0ull) continue;
+        if (e >= kGapEmitMax) { G->overflow = 1; break; }
+        ws.eh[e] = ws.h[sel];
+        ws.ep[e] = (uint16_t)((uint32_t)(a + 1) + sel);
+        ++e;
+    }
+    G->e0[gi + 1] = (uint16_t)e;
+}
+
+// which thread writes the minimizers of stretch gi: the owner of the candidate after it
+SW_HD uint32_t gap_owner_thread(const GapList& G, uint32_t gi, uint32_t m, uint32_t per)
+{
+    const uint32_t j = G.owner[gi] <= m ? G.owner[gi] : m;
+    return (j - 1) / per;
+}
+
+SW_HD uint32_t sparse_gap_count(int tid, uint32_t m, uint32_t per, const GapList& G)
+{
+    uint32_t c = 0;
+    for (uint32_t gi = 0; gi < G.n; ++gi)
+        if (gap_owner_thread(G, gi, m, per) == (uint32_t)tid) c += (uint32_t)G.e0[gi + 1] - G.e0[gi];
+    return c;
+}
+
+SW_HD void gap_write(uint32_t gi, unsigned long long& slot, const GapList& G, const Piece& pc, const SketchParams& P,
+                     const Tile& T, const SparseSmem& S)
+{
+    const GapWs ws = gap_workspace(S);
+    for (uint32_t e = G.e0[gi]; e < G.e0[gi + 1]; ++e, ++slot) {
+        if (slot < P.capacity) {
+            P.out_key[slot] = h1_of(ws.eh[e], P.h1_mult);
+            const uint32_t pos = pc.pos + (uint32_t)((uint64_t)T.e0 + ws.ep[e] - pc.kidx);
+            P.out_val[slot] = (uint64_t)pos | ((uint64_t)(P.rec_base + T.rec) << 32);
+        }
+    }
+}
+
+// D with stretches: the thread's candidates in order, each preceded by the minimizers of the stretch before it
+template <int NT>
+SW_HD void sparseD_write_gaps(int tid, uint32_t m, uint32_t per, uint32_t flags, unsigned long long slot, const GapList& G,
+                              const SketchParams& P, const Tile& T, const SparseSmem& S)
+{
+    const Piece pc = P.pieces[T.piece_lo];
+    for (uint32_t i = 0; i < per; ++i) {
+        const uint32_t j = 1 + (uint32_t)tid * per + i;
+        if (j > m) break;
+        for (uint32_t gi = 0; gi < G.n; ++gi)
+            if (G.owner[gi] == j) gap_write(gi, slot, G, pc, P, T, S);
+        if (flags & (1u << i)) {
+            const uint64_t kj = S.key[j];
+            const uint64_t h = (kj << 32) | S.lo[j];
+            if (slot < P.capacity) {
+                P.out_key[slot] = h1_of(h, P.h1_mult);
+                const uint32_t pos = pc.pos + (uint32_t)((uint64_t)T.e0 + (uint32_t)(kj >> 32) - pc.kidx);
+                P.out_val[slot] = (uint64_t)pos | ((uint64_t)(P.rec_base + T.rec) << 32);
+            }
+            ++slot;
+        }
+        if (j == m)
+            for (uint32_t gi = 0; gi < G.n; ++gi)
+                if (G.owner[gi] == m + 1) gap_write(gi, slot, G, pc, P, T, S);
     }
 }
 

@@ -171,17 +171,20 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
     // block of exactly its size, so that AddressSanitizer sees an overrun from one array into the next
     const size_t mc = sparse_mc(NT) + 2, ma = sparse_ma(NT) + 2;
     std::vector<RollEntry> v_tab(20);
-    std::vector<uint64_t> v_list((size_t)CAP * NT), v_key(mc), v_akey(ma);
+    std::vector<uint64_t> v_list(sparse_list_words(NT, CAP)), v_key(mc), v_akey(ma);
     std::vector<uint32_t> v_lo(mc), v_sel(mc / 32 + 2);
     std::vector<uint16_t> v_aj(ma), v_na(mc);
     S = SparseSmem{v_tab.data(), v_list.data(), v_key.data(), v_akey.data(), v_lo.data(), v_sel.data(), v_aj.data(), v_na.data()};
 #endif
     std::vector<uint32_t> fallback;
+    uint32_t n_gap_tiles = 0;
     for (uint32_t t : scrambled_order(P.n_tiles)) {
         memset(smem.data(), 0xA5, smem.size());
         for (int i = 0; i < 20; ++i) S.tab[i] = P.table.e[i];
         const Tile T = P.tiles[t];
         std::vector<uint64_t> mask(NT, 0);
+        GapList gaps;
+        memset(&gaps, 0, sizeof(gaps));
         bool hand_over = T.n_pieces != 1;
         if (!hand_over)
             for (int tid = 0; tid < NT; ++tid)
@@ -203,9 +206,19 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
             for (int tid = 0; tid < NT; ++tid) sparseC_compact<NT, C1>(tid, mask[tid], off[tid], aoff[tid], m, ma, P, T, S);
             for (int tid = 0; tid < NT; ++tid) {
                 bool bad;
-                flags[tid] = sparseS_main<NT>(tid, m, per, P, T, S, &bad);
+                flags[tid] = sparseS_main<NT>(tid, m, per, P, T, S, &gaps, &bad);
                 sparseS_small<NT>(tid, ma, P, T, S);
                 if (bad) hand_over = true;
+            }
+            if (!hand_over && gaps.n != 0) {
+                sparseG_sort(&gaps);
+                for (uint32_t gi = 0; gi < gaps.n; ++gi) {
+                    for (int tid = 0; tid < NT; ++tid) sparseG_hash<NT>(tid, gi, gaps, P, T, S);
+                    for (int tid = 0; tid < NT; ++tid) sparseG_windows<NT>(tid, gi, gaps, P, S);
+                    sparseG_emit(gi, &gaps, P, T, S);
+                }
+                hand_over = gaps.overflow != 0;
+                if (!hand_over) ++n_gap_tiles;
             }
         }
         if (hand_over) { fallback.push_back(t); continue; }
@@ -213,15 +226,19 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
         for (int tid = 0; tid < NT; ++tid) {
             flags[tid] = sparse_merge_flags(tid, m, per, flags[tid], S);
             excl[tid] = total;
-            total += (uint32_t)__builtin_popcount(flags[tid]);
+            total += (uint32_t)__builtin_popcount(flags[tid]) + (gaps.n ? sparse_gap_count(tid, m, per, gaps) : 0u);
         }
         o.tile_count[t] = total;
         o.tile_slot[t] = o.cursor;
-        for (int tid = 0; tid < NT; ++tid)
-            if (flags[tid]) sparseD_write<NT>(tid, per, flags[tid], o.cursor + excl[tid], P, T, S);
+        for (int tid = 0; tid < NT; ++tid) {
+            if (gaps.n) sparseD_write_gaps<NT>(tid, m, per, flags[tid], o.cursor + excl[tid], gaps, P, T, S);
+            else if (flags[tid]) sparseD_write<NT>(tid, per, flags[tid], o.cursor + excl[tid], P, T, S);
+        }
         o.cursor += total;
     }
     *n_fallback_out = (uint32_t)fallback.size();
+    if (getenv("EMUL_GAP_STATS")) fprintf(stderr, "[emul] %u tiles, %zu handed over, %u settled stretches in place\n",
+                                          P.n_tiles, fallback.size(), n_gap_tiles);
     const bool fast = w - 1 >= (uint32_t)FC1;
     for (uint32_t t : fallback) dense_tile<FNT, FC1>(P, t, fast, o);
     reorder(o, keys, vals);
