@@ -26,6 +26,7 @@
 #include <cstdint>
 
 #include "common.h"
+#include "sample.cuh"
 
 namespace sw {
 namespace agg {
@@ -38,7 +39,7 @@ constexpr int kMaxDistinct = 1024;           // distinct keys a bucket may hold 
 constexpr int kItems = 8;                    // items per thread and placement chunk
 constexpr int kChunk = kNT * kItems;
 static_assert(kMaxDistinct == 4 * kNT, "group_place_kernel scans 4 groups per thread");
-constexpr unsigned long long kEmptyKey = ~0ull;   // in-bucket keys have their top P >= 1 bits cleared
+// kEmptyKey (sample.cuh): in-bucket keys have their top P >= 1 bits cleared, so ~0 never occurs
 constexpr uint32_t kOverflow = 0xFFFFFFFFu;       // bucket_d value of a bucket left to the sort-based path
 
 // smallest P >= 1 with n / 2^P <= per_bucket
@@ -68,43 +69,12 @@ __device__ __forceinline__ uint32_t first_slot(uint64_t kb, int = 0)
     return (uint32_t)((kb * 0x9E3779B97F4A7C15ull) >> (64 - kSlotBits));
 }
 
-// ---- how many items per distinct key?  (sizes the buckets) ----------------------------------------------------
-// A hash-range sample: every item whose mixed key has its top `sbits` bits zero -- i.e. ALL occurrences of
-// about 1 in 2^sbits distinct keys -- is counted (out[0]) and inserted into a small global set (out[1] =
-// distinct keys inserted).  out[0] / out[1] estimates items per distinct key without bias.
-constexpr int kSampleSetBits = 17;
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
-{
-    x ^= x >> 31;
-    x *= 0x9E3779B97F4A7C15ull;
-    x ^= x >> 29;
-    return x;
-}
 __global__ void __launch_bounds__(256) distinct_sample_kernel(const uint64_t* __restrict__ keys, uint64_t n, int sbits,
                                                               unsigned long long* __restrict__ set, unsigned long long* out)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long k = keys[i];
-        const unsigned long long m = mix64(k);
-        if (sbits && (m >> (64 - sbits)) != 0) continue;
-        atomicAdd(&out[0], 1ull);
-        uint32_t s = (uint32_t)(m >> 8) & ((1u << kSampleSetBits) - 1);
-        const unsigned long long tag = k == kEmptyKey ? k - 1 : k;   // the empty marker cannot be stored (off by one key at most)
-        for (int probes = 0; probes < 4096; ++probes) {
-            const unsigned long long prev = atomicCAS(&set[s], kEmptyKey, tag);
-            if (prev == kEmptyKey) atomicAdd(&out[1], 1ull);
-            if (prev == kEmptyKey || prev == tag) break;
-            s = (s + 1) & ((1u << kSampleSetBits) - 1);
-        }
-    }
-}
-// sample 1 key in 2^sbits so that about 2^15 items are looked at
-inline int sample_bits(uint64_t n)
-{
-    int b = 0;
-    while (b < 40 && (n >> b) > (1ull << 15)) ++b;
-    return b;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        distinct_sample_item(keys[i], sbits, set, out);
 }
 // bucket bits from the estimate: `distinct_target` distinct keys per bucket on average, at most max_items items
 inline int partition_bits_for(uint64_t n, double items_per_key, double distinct_target, uint32_t max_items)
@@ -148,7 +118,9 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
     __shared__ uint32_t t_cnt[kSlots];              // items per slot; afterwards: rank of the slot's key
     __shared__ unsigned long long dk[kMaxDistinct];
     __shared__ uint16_t dslot[kMaxDistinct];
-    __shared__ uint32_t s_n, s_m;
+    __shared__ uint32_t s_sub[kNT], s_sub_start[kNT + 1], s_wsum[kNW];
+    __shared__ uint32_t s_n;
+    static_assert(kNT == 256, "one thread per 8-bit sub-range");
     const uint32_t b = blockIdx.x, tid = threadIdx.x;
     const uint32_t bs = start[b], n = start[b + 1] - bs;
     if (n == 0) {
@@ -159,7 +131,7 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
         t_key[s] = kEmptyKey;
         t_cnt[s] = 0;
     }
-    if (tid == 0) { s_n = 0; s_m = 0; }
+    if (tid == 0) s_n = 0;
     __syncthreads();
     const uint64_t lowmask = (1ull << key_bits) - 1;
     for (uint32_t i0 = tid; i0 < n; i0 += 4 * kNT) {
@@ -186,9 +158,37 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
         if (tid == 0) bucket_d[b] = kOverflow;
         return;
     }
+    // distinct keys in ascending order: first by their next 8 key bits (a counting sort into dk[]), then each
+    // key is ranked against the few keys that share those bits
+    const int sshift = key_bits > 8 ? key_bits - 8 : 0;
+    s_sub[tid] = 0;
+    __syncthreads();
+    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT)
+        if (t_key[s] != kEmptyKey) atomicAdd(&s_sub[(uint32_t)(t_key[s] >> sshift) & 255u], 1u);
+    __syncthreads();
+    {
+        const uint32_t lane = tid & 31, wid = tid >> 5;
+        const uint32_t c = s_sub[tid];
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        uint32_t ex = inc - c;
+#pragma unroll
+        for (int w = 0; w < kNW; ++w)
+            if ((uint32_t)w < wid) ex += s_wsum[w];
+        s_sub_start[tid] = ex;
+        s_sub[tid] = ex;           // now: cursor of the sub-range
+        if (tid == kNT - 1) s_sub_start[kNT] = ex + c;
+    }
+    __syncthreads();
     for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) {
         if (t_key[s] != kEmptyKey) {
-            const uint32_t i = atomicAdd(&s_m, 1u);
+            const uint32_t i = atomicAdd(&s_sub[(uint32_t)(t_key[s] >> sshift) & 255u], 1u);
             dk[i] = t_key[s];
             dslot[i] = (uint16_t)s;
         }
@@ -197,8 +197,10 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
     const uint64_t prefix = (uint64_t)b << key_bits;
     for (uint32_t i = tid; i < D; i += kNT) {
         const unsigned long long k = dk[i];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < D; ++j) r += dk[j] < k ? 1u : 0u;
+        const uint32_t sb = (uint32_t)(k >> sshift) & 255u;
+        const uint32_t lo = s_sub_start[sb], hi = s_sub_start[sb + 1];
+        uint32_t r = lo;
+        for (uint32_t j = lo; j < hi; ++j) r += dk[j] < k ? 1u : 0u;
         const uint32_t sl = dslot[i];
         grp_keys[bs + r] = k | prefix;
         grp_cnt[bs + r] = t_cnt[sl];
@@ -490,7 +492,8 @@ __global__ void __launch_bounds__(kNT) edge_emit_kernel(const uint64_t* __restri
                                                         const uint32_t* __restrict__ ftable, int fshift,
                                                         const uint32_t* __restrict__ rec_asm, uint32_t rec_base,
                                                         const unsigned long long* __restrict__ block_off, int rank_bits,
-                                                        uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm)
+                                                        uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm, int sbits,
+                                                        unsigned long long* __restrict__ sample_set, unsigned long long* sample_out)
 {
     __shared__ uint32_t s_rank[kEmitItems + 1];
     __shared__ uint32_t s_cnt[8][kNW];
@@ -531,8 +534,10 @@ __global__ void __launch_bounds__(kNT) edge_emit_kernel(const uint64_t* __restri
             uint32_t u = s_rank[t], v = s_rank[t + 1];
             if (v < u) { const uint32_t x = u; u = v; v = x; }
             const unsigned long long slot = running + before + prefix[r];
-            ekey[slot] = ((uint64_t)u << (64 - rank_bits)) | ((uint64_t)v << (64 - 2 * rank_bits));
+            const uint64_t key = ((uint64_t)u << (64 - rank_bits)) | ((uint64_t)v << (64 - 2 * rank_bits));
+            ekey[slot] = key;
             easm[slot] = rec_asm[rec[r] - rec_base];
+            if (sample_set) distinct_sample_item(key, sbits, sample_set, sample_out);   // records per distinct pair (bucket sizing)
         }
         running += total;
     }

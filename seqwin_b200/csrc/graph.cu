@@ -604,8 +604,11 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     // -- nodes: partition (h1, kmer) on the top P bits, distinct hashes per bucket ----------------------------
     // bucket size: about 400 distinct hashes each, which takes an estimate of the k-mers per distinct hash
     DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
-    const double per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
-    tm.launches += 1;
+    double per_node = st.items_per_key;   // taken by the sketch's reorder pass; a stream from elsewhere is sampled here
+    if (per_node <= 0) {
+        per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
+        tm.launches += 1;
+    }
     const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
     const int P = fixed_nb ? partition_bits(M, fixed_nb)
                            : partition_bits_for(M, per_node, 400.0, env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
@@ -685,8 +688,11 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         while (fbits < 28 && (1ull << fbits) < n_nodes) ++fbits;
         DevBuf<uint32_t> ftable((1ull << fbits) + 1, s, true);
         bucket_bounds_kernel<<<stride_grid(n_nodes + 1), 256, 0, s>>>(node_hash.p, n_nodes, 64 - fbits, 1ull << fbits, ftable.p);
+        // the emitter also takes the hash-range sample of its keys (records per distinct pair)
+        SW_CUDA(cudaMemsetAsync(sample_set.p, 0xFF, sample_set.bytes(), s));
+        SW_CUDA(cudaMemsetAsync(sample_out.p, 0, sample_out.bytes(), s));
         edge_emit_kernel<<<nb, kNT, 0, s>>>(st.keys.p, st.vals.p, M, node_hash.p, ftable.p, 64 - fbits, d_rec_asm, rec_base, ecnt.p,
-                                            rank_bits, ekey0, easm0);
+                                            rank_bits, ekey0, easm0, sample_bits(n_raw), sample_set.p, sample_out.p);
         SW_CUDA(cudaGetLastError());
         tm.launches += 2;
     }
@@ -699,8 +705,9 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         evb.alloc(M, s, true);
         placed.alloc(M, s, true);
         // records per distinct pair -> about 192 distinct pairs per bucket (min(u, v) makes the low buckets twice as full)
-        const double per_edge = estimate_items_per_key(ekey0, n_raw, sample_set.p, sample_out.p, s);
-        tm.launches += 1;
+        const unsigned long long* eh = readback_u64(sample_out.p, 2, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        const double per_edge = eh[1] ? (double)eh[0] / (double)eh[1] : 1.0;
         const uint32_t fixed_eb = env_u32("SEQWIN_AGG_EDGE_BUCKET", 0);
         const int Pe = std::min(fixed_eb ? partition_bits(n_raw, fixed_eb)
                                          : partition_bits_for(n_raw, per_edge, 192.0, env_u32("SEQWIN_AGG_MAX_ITEMS", 4096)),

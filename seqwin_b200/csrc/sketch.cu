@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "device.h"
+#include "sample.cuh"
 #include "nthash.h"
 #include "scan.cuh"
 #include "sketch_tile.h"
@@ -178,14 +179,14 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
     static_assert(NT * CAP < 65536, "candidate counts are scanned as 16-bit halves");
 
     for (;;) {
-        if (tid == 0) {
-            s_tile = atomicAdd(P.tile_counter, 1u);
-            s_gaps.n = 0;
-        }
+        if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1u);
         __syncthreads();  // also: table visible / previous tile's smem reads done
         uint32_t tile_id;
         if (!next_tile(P, s_tile, &tile_id)) break;
         const Tile T = P.tiles[tile_id];
+        // every thread is past the previous tile's write phase (which reads the stretch list); the selection
+        // pass that fills it again comes several barriers later
+        if (tid == 0) s_gaps.n = 0;
 
         uint64_t mask = 0;
         bool ok = T.n_pieces == 1;
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(256) reorder_kernel(const uint64_t* __restrict
                                                       const unsigned long long* __restrict__ tile_off,
                                                       const unsigned long long* __restrict__ tile_slot, uint32_t n_tiles,
                                                       unsigned long long total, uint64_t* __restrict__ okey,
-                                                      uint64_t* __restrict__ oval)
+                                                      uint64_t* __restrict__ oval, int sbits,
+                                                      unsigned long long* __restrict__ sample_set, unsigned long long* sample_out)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -261,7 +263,9 @@ __global__ void __launch_bounds__(256) reorder_kernel(const uint64_t* __restrict
         const unsigned long long src = tile_slot[t];
         const uint32_t n = (uint32_t)(end - dst);
         for (uint32_t i = lane; i < n; i += 32) {
-            okey[dst + i] = ukey[src + i];
+            const uint64_t key = ukey[src + i];
+            okey[dst + i] = key;
+            agg::distinct_sample_item(key, sbits, sample_set, sample_out);   // k-mers per distinct hash: sizes the node buckets
             oval[dst + i] = uval[src + i];
         }
     }
@@ -458,6 +462,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
 {
     out.n = 0;
     out.launches = 0;
+    out.items_per_key = 0;
     if (plan.n_tiles == 0) {
         out.keys.alloc(0, s, true);
         out.vals.alloc(0, s, true);
@@ -501,6 +506,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     capacity = std::min<uint64_t>(capacity, plan.n_windows);
     // The ordered stream is allocated first, with the capacity of the unordered one, so that the unordered
     // buffers (dead after the reorder) sit on top of the scratch arena and can be handed back.
+    DevBuf<unsigned long long> sample_set(1ull << agg::kSampleSetBits, s, true), sample_out(2, s, true);
     DevBuf<uint64_t> ukeys, uvals;
     const ArenaMark stream_mark = arena_mark();
     ArenaMark unordered_mark = stream_mark;
@@ -593,13 +599,18 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     cudaEventRecord(ev[2], s);
     exclusive_scan_u64(tile_info.p, plan.n_tiles, counters.p + 1, s);
     const uint32_t rgrid = (uint32_t)std::min<uint64_t>(((uint64_t)plan.n_tiles + 7) / 8, (uint64_t)sm_count() * 8);
+    SW_CUDA(cudaMemsetAsync(sample_set.p, 0xFF, sample_set.bytes(), s));
+    SW_CUDA(cudaMemsetAsync(sample_out.p, 0, sample_out.bytes(), s));
     reorder_kernel<<<rgrid, 256, 0, s>>>(ukeys.p, uvals.p, tile_info.p, tile_info.p + plan.n_tiles, plan.n_tiles,
-                                         total, out.keys.p, out.vals.p);
+                                         total, out.keys.p, out.vals.p, agg::sample_bits(total), sample_set.p, sample_out.p);
+    const unsigned long long* sample_h = readback_u64(sample_out.p, 2, s);
     cudaEventRecord(ev[3], s);
     SW_CUDA(cudaGetLastError());
     out.launches += 2;
     SW_CUDA(cudaEventSynchronize(ev[3]));
     cudaEventElapsedTime(&out.reorder_ms, ev[2], ev[3]);
+    SW_CUDA(cudaStreamSynchronize(s));   // the readback kernel follows the event
+    out.items_per_key = sample_h[1] ? (double)sample_h[0] / (double)sample_h[1] : 1.0;
     arena_release(unordered_mark);   // the reorder has finished: the unordered buffers go back to the arena
 }
 

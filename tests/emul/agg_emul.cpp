@@ -112,7 +112,7 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     std::vector<uint32_t> easm(E);
     cuemu::launch(dim3(n_blocks), dim3(kNT), [&] {
         edge_emit_kernel(stream_keys, stream_vals, M, node_hash.data(), ftable.data(), 64 - fbits, rec_asm, rec_base,
-                         block_off.data(), rank_bits, ekey.data(), easm.data());
+                         block_off.data(), rank_bits, ekey.data(), easm.data(), 0, nullptr, nullptr);
     });
     const int Pe = partition_bits(E, per_bucket_edges);
     const int ekey_bits = 64 - Pe;
