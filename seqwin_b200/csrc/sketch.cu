@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
                     if (tid == 0) sparseG_emit(gi, &s_gaps, P, T, S);
                     __syncthreads();
                 }
-                hand_over = s_gaps.overflow != 0;
+                hand_over = (s_gaps.n & kGapOverflow) != 0;
             }
         }
         if (hand_over) {   // uniform: a dense kernel recomputes the tile

@@ -649,17 +649,18 @@ inline double sparse_small_per_window(uint32_t w) { return sparse_cand_per_windo
 // Windows without any candidate (low-complexity stretches) are settled in place: the k-mers between the
 // two candidates around such a stretch are hashed again into a workspace that overlays the private lists
 // (dead after the compaction) and their windows are evaluated directly.
-constexpr uint32_t kGapMax = 8;         // stretches per tile handled in place
+constexpr uint32_t kGapMax = 6;         // stretches per tile handled in place
 constexpr uint32_t kGapLenMax = 1024;   // k-mers per stretch
 constexpr uint32_t kGapEmitMax = 192;   // minimizers they may add per tile
+// (kept small: the sparse kernel's shared memory is sized to the byte for 7 CTAs per SM)
 struct GapList {
-    uint32_t n;                   // stretches registered by the selection pass
-    uint32_t overflow;            // more minimizers than kGapEmitMax
-    int32_t a[kGapMax];           // tile-local index of the candidate before the stretch (-1: none)
-    int32_t b[kGapMax];           // ... and after it (n_kmers: none)
+    uint32_t n;                   // stretches registered by the selection pass; bit 31: more minimizers than kGapEmitMax
+    int16_t a[kGapMax];           // tile-local index of the candidate before the stretch (-1: none)
+    int16_t b[kGapMax];           // ... and after it (n_kmers: none)
     uint16_t owner[kGapMax];      // index in key[] of the candidate after it (m + 1: none)
     uint16_t e0[kGapMax + 1];     // first entry of the stretch in the emit arrays
 };
+constexpr uint32_t kGapOverflow = 0x80000000u;
 SW_HD constexpr size_t sparse_gap_ws_words() { return kGapLenMax + kGapLenMax / 4 + kGapEmitMax + kGapEmitMax / 4; }
 SW_HD constexpr size_t sparse_list_words(uint32_t nt, uint32_t cap)
 {
@@ -907,8 +908,8 @@ SW_HD void gap_register(GapList* G, int32_t a, int32_t b, uint32_t owner, bool* 
     const uint32_t i = G->n++;
 #endif
     if (i >= kGapMax) { *bad = true; return; }
-    G->a[i] = a;
-    G->b[i] = b;
+    G->a[i] = (int16_t)a;
+    G->b[i] = (int16_t)b;
     G->owner[i] = (uint16_t)owner;
 }
 
@@ -994,13 +995,12 @@ SW_HD void sparseG_sort(GapList* G)
 {
     for (uint32_t i = 1; i < G->n; ++i)
         for (uint32_t j = i; j > 0 && G->a[j] < G->a[j - 1]; --j) {
-            const int32_t ta = G->a[j], tb = G->b[j];
+            const int16_t ta = G->a[j], tb = G->b[j];
             const uint16_t to = G->owner[j];
             G->a[j] = G->a[j - 1]; G->b[j] = G->b[j - 1]; G->owner[j] = G->owner[j - 1];
             G->a[j - 1] = ta; G->b[j - 1] = tb; G->owner[j - 1] = to;
         }
     G->e0[0] = 0;
-    G->overflow = 0;
 }
 
 // thread t hashes k-mers [16 t, 16 t + 16), [16 (t + NT), ...) ... of stretch gi (one seed, then rolling steps)
@@ -1054,7 +1054,7 @@ SW_HD void sparseG_emit(uint32_t gi, GapList* G, const SketchParams& P, const Ti
         // is not the record's first only provides the previous selection
         const bool emit = i == 0 ? (a >= 0 || T.first != 0) : sel != ws.sel[i - 1];
         if (!emit || ws.h[sel] == ~0ull) continue;
-        if (e >= kGapEmitMax) { G->overflow = 1; break; }
+        if (e >= kGapEmitMax) { G->n |= kGapOverflow; break; }
         ws.eh[e] = ws.h[sel];
         ws.ep[e] = (uint16_t)((uint32_t)(a + 1) + sel);
         ++e;
