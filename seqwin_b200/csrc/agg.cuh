@@ -2,17 +2,18 @@
 //
 // The minimizer stream (h1, pos | record << 32) and the adjacent-pair records (rank pair, assembly) are
 // both aggregated the same way: a STABLE partition on the top P bits of the key (radix.cu, 1-3 passes)
-// leaves every bucket holding a few hundred items in input order; one CTA then groups a bucket by key in
-// shared memory -- an open-addressing table of its distinct keys -- and
+// leaves every bucket holding a few hundred to a few thousand items in input order; one CTA then groups a
+// bucket by key in shared memory -- an open-addressing table of its distinct keys.
 //
-//   group_count_kernel   counts the items of every distinct key and writes the bucket's distinct keys in
-//                        ascending order (rank by counting) next to their sizes,
-//   group_place_kernel   after an exclusive scan of the per-bucket distinct counts: moves every item to its
-//                        final place -- group offset + stable rank inside the group, so a node's k-mers stay
-//                        in (record, pos) order and an edge's records in assembly order --, counts the
-//                        distinct assemblies of every group (by class for nodes: get_penalty,
-//                        cpp/src/seqwin/filter.cpp:92-136; once for edges: the edge weight,
-//                        cpp/src/seqwin/build.cpp:177-189) and writes the nodes / edges.
+//   nodes   group_count_kernel  counts the items of every distinct hash and writes the bucket's distinct hashes in
+//                               ascending order (rank by counting) next to their sizes,
+//           group_place_kernel  after an exclusive scan of the per-bucket distinct counts: moves every k-mer to its
+//                               final place -- group offset + stable rank inside the group, so a node's k-mers
+//                               stay in (record, pos) order --, counts the distinct assemblies of every node by
+//                               class (get_penalty, cpp/src/seqwin/filter.cpp:92-136) and writes the nodes.
+//   edges   edge_group_kernel   distinct pairs of the bucket in ascending order with their weights (distinct
+//                               assemblies, cpp/src/seqwin/build.cpp:177-189) in one pass: no record is moved,
+//           edge_out_kernel     after the scan: pairs of ranks -> pairs of hashes, the finished edges.
 //
 // This is what build_worker + merge_thread_graphs do with two hash maps and a CPU radix sort
 // (cpp/src/seqwin/build.cpp:152-241, build_internals.cpp:159-291); the data is touched twice after the
@@ -61,6 +62,34 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __re
         for (uint64_t b = lo; b <= hi; ++b) start[b] = (uint32_t)j;
     }
 }
+
+// The same bounds by binary search, one thread per bucket: cheaper than the scan above when a bucket holds many
+// items (the keys only need to be partitioned on key >> shift, not sorted).
+__global__ void __launch_bounds__(256) bucket_search_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift,
+                                                            uint64_t n_buckets, uint32_t* __restrict__ start)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += stride) {
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if ((keys[mid] >> shift) < b) lo = mid + 1; else hi = mid;
+        }
+        start[b] = (uint32_t)lo;
+    }
+}
+
+// Shared state too large for a static __shared__ array lives in dynamic shared memory on the device and in a
+// static object in the CPU emulator (which runs one block at a time).
+#if defined(__CUDACC__)
+#define SW_DYN_SMEM(T, name)                                         \
+    extern __shared__ __align__(16) unsigned char name##_raw[];      \
+    T& name = *reinterpret_cast<T*>(name##_raw)
+#else
+#define SW_DYN_SMEM(T, name) \
+    static T name##_obj;     \
+    T& name = name##_obj
+#endif
 
 // Table slot of an in-bucket key.  Multiplicative hashing: node keys are uniform in every bit, but the edge
 // keys of one bucket share most of `first` -- a hub node's pairs differ only further down, in `second`.
@@ -224,6 +253,166 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
     }
 }
 
+// ---- edges: distinct pairs of a bucket with their weights, in ONE pass over its records ---------------------
+// The records of a bucket are in stream order (stable partition), and the stream is in assembly order, so the
+// assemblies of a bucket never decrease.  weight = number of distinct (pair, assembly) combinations
+// (cpp/src/seqwin/build.cpp:177-189: last_seen_assembly): a record counts unless an earlier record of the bucket
+// shows the same pair in the same assembly.  The bucket is taken kEdgeChunk records at a time; inside a chunk a
+// small set of (table slot, assembly) tags decides (whichever of several equal records gets there first
+// counts, the order is irrelevant), across chunks the last assembly seen per pair does: an earlier chunk can
+// only hold the same assembly or a smaller one.  No record is moved, nothing but the distinct pairs is written.
+constexpr int kSetBits = 11;
+constexpr int kSetSlots = 1 << kSetBits;
+constexpr int kEdgeChunk = kSetSlots / 2;        // set load <= 0.5
+static_assert(kEdgeChunk == 4 * kNT, "edge_group_kernel takes four records per thread and chunk");
+
+struct EdgeGroupSmem {
+    unsigned long long t_key[kSlots];            // distinct pairs of the bucket (open addressing)
+    uint32_t t_w[kSlots];                        // distinct assemblies of the slot's pair
+    uint32_t t_last[kSlots];                     // 1 + the largest assembly earlier chunks showed for it (0: none)
+    union {
+        unsigned long long set[kSetSlots];       // (slot << 32 | assembly) tags of the current chunk
+        struct {
+            unsigned long long dk[kMaxDistinct]; // afterwards: the distinct pairs ordered by their next 8 key bits
+            uint16_t dslot[kMaxDistinct];
+        } d;
+    } u;
+    uint16_t dlist[kMaxDistinct];                // slots in insertion order
+    uint32_t sub[kNT], sub_start[kNT + 1], wsum[kNW];
+    uint32_t n_distinct;
+};
+
+// true if tag was not in the set yet (and now is)
+__device__ __forceinline__ bool set_insert(unsigned long long* set, unsigned long long tag)
+{
+    uint32_t h = (uint32_t)((tag * 0x9E3779B97F4A7C15ull) >> (64 - kSetBits));
+    for (;;) {
+        unsigned long long cur = set[h];
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(&set[h], kEmptyKey, tag);
+            if (cur == kEmptyKey) return true;
+        }
+        if (cur == tag) return false;
+        h = (h + 1) & (kSetSlots - 1);
+    }
+}
+
+// grp_keys / grp_w are indexed like the records: bucket b owns [start[b], start[b] + D_b) of them, pairs ascending.
+__global__ void __launch_bounds__(kNT) edge_group_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ easm,
+                                                         const uint32_t* __restrict__ start, int key_bits, uint32_t max_distinct,
+                                                         uint64_t* __restrict__ grp_keys, uint32_t* __restrict__ grp_w,
+                                                         uint32_t* __restrict__ bucket_d)
+{
+    SW_DYN_SMEM(EdgeGroupSmem, sm);
+    static_assert(kNT == 256, "one thread per 8-bit sub-range");
+    const uint32_t b = blockIdx.x, tid = threadIdx.x;
+    const uint32_t bs = start[b], n = start[b + 1] - bs;
+    if (n == 0) {
+        if (tid == 0) bucket_d[b] = 0;
+        return;
+    }
+    const bool multi = n > (uint32_t)kEdgeChunk;
+    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) {
+        sm.t_key[s] = kEmptyKey;
+        sm.t_w[s] = 0;
+        if (multi) sm.t_last[s] = 0;
+    }
+    for (uint32_t s = tid; s < (uint32_t)kSetSlots; s += kNT) sm.u.set[s] = kEmptyKey;
+    if (tid == 0) sm.n_distinct = 0;
+    __syncthreads();
+    const uint64_t lowmask = (1ull << key_bits) - 1;
+    for (uint32_t c0 = 0; c0 < n; c0 += kEdgeChunk) {
+        unsigned long long kq[4];
+        uint32_t aq[4], sl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // the chunk's loads are issued before the first is used
+            const uint32_t i = c0 + tid + q * kNT;
+            kq[q] = i < n ? keys[bs + i] : 0;
+            aq[q] = i < n ? easm[bs + i] : 0;
+            sl[q] = (uint32_t)kSlots;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (c0 + tid + q * kNT >= n) break;
+            if (*(volatile uint32_t*)&sm.n_distinct > max_distinct) break;   // the sort-based path takes the bucket
+            bool inserted;
+            const uint32_t s = table_upsert(sm.t_key, kq[q] & lowmask, &inserted);
+            if (s == (uint32_t)kSlots) {
+                atomicAdd(&sm.n_distinct, (uint32_t)kSlots);
+                break;
+            }
+            if (inserted) {
+                const uint32_t at = atomicAdd(&sm.n_distinct, 1u);
+                if (at < (uint32_t)kMaxDistinct) sm.dlist[at] = (uint16_t)s;
+            }
+            sl[q] = s;
+            bool fresh = set_insert(sm.u.set, ((unsigned long long)s << 32) | aq[q]);
+            if (fresh && multi) fresh = aq[q] + 1u > sm.t_last[s];
+            if (fresh) atomicAdd(&sm.t_w[s], 1u);
+        }
+        if (c0 + (uint32_t)kEdgeChunk < n) {   // uniform: another chunk follows
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (sl[q] != (uint32_t)kSlots) atomicMax(&sm.t_last[sl[q]], aq[q] + 1u);
+            for (uint32_t s = tid; s < (uint32_t)kSetSlots; s += kNT) sm.u.set[s] = kEmptyKey;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const uint32_t D = sm.n_distinct;
+    if (D > max_distinct) {
+        if (tid == 0) bucket_d[b] = kOverflow;
+        return;
+    }
+    // ascending order: counting sort on the next 8 key bits into dk[] (over the dead set), then every pair is
+    // ranked against the few that share those bits
+    const int sshift = key_bits > 8 ? key_bits - 8 : 0;
+    sm.sub[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < D; i += kNT) atomicAdd(&sm.sub[(uint32_t)(sm.t_key[sm.dlist[i]] >> sshift) & 255u], 1u);
+    __syncthreads();
+    {
+        const uint32_t lane = tid & 31, wid = tid >> 5;
+        const uint32_t c = sm.sub[tid];
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) sm.wsum[wid] = inc;
+        __syncthreads();
+        uint32_t ex = inc - c;
+#pragma unroll
+        for (int w = 0; w < kNW; ++w)
+            if ((uint32_t)w < wid) ex += sm.wsum[w];
+        sm.sub_start[tid] = ex;
+        sm.sub[tid] = ex;
+        if (tid == kNT - 1) sm.sub_start[kNT] = ex + c;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < D; i += kNT) {
+        const uint32_t s = sm.dlist[i];
+        const unsigned long long k = sm.t_key[s];
+        const uint32_t at = atomicAdd(&sm.sub[(uint32_t)(k >> sshift) & 255u], 1u);
+        sm.u.d.dk[at] = k;
+        sm.u.d.dslot[at] = (uint16_t)s;
+    }
+    __syncthreads();
+    const uint64_t prefix = (uint64_t)b << key_bits;
+    for (uint32_t i = tid; i < D; i += kNT) {
+        const unsigned long long k = sm.u.d.dk[i];
+        const uint32_t sb = (uint32_t)(k >> sshift) & 255u;
+        const uint32_t lo = sm.sub_start[sb], hi = sm.sub_start[sb + 1];
+        uint32_t r = lo;
+        for (uint32_t j = lo; j < hi; ++j) r += sm.u.d.dk[j] < k ? 1u : 0u;
+        grp_keys[bs + r] = k | prefix;
+        grp_w[bs + r] = sm.t_w[sm.u.d.dslot[i]];
+    }
+    if (tid == 0) bucket_d[b] = D;
+}
+
 // bucket_d -> 64-bit counts for the scans: distinct keys of the buckets grouped here (0 for the others), and
 // the item counts of the buckets that were not (tot[0] += such buckets, tot[1] += their items)
 __global__ void __launch_bounds__(256) bucket_counts_kernel(const uint32_t* __restrict__ bucket_d, const uint32_t* __restrict__ start,
@@ -258,16 +447,6 @@ struct NodeOut {
     double inv_t, inv_n;
     int counts_only;                                // a shard of a multi-GPU build: penalty left at 0
 };
-struct EdgeOut {
-    static constexpr bool kNodes = false;
-    using Val = uint32_t;                           // assembly of the adjacent-pair record
-    const Val* vals;
-    Val* placed;                                    // unused: the placed assemblies are the values
-    uint32_t* placed_asm;                           // [records] assemblies in final order
-    sw_edge* edges;
-    const uint64_t* node_hash;
-    int rank_bits;                                  // key = first << (64 - rank_bits) | second << (64 - 2 rank_bits)
-};
 
 struct PlaceArgs {
     const uint16_t* item_rank;           // rank of every item's key inside its bucket (group_count_kernel)
@@ -287,13 +466,7 @@ __device__ __forceinline__ void place_item(const NodeOut& o, uint64_t dst, unsig
     o.placed[dst] = v;
     if (COUNT) o.placed_asm[dst] = o.rec_asm[(uint32_t)(v >> 32) - o.rec_base];
 }
-template <bool COUNT>
-__device__ __forceinline__ void place_item(const EdgeOut& o, uint64_t dst, uint32_t v)
-{
-    o.placed_asm[dst] = v;
-}
 __device__ __forceinline__ bool is_class_a(const NodeOut& o, uint32_t as) { return o.is_target[as] != 0; }
-__device__ __forceinline__ bool is_class_a(const EdgeOut&, uint32_t) { return true; }
 
 
 
@@ -316,15 +489,6 @@ __device__ __forceinline__ void write_group(const NodeOut& no, unsigned long lon
     }
     no.nodes[idx] = nd;
     no.node_hash[idx] = key;
-}
-__device__ __forceinline__ void write_group(const EdgeOut& eo, unsigned long long key, unsigned long long idx, uint64_t, uint64_t,
-                                            uint32_t ca, uint32_t, bool)
-{
-    sw_edge e;
-    e.first = eo.node_hash[key >> (64 - eo.rank_bits)];
-    e.second = eo.node_hash[(key >> (64 - 2 * eo.rank_bits)) & ((1ull << eo.rank_bits) - 1)];
-    e.weight = ca;
-    eo.edges[idx] = e;
 }
 
 template <class Out, bool COUNT>
@@ -472,6 +636,32 @@ __global__ void __launch_bounds__(kNT, 4) group_place_kernel(PlaceArgs a, Out o)
     for (uint32_t r = tid; r < D; r += kNT) write_group(o, a.grp_keys[bs + r], base + r, (uint64_t)bs + goff[r], (uint64_t)bs + goff[r + 1],
                                                        COUNT ? c_a[r] : 0u, COUNT ? c_b[r] : 0u, COUNT);
 }
+// the grouped pairs of every bucket -> edges (a warp per bucket; grp_base = exclusive scan of the distinct counts)
+__global__ void __launch_bounds__(256) edge_out_kernel(const uint64_t* __restrict__ grp_keys, const uint32_t* __restrict__ grp_w,
+                                                         const uint32_t* __restrict__ start, const uint32_t* __restrict__ bucket_d,
+                                                         const unsigned long long* __restrict__ grp_base, uint64_t n_buckets,
+                                                         const uint64_t* __restrict__ node_hash, int rank_bits,
+                                                         sw_edge* __restrict__ edges)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long rmask = (1ull << rank_bits) - 1;
+    for (uint64_t b = warp; b < n_buckets; b += n_warps) {
+        const uint32_t D = bucket_d[b];
+        if (D == kOverflow) continue;
+        const uint32_t bs = start[b];
+        const unsigned long long base = grp_base[b];
+        for (uint32_t r = lane; r < D; r += 32) {
+            const unsigned long long key = grp_keys[bs + r];
+            sw_edge e;
+            e.first = node_hash[key >> (64 - rank_bits)];
+            e.second = node_hash[(key >> (64 - 2 * rank_bits)) & rmask];
+            e.weight = grp_w[bs + r];
+            edges[base + r] = e;
+        }
+    }
+}
+
 // ---- adjacent-pair records with node ranks looked up through a bucket table ----------------------------------
 
 // rank of hash h among the sorted node hashes: ftable[h >> fshift] = first node of that fine bucket

@@ -611,7 +611,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     }
     const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
     const int P = fixed_nb ? partition_bits(M, fixed_nb)
-                           : partition_bits_for(M, per_node, 400.0, env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
+                           : partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 400), env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
     const int key_bits = 64 - P;
     const uint64_t n_buckets = 1ull << P;
     const uint64_t* pk = nullptr;
@@ -623,7 +623,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(pk == w0.p ? w3.p : w2.p);
     DevBuf<uint32_t> start(n_buckets + 1, s, true), bucket_d(n_buckets, s, true);
     DevBuf<unsigned long long> d64(n_buckets + 1, s, true), tot(3, s, true);
-    bucket_bounds_kernel<<<stride_grid(M + 1), 256, 0, s>>>(pk, M, key_bits, n_buckets, start.p);
+    bucket_search_kernel<<<stride_grid(n_buckets + 1), 256, 0, s>>>(pk, M, key_bits, n_buckets, start.p);
     group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(pk, start.p, key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
                                                            bucket_d.p, item_rank.p);
     SW_CUDA(cudaMemsetAsync(tot.p, 0, 3 * sizeof(unsigned long long), s));
@@ -681,7 +681,7 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     uint64_t* ekb = w2.p;
     uint32_t* easm0 = reinterpret_cast<uint32_t*>(w3.p);
     uint32_t* eva = easm0 + M;
-    DevBuf<uint32_t> evb, placed;
+    DevBuf<uint32_t> evb;
     if (n_raw) {
         // ranks are looked up: fine bucket table over the sorted node hashes (about one node per bucket)
         int fbits = 1;
@@ -703,14 +703,13 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         g.edges.alloc(0, s);
     } else {
         evb.alloc(M, s, true);
-        placed.alloc(M, s, true);
         // records per distinct pair -> about 192 distinct pairs per bucket (min(u, v) makes the low buckets twice as full)
         const unsigned long long* eh = readback_u64(sample_out.p, 2, s);
         SW_CUDA(cudaStreamSynchronize(s));
         const double per_edge = eh[1] ? (double)eh[0] / (double)eh[1] : 1.0;
         const uint32_t fixed_eb = env_u32("SEQWIN_AGG_EDGE_BUCKET", 0);
         const int Pe = std::min(fixed_eb ? partition_bits(n_raw, fixed_eb)
-                                         : partition_bits_for(n_raw, per_edge, 192.0, env_u32("SEQWIN_AGG_MAX_ITEMS", 4096)),
+                                         : partition_bits_for(n_raw, per_edge, (double)env_u32("SEQWIN_AGG_EDGE_TARGET", 192), env_u32("SEQWIN_AGG_MAX_ITEMS", 4096)),
                                 2 * rank_bits);
         const int ekey_bits = 64 - Pe;
         const uint64_t neb = 1ull << Pe;
@@ -721,10 +720,12 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         uint32_t* egrp_cnt = pek == eka ? evb.p : eva;
         DevBuf<uint32_t> estart(neb + 1, s, true), ebucket_d(neb, s, true);
         DevBuf<unsigned long long> ed64(neb + 1, s, true), ebase(neb + 1, s, true), ovf_items(neb + 1, s, true), etot(4, s, true);
-        bucket_bounds_kernel<<<stride_grid(n_raw + 1), 256, 0, s>>>(pek, n_raw, ekey_bits, neb, estart.p);
-        group_count_kernel<<<(uint32_t)neb, kNT, 0, s>>>(pek, estart.p, ekey_bits,
-                                                         std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", kMaxDistinct), kMaxDistinct),
-                                                         egrp_keys, egrp_cnt, ebucket_d.p, item_rank.p);
+        bucket_search_kernel<<<stride_grid(neb + 1), 256, 0, s>>>(pek, n_raw, ekey_bits, neb, estart.p);
+        // distinct pairs of every bucket and their weights (distinct assemblies), in one pass over the records
+        SW_CUDA(cudaFuncSetAttribute(edge_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeGroupSmem)));
+        edge_group_kernel<<<(uint32_t)neb, kNT, sizeof(EdgeGroupSmem), s>>>(
+            pek, pev, estart.p, ekey_bits, std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", kMaxDistinct), kMaxDistinct),
+            egrp_keys, egrp_cnt, ebucket_d.p);
         SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
         SW_CUDA(cudaMemsetAsync(ed64.p + neb, 0, sizeof(unsigned long long), s));
         SW_CUDA(cudaMemsetAsync(ovf_items.p + neb, 0, sizeof(unsigned long long), s));
@@ -776,15 +777,8 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         }
         g.n_edges = n_edges;
         g.edges.alloc(n_edges, s);
-        const PlaceArgs epa{item_rank.p, estart.p, ekey_bits, egrp_keys, egrp_cnt, ebucket_d.p, ebase.p};
-        EdgeOut eo{};
-        eo.vals = pev;
-        eo.placed = nullptr;
-        eo.placed_asm = placed.p;
-        eo.edges = g.edges.p;
-        eo.node_hash = node_hash.p;
-        eo.rank_bits = rank_bits;
-        group_place_kernel<EdgeOut, true><<<(uint32_t)neb, kNT, 0, s>>>(epa, eo);
+        edge_out_kernel<<<(uint32_t)std::min<uint64_t>((neb + 7) / 8, (uint64_t)sm_count() * 16), 256, 0, s>>>(
+            egrp_keys, egrp_cnt, estart.p, ebucket_d.p, ebase.p, neb, node_hash.p, rank_bits, g.edges.p);
         ++tm.launches;
         if (n_ovf) {
             overflow_copy_kernel<<<(uint32_t)neb, kNT, 0, s>>>(side_edges.p, ebucket_d.p, ebase.p, ovf_d64.p, g.edges.p);

@@ -120,12 +120,16 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     stable_partition_top_bits(ekey, easm, ekey_bits);
     std::vector<uint32_t> estart(neb + 1), ebucket_d(neb);
     cuemu::launch(dim3(3), dim3(256), [&] { bucket_bounds_kernel(ekey.data(), E, ekey_bits, neb, estart.data()); });
+    {   // the binary-search variant of the bounds must agree with the scan
+        std::vector<uint32_t> estart2(neb + 1, 0xDEADBEEFu);
+        cuemu::launch(dim3(3), dim3(256), [&] { bucket_search_kernel(ekey.data(), E, ekey_bits, neb, estart2.data()); });
+        if (estart2 != estart) return -2;
+    }
     std::vector<uint64_t> egrp_keys(E);
-    std::vector<uint32_t> egrp_cnt(E), placed(E);
-    std::vector<uint16_t> eitem_rank(E, 0xEEEE);
+    std::vector<uint32_t> egrp_cnt(E);
     cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
-        group_count_kernel(ekey.data(), estart.data(), ekey_bits, max_distinct_edges, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data(),
-                           eitem_rank.data());
+        edge_group_kernel(ekey.data(), easm.data(), estart.data(), ekey_bits, max_distinct_edges, egrp_keys.data(), egrp_cnt.data(),
+                          ebucket_d.data());
     });
     std::vector<unsigned long long> ed64(neb), ovf_items(neb), etot(2, 0);
     cuemu::launch(dim3(2), dim3(256), [&] { bucket_counts_kernel(ebucket_d.data(), estart.data(), neb, ed64.data(), ovf_items.data(), etot.data()); });
@@ -160,15 +164,10 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     }
     std::vector<unsigned long long> egrp_base = exclusive_scan(ed64);
     const uint64_t UE = egrp_base[neb];
-    PlaceArgs epa{eitem_rank.data(), estart.data(), ekey_bits, egrp_keys.data(), egrp_cnt.data(), ebucket_d.data(), egrp_base.data()};
-    EdgeOut eo{};
-    eo.vals = easm.data();
-    eo.placed = nullptr;
-    eo.placed_asm = placed.data();
-    eo.edges = edges_out;
-    eo.node_hash = node_hash.data();
-    eo.rank_bits = rank_bits;
-    cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] { group_place_kernel<EdgeOut, true>(epa, eo); });
+    cuemu::launch(dim3(2), dim3(256), [&] {
+        edge_out_kernel(egrp_keys.data(), egrp_cnt.data(), estart.data(), ebucket_d.data(), egrp_base.data(), neb, node_hash.data(),
+                          rank_bits, edges_out);
+    });
     if (etot[0])
         cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
             overflow_copy_kernel(side_edges.data(), ebucket_d.data(), egrp_base.data(), ovf_base.data(), edges_out);

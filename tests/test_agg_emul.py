@@ -156,3 +156,32 @@ def test_emulated_distinct_estimate(agg):
     assert abs(exact - 3.0) < 1e-9
     est = agg.agg_emul_estimate(C.c_void_p(keys.ctypes.data), C.c_uint64(len(keys)), C.c_int(3))
     assert abs(est - 3.0) < 0.3
+
+
+@pytest.mark.parametrize("per_edges", [700, 6000], ids=["two-chunks", "many-chunks"])
+def test_emulated_edge_buckets_span_chunks(agg, per_edges):
+    """Few distinct hashes, many records: edge buckets hold several chunks of records and the same (pair,
+    assembly) shows up in more than one of them -- the weight must still count every assembly once."""
+    rng = np.random.default_rng(7)
+    n_rec, per = 60, 250
+    pool = rng.integers(0, 2**63, 40, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    keys, vals, rec_asm = [], [], []
+    for r in range(n_rec):
+        keys.append(pool[rng.integers(0, len(pool), per)])
+        vals.append(np.arange(per, dtype=np.uint64) * np.uint64(3) | (np.uint64(r) << np.uint64(32)))
+        rec_asm.append(r // 5)
+    keys, vals = np.concatenate(keys), np.concatenate(vals)
+    rec_asm = np.asarray(rec_asm, dtype=np.uint32)
+    is_t = np.arange(12) < 4
+    kmers, nodes, edges, n_ovf = _run(agg, keys, vals, rec_asm, is_t, True, 512, per_edges)
+    assert n_ovf == 0
+    uk = np.unique(keys)
+    rank = np.searchsorted(uk, keys)
+    same = (vals[:-1] >> np.uint64(32)) == (vals[1:] >> np.uint64(32))
+    u, v = np.minimum(rank[:-1], rank[1:])[same], np.maximum(rank[:-1], rank[1:])[same]
+    a = rec_asm[(vals[:-1] >> np.uint64(32)).astype(np.int64)][same]
+    trip = np.unique(np.stack([u, v, a], axis=1), axis=0)
+    pairs, wgt = np.unique(trip[:, :2], axis=0, return_counts=True)
+    assert len(edges) == len(pairs)
+    assert np.array_equal(edges["first"], uk[pairs[:, 0]]) and np.array_equal(edges["second"], uk[pairs[:, 1]])
+    assert np.array_equal(edges["weight"], wgt.astype(np.uint64))
