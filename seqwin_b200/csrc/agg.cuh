@@ -27,6 +27,7 @@
 #include <cstdint>
 
 #include "common.h"
+#include "nbr.cuh"
 #include "sample.cuh"
 
 namespace sw {
@@ -253,166 +254,6 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
     }
 }
 
-// ---- edges: distinct pairs of a bucket with their weights, in ONE pass over its records ---------------------
-// The records of a bucket are in stream order (stable partition), and the stream is in assembly order, so the
-// assemblies of a bucket never decrease.  weight = number of distinct (pair, assembly) combinations
-// (cpp/src/seqwin/build.cpp:177-189: last_seen_assembly): a record counts unless an earlier record of the bucket
-// shows the same pair in the same assembly.  The bucket is taken kEdgeChunk records at a time; inside a chunk a
-// small set of (table slot, assembly) tags decides (whichever of several equal records gets there first
-// counts, the order is irrelevant), across chunks the last assembly seen per pair does: an earlier chunk can
-// only hold the same assembly or a smaller one.  No record is moved, nothing but the distinct pairs is written.
-constexpr int kSetBits = 11;
-constexpr int kSetSlots = 1 << kSetBits;
-constexpr int kEdgeChunk = kSetSlots / 2;        // set load <= 0.5
-static_assert(kEdgeChunk == 4 * kNT, "edge_group_kernel takes four records per thread and chunk");
-
-struct EdgeGroupSmem {
-    unsigned long long t_key[kSlots];            // distinct pairs of the bucket (open addressing)
-    uint32_t t_w[kSlots];                        // distinct assemblies of the slot's pair
-    uint32_t t_last[kSlots];                     // 1 + the largest assembly earlier chunks showed for it (0: none)
-    union {
-        unsigned long long set[kSetSlots];       // (slot << 32 | assembly) tags of the current chunk
-        struct {
-            unsigned long long dk[kMaxDistinct]; // afterwards: the distinct pairs ordered by their next 8 key bits
-            uint16_t dslot[kMaxDistinct];
-        } d;
-    } u;
-    uint16_t dlist[kMaxDistinct];                // slots in insertion order
-    uint32_t sub[kNT], sub_start[kNT + 1], wsum[kNW];
-    uint32_t n_distinct;
-};
-
-// true if tag was not in the set yet (and now is)
-__device__ __forceinline__ bool set_insert(unsigned long long* set, unsigned long long tag)
-{
-    uint32_t h = (uint32_t)((tag * 0x9E3779B97F4A7C15ull) >> (64 - kSetBits));
-    for (;;) {
-        unsigned long long cur = set[h];
-        if (cur == kEmptyKey) {
-            cur = atomicCAS(&set[h], kEmptyKey, tag);
-            if (cur == kEmptyKey) return true;
-        }
-        if (cur == tag) return false;
-        h = (h + 1) & (kSetSlots - 1);
-    }
-}
-
-// grp_keys / grp_w are indexed like the records: bucket b owns [start[b], start[b] + D_b) of them, pairs ascending.
-__global__ void __launch_bounds__(kNT) edge_group_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ easm,
-                                                         const uint32_t* __restrict__ start, int key_bits, uint32_t max_distinct,
-                                                         uint64_t* __restrict__ grp_keys, uint32_t* __restrict__ grp_w,
-                                                         uint32_t* __restrict__ bucket_d)
-{
-    SW_DYN_SMEM(EdgeGroupSmem, sm);
-    static_assert(kNT == 256, "one thread per 8-bit sub-range");
-    const uint32_t b = blockIdx.x, tid = threadIdx.x;
-    const uint32_t bs = start[b], n = start[b + 1] - bs;
-    if (n == 0) {
-        if (tid == 0) bucket_d[b] = 0;
-        return;
-    }
-    const bool multi = n > (uint32_t)kEdgeChunk;
-    for (uint32_t s = tid; s < (uint32_t)kSlots; s += kNT) {
-        sm.t_key[s] = kEmptyKey;
-        sm.t_w[s] = 0;
-        if (multi) sm.t_last[s] = 0;
-    }
-    for (uint32_t s = tid; s < (uint32_t)kSetSlots; s += kNT) sm.u.set[s] = kEmptyKey;
-    if (tid == 0) sm.n_distinct = 0;
-    __syncthreads();
-    const uint64_t lowmask = (1ull << key_bits) - 1;
-    for (uint32_t c0 = 0; c0 < n; c0 += kEdgeChunk) {
-        unsigned long long kq[4];
-        uint32_t aq[4], sl[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {   // the chunk's loads are issued before the first is used
-            const uint32_t i = c0 + tid + q * kNT;
-            kq[q] = i < n ? keys[bs + i] : 0;
-            aq[q] = i < n ? easm[bs + i] : 0;
-            sl[q] = (uint32_t)kSlots;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (c0 + tid + q * kNT >= n) break;
-            if (*(volatile uint32_t*)&sm.n_distinct > max_distinct) break;   // the sort-based path takes the bucket
-            bool inserted;
-            const uint32_t s = table_upsert(sm.t_key, kq[q] & lowmask, &inserted);
-            if (s == (uint32_t)kSlots) {
-                atomicAdd(&sm.n_distinct, (uint32_t)kSlots);
-                break;
-            }
-            if (inserted) {
-                const uint32_t at = atomicAdd(&sm.n_distinct, 1u);
-                if (at < (uint32_t)kMaxDistinct) sm.dlist[at] = (uint16_t)s;
-            }
-            sl[q] = s;
-            bool fresh = set_insert(sm.u.set, ((unsigned long long)s << 32) | aq[q]);
-            if (fresh && multi) fresh = aq[q] + 1u > sm.t_last[s];
-            if (fresh) atomicAdd(&sm.t_w[s], 1u);
-        }
-        if (c0 + (uint32_t)kEdgeChunk < n) {   // uniform: another chunk follows
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (sl[q] != (uint32_t)kSlots) atomicMax(&sm.t_last[sl[q]], aq[q] + 1u);
-            for (uint32_t s = tid; s < (uint32_t)kSetSlots; s += kNT) sm.u.set[s] = kEmptyKey;
-            __syncthreads();
-        }
-    }
-    __syncthreads();
-    const uint32_t D = sm.n_distinct;
-    if (D > max_distinct) {
-        if (tid == 0) bucket_d[b] = kOverflow;
-        return;
-    }
-    // ascending order: counting sort on the next 8 key bits into dk[] (over the dead set), then every pair is
-    // ranked against the few that share those bits
-    const int sshift = key_bits > 8 ? key_bits - 8 : 0;
-    sm.sub[tid] = 0;
-    __syncthreads();
-    for (uint32_t i = tid; i < D; i += kNT) atomicAdd(&sm.sub[(uint32_t)(sm.t_key[sm.dlist[i]] >> sshift) & 255u], 1u);
-    __syncthreads();
-    {
-        const uint32_t lane = tid & 31, wid = tid >> 5;
-        const uint32_t c = sm.sub[tid];
-        uint32_t inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= (uint32_t)d) inc += t;
-        }
-        if (lane == 31) sm.wsum[wid] = inc;
-        __syncthreads();
-        uint32_t ex = inc - c;
-#pragma unroll
-        for (int w = 0; w < kNW; ++w)
-            if ((uint32_t)w < wid) ex += sm.wsum[w];
-        sm.sub_start[tid] = ex;
-        sm.sub[tid] = ex;
-        if (tid == kNT - 1) sm.sub_start[kNT] = ex + c;
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < D; i += kNT) {
-        const uint32_t s = sm.dlist[i];
-        const unsigned long long k = sm.t_key[s];
-        const uint32_t at = atomicAdd(&sm.sub[(uint32_t)(k >> sshift) & 255u], 1u);
-        sm.u.d.dk[at] = k;
-        sm.u.d.dslot[at] = (uint16_t)s;
-    }
-    __syncthreads();
-    const uint64_t prefix = (uint64_t)b << key_bits;
-    for (uint32_t i = tid; i < D; i += kNT) {
-        const unsigned long long k = sm.u.d.dk[i];
-        const uint32_t sb = (uint32_t)(k >> sshift) & 255u;
-        const uint32_t lo = sm.sub_start[sb], hi = sm.sub_start[sb + 1];
-        uint32_t r = lo;
-        for (uint32_t j = lo; j < hi; ++j) r += sm.u.d.dk[j] < k ? 1u : 0u;
-        grp_keys[bs + r] = k | prefix;
-        grp_w[bs + r] = sm.t_w[sm.u.d.dslot[i]];
-    }
-    if (tid == 0) bucket_d[b] = D;
-}
-
 // bucket_d -> 64-bit counts for the scans: distinct keys of the buckets grouped here (0 for the others), and
 // the item counts of the buckets that were not (tot[0] += such buckets, tot[1] += their items)
 __global__ void __launch_bounds__(256) bucket_counts_kernel(const uint32_t* __restrict__ bucket_d, const uint32_t* __restrict__ start,
@@ -440,7 +281,7 @@ struct NodeOut {
     Val* placed;                                    // kmers (final order)
     uint32_t* placed_asm;                           // [items] assembly of every placed k-mer (scoring only)
     sw_node* nodes;
-    uint64_t* node_hash;                            // compact copy of nodes[].hash for the edge stage
+    uint64_t* node_hash;                            // optional compact copy of nodes[].hash (null: not written)
     const uint32_t* rec_asm;                        // [records] assembly of a record   (scoring only)
     uint32_t rec_base;
     const uint8_t* is_target;                       // [assemblies]                      (scoring only)
@@ -488,7 +329,7 @@ __device__ __forceinline__ void write_group(const NodeOut& no, unsigned long lon
         nd.penalty = __dsqrt_rn(__dadd_rn(__dmul_rn(d1, d1), __dmul_rn(fn, fn)));
     }
     no.nodes[idx] = nd;
-    no.node_hash[idx] = key;
+    if (no.node_hash) no.node_hash[idx] = key;
 }
 
 template <class Out, bool COUNT>
@@ -636,33 +477,285 @@ __global__ void __launch_bounds__(kNT, 4) group_place_kernel(PlaceArgs a, Out o)
     for (uint32_t r = tid; r < D; r += kNT) write_group(o, a.grp_keys[bs + r], base + r, (uint64_t)bs + goff[r], (uint64_t)bs + goff[r + 1],
                                                        COUNT ? c_a[r] : 0u, COUNT ? c_b[r] : 0u, COUNT);
 }
-// the grouped pairs of every bucket -> edges (a warp per bucket; grp_base = exclusive scan of the distinct counts)
-__global__ void __launch_bounds__(256) edge_out_kernel(const uint64_t* __restrict__ grp_keys, const uint32_t* __restrict__ grp_w,
-                                                         const uint32_t* __restrict__ start, const uint32_t* __restrict__ bucket_d,
-                                                         const unsigned long long* __restrict__ grp_base, uint64_t n_buckets,
-                                                         const uint64_t* __restrict__ node_hash, int rank_bits,
-                                                         sw_edge* __restrict__ edges)
+// ---- edges: grouped inside the NODE buckets ---------------------------------------------------------------------
+// An adjacent pair of the stream belongs to the minimizer with the smaller hash (the earlier one on a tie), so
+// every edge {first <= second} is owned by items of node `first` -- which a node bucket already holds together.
+// The node partition therefore carries, per item, the hashes of the (at most two) neighbours whose pair it owns
+// (radix.cu, NbrArrays; 0 = none), and one CTA per bucket groups the records (node rank in the bucket, second
+// hash, assembly) in shared memory:
+//   * a table of the distinct (rank, second) pairs.  Its 64-bit key is second << 10 | rank; the 10 bits of
+//     `second` that do not fit are kept beside it and checked after the barrier -- two pairs that agree in
+//     everything else send the bucket to the side path, like a full table does;
+//   * weight = distinct (pair, assembly) combinations (cpp/src/seqwin/build.cpp:177-189).  The items of a bucket
+//     are in stream order, so its assemblies never decrease: inside a chunk of items a small set of
+//     (slot, assembly) tags decides (whichever of several equal records comes first counts), across chunks the
+//     largest assembly seen so far per pair does;
+//   * the distinct pairs leave in (rank, second) order -- counting sort on the rank, then a rank by counting
+//     among the few pairs of one node -- so that concatenating the buckets gives the edges in (first, second)
+//     order with no sort at all.
+// No node ranks, no lookups, no second partition: this replaces merge_edges' sort (build_internals.cpp:253-291).
+constexpr int kRankBits = 10;                    // node rank inside a bucket
+static_assert((1 << kRankBits) == kMaxDistinct, "ranks of a bucket's nodes fit kRankBits");
+
+template <int ESB, int EI>
+struct BucketEdgeSmem {
+    static constexpr int kES = 1 << ESB;                 // pair table slots
+    static constexpr int kEMax = kES / 2;                // distinct pairs a bucket may hold
+    static constexpr int kChunkItems = kNT * EI;
+    static constexpr int kSetSlots = 4 * kChunkItems;    // <= 2 records per item, load <= 0.5
+    unsigned long long t_key[kES];                       // second << 10 | rank
+    uint32_t t_w[kES];                                   // distinct assemblies of the pair
+    uint16_t t_hi[kES];                                  // second >> 54
+    uint16_t dlist[kEMax];                               // slots in insertion order
+    union {
+        struct {
+            unsigned long long set[kSetSlots];           // (slot << 32 | assembly) tags of the current chunk
+            uint32_t t_last[kES];                        // 1 + the largest assembly earlier chunks showed for the pair
+        } a;
+        struct {                                         // afterwards: ordering
+            uint32_t r_start[kMaxDistinct + 1], cursor[kMaxDistinct];
+            unsigned long long dk[kEMax];
+            uint16_t dslot[kEMax];
+        } b;
+    } u;
+    uint32_t wsum[kNW];
+    uint32_t n_distinct, n_records, bad;
+};
+
+template <int BITS>
+__device__ __forceinline__ uint32_t upsert_t(unsigned long long* t_key, unsigned long long key, bool* inserted)
+{
+    constexpr uint32_t kN = 1u << BITS;
+    uint32_t s = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - BITS));
+    *inserted = false;
+    for (uint32_t probes = 0; probes < kN; ++probes) {
+        unsigned long long cur = t_key[s];
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(&t_key[s], kEmptyKey, key);
+            if (cur == kEmptyKey) {
+                *inserted = true;
+                return s;
+            }
+        }
+        if (cur == key) return s;
+        s = (s + 1) & (kN - 1);
+    }
+    return kN;
+}
+
+// true if tag was not in the set yet (and now is); the set never fills up (load <= 0.5)
+template <int SLOTS>
+__device__ __forceinline__ bool set_insert_t(unsigned long long* set, unsigned long long tag)
+{
+    static_assert((SLOTS & (SLOTS - 1)) == 0, "power of two");
+    uint32_t h = (uint32_t)((tag * 0x9E3779B97F4A7C15ull) >> 40) & (SLOTS - 1);
+    for (;;) {
+        unsigned long long cur = set[h];
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(&set[h], kEmptyKey, tag);
+            if (cur == kEmptyKey) return true;
+        }
+        if (cur == tag) return false;
+        h = (h + 1) & (SLOTS - 1);
+    }
+}
+
+struct BucketEdgeArgs {
+    const uint16_t* item_rank;            // rank of every item's hash inside its bucket (group_count_kernel)
+    const uint64_t* nb_prev;              // owned neighbour hashes, partitioned like the items (0 = none)
+    const uint64_t* nb_next;
+    const unsigned long long* vals;       // pos | record << 32
+    const uint32_t* start;                // bucket bounds
+    const uint32_t* rec_asm;
+    uint32_t rec_base;
+    uint32_t max_distinct;                // <= kEMax (tests lower it to reach the side path)
+    // bucket b's distinct pairs, in (rank, second) order, at [2 * start[b], 2 * start[b] + bucket_e[b])
+    uint64_t* te_second;
+    uint32_t* te_w;
+    uint16_t* te_r;
+    uint32_t* bucket_e;                   // distinct pairs, kOverflow: the side path takes the bucket
+    uint32_t* bucket_rec;                 // records (owned pairs) of the bucket
+};
+
+template <int ESB, int EI>
+__global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs a)
+{
+    using Smem = BucketEdgeSmem<ESB, EI>;
+    SW_DYN_SMEM(Smem, sm);
+    constexpr uint32_t kES = Smem::kES;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t bs = a.start[b], n = a.start[b + 1] - bs;
+    if (n == 0) {
+        if (tid == 0) {
+            a.bucket_e[b] = 0;
+            a.bucket_rec[b] = 0;
+        }
+        return;
+    }
+    const bool multi = n > (uint32_t)Smem::kChunkItems;
+    for (uint32_t s = tid; s < kES; s += kNT) {
+        sm.t_key[s] = kEmptyKey;
+        sm.t_w[s] = 0;
+        if (multi) sm.u.a.t_last[s] = 0;
+    }
+    for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += kNT) sm.u.a.set[s] = kEmptyKey;
+    if (tid == 0) sm.n_distinct = sm.n_records = sm.bad = 0;
+    __syncthreads();
+    uint32_t my_records = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += Smem::kChunkItems) {
+        unsigned long long sec[2 * EI];
+        uint32_t rk[EI], as[EI], sl[2 * EI];
+#pragma unroll
+        for (int q = 0; q < EI; ++q) {   // the chunk's loads are issued before the first is used
+            const uint32_t i = c0 + tid + q * kNT;
+            const bool have = i < n;
+            sec[2 * q] = have ? a.nb_prev[bs + i] : 0;
+            sec[2 * q + 1] = have ? a.nb_next[bs + i] : 0;
+            rk[q] = have ? (uint32_t)a.item_rank[bs + i] : 0;
+            as[q] = have ? a.rec_asm[(uint32_t)(a.vals[bs + i] >> 32) - a.rec_base] : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < 2 * EI; ++e) {
+            sl[e] = kES;
+            if (sec[e] == 0) continue;
+            ++my_records;
+            if (*(volatile uint32_t*)&sm.n_distinct > a.max_distinct) continue;   // the side path takes the bucket
+            const unsigned long long key = (sec[e] << kRankBits) | rk[e >> 1];
+            if (key == kEmptyKey) {
+                sm.bad = 1;
+                continue;
+            }
+            bool inserted;
+            const uint32_t s = upsert_t<ESB>(sm.t_key, key, &inserted);
+            if (s == kES) {
+                atomicAdd(&sm.n_distinct, kES);
+                continue;
+            }
+            if (inserted) {
+                sm.t_hi[s] = (uint16_t)(sec[e] >> (64 - kRankBits));
+                const uint32_t at = atomicAdd(&sm.n_distinct, 1u);
+                if (at < (uint32_t)Smem::kEMax) sm.dlist[at] = (uint16_t)s;
+            }
+            sl[e] = s;
+            bool fresh = set_insert_t<Smem::kSetSlots>(sm.u.a.set, ((unsigned long long)s << 32) | as[e >> 1]);
+            if (fresh && multi) fresh = as[e >> 1] + 1u > sm.u.a.t_last[s];
+            if (fresh) atomicAdd(&sm.t_w[s], 1u);
+        }
+        __syncthreads();
+        // the bits of `second` the key leaves out: the slot's first record wrote them, everybody checks
+#pragma unroll
+        for (int e = 0; e < 2 * EI; ++e)
+            if (sl[e] != kES && sm.t_hi[sl[e]] != (uint16_t)(sec[e] >> (64 - kRankBits))) sm.bad = 1;
+        if (c0 + (uint32_t)Smem::kChunkItems < n) {   // uniform: another chunk follows
+#pragma unroll
+            for (int e = 0; e < 2 * EI; ++e)
+                if (sl[e] != kES) atomicMax(&sm.u.a.t_last[sl[e]], as[e >> 1] + 1u);
+            for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += kNT) sm.u.a.set[s] = kEmptyKey;
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) my_records += __shfl_xor_sync(0xffffffffu, my_records, d);
+    if (lane == 0 && my_records) atomicAdd(&sm.n_records, my_records);
+    __syncthreads();
+    const uint32_t D = sm.n_distinct;
+    if (D > a.max_distinct || sm.bad) {
+        if (tid == 0) {
+            a.bucket_e[b] = kOverflow;
+            a.bucket_rec[b] = sm.n_records;
+        }
+        return;
+    }
+    // (rank, second) order: counting sort on the rank into dk[] (over the dead set), then every pair is ranked
+    // against the other pairs of its node
+    for (uint32_t r = tid; r <= (uint32_t)kMaxDistinct; r += kNT) sm.u.b.r_start[r] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < D; i += kNT)
+        atomicAdd(&sm.u.b.r_start[(uint32_t)sm.t_key[sm.dlist[i]] & (kMaxDistinct - 1)], 1u);
+    __syncthreads();
+    {   // exclusive scan of the kMaxDistinct counts, four consecutive ranks per thread
+        uint32_t cnt[4], sum4 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            cnt[q] = sm.u.b.r_start[tid * 4 + q];
+            sum4 += cnt[q];
+        }
+        uint32_t inc = sum4;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) sm.wsum[wid] = inc;
+        __syncthreads();
+        uint32_t run = inc - sum4;
+#pragma unroll
+        for (int w = 0; w < kNW; ++w)
+            if ((uint32_t)w < wid) run += sm.wsum[w];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sm.u.b.r_start[tid * 4 + q] = run;
+            sm.u.b.cursor[tid * 4 + q] = run;
+            run += cnt[q];
+        }
+        if (tid == kNT - 1) sm.u.b.r_start[kMaxDistinct] = run;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < D; i += kNT) {
+        const uint32_t s = sm.dlist[i];
+        const unsigned long long key = sm.t_key[s];
+        const uint32_t at = atomicAdd(&sm.u.b.cursor[(uint32_t)key & (kMaxDistinct - 1)], 1u);
+        sm.u.b.dk[at] = (key >> kRankBits) | ((unsigned long long)sm.t_hi[s] << (64 - kRankBits));
+        sm.u.b.dslot[at] = (uint16_t)s;
+    }
+    __syncthreads();
+    const uint64_t out0 = 2ull * bs;
+    for (uint32_t i = tid; i < D; i += kNT) {
+        const unsigned long long second = sm.u.b.dk[i];
+        const uint32_t s = sm.u.b.dslot[i];
+        const uint32_t r = (uint32_t)sm.t_key[s] & (kMaxDistinct - 1);
+        const uint32_t lo = sm.u.b.r_start[r], hi = sm.u.b.r_start[r + 1];
+        uint32_t at = lo;
+        for (uint32_t j = lo; j < hi; ++j) at += sm.u.b.dk[j] < second ? 1u : 0u;
+        a.te_second[out0 + at] = second;
+        a.te_w[out0 + at] = sm.t_w[s];
+        a.te_r[out0 + at] = (uint16_t)r;
+    }
+    if (tid == 0) {
+        a.bucket_e[b] = D;
+        a.bucket_rec[b] = sm.n_records;
+    }
+}
+
+// the grouped pairs of every bucket -> edges (a warp per bucket; edge_base = exclusive scan of the distinct counts;
+// grp_keys[start[b] + r] = hash of the bucket's node of rank r, from group_count_kernel)
+__global__ void __launch_bounds__(256) bucket_edges_out_kernel(const uint64_t* __restrict__ te_second, const uint32_t* __restrict__ te_w,
+                                                               const uint16_t* __restrict__ te_r, const uint32_t* __restrict__ start,
+                                                               const uint32_t* __restrict__ bucket_e,
+                                                               const unsigned long long* __restrict__ edge_base, uint64_t n_buckets,
+                                                               const uint64_t* __restrict__ grp_keys, sw_edge* __restrict__ edges)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const unsigned long long rmask = (1ull << rank_bits) - 1;
     for (uint64_t b = warp; b < n_buckets; b += n_warps) {
-        const uint32_t D = bucket_d[b];
+        const uint32_t D = bucket_e[b];
         if (D == kOverflow) continue;
         const uint32_t bs = start[b];
-        const unsigned long long base = grp_base[b];
-        for (uint32_t r = lane; r < D; r += 32) {
-            const unsigned long long key = grp_keys[bs + r];
+        const unsigned long long base = edge_base[b];
+        for (uint32_t j = lane; j < D; j += 32) {
             sw_edge e;
-            e.first = node_hash[key >> (64 - rank_bits)];
-            e.second = node_hash[(key >> (64 - 2 * rank_bits)) & rmask];
-            e.weight = grp_w[bs + r];
-            edges[base + r] = e;
+            e.first = grp_keys[bs + te_r[2ull * bs + j]];
+            e.second = te_second[2ull * bs + j];
+            e.weight = te_w[2ull * bs + j];
+            edges[base + j] = e;
         }
     }
 }
 
-// ---- adjacent-pair records with node ranks looked up through a bucket table ----------------------------------
+// ---- buckets left to the sort-based path (hub nodes, or a clash of the checked key bits) ----------------------------
+// Their records become (rank pair, assembly) records -- global node ranks, `second` looked up through a bucket
+// table over the sorted node hashes -- which radix.cu sorts and graph.cu run-length encodes as the sort-based path
+// does for everything; the finished edges are copied to their place among the others.
 
 // rank of hash h among the sorted node hashes: ftable[h >> fshift] = first node of that fine bucket
 __device__ __forceinline__ uint32_t rank_of_hash(uint64_t h, const uint64_t* __restrict__ node_hash,
@@ -673,108 +766,104 @@ __device__ __forceinline__ uint32_t rank_of_hash(uint64_t h, const uint64_t* __r
     return i;
 }
 
-constexpr int kEmitItems = kNT * 8;
-
-// One record per pair of stream-adjacent minimizers of one record: key = (min rank, max rank) left-aligned,
-// value = assembly.  block_off[blockIdx.x] = records emitted by earlier blocks (edge_count_kernel + scan).
-__global__ void __launch_bounds__(kNT) edge_emit_kernel(const uint64_t* __restrict__ stream_keys, const uint64_t* __restrict__ stream_vals,
-                                                        uint64_t n, const uint64_t* __restrict__ node_hash,
-                                                        const uint32_t* __restrict__ ftable, int fshift,
-                                                        const uint32_t* __restrict__ rec_asm, uint32_t rec_base,
-                                                        const unsigned long long* __restrict__ block_off, int rank_bits,
-                                                        uint64_t* __restrict__ ekey, uint32_t* __restrict__ easm, int sbits,
-                                                        unsigned long long* __restrict__ sample_set, unsigned long long* sample_out)
+// per-bucket 64-bit counts for the scans: distinct pairs of the buckets grouped above (0 for the others), the
+// record counts of the others; tot[0] += such buckets, tot[1] += their records
+__global__ void __launch_bounds__(256) bucket_edge_counts_kernel(const uint32_t* __restrict__ bucket_e, const uint32_t* __restrict__ bucket_rec,
+                                                                 uint64_t n_buckets, unsigned long long* __restrict__ e64,
+                                                                 unsigned long long* __restrict__ side_rec64, unsigned long long* tot)
 {
-    __shared__ uint32_t s_rank[kEmitItems + 1];
-    __shared__ uint32_t s_cnt[8][kNW];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t base = (uint64_t)blockIdx.x * kEmitItems;
-    for (uint32_t t = tid; t <= (uint32_t)kEmitItems; t += kNT) {
-        const uint64_t i = base + t;
-        if (i < n) s_rank[t] = rank_of_hash(stream_keys[i], node_hash, ftable, fshift);
-    }
-    bool flag[8];
-    uint32_t rec[8], prefix[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint64_t i = base + (uint64_t)r * kNT + tid;
-        flag[r] = false;
-        rec[r] = 0;
-        if (i + 1 < n) {
-            rec[r] = (uint32_t)(stream_vals[i] >> 32);
-            flag[r] = rec[r] == (uint32_t)(stream_vals[i + 1] >> 32);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += stride) {
+        const bool ovf = bucket_e[b] == kOverflow;
+        e64[b] = ovf ? 0ull : (unsigned long long)bucket_e[b];
+        side_rec64[b] = ovf ? (unsigned long long)bucket_rec[b] : 0ull;
+        if (ovf) {
+            atomicAdd(&tot[0], 1ull);
+            atomicAdd(&tot[1], (unsigned long long)bucket_rec[b]);
         }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, flag[r]);
-        prefix[r] = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) s_cnt[r][wid] = __popc(ballot);
     }
-    __syncthreads();
-    unsigned long long running = block_off[blockIdx.x];
+}
+
+// the records of those buckets in bucket order (side_off = exclusive scan of their record counts): items in
+// stream order, so the assemblies of one pair never decrease, which the run-length encoding relies on
+__global__ void __launch_bounds__(kNT) side_emit_kernel(const BucketEdgeArgs a, const uint32_t* __restrict__ bucket_e,
+                                                        const unsigned long long* __restrict__ side_off,
+                                                        const unsigned long long* __restrict__ node_base,
+                                                        const uint64_t* __restrict__ node_hash, const uint32_t* __restrict__ ftable,
+                                                        int fshift, int rank_bits, uint64_t* __restrict__ side_keys,
+                                                        uint32_t* __restrict__ side_asm)
+{
+    __shared__ uint32_t s_warp[kNW];
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (bucket_e[b] != kOverflow) return;
+    const uint32_t bs = a.start[b], n = a.start[b + 1] - bs;
+    unsigned long long running = side_off[b];
+    const unsigned long long nbase = node_base[b];
+    for (uint32_t c0 = 0; c0 < n; c0 += kNT) {
+        const uint32_t i = c0 + tid;
+        unsigned long long sp = 0, sn = 0;
+        uint32_t r = 0, as = 0;
+        if (i < n) {
+            sp = a.nb_prev[bs + i];
+            sn = a.nb_next[bs + i];
+            r = a.item_rank[bs + i];
+            as = a.rec_asm[(uint32_t)(a.vals[bs + i] >> 32) - a.rec_base];
+        }
+        const uint32_t cnt = (sp ? 1u : 0u) + (sn ? 1u : 0u);
+        uint32_t inc = cnt;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        uint32_t before = 0, total = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t before = inc - cnt, total = 0;
 #pragma unroll
         for (int w = 0; w < kNW; ++w) {
-            const uint32_t t = s_cnt[r][w];
+            const uint32_t t = s_warp[w];
             if ((uint32_t)w < wid) before += t;
             total += t;
         }
-        if (flag[r]) {
-            const uint32_t t = (uint32_t)r * kNT + tid;
-            uint32_t u = s_rank[t], v = s_rank[t + 1];
-            if (v < u) { const uint32_t x = u; u = v; v = x; }
-            const unsigned long long slot = running + before + prefix[r];
-            const uint64_t key = ((uint64_t)u << (64 - rank_bits)) | ((uint64_t)v << (64 - 2 * rank_bits));
-            ekey[slot] = key;
-            easm[slot] = rec_asm[rec[r] - rec_base];
-            if (sample_set) distinct_sample_item(key, sbits, sample_set, sample_out);   // records per distinct pair (bucket sizing)
+        __syncthreads();
+        unsigned long long slot = running + before;
+        const uint64_t u = nbase + r;   // first <= second in hash order, hence in rank order
+        if (sp) {
+            const uint64_t v = rank_of_hash(sp, node_hash, ftable, fshift);
+            side_keys[slot] = (u << (64 - rank_bits)) | (v << (64 - 2 * rank_bits));
+            side_asm[slot] = as;
+            ++slot;
+        }
+        if (sn) {
+            const uint64_t v = rank_of_hash(sn, node_hash, ftable, fshift);
+            side_keys[slot] = (u << (64 - rank_bits)) | (v << (64 - 2 * rank_bits));
+            side_asm[slot] = as;
         }
         running += total;
     }
 }
 
-// ---- buckets left to the sort-based path (edge hubs) -----------------------------------------------------------
-
-// copy the items of those buckets, bucket after bucket, into side arrays (side_off = exclusive scan of their sizes)
-template <typename V>
-__global__ void __launch_bounds__(kNT) overflow_gather_kernel(const uint64_t* __restrict__ keys, const V* __restrict__ vals,
-                                                              const uint32_t* __restrict__ start, const uint32_t* __restrict__ bucket_d,
-                                                              const unsigned long long* __restrict__ side_off,
-                                                              uint64_t* __restrict__ side_keys, V* __restrict__ side_vals)
+// distinct pairs (runs of the sorted side array) of every such bucket: its records are [side_off[b], side_off[b + 1])
+__global__ void __launch_bounds__(kNT) side_count_kernel(const uint64_t* __restrict__ side_keys, const uint32_t* __restrict__ bucket_e,
+                                                         const unsigned long long* __restrict__ side_off,
+                                                         unsigned long long* __restrict__ e64, unsigned long long* __restrict__ ovf_e64)
 {
+    __shared__ unsigned long long s_sum;
     const uint32_t b = blockIdx.x;
-    if (bucket_d[b] != kOverflow) return;
-    const uint32_t bs = start[b], n = start[b + 1] - bs;
-    const unsigned long long so = side_off[b];
-    for (uint32_t i = threadIdx.x; i < n; i += kNT) {
-        side_keys[so + i] = keys[bs + i];
-        side_vals[so + i] = vals[bs + i];
-    }
-}
-
-// distinct keys (runs of the sorted side array) of every such bucket
-__global__ void __launch_bounds__(kNT) overflow_count_kernel(const uint64_t* __restrict__ side_keys, const uint32_t* __restrict__ start,
-                                                             const uint32_t* __restrict__ bucket_d,
-                                                             const unsigned long long* __restrict__ side_off,
-                                                             unsigned long long* __restrict__ d64, unsigned long long* __restrict__ ovf_d64)
-{
-    __shared__ uint32_t s_sum;
-    const uint32_t b = blockIdx.x;
-    if (bucket_d[b] != kOverflow) {
-        if (threadIdx.x == 0) ovf_d64[b] = 0;
+    if (bucket_e[b] != kOverflow) {
+        if (threadIdx.x == 0) ovf_e64[b] = 0;
         return;
     }
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
-    const uint32_t n = start[b + 1] - start[b];
-    const unsigned long long so = side_off[b];
-    uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += kNT) c += (i == 0 || side_keys[so + i] != side_keys[so + i - 1]) ? 1u : 0u;
+    const unsigned long long so = side_off[b], n = side_off[b + 1] - so;
+    unsigned long long c = 0;
+    for (unsigned long long i = threadIdx.x; i < n; i += kNT) c += (i == 0 || side_keys[so + i] != side_keys[so + i - 1]) ? 1u : 0u;
     if (c) atomicAdd(&s_sum, c);
     __syncthreads();
     if (threadIdx.x == 0) {
-        d64[b] = s_sum;
-        ovf_d64[b] = s_sum;
+        e64[b] = s_sum;
+        ovf_e64[b] = s_sum;
     }
 }
 

@@ -145,6 +145,20 @@ template <typename V>
 uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, int top_bits, uint64_t* ka, V* va, uint64_t* kb,
                              V* vb, cudaStream_t s, const uint64_t** out_k, const V** out_v);
 
+// Node-stage partition: (h1, k-mer) plus, per minimizer, the hashes of the stream neighbours whose adjacent pair
+// it OWNS (the pair belongs to the item with the smaller hash; 0 = none) -- what the edge grouping needs
+// (agg.cuh).  The first pass derives the two arrays from the stream; A / B are the ping-pong sets (n entries per
+// array) and *out points at the one holding the result.  *d_zero_key is set if a key is 0 (marker ambiguous: the
+// caller takes the sort-based path).  top_bits >= 1.  Returns the number of kernels launched; no host sync.
+struct NbrBuffers {
+    uint64_t* keys;
+    uint64_t* vals;
+    uint64_t* prev;
+    uint64_t* next;
+};
+uint32_t radix_partition_top_nbr(const uint64_t* keys, const uint64_t* vals, uint64_t n, int top_bits, const NbrBuffers& A,
+                                 const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out, unsigned int* d_zero_key);
+
 // ---- graph stage ------------------------------------------------------------------------------
 struct DevGraph {
     DevBuf<sw_kmer> kmers;

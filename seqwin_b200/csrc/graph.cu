@@ -576,10 +576,20 @@ double estimate_items_per_key(const uint64_t* keys, uint64_t n, unsigned long lo
     return h[1] ? (double)h[0] / (double)h[1] : 1.0;
 }
 
-// Bucketed aggregation (agg.cuh): stable partition on the top bits of the key, then one CTA per bucket groups
-// by key in shared memory.  Returns false -- nothing of `g` touched -- if a NODE bucket holds more distinct
-// hashes than its table takes (not expected: the bucket count follows the item count and h1 is a 64-bit mix);
-// the caller then runs the sort-based path.
+// Bucketed aggregation (agg.cuh): stable partition of the stream on the top bits of h1 -- every item taking along the
+// neighbour hashes whose adjacent pair it owns --, then one CTA per bucket groups the nodes, and a second one the
+// edges those nodes own, in shared memory.  Returns false -- nothing of `g` touched -- if a bucket holds more
+// distinct hashes than its table takes (not expected: the bucket count follows the item count and h1 is a 64-bit
+// mix) or a hash is 0 (the "no neighbour" marker); the caller then runs the sort-based path.
+constexpr int kEdgeSlotBits = 11, kEdgeItems = 2;
+using EdgeSmem = agg::BucketEdgeSmem<kEdgeSlotBits, kEdgeItems>;
+
+__global__ void node_hash_gather_kernel(const sw_node* __restrict__ nodes, uint64_t n, uint64_t* __restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = nodes[i].hash;
+}
+
 bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                           GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
 {
@@ -588,55 +598,48 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     GraphTimes tm;
     EventTimer timer(s);
     timer.start();
-    // adjacent-pair records per block of the stream (read at the node stage's synchronisation point)
-    const uint32_t nb = blocks_for(M);
-    DevBuf<unsigned long long> ecnt((size_t)nb + 1, s, true);
-    edge_count_kernel<<<nb, kNT, 0, s>>>(st.vals.p, M, ecnt.p);
-    exclusive_scan_u64(ecnt.p, nb, ecnt.p + nb, s);
-    SW_CUDA(cudaGetLastError());
-    const unsigned long long* n_raw_p = readback_u64(ecnt.p + nb, 1, s);
-    tm.launches += 2;
 
-    // scratch: four arrays of M 64-bit words, carved again for the edge stage
-    DevBuf<uint64_t> w0(M, s, true), w1(M, s, true), w2(M, s, true), w3(M, s, true);
-    DevBuf<uint16_t> item_rank(M, s, true);   // rank of every item's key inside its bucket (nodes, then edges)
+    // scratch: two sets of four M-word arrays (keys | k-mers | owned previous | owned next neighbour), each one block
+    DevBuf<uint64_t> setA(4 * M, s, true), setB(4 * M, s, true);
+    const NbrBuffers A{setA.p, setA.p + M, setA.p + 2 * M, setA.p + 3 * M};
+    const NbrBuffers B{setB.p, setB.p + M, setB.p + 2 * M, setB.p + 3 * M};
+    DevBuf<uint16_t> item_rank(M, s, true);   // rank of every item's hash inside its bucket
 
-    // -- nodes: partition (h1, kmer) on the top P bits, distinct hashes per bucket ----------------------------
-    // bucket size: about 400 distinct hashes each, which takes an estimate of the k-mers per distinct hash
-    DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
+    // -- nodes: partition on the top P bits of h1, distinct hashes per bucket ---------------------------------------
+    // bucket size: about `target` distinct hashes each, which takes an estimate of the k-mers per distinct hash
     double per_node = st.items_per_key;   // taken by the sketch's reorder pass; a stream from elsewhere is sampled here
     if (per_node <= 0) {
+        DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
         per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
         tm.launches += 1;
     }
     const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
     const int P = fixed_nb ? partition_bits(M, fixed_nb)
-                           : partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 400), env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
+                           : partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 300),
+                                                env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
     const int key_bits = 64 - P;
     const uint64_t n_buckets = 1ull << P;
-    const uint64_t* pk = nullptr;
-    const unsigned long long* pv = nullptr;
-    tm.launches += radix_partition_top<unsigned long long>(st.keys.p, reinterpret_cast<const unsigned long long*>(st.vals.p), M, P,
-                                                           w0.p, reinterpret_cast<unsigned long long*>(w2.p), w1.p,
-                                                           reinterpret_cast<unsigned long long*>(w3.p), s, &pk, &pv);
-    uint64_t* grp_keys = pk == w0.p ? w1.p : w0.p;     // the ping-pong pair that does not hold the result is free
-    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(pk == w0.p ? w3.p : w2.p);
+    DevBuf<unsigned long long> tot(4, s, true);   // [0] overflowing node buckets [1] their items [2] nodes; [3] low word: a key is 0
+    SW_CUDA(cudaMemsetAsync(tot.p, 0, 4 * sizeof(unsigned long long), s));
+    const NbrBuffers* R = nullptr;
+    tm.launches += radix_partition_top_nbr(st.keys.p, st.vals.p, M, P, A, B, s, &R, reinterpret_cast<unsigned int*>(tot.p + 3));
+    const NbrBuffers& Dd = R == &A ? B : A;            // the set that does not hold the result is free
+    uint64_t* grp_keys = Dd.keys;                      // distinct hashes of every bucket (live until the edges are written)
+    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(Dd.vals);
     DevBuf<uint32_t> start(n_buckets + 1, s, true), bucket_d(n_buckets, s, true);
-    DevBuf<unsigned long long> d64(n_buckets + 1, s, true), tot(3, s, true);
-    bucket_search_kernel<<<stride_grid(n_buckets + 1), 256, 0, s>>>(pk, M, key_bits, n_buckets, start.p);
-    group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(pk, start.p, key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
+    DevBuf<unsigned long long> d64(n_buckets + 1, s, true);
+    bucket_search_kernel<<<stride_grid(n_buckets + 1), 256, 0, s>>>(R->keys, M, key_bits, n_buckets, start.p);
+    group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(R->keys, start.p, key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
                                                            bucket_d.p, item_rank.p);
-    SW_CUDA(cudaMemsetAsync(tot.p, 0, 3 * sizeof(unsigned long long), s));
     SW_CUDA(cudaMemsetAsync(d64.p + n_buckets, 0, sizeof(unsigned long long), s));
     bucket_counts_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_d.p, start.p, n_buckets, d64.p, nullptr, tot.p);
     tm.launches += 3 + exclusive_scan_u64(d64.p, n_buckets + 1, tot.p + 2, s);
     SW_CUDA(cudaGetLastError());
-    const unsigned long long* tot_p = readback_u64(tot.p, 3, s);
+    const unsigned long long* tot_p = readback_u64(tot.p, 4, s);
     SW_CUDA(cudaStreamSynchronize(s));
     tm.sort_nodes_ms = timer.stop();
-    if (tot_p[0] != 0) return false;
+    if (tot_p[0] != 0 || tot_p[3] != 0) return false;
     const unsigned long long n_nodes = tot_p[2];
-    const unsigned long long n_raw = *n_raw_p;
 
     // -- nodes + kmers (+ scoring) -----------------------------------------------------------------------------
     timer.start();
@@ -644,16 +647,15 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     g.n_nodes = n_nodes;
     g.kmers.alloc(M, s);
     g.nodes.alloc(n_nodes, s);
-    DevBuf<uint64_t> node_hash(n_nodes, s, true);
     const ArenaMark node_mark = arena_mark();   // what follows is dead once the placement kernel has run
     DevBuf<uint32_t> node_asm(score ? M : 0, s, true);
     const PlaceArgs pa{item_rank.p, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
     NodeOut no{};
-    no.vals = pv;
+    no.vals = reinterpret_cast<const unsigned long long*>(R->vals);
     no.placed = reinterpret_cast<unsigned long long*>(g.kmers.p);
     no.placed_asm = node_asm.p;
     no.nodes = g.nodes.p;
-    no.node_hash = node_hash.p;
+    no.node_hash = nullptr;
     no.rec_asm = d_rec_asm;
     no.rec_base = rec_base;
     if (score) {
@@ -670,118 +672,96 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     timer.mark();
     arena_release(node_mark);
 
-    // -- edges ---------------------------------------------------------------------------------------------------
+    // -- edges: grouped inside the node buckets (the group sizes in Dd.vals and the keys of R are dead now) ------------
     EventTimer etimer(s);
     etimer.start();
-    int rank_bits = 1;
-    while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
-    // edge-stage views of the scratch (n_raw < M): raw records, two ping-pong pairs, placed assemblies
-    uint64_t* ekey0 = w0.p;
-    uint64_t* eka = w1.p;
-    uint64_t* ekb = w2.p;
-    uint32_t* easm0 = reinterpret_cast<uint32_t*>(w3.p);
-    uint32_t* eva = easm0 + M;
-    DevBuf<uint32_t> evb;
-    if (n_raw) {
-        // ranks are looked up: fine bucket table over the sorted node hashes (about one node per bucket)
-        int fbits = 1;
-        while (fbits < 28 && (1ull << fbits) < n_nodes) ++fbits;
-        DevBuf<uint32_t> ftable((1ull << fbits) + 1, s, true);
-        bucket_bounds_kernel<<<stride_grid(n_nodes + 1), 256, 0, s>>>(node_hash.p, n_nodes, 64 - fbits, 1ull << fbits, ftable.p);
-        // the emitter also takes the hash-range sample of its keys (records per distinct pair)
-        SW_CUDA(cudaMemsetAsync(sample_set.p, 0xFF, sample_set.bytes(), s));
-        SW_CUDA(cudaMemsetAsync(sample_out.p, 0, sample_out.bytes(), s));
-        edge_emit_kernel<<<nb, kNT, 0, s>>>(st.keys.p, st.vals.p, M, node_hash.p, ftable.p, 64 - fbits, d_rec_asm, rec_base, ecnt.p,
-                                            rank_bits, ekey0, easm0, sample_bits(n_raw), sample_set.p, sample_out.p);
-        SW_CUDA(cudaGetLastError());
-        tm.launches += 2;
-    }
+    DevBuf<uint32_t> bucket_e(n_buckets, s, true), bucket_rec(n_buckets, s, true);
+    DevBuf<unsigned long long> e64(n_buckets + 1, s, true), ebase(n_buckets + 1, s, true), side_rec(n_buckets + 1, s, true),
+        etot(4, s, true);
+    BucketEdgeArgs ea{};
+    ea.item_rank = item_rank.p;
+    ea.nb_prev = R->prev;
+    ea.nb_next = R->next;
+    ea.vals = reinterpret_cast<const unsigned long long*>(R->vals);
+    ea.start = start.p;
+    ea.rec_asm = d_rec_asm;
+    ea.rec_base = rec_base;
+    ea.max_distinct = std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", EdgeSmem::kEMax), EdgeSmem::kEMax);
+    ea.te_second = Dd.prev;                                   // 2 M words: Dd.prev | Dd.next
+    ea.te_w = reinterpret_cast<uint32_t*>(Dd.vals);           // 2 M u32
+    ea.te_r = reinterpret_cast<uint16_t*>(R->keys);           // 2 M u16
+    ea.bucket_e = bucket_e.p;
+    ea.bucket_rec = bucket_rec.p;
+    SW_CUDA(cudaFuncSetAttribute(bucket_edges_kernel<kEdgeSlotBits, kEdgeItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(EdgeSmem)));
+    bucket_edges_kernel<kEdgeSlotBits, kEdgeItems><<<(uint32_t)n_buckets, kNT, sizeof(EdgeSmem), s>>>(ea);
+    SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
+    SW_CUDA(cudaMemsetAsync(e64.p + n_buckets, 0, sizeof(unsigned long long), s));
+    SW_CUDA(cudaMemsetAsync(side_rec.p + n_buckets, 0, sizeof(unsigned long long), s));
+    bucket_edge_counts_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_e.p, bucket_rec.p, n_buckets, e64.p, side_rec.p, etot.p);
+    SW_CUDA(cudaMemcpyAsync(ebase.p, e64.p, (n_buckets + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    tm.launches += 2 + exclusive_scan_u64(ebase.p, n_buckets + 1, etot.p + 2, s);
+    SW_CUDA(cudaGetLastError());
     if (after_nodes) (*after_nodes)();
     tm.nodes_ms = timer.read();
-    if (n_raw == 0) {
-        g.n_edges = 0;
-        g.edges.alloc(0, s);
-    } else {
-        evb.alloc(M, s, true);
-        // records per distinct pair -> about 192 distinct pairs per bucket (min(u, v) makes the low buckets twice as full)
-        const unsigned long long* eh = readback_u64(sample_out.p, 2, s);
-        SW_CUDA(cudaStreamSynchronize(s));
-        const double per_edge = eh[1] ? (double)eh[0] / (double)eh[1] : 1.0;
-        const uint32_t fixed_eb = env_u32("SEQWIN_AGG_EDGE_BUCKET", 0);
-        const int Pe = std::min(fixed_eb ? partition_bits(n_raw, fixed_eb)
-                                         : partition_bits_for(n_raw, per_edge, (double)env_u32("SEQWIN_AGG_EDGE_TARGET", 192), env_u32("SEQWIN_AGG_MAX_ITEMS", 4096)),
-                                2 * rank_bits);
-        const int ekey_bits = 64 - Pe;
-        const uint64_t neb = 1ull << Pe;
-        const uint64_t* pek = nullptr;
-        const uint32_t* pev = nullptr;
-        tm.launches += radix_partition_top<uint32_t>(ekey0, easm0, n_raw, Pe, eka, eva, ekb, evb.p, s, &pek, &pev);
-        uint64_t* egrp_keys = pek == eka ? ekb : eka;
-        uint32_t* egrp_cnt = pek == eka ? evb.p : eva;
-        DevBuf<uint32_t> estart(neb + 1, s, true), ebucket_d(neb, s, true);
-        DevBuf<unsigned long long> ed64(neb + 1, s, true), ebase(neb + 1, s, true), ovf_items(neb + 1, s, true), etot(4, s, true);
-        bucket_search_kernel<<<stride_grid(neb + 1), 256, 0, s>>>(pek, n_raw, ekey_bits, neb, estart.p);
-        // distinct pairs of every bucket and their weights (distinct assemblies), in one pass over the records
-        SW_CUDA(cudaFuncSetAttribute(edge_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeGroupSmem)));
-        edge_group_kernel<<<(uint32_t)neb, kNT, sizeof(EdgeGroupSmem), s>>>(
-            pek, pev, estart.p, ekey_bits, std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", kMaxDistinct), kMaxDistinct),
-            egrp_keys, egrp_cnt, ebucket_d.p);
-        SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
-        SW_CUDA(cudaMemsetAsync(ed64.p + neb, 0, sizeof(unsigned long long), s));
-        SW_CUDA(cudaMemsetAsync(ovf_items.p + neb, 0, sizeof(unsigned long long), s));
-        bucket_counts_kernel<<<stride_grid(neb), 256, 0, s>>>(ebucket_d.p, estart.p, neb, ed64.p, ovf_items.p, etot.p);
-        SW_CUDA(cudaMemcpyAsync(ebase.p, ed64.p, (neb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-        tm.launches += 3 + exclusive_scan_u64(ebase.p, neb + 1, etot.p + 2, s);
+    const unsigned long long* etot_p = readback_u64(etot.p, 4, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    unsigned long long n_edges = etot_p[2];
+    const unsigned long long n_ovf = etot_p[0], n_side = etot_p[1];
+    if (getenv("SEQWIN_DEBUG_AGG"))
+        fprintf(stderr, "[agg] M %llu (%.2f per node) P %d nodes %llu edges %llu, %llu buckets (%llu records) to the sort path\n",
+                (unsigned long long)M, per_node, P, n_nodes, n_edges, n_ovf, n_side);
+    DevBuf<sw_edge> side_edges;
+    DevBuf<unsigned long long> ovf_e64;
+    if (n_ovf) {
+        // buckets with more distinct pairs than a table takes (hub nodes): their records get global rank pairs,
+        // are sorted on the whole key and run-length encoded, as the sort-based path does for everything
+        int rank_bits = 1;
+        while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
+        int fbits = 1;
+        while (fbits < 28 && (1ull << fbits) < n_nodes) ++fbits;
+        DevBuf<uint64_t> node_hash(n_nodes, s, true);
+        DevBuf<uint32_t> ftable((1ull << fbits) + 1, s, true);
+        node_hash_gather_kernel<<<stride_grid(n_nodes), 256, 0, s>>>(g.nodes.p, n_nodes, node_hash.p);
+        bucket_bounds_kernel<<<stride_grid(n_nodes + 1), 256, 0, s>>>(node_hash.p, n_nodes, 64 - fbits, 1ull << fbits, ftable.p);
+        exclusive_scan_u64(side_rec.p, n_buckets + 1, etot.p + 3, s);     // -> first side slot of every such bucket
+        SortPairs sp;
+        sp.n = n_side;
+        sp.keys.alloc(n_side, s, true);
+        sp.vals.alloc(n_side, s, true);
+        side_emit_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(ea, bucket_e.p, side_rec.p, d64.p, node_hash.p, ftable.p, 64 - fbits,
+                                                             rank_bits, sp.keys.p, sp.vals.p);
         SW_CUDA(cudaGetLastError());
-        const unsigned long long* etot_p = readback_u64(etot.p, 4, s);
+        tm.launches += 4 + radix_sort_pairs(sp, 64, s, (64 - 2 * rank_bits) & ~7);
+        ovf_e64.alloc(n_buckets + 1, s, true);
+        SW_CUDA(cudaMemsetAsync(ovf_e64.p + n_buckets, 0, sizeof(unsigned long long), s));
+        side_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(sp.keys.p, bucket_e.p, side_rec.p, e64.p, ovf_e64.p);
+        exclusive_scan_u64(ovf_e64.p, n_buckets + 1, etot.p + 3, s);
+        SW_CUDA(cudaMemcpyAsync(ebase.p, e64.p, (n_buckets + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        exclusive_scan_u64(ebase.p, n_buckets + 1, etot.p + 2, s);
+        const uint32_t sb = blocks_for(n_side);
+        DevBuf<unsigned long long> scounts((size_t)sb + 1, s, true);
+        key_run_count_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, n_side, scounts.p);
+        exclusive_scan_u64(scounts.p, sb, scounts.p + sb, s);
+        SW_CUDA(cudaGetLastError());
+        const unsigned long long* e2 = readback_u64(etot.p, 4, s);
         SW_CUDA(cudaStreamSynchronize(s));
-        unsigned long long n_edges = etot_p[2];
-        const unsigned long long n_ovf = etot_p[0], n_side = etot_p[1];
-        if (getenv("SEQWIN_DEBUG_AGG"))
-            fprintf(stderr, "[agg] M %llu (%.2f per node) P %d nodes %llu | pairs %llu (%.2f per edge) Pe %d edges %llu, %llu buckets (%llu records) to the sort path\n",
-                    (unsigned long long)M, per_node, P, n_nodes, n_raw, per_edge, Pe, n_edges, n_ovf, n_side);
-        DevBuf<sw_edge> side_edges;
-        DevBuf<unsigned long long> ovf_d64;
-        if (n_ovf) {
-            // buckets with more distinct pairs than a table takes (hub nodes): their records are sorted on the
-            // whole key and run-length encoded, as the sort-based path does for everything
-            exclusive_scan_u64(ovf_items.p, neb + 1, etot.p + 3, s);     // -> first side slot of every such bucket
-            SortPairs sp;
-            sp.n = n_side;
-            sp.keys.alloc(n_side, s, true);
-            sp.vals.alloc(n_side, s, true);
-            overflow_gather_kernel<uint32_t><<<(uint32_t)neb, kNT, 0, s>>>(pek, pev, estart.p, ebucket_d.p, ovf_items.p, sp.keys.p,
-                                                                           sp.vals.p);
-            SW_CUDA(cudaGetLastError());
-            tm.launches += 2 + radix_sort_pairs(sp, 64, s, (64 - 2 * rank_bits) & ~7);
-            ovf_d64.alloc(neb + 1, s, true);
-            SW_CUDA(cudaMemsetAsync(ovf_d64.p + neb, 0, sizeof(unsigned long long), s));
-            overflow_count_kernel<<<(uint32_t)neb, kNT, 0, s>>>(sp.keys.p, estart.p, ebucket_d.p, ovf_items.p, ed64.p, ovf_d64.p);
-            exclusive_scan_u64(ovf_d64.p, neb + 1, etot.p + 3, s);
-            SW_CUDA(cudaMemcpyAsync(ebase.p, ed64.p, (neb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-            exclusive_scan_u64(ebase.p, neb + 1, etot.p + 2, s);
-            const uint32_t sb = blocks_for(n_side);
-            DevBuf<unsigned long long> scounts((size_t)sb + 1, s, true);
-            key_run_count_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, n_side, scounts.p);
-            exclusive_scan_u64(scounts.p, sb, scounts.p + sb, s);
-            SW_CUDA(cudaGetLastError());
-            const unsigned long long* e2 = readback_u64(etot.p, 4, s);
-            SW_CUDA(cudaStreamSynchronize(s));
-            n_edges = e2[2];
-            const unsigned long long n_side_edges = e2[3];
-            side_edges.alloc(n_side_edges, s, true);
-            SW_CUDA(cudaMemsetAsync(side_edges.p, 0, n_side_edges * sizeof(sw_edge), s));
-            edge_final_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_side, scounts.p, rank_bits, node_hash.p, side_edges.p);
-            SW_CUDA(cudaGetLastError());
-            tm.launches += 8;
-        }
-        g.n_edges = n_edges;
-        g.edges.alloc(n_edges, s);
-        edge_out_kernel<<<(uint32_t)std::min<uint64_t>((neb + 7) / 8, (uint64_t)sm_count() * 16), 256, 0, s>>>(
-            egrp_keys, egrp_cnt, estart.p, ebucket_d.p, ebase.p, neb, node_hash.p, rank_bits, g.edges.p);
+        n_edges = e2[2];
+        const unsigned long long n_side_edges = e2[3];
+        side_edges.alloc(n_side_edges, s, true);
+        SW_CUDA(cudaMemsetAsync(side_edges.p, 0, n_side_edges * sizeof(sw_edge), s));
+        edge_final_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_side, scounts.p, rank_bits, node_hash.p, side_edges.p);
+        SW_CUDA(cudaGetLastError());
+        tm.launches += 8;
+    }
+    g.n_edges = n_edges;
+    g.edges.alloc(n_edges, s);
+    if (n_edges) {
+        bucket_edges_out_kernel<<<(uint32_t)std::min<uint64_t>((n_buckets + 7) / 8, (uint64_t)sm_count() * 16), 256, 0, s>>>(
+            ea.te_second, ea.te_w, ea.te_r, start.p, bucket_e.p, ebase.p, n_buckets, grp_keys, g.edges.p);
         ++tm.launches;
         if (n_ovf) {
-            overflow_copy_kernel<<<(uint32_t)neb, kNT, 0, s>>>(side_edges.p, ebucket_d.p, ebase.p, ovf_d64.p, g.edges.p);
+            overflow_copy_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(side_edges.p, bucket_e.p, ebase.p, ovf_e64.p, g.edges.p);
             ++tm.launches;
         }
         SW_CUDA(cudaGetLastError());

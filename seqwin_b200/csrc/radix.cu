@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "device.h"
+#include "nbr.cuh"
 
 namespace sw {
 
@@ -107,13 +108,25 @@ struct OnesweepSmem {
 };
 
 // One tile of one pass.  FULL = the tile holds NT * ITEMS items (no bounds checks).
-template <int NT, int ITEMS, bool FULL, typename V>
+// Two more 64-bit value arrays that travel with the pairs: the OWNED neighbour hashes of every minimizer
+// (agg.cuh, bucket_edges_kernel).  gen: the first pass of a partition derives them from the stream itself
+// (in.a / in.b are not read); the later passes carry them.
+struct NbrArrays {
+    const uint64_t* in_a = nullptr;
+    const uint64_t* in_b = nullptr;
+    uint64_t* out_a = nullptr;
+    uint64_t* out_b = nullptr;
+    uint64_t n_total = 0;            // gen: items of the whole stream (neighbours across tile borders)
+    unsigned int* zero_key = nullptr;   // gen: set when a key is 0 (the "not owned" marker would be ambiguous)
+};
+
+template <int NT, int ITEMS, bool FULL, typename V, int NBR>   // NBR: 0 = pairs only, 1 = carry the neighbour arrays, 2 = generate them
 __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint64_t* s_buf, V* s_vin,
                                               const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
                                               const V* __restrict__ vin, V* __restrict__ vout,
                                               uint32_t n_valid, uint32_t tile, int shift, uint32_t dmask,
                                               const unsigned long long* __restrict__ goff, unsigned long long* status,
-                                              uint32_t n_tiles)
+                                              uint32_t n_tiles, const NbrArrays& nb, uint64_t tile_base)
 {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -247,13 +260,51 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
         const uint32_t p = (uint32_t)i * NT + tid;
         if (FULL || p < n_valid) vout[sm.dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_val[p];
     }
+    if (NBR != 0) {
+        // the two neighbour arrays take the same route, one after the other; their loads are issued together
+        static_assert(NBR == 0 || sizeof(V) == 8, "neighbour arrays travel with 64-bit values");
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            uint64_t tmp[ITEMS];
+            if (NBR == 2) {
+                const uint64_t* keys = kin - tile_base;    // whole-stream views (kin / vin point at the tile)
+                const uint64_t* vals = reinterpret_cast<const uint64_t*>(vin) - tile_base;
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    tmp[i] = 0;
+                    if (FULL || wofs + i * 32 < n_valid) {
+                        const uint64_t g = tile_base + wofs + i * 32;
+                        const uint64_t h = keys[g];
+                        const uint32_t rec = (uint32_t)(vals[g] >> 32);
+                        tmp[i] = a == 0 ? agg::owned_prev(keys, vals, g, h, rec) : agg::owned_next(keys, vals, g, nb.n_total, h, rec);
+                        if (a == 0 && h == 0) *nb.zero_key = 1u;
+                    }
+                }
+            } else {
+                const uint64_t* src = (a == 0 ? nb.in_a : nb.in_b) + tile_base + wofs;
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) tmp[i] = (FULL || wofs + i * 32 < n_valid) ? src[i * 32] : 0;
+            }
+            __syncthreads();   // the previous array has left the staging buffer
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i)
+                if (FULL || wofs + i * 32 < n_valid) s_buf[rank[i]] = tmp[i];
+            __syncthreads();
+            uint64_t* dst = a == 0 ? nb.out_a : nb.out_b;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t p = (uint32_t)i * NT + tid;
+                if (FULL || p < n_valid) dst[sm.dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_buf[p];
+            }
+        }
+    }
 }
 
-template <int NT, int ITEMS, typename V>
+template <int NT, int ITEMS, typename V, int NBR = 0>
 __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const V* __restrict__ vin,
     V* __restrict__ vout, uint64_t n, int shift, uint32_t dmask, const unsigned long long* __restrict__ goff,
-    unsigned long long* status, unsigned int* ticket)
+    unsigned long long* status, unsigned int* ticket, const NbrArrays nb = NbrArrays())
 {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * ITEMS;
@@ -271,11 +322,11 @@ __global__ void __launch_bounds__(NT, SW_SORT_MINB) radix_onesweep_kernel(
     const uint64_t tile_base = (uint64_t)tile * TILE;
     const uint32_t n_valid = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
     if (n_valid == (uint32_t)TILE)
-        onesweep_tile<NT, ITEMS, true, V>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
-                                          shift, dmask, goff, status, gridDim.x);
+        onesweep_tile<NT, ITEMS, true, V, NBR>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
+                                               shift, dmask, goff, status, gridDim.x, nb, tile_base);
     else
-        onesweep_tile<NT, ITEMS, false, V>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
-                                           shift, dmask, goff, status, gridDim.x);
+        onesweep_tile<NT, ITEMS, false, V, NBR>(sm, s_buf, s_vin, kin + tile_base, kout, vin + tile_base, vout, n_valid, tile,
+                                                shift, dmask, goff, status, gridDim.x, nb, tile_base);
 }
 
 // The passes of `ps` over (kin, vin): pass 0 reads the input (left untouched), the others ping-pong between
@@ -376,6 +427,68 @@ uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, in
     *out_v = where < 0 ? vals : (where == 0 ? va : vb);
     return launches;
 }
+// The same partition for the node stage: (key, value) plus the two owned-neighbour arrays, which the first
+// pass generates from the stream (every pass runs, also one whose keys share a digit).
+uint32_t radix_partition_top_nbr(const uint64_t* keys, const uint64_t* vals, uint64_t n, int top_bits, const NbrBuffers& A,
+                                 const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out, unsigned int* d_zero_key)
+{
+    using V = unsigned long long;
+    RadixPasses ps{};
+    const int np = (top_bits + kRadixBits - 1) / kRadixBits;
+    int lo = 64 - top_bits;
+    for (int p = 0; p < np; ++p) {
+        const int bits = p == 0 ? top_bits - kRadixBits * (np - 1) : kRadixBits;
+        ps.shift[ps.n] = lo;
+        ps.bits[ps.n] = bits;
+        ++ps.n;
+        lo += bits;
+    }
+    uint32_t launches = 0;
+    DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s, true);
+    SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
+    const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
+    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(keys, n, ps, ghist.p);
+    DevBuf<unsigned long long> max_bin(kMaxPasses, s, true);
+    radix_offsets_kernel<<<ps.n, kRadix, 0, s>>>(ghist.p, max_bin.p);
+    SW_CUDA(cudaGetLastError());
+    launches += 2;
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);
+    DevBuf<unsigned int> ticket(1, s, true);
+    constexpr size_t kSortSmem = (size_t)kSortTile * (8 + sizeof(V));
+    SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems, V, 1>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems, V, 2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    const NbrBuffers* src = nullptr;
+    for (int p = 0; p < ps.n; ++p) {
+        const NbrBuffers* dst = src == &A ? &B : &A;
+        SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
+        SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
+        NbrArrays nb;
+        nb.out_a = dst->prev;
+        nb.out_b = dst->next;
+        if (p == 0) {
+            nb.n_total = n;
+            nb.zero_key = d_zero_key;
+            radix_onesweep_kernel<kSortThreads, kSortItems, V, 2><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
+                keys, dst->keys, reinterpret_cast<const V*>(vals), reinterpret_cast<V*>(dst->vals), n, ps.shift[p],
+                (1u << ps.bits[p]) - 1u, ghist.p + (size_t)p * kRadix, status.p, ticket.p, nb);
+        } else {
+            nb.in_a = src->prev;
+            nb.in_b = src->next;
+            radix_onesweep_kernel<kSortThreads, kSortItems, V, 1><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
+                src->keys, dst->keys, reinterpret_cast<const V*>(src->vals), reinterpret_cast<V*>(dst->vals), n, ps.shift[p],
+                (1u << ps.bits[p]) - 1u, ghist.p + (size_t)p * kRadix, status.p, ticket.p, nb);
+        }
+        SW_CUDA(cudaGetLastError());
+        ++launches;
+        src = dst;
+    }
+    *out = src;
+    return launches;
+}
+
 template uint32_t radix_partition_top<uint32_t>(const uint64_t*, const uint32_t*, uint64_t, int, uint64_t*, uint32_t*, uint64_t*,
                                                 uint32_t*, cudaStream_t, const uint64_t**, const uint32_t**);
 template uint32_t radix_partition_top<unsigned long long>(const uint64_t*, const unsigned long long*, uint64_t, int, uint64_t*,

@@ -48,7 +48,7 @@ extern "C" double agg_emul_estimate(const uint64_t* keys, uint64_t n, int sbits)
 
 extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream_vals, uint64_t M, const uint32_t* rec_asm,
                              uint32_t rec_base, const uint8_t* is_target, int score, uint32_t n_targets, uint32_t n_non_targets,
-                             uint32_t per_bucket_nodes, uint32_t per_bucket_edges, uint32_t max_distinct_edges, sw_kmer* kmers_out,
+                             uint32_t per_bucket_nodes, uint32_t max_distinct_edges, sw_kmer* kmers_out,
                              sw_node* nodes_out, sw_edge* edges_out, uint64_t* n_nodes_out, uint64_t* n_edges_out,
                              uint64_t* n_overflow_out)
 {
@@ -58,11 +58,40 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     const int P = partition_bits(M, per_bucket_nodes);
     const int key_bits = 64 - P;
     const uint64_t nb = 1ull << P;
+    // what the first partition pass generates on the device (radix.cu): the owned neighbour hashes of every item
+    std::vector<uint64_t> prev(M), next(M);
+    for (uint64_t g = 0; g < M; ++g) {
+        if (stream_keys[g] == 0) return -3;   // the product takes the sort-based path
+        const uint32_t rec = (uint32_t)(stream_vals[g] >> 32);
+        prev[g] = owned_prev(stream_keys, stream_vals, g, stream_keys[g], rec);
+        next[g] = owned_next(stream_keys, stream_vals, g, M, stream_keys[g], rec);
+    }
     std::vector<uint64_t> keys(stream_keys, stream_keys + M);
     std::vector<unsigned long long> vals(stream_vals, stream_vals + M);
-    stable_partition_top_bits(keys, vals, key_bits);
+    {   // stable partition of the four arrays on the top P bits
+        std::vector<uint32_t> idx(M);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return (keys[x] >> key_bits) < (keys[y] >> key_bits); });
+        std::vector<uint64_t> k2(M), p2(M), n2(M);
+        std::vector<unsigned long long> v2(M);
+        for (uint64_t i = 0; i < M; ++i) {
+            k2[i] = keys[idx[i]];
+            v2[i] = vals[idx[i]];
+            p2[i] = prev[idx[i]];
+            n2[i] = next[idx[i]];
+        }
+        keys.swap(k2);
+        vals.swap(v2);
+        prev.swap(p2);
+        next.swap(n2);
+    }
     std::vector<uint32_t> start(nb + 1, 0xDEADBEEFu), bucket_d(nb, 0xABABABABu);
-    cuemu::launch(dim3(3), dim3(256), [&] { bucket_bounds_kernel(keys.data(), M, key_bits, nb, start.data()); });
+    cuemu::launch(dim3(3), dim3(256), [&] { bucket_search_kernel(keys.data(), M, key_bits, nb, start.data()); });
+    {   // the scan variant of the bounds must agree with the binary search
+        std::vector<uint32_t> start2(nb + 1, 0xDEADBEEFu);
+        cuemu::launch(dim3(3), dim3(256), [&] { bucket_bounds_kernel(keys.data(), M, key_bits, nb, start2.data()); });
+        if (start2 != start) return -2;
+    }
     std::vector<uint64_t> grp_keys(M);
     std::vector<uint32_t> grp_cnt(M);
     std::vector<uint16_t> item_rank(M, 0xEEEE);
@@ -75,7 +104,6 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     if (tot[0]) return -1;   // a node bucket overflowed: the product falls back to the sort-based path
     std::vector<unsigned long long> grp_base = exclusive_scan(d64);
     const uint64_t U = grp_base[nb];
-    std::vector<uint64_t> node_hash(U);
     PlaceArgs pa{item_rank.data(), start.data(), key_bits, grp_keys.data(), grp_cnt.data(), bucket_d.data(), grp_base.data()};
     NodeOut no{};
     no.vals = vals.data();
@@ -83,7 +111,7 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     std::vector<uint32_t> node_asm(M);
     no.placed_asm = node_asm.data();
     no.nodes = nodes_out;
-    no.node_hash = node_hash.data();
+    no.node_hash = nullptr;
     no.rec_asm = rec_asm;
     no.rec_base = rec_base;
     no.is_target = is_target;
@@ -94,62 +122,57 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     else cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] { group_place_kernel<NodeOut, false>(pa, no); });
     *n_nodes_out = U;
 
-    // ---- edges ----
-    int fbits = 1;
-    while (fbits < 28 && (1ull << fbits) < U) ++fbits;
-    std::vector<uint32_t> ftable((1ull << fbits) + 1);
-    cuemu::launch(dim3(2), dim3(256), [&] { bucket_bounds_kernel(node_hash.data(), U, 64 - fbits, 1ull << fbits, ftable.data()); });
-    int rank_bits = 1;
-    while (rank_bits < 32 && (1ull << rank_bits) < U) ++rank_bits;
-    const uint32_t n_blocks = (uint32_t)((M + kEmitItems - 1) / kEmitItems);
-    std::vector<unsigned long long> block_cnt(n_blocks, 0);
-    for (uint64_t i = 0; i + 1 < M; ++i)
-        if ((stream_vals[i] >> 32) == (stream_vals[i + 1] >> 32)) ++block_cnt[i / kEmitItems];
-    std::vector<unsigned long long> block_off = exclusive_scan(block_cnt);
-    const uint64_t E = block_off[n_blocks];
-    if (E == 0) return 0;
-    std::vector<uint64_t> ekey(E);
-    std::vector<uint32_t> easm(E);
-    cuemu::launch(dim3(n_blocks), dim3(kNT), [&] {
-        edge_emit_kernel(stream_keys, stream_vals, M, node_hash.data(), ftable.data(), 64 - fbits, rec_asm, rec_base,
-                         block_off.data(), rank_bits, ekey.data(), easm.data(), 0, nullptr, nullptr);
+    // ---- edges: grouped inside the node buckets ----
+    constexpr int ESB = 11, EI = 2;
+    using Smem = BucketEdgeSmem<ESB, EI>;
+    std::vector<uint64_t> te_second(2 * M, 0xDDDDDDDDDDDDDDDDull);
+    std::vector<uint32_t> te_w(2 * M, 0xDDDDDDDDu), bucket_e(nb, 0xABABABABu), bucket_rec(nb, 0xABABABABu);
+    std::vector<uint16_t> te_r(2 * M, 0xDDDD);
+    BucketEdgeArgs ea{};
+    ea.item_rank = item_rank.data();
+    ea.nb_prev = prev.data();
+    ea.nb_next = next.data();
+    ea.vals = vals.data();
+    ea.start = start.data();
+    ea.rec_asm = rec_asm;
+    ea.rec_base = rec_base;
+    ea.max_distinct = std::min<uint32_t>(max_distinct_edges, Smem::kEMax);
+    ea.te_second = te_second.data();
+    ea.te_w = te_w.data();
+    ea.te_r = te_r.data();
+    ea.bucket_e = bucket_e.data();
+    ea.bucket_rec = bucket_rec.data();
+    cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] { bucket_edges_kernel<ESB, EI>(ea); });
+    std::vector<unsigned long long> e64(nb), side_rec(nb), etot(2, 0);
+    cuemu::launch(dim3(2), dim3(256), [&] {
+        bucket_edge_counts_kernel(bucket_e.data(), bucket_rec.data(), nb, e64.data(), side_rec.data(), etot.data());
     });
-    const int Pe = partition_bits(E, per_bucket_edges);
-    const int ekey_bits = 64 - Pe;
-    const uint64_t neb = 1ull << Pe;
-    stable_partition_top_bits(ekey, easm, ekey_bits);
-    std::vector<uint32_t> estart(neb + 1), ebucket_d(neb);
-    cuemu::launch(dim3(3), dim3(256), [&] { bucket_bounds_kernel(ekey.data(), E, ekey_bits, neb, estart.data()); });
-    {   // the binary-search variant of the bounds must agree with the scan
-        std::vector<uint32_t> estart2(neb + 1, 0xDEADBEEFu);
-        cuemu::launch(dim3(3), dim3(256), [&] { bucket_search_kernel(ekey.data(), E, ekey_bits, neb, estart2.data()); });
-        if (estart2 != estart) return -2;
-    }
-    std::vector<uint64_t> egrp_keys(E);
-    std::vector<uint32_t> egrp_cnt(E);
-    cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
-        edge_group_kernel(ekey.data(), easm.data(), estart.data(), ekey_bits, max_distinct_edges, egrp_keys.data(), egrp_cnt.data(),
-                          ebucket_d.data());
-    });
-    std::vector<unsigned long long> ed64(neb), ovf_items(neb), etot(2, 0);
-    cuemu::launch(dim3(2), dim3(256), [&] { bucket_counts_kernel(ebucket_d.data(), estart.data(), neb, ed64.data(), ovf_items.data(), etot.data()); });
     std::vector<sw_edge> side_edges;
-    std::vector<unsigned long long> ovf_d64(neb, 0), ovf_base;
+    std::vector<unsigned long long> ovf_e64(nb, 0), ovf_base;
     if (etot[0]) {
-        // buckets with too many distinct pairs: the device sorts their records (radix sort) and run-length
-        // encodes them; here the sort and the encoding are host code, the index plumbing is the kernels'
+        // buckets left to the side path: the device sorts their records (radix sort) and run-length encodes them;
+        // here the sort and the encoding are host code, the record emission and the index plumbing are the kernels'
         *n_overflow_out = etot[0];
-        std::vector<unsigned long long> side_off = exclusive_scan(ovf_items);
-        std::vector<uint64_t> skeys(etot[1]);
+        std::vector<uint64_t> node_hash(U);
+        for (uint64_t i = 0; i < U; ++i) node_hash[i] = nodes_out[i].hash;
+        int fbits = 1;
+        while (fbits < 28 && (1ull << fbits) < U) ++fbits;
+        std::vector<uint32_t> ftable((1ull << fbits) + 1);
+        cuemu::launch(dim3(2), dim3(256), [&] { bucket_bounds_kernel(node_hash.data(), U, 64 - fbits, 1ull << fbits, ftable.data()); });
+        int rank_bits = 1;
+        while (rank_bits < 32 && (1ull << rank_bits) < U) ++rank_bits;
+        std::vector<unsigned long long> side_off = exclusive_scan(side_rec);
+        std::vector<uint64_t> skeys(etot[1], 0xDDDDDDDDDDDDDDDDull);
         std::vector<uint32_t> sasm(etot[1]);
-        cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
-            overflow_gather_kernel<uint32_t>(ekey.data(), easm.data(), estart.data(), ebucket_d.data(), side_off.data(), skeys.data(), sasm.data());
+        cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] {
+            side_emit_kernel(ea, bucket_e.data(), side_off.data(), grp_base.data(), node_hash.data(), ftable.data(), 64 - fbits, rank_bits,
+                             skeys.data(), sasm.data());
         });
         stable_partition_top_bits(skeys, sasm, 0);
-        cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
-            overflow_count_kernel(skeys.data(), estart.data(), ebucket_d.data(), side_off.data(), ed64.data(), ovf_d64.data());
+        cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] {
+            side_count_kernel(skeys.data(), bucket_e.data(), side_off.data(), e64.data(), ovf_e64.data());
         });
-        ovf_base = exclusive_scan(ovf_d64);
+        ovf_base = exclusive_scan(ovf_e64);
         for (size_t i = 0; i < skeys.size(); ++i) {
             if (i == 0 || skeys[i] != skeys[i - 1]) {
                 sw_edge e;
@@ -162,15 +185,15 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
             }
         }
     }
-    std::vector<unsigned long long> egrp_base = exclusive_scan(ed64);
-    const uint64_t UE = egrp_base[neb];
+    std::vector<unsigned long long> ebase = exclusive_scan(e64);
+    const uint64_t UE = ebase[nb];
     cuemu::launch(dim3(2), dim3(256), [&] {
-        edge_out_kernel(egrp_keys.data(), egrp_cnt.data(), estart.data(), ebucket_d.data(), egrp_base.data(), neb, node_hash.data(),
-                          rank_bits, edges_out);
+        bucket_edges_out_kernel(te_second.data(), te_w.data(), te_r.data(), start.data(), bucket_e.data(), ebase.data(), nb,
+                                grp_keys.data(), edges_out);
     });
     if (etot[0])
-        cuemu::launch(dim3((unsigned)neb), dim3(kNT), [&] {
-            overflow_copy_kernel(side_edges.data(), ebucket_d.data(), egrp_base.data(), ovf_base.data(), edges_out);
+        cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] {
+            overflow_copy_kernel(side_edges.data(), bucket_e.data(), ebase.data(), ovf_base.data(), edges_out);
         });
     *n_edges_out = UE;
     return 0;
