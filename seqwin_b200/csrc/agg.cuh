@@ -518,6 +518,10 @@ struct BucketEdgeSmem {
             uint16_t dslot[kEMax];
         } b;
     } u;
+    // the chunk's records, dense per warp (half of the 2 * EI slots of an item are empty on average)
+    unsigned long long st_sec[kNW][2 * EI * 32];         // second
+    unsigned long long st_ra[kNW][2 * EI * 32];          // node rank << 32 | assembly
+    uint16_t st_slot[kNW][2 * EI * 32];                  // table slot (kES: none)
     uint32_t wsum[kNW];
     uint32_t n_distinct, n_records, bad;
 };
@@ -601,10 +605,16 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
     for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += kNT) sm.u.a.set[s] = kEmptyKey;
     if (tid == 0) sm.n_distinct = sm.n_records = sm.bad = 0;
     __syncthreads();
-    uint32_t my_records = 0;
+    static_assert(Smem::kES < 65536, "slots are staged as 16-bit values");
+    uint32_t my_records = 0;   // of the warp (every lane holds the same count)
+    bool skip = false;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long* st_sec = sm.st_sec[wid];
+    unsigned long long* st_ra = sm.st_ra[wid];
+    uint16_t* st_slot = sm.st_slot[wid];
     for (uint32_t c0 = 0; c0 < n; c0 += Smem::kChunkItems) {
         unsigned long long sec[2 * EI];
-        uint32_t rk[EI], as[EI], sl[2 * EI];
+        uint32_t rk[EI], as[EI];
 #pragma unroll
         for (int q = 0; q < EI; ++q) {   // the chunk's loads are issued before the first is used
             const uint32_t i = c0 + tid + q * kNT;
@@ -614,48 +624,64 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
             rk[q] = have ? (uint32_t)a.item_rank[bs + i] : 0;
             as[q] = have ? a.rec_asm[(uint32_t)(a.vals[bs + i] >> 32) - a.rec_base] : 0;
         }
+        // the warp's records, dense, in its staging area
+        uint32_t cnt = 0;
 #pragma unroll
         for (int e = 0; e < 2 * EI; ++e) {
-            sl[e] = kES;
-            if (sec[e] == 0) continue;
-            ++my_records;
-            if (*(volatile uint32_t*)&sm.n_distinct > a.max_distinct) continue;   // the side path takes the bucket
-            const unsigned long long key = (sec[e] << kRankBits) | rk[e >> 1];
-            if (key == kEmptyKey) {
-                sm.bad = 1;
-                continue;
+            const bool act = sec[e] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const uint32_t at = cnt + (uint32_t)__popc(bal & lt_mask);
+                st_sec[at] = sec[e];
+                st_ra[at] = ((unsigned long long)rk[e >> 1] << 32) | as[e >> 1];
             }
-            bool inserted;
-            const uint32_t s = upsert_t<ESB>(sm.t_key, key, &inserted);
-            if (s == kES) {
-                atomicAdd(&sm.n_distinct, kES);
-                continue;
+            cnt += (uint32_t)__popc(bal);
+        }
+        my_records += cnt;
+        if (skip) continue;   // uniform: the bucket already belongs to the side path, which needs the record count
+        __syncwarp();
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool act = j < cnt;
+            const uint32_t mask = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const unsigned long long second = st_sec[j], ra = st_ra[j];
+                const unsigned long long key = (second << kRankBits) | (ra >> 32);
+                uint32_t s = kES;
+                bool inserted = false;
+                if (key != kEmptyKey) s = upsert_t<ESB>(sm.t_key, key, &inserted);
+                if (inserted) {
+                    sm.t_hi[s] = (uint16_t)(second >> (64 - kRankBits));
+                    const uint32_t at = atomicAdd(&sm.n_distinct, 1u);
+                    if (at < (uint32_t)Smem::kEMax) sm.dlist[at] = (uint16_t)s;
+                }
+                __syncwarp(mask);
+                if (s != kES) {
+                    bool fresh = set_insert_t<Smem::kSetSlots>(sm.u.a.set, ((unsigned long long)s << 32) | (uint32_t)ra);
+                    if (fresh && multi) fresh = (uint32_t)ra + 1u > sm.u.a.t_last[s];
+                    if (fresh) atomicAdd(&sm.t_w[s], 1u);
+                } else {
+                    sm.bad = 1;   // the empty marker as a key, or a full table
+                }
+                st_slot[j] = (uint16_t)s;
+                __syncwarp(mask);
             }
-            if (inserted) {
-                sm.t_hi[s] = (uint16_t)(sec[e] >> (64 - kRankBits));
-                const uint32_t at = atomicAdd(&sm.n_distinct, 1u);
-                if (at < (uint32_t)Smem::kEMax) sm.dlist[at] = (uint16_t)s;
-            }
-            sl[e] = s;
-            bool fresh = set_insert_t<Smem::kSetSlots>(sm.u.a.set, ((unsigned long long)s << 32) | as[e >> 1]);
-            if (fresh && multi) fresh = as[e >> 1] + 1u > sm.u.a.t_last[s];
-            if (fresh) atomicAdd(&sm.t_w[s], 1u);
         }
         __syncthreads();
         // the bits of `second` the key leaves out: the slot's first record wrote them, everybody checks
-#pragma unroll
-        for (int e = 0; e < 2 * EI; ++e)
-            if (sl[e] != kES && sm.t_hi[sl[e]] != (uint16_t)(sec[e] >> (64 - kRankBits))) sm.bad = 1;
-        if (c0 + (uint32_t)Smem::kChunkItems < n) {   // uniform: another chunk follows
-#pragma unroll
-            for (int e = 0; e < 2 * EI; ++e)
-                if (sl[e] != kES) atomicMax(&sm.u.a.t_last[sl[e]], as[e >> 1] + 1u);
+        const bool more = c0 + (uint32_t)Smem::kChunkItems < n;   // uniform: another chunk follows
+        for (uint32_t j = lane; j < cnt; j += 32) {
+            const uint32_t s = st_slot[j];
+            if (s == kES) continue;
+            if (sm.t_hi[s] != (uint16_t)(st_sec[j] >> (64 - kRankBits))) sm.bad = 1;
+            if (more) atomicMax(&sm.u.a.t_last[s], (uint32_t)st_ra[j] + 1u);
+        }
+        if (sm.n_distinct > a.max_distinct) skip = true;   // uniform (read between the barriers)
+        if (more) {
             for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += kNT) sm.u.a.set[s] = kEmptyKey;
             __syncthreads();
         }
     }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) my_records += __shfl_xor_sync(0xffffffffu, my_records, d);
     if (lane == 0 && my_records) atomicAdd(&sm.n_records, my_records);
     __syncthreads();
     const uint32_t D = sm.n_distinct;

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <vector>
 
 #define __global__
@@ -50,10 +51,14 @@ struct WarpCtx {
     unsigned gen = 0;
     unsigned long long val[32];
 };
+// one context per member mask: lanes outside a partial-mask collective may meanwhile wait in another one
+struct WarpSet {
+    std::map<unsigned, WarpCtx> by_mask;
+};
 
 struct State {
     std::vector<Fiber> fibers;
-    std::vector<WarpCtx> warps;
+    std::vector<WarpSet> warps;
     ucontext_t main_ctx;
     int cur = 0, n_threads = 0, n_done = 0;
     unsigned bar_arrived = 0, bar_gen = 0;
@@ -125,7 +130,7 @@ void launch(dim3 grid, dim3 block, F&& kernel)
         s.n_done = 0;
         s.bar_arrived = 0;
         s.fibers.resize(nt);
-        s.warps.assign(nt / 32, WarpCtx());
+        s.warps.assign(nt / 32, WarpSet());
         for (int t = 0; t < nt; ++t) {
             Fiber& f = s.fibers[t];
             f.done = false;
@@ -158,17 +163,22 @@ inline void block_barrier()
     }
 }
 
-// All 32 lanes of the calling warp exchange a 64-bit value; returns the warp's context with val[] filled.
+// The lanes of `mask` of the calling warp exchange a 64-bit value; returns the context with val[] filled.
 // Two phases so that a lane racing ahead into the next collective cannot overwrite values still being read.
-inline WarpCtx& warp_exchange(unsigned long long v)
+inline WarpCtx& warp_exchange(unsigned mask, unsigned long long v)
 {
     State& s = st();
-    WarpCtx& w = s.warps[threadIdx.x >> 5];
+    WarpCtx& w = s.warps[threadIdx.x >> 5].by_mask[mask];
     const unsigned lane = threadIdx.x & 31;
+    const unsigned expect = (unsigned)__builtin_popcount(mask);
+    if (!((mask >> lane) & 1u)) {
+        fprintf(stderr, "cuemu: lane %u calls a collective whose mask %08x excludes it\n", lane, mask);
+        abort();
+    }
     // phase 1: publish
     unsigned gen = w.gen;
     w.val[lane] = v;
-    if (++w.arrived == 32) {
+    if (++w.arrived == expect) {
         w.arrived = 0;
         ++w.gen;
     } else {
@@ -176,12 +186,13 @@ inline WarpCtx& warp_exchange(unsigned long long v)
     }
     return w;
 }
-inline void warp_release()
+inline void warp_release(unsigned mask)
 {
     State& s = st();
-    WarpCtx& w = s.warps[threadIdx.x >> 5];
+    WarpCtx& w = s.warps[threadIdx.x >> 5].by_mask[mask];
+    const unsigned expect = (unsigned)__builtin_popcount(mask);
     const unsigned gen = w.gen;
-    if (++w.arrived == 32) {
+    if (++w.arrived == expect) {
         w.arrived = 0;
         ++w.gen;
     } else {
@@ -192,10 +203,10 @@ inline void warp_release()
 }  // namespace cuemu
 
 inline void __syncthreads() { cuemu::block_barrier(); }
-inline void __syncwarp(unsigned = 0xffffffffu)
+inline void __syncwarp(unsigned mask = 0xffffffffu)
 {
-    cuemu::warp_exchange(0);
-    cuemu::warp_release();
+    cuemu::warp_exchange(mask, 0);
+    cuemu::warp_release(mask);
 }
 inline int __syncthreads_or(int pred)
 {
@@ -209,22 +220,23 @@ inline int __syncthreads_or(int pred)
     return r;
 }
 
-inline unsigned __ballot_sync(unsigned, int pred)
+inline unsigned __ballot_sync(unsigned mask, int pred)
 {
-    cuemu::WarpCtx& w = cuemu::warp_exchange(pred ? 1 : 0);
+    cuemu::WarpCtx& w = cuemu::warp_exchange(mask, pred ? 1 : 0);
     unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m |= (w.val[i] ? 1u : 0u) << i;
-    cuemu::warp_release();
+    for (int i = 0; i < 32; ++i)
+        if ((mask >> i) & 1u) m |= (w.val[i] ? 1u : 0u) << i;
+    cuemu::warp_release(mask);
     return m;
 }
 template <typename T>
-inline T __shfl_sync(unsigned, T v, int src)
+inline T __shfl_sync(unsigned mask, T v, int src)
 {
     unsigned long long raw = 0;
     memcpy(&raw, &v, sizeof(T));
-    cuemu::WarpCtx& w = cuemu::warp_exchange(raw);
+    cuemu::WarpCtx& w = cuemu::warp_exchange(mask, raw);
     const unsigned long long r = w.val[src & 31];
-    cuemu::warp_release();
+    cuemu::warp_release(mask);
     T out;
     memcpy(&out, &r, sizeof(T));
     return out;
@@ -250,14 +262,15 @@ inline T __shfl_xor_sync(unsigned m, T v, int x)
     return __shfl_sync(m, v, lane ^ x);
 }
 template <typename T>
-inline unsigned __match_any_sync(unsigned, T v)
+inline unsigned __match_any_sync(unsigned mask, T v)
 {
     unsigned long long raw = 0;
     memcpy(&raw, &v, sizeof(T));
-    cuemu::WarpCtx& w = cuemu::warp_exchange(raw);
+    cuemu::WarpCtx& w = cuemu::warp_exchange(mask, raw);
     unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m |= (w.val[i] == raw ? 1u : 0u) << i;
-    cuemu::warp_release();
+    for (int i = 0; i < 32; ++i)
+        if ((mask >> i) & 1u) m |= (w.val[i] == raw ? 1u : 0u) << i;
+    cuemu::warp_release(mask);
     return m;
 }
 
