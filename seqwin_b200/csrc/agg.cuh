@@ -612,18 +612,32 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
     unsigned long long* st_sec = sm.st_sec[wid];
     unsigned long long* st_ra = sm.st_ra[wid];
     uint16_t* st_slot = sm.st_slot[wid];
+    // the items of a chunk are loaded while the chunk before is being grouped (the assembly is a dependent load)
+    unsigned long long nsec[2 * EI];
+    uint32_t nrk[EI], nas[EI];
+    auto load_chunk = [&](uint32_t c0) {
+#pragma unroll
+        for (int q = 0; q < EI; ++q) {
+            const uint32_t i = c0 + tid + q * kNT;
+            const bool have = i < n;
+            nsec[2 * q] = have ? a.nb_prev[bs + i] : 0;
+            nsec[2 * q + 1] = have ? a.nb_next[bs + i] : 0;
+            nrk[q] = have ? (uint32_t)a.item_rank[bs + i] : 0;
+            nas[q] = have ? a.rec_asm[(uint32_t)(a.vals[bs + i] >> 32) - a.rec_base] : 0;
+        }
+    };
+    load_chunk(0);
     for (uint32_t c0 = 0; c0 < n; c0 += Smem::kChunkItems) {
         unsigned long long sec[2 * EI];
         uint32_t rk[EI], as[EI];
 #pragma unroll
-        for (int q = 0; q < EI; ++q) {   // the chunk's loads are issued before the first is used
-            const uint32_t i = c0 + tid + q * kNT;
-            const bool have = i < n;
-            sec[2 * q] = have ? a.nb_prev[bs + i] : 0;
-            sec[2 * q + 1] = have ? a.nb_next[bs + i] : 0;
-            rk[q] = have ? (uint32_t)a.item_rank[bs + i] : 0;
-            as[q] = have ? a.rec_asm[(uint32_t)(a.vals[bs + i] >> 32) - a.rec_base] : 0;
+        for (int q = 0; q < EI; ++q) {
+            sec[2 * q] = nsec[2 * q];
+            sec[2 * q + 1] = nsec[2 * q + 1];
+            rk[q] = nrk[q];
+            as[q] = nas[q];
         }
+        if (c0 + (uint32_t)Smem::kChunkItems < n) load_chunk(c0 + Smem::kChunkItems);
         // the warp's records, dense, in its staging area
         uint32_t cnt = 0;
 #pragma unroll

@@ -111,6 +111,7 @@ struct SketchStream {
     uint32_t launches = 0;
     float kernel_ms = 0, reorder_ms = 0;  // CUDA-event times of the last run
     double items_per_key = 0;             // minimizers per distinct hash, estimated from a hash-range sample (0: unknown)
+    double pairs_per_edge = 0;            // adjacent pairs per distinct pair, same kind of estimate (0: unknown)
 };
 
 int sketch_pick_config(uint32_t w, uint32_t* tk_out, bool* sparse_out);

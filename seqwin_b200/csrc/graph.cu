@@ -581,8 +581,25 @@ double estimate_items_per_key(const uint64_t* keys, uint64_t n, unsigned long lo
 // edges those nodes own, in shared memory.  Returns false -- nothing of `g` touched -- if a bucket holds more
 // distinct hashes than its table takes (not expected: the bucket count follows the item count and h1 is a 64-bit
 // mix) or a hash is 0 (the "no neighbour" marker); the caller then runs the sort-based path.
-constexpr int kEdgeSlotBits = 11, kEdgeItems = 2;
-using EdgeSmem = agg::BucketEdgeSmem<kEdgeSlotBits, kEdgeItems>;
+// table geometry of the edge kernel: (slot bits, items per thread and chunk); SEQWIN_AGG_EDGE_GEOM picks one
+struct EdgeGeom {
+    int slot_bits, items;
+    uint32_t e_max;
+    size_t smem;
+    void (*kernel)(const agg::BucketEdgeArgs);
+};
+template <int ESB, int EI>
+EdgeGeom edge_geom()
+{
+    return EdgeGeom{ESB, EI, (uint32_t)agg::BucketEdgeSmem<ESB, EI>::kEMax, sizeof(agg::BucketEdgeSmem<ESB, EI>),
+                    agg::bucket_edges_kernel<ESB, EI>};
+}
+const EdgeGeom& pick_edge_geom()
+{
+    static const EdgeGeom geoms[] = {edge_geom<11, 2>(), edge_geom<12, 2>(), edge_geom<12, 4>(), edge_geom<11, 1>()};
+    const uint32_t i = env_u32("SEQWIN_AGG_EDGE_GEOM", 1) - 1;
+    return geoms[i < 4 ? i : 0];
+}
 
 __global__ void node_hash_gather_kernel(const sw_node* __restrict__ nodes, uint64_t n, uint64_t* __restrict__ out)
 {
@@ -613,10 +630,18 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
         tm.launches += 1;
     }
+    // ... and few enough distinct pairs for the edge kernel's table: a bucket owns the pairs whose smaller hash falls into
+    // it, so the low buckets hold twice the average; a stream from elsewhere is assumed to hold no pair twice
+    const EdgeGeom& eg = pick_edge_geom();
+    const double per_edge = st.pairs_per_edge > 0 ? st.pairs_per_edge : 1.0;
     const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
-    const int P = fixed_nb ? partition_bits(M, fixed_nb)
-                           : partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 300),
-                                                env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
+    int P = fixed_nb ? partition_bits(M, fixed_nb)
+                     : partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 300),
+                                          env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
+    if (!fixed_nb) {
+        const double edge_target = (double)env_u32("SEQWIN_AGG_EDGE_TARGET", eg.e_max * 2 / 3);
+        while (P < 40 && 2.0 * ((double)M / per_edge) / (double)(1ull << P) > edge_target) ++P;
+    }
     const int key_bits = 64 - P;
     const uint64_t n_buckets = 1ull << P;
     DevBuf<unsigned long long> tot(4, s, true);   // [0] overflowing node buckets [1] their items [2] nodes; [3] low word: a key is 0
@@ -686,15 +711,14 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     ea.start = start.p;
     ea.rec_asm = d_rec_asm;
     ea.rec_base = rec_base;
-    ea.max_distinct = std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", EdgeSmem::kEMax), EdgeSmem::kEMax);
+    ea.max_distinct = std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", eg.e_max), eg.e_max);
     ea.te_second = Dd.prev;                                   // 2 M words: Dd.prev | Dd.next
     ea.te_w = reinterpret_cast<uint32_t*>(Dd.vals);           // 2 M u32
     ea.te_r = reinterpret_cast<uint16_t*>(R->keys);           // 2 M u16
     ea.bucket_e = bucket_e.p;
     ea.bucket_rec = bucket_rec.p;
-    SW_CUDA(cudaFuncSetAttribute(bucket_edges_kernel<kEdgeSlotBits, kEdgeItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(EdgeSmem)));
-    bucket_edges_kernel<kEdgeSlotBits, kEdgeItems><<<(uint32_t)n_buckets, kNT, sizeof(EdgeSmem), s>>>(ea);
+    SW_CUDA(cudaFuncSetAttribute(eg.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg.smem));
+    eg.kernel<<<(uint32_t)n_buckets, kNT, eg.smem, s>>>(ea);
     SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
     SW_CUDA(cudaMemsetAsync(e64.p + n_buckets, 0, sizeof(unsigned long long), s));
     SW_CUDA(cudaMemsetAsync(side_rec.p + n_buckets, 0, sizeof(unsigned long long), s));
@@ -709,8 +733,8 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     unsigned long long n_edges = etot_p[2];
     const unsigned long long n_ovf = etot_p[0], n_side = etot_p[1];
     if (getenv("SEQWIN_DEBUG_AGG"))
-        fprintf(stderr, "[agg] M %llu (%.2f per node) P %d nodes %llu edges %llu, %llu buckets (%llu records) to the sort path\n",
-                (unsigned long long)M, per_node, P, n_nodes, n_edges, n_ovf, n_side);
+        fprintf(stderr, "[agg] M %llu (%.2f per node, %.2f pairs per edge) P %d nodes %llu edges %llu, %llu buckets (%llu records) to the sort path\n",
+                (unsigned long long)M, per_node, per_edge, P, n_nodes, n_edges, n_ovf, n_side);
     DevBuf<sw_edge> side_edges;
     DevBuf<unsigned long long> ovf_e64;
     if (n_ovf) {

@@ -266,6 +266,12 @@ __global__ void __launch_bounds__(256) reorder_kernel(const uint64_t* __restrict
             const uint64_t key = ukey[src + i];
             okey[dst + i] = key;
             agg::distinct_sample_item(key, sbits, sample_set, sample_out);   // k-mers per distinct hash: sizes the node buckets
+            if (i + 1 < n) {
+                // adjacent pairs per distinct pair (those inside a tile will do): the edges a bucket has to expect
+                const uint64_t nxt = ukey[src + i + 1];
+                const uint64_t lo = key < nxt ? key : nxt, hi = key < nxt ? nxt : key;
+                agg::distinct_sample_item(agg::mix64(lo) + hi, sbits, sample_set + (1ull << agg::kSampleSetBits), sample_out + 2);
+            }
             oval[dst + i] = uval[src + i];
         }
     }
@@ -463,6 +469,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     out.n = 0;
     out.launches = 0;
     out.items_per_key = 0;
+    out.pairs_per_edge = 0;
     if (plan.n_tiles == 0) {
         out.keys.alloc(0, s, true);
         out.vals.alloc(0, s, true);
@@ -506,7 +513,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     capacity = std::min<uint64_t>(capacity, plan.n_windows);
     // The ordered stream is allocated first, with the capacity of the unordered one, so that the unordered
     // buffers (dead after the reorder) sit on top of the scratch arena and can be handed back.
-    DevBuf<unsigned long long> sample_set(1ull << agg::kSampleSetBits, s, true), sample_out(2, s, true);
+    DevBuf<unsigned long long> sample_set(2ull << agg::kSampleSetBits, s, true), sample_out(4, s, true);   // hashes | pairs
     DevBuf<uint64_t> ukeys, uvals;
     const ArenaMark stream_mark = arena_mark();
     ArenaMark unordered_mark = stream_mark;
@@ -603,7 +610,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     SW_CUDA(cudaMemsetAsync(sample_out.p, 0, sample_out.bytes(), s));
     reorder_kernel<<<rgrid, 256, 0, s>>>(ukeys.p, uvals.p, tile_info.p, tile_info.p + plan.n_tiles, plan.n_tiles,
                                          total, out.keys.p, out.vals.p, agg::sample_bits(total), sample_set.p, sample_out.p);
-    const unsigned long long* sample_h = readback_u64(sample_out.p, 2, s);
+    const unsigned long long* sample_h = readback_u64(sample_out.p, 4, s);
     cudaEventRecord(ev[3], s);
     SW_CUDA(cudaGetLastError());
     out.launches += 2;
@@ -611,6 +618,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     cudaEventElapsedTime(&out.reorder_ms, ev[2], ev[3]);
     SW_CUDA(cudaStreamSynchronize(s));   // the readback kernel follows the event
     out.items_per_key = sample_h[1] ? (double)sample_h[0] / (double)sample_h[1] : 1.0;
+    out.pairs_per_edge = sample_h[3] ? (double)sample_h[2] / (double)sample_h[3] : 1.0;
     arena_release(unordered_mark);   // the reorder has finished: the unordered buffers go back to the arena
 }
 
