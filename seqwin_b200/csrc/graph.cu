@@ -594,11 +594,36 @@ EdgeGeom edge_geom()
     return EdgeGeom{ESB, EI, (uint32_t)agg::BucketEdgeSmem<ESB, EI>::kEMax, sizeof(agg::BucketEdgeSmem<ESB, EI>),
                     agg::bucket_edges_kernel<ESB, EI>};
 }
-const EdgeGeom& pick_edge_geom()
+const EdgeGeom& edge_geom_at(uint32_t i)
 {
-    static const EdgeGeom geoms[] = {edge_geom<11, 2>(), edge_geom<12, 2>(), edge_geom<12, 4>(), edge_geom<11, 1>()};
-    const uint32_t i = env_u32("SEQWIN_AGG_EDGE_GEOM", 1) - 1;
-    return geoms[i < 4 ? i : 0];
+    static const EdgeGeom geoms[] = {edge_geom<11, 2>(), edge_geom<12, 2>()};
+    return geoms[i < 2 ? i : 0];
+}
+
+// Bucket bits and edge-table geometry.  A bucket must hold few enough distinct hashes for the node table (about
+// `node_target` on average) and few enough distinct pairs for the edge table: a bucket owns the pairs whose smaller
+// hash falls into it, so the low buckets hold twice the average, and the fill aimed at is half the table's limit.
+// The small table is the faster one; the large one is taken when it saves a whole radix pass (8 bucket bits).
+int choose_bucket_bits(uint64_t M, double per_node, double per_edge, const EdgeGeom** geom)
+{
+    const int p_nodes = agg::partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 300),
+                                                env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
+    const double pairs = (double)M / (per_edge < 1.0 ? 1.0 : per_edge);
+    auto bits_for = [&](const EdgeGeom& g) {
+        const double target = (double)env_u32("SEQWIN_AGG_EDGE_TARGET", g.e_max / 2);
+        int p = p_nodes;
+        while (p < 40 && 2.0 * pairs / (double)(1ull << p) > target) ++p;
+        return p;
+    };
+    const uint32_t forced = env_u32("SEQWIN_AGG_EDGE_GEOM", 0);
+    if (forced) {
+        *geom = &edge_geom_at(forced - 1);
+        return bits_for(**geom);
+    }
+    const int p_small = bits_for(edge_geom_at(0)), p_large = bits_for(edge_geom_at(1));
+    const bool large = (p_large + 7) / 8 < (p_small + 7) / 8;
+    *geom = &edge_geom_at(large ? 1 : 0);
+    return large ? p_large : p_small;
 }
 
 __global__ void node_hash_gather_kernel(const sw_node* __restrict__ nodes, uint64_t n, uint64_t* __restrict__ out)
@@ -630,18 +655,12 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
         tm.launches += 1;
     }
-    // ... and few enough distinct pairs for the edge kernel's table: a bucket owns the pairs whose smaller hash falls into
-    // it, so the low buckets hold twice the average; a stream from elsewhere is assumed to hold no pair twice
-    const EdgeGeom& eg = pick_edge_geom();
-    const double per_edge = st.pairs_per_edge > 0 ? st.pairs_per_edge : 1.0;
+    const double per_edge = st.pairs_per_edge > 0 ? st.pairs_per_edge : 1.0;   // a stream from elsewhere: no pair assumed twice
+    const EdgeGeom* egp = nullptr;
     const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
-    int P = fixed_nb ? partition_bits(M, fixed_nb)
-                     : partition_bits_for(M, per_node, (double)env_u32("SEQWIN_AGG_NODE_TARGET", 300),
-                                          env_u32("SEQWIN_AGG_MAX_ITEMS", 4096));
-    if (!fixed_nb) {
-        const double edge_target = (double)env_u32("SEQWIN_AGG_EDGE_TARGET", eg.e_max * 2 / 3);
-        while (P < 40 && 2.0 * ((double)M / per_edge) / (double)(1ull << P) > edge_target) ++P;
-    }
+    int P = choose_bucket_bits(M, per_node, per_edge, &egp);
+    if (fixed_nb) P = partition_bits(M, fixed_nb);
+    const EdgeGeom& eg = *egp;
     const int key_bits = 64 - P;
     const uint64_t n_buckets = 1ull << P;
     DevBuf<unsigned long long> tot(4, s, true);   // [0] overflowing node buckets [1] their items [2] nodes; [3] low word: a key is 0
