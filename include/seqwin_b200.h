@@ -212,6 +212,16 @@ int sw_graph_count_sums(sw_graph* g, uint64_t sums[3]);
  * out[3] = bytes in use on the device right now (all processes). */
 int sw_mem_stats(uint64_t out[4]);
 
+/* The reduced-footprint plan for the device-resident entry points (sw_dev_build*, sw_build_from_batch*), per host
+ * thread: what sw_build's low_memory argument selects (cpp/src/seqwin/build.cpp:264-325).  The aggregation runs
+ * over hash slices of the minimizer stream, one after the other (csrc/graph.cu): identical output, the scratch a
+ * fraction of the single-pass plan's.  The same plan is taken without being asked for when the single pass would
+ * not fit into the free device memory. */
+int sw_set_low_memory(int on);
+/* Hand the calling thread's scratch arena and the unused part of the stream-ordered pool back to the driver
+ * (the arena otherwise stays at its high-water mark between builds). */
+int sw_trim_memory(void);
+
 /* Measured peak of the INT32 ALU pipe, the roofline that bounds the sketch kernels: lane-operations per
  * second of dependent-chain LOP3, SHF, IADD and of their 1:1:1 mix (CUDA-event timed, ~10 ms). */
 int sw_measure_int_peak(double lane_ops_per_s[4]);

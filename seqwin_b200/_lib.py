@@ -65,6 +65,8 @@ PROTOTYPES = {
     "sw_dist_merge_edges": (_I, [_P, _P, _P, _U32, C.POINTER(_U32)]),
     "sw_graph_count_sums": (_I, [_P, _P]),
     "sw_mem_stats": (_I, [C.POINTER(C.c_uint64)]),
+    "sw_set_low_memory": (_I, [_I]),
+    "sw_trim_memory": (_I, []),
     "sw_measure_int_peak": (_I, [C.POINTER(C.c_double)]),
     "sw_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ)]),
 }

@@ -66,15 +66,16 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint64_t* __re
 
 // The same bounds by binary search, one thread per bucket: cheaper than the scan above when a bucket holds many
 // items (the keys only need to be partitioned on key >> shift, not sorted).
+// bucket0: the keys belong to one hash slice of a sliced build, whose first bucket has this (global) number.
 __global__ void __launch_bounds__(256) bucket_search_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift,
-                                                            uint64_t n_buckets, uint32_t* __restrict__ start)
+                                                            uint64_t n_buckets, uint32_t* __restrict__ start, uint64_t bucket0 = 0)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += stride) {
         uint64_t lo = 0, hi = n;
         while (lo < hi) {
             const uint64_t mid = (lo + hi) >> 1;
-            if ((keys[mid] >> shift) < b) lo = mid + 1; else hi = mid;
+            if ((keys[mid] >> shift) < bucket0 + b) lo = mid + 1; else hi = mid;
         }
         start[b] = (uint32_t)lo;
     }
@@ -142,7 +143,7 @@ __device__ __forceinline__ uint32_t table_upsert(unsigned long long* t_key, unsi
 __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ start,
                                                           int key_bits, uint32_t max_distinct, uint64_t* __restrict__ grp_keys,
                                                           uint32_t* __restrict__ grp_cnt, uint32_t* __restrict__ bucket_d,
-                                                          uint16_t* __restrict__ item_rank)
+                                                          uint16_t* __restrict__ item_rank, uint64_t bucket0 = 0)
 {
     __shared__ unsigned long long t_key[kSlots];
     __shared__ uint32_t t_cnt[kSlots];              // items per slot; afterwards: rank of the slot's key
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kNT) group_count_kernel(const uint64_t* __rest
         }
     }
     __syncthreads();
-    const uint64_t prefix = (uint64_t)b << key_bits;
+    const uint64_t prefix = (bucket0 + b) << key_bits;
     for (uint32_t i = tid; i < D; i += kNT) {
         const unsigned long long k = dk[i];
         const uint32_t sb = (uint32_t)(k >> sshift) & 255u;
@@ -287,6 +288,7 @@ struct NodeOut {
     const uint8_t* is_target;                       // [assemblies]                      (scoring only)
     double inv_t, inv_n;
     int counts_only;                                // a shard of a multi-GPU build: penalty left at 0
+    uint64_t kmer_base;                             // sliced build: k-mers placed by earlier slices (nodes[].start / stop are global)
 };
 
 struct PlaceArgs {
@@ -316,8 +318,8 @@ __device__ __forceinline__ void write_group(const NodeOut& no, unsigned long lon
 {
     sw_node nd;
     nd.hash = key;
-    nd.start = start;
-    nd.stop = stop;
+    nd.start = start + no.kmer_base;
+    nd.stop = stop + no.kmer_base;
     nd.n_tar = ca;
     nd.n_neg = cb;
     nd.penalty = 0.0;
@@ -793,18 +795,10 @@ __global__ void __launch_bounds__(256) bucket_edges_out_kernel(const uint64_t* _
 }
 
 // ---- buckets left to the sort-based path (hub nodes, or a clash of the checked key bits) ----------------------------
-// Their records become (rank pair, assembly) records -- global node ranks, `second` looked up through a bucket
-// table over the sorted node hashes -- which radix.cu sorts and graph.cu run-length encodes as the sort-based path
-// does for everything; the finished edges are copied to their place among the others.
-
-// rank of hash h among the sorted node hashes: ftable[h >> fshift] = first node of that fine bucket
-__device__ __forceinline__ uint32_t rank_of_hash(uint64_t h, const uint64_t* __restrict__ node_hash,
-                                                 const uint32_t* __restrict__ ftable, int fshift)
-{
-    uint32_t i = ftable[h >> fshift];
-    while (node_hash[i] != h) ++i;
-    return i;
-}
+// Their records (global index of the owning node, second hash, assembly) are written out in bucket order, sorted
+// by (node, second) with two stable radix sorts (radix.cu) and run-length encoded (side_final_kernel); the
+// finished edges are copied to their place among the others.  Like the bucket kernel this needs no rank of
+// `second`, so it also works when the node that hash belongs to has not been built yet (sliced builds).
 
 // per-bucket 64-bit counts for the scans: distinct pairs of the buckets grouped above (0 for the others), the
 // record counts of the others; tot[0] += such buckets, tot[1] += their records
@@ -825,12 +819,12 @@ __global__ void __launch_bounds__(256) bucket_edge_counts_kernel(const uint32_t*
 }
 
 // the records of those buckets in bucket order (side_off = exclusive scan of their record counts): items in
-// stream order, so the assemblies of one pair never decrease, which the run-length encoding relies on
+// stream order, so the assemblies of one pair never decrease, which the run-length encoding relies on.
+// node_base[b] = index of the bucket's first node among the nodes of this build (slice).
 __global__ void __launch_bounds__(kNT) side_emit_kernel(const BucketEdgeArgs a, const uint32_t* __restrict__ bucket_e,
                                                         const unsigned long long* __restrict__ side_off,
                                                         const unsigned long long* __restrict__ node_base,
-                                                        const uint64_t* __restrict__ node_hash, const uint32_t* __restrict__ ftable,
-                                                        int fshift, int rank_bits, uint64_t* __restrict__ side_keys,
+                                                        uint32_t* __restrict__ side_node, uint64_t* __restrict__ side_second,
                                                         uint32_t* __restrict__ side_asm)
 {
     __shared__ uint32_t s_warp[kNW];
@@ -867,43 +861,78 @@ __global__ void __launch_bounds__(kNT) side_emit_kernel(const BucketEdgeArgs a, 
         }
         __syncthreads();
         unsigned long long slot = running + before;
-        const uint64_t u = nbase + r;   // first <= second in hash order, hence in rank order
         if (sp) {
-            const uint64_t v = rank_of_hash(sp, node_hash, ftable, fshift);
-            side_keys[slot] = (u << (64 - rank_bits)) | (v << (64 - 2 * rank_bits));
+            side_node[slot] = (uint32_t)(nbase + r);
+            side_second[slot] = sp;
             side_asm[slot] = as;
             ++slot;
         }
         if (sn) {
-            const uint64_t v = rank_of_hash(sn, node_hash, ftable, fshift);
-            side_keys[slot] = (u << (64 - rank_bits)) | (v << (64 - 2 * rank_bits));
+            side_node[slot] = (uint32_t)(nbase + r);
+            side_second[slot] = sn;
             side_asm[slot] = as;
         }
         running += total;
     }
 }
 
-// distinct pairs (runs of the sorted side array) of every such bucket: its records are [side_off[b], side_off[b + 1])
-__global__ void __launch_bounds__(kNT) side_count_kernel(const uint64_t* __restrict__ side_keys, const uint32_t* __restrict__ bucket_e,
-                                                         const unsigned long long* __restrict__ side_off,
+// gather for the second of the two sorts: key2[j] = node of the record that the first sort (by `second`) put at j
+__global__ void __launch_bounds__(256) side_gather_node_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ side_node,
+                                                               uint64_t n, uint64_t* __restrict__ key2)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) key2[j] = side_node[perm[j]];
+}
+
+// Run-length encode the records in (node, second) order (perm = the order after both sorts).
+// Pass 1 (scanned == nullptr): flags[j] = (record starts a new pair) | (new pair or new assembly) << 32, so that one
+// exclusive scan numbers the pairs (low word) -- the high word is not needed afterwards.
+// Pass 2: a run start writes its edge (the host zeroed the weights), every record that shows a new assembly
+// adds one to the weight of its pair.
+__global__ void __launch_bounds__(256) side_final_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ side_node,
+                                                         const uint64_t* __restrict__ side_second, const uint32_t* __restrict__ side_asm,
+                                                         uint64_t n, unsigned long long* __restrict__ flags,
+                                                         const unsigned long long* __restrict__ scanned, const sw_node* __restrict__ nodes,
+                                                         sw_edge* __restrict__ side_edges)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint32_t i = perm[j];
+        const uint32_t nd = side_node[i];
+        const uint64_t sec = side_second[i];
+        bool first = j == 0, fresh = j == 0;
+        if (!first) {
+            const uint32_t ip = perm[j - 1];
+            first = side_node[ip] != nd || side_second[ip] != sec;
+            fresh = first || side_asm[ip] != side_asm[i];
+        }
+        if (!scanned) {
+            flags[j] = (first ? 1ull : 0ull) | (fresh ? 1ull << 32 : 0ull);
+            continue;
+        }
+        const unsigned long long pair = (scanned[j] & 0xFFFFFFFFull) + (first ? 1u : 0u) - 1u;
+        if (first) {
+            side_edges[pair].first = nodes[nd].hash;
+            side_edges[pair].second = sec;
+        }
+        if (fresh) atomicAdd(reinterpret_cast<unsigned long long*>(&side_edges[pair].weight), 1ull);
+    }
+}
+
+// distinct pairs of every such bucket: its records are [side_off[b], side_off[b + 1]) of the sorted order, whose
+// flags have been scanned (scanned[n] = totals)
+__global__ void __launch_bounds__(256) side_count_kernel(const uint32_t* __restrict__ bucket_e, const unsigned long long* __restrict__ side_off,
+                                                         const unsigned long long* __restrict__ scanned, uint64_t n_buckets,
                                                          unsigned long long* __restrict__ e64, unsigned long long* __restrict__ ovf_e64)
 {
-    __shared__ unsigned long long s_sum;
-    const uint32_t b = blockIdx.x;
-    if (bucket_e[b] != kOverflow) {
-        if (threadIdx.x == 0) ovf_e64[b] = 0;
-        return;
-    }
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
-    const unsigned long long so = side_off[b], n = side_off[b + 1] - so;
-    unsigned long long c = 0;
-    for (unsigned long long i = threadIdx.x; i < n; i += kNT) c += (i == 0 || side_keys[so + i] != side_keys[so + i - 1]) ? 1u : 0u;
-    if (c) atomicAdd(&s_sum, c);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        e64[b] = s_sum;
-        ovf_e64[b] = s_sum;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += stride) {
+        unsigned long long c = 0;
+        if (bucket_e[b] == kOverflow) {
+            c = (scanned[side_off[b + 1]] & 0xFFFFFFFFull) - (scanned[side_off[b]] & 0xFFFFFFFFull);
+            e64[b] = c;
+        }
+        ovf_e64[b] = c;
     }
 }
 

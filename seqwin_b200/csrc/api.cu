@@ -140,8 +140,25 @@ struct Arena {
         off += bytes;
         return r;
     }
+    void trim()
+    {
+        for (auto& sl : slabs) cudaFree(sl.p);
+        slabs.clear();
+        cur = 0;
+        off = 0;
+    }
     void reset()
     {
+        size_t held = 0;
+        for (auto& sl : slabs) held += sl.bytes;
+        size_t free_b = 0, total_b = 0;
+        if (held && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && held > total_b / 4) {
+            // a build that needed a large part of the device: the next one may be shaped differently (outputs come
+            // from the stream-ordered pool), so the slabs go back to the driver instead of staying reserved
+            cudaDeviceSynchronize();
+            trim();
+            return;
+        }
         if (slabs.size() > 1) {  // grew during the last build: come back as one slab next time
             size_t total = 0;
             for (auto& sl : slabs) { total += sl.bytes; cudaFree(sl.p); }
@@ -221,11 +238,24 @@ void arena_release(const ArenaMark& m)
     tls_arena().cur = m.slab;
     tls_arena().off = m.off;
 }
+size_t arena_free_bytes()
+{
+    const Arena& a = tls_arena();
+    size_t t = 0;
+    for (size_t i = a.cur; i < a.slabs.size(); ++i) t += a.slabs[i].bytes - (i == a.cur ? a.off : 0);
+    return t;
+}
 void arena_reset()
 {
     tls_arena().reset();
     tls_readback().release_retired();
 }
+void arena_trim() { tls_arena().trim(); }
+namespace {
+thread_local bool g_low_memory = false;
+}
+void set_low_memory(bool on) { g_low_memory = on; }
+bool low_memory() { return g_low_memory; }
 
 const unsigned long long* readback_u64(const unsigned long long* d_src, size_t count, cudaStream_t s)
 {
@@ -883,6 +913,25 @@ int sw_graph_split(sw_graph* g, uint32_t n_parts, uint64_t* node_split, uint64_t
     });
 }
 
+int sw_set_low_memory(int on)
+{
+    sw::set_low_memory(on != 0);
+    return SW_OK;
+}
+
+int sw_trim_memory(void)
+{
+    return guarded([&] {
+        init_device_once();
+        SW_CUDA(cudaDeviceSynchronize());
+        arena_trim();
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolTrimTo(pool, 0);
+    });
+}
+
 int sw_set_nodes_ready(sw_nodes_ready_fn fn, void* user)
 {
     g_nodes_ready = fn;
@@ -981,10 +1030,16 @@ int sw_graph_fetch(sw_graph* g)
 int sw_build(const char* const* paths, size_t n_paths, uint32_t k, uint32_t w, uint32_t n_host_threads,
              int low_memory, sw_graph** out)
 {
-    (void)low_memory;  // identical output by contract (build.cpp:380-391, test_graph.py:222-245)
+    // low_memory: identical output by contract (build.cpp:380-391, test_graph.py:222-245); here it selects the
+    // hash-sliced aggregation (graph.cu), whose scratch is a fraction of the single-pass plan's
     return guarded([&] {
         check_kw(k, w);
         init_device_once();
+        struct LowMemoryScope {
+            bool prev;
+            explicit LowMemoryScope(bool on) : prev(sw::low_memory()) { sw::set_low_memory(on || prev); }
+            ~LowMemoryScope() { sw::set_low_memory(prev); }
+        } scope(low_memory != 0);
         std::unique_ptr<sw_batch> b(batch_from_fasta(paths, n_paths, n_host_threads));
         // the arrays land in pinned host memory while the edge stage still runs; sw_graph_export then
         // copies them into the caller's (numpy) arrays with several threads, because first-touch page

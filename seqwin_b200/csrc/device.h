@@ -26,11 +26,16 @@ namespace sw {
 // of every build, so the steady state performs no cudaMalloc / cudaFree at all.
 void* arena_alloc(size_t bytes);
 void arena_reset();
+void arena_trim();   // give every slab back to the driver
 // Stack discipline inside one build: everything allocated after arena_mark() is handed back by
 // arena_release(mark) (stream order keeps a later owner of the bytes behind the kernels of the earlier one).
 struct ArenaMark { size_t slab, off; };
 ArenaMark arena_mark();
 void arena_release(const ArenaMark& m);
+size_t arena_free_bytes();   // unused bytes of the slabs the arena already owns
+// the caller asked for the reduced-footprint plan (thread-local; cpp/src/seqwin/build.cpp:264-325)
+void set_low_memory(bool on);
+bool low_memory();
 
 // Small device -> host readbacks (counts, histograms) go through a pinned, device-mapped buffer
 // written by a tiny kernel instead of cudaMemcpyAsync: a copy-engine transfer would queue behind
@@ -148,17 +153,20 @@ uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, in
 
 // Node-stage partition: (h1, k-mer) plus, per minimizer, the hashes of the stream neighbours whose adjacent pair
 // it OWNS (the pair belongs to the item with the smaller hash; 0 = none) -- what the edge grouping needs
-// (agg.cuh).  The first pass derives the two arrays from the stream; A / B are the ping-pong sets (n entries per
-// array) and *out points at the one holding the result.  *d_zero_key is set if a key is 0 (marker ambiguous: the
-// caller takes the sort-based path).  top_bits >= 1.  Returns the number of kernels launched; no host sync.
+// (agg.cuh).  Stable, on the key bits [lo_bit, lo_bit + n_bits).  in == nullptr: (keys, vals) is the stream and the
+// first pass derives the two arrays from it (*d_zero_key is set if a key is 0: the marker would be ambiguous and
+// the caller takes the sort-based path); otherwise `in` already holds all four arrays and (keys, vals) are not
+// read.  A / B are the ping-pong sets (n entries per array; `in` may be one of them) and *out points at the set
+// holding the result.  Returns the number of kernels launched; no host synchronisation.
 struct NbrBuffers {
     uint64_t* keys;
     uint64_t* vals;
     uint64_t* prev;
     uint64_t* next;
 };
-uint32_t radix_partition_top_nbr(const uint64_t* keys, const uint64_t* vals, uint64_t n, int top_bits, const NbrBuffers& A,
-                                 const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out, unsigned int* d_zero_key);
+uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const NbrBuffers* in, uint64_t n, int lo_bit, int n_bits,
+                             const NbrBuffers& A, const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out,
+                             unsigned int* d_zero_key);
 
 // ---- graph stage ------------------------------------------------------------------------------
 struct DevGraph {

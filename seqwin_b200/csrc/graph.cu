@@ -626,82 +626,133 @@ int choose_bucket_bits(uint64_t M, double per_node, double per_edge, const EdgeG
     return large ? p_large : p_small;
 }
 
-__global__ void node_hash_gather_kernel(const sw_node* __restrict__ nodes, uint64_t n, uint64_t* __restrict__ out)
+// ---- hash slices (reduced-footprint plan) -------------------------------------------------------------------
+// The scratch of the bucketed aggregation is 64 bytes per minimizer.  When that does not fit (or low_memory is
+// asked for, cpp/src/seqwin/build.cpp:264-325), the build runs over H = 2^hb hash slices one after the other: the
+// items of a slice are cut out of the stream -- in stream order, with their owned neighbours --, aggregated like
+// a whole stream, and their k-mers / nodes / edges appended to the outputs.  Slices are independent because a
+// node owns its k-mers AND the edges towards larger hashes; concatenating them in hash order is the graph.
+
+// items per (slice, block of the stream): counts[slice * n_blocks + block]
+__global__ void __launch_bounds__(kNT) slice_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int hshift, uint32_t H,
+                                                          uint32_t n_blocks, unsigned long long* __restrict__ counts)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = nodes[i].hash;
+    __shared__ uint32_t s_cnt[64];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        if (j < n) atomicAdd(&s_cnt[(uint32_t)(keys[j] >> hshift)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < H) counts[(uint64_t)threadIdx.x * n_blocks + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
-                          GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
+// the items of slice h, in stream order, with the neighbour hashes they own (what the first partition pass
+// generates for a whole stream, radix.cu); off = exclusive scan of the counts above
+__global__ void __launch_bounds__(kNT) slice_extract_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals,
+                                                            uint64_t n, int hshift, uint32_t h, uint32_t n_blocks,
+                                                            const unsigned long long* __restrict__ off, NbrBuffers out,
+                                                            unsigned int* zero_key)
+{
+    __shared__ uint32_t s_cnt[kRounds][kNT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kBlockItems;
+    const unsigned long long first = off[(uint64_t)h * n_blocks];
+    const unsigned long long dst0 = off[(uint64_t)h * n_blocks + blockIdx.x] - first;
+    uint64_t key[kRounds];
+    bool flag[kRounds];
+    uint32_t rank[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        key[r] = j < n ? keys[j] : 0;
+        flag[r] = j < n && (uint32_t)(key[r] >> hshift) == h;
+    }
+    block_ranks(flag, rank, s_cnt);
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        if (!flag[r]) continue;
+        const uint64_t j = base + (uint64_t)r * kNT + threadIdx.x;
+        const uint64_t v = vals[j];
+        const uint32_t rec = (uint32_t)(v >> 32);
+        const unsigned long long d = dst0 + rank[r];
+        out.keys[d] = key[r];
+        out.vals[d] = v;
+        out.prev[d] = agg::owned_prev(keys, vals, j, key[r], rec);
+        out.next[d] = agg::owned_next(keys, vals, j, n, key[r], rec);
+        if (key[r] == 0) *zero_key = 1u;
+    }
+}
+
+struct CapacityExceeded {};   // sliced build: an output array sized from the estimates is too small
+
+// What one pass of the aggregation needs to know about where it is: the whole stream, or one hash slice of it.
+struct SliceJob {
+    const NbrBuffers* R;        // partitioned items (keys | vals | prev | next)
+    const NbrBuffers* Dd;       // the free set of the same size
+    uint64_t n;                 // items
+    uint64_t bucket0, n_buckets;
+    int key_bits;
+    uint64_t kmer_base, node_base, edge_base;   // outputs of the earlier slices
+    bool exact;                 // whole stream: the outputs are allocated here, with their exact sizes
+    uint64_t node_cap, edge_cap;
+};
+
+// nodes + k-mers (+ scoring) and the edges of the buckets of one job; the counters of `tot` were zeroed by the caller
+void aggregate_buckets(const SliceJob& J, uint16_t* item_rank, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s,
+                       DevGraph& g, GraphTimes& tm, EventTimer& timer, const EdgeGeom& eg, const ScoreArgs* score,
+                       const std::function<void()>* after_nodes, unsigned long long* tot, uint64_t* n_nodes_out,
+                       uint64_t* n_edges_out, bool* fallback)
 {
     using namespace agg;
-    const uint64_t M = st.n;
-    GraphTimes tm;
-    EventTimer timer(s);
-    timer.start();
-
-    // scratch: two sets of four M-word arrays (keys | k-mers | owned previous | owned next neighbour), each one block
-    DevBuf<uint64_t> setA(4 * M, s, true), setB(4 * M, s, true);
-    const NbrBuffers A{setA.p, setA.p + M, setA.p + 2 * M, setA.p + 3 * M};
-    const NbrBuffers B{setB.p, setB.p + M, setB.p + 2 * M, setB.p + 3 * M};
-    DevBuf<uint16_t> item_rank(M, s, true);   // rank of every item's hash inside its bucket
-
-    // -- nodes: partition on the top P bits of h1, distinct hashes per bucket ---------------------------------------
-    // bucket size: about `target` distinct hashes each, which takes an estimate of the k-mers per distinct hash
-    double per_node = st.items_per_key;   // taken by the sketch's reorder pass; a stream from elsewhere is sampled here
-    if (per_node <= 0) {
-        DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
-        per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
-        tm.launches += 1;
-    }
-    const double per_edge = st.pairs_per_edge > 0 ? st.pairs_per_edge : 1.0;   // a stream from elsewhere: no pair assumed twice
-    const EdgeGeom* egp = nullptr;
-    const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
-    int P = choose_bucket_bits(M, per_node, per_edge, &egp);
-    if (fixed_nb) P = partition_bits(M, fixed_nb);
-    const EdgeGeom& eg = *egp;
-    const int key_bits = 64 - P;
-    const uint64_t n_buckets = 1ull << P;
-    DevBuf<unsigned long long> tot(4, s, true);   // [0] overflowing node buckets [1] their items [2] nodes; [3] low word: a key is 0
-    SW_CUDA(cudaMemsetAsync(tot.p, 0, 4 * sizeof(unsigned long long), s));
-    const NbrBuffers* R = nullptr;
-    tm.launches += radix_partition_top_nbr(st.keys.p, st.vals.p, M, P, A, B, s, &R, reinterpret_cast<unsigned int*>(tot.p + 3));
-    const NbrBuffers& Dd = R == &A ? B : A;            // the set that does not hold the result is free
+    const NbrBuffers& R = *J.R;
+    const NbrBuffers& Dd = *J.Dd;
+    const uint64_t n_buckets = J.n_buckets;
     uint64_t* grp_keys = Dd.keys;                      // distinct hashes of every bucket (live until the edges are written)
     uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(Dd.vals);
     DevBuf<uint32_t> start(n_buckets + 1, s, true), bucket_d(n_buckets, s, true);
     DevBuf<unsigned long long> d64(n_buckets + 1, s, true);
-    bucket_search_kernel<<<stride_grid(n_buckets + 1), 256, 0, s>>>(R->keys, M, key_bits, n_buckets, start.p);
-    group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(R->keys, start.p, key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
-                                                           bucket_d.p, item_rank.p);
+    bucket_search_kernel<<<stride_grid(n_buckets + 1), 256, 0, s>>>(R.keys, J.n, J.key_bits, n_buckets, start.p, J.bucket0);
+    group_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(R.keys, start.p, J.key_bits, (uint32_t)kMaxDistinct, grp_keys, grp_cnt,
+                                                           bucket_d.p, item_rank, J.bucket0);
     SW_CUDA(cudaMemsetAsync(d64.p + n_buckets, 0, sizeof(unsigned long long), s));
-    bucket_counts_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_d.p, start.p, n_buckets, d64.p, nullptr, tot.p);
-    tm.launches += 3 + exclusive_scan_u64(d64.p, n_buckets + 1, tot.p + 2, s);
+    bucket_counts_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_d.p, start.p, n_buckets, d64.p, nullptr, tot);
+    tm.launches += 3 + exclusive_scan_u64(d64.p, n_buckets + 1, tot + 2, s);
     SW_CUDA(cudaGetLastError());
-    const unsigned long long* tot_p = readback_u64(tot.p, 4, s);
+    const unsigned long long* tot_p = readback_u64(tot, 4, s);
     SW_CUDA(cudaStreamSynchronize(s));
-    tm.sort_nodes_ms = timer.stop();
-    if (tot_p[0] != 0 || tot_p[3] != 0) return false;
+    tm.sort_nodes_ms += timer.stop();
+    if (tot_p[0] != 0 || tot_p[3] != 0) {
+        *fallback = true;
+        return;
+    }
     const unsigned long long n_nodes = tot_p[2];
+    *n_nodes_out = n_nodes;
 
     // -- nodes + kmers (+ scoring) -----------------------------------------------------------------------------
     timer.start();
-    g.n_kmers = M;
-    g.n_nodes = n_nodes;
-    g.kmers.alloc(M, s);
-    g.nodes.alloc(n_nodes, s);
+    if (J.exact) {
+        g.n_kmers = J.n;
+        g.n_nodes = n_nodes;
+        g.kmers.alloc(J.n, s);
+        g.nodes.alloc(n_nodes, s);
+    } else if (J.node_base + n_nodes > J.node_cap) {
+        throw CapacityExceeded();
+    }
     const ArenaMark node_mark = arena_mark();   // what follows is dead once the placement kernel has run
-    DevBuf<uint32_t> node_asm(score ? M : 0, s, true);
-    const PlaceArgs pa{item_rank.p, start.p, key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
+    DevBuf<uint32_t> node_asm(score ? J.n : 0, s, true);
+    const PlaceArgs pa{item_rank, start.p, J.key_bits, grp_keys, grp_cnt, bucket_d.p, d64.p};
     NodeOut no{};
-    no.vals = reinterpret_cast<const unsigned long long*>(R->vals);
-    no.placed = reinterpret_cast<unsigned long long*>(g.kmers.p);
+    no.vals = reinterpret_cast<const unsigned long long*>(R.vals);
+    no.placed = reinterpret_cast<unsigned long long*>(g.kmers.p + J.kmer_base);
     no.placed_asm = node_asm.p;
-    no.nodes = g.nodes.p;
+    no.nodes = g.nodes.p + J.node_base;
     no.node_hash = nullptr;
     no.rec_asm = d_rec_asm;
     no.rec_base = rec_base;
+    no.kmer_base = J.kmer_base;
     if (score) {
         no.is_target = score->d_is_target;
         no.inv_t = score->inv_t;
@@ -723,17 +774,17 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     DevBuf<unsigned long long> e64(n_buckets + 1, s, true), ebase(n_buckets + 1, s, true), side_rec(n_buckets + 1, s, true),
         etot(4, s, true);
     BucketEdgeArgs ea{};
-    ea.item_rank = item_rank.p;
-    ea.nb_prev = R->prev;
-    ea.nb_next = R->next;
-    ea.vals = reinterpret_cast<const unsigned long long*>(R->vals);
+    ea.item_rank = item_rank;
+    ea.nb_prev = R.prev;
+    ea.nb_next = R.next;
+    ea.vals = reinterpret_cast<const unsigned long long*>(R.vals);
     ea.start = start.p;
     ea.rec_asm = d_rec_asm;
     ea.rec_base = rec_base;
     ea.max_distinct = std::min<uint32_t>(env_u32("SEQWIN_AGG_EDGE_DISTINCT", eg.e_max), eg.e_max);
-    ea.te_second = Dd.prev;                                   // 2 M words: Dd.prev | Dd.next
-    ea.te_w = reinterpret_cast<uint32_t*>(Dd.vals);           // 2 M u32
-    ea.te_r = reinterpret_cast<uint16_t*>(R->keys);           // 2 M u16
+    ea.te_second = Dd.prev;                                   // 2 n words: Dd.prev | Dd.next
+    ea.te_w = reinterpret_cast<uint32_t*>(Dd.vals);           // 2 n u32
+    ea.te_r = reinterpret_cast<uint16_t*>(R.keys);            // 2 n u16
     ea.bucket_e = bucket_e.p;
     ea.bucket_rec = bucket_rec.p;
     SW_CUDA(cudaFuncSetAttribute(eg.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg.smem));
@@ -746,46 +797,48 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
     tm.launches += 2 + exclusive_scan_u64(ebase.p, n_buckets + 1, etot.p + 2, s);
     SW_CUDA(cudaGetLastError());
     if (after_nodes) (*after_nodes)();
-    tm.nodes_ms = timer.read();
+    tm.nodes_ms += timer.read();
     const unsigned long long* etot_p = readback_u64(etot.p, 4, s);
     SW_CUDA(cudaStreamSynchronize(s));
     unsigned long long n_edges = etot_p[2];
     const unsigned long long n_ovf = etot_p[0], n_side = etot_p[1];
     if (getenv("SEQWIN_DEBUG_AGG"))
-        fprintf(stderr, "[agg] M %llu (%.2f per node, %.2f pairs per edge) P %d nodes %llu edges %llu, %llu buckets (%llu records) to the sort path\n",
-                (unsigned long long)M, per_node, per_edge, P, n_nodes, n_edges, n_ovf, n_side);
+        fprintf(stderr, "[agg] items %llu buckets %llu (first %llu) nodes %llu edges %llu, %llu buckets (%llu records) to the sort path\n",
+                (unsigned long long)J.n, (unsigned long long)n_buckets, (unsigned long long)J.bucket0, n_nodes, n_edges, n_ovf, n_side);
     DevBuf<sw_edge> side_edges;
     DevBuf<unsigned long long> ovf_e64;
     if (n_ovf) {
-        // buckets with more distinct pairs than a table takes (hub nodes): their records get global rank pairs,
-        // are sorted on the whole key and run-length encoded, as the sort-based path does for everything
-        int rank_bits = 1;
-        while (rank_bits < 32 && (1ull << rank_bits) < n_nodes) ++rank_bits;
-        int fbits = 1;
-        while (fbits < 28 && (1ull << fbits) < n_nodes) ++fbits;
-        DevBuf<uint64_t> node_hash(n_nodes, s, true);
-        DevBuf<uint32_t> ftable((1ull << fbits) + 1, s, true);
-        node_hash_gather_kernel<<<stride_grid(n_nodes), 256, 0, s>>>(g.nodes.p, n_nodes, node_hash.p);
-        bucket_bounds_kernel<<<stride_grid(n_nodes + 1), 256, 0, s>>>(node_hash.p, n_nodes, 64 - fbits, 1ull << fbits, ftable.p);
+        // buckets with more distinct pairs than a table takes (hub nodes): their records are sorted by (owner, second
+        // hash) -- two stable radix sorts, `second` first -- and run-length encoded
+        if (n_side > 0xFFFFFFFFull || n_nodes > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 edge records on the sort path");
         exclusive_scan_u64(side_rec.p, n_buckets + 1, etot.p + 3, s);     // -> first side slot of every such bucket
+        DevBuf<uint32_t> side_node(n_side, s, true), side_asm(n_side, s, true);
+        DevBuf<uint64_t> side_second(n_side, s, true);
+        side_emit_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(ea, bucket_e.p, side_rec.p, d64.p, side_node.p, side_second.p, side_asm.p);
         SortPairs sp;
         sp.n = n_side;
         sp.keys.alloc(n_side, s, true);
         sp.vals.alloc(n_side, s, true);
-        side_emit_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(ea, bucket_e.p, side_rec.p, d64.p, node_hash.p, ftable.p, 64 - fbits,
-                                                             rank_bits, sp.keys.p, sp.vals.p);
+        SW_CUDA(cudaMemcpyAsync(sp.keys.p, side_second.p, n_side * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        iota_kernel<<<(uint32_t)std::min<uint64_t>((n_side + 255) / 256, 65535), 256, 0, s>>>(sp.vals.p, n_side);
         SW_CUDA(cudaGetLastError());
-        tm.launches += 4 + radix_sort_pairs(sp, 64, s, (64 - 2 * rank_bits) & ~7);
+        tm.launches += 3 + radix_sort_pairs(sp, 64, s, 0);
+        side_gather_node_kernel<<<stride_grid(n_side), 256, 0, s>>>(sp.vals.p, side_node.p, n_side, sp.keys.p);
+        SW_CUDA(cudaGetLastError());
+        int node_bits = 1;
+        while (node_bits < 32 && (1ull << node_bits) < n_nodes) ++node_bits;
+        tm.launches += 1 + radix_sort_pairs(sp, node_bits, s, 0);
+        DevBuf<unsigned long long> flags(n_side + 1, s, true);
+        SW_CUDA(cudaMemsetAsync(flags.p + n_side, 0, sizeof(unsigned long long), s));
+        side_final_kernel<<<stride_grid(n_side), 256, 0, s>>>(sp.vals.p, side_node.p, side_second.p, side_asm.p, n_side, flags.p,
+                                                              nullptr, nullptr, nullptr);
+        exclusive_scan_u64(flags.p, n_side + 1, etot.p + 3, s);
         ovf_e64.alloc(n_buckets + 1, s, true);
         SW_CUDA(cudaMemsetAsync(ovf_e64.p + n_buckets, 0, sizeof(unsigned long long), s));
-        side_count_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(sp.keys.p, bucket_e.p, side_rec.p, e64.p, ovf_e64.p);
+        side_count_kernel<<<stride_grid(n_buckets), 256, 0, s>>>(bucket_e.p, side_rec.p, flags.p, n_buckets, e64.p, ovf_e64.p);
         exclusive_scan_u64(ovf_e64.p, n_buckets + 1, etot.p + 3, s);
         SW_CUDA(cudaMemcpyAsync(ebase.p, e64.p, (n_buckets + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
         exclusive_scan_u64(ebase.p, n_buckets + 1, etot.p + 2, s);
-        const uint32_t sb = blocks_for(n_side);
-        DevBuf<unsigned long long> scounts((size_t)sb + 1, s, true);
-        key_run_count_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, n_side, scounts.p);
-        exclusive_scan_u64(scounts.p, sb, scounts.p + sb, s);
         SW_CUDA(cudaGetLastError());
         const unsigned long long* e2 = readback_u64(etot.p, 4, s);
         SW_CUDA(cudaStreamSynchronize(s));
@@ -793,23 +846,201 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
         const unsigned long long n_side_edges = e2[3];
         side_edges.alloc(n_side_edges, s, true);
         SW_CUDA(cudaMemsetAsync(side_edges.p, 0, n_side_edges * sizeof(sw_edge), s));
-        edge_final_kernel<<<sb, kNT, 0, s>>>(sp.keys.p, sp.vals.p, n_side, scounts.p, rank_bits, node_hash.p, side_edges.p);
+        side_final_kernel<<<stride_grid(n_side), 256, 0, s>>>(sp.vals.p, side_node.p, side_second.p, side_asm.p, n_side, nullptr,
+                                                              flags.p, g.nodes.p + J.node_base, side_edges.p);
         SW_CUDA(cudaGetLastError());
-        tm.launches += 8;
+        tm.launches += 9;
     }
-    g.n_edges = n_edges;
-    g.edges.alloc(n_edges, s);
+    *n_edges_out = n_edges;
+    if (J.exact) {
+        g.n_edges = n_edges;
+        g.edges.alloc(n_edges, s);
+    } else if (J.edge_base + n_edges > J.edge_cap) {
+        throw CapacityExceeded();
+    }
     if (n_edges) {
+        sw_edge* edges_out = g.edges.p + J.edge_base;
         bucket_edges_out_kernel<<<(uint32_t)std::min<uint64_t>((n_buckets + 7) / 8, (uint64_t)sm_count() * 16), 256, 0, s>>>(
-            ea.te_second, ea.te_w, ea.te_r, start.p, bucket_e.p, ebase.p, n_buckets, grp_keys, g.edges.p);
+            ea.te_second, ea.te_w, ea.te_r, start.p, bucket_e.p, ebase.p, n_buckets, grp_keys, edges_out);
         ++tm.launches;
         if (n_ovf) {
-            overflow_copy_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(side_edges.p, bucket_e.p, ebase.p, ovf_e64.p, g.edges.p);
+            overflow_copy_kernel<<<(uint32_t)n_buckets, kNT, 0, s>>>(side_edges.p, bucket_e.p, ebase.p, ovf_e64.p, edges_out);
             ++tm.launches;
         }
         SW_CUDA(cudaGetLastError());
     }
-    tm.edges_ms = etimer.stop();
+    tm.edges_ms += etimer.stop();
+}
+
+// how many hash slices (a power of two, <= 64) the aggregation needs so that its scratch and the outputs fit
+uint32_t choose_slices(uint64_t M, double per_node, double per_edge, bool scored)
+{
+    if (const uint32_t forced = env_u32("SEQWIN_AGG_SLICES", 0)) {
+        uint32_t h = 1;
+        while (h < forced && h < 64) h <<= 1;
+        return h;
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+    const double avail = 0.9 * ((double)free_b + (double)arena_free_bytes());
+    const double outputs = 8.0 * (double)M + 1.1 * (40.0 * (double)M / per_node + 24.0 * (double)M / per_edge);
+    uint32_t h = low_memory() ? 4 : 1;
+    for (; h < 64; h <<= 1) {
+        const double scratch = (64.0 + 2.0 + (scored ? 4.0 : 0.0) + 2.0) * 1.25 * (double)M / (double)h;
+        if (outputs + scratch <= avail) break;
+    }
+    return h;
+}
+
+// Bucketed aggregation (agg.cuh): stable partition of the stream on the top bits of h1 -- every item taking along the
+// neighbour hashes whose adjacent pair it owns --, then one CTA per bucket groups the nodes, and a second one the
+// edges those nodes own, in shared memory.  Returns false -- `g` left empty -- if a bucket holds more distinct hashes
+// than its table takes (not expected: the bucket count follows the item count and h1 is a 64-bit mix) or a hash is
+// 0 (the "no neighbour" marker); the caller then runs the sort-based path.
+bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
+                          GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)
+{
+    using namespace agg;
+    const uint64_t M = st.n;
+    GraphTimes tm;
+    EventTimer timer(s);
+    timer.start();
+
+    // bucket size: about `target` distinct hashes each, which takes an estimate of the k-mers per distinct hash
+    double per_node = st.items_per_key;   // taken by the sketch's reorder pass; a stream from elsewhere is sampled here
+    if (per_node <= 0) {
+        DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
+        per_node = estimate_items_per_key(st.keys.p, M, sample_set.p, sample_out.p, s);
+        tm.launches += 1;
+    }
+    const double per_edge = st.pairs_per_edge > 0 ? st.pairs_per_edge : 1.0;   // a stream from elsewhere: no pair assumed twice
+    const EdgeGeom* egp = nullptr;
+    const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0);
+    int P = choose_bucket_bits(M, per_node, per_edge, &egp);
+    if (fixed_nb) P = partition_bits(M, fixed_nb);
+    const EdgeGeom& eg = *egp;
+    const int key_bits = 64 - P;
+    uint32_t H = choose_slices(M, per_node, per_edge, score != nullptr);
+    while (H > 1 && (1ull << P) < H) H >>= 1;   // at least one bucket per slice
+    int hb = 0;
+    while ((1u << hb) < H) ++hb;
+    DevBuf<unsigned long long> tot(4, s, true);   // [0] overflowing node buckets [1] their items [2] nodes; [3] low word: a key is 0
+    SW_CUDA(cudaMemsetAsync(tot.p, 0, 4 * sizeof(unsigned long long), s));
+    bool fallback = false;
+    uint64_t n_nodes = 0, n_edges = 0;
+
+    if (H == 1) {
+        if (M > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers in one aggregation pass");
+        // scratch: two sets of four M-word arrays (keys | k-mers | owned previous | owned next neighbour), each one block
+        DevBuf<uint64_t> setA(4 * M, s, true), setB(4 * M, s, true);
+        const NbrBuffers A{setA.p, setA.p + M, setA.p + 2 * M, setA.p + 3 * M};
+        const NbrBuffers B{setB.p, setB.p + M, setB.p + 2 * M, setB.p + 3 * M};
+        DevBuf<uint16_t> item_rank(M, s, true);   // rank of every item's hash inside its bucket
+        const NbrBuffers* R = nullptr;
+        tm.launches += radix_partition_nbr(st.keys.p, st.vals.p, nullptr, M, key_bits, P, A, B, s, &R,
+                                           reinterpret_cast<unsigned int*>(tot.p + 3));
+        SliceJob J{};
+        J.R = R;
+        J.Dd = R == &A ? &B : &A;
+        J.n = M;
+        J.bucket0 = 0;
+        J.n_buckets = 1ull << P;
+        J.key_bits = key_bits;
+        J.exact = true;
+        aggregate_buckets(J, item_rank.p, d_rec_asm, rec_base, s, g, tm, timer, eg, score, after_nodes, tot.p, &n_nodes, &n_edges,
+                          &fallback);
+        if (fallback) return false;
+        if (times) *times = tm;
+        return true;
+    }
+
+    // ---- sliced ----
+    const int hshift = 64 - hb;
+    const uint32_t nb = blocks_for(M);
+    DevBuf<unsigned long long> counts((uint64_t)H * nb + 1, s, true);
+    slice_count_kernel<<<nb, kNT, 0, s>>>(st.keys.p, M, hshift, H, nb, counts.p);
+    tm.launches += 1 + exclusive_scan_u64(counts.p, (uint64_t)H * nb, counts.p + (uint64_t)H * nb, s);
+    SW_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> slice_start(H + 1, M);
+    {
+        DevBuf<unsigned long long> firsts(H, s, true);
+        SW_CUDA(cudaMemcpy2DAsync(firsts.p, sizeof(unsigned long long), counts.p, (size_t)nb * sizeof(unsigned long long),
+                                  sizeof(unsigned long long), H, cudaMemcpyDeviceToDevice, s));
+        const unsigned long long* hp = readback_u64(firsts.p, H, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        std::copy(hp, hp + H, slice_start.begin());
+    }
+    uint64_t max_items = 0;
+    for (uint32_t h = 0; h < H; ++h) max_items = std::max<uint64_t>(max_items, slice_start[h + 1] - slice_start[h]);
+    if (max_items > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers in one hash slice");
+    DevBuf<uint64_t> setA(4 * max_items, s, true), setB(4 * max_items, s, true);
+    const NbrBuffers A{setA.p, setA.p + max_items, setA.p + 2 * max_items, setA.p + 3 * max_items};
+    const NbrBuffers B{setB.p, setB.p + max_items, setB.p + 2 * max_items, setB.p + 3 * max_items};
+    DevBuf<uint16_t> item_rank(max_items, s, true);
+    double slack = (double)env_u32("SEQWIN_AGG_SLACK_PCT", 110) / 100.0;   // head room over the estimated node / edge counts
+    for (int attempt = 0;; ++attempt) {
+        const uint64_t node_cap = std::min<uint64_t>(M, (uint64_t)(slack * (double)M / per_node) + env_u32("SEQWIN_AGG_SLACK_ITEMS", 1u << 20));
+        const uint64_t edge_cap = std::min<uint64_t>(M, (uint64_t)(slack * (double)M / per_edge) + env_u32("SEQWIN_AGG_SLACK_ITEMS", 1u << 20));
+        g.n_kmers = M;
+        g.kmers.alloc(M, s);
+        g.nodes.alloc(node_cap, s);
+        g.edges.alloc(edge_cap, s);
+        uint64_t node_base = 0, edge_base = 0;
+        try {
+            for (uint32_t h = 0; h < H; ++h) {
+                const uint64_t n_h = slice_start[h + 1] - slice_start[h];
+                if (n_h == 0) continue;
+                if (h) timer.start();
+                const ArenaMark slice_mark = arena_mark();
+                slice_extract_kernel<<<nb, kNT, 0, s>>>(st.keys.p, st.vals.p, M, hshift, h, nb, counts.p, A,
+                                                        reinterpret_cast<unsigned int*>(tot.p + 3));
+                SW_CUDA(cudaGetLastError());
+                const NbrBuffers* R = nullptr;
+                tm.launches += 1 + radix_partition_nbr(nullptr, nullptr, &A, n_h, key_bits, P - hb, A, B, s, &R, nullptr);
+                SliceJob J{};
+                J.R = R;
+                J.Dd = R == &A ? &B : &A;
+                J.n = n_h;
+                J.n_buckets = 1ull << (P - hb);
+                J.bucket0 = (uint64_t)h * J.n_buckets;
+                J.key_bits = key_bits;
+                J.kmer_base = slice_start[h];
+                J.node_base = node_base;
+                J.edge_base = edge_base;
+                J.exact = false;
+                J.node_cap = node_cap;
+                J.edge_cap = edge_cap;
+                uint64_t nn = 0, ne = 0;
+                SW_CUDA(cudaMemsetAsync(tot.p, 0, 3 * sizeof(unsigned long long), s));
+                aggregate_buckets(J, item_rank.p, d_rec_asm, rec_base, s, g, tm, timer, eg, score, nullptr, tot.p, &nn, &ne, &fallback);
+                if (fallback) break;
+                node_base += nn;
+                edge_base += ne;
+                arena_release(slice_mark);
+            }
+        } catch (const CapacityExceeded&) {
+            if (attempt >= 3) fail_runtime("sliced aggregation: output estimate exceeded repeatedly");
+            slack *= 2.0;
+            SW_CUDA(cudaStreamSynchronize(s));
+            continue;
+        }
+        n_nodes = node_base;
+        n_edges = edge_base;
+        break;
+    }
+    if (fallback) {
+        SW_CUDA(cudaStreamSynchronize(s));
+        g.kmers.release();
+        g.nodes.release();
+        g.edges.release();
+        return false;
+    }
+    g.n_nodes = n_nodes;
+    g.n_edges = n_edges;
+    if (after_nodes) (*after_nodes)();
+    if (getenv("SEQWIN_DEBUG_AGG"))
+        fprintf(stderr, "[agg] %u hash slices: M %llu nodes %llu edges %llu\n", H, (unsigned long long)M, (unsigned long long)n_nodes,
+                (unsigned long long)n_edges);
     if (times) *times = tm;
     return true;
 }

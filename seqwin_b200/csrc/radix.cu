@@ -427,27 +427,36 @@ uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, in
     *out_v = where < 0 ? vals : (where == 0 ? va : vb);
     return launches;
 }
-// The same partition for the node stage: (key, value) plus the two owned-neighbour arrays, which the first
-// pass generates from the stream (every pass runs, also one whose keys share a digit).
-uint32_t radix_partition_top_nbr(const uint64_t* keys, const uint64_t* vals, uint64_t n, int top_bits, const NbrBuffers& A,
-                                 const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out, unsigned int* d_zero_key)
+// The partition of the node stage: (key, value) plus the two owned-neighbour arrays, stable, on the key bits
+// [lo_bit, lo_bit + n_bits), lowest digit first.  Either the input is the stream itself (in == nullptr): the first
+// pass derives the neighbour arrays from it (and runs even for n_bits == 0); or it is a set that already holds
+// them (a hash slice cut out of the stream, graph.cu): every pass carries them.  Every pass runs, also one whose
+// keys share a digit.
+uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const NbrBuffers* in, uint64_t n, int lo_bit, int n_bits,
+                             const NbrBuffers& A, const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out,
+                             unsigned int* d_zero_key)
 {
     using V = unsigned long long;
     RadixPasses ps{};
-    const int np = (top_bits + kRadixBits - 1) / kRadixBits;
-    int lo = 64 - top_bits;
+    const int np = n_bits > 0 ? (n_bits + kRadixBits - 1) / kRadixBits : (in ? 0 : 1);
+    int lo = lo_bit;
     for (int p = 0; p < np; ++p) {
-        const int bits = p == 0 ? top_bits - kRadixBits * (np - 1) : kRadixBits;
+        const int bits = p == 0 ? n_bits - kRadixBits * (np - 1) : kRadixBits;
         ps.shift[ps.n] = lo;
         ps.bits[ps.n] = bits;
         ++ps.n;
         lo += bits;
     }
+    if (ps.n == 0 || n == 0) {
+        *out = in ? in : &A;
+        return 0;
+    }
+    const uint64_t* hist_keys = in ? in->keys : keys;
     uint32_t launches = 0;
     DevBuf<unsigned long long> ghist((size_t)kMaxPasses * kRadix, s, true);
     SW_CUDA(cudaMemsetAsync(ghist.p, 0, ghist.bytes(), s));
     const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
-    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(keys, n, ps, ghist.p);
+    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(hist_keys, n, ps, ghist.p);
     DevBuf<unsigned long long> max_bin(kMaxPasses, s, true);
     radix_offsets_kernel<<<ps.n, kRadix, 0, s>>>(ghist.p, max_bin.p);
     SW_CUDA(cudaGetLastError());
@@ -460,7 +469,7 @@ uint32_t radix_partition_top_nbr(const uint64_t* keys, const uint64_t* vals, uin
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
     SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems, V, 2>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
-    const NbrBuffers* src = nullptr;
+    const NbrBuffers* src = in;
     for (int p = 0; p < ps.n; ++p) {
         const NbrBuffers* dst = src == &A ? &B : &A;
         SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
@@ -468,7 +477,7 @@ uint32_t radix_partition_top_nbr(const uint64_t* keys, const uint64_t* vals, uin
         NbrArrays nb;
         nb.out_a = dst->prev;
         nb.out_b = dst->next;
-        if (p == 0) {
+        if (src == nullptr) {
             nb.n_total = n;
             nb.zero_key = d_zero_key;
             radix_onesweep_kernel<kSortThreads, kSortItems, V, 2><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(

@@ -150,40 +150,34 @@ extern "C" long agg_emul_run(const uint64_t* stream_keys, const uint64_t* stream
     std::vector<sw_edge> side_edges;
     std::vector<unsigned long long> ovf_e64(nb, 0), ovf_base;
     if (etot[0]) {
-        // buckets left to the side path: the device sorts their records (radix sort) and run-length encodes them;
-        // here the sort and the encoding are host code, the record emission and the index plumbing are the kernels'
+        // buckets left to the side path: the device sorts their records by (node, second hash) with two stable
+        // radix sorts; here that order comes from a host sort, everything else is the device code
         *n_overflow_out = etot[0];
-        std::vector<uint64_t> node_hash(U);
-        for (uint64_t i = 0; i < U; ++i) node_hash[i] = nodes_out[i].hash;
-        int fbits = 1;
-        while (fbits < 28 && (1ull << fbits) < U) ++fbits;
-        std::vector<uint32_t> ftable((1ull << fbits) + 1);
-        cuemu::launch(dim3(2), dim3(256), [&] { bucket_bounds_kernel(node_hash.data(), U, 64 - fbits, 1ull << fbits, ftable.data()); });
-        int rank_bits = 1;
-        while (rank_bits < 32 && (1ull << rank_bits) < U) ++rank_bits;
         std::vector<unsigned long long> side_off = exclusive_scan(side_rec);
-        std::vector<uint64_t> skeys(etot[1], 0xDDDDDDDDDDDDDDDDull);
-        std::vector<uint32_t> sasm(etot[1]);
+        const uint64_t ns = etot[1];
+        std::vector<uint32_t> side_node(ns, 0xDDDDDDDDu), side_asm(ns), perm(ns);
+        std::vector<uint64_t> side_second(ns);
         cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] {
-            side_emit_kernel(ea, bucket_e.data(), side_off.data(), grp_base.data(), node_hash.data(), ftable.data(), 64 - fbits, rank_bits,
-                             skeys.data(), sasm.data());
+            side_emit_kernel(ea, bucket_e.data(), side_off.data(), grp_base.data(), side_node.data(), side_second.data(), side_asm.data());
         });
-        stable_partition_top_bits(skeys, sasm, 0);
-        cuemu::launch(dim3((unsigned)nb), dim3(kNT), [&] {
-            side_count_kernel(skeys.data(), bucket_e.data(), side_off.data(), e64.data(), ovf_e64.data());
+        std::iota(perm.begin(), perm.end(), 0u);
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) {
+            return side_node[x] != side_node[y] ? side_node[x] < side_node[y] : side_second[x] < side_second[y];
+        });
+        std::vector<unsigned long long> flags(ns + 1, 0);
+        cuemu::launch(dim3(2), dim3(256), [&] {
+            side_final_kernel(perm.data(), side_node.data(), side_second.data(), side_asm.data(), ns, flags.data(), nullptr, nullptr, nullptr);
+        });
+        std::vector<unsigned long long> scanned = exclusive_scan(std::vector<unsigned long long>(flags.begin(), flags.end() - 1));
+        cuemu::launch(dim3(2), dim3(256), [&] {
+            side_count_kernel(bucket_e.data(), side_off.data(), scanned.data(), nb, e64.data(), ovf_e64.data());
         });
         ovf_base = exclusive_scan(ovf_e64);
-        for (size_t i = 0; i < skeys.size(); ++i) {
-            if (i == 0 || skeys[i] != skeys[i - 1]) {
-                sw_edge e;
-                e.first = node_hash[skeys[i] >> (64 - rank_bits)];
-                e.second = node_hash[(skeys[i] >> (64 - 2 * rank_bits)) & ((1ull << rank_bits) - 1)];
-                e.weight = 1;
-                side_edges.push_back(e);
-            } else if (sasm[i] != sasm[i - 1]) {
-                ++side_edges.back().weight;
-            }
-        }
+        side_edges.assign(scanned[ns] & 0xFFFFFFFFull, sw_edge{0, 0, 0});
+        cuemu::launch(dim3(2), dim3(256), [&] {
+            side_final_kernel(perm.data(), side_node.data(), side_second.data(), side_asm.data(), ns, nullptr, scanned.data(), nodes_out,
+                              side_edges.data());
+        });
     }
     std::vector<unsigned long long> ebase = exclusive_scan(e64);
     const uint64_t UE = ebase[nb];

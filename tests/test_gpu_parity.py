@@ -284,8 +284,15 @@ def test_window_too_large_fails_loudly():
 AGG_MODES = {
     "legacy": {"SEQWIN_AGG": "legacy"},                               # sort + run-length path (round 1)
     "edge-overflow": {"SEQWIN_AGG_EDGE_DISTINCT": "6"},               # most edge buckets take the side (sort) path
-    "tiny-buckets": {"SEQWIN_AGG_NODE_BUCKET": "12", "SEQWIN_AGG_EDGE_BUCKET": "5"},   # 2-3 partition passes, tiny groups
-    "one-bucket-pair": {"SEQWIN_AGG_NODE_BUCKET": "700", "SEQWIN_AGG_EDGE_BUCKET": "700", "SEQWIN_AGG_EDGE_DISTINCT": "700"},
+    "tiny-buckets": {"SEQWIN_AGG_NODE_BUCKET": "12"},                 # 2-3 partition passes, tiny groups
+    "one-bucket-pair": {"SEQWIN_AGG_NODE_BUCKET": "700", "SEQWIN_AGG_EDGE_DISTINCT": "700"},
+    "large-edge-table": {"SEQWIN_AGG_EDGE_GEOM": "2"},
+    # the reduced-footprint plan: hash slices of the stream aggregated one after the other
+    "slices-4": {"SEQWIN_AGG_SLICES": "4"},
+    "slices-16-tiny-buckets": {"SEQWIN_AGG_SLICES": "16", "SEQWIN_AGG_NODE_BUCKET": "12"},
+    "slices-edge-overflow": {"SEQWIN_AGG_SLICES": "4", "SEQWIN_AGG_EDGE_DISTINCT": "6"},
+    # ... with output arrays sized too small at first (the estimate is retried with more head room)
+    "slices-capacity-retry": {"SEQWIN_AGG_SLICES": "2", "SEQWIN_AGG_SLACK_PCT": "40", "SEQWIN_AGG_SLACK_ITEMS": "1"},
 }
 
 
