@@ -12,8 +12,11 @@
 
 #if defined(__CUDACC__)
 #define SW_HD __host__ __device__ __forceinline__
+// rarely executed device code: kept out of line, so that it does not sit inside the hot loops' instruction footprint
+#define SW_COLD __host__ __device__ __noinline__
 #else
 #define SW_HD inline
+#define SW_COLD inline
 #endif
 
 namespace sw {

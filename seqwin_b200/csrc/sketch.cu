@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -163,7 +164,9 @@ __global__ void __launch_bounds__(NT) sketch_generic_kernel(const __grid_constan
 }
 
 // Sparse path (sketch_tile.h): candidates only, no per-k-mer shared memory.
-template <int NT, int C1, int CAP>
+// GAPS = false: the variant without the in-place handling of candidate-free stretches -- on ordinary sequence it is
+// the faster one (the extra code costs about 7 % even when it never runs); tiles with such a stretch go to the list.
+template <int NT, int C1, int CAP, bool GAPS>
 __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant__ SketchParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
         const Tile T = P.tiles[tile_id];
         // every thread is past the previous tile's write phase (which reads the stretch list); the selection
         // pass that fills it again comes several barriers later
-        if (tid == 0) s_gaps.n = 0;
+        if (GAPS && tid == 0) s_gaps.n = 0;
 
         uint64_t mask = 0;
         bool ok = T.n_pieces == 1;
@@ -208,10 +211,10 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
             sparseC_compact<NT, C1>(tid, mask, off, aoff, m, ma, P, T, S);
             __syncthreads();
             bool bad;
-            flags = sparseS_main<NT>(tid, m, per, P, T, S, &s_gaps, &bad);
+            flags = sparseS_main<NT, GAPS>(tid, m, per, P, T, S, &s_gaps, &bad);
             sparseS_small<NT>(tid, ma, P, T, S);
             hand_over = __syncthreads_or(bad) != 0;
-            if (!hand_over && s_gaps.n != 0) {
+            if (GAPS && !hand_over && s_gaps.n != 0) {
                 // stretches of more than w k-mers without a candidate (low-complexity sequence): their windows
                 // are evaluated directly, in the shared memory of the private lists
                 if (tid == 0) sparseG_sort(&s_gaps);
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
             continue;
         }
         flags = sparse_merge_flags(tid, m, per, flags, S);
-        const uint32_t n_gaps = s_gaps.n;
+        const uint32_t n_gaps = GAPS ? s_gaps.n : 0u;
         const uint32_t cnt = (uint32_t)__popc(flags) + (n_gaps ? sparse_gap_count(tid, m, per, s_gaps) : 0u);
         uint32_t total;
         const uint32_t excl = block_excl_scan<NT>(cnt, s_warp_sums, &total);
@@ -490,7 +493,7 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
     int nt = kc.nt;
     uint32_t grid = dense_grid;
     if (plan.sparse) {
-        kernel = sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap>;
+        kernel = sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap, true>;   // (the first pass picks its variant below)
         smem = sparse_smem_bytes(kSparseNT, kSparseCap);
         nt = kSparseNT;
         SW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -499,14 +502,17 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         if (ctas < 1) fail_runtime("sketch kernel does not fit on this device");
         grid = (uint32_t)std::min<uint64_t>(plan.n_tiles, (uint64_t)sm_count() * ctas);
     }
-    DevBuf<uint32_t> fallback_tiles(plan.sparse ? plan.n_tiles : 0, s, true);
+    // tiles the sparse kernels cannot finish: list 1 (from the first pass) is retried by the variant that settles
+    // candidate-free stretches in place, list 2 (what that one hands over) goes to the dense kernel
+    DevBuf<uint32_t> fallback_tiles(plan.sparse ? plan.n_tiles : 0, s, true), fallback_tiles2(plan.sparse ? plan.n_tiles : 0, s, true);
 
     // [0, n_tiles): per-tile counts (scanned in place into ordered offsets); then the slots
     DevBuf<unsigned long long> tile_info((size_t)plan.n_tiles * 2, s, true);
-    // [0] cursor, [1] scan total, [2] handed-over tiles | their ticket counter << 32,
-    // [3..] one ticket counter (as u32) per launch
+    // [0] cursor, [1] scan total, [2] / [3] tiles on list 1 / 2 | the ticket counter of the launch reading it << 32,
+    // [4] ticket counter of the probe launch, [5..] one ticket counter (as u32) per launch
     const size_t n_launch = chunks && !chunks->empty() ? chunks->size() : 1;
-    DevBuf<unsigned long long> counters(3 + n_launch, s, true);
+    constexpr size_t kFirstTicket = 5;
+    DevBuf<unsigned long long> counters(kFirstTicket + n_launch, s, true);
 
     // expected density 2/(w+1); leave 50 % headroom and re-run with the exact size on overflow
     uint64_t capacity = (uint64_t)((double)plan.n_kmers * 3.0 / ((double)w + 1.0)) + 4096;
@@ -562,37 +568,83 @@ void run_sketch(const uint32_t* d_words, const uint64_t* d_rec_word_off, const D
         P.tile_list = nullptr;
         P.tile_list_n = nullptr;
         cudaEventRecord(ev[0], s);
+        // Which sparse variant runs the first pass: the one without in-place stretch handling is about 6 % faster on
+        // ordinary sequence, but every tile with a candidate-free stretch then costs a second attempt.  A probe over
+        // the first tiles decides (SEQWIN_SPARSE_GAPS = 0 / 1 overrides).
+        uint32_t probe_hi = 0;
+        if (plan.sparse) {
+            const char* force = getenv("SEQWIN_SPARSE_GAPS");
+            bool gaps = force ? atoi(force) != 0 : false;
+            const uint32_t n_probe = std::min<uint32_t>(plan.n_tiles / 16, 8192);
+            if (!force && n_probe >= 1024) {
+                probe_hi = n_probe;
+                if (chunks && !chunks->empty()) {
+                    probe_hi = std::min(probe_hi, (*chunks)[0].tile_hi);
+                    if ((*chunks)[0].ready && attempt == 0) SW_CUDA(cudaStreamWaitEvent(s, (*chunks)[0].ready, 0));
+                }
+                P.tile_lo = 0;
+                P.n_tiles = probe_hi;
+                P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 4);
+                sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap, false><<<std::min(probe_hi, grid), nt, smem, s>>>(P);
+                SW_CUDA(cudaGetLastError());
+                ++out.launches;
+                const unsigned long long* fp = readback_u64(counters.p + 2, 1, s);
+                SW_CUDA(cudaStreamSynchronize(s));
+                gaps = (uint32_t)(*fp & 0xFFFFFFFFull) * 16u > probe_hi;   // more than 1 tile in 16 handed over
+                if (getenv("SEQWIN_DEBUG_SKETCH"))
+                    fprintf(stderr, "[sketch] probe: %u of %u tiles handed over -> %s\n", (unsigned)(*fp & 0xFFFFFFFFull), probe_hi,
+                            gaps ? "stretches settled in the first pass" : "plain first pass");
+            }
+            kernel = gaps ? sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap, true>
+                          : sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap, false>;
+            SW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         for (size_t c = 0; c < n_launch; ++c) {
-            P.tile_lo = 0;
+            P.tile_lo = probe_hi;
+            P.n_tiles = plan.n_tiles;
             if (chunks && !chunks->empty()) {
                 // tiles of one uploaded slice of the packed stream: wait for its H2D copy only
                 const SketchChunk& ch = (*chunks)[c];
                 if (ch.tile_hi <= ch.tile_lo) continue;
                 if (ch.ready && attempt == 0) SW_CUDA(cudaStreamWaitEvent(s, ch.ready, 0));
-                P.tile_lo = ch.tile_lo;
+                P.tile_lo = std::max(ch.tile_lo, probe_hi);
                 P.n_tiles = ch.tile_hi;
+                if (P.n_tiles <= P.tile_lo) continue;
             }
-            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 3 + c);
+            if (P.n_tiles <= P.tile_lo) continue;
+            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + kFirstTicket + c);
             const uint32_t g = (uint32_t)std::min<uint64_t>(P.n_tiles - P.tile_lo, grid);
             kernel<<<g, nt, smem, s>>>(P);
             SW_CUDA(cudaGetLastError());
             ++out.launches;
         }
         if (plan.sparse) {
-            // the tiles the sparse kernel handed over (few; the count stays on the device)
+            // list 1 (few tiles; the counts stay on the device) -> the variant that settles stretches in place ...
             P.tile_lo = 0;
             P.n_tiles = plan.n_tiles;
             P.tile_list = fallback_tiles.p;
-            P.tile_list_n = P.fallback_count;
-            P.tile_counter = P.fallback_count + 1;
+            P.tile_list_n = reinterpret_cast<unsigned int*>(counters.p + 2);
+            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 2) + 1;
+            P.fallback_tiles = fallback_tiles2.p;
+            P.fallback_count = reinterpret_cast<unsigned int*>(counters.p + 3);
+            auto retry = sketch_sparse_kernel<kSparseNT, kSparseC1, kSparseCap, true>;
+            SW_CUDA(cudaFuncSetAttribute(retry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            retry<<<grid, nt, smem, s>>>(P);
+            // ... and what that one hands over (tiles across runs of unhashable bases, very long stretches) -> dense kernel
+            P.tile_list = fallback_tiles2.p;
+            P.tile_list_n = reinterpret_cast<unsigned int*>(counters.p + 3);
+            P.tile_counter = reinterpret_cast<unsigned int*>(counters.p + 3) + 1;
             dense_kernel<<<dense_grid, kc.nt, dense_smem, s>>>(P);
             SW_CUDA(cudaGetLastError());
-            ++out.launches;
+            out.launches += 2;
         }
         cudaEventRecord(ev[1], s);
-        const unsigned long long* tp = readback_u64(counters.p, 1, s);
+        const unsigned long long* tp = readback_u64(counters.p, 4, s);
         SW_CUDA(cudaStreamSynchronize(s));
         total = *tp;
+        if (plan.sparse && getenv("SEQWIN_DEBUG_SKETCH"))
+            fprintf(stderr, "[sketch] %u tiles, %u to the second sparse pass, %u to the dense kernel, %llu minimizers\n", plan.n_tiles,
+                    (unsigned)(tp[2] & 0xFFFFFFFFull), (unsigned)(tp[3] & 0xFFFFFFFFull), total);
         if (total <= capacity) break;
         if (attempt) fail_runtime("sketch output overflow after resize");
         capacity = total;  // low-complexity input: more minimizers than the density estimate

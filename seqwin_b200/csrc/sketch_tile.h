@@ -724,37 +724,40 @@ SW_HD bool sparseA_hash(int tid, const SketchParams& P, const Tile& T, const Spa
 #define SW_LIST_PUSH(h) do { *slot = (h); slot += NT; } while (0)
 #endif
     uint32_t thr = P.cand_hi;
-    uint32_t m_lo = 0, m_hi = 0;
+    uint64_t mask = 0;
     bool ok = true;
     {
         const uint64_t h = fwd + rev;
-        if ((uint32_t)(h >> 32) < thr) { SW_LIST_PUSH(h); m_lo |= 1u; }
+        if ((uint32_t)(h >> 32) < thr) { SW_LIST_PUSH(h); mask |= 1u; }
     }
-#pragma unroll
-    for (int b = 0; b < (C1 - 1 + 15) / 16; ++b) {
+    // 16 rolling steps (one word of bases in, one out) unrolled, the words in a loop: the unrolled body of all
+    // C1 steps would be most of the kernel's instruction footprint
+    constexpr int NB = (C1 - 1 + 15) / 16;
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
         const uint32_t in = fetch16(W, p0 + P.k + 16 * b);
         const uint32_t out = fetch16(W, p0 + 16 * b);
         const uint32_t x = (in & 0x33333333u) | ((out & 0x33333333u) << 2);
         const uint32_t y = ((in >> 2) & 0x33333333u) | (out & 0xCCCCCCCCu);
+        uint32_t m16 = 0;
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
-            const int n = 16 * b + s + 1;
-            if (n < C1) {
-                if (n % (int)kSparseCheck == 0 && n > CAP - (int)kSparseCheck) {
-                    if (slot > slot_limit) { ok = false; thr = 0; }   // stop recording: the tile is recomputed
-                }
-                const uint32_t idx = (((s & 1) ? y : x) >> (4 * (s >> 1))) & 15u;
-                roll_step(fwd, rev, S.tab[idx]);
-                const uint64_t h = fwd + rev;
-                if ((uint32_t)(h >> 32) < thr) {
-                    SW_LIST_PUSH(h);
-                    if (n < 32) m_lo |= 1u << (n & 31); else m_hi |= 1u << (n & 31);
-                }
+            // step n = 16 b + s + 1; the last word may be a partial one
+            if ((C1 - 1) % 16 != 0 && s >= (C1 - 1) % 16 && b == NB - 1) break;
+            if ((s + 1) % (int)kSparseCheck == 0 && 16 * b + s + 1 > CAP - (int)kSparseCheck) {
+                if (slot > slot_limit) { ok = false; thr = 0; }   // stop recording: the tile is recomputed
+            }
+            const uint32_t idx = (((s & 1) ? y : x) >> (4 * (s >> 1))) & 15u;
+            roll_step(fwd, rev, S.tab[idx]);
+            const uint64_t h = fwd + rev;
+            if ((uint32_t)(h >> 32) < thr) {
+                SW_LIST_PUSH(h);
+                m16 |= 1u << s;
             }
         }
+        mask |= (uint64_t)m16 << (16 * b + 1);
     }
 #undef SW_LIST_PUSH
-    uint64_t mask = ((uint64_t)m_hi << 32) | m_lo;
     const uint32_t lim = T.n_kmers - j0;   // k-mers of this chunk that exist
     if (lim < (uint32_t)C1) mask &= (1ULL << lim) - 1;
     *mask_out = mask;
@@ -899,7 +902,7 @@ SW_HD void sparseS_small(int tid, uint32_t ma, const SketchParams& P, const Tile
 // S (main pass): thread owns candidates [1 + tid * per, 1 + (tid + 1) * per) of m; the small ones
 // are skipped.  Returns the selection flags of its other candidates (bit i: candidate
 // 1 + tid * per + i); *bad is set if some window of the tile holds no candidate.
-SW_HD void gap_register(GapList* G, int32_t a, int32_t b, uint32_t owner, bool* bad)
+SW_COLD void gap_register(GapList* G, int32_t a, int32_t b, uint32_t owner, bool* bad)
 {
     if ((uint32_t)(b - a - 1) > kGapLenMax) { *bad = true; return; }
 #if defined(__CUDA_ARCH__)
@@ -913,7 +916,7 @@ SW_HD void gap_register(GapList* G, int32_t a, int32_t b, uint32_t owner, bool* 
     G->owner[i] = (uint16_t)owner;
 }
 
-template <int NT>
+template <int NT, bool GAPS = true>
 SW_HD uint32_t sparseS_main(int tid, uint32_t m, uint32_t per, const SketchParams& P, const Tile& T,
                             const SparseSmem& S, GapList* G, bool* bad)
 {
@@ -928,8 +931,12 @@ SW_HD uint32_t sparseS_main(int tid, uint32_t m, uint32_t per, const SketchParam
         const uint32_t hh = (uint32_t)kj;
         // coverage: no stretch of w k-mers without candidate before this one / after the last one
         const int32_t prev = (int32_t)(S.key[j - 1] >> 32);
-        if (p - prev > w) gap_register(G, prev, p, j, bad);
-        if (j == m && n - p > w) gap_register(G, p, n, m + 1, bad);
+        if (GAPS) {
+            if (p - prev > w) gap_register(G, prev, p, j, bad);
+            if (j == m && n - p > w) gap_register(G, p, n, m + 1, bad);
+        } else if (p - prev > w || (j == m && n - p > w)) {
+            *bad = true;   // this variant leaves such tiles to the one that settles stretches in place
+        }
         if (hh < P.cand_hi_a) continue;
         // every small candidate is smaller: unless w k-mers fit between the nearest ones on either
         // side (about one window in fifty has no small candidate), this one is never selected
@@ -991,7 +998,7 @@ SW_HD GapWs gap_workspace(const SparseSmem& S)
 }
 
 // one thread: order the stretches by position (they were registered in any order)
-SW_HD void sparseG_sort(GapList* G)
+SW_COLD void sparseG_sort(GapList* G)
 {
     for (uint32_t i = 1; i < G->n; ++i)
         for (uint32_t j = i; j > 0 && G->a[j] < G->a[j - 1]; --j) {
@@ -1005,7 +1012,7 @@ SW_HD void sparseG_sort(GapList* G)
 
 // thread t hashes k-mers [16 t, 16 t + 16), [16 (t + NT), ...) ... of stretch gi (one seed, then rolling steps)
 template <int NT>
-SW_HD void sparseG_hash(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const Tile& T, const SparseSmem& S)
+SW_COLD void sparseG_hash(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const Tile& T, const SparseSmem& S)
 {
     const GapWs ws = gap_workspace(S);
     const uint32_t g = (uint32_t)(G.b[gi] - G.a[gi] - 1);
@@ -1026,7 +1033,7 @@ SW_HD void sparseG_hash(int tid, uint32_t gi, const GapList& G, const SketchPara
 
 // thread t evaluates windows t, t + NT, ... of the stretch: rightmost minimum of w consecutive k-mers
 template <int NT>
-SW_HD void sparseG_windows(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const SparseSmem& S)
+SW_COLD void sparseG_windows(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const SparseSmem& S)
 {
     const GapWs ws = gap_workspace(S);
     const uint32_t g = (uint32_t)(G.b[gi] - G.a[gi] - 1), nw = g - P.w + 1;
@@ -1042,7 +1049,7 @@ SW_HD void sparseG_windows(int tid, uint32_t gi, const GapList& G, const SketchP
 }
 
 // one thread: the windows' selections, each once, in position order (minimizer.cpp:41-47)
-SW_HD void sparseG_emit(uint32_t gi, GapList* G, const SketchParams& P, const Tile& T, const SparseSmem& S)
+SW_COLD void sparseG_emit(uint32_t gi, GapList* G, const SketchParams& P, const Tile& T, const SparseSmem& S)
 {
     const GapWs ws = gap_workspace(S);
     const int32_t a = G->a[gi];
@@ -1069,7 +1076,7 @@ SW_HD uint32_t gap_owner_thread(const GapList& G, uint32_t gi, uint32_t m, uint3
     return (j - 1) / per;
 }
 
-SW_HD uint32_t sparse_gap_count(int tid, uint32_t m, uint32_t per, const GapList& G)
+SW_COLD uint32_t sparse_gap_count(int tid, uint32_t m, uint32_t per, const GapList& G)
 {
     uint32_t c = 0;
     for (uint32_t gi = 0; gi < G.n; ++gi)
@@ -1092,7 +1099,7 @@ SW_HD void gap_write(uint32_t gi, unsigned long long& slot, const GapList& G, co
 
 // D with stretches: the thread's candidates in order, each preceded by the minimizers of the stretch before it
 template <int NT>
-SW_HD void sparseD_write_gaps(int tid, uint32_t m, uint32_t per, uint32_t flags, unsigned long long slot, const GapList& G,
+SW_COLD void sparseD_write_gaps(int tid, uint32_t m, uint32_t per, uint32_t flags, unsigned long long slot, const GapList& G,
                               const SketchParams& P, const Tile& T, const SparseSmem& S)
 {
     const Piece pc = P.pieces[T.piece_lo];
