@@ -396,11 +396,21 @@ def main():
     ag_t = traffic.get("aggregation")
     path_bytes = n_bases_local / 4 + 40 * M_loc + 40 * Un_loc + 24 * Ue_loc
     local_ms = float(np.mean([s.get("local_build_ms", s["total_ms"]) for s in stages]))
-    roofline = {"bound": "int", "kernel": kernel_name, "achieved": int_ach, "peak": ip["lop3_Tops"], "unit": "Tlane-op/s",
-                "frac": int_ach / ip["lop3_Tops"], "traffic": sketch_traffic,
-                "peak_source": "measured in this run: dependent LOP3 chains on every SM (sw_measure_int_peak, csrc/diag.cu)",
+    # The model counts integer instructions of any kind, so the denominator is the measured integer ISSUE rate (four
+    # schedulers x 32 lanes per clock: what independent IADD chains reach, since adds go down two pipes).  LOP3 / SHF /
+    # ISETP -- most of a hash step -- share ONE of those pipes at half that rate: the ALU-pipe view (ncu) is the
+    # tighter bound and is reported beside it.
+    roofline = {"bound": "int", "kernel": kernel_name, "achieved": int_ach, "peak": ip["iadd_Tops"], "unit": "Tlane-op/s",
+                "frac": int_ach / ip["iadd_Tops"], "traffic": sketch_traffic,
+                "peak_source": "measured in this run: integer issue rate, independent IADD chains on every SM "
+                               "(sw_measure_int_peak, csrc/diag.cu)",
                 "algorithmic_ops_per_launch": int_alg, "kernel_ms": sketch_ms, "int_peaks_measured": ip,
                 "model": "I_alg = 45*N + 12*M lane-ops (SURVEY 8d)",
+                "alu_pipe_view": {"peak_lop3_Tops": ip["lop3_Tops"],
+                                  "busy_pct_ncu": (sk_t or {}).get("alu_pipe_busy_pct"),
+                                  "issue_slots_busy_pct_ncu": (sk_t or {}).get("issue_active_pct"),
+                                  "what": "LOP3 / SHF / ISETP issue on one pipe at half the issue rate; ncu capture of this "
+                                          "round (profiles/r2_traffic.json)"},
                 "hbm_view": {"achieved": sketch_bytes / (sketch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": sketch_bytes / (sketch_ms * 1e-3) / 1e9 / hbm_peak,
                              "algorithmic_bytes_per_launch": sketch_bytes, "peak_source": peak_src},

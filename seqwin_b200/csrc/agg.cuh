@@ -499,11 +499,12 @@ __global__ void __launch_bounds__(kNT, 4) group_place_kernel(PlaceArgs a, Out o)
 constexpr int kRankBits = 10;                    // node rank inside a bucket
 static_assert((1 << kRankBits) == kMaxDistinct, "ranks of a bucket's nodes fit kRankBits");
 
-template <int ESB, int EI>
+template <int ESB, int EI, int NTE = kNT>
 struct BucketEdgeSmem {
+    static constexpr int kNWE = NTE / 32;
     static constexpr int kES = 1 << ESB;                 // pair table slots
     static constexpr int kEMax = kES / 2;                // distinct pairs a bucket may hold
-    static constexpr int kChunkItems = kNT * EI;
+    static constexpr int kChunkItems = NTE * EI;
     static constexpr int kSetSlots = 4 * kChunkItems;    // <= 2 records per item, load <= 0.5
     unsigned long long t_key[kES];                       // second << 10 | rank
     uint32_t t_w[kES];                                   // distinct assemblies of the pair
@@ -521,10 +522,10 @@ struct BucketEdgeSmem {
         } b;
     } u;
     // the chunk's records, dense per warp (half of the 2 * EI slots of an item are empty on average)
-    unsigned long long st_sec[kNW][2 * EI * 32];         // second
-    unsigned long long st_ra[kNW][2 * EI * 32];          // node rank << 32 | assembly
-    uint16_t st_slot[kNW][2 * EI * 32];                  // table slot (kES: none)
-    uint32_t wsum[kNW];
+    unsigned long long st_sec[kNWE][2 * EI * 32];         // second
+    unsigned long long st_ra[kNWE][2 * EI * 32];          // node rank << 32 | assembly
+    uint16_t st_slot[kNWE][2 * EI * 32];                  // table slot (kES: none)
+    uint32_t wsum[kNWE];
     uint32_t n_distinct, n_records, bad;
 };
 
@@ -583,10 +584,12 @@ struct BucketEdgeArgs {
     uint32_t* bucket_rec;                 // records (owned pairs) of the bucket
 };
 
-template <int ESB, int EI>
-__global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs a)
+template <int ESB, int EI, int NTE = kNT>
+__global__ void __launch_bounds__(NTE) bucket_edges_kernel(const BucketEdgeArgs a)
 {
-    using Smem = BucketEdgeSmem<ESB, EI>;
+    using Smem = BucketEdgeSmem<ESB, EI, NTE>;
+    constexpr int kNWE = NTE / 32;
+    static_assert(kMaxDistinct % NTE == 0, "the rank counts are scanned in equal shares");
     SW_DYN_SMEM(Smem, sm);
     constexpr uint32_t kES = Smem::kES;
     const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -599,12 +602,12 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
         return;
     }
     const bool multi = n > (uint32_t)Smem::kChunkItems;
-    for (uint32_t s = tid; s < kES; s += kNT) {
+    for (uint32_t s = tid; s < kES; s += NTE) {
         sm.t_key[s] = kEmptyKey;
         sm.t_w[s] = 0;
         if (multi) sm.u.a.t_last[s] = 0;
     }
-    for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += kNT) sm.u.a.set[s] = kEmptyKey;
+    for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += NTE) sm.u.a.set[s] = kEmptyKey;
     if (tid == 0) sm.n_distinct = sm.n_records = sm.bad = 0;
     __syncthreads();
     static_assert(Smem::kES < 65536, "slots are staged as 16-bit values");
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
     auto load_chunk = [&](uint32_t c0) {
 #pragma unroll
         for (int q = 0; q < EI; ++q) {
-            const uint32_t i = c0 + tid + q * kNT;
+            const uint32_t i = c0 + tid + q * NTE;
             const bool have = i < n;
             nsec[2 * q] = have ? a.nb_prev[bs + i] : 0;
             nsec[2 * q + 1] = have ? a.nb_next[bs + i] : 0;
@@ -694,7 +697,7 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
         }
         if (sm.n_distinct > a.max_distinct) skip = true;   // uniform (read between the barriers)
         if (more) {
-            for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += kNT) sm.u.a.set[s] = kEmptyKey;
+            for (uint32_t s = tid; s < (uint32_t)Smem::kSetSlots; s += NTE) sm.u.a.set[s] = kEmptyKey;
             __syncthreads();
         }
     }
@@ -710,16 +713,17 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
     }
     // (rank, second) order: counting sort on the rank into dk[] (over the dead set), then every pair is ranked
     // against the other pairs of its node
-    for (uint32_t r = tid; r <= (uint32_t)kMaxDistinct; r += kNT) sm.u.b.r_start[r] = 0;
+    for (uint32_t r = tid; r <= (uint32_t)kMaxDistinct; r += NTE) sm.u.b.r_start[r] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < D; i += kNT)
+    for (uint32_t i = tid; i < D; i += NTE)
         atomicAdd(&sm.u.b.r_start[(uint32_t)sm.t_key[sm.dlist[i]] & (kMaxDistinct - 1)], 1u);
     __syncthreads();
-    {   // exclusive scan of the kMaxDistinct counts, four consecutive ranks per thread
-        uint32_t cnt[4], sum4 = 0;
+    {   // exclusive scan of the kMaxDistinct counts, kPer consecutive ranks per thread
+        constexpr int kPer = kMaxDistinct / NTE;
+        uint32_t cnt[kPer], sum4 = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            cnt[q] = sm.u.b.r_start[tid * 4 + q];
+        for (int q = 0; q < kPer; ++q) {
+            cnt[q] = sm.u.b.r_start[tid * kPer + q];
             sum4 += cnt[q];
         }
         uint32_t inc = sum4;
@@ -732,18 +736,18 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
         __syncthreads();
         uint32_t run = inc - sum4;
 #pragma unroll
-        for (int w = 0; w < kNW; ++w)
+        for (int w = 0; w < kNWE; ++w)
             if ((uint32_t)w < wid) run += sm.wsum[w];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            sm.u.b.r_start[tid * 4 + q] = run;
-            sm.u.b.cursor[tid * 4 + q] = run;
+        for (int q = 0; q < kPer; ++q) {
+            sm.u.b.r_start[tid * kPer + q] = run;
+            sm.u.b.cursor[tid * kPer + q] = run;
             run += cnt[q];
         }
-        if (tid == kNT - 1) sm.u.b.r_start[kMaxDistinct] = run;
+        if (tid == NTE - 1) sm.u.b.r_start[kMaxDistinct] = run;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < D; i += kNT) {
+    for (uint32_t i = tid; i < D; i += NTE) {
         const uint32_t s = sm.dlist[i];
         const unsigned long long key = sm.t_key[s];
         const uint32_t at = atomicAdd(&sm.u.b.cursor[(uint32_t)key & (kMaxDistinct - 1)], 1u);
@@ -752,7 +756,7 @@ __global__ void __launch_bounds__(kNT) bucket_edges_kernel(const BucketEdgeArgs 
     }
     __syncthreads();
     const uint64_t out0 = 2ull * bs;
-    for (uint32_t i = tid; i < D; i += kNT) {
+    for (uint32_t i = tid; i < D; i += NTE) {
         const unsigned long long second = sm.u.b.dk[i];
         const uint32_t s = sm.u.b.dslot[i];
         const uint32_t r = (uint32_t)sm.t_key[s] & (kMaxDistinct - 1);

@@ -152,7 +152,7 @@ struct Arena {
         size_t held = 0;
         for (auto& sl : slabs) held += sl.bytes;
         size_t free_b = 0, total_b = 0;
-        if (held && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && held > total_b / 4) {
+        if (held > ((size_t)16 << 30) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && held > total_b / 4) {
             // a build that needed a large part of the device: the next one may be shaped differently (outputs come
             // from the stream-ordered pool), so the slabs go back to the driver instead of staying reserved
             cudaDeviceSynchronize();

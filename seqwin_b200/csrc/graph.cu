@@ -583,21 +583,23 @@ double estimate_items_per_key(const uint64_t* keys, uint64_t n, unsigned long lo
 // mix) or a hash is 0 (the "no neighbour" marker); the caller then runs the sort-based path.
 // table geometry of the edge kernel: (slot bits, items per thread and chunk); SEQWIN_AGG_EDGE_GEOM picks one
 struct EdgeGeom {
-    int slot_bits, items;
+    int slot_bits, items, threads;
     uint32_t e_max;
     size_t smem;
     void (*kernel)(const agg::BucketEdgeArgs);
 };
-template <int ESB, int EI>
+template <int ESB, int EI, int NTE>
 EdgeGeom edge_geom()
 {
-    return EdgeGeom{ESB, EI, (uint32_t)agg::BucketEdgeSmem<ESB, EI>::kEMax, sizeof(agg::BucketEdgeSmem<ESB, EI>),
-                    agg::bucket_edges_kernel<ESB, EI>};
+    return EdgeGeom{ESB, EI, NTE, (uint32_t)agg::BucketEdgeSmem<ESB, EI, NTE>::kEMax, sizeof(agg::BucketEdgeSmem<ESB, EI, NTE>),
+                    agg::bucket_edges_kernel<ESB, EI, NTE>};
 }
+// [0] the small table, [1] the large one (choose_bucket_bits); the rest are tuning variants (SEQWIN_AGG_EDGE_GEOM = index + 1)
 const EdgeGeom& edge_geom_at(uint32_t i)
 {
-    static const EdgeGeom geoms[] = {edge_geom<11, 2>(), edge_geom<12, 2>()};
-    return geoms[i < 2 ? i : 0];
+    static const EdgeGeom geoms[] = {edge_geom<11, 1, 512>(), edge_geom<12, 1, 512>(), edge_geom<11, 2, 256>(),
+                                     edge_geom<12, 2, 256>()};
+    return geoms[i < 4 ? i : 0];
 }
 
 // Bucket bits and edge-table geometry.  A bucket must hold few enough distinct hashes for the node table (about
@@ -788,7 +790,7 @@ void aggregate_buckets(const SliceJob& J, uint16_t* item_rank, const uint32_t* d
     ea.bucket_e = bucket_e.p;
     ea.bucket_rec = bucket_rec.p;
     SW_CUDA(cudaFuncSetAttribute(eg.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg.smem));
-    eg.kernel<<<(uint32_t)n_buckets, kNT, eg.smem, s>>>(ea);
+    eg.kernel<<<(uint32_t)n_buckets, eg.threads, eg.smem, s>>>(ea);
     SW_CUDA(cudaMemsetAsync(etot.p, 0, 4 * sizeof(unsigned long long), s));
     SW_CUDA(cudaMemsetAsync(e64.p + n_buckets, 0, sizeof(unsigned long long), s));
     SW_CUDA(cudaMemsetAsync(side_rec.p + n_buckets, 0, sizeof(unsigned long long), s));
@@ -880,15 +882,21 @@ uint32_t choose_slices(uint64_t M, double per_node, double per_edge, bool scored
         while (h < forced && h < 64) h <<= 1;
         return h;
     }
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
-    const double avail = 0.9 * ((double)free_b + (double)arena_free_bytes());
     const double outputs = 8.0 * (double)M + 1.1 * (40.0 * (double)M / per_node + 24.0 * (double)M / per_edge);
+    const double per_item = (64.0 + 2.0 + (scored ? 4.0 : 0.0) + 2.0) * 1.25;
     uint32_t h = low_memory() ? 4 : 1;
-    for (; h < 64; h <<= 1) {
-        const double scratch = (64.0 + 2.0 + (scored ? 4.0 : 0.0) + 2.0) * 1.25 * (double)M / (double)h;
-        if (outputs + scratch <= avail) break;
-    }
+    // builds that need less than 40 % of the device do not ask the driver (cudaMemGetInfo costs milliseconds next to a
+    // large memory pool): that much is assumed to fit beside the stream and the packed input
+    static const double device_bytes = [] {
+        size_t f = 0, t = 0;
+        return cudaMemGetInfo(&f, &t) == cudaSuccess ? (double)t : 0.0;
+    }();
+    if (outputs + per_item * (double)M / (double)h <= 0.4 * device_bytes) return h;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return h;
+    const double avail = 0.9 * ((double)free_b + (double)arena_free_bytes());
+    for (; h < 64; h <<= 1)
+        if (outputs + per_item * (double)M / (double)h <= avail) break;
     return h;
 }
 
