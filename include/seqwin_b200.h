@@ -184,6 +184,31 @@ int sw_dist_merge(const void* recv_nodes, const uint64_t* node_counts, const voi
 int sw_dist_merge_edges(sw_graph* g, const void* recv_edges, const uint64_t* edge_counts, uint32_t n_src,
                         uint32_t* launches);
 
+/* ---- multi-GPU, routed: minimizer records travel to the owner of their hash range BEFORE they are aggregated --------
+ * ("all-to-all of minimizer records range-partitioned by the top bits of h1 ... the owner then reduces
+ * its key range").  A record carries the hashes of the stream neighbours whose adjacent pair it owns -- the pair
+ * belongs to the minimizer with the smaller hash --, so the owner of a hash range has everything it needs for the
+ * nodes of the range AND the edges they own: no merge of per-shard graphs (cpp/src/seqwin/build_internals.cpp:295-392)
+ * is left. */
+typedef struct sw_routed sw_routed;
+/* Sketch a device-resident shard (global record indices start at rec_base) and partition its records, stably, on the
+ * top byte of h1. */
+int sw_dev_sketch_route(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_routed** out, sw_stage_times* t);
+/* Device pointers of the four record arrays (n 64-bit words each: h1 | pos + record << 32 | owned previous | owned
+ * next neighbour hash, 0 = none), byte_off[257] = first record of every top-byte value, stats = {k-mers per distinct
+ * hash, adjacent pairs per distinct pair} as sampled on this shard.  Any output may be NULL. */
+int sw_routed_info(const sw_routed* r, void** keys, void** vals, void** prev, void** next, uint64_t* n, uint64_t* byte_off,
+                   double* stats);
+void sw_routed_free(sw_routed* r);
+/* Nodes, k-mers and edges (scored when is_targets != NULL) of the records whose h1 has its top byte in
+ * [byte_lo, byte_hi): the four device arrays hold exactly those records of ALL shards, concatenated in shard order
+ * (each shard's in its own stream order).  record_offsets / is_targets describe all assemblies of all shards
+ * (global record indices).  The key array is used as scratch.  Concatenating the owners' graphs in range order gives
+ * the reference graph. */
+int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const void* next, uint64_t n, uint32_t byte_lo,
+                     uint32_t byte_hi, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
+                     size_t n_assemblies, double pairs_per_edge, sw_graph** out, sw_stage_times* t);
+
 /* ---- first consumers of the graph, on the device-resident arrays ------------ */
 /* Edge-weight filter + isolated-node removal, the array part of _filter_edges_and_nodes
  * (src/seqwin/kmers.py:132-162): keeps edges with weight > weight_th and the nodes that are an

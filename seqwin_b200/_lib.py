@@ -65,6 +65,11 @@ PROTOTYPES = {
     "sw_dist_merge_edges": (_I, [_P, _P, _P, _U32, C.POINTER(_U32)]),
     "sw_graph_count_sums": (_I, [_P, _P]),
     "sw_mem_stats": (_I, [C.POINTER(C.c_uint64)]),
+    "sw_dev_sketch_route": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
+    "sw_routed_info": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), _P, _P]),
+    "sw_routed_free": (None, [_P]),
+    "sw_dev_aggregate": (_I, [_P, _P, _P, _P, C.c_uint64, _U32, _U32, _P, _SZ, _P, _SZ, C.c_double, C.POINTER(_P),
+                              C.POINTER(StageTimes)]),
     "sw_set_low_memory": (_I, [_I]),
     "sw_trim_memory": (_I, []),
     "sw_measure_int_peak": (_I, [C.POINTER(C.c_double)]),

@@ -873,6 +873,133 @@ int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_
     return guarded([&] { *out = dev_build(*d, k, w, t, rec_base, is_targets, n_assemblies, /*shard=*/true); });
 }
 
+struct sw_routed {
+    sw::RoutedStream rs;
+    cudaStream_t stream = nullptr;
+};
+
+int sw_dev_sketch_route(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_routed** out, sw_stage_times* t)
+{
+    return guarded([&] {
+        init_device_once();
+        check_kw(k, w);
+        cudaStream_t s = d->stream;
+        arena_reset();
+        auto r = std::make_unique<sw_routed>();
+        r->stream = s;
+        cudaEvent_t e0, e1, e2;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventCreate(&e2);
+        struct EvGuard {
+            cudaEvent_t &a, &b, &c;
+            ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); }
+        } guard{e0, e1, e2};
+        cudaEventRecord(e0, s);
+        const auto host_t0 = std::chrono::steady_clock::now();
+        DevPlan plan = make_plan(*d, k, w, s);
+        const float plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        SketchStream st;
+        run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, rec_base, s, st);
+        cudaEventRecord(e1, s);
+        route_stream(st, s, r->rs);
+        cudaEventRecord(e2, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        if (r->rs.zero_key) fail_runtime("a minimizer hash is 0: the routed multi-GPU build cannot mark 'no neighbour' (use the merge-based one)");
+        if (t) {
+            memset(t, 0, sizeof(*t));
+            cudaEventElapsedTime(&t->sketch_ms, e0, e1);
+            cudaEventElapsedTime(&t->sort_nodes_ms, e1, e2);   // the routing pass
+            cudaEventElapsedTime(&t->total_ms, e0, e2);
+            t->plan_ms = plan_ms;
+            t->sketch_kernel_ms = st.kernel_ms;
+            t->reorder_ms = st.reorder_ms;
+            t->n_bases = d->meta.n_bases;
+            t->n_kmers = st.n;
+            t->n_tiles = plan.n_tiles;
+            t->sketch_launches = st.launches;
+            t->total_launches = st.launches + r->rs.launches;
+        }
+        *out = r.release();
+    });
+}
+
+int sw_routed_info(const sw_routed* r, void** keys, void** vals, void** prev, void** next, uint64_t* n, uint64_t* byte_off,
+                   double* stats)
+{
+    const uint64_t M = r->rs.n;
+    if (keys) *keys = r->rs.set.p;
+    if (vals) *vals = r->rs.set.p + M;
+    if (prev) *prev = r->rs.set.p + 2 * M;
+    if (next) *next = r->rs.set.p + 3 * M;
+    if (n) *n = M;
+    if (byte_off) std::copy(r->rs.byte_off, r->rs.byte_off + 257, byte_off);
+    if (stats) {
+        stats[0] = r->rs.items_per_key;
+        stats[1] = r->rs.pairs_per_edge;
+    }
+    return SW_OK;
+}
+
+void sw_routed_free(sw_routed* r)
+{
+    if (!r) return;
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    delete r;
+}
+
+int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const void* next, uint64_t n, uint32_t byte_lo,
+                     uint32_t byte_hi, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
+                     size_t n_assemblies, double pairs_per_edge, sw_graph** out, sw_stage_times* t)
+{
+    return guarded([&] {
+        init_device_once();
+        if (byte_lo > byte_hi || byte_hi > 256) fail_value("hash range must be 0 <= byte_lo <= byte_hi <= 256");
+        if (n_offsets == 0 || record_offsets[0] != 0) fail_value("record_offsets must start with 0");
+        for (size_t i = 0; i + 1 < n_offsets; ++i)
+            if (record_offsets[i + 1] < record_offsets[i]) fail_value("record_offsets must be nondecreasing");
+        cudaStream_t s = lib_stream();
+        arena_reset();
+        const std::vector<uint32_t> offsets(record_offsets, record_offsets + n_offsets);
+        const std::vector<uint32_t> ra = record_assembly_map(offsets);
+        DevBuf<uint32_t> d_ra(ra.size(), s, true);
+        if (!ra.empty()) SW_CUDA(cudaMemcpyAsync(d_ra.p, ra.data(), ra.size() * 4, cudaMemcpyHostToDevice, s));
+        std::unique_ptr<ScoreUpload> score;
+        if (is_targets) score = std::make_unique<ScoreUpload>(is_targets, n_assemblies, n_offsets - 1, s, /*shard=*/false);
+        auto g = std::make_unique<sw_graph>();
+        g->stream = s;
+        g->record_offsets = offsets;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+        const NbrBuffers in{const_cast<uint64_t*>(static_cast<const uint64_t*>(keys)), const_cast<uint64_t*>(static_cast<const uint64_t*>(vals)),
+                            const_cast<uint64_t*>(static_cast<const uint64_t*>(prev)), const_cast<uint64_t*>(static_cast<const uint64_t*>(next))};
+        GraphTimes gt;
+        aggregate_range(in, n, byte_lo, byte_hi, d_ra.p, s, g->dev, &gt, score ? &score->args : nullptr, pairs_per_edge);
+        cudaEventRecord(e1, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        g->on_device = true;
+        g->n_kmers = g->dev.n_kmers;
+        g->n_nodes = g->dev.n_nodes;
+        g->n_edges = g->dev.n_edges;
+        if (t) {
+            memset(t, 0, sizeof(*t));
+            cudaEventElapsedTime(&t->total_ms, e0, e1);
+            t->sort_nodes_ms = gt.sort_nodes_ms;
+            t->nodes_ms = gt.nodes_ms;
+            t->edges_ms = gt.edges_ms;
+            t->n_kmers = g->dev.n_kmers;
+            t->n_nodes = g->dev.n_nodes;
+            t->n_edges = g->dev.n_edges;
+            t->total_launches = gt.launches;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *out = g.release();
+    });
+}
+
 int sw_graph_finish_penalty(sw_graph* g, uint64_t n_targets, uint64_t n_non_targets)
 {
     return guarded([&] {

@@ -157,7 +157,8 @@ uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, in
 // first pass derives the two arrays from it (*d_zero_key is set if a key is 0: the marker would be ambiguous and
 // the caller takes the sort-based path); otherwise `in` already holds all four arrays and (keys, vals) are not
 // read.  A / B are the ping-pong sets (n entries per array; `in` may be one of them) and *out points at the set
-// holding the result.  Returns the number of kernels launched; no host synchronisation.
+// holding the result.  key_bias is subtracted from every key before its digits are taken (the items of a key range:
+// its first key).  Returns the number of kernels launched; no host synchronisation.
 struct NbrBuffers {
     uint64_t* keys;
     uint64_t* vals;
@@ -166,7 +167,7 @@ struct NbrBuffers {
 };
 uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const NbrBuffers* in, uint64_t n, int lo_bit, int n_bits,
                              const NbrBuffers& A, const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out,
-                             unsigned int* d_zero_key);
+                             unsigned int* d_zero_key, uint64_t key_bias = 0);
 
 // ---- graph stage ------------------------------------------------------------------------------
 struct DevGraph {
@@ -195,6 +196,25 @@ void finish_penalty(sw_node* d_nodes, uint64_t n_nodes, double inv_t, double inv
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                  GraphTimes* times, const std::function<void()>* after_nodes = nullptr,
                  const ScoreArgs* score = nullptr);
+
+// ---- multi-GPU: route the stream to the owners of its hash ranges, aggregate a range (graph.cu) -------------------
+// The minimizer stream of a shard with the owned neighbour hashes of every item (NbrBuffers), stably partitioned on
+// the top byte of h1: byte_off[b] = first item whose top byte is >= b.  The four arrays are one pool allocation of
+// 4 n words (keys | vals | prev | next), alive until the caller frees it: slices of it travel to the owners.
+struct RoutedStream {
+    DevBuf<uint64_t> set;
+    uint64_t n = 0;
+    unsigned long long byte_off[257] = {};
+    bool zero_key = false;          // a hash is 0: the "no neighbour" marker is ambiguous, the caller must not go on
+    double items_per_key = 0, pairs_per_edge = 0;
+    uint32_t launches = 0;
+};
+void route_stream(SketchStream& st, cudaStream_t s, RoutedStream& out);
+// Nodes, k-mers and edges of the items whose h1 has its top byte in [byte_lo, byte_hi) -- `in` holds exactly those,
+// in global stream order (ties between sources: source order) -- with the single-GPU bucket kernels.  Fails loudly
+// if a node bucket overflows (there is no sort-based path for a range).
+void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_t byte_hi, const uint32_t* d_rec_asm,
+                     cudaStream_t s, DevGraph& g, GraphTimes* times, const ScoreArgs* score, double pairs_per_edge);
 
 // ---- consumers of a device-resident graph (filter.cu), in place on g ---------------------------------
 // edges with weight > weight_th and the nodes that keep an edge (kmers.py:132-162); k-mers untouched

@@ -131,6 +131,11 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp)
     return t;
 }
 
+__global__ void widen_u32_kernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
+}
+
 __global__ void iota_kernel(uint32_t* v, uint64_t n)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -1054,6 +1059,89 @@ bool build_graph_bucketed(SketchStream& st, const uint32_t* d_rec_asm, uint32_t 
 }
 
 }  // namespace
+
+void route_stream(SketchStream& st, cudaStream_t s, RoutedStream& out)
+{
+    using namespace agg;
+    const uint64_t M = st.n;
+    out.n = M;
+    out.items_per_key = st.items_per_key;
+    out.pairs_per_edge = st.pairs_per_edge;
+    out.set.alloc(4 * M, s);
+    std::fill(out.byte_off, out.byte_off + 257, 0ull);
+    if (M == 0) return;
+    if (M > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers on one device");
+    const NbrBuffers A{out.set.p, out.set.p + M, out.set.p + 2 * M, out.set.p + 3 * M};
+    DevBuf<unsigned long long> flag(1, s, true);
+    SW_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(unsigned long long), s));
+    const NbrBuffers* R = nullptr;
+    out.launches += radix_partition_nbr(st.keys.p, st.vals.p, nullptr, M, 56, 8, A, A, s, &R, reinterpret_cast<unsigned int*>(flag.p));
+    DevBuf<uint32_t> start(257, s, true);
+    DevBuf<unsigned long long> start64(257, s, true);
+    bucket_search_kernel<<<2, 256, 0, s>>>(R->keys, M, 56, 256, start.p);
+    widen_u32_kernel<<<2, 256, 0, s>>>(start.p, 257, start64.p);
+    SW_CUDA(cudaGetLastError());
+    out.launches += 2;
+    const unsigned long long* h = readback_u64(start64.p, 257, s);
+    const unsigned long long* hz = readback_u64(flag.p, 1, s);
+    SW_CUDA(cudaStreamSynchronize(s));
+    std::copy(h, h + 257, out.byte_off);
+    out.zero_key = (*hz & 0xFFFFFFFFull) != 0;
+}
+
+void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_t byte_hi, const uint32_t* d_rec_asm,
+                     cudaStream_t s, DevGraph& g, GraphTimes* times, const ScoreArgs* score, double pairs_per_edge)
+{
+    using namespace agg;
+    GraphTimes tm;
+    g.n_kmers = n;
+    g.n_nodes = g.n_edges = 0;
+    if (n == 0 || byte_hi <= byte_lo) {
+        g.kmers.alloc(0, s);
+        g.nodes.alloc(0, s);
+        g.edges.alloc(0, s);
+        if (times) *times = tm;
+        return;
+    }
+    if (n > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers in one hash range");
+    EventTimer timer(s);
+    timer.start();
+    DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
+    const double per_node = estimate_items_per_key(in.keys, n, sample_set.p, sample_out.p, s);
+    // bucket bits as if the whole hash space were this dense; at least the 8 bits the range is cut on
+    const uint32_t width = byte_hi - byte_lo;
+    const EdgeGeom* egp = nullptr;
+    int P = choose_bucket_bits((uint64_t)((double)n * 256.0 / (double)width), per_node, pairs_per_edge > 0 ? pairs_per_edge : 1.0, &egp);
+    if (const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0)) P = partition_bits((uint64_t)((double)n * 256.0 / (double)width), fixed_nb);
+    P = std::max(P, 8);
+    const int key_bits = 64 - P;
+    int top_bits = 0;
+    while ((1u << top_bits) < width) ++top_bits;
+    DevBuf<uint64_t> setA(4 * n, s, true), setB(4 * n, s, true);
+    const NbrBuffers A{setA.p, setA.p + n, setA.p + 2 * n, setA.p + 3 * n};
+    const NbrBuffers B{setB.p, setB.p + n, setB.p + 2 * n, setB.p + 3 * n};
+    DevBuf<uint16_t> item_rank(n, s, true);
+    DevBuf<unsigned long long> tot(4, s, true);
+    SW_CUDA(cudaMemsetAsync(tot.p, 0, 4 * sizeof(unsigned long long), s));
+    const NbrBuffers* R = nullptr;
+    tm.launches += 1 + radix_partition_nbr(nullptr, nullptr, &in, n, key_bits, P - 8 + top_bits, A, B, s, &R, nullptr,
+                                           (uint64_t)byte_lo << 56);
+    const NbrBuffers* Dd = R == &A ? &B : &A;
+    if (R == &in) Dd = &A;   // no pass ran (one bucket): the input is the result, any set is free
+    SliceJob J{};
+    J.R = R;
+    J.Dd = Dd;
+    J.n = n;
+    J.n_buckets = (uint64_t)width << (P - 8);
+    J.bucket0 = (uint64_t)byte_lo << (P - 8);
+    J.key_bits = key_bits;
+    J.exact = true;
+    bool fallback = false;
+    uint64_t nn = 0, ne = 0;
+    aggregate_buckets(J, item_rank.p, d_rec_asm, 0, s, g, tm, timer, *egp, score, nullptr, tot.p, &nn, &ne, &fallback);
+    if (fallback) fail_runtime("a node bucket of the hash range overflowed (more distinct hashes than its table takes)");
+    if (times) *times = tm;
+}
 
 void build_graph(SketchStream& st, const uint32_t* d_rec_asm, uint32_t rec_base, cudaStream_t s, DevGraph& g,
                  GraphTimes* times, const std::function<void()>* after_nodes, const ScoreArgs* score)

@@ -32,6 +32,7 @@ struct RadixPasses {
     int n;
     int shift[kMaxPasses];
     int bits[kMaxPasses];
+    uint64_t bias;   // subtracted from every key before its digits are taken (a partition of a key RANGE)
 };
 
 constexpr unsigned long long kStAgg = 1ULL << 62;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restr
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t key = keys[i];
+        const uint64_t key = keys[i] - ps.bias;
         for (int p = 0; p < ps.n; ++p)
             atomicAdd(&sh[p][(key >> ps.shift[p]) & ((1u << ps.bits[p]) - 1u)], 1u);
     }
@@ -116,6 +117,7 @@ struct NbrArrays {
     const uint64_t* in_b = nullptr;
     uint64_t* out_a = nullptr;
     uint64_t* out_b = nullptr;
+    uint64_t key_bias = 0;           // subtracted from a key before its digit is taken
     uint64_t n_total = 0;            // gen: items of the whole stream (neighbours across tile borders)
     unsigned int* zero_key = nullptr;   // gen: set when a key is 0 (the "not owned" marker would be ambiguous)
 };
@@ -151,7 +153,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const bool valid = FULL || wofs + i * 32 < n_valid;
-        const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+        const uint32_t d = (uint32_t)((key[i] - nb.key_bias) >> shift) & dmask;
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x1FFu);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -205,7 +207,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         if (FULL || wofs + i * 32 < n_valid) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+            const uint32_t d = (uint32_t)((key[i] - nb.key_bias) >> shift) & dmask;
             rank[i] += sm.whist[wid][d];
             s_buf[rank[i]] = key[i];
         }
@@ -242,7 +244,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
         if ((i & 3) == 0) dig[i >> 2] = 0;
         if (FULL || p < n_valid) {
             const uint64_t k2 = s_buf[p];
-            const uint32_t d = (uint32_t)(k2 >> shift) & dmask;
+            const uint32_t d = (uint32_t)((k2 - nb.key_bias) >> shift) & dmask;
             dig[i >> 2] |= d << (8 * (i & 3));
             kout[sm.dbase[d] + p] = k2;
         }
@@ -434,10 +436,11 @@ uint32_t radix_partition_top(const uint64_t* keys, const V* vals, uint64_t n, in
 // keys share a digit.
 uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const NbrBuffers* in, uint64_t n, int lo_bit, int n_bits,
                              const NbrBuffers& A, const NbrBuffers& B, cudaStream_t s, const NbrBuffers** out,
-                             unsigned int* d_zero_key)
+                             unsigned int* d_zero_key, uint64_t key_bias)
 {
     using V = unsigned long long;
     RadixPasses ps{};
+    ps.bias = key_bias;
     const int np = n_bits > 0 ? (n_bits + kRadixBits - 1) / kRadixBits : (in ? 0 : 1);
     int lo = lo_bit;
     for (int p = 0; p < np; ++p) {
@@ -475,6 +478,7 @@ uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const N
         SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
         SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
         NbrArrays nb;
+        nb.key_bias = key_bias;
         nb.out_a = dst->prev;
         nb.out_b = dst->next;
         if (src == nullptr) {

@@ -1,20 +1,26 @@
 """Multi-GPU graph build: one process per GPU, genomes sharded, hash ranges owned.
 
-    rank r:  shard of assemblies --(single-GPU kernels)--> local graph (global record indices)
-             cut the sorted node / k-mer / edge arrays at the hash boundaries i * 2^64 / P
-             all-to-all the slices (NCCL over NVLink; torch.distributed is only the plumbing)
-             merge what arrived for hash range r  (csrc/dist.cu, mirrors merge_thread_graphs,
-             cpp/src/seqwin/build_internals.cpp:295-392)
+Routed build (the default):
+    rank r:  shard of assemblies --sketch--> minimizer records (h1, k-mer, owned neighbour hashes), stably
+             partitioned on the top byte of h1 (csrc/graph.cu route_stream)
+             all-to-all of the records by hash range (NCCL over NVLink; torch.distributed is only the plumbing)
+             the owner aggregates its range with the single-GPU bucket kernels (csrc/agg.cuh): nodes, k-mers,
+             the edges those nodes own, scoring -- nothing is left to merge
+Merge-based build (SEQWIN_DIST=merge; round 1): every rank builds the graph of its shard, the sorted node / k-mer /
+edge arrays are cut at the hash boundaries, exchanged and merged by the owner (csrc/dist.cu, mirrors
+merge_thread_graphs, cpp/src/seqwin/build_internals.cpp:295-392).
 
-An assembly lives on exactly one rank, so k-mer lists concatenate in rank order and edge weights
-add; concatenating the ranks' outputs in rank order is the reference graph.
+An assembly lives on exactly one rank and ranks hold consecutive assemblies, so the records a range owner
+receives, concatenated in rank order, are in global stream order; concatenating the ranks' outputs in rank order is
+the reference graph.
 
-The exchange logic is backend-agnostic: :class:`CudaStages` runs the stages through the C ABI on
-device pointers; tests drive the same :func:`exchange_and_merge` over ``gloo`` with a numpy stand-in.
+The exchange logic is backend-agnostic: :class:`CudaStages` runs the stages through the C ABI on device
+pointers; tests drive the same functions over ``gloo`` with a numpy stand-in.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -163,6 +169,86 @@ def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
 
 # ---- CUDA stages (C ABI) ------------------------------------------------------------------------
 
+# ---- routed build -----------------------------------------------------------------------------------------
+
+def range_bounds(world: int) -> np.ndarray:
+    """Top-byte boundaries of the ranks' hash ranges, [world + 1] ascending from 0 to 256.  A range owner handles the
+    records of its range and the adjacent pairs they own; a pair belongs to the smaller hash, so low ranges own more
+    pairs (density 2 (1 - x)): the boundaries are the quantiles of records + pairs, (3 x - x^2) / 2 = i / world."""
+    if world > 256:
+        raise ValueError("at most 256 hash ranges")
+    b = [int(round(256.0 * (3.0 - np.sqrt(9.0 - 8.0 * i / world)) / 2.0)) for i in range(world + 1)]
+    b[0], b[-1] = 0, 256
+    for i in range(1, world):          # strictly increasing, whatever the rounding did
+        b[i] = min(max(b[i], b[i - 1] + 1), 256 - (world - i))
+    return np.asarray(b, dtype=np.int64)
+
+
+@dataclass
+class RoutedContext:
+    """Input metadata every rank needs once per set of shards: where its records start, and the record offsets and
+    classes of ALL assemblies (the owner of a hash range scores records of every shard)."""
+    rec_base: int
+    record_offsets: np.ndarray          # [A_total + 1] uint32, global record indices
+    is_targets: np.ndarray | None       # [A_total] bool
+    bounds: np.ndarray                  # [world + 1] top-byte boundaries
+
+
+def routed_context(record_offsets_local: np.ndarray, is_targets_local, group=None) -> RoutedContext:
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = np.diff(np.asarray(record_offsets_local, dtype=np.int64))
+    mine = (counts, None if is_targets_local is None else np.asarray(is_targets_local, dtype=np.bool_))
+    every = [None] * world
+    dist.all_gather_object(every, mine, group=group)
+    all_counts = np.concatenate([c for c, _ in every])
+    offsets = np.concatenate([[0], np.cumsum(all_counts)])
+    if offsets[-1] > 0xFFFFFFFF:
+        raise RuntimeError("more than 2^32-1 records")
+    is_t = None if any(t is None for _, t in every) else np.ascontiguousarray(np.concatenate([t for _, t in every]), dtype=np.bool_)
+    rec_base = int(sum(int(c.sum()) for c, _ in every[:rank]))
+    return RoutedContext(rec_base, np.ascontiguousarray(offsets, dtype=np.uint32), is_t, range_bounds(world))
+
+
+def dist_build_routed(stages, dev_batch, k: int, w: int, ctx: RoutedContext, group=None, host_batch=None, inspect=None):
+    """The routed multi-GPU build of this rank's hash range; returns the graph handle (scored when the context holds
+    the classes)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    timed = torch.device(stages.device).type == "cuda"
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+    if timed:
+        ev[0].record()
+    routed = stages.sketch_route(dev_batch, k, w, ctx.rec_base, host_batch=host_batch)
+    if timed:
+        ev[1].record()
+    try:
+        split = np.asarray([routed.byte_off[int(b)] for b in ctx.bounds], dtype=np.uint64)
+        recv, counts, _, _ = all_to_all_slices(routed.arrays, [split] * 4, [8] * 4, group)
+    finally:
+        stages.free_routed(routed)
+    if timed:
+        ev[2].record()
+    n = int(counts[0].sum())
+    g = stages.aggregate(recv, n, int(ctx.bounds[rank]), int(ctx.bounds[rank + 1]), ctx.record_offsets, ctx.is_targets,
+                         routed.pairs_per_edge)
+    if inspect is not None:
+        inspect(None, g)
+    if timed:
+        ev[3].record()
+        stages.phase_events = [ev[0], ev[1], ev[3]]
+        stages._merge_events = (ev[2], ev[3])
+    return g
+
+
+@dataclass
+class Routed:
+    """A shard's routed records: four flat uint8 tensors (keys, vals, prev, next; 8 bytes per record)."""
+    arrays: list
+    byte_off: np.ndarray        # [257] first record of every top-byte value
+    pairs_per_edge: float
+    handle: object = None
+    dev_batch: object = None    # a batch uploaded for this call only
+
+
 class _DevView:
     """Zero-copy uint8 view of device memory owned by libseqwin_b200 (CUDA array interface)."""
 
@@ -243,6 +329,59 @@ class CudaStages:
             self.L.sw_graph_free(local.handle)
             local.handle = None
 
+    def sketch_route(self, dev_batch, k: int, w: int, rec_base: int, host_batch=None) -> Routed:
+        """Sketch this rank's shard and partition its records on the top byte of h1 (sw_dev_sketch_route)."""
+        L, lb = self.L, self._lib
+        own = None
+        if dev_batch is None:      # end-to-end: the packed batch starts in pinned host memory
+            own = C.c_void_p()
+            lb.check(L.sw_dev_upload(host_batch, C.byref(own)))
+            dev_batch = own
+        r = C.c_void_p()
+        self.times = lb.StageTimes()
+        try:
+            lb.check(L.sw_dev_sketch_route(dev_batch, k, w, rec_base, C.byref(r), C.byref(self.times)))
+        except BaseException:
+            if own is not None:
+                L.sw_dev_batch_free(own)
+            raise
+        ptrs = [C.c_void_p() for _ in range(4)]
+        n = C.c_uint64()
+        off = np.zeros(257, dtype=np.uint64)
+        stats = np.zeros(2, dtype=np.float64)
+        lb.check(L.sw_routed_info(r, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(ptrs[2]), C.byref(ptrs[3]), C.byref(n),
+                                  off.ctypes.data, stats.ctypes.data))
+        arrays = [_view(p_.value, n.value * 8, self.device) for p_ in ptrs]
+        self.merge_launches = 0
+        return Routed(arrays, off, float(stats[1]), handle=r, dev_batch=own)
+
+    def free_routed(self, routed: Routed) -> None:
+        if routed.handle:
+            self.L.sw_routed_free(routed.handle)
+            routed.handle = None
+        if routed.dev_batch is not None:
+            self.L.sw_dev_batch_free(routed.dev_batch)
+            routed.dev_batch = None
+
+    def aggregate(self, recv, n: int, byte_lo: int, byte_hi: int, record_offsets, is_targets, pairs_per_edge: float):
+        """Graph of the records this rank owns (sw_dev_aggregate): the single-GPU bucket kernels on what arrived."""
+        L, lb = self.L, self._lib
+        torch.cuda.current_stream(self.device).synchronize()   # received records visible to the library stream
+        g = C.c_void_p()
+        agg = lb.StageTimes()
+        t_ptr = is_targets.ctypes.data if is_targets is not None else None
+        t_len = len(is_targets) if is_targets is not None else 0
+        lb.check(L.sw_dev_aggregate(C.c_void_p(recv[0].data_ptr()), C.c_void_p(recv[1].data_ptr()), C.c_void_p(recv[2].data_ptr()),
+                                    C.c_void_p(recv[3].data_ptr()), n, byte_lo, byte_hi, record_offsets.ctypes.data,
+                                    len(record_offsets), t_ptr, t_len, float(pairs_per_edge), C.byref(g), C.byref(agg)))
+        if self.times is not None:    # one stage record per step: the routing pass counts as part of the sort stage
+            self.times.sort_nodes_ms += agg.sort_nodes_ms
+            self.times.nodes_ms, self.times.edges_ms = agg.nodes_ms, agg.edges_ms
+            self.times.n_nodes, self.times.n_edges = agg.n_nodes, agg.n_edges
+            self.times.total_ms += agg.total_ms
+            self.times.total_launches += agg.total_launches
+        return g
+
     def merge(self, nodes, node_counts, kmers, kmer_counts, kmer_base, edges, edge_counts):
         g = self.merge_nodes(nodes, node_counts, kmers, kmer_counts, kmer_base)
         self.merge_edges(g, edges, edge_counts)
@@ -278,14 +417,18 @@ class CudaStages:
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
-               host_batch=None, overlap: bool = True, is_targets=None, class_totals=None, inspect=None):
-    """Full multi-GPU build of this rank's hash range; returns the merged sw_graph handle.
+               host_batch=None, overlap: bool = True, is_targets=None, class_totals=None, inspect=None, ctx=None):
+    """Full multi-GPU build of this rank's hash range; returns the sw_graph handle.
+    With ctx (routed_context()) the records are routed to their range owners before they are aggregated
+    (dist_build_routed) unless SEQWIN_DIST=merge; without it the merge-based build below runs.
     With is_targets (bool array, the classes of THIS rank's assemblies) the graph comes back scored:
     every shard counts its own assemblies, the merge adds the counts, and the penalty is finished with
     class_totals = (targets, non-targets) over all ranks (all-reduced here when not given).
     inspect(local, merged_handle), if given, runs after the merge while the shard's own graph is still alive
     (verification hooks of bench.py)."""
     world = dist.get_world_size(group)
+    if ctx is not None and os.environ.get("SEQWIN_DIST", "routed") != "merge":
+        return dist_build_routed(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
     timed = torch.device(stages.device).type == "cuda"   # phase events for bench.py (the CPU stand-in has none)
@@ -428,45 +571,81 @@ def _wrap64(x: int) -> int:
     return x & (2**64 - 1)
 
 
-def full_size_checks(stages: "CudaStages", dev, n_records: int, k: int, w: int, rec_base: int, is_t_local, totals) -> dict:
-    """One more full-size distributed step with the checksums of every shard's own graph (before the
-    exchange) and of every rank's merged hash range (after it), summed over the ranks."""
+def batch_record_offsets(L, batch, n_assemblies: int) -> np.ndarray:
+    """[A + 1] record offsets of a packed host batch (records per assembly, cumulative)."""
+    from . import _lib
+    buf = np.zeros(n_assemblies + 1, dtype=np.int64)
+    _lib.check(L.sw_batch_record_offsets(batch, buf.ctypes.data, len(buf)))
+    return buf
+
+
+def full_size_checks(stages: "CudaStages", dev, n_records: int, k: int, w: int, rec_base: int, is_t_local, totals, ctx=None) -> dict:
+    """Two more full-size distributed steps.  The merge-based build gives the checksums of every shard's own graph
+    (before any exchange) and of every rank's merged hash range; the routed build -- the one that is timed -- those
+    of every rank's range as its owner aggregated it.  Summed over the ranks all three must agree: nothing lost,
+    nothing counted twice, whichever way the records travelled."""
     from . import _lib
     L = stages.L
     world, rank = dist.get_world_size(), dist.get_rank()
     device = stages.device
     got = {}
 
-    def inspect(local, g):
-        got["local"] = graph_checksums(local.kmers, local.nodes, local.edges)
+    def sums_of(g):
         pk, pn, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _lib.check(L.sw_graph_device_ptrs(g, C.byref(pk), C.byref(pn), C.byref(pe)))
         n_k, n_n, n_e = (L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES))
-        got["merged"] = graph_checksums(_view(pk.value, n_k * KMER_BYTES, device), _view(pn.value, n_n * NODE_BYTES, device),
-                                        _view(pe.value, n_e * EDGE_BYTES, device))
+        return graph_checksums(_view(pk.value, n_k * KMER_BYTES, device), _view(pn.value, n_n * NODE_BYTES, device),
+                               _view(pe.value, n_e * EDGE_BYTES, device))
 
-    g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, is_targets=is_t_local, class_totals=totals,
-                   inspect=inspect)
+    def inspect(local, g):
+        got["local"] = graph_checksums(local.kmers, local.nodes, local.edges)
+        got["merged"] = sums_of(g)
+
+    prev_mode = os.environ.get("SEQWIN_DIST")
+    os.environ["SEQWIN_DIST"] = "merge"
+    try:
+        g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, is_targets=is_t_local, class_totals=totals,
+                       inspect=inspect)
+    finally:
+        if prev_mode is None:
+            del os.environ["SEQWIN_DIST"]
+        else:
+            os.environ["SEQWIN_DIST"] = prev_mode
     L.sw_graph_free(g)
+    if ctx is not None and os.environ.get("SEQWIN_DIST", "routed") != "merge":
+        g = dist_build(stages, dev, n_records, k, w, ctx=ctx)
+        got["routed"] = sums_of(g)
+        L.sw_graph_free(g)
     every = [None] * world
     dist.all_gather_object(every, got)
     if rank != 0:
         return {}
     loc, mer = [x["local"] for x in every], [x["merged"] for x in every]
     tot = lambda rows, key: _wrap64(sum(r[key] for r in rows))   # noqa: E731
-    res = {
-        "kmers_conserved": sum(r["n_kmers"] for r in loc) == sum(r["n_kmers"] for r in mer),
-        "kmer_multiset_conserved": all(r["kmer_sum"] is not None for r in loc + mer) and tot(loc, "kmer_sum") == tot(mer, "kmer_sum"),
-        "edge_weight_multiset_conserved": tot(loc, "edge_sum") == tot(mer, "edge_sum") and
-                                          sum(r["weight_sum"] for r in loc) == sum(r["weight_sum"] for r in mer),
-        "class_counts_conserved": sum(r["n_tar_sum"] for r in loc) == sum(r["n_tar_sum"] for r in mer) and
-                                  sum(r["n_neg_sum"] for r in loc) == sum(r["n_neg_sum"] for r in mer),
-        "sorted_and_tiled_on_every_rank": all(r["nodes_sorted"] and r["nodes_tile"] and r["kmers_sorted_in_node"] and r["edges_sorted"]
-                                              for r in mer),
-        "rank_ranges_ascending": all(a["last_hash"] is None or b["first_hash"] is None or a["last_hash"] < b["first_hash"]
-                                     for a, b in zip(mer[:-1], mer[1:])),
-        "n_kmers": sum(r["n_kmers"] for r in mer), "n_nodes": sum(r["n_nodes"] for r in mer), "n_edges": sum(r["n_edges"] for r in mer),
-    }
+
+    def conserved(out):
+        return {
+            "kmers_conserved": sum(r["n_kmers"] for r in loc) == sum(r["n_kmers"] for r in out),
+            "kmer_multiset_conserved": all(r["kmer_sum"] is not None for r in loc + out) and tot(loc, "kmer_sum") == tot(out, "kmer_sum"),
+            "edge_weight_multiset_conserved": tot(loc, "edge_sum") == tot(out, "edge_sum") and
+                                              sum(r["weight_sum"] for r in loc) == sum(r["weight_sum"] for r in out),
+            "class_counts_conserved": sum(r["n_tar_sum"] for r in loc) == sum(r["n_tar_sum"] for r in out) and
+                                      sum(r["n_neg_sum"] for r in loc) == sum(r["n_neg_sum"] for r in out),
+            "sorted_and_tiled_on_every_rank": all(r["nodes_sorted"] and r["nodes_tile"] and r["kmers_sorted_in_node"] and r["edges_sorted"]
+                                                  for r in out),
+            "rank_ranges_ascending": all(a["last_hash"] is None or b["first_hash"] is None or a["last_hash"] < b["first_hash"]
+                                         for a, b in zip(out[:-1], out[1:])),
+        }
+    res = conserved(mer)
+    final = mer
+    if "routed" in every[0]:
+        final = [x["routed"] for x in every]
+        routed = conserved(final)
+        res = {k2: bool(v and routed[k2]) for k2, v in res.items()}
+        res["routed_equals_merged_totals"] = all(sum(r[key] for r in final) == sum(r[key] for r in mer)
+                                                 for key in ("n_kmers", "n_nodes", "n_edges", "weight_sum", "n_tar_sum", "n_neg_sum"))
+    res.update({"n_kmers": sum(r["n_kmers"] for r in final), "n_nodes": sum(r["n_nodes"] for r in final),
+                "n_edges": sum(r["n_edges"] for r in final)})
     res["all_ok"] = all(v for k2, v in res.items() if not k2.startswith("n_"))
     return res
 
@@ -492,11 +671,13 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     overlap = os.environ.get("SEQWIN_DIST_OVERLAP", "1") != "0"   # A/B switch for profiles/
     is_t_local = np.ascontiguousarray(is_t[rank * n_asm_local:(rank + 1) * n_asm_local])
     totals = (int(is_t.sum()), int(len(is_t) - is_t.sum()))   # class sizes are input metadata too
+    # ... and so are the record offsets / classes of all shards, which the owner of a hash range scores with
+    ctx = routed_context(batch_record_offsets(L, batch, n_asm_local), is_t_local)
 
     def step():
-        # build + scoring: every shard counts its assemblies, the merge adds, the penalty is finished last
+        # build + scoring: records routed to the owners of their hash ranges, aggregated and scored there
         g = dist_build(stages, dev, n_records, k, w, rec_base=rec_base, overlap=overlap, is_targets=is_t_local,
-                       class_totals=totals)
+                       class_totals=totals, ctx=ctx)
         sizes = [L.sw_graph_size(g, i) for i in (_lib.SW_KMERS, _lib.SW_NODES, _lib.SW_EDGES)]
         L.sw_graph_free(g)
         return sizes
@@ -542,7 +723,7 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     sg = torch.tensor([float(np.mean(single))], device=device)
     dist.all_reduce(sg, op=dist.ReduceOp.MAX)
 
-    checks = full_size_checks(stages, dev, n_records, k, w, rec_base, is_t_local, totals)
+    checks = full_size_checks(stages, dev, n_records, k, w, rec_base, is_t_local, totals, ctx=ctx)
     L.sw_dev_batch_free(dev)
 
     # end to end: pinned host batch -> H2D -> distributed build -> D2H of this rank's range
@@ -552,7 +733,7 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         g = dist_build(stages, None, n_records, k, w, rec_base=rec_base, host_batch=batch, overlap=overlap,
-                       is_targets=is_t_local, class_totals=totals)
+                       is_targets=is_t_local, class_totals=totals, ctx=ctx)
         t1 = time.perf_counter()
         _lib.check(L.sw_graph_fetch(g))     # this rank's hash range -> pinned host memory
         t2 = time.perf_counter()
@@ -598,7 +779,8 @@ def bench_parity(L, parity_batch, ss, rank: int, world: int, per_gpu: int, per_r
     n_records = L.sw_batch_n_records(parity_batch)
     dev = C.c_void_p()
     _lib.check(L.sw_dev_upload(parity_batch, C.byref(dev)))
-    g = dist_build(stages, dev, n_records, k, w, is_targets=is_t_local)
+    ctx = routed_context(batch_record_offsets(L, parity_batch, len(mine)), is_t_local)
+    g = dist_build(stages, dev, n_records, k, w, is_targets=is_t_local, ctx=ctx)
     kmers, nodes, edges = export_graph(L, g)
     L.sw_graph_free(g)
     L.sw_dev_batch_free(dev)
@@ -649,7 +831,7 @@ def bench_parity(L, parity_batch, ss, rank: int, world: int, per_gpu: int, per_r
             res = {"bit_exact": bool(ok and single_ok), "nccl_pieces_match_reference": pieces,
                    "single_gpu_from_fasta_matches_reference": single_ok, "against": ref["kind"],
                    "what": f"{len(subset)} genomes ({int(nb) / 1e6:.0f} Mbp; the first {per_rank} of every shard) through the same "
-                           f"{world}-rank NCCL exchange + merge + scoring; every rank's slice of kmers / nodes / edges compared by "
+                           f"{world}-rank NCCL exchange of minimizer records + aggregation + scoring by the range owners; every rank's slice of kmers / nodes / edges compared by "
                            "SHA-256 with the reference's arrays built from FASTA",
                    "graph": {"n_kmers": len(rk), "n_nodes": len(rn), "n_edges": len(re_)},
                    "sha256": {"kmers": sha(rk), "nodes": sha(rn), "edges": sha(re_)},

@@ -89,11 +89,112 @@ class NumpyStages:
         return mk, mn, mee
 
 
+    # ---- routed build: records to the owners of their hash ranges, aggregated there ----
+    def sketch_route(self, paths, k, w, rec_base, host_batch=None):
+        from oracle import oracle as O
+        from seqwin_b200.dist import Routed
+        keys, vals = [], []
+        rec = rec_base
+        for path in paths:
+            for seq in _fasta_records(path):
+                h1, pos = O.minimize(seq, k, w)
+                keys.append(h1.astype(np.uint64))
+                vals.append(pos.astype(np.uint64) | (np.uint64(rec) << np.uint64(32)))
+                rec += 1
+        keys = np.concatenate(keys) if keys else np.empty(0, np.uint64)
+        vals = np.concatenate(vals) if vals else np.empty(0, np.uint64)
+        n = len(keys)
+        prev, nxt = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        if n > 1:   # csrc/nbr.cuh: the adjacent pair belongs to the smaller hash, the earlier item on a tie
+            same = (vals[:-1] >> np.uint64(32)) == (vals[1:] >> np.uint64(32))
+            own_next = same & (keys[1:] >= keys[:-1])
+            own_prev = same & (keys[:-1] > keys[1:])
+            nxt[:-1][own_next] = keys[1:][own_next]
+            prev[1:][own_prev] = keys[:-1][own_prev]
+        order = np.argsort(keys >> np.uint64(56), kind="stable")
+        keys, vals, prev, nxt = keys[order], vals[order], prev[order], nxt[order]
+        byte_off = np.searchsorted(keys >> np.uint64(56), np.arange(257, dtype=np.uint64), "left").astype(np.uint64)
+        as_t = lambda a: torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy())  # noqa: E731
+        return Routed([as_t(keys), as_t(vals), as_t(prev), as_t(nxt)], byte_off, 1.0)
+
+    def free_routed(self, routed):
+        pass
+
+    def aggregate(self, recv, n, byte_lo, byte_hi, record_offsets, is_targets, pairs_per_edge):
+        from oracle.oracle import EDGE_DTYPE, KMER_DTYPE, NODE_DTYPE
+        keys, vals, prev, nxt = (np.frombuffer(t.numpy().tobytes(), dtype=np.uint64) for t in recv)
+        assert len(keys) == n and (n == 0 or (int(keys.min() >> np.uint64(56)) >= byte_lo and int(keys.max() >> np.uint64(56)) < byte_hi))
+        order = np.argsort(keys, kind="stable")
+        kmers = np.zeros(n, dtype=KMER_DTYPE)
+        kmers["pos"] = (vals[order] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        kmers["record_idx"] = (vals[order] >> np.uint64(32)).astype(np.uint32)
+        uk, first, cnt = np.unique(keys[order], return_index=True, return_counts=True)
+        nodes = np.zeros(len(uk), dtype=NODE_DTYPE)
+        nodes["hash"], nodes["start"], nodes["stop"] = uk, first, first + cnt
+        asm_of_rec = np.searchsorted(record_offsets.astype(np.int64), np.arange(int(record_offsets[-1])), "right") - 1
+        if is_targets is not None:
+            n_t, n_n = int(is_targets.sum()), int(len(is_targets) - is_targets.sum())
+            for i in range(len(nodes)):
+                a = np.unique(asm_of_rec[kmers["record_idx"][first[i]:first[i] + cnt[i]]])
+                nodes["n_tar"][i] = int(np.count_nonzero(is_targets[a]))
+                nodes["n_neg"][i] = len(a) - int(nodes["n_tar"][i])
+            ft = nodes["n_tar"] * (1.0 / n_t)
+            fn = nodes["n_neg"] * (1.0 / n_n)
+            nodes["penalty"] = np.sqrt((1.0 - ft) * (1.0 - ft) + fn * fn)
+        asm = asm_of_rec[(vals >> np.uint64(32)).astype(np.int64)] if n else np.empty(0, np.int64)
+        trip = set()
+        for k_, s_, a_ in zip(np.concatenate([keys[prev != 0], keys[nxt != 0]]), np.concatenate([prev[prev != 0], nxt[nxt != 0]]),
+                              np.concatenate([asm[prev != 0], asm[nxt != 0]])):
+            trip.add((int(k_), int(s_), int(a_)))
+        weight = {}
+        for f_, s_, _ in trip:
+            weight[(f_, s_)] = weight.get((f_, s_), 0) + 1
+        edges = np.zeros(len(weight), dtype=EDGE_DTYPE)
+        for i, ((f_, s_), w_) in enumerate(sorted(weight.items())):
+            edges[i] = (f_, s_, w_)
+        return kmers, nodes, edges
+
     def finish_penalty(self, g, class_totals):
         nodes = g[1]
         ft = nodes["n_tar"] * (1.0 / class_totals[0])
         fn = nodes["n_neg"] * (1.0 / class_totals[1])
         nodes["penalty"] = np.sqrt((1.0 - ft) * (1.0 - ft) + fn * fn)
+
+
+def _fasta_records(path):
+    """Sequences of a plain FASTA file (test sets: no blank lines inside records)."""
+    seq = None
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if line.startswith(">"):
+                if seq is not None:
+                    yield "".join(seq)
+                seq = []
+            elif seq is not None:
+                seq.append(line)
+    if seq is not None:
+        yield "".join(seq)
+
+
+def _routed_worker(rank, world, port, paths, is_t, k, w, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from seqwin_b200 import dist as swd
+        per = (len(paths) + world - 1) // world
+        mine = paths[rank * per:(rank + 1) * per]
+        mine_t = None if is_t is None else np.asarray(is_t[rank * per:(rank + 1) * per], dtype=np.bool_)
+        offsets_local = O._build_native(mine, k, w)[3]
+        ctx = swd.routed_context(offsets_local, mine_t)
+        merged = swd.dist_build(NumpyStages(), mine, int(offsets_local[-1]), k, w, is_targets=mine_t, ctx=ctx)
+        full = swd.gather_graph(merged)
+        if rank == 0:
+            np.savez(out_path, kmers=full[0], nodes=full[1], edges=full[2], bounds=ctx.bounds, rec_base=np.array([ctx.rec_base]))
+    finally:
+        dist.destroy_process_group()
 
 
 def _scored_worker(rank, world, port, paths, is_t, k, w, out_path):
@@ -172,3 +273,38 @@ def test_dist_build_scored_flow_over_gloo(synth_sets, tmp_path, world):
     O._get_penalty_native(kmers, nodes, offsets, np.asarray(is_t, dtype=np.bool_))
     assert np.array_equal(got["kmers"], kmers) and np.array_equal(got["edges"], edges)
     assert np.array_equal(got["nodes"], nodes)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("scored", [False, True], ids=["build", "scored"])
+def test_routed_build_over_gloo(synth_sets, tmp_path, world, scored):
+    """seqwin_b200.dist routed flow, host logic only: global record offsets / classes gathered once, records cut at
+    the top-byte boundaries of the ranks' hash ranges, exchanged, aggregated by the owners; the ranks' graphs
+    concatenated in rank order == the oracle's graph (and its get_penalty) on all assemblies."""
+    from oracle import oracle as O
+    k, w = 17, 10
+    paths, is_t = synth_sets["synth_small"]
+    paths = [str(p) for p in paths]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "routed.npz"
+    mp.spawn(_routed_worker, args=(world, port, paths, list(map(bool, is_t)) if scored else None, k, w, str(out)),
+             nprocs=world, join=True)
+    got = np.load(out)
+    kmers, nodes, edges, offsets, _ = O._build_native(paths, k, w)
+    if scored:
+        O._get_penalty_native(kmers, nodes, offsets, np.asarray(is_t, dtype=np.bool_))
+    assert np.array_equal(got["kmers"], kmers) and np.array_equal(got["edges"], edges)
+    assert np.array_equal(got["nodes"], nodes)
+    b = got["bounds"]
+    assert b[0] == 0 and b[-1] == 256 and np.all(np.diff(b) > 0)
+
+
+def test_range_bounds():
+    from seqwin_b200.dist import range_bounds
+    for world in (1, 2, 3, 4, 8, 64, 256):
+        b = range_bounds(world)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == 256 and np.all(np.diff(b) >= 1)
+    b8 = range_bounds(8)
+    assert b8[1] < 32 and 256 - b8[-2] > 32      # low ranges own more pairs, so they are narrower

@@ -1,7 +1,8 @@
-"""Multi-rank build on real hardware: the CUDA stages of seqwin_b200.dist (local build with a record
-base, hash-range split, merge kernels of csrc/dist.cu) against the oracle.  Uses NCCL when two GPUs
-are visible; on a single GPU both ranks share cuda:0 and exchange through gloo (the device kernels
-exercised are the same)."""
+"""Multi-rank build on real hardware against the oracle, both ways seqwin_b200.dist knows: routed (records
+partitioned on the top byte of h1, sent to the owners of their hash ranges, aggregated there with the
+single-GPU bucket kernels) and merge-based (local build with a record base, hash-range split, merge kernels of
+csrc/dist.cu).  Uses NCCL when one GPU per rank is visible; on a single GPU the ranks share cuda:0 and exchange
+through gloo (the device kernels exercised are the same)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -19,7 +20,7 @@ from tests.helpers import assert_graph_equal, check_graph_invariants
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is_targets=None):
+def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is_targets=None, mode="routed"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev_index = rank if use_nccl else 0
@@ -41,7 +42,10 @@ def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is
         _lib.check(L.sw_batch_from_fasta(arr, len(mine), 2, C.byref(b)))
         _lib.check(L.sw_dev_upload(b, C.byref(d)))
         mine_t = None if is_targets is None else np.asarray(is_targets[rank * per:(rank + 1) * per], dtype=np.bool_)
-        g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t)
+        ctx = None
+        if mode == "routed":
+            ctx = swd.routed_context(swd.batch_record_offsets(L, b, len(mine)), mine_t)
+        g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t, ctx=ctx)
         parts = swd.export_graph(L, g)
         L.sw_graph_free(g)
         L.sw_dev_batch_free(d)
@@ -62,9 +66,10 @@ def _backend(world: int) -> bool:
     return use_nccl
 
 
+@pytest.mark.parametrize("mode", ["routed", "merge"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("kw", [(21, 200), (17, 10)], ids=lambda kw: f"k{kw[0]}w{kw[1]}")
-def test_multi_rank_build_matches_oracle(synth_sets, tmp_path, kw, world):
+def test_multi_rank_build_matches_oracle(synth_sets, tmp_path, kw, world, mode):
     from oracle import oracle as O
     use_nccl = _backend(world)
     paths, _ = synth_sets["synth_medium"]
@@ -73,10 +78,10 @@ def test_multi_rank_build_matches_oracle(synth_sets, tmp_path, kw, world):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = tmp_path / "merged.npz"
-    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, True, None, mode), nprocs=world, join=True)
     got = np.load(out)
     want = O._build_native(paths, *kw)
-    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"{world} ranks {kw}")
+    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"{world} ranks {kw} {mode}")
     check_graph_invariants(got["kmers"], got["nodes"], got["edges"], want[3])
 
 
@@ -90,14 +95,16 @@ def test_multi_rank_build_without_overlap(synth_sets, tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = tmp_path / "merged.npz"
-    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, False), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, False, None, "merge"), nprocs=world, join=True)
     got = np.load(out)
     want = O._build_native(paths, *kw)
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, "2 ranks, no overlap")
 
 
-def test_more_ranks_than_assemblies(synth_sets, tmp_path):
-    """A rank with an empty shard never reaches the nodes-ready hook and must still join every collective."""
+@pytest.mark.parametrize("mode", ["routed", "merge"])
+def test_more_ranks_than_assemblies(synth_sets, tmp_path, mode):
+    """A rank with an empty shard (no records to route; in the merge-based build it never reaches the nodes-ready
+    hook) must still join every collective."""
     from oracle import oracle as O
     world, kw = 3, (21, 50)
     use_nccl = torch.cuda.device_count() >= world
@@ -106,16 +113,18 @@ def test_more_ranks_than_assemblies(synth_sets, tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = tmp_path / "merged.npz"
-    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, True, None, mode), nprocs=world, join=True)
     got = np.load(out)
     want = O._build_native(paths, *kw)
-    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, "3 ranks, 2 assemblies")
+    assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"3 ranks, 2 assemblies, {mode}")
 
 
+@pytest.mark.parametrize("mode", ["routed", "merge"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_multi_rank_scored_build(synth_sets, tmp_path, world):
-    """Scoring across ranks: every shard counts its own assemblies (targets first, so some shards hold
-    one class only), the merge adds the counts, the penalty is finished with the global class sizes.
+def test_multi_rank_scored_build(synth_sets, tmp_path, world, mode):
+    """Scoring across ranks.  Routed: the owner of a hash range scores the records of every shard with the global
+    record offsets and classes.  Merge-based: every shard counts its own assemblies (targets first, so some shards
+    hold one class only), the merge adds the counts, the penalty is finished with the global class sizes.
     Must equal build + get_penalty of the oracle on all assemblies."""
     from oracle import oracle as O
     kw = (21, 200)
@@ -126,7 +135,7 @@ def test_multi_rank_scored_build(synth_sets, tmp_path, world):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = tmp_path / "merged.npz"
-    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, True, list(map(bool, is_t))),
+    mp.spawn(_worker, args=(world, port, paths, kw[0], kw[1], str(out), use_nccl, True, list(map(bool, is_t)), mode),
              nprocs=world, join=True)
     got = np.load(out)
     kmers, nodes, edges, offsets, _ = O._build_native(paths, *kw)
