@@ -286,6 +286,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # the record exchange is one large all-to-all per array: with NCCL's default P2P channel count it reaches
+        # about 430 GB/s per GPU over NVLink 5, with 64 channels about 620 (tools/a2a_bench.py, profiles/)
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "64")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "64")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     threads = max(1, cores // max(1, world))
