@@ -416,6 +416,13 @@ class CudaStages:
         self._merge_events[1].record()
 
 
+def dist_mode() -> str:
+    """SEQWIN_DIST: 'merge' (default: shard graphs merged by the range owners) or 'routed' (records exchanged
+    through NCCL before they are aggregated).  Measured on 8 B200 (15,000 genomes): merge 45 ms, routed 50 ms per
+    step -- the NCCL exchange of the 32-byte records is not hidden behind anything (profiles/)."""
+    return os.environ.get("SEQWIN_DIST", "merge")
+
+
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
                host_batch=None, overlap: bool = True, is_targets=None, class_totals=None, inspect=None, ctx=None):
     """Full multi-GPU build of this rank's hash range; returns the sw_graph handle.
@@ -427,7 +434,7 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
     inspect(local, merged_handle), if given, runs after the merge while the shard's own graph is still alive
     (verification hooks of bench.py)."""
     world = dist.get_world_size(group)
-    if ctx is not None and os.environ.get("SEQWIN_DIST", "routed") != "merge":
+    if ctx is not None and dist_mode() != "merge":
         return dist_build_routed(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
@@ -612,7 +619,7 @@ def full_size_checks(stages: "CudaStages", dev, n_records: int, k: int, w: int, 
         else:
             os.environ["SEQWIN_DIST"] = prev_mode
     L.sw_graph_free(g)
-    if ctx is not None and os.environ.get("SEQWIN_DIST", "routed") != "merge":
+    if ctx is not None and dist_mode() != "merge":
         g = dist_build(stages, dev, n_records, k, w, ctx=ctx)
         got["routed"] = sums_of(g)
         L.sw_graph_free(g)
