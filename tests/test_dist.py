@@ -180,6 +180,7 @@ def _fasta_records(path):
 def _routed_worker(rank, world, port, paths, is_t, k, w, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["SEQWIN_DIST"] = "routed"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import oracle as O

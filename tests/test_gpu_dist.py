@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is_targets=None, mode="routed"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["SEQWIN_DIST"] = mode
     dev_index = rank if use_nccl else 0
     torch.cuda.set_device(dev_index)
     if use_nccl:
