@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--n-kmers", type=float, required=True)
     ap.add_argument("--n-nodes", type=float, required=True)
     ap.add_argument("--n-edges", type=float, required=True)
-    ap.add_argument("--launches-per-build", default="radix_onesweep_kernel=2",
+    ap.add_argument("--launches-per-build", default="",
                     help="kernels launched more than once per build, name=count[,name=count]")
     ap.add_argument("--out", default="profiles/r2_traffic.json")
     a = ap.parse_args()
