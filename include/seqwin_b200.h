@@ -207,7 +207,27 @@ void sw_routed_free(sw_routed* r);
  * the reference graph. */
 int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const void* next, uint64_t n, uint32_t byte_lo,
                      uint32_t byte_hi, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
-                     size_t n_assemblies, double pairs_per_edge, sw_graph** out, sw_stage_times* t);
+                     size_t n_assemblies, double pairs_per_edge, const uint64_t* byte_off, sw_graph** out, sw_stage_times* t);
+/* byte_off != NULL (byte_hi - byte_lo + 1 entries from 0 to n): the records arrive stably partitioned on the top byte,
+ * byte_off[i] = first record of top byte byte_lo + i -- what the fused routing below delivers; the owner then skips
+ * the partition pass on that byte.
+ *
+ * Fused routing: the exchange is part of the routing pass.  Every rank allocates its receive arrays with
+ * sw_peer_alloc (plain cudaMalloc memory with a CUDA IPC handle) and opens the other ranks' with sw_peer_open
+ * (peer access over NVLink); sw_dev_sketch_hist sketches the shard and counts its records per top byte; the ranks
+ * all-gather those counts (the only collective) and derive where every shard's records of every top byte go in the
+ * owner's arrays -- (top byte, source rank) order, i.e. global stream order inside a byte --; sw_routed_scatter runs
+ * the ONE pass that generates the owned neighbours and scatters keys / k-mers / neighbours straight into those
+ * arrays (route_ptrs: 4 x 256 device pointers, array-major: the owner's keys, vals, prev, next base for every top
+ * byte; byte_base[256]: first position of this shard's records there).  After a barrier the owner calls
+ * sw_dev_aggregate on its own arrays. */
+int sw_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle /* 64 bytes out */);
+int sw_peer_open(const void* ipc_handle, void** dev_ptr);
+int sw_peer_close(void* dev_ptr);
+int sw_peer_free(void* dev_ptr);
+int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_routed** out, uint64_t* byte_counts /* 256 */,
+                       sw_stage_times* t);
+int sw_routed_scatter(sw_routed* r, const void* const* route_ptrs, const uint64_t* byte_base, float* kernel_ms);
 
 /* ---- first consumers of the graph, on the device-resident arrays ------------ */
 /* Edge-weight filter + isolated-node removal, the array part of _filter_edges_and_nodes

@@ -875,6 +875,7 @@ int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_
 
 struct sw_routed {
     sw::RoutedStream rs;
+    sw::SketchStream st;       // fused build: the stream waits here (scratch arena) between the histogram and the scatter
     cudaStream_t stream = nullptr;
 };
 
@@ -924,6 +925,125 @@ int sw_dev_sketch_route(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t 
     });
 }
 
+// ---- fused routing: the scatter of the routing pass writes into the owners' memory (peer access over NVLink) ----------
+int sw_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle)
+{
+    return guarded([&] {
+        init_device_once();
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as 64 bytes");
+        void* p = nullptr;
+        SW_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        cudaIpcMemHandle_t h;
+        const cudaError_t err = cudaIpcGetMemHandle(&h, p);
+        if (err != cudaSuccess) {
+            cudaFree(p);
+            SW_CUDA(err);
+        }
+        memcpy(ipc_handle, &h, sizeof(h));
+        *dev_ptr = p;
+    });
+}
+
+int sw_peer_open(const void* ipc_handle, void** dev_ptr)
+{
+    return guarded([&] {
+        init_device_once();
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle, sizeof(h));
+        SW_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+
+int sw_peer_close(void* dev_ptr)
+{
+    return guarded([&] { SW_CUDA(cudaIpcCloseMemHandle(dev_ptr)); });
+}
+
+int sw_peer_free(void* dev_ptr)
+{
+    return guarded([&] {
+        SW_CUDA(cudaDeviceSynchronize());
+        SW_CUDA(cudaFree(dev_ptr));
+    });
+}
+
+int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_routed** out, uint64_t* byte_counts,
+                       sw_stage_times* t)
+{
+    return guarded([&] {
+        init_device_once();
+        check_kw(k, w);
+        cudaStream_t s = d->stream;
+        arena_reset();
+        auto r = std::make_unique<sw_routed>();
+        r->stream = s;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        struct EvGuard {
+            cudaEvent_t &a, &b;
+            ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); }
+        } guard{e0, e1};
+        cudaEventRecord(e0, s);
+        const auto host_t0 = std::chrono::steady_clock::now();
+        DevPlan plan = make_plan(*d, k, w, s);
+        const float plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, rec_base, s, r->st);
+        if (r->st.n > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers on one device");
+        DevBuf<unsigned long long> counts(256, s, true);
+        route_histogram(r->st.keys.p, r->st.n, counts.p, s);
+        cudaEventRecord(e1, s);
+        const unsigned long long* h = readback_u64(counts.p, 256, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        std::copy(h, h + 256, byte_counts);
+        r->rs.n = r->st.n;
+        r->rs.items_per_key = r->st.items_per_key;
+        r->rs.pairs_per_edge = r->st.pairs_per_edge;
+        if (t) {
+            memset(t, 0, sizeof(*t));
+            cudaEventElapsedTime(&t->sketch_ms, e0, e1);
+            t->total_ms = t->sketch_ms;
+            t->plan_ms = plan_ms;
+            t->sketch_kernel_ms = r->st.kernel_ms;
+            t->reorder_ms = r->st.reorder_ms;
+            t->n_bases = d->meta.n_bases;
+            t->n_kmers = r->st.n;
+            t->n_tiles = plan.n_tiles;
+            t->sketch_launches = r->st.launches;
+            t->total_launches = r->st.launches + 1;
+        }
+        *out = r.release();
+    });
+}
+
+int sw_routed_scatter(sw_routed* r, const void* const* route_ptrs, const uint64_t* byte_base, float* kernel_ms)
+{
+    return guarded([&] {
+        cudaStream_t s = r->stream;
+        DevBuf<unsigned long long> d_base(256, s, true);
+        DevBuf<uint64_t*> d_route(4 * 256, s, true);
+        DevBuf<unsigned long long> flag(1, s, true);
+        SW_CUDA(cudaMemcpyAsync(d_base.p, byte_base, 256 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemcpyAsync(d_route.p, route_ptrs, 4 * 256 * sizeof(void*), cudaMemcpyHostToDevice, s));
+        SW_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(unsigned long long), s));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+        route_scatter(r->st.keys.p, r->st.vals.p, r->st.n, d_base.p, d_route.p, reinterpret_cast<unsigned int*>(flag.p), s);
+        cudaEventRecord(e1, s);
+        const unsigned long long* hz = readback_u64(flag.p, 1, s);
+        SW_CUDA(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (kernel_ms) *kernel_ms = ms;
+        if ((*hz & 0xFFFFFFFFull) != 0)
+            fail_runtime("a minimizer hash is 0: the routed multi-GPU build cannot mark 'no neighbour' (use the merge-based one)");
+    });
+}
+
 int sw_routed_info(const sw_routed* r, void** keys, void** vals, void** prev, void** next, uint64_t* n, uint64_t* byte_off,
                    double* stats)
 {
@@ -950,11 +1070,12 @@ void sw_routed_free(sw_routed* r)
 
 int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const void* next, uint64_t n, uint32_t byte_lo,
                      uint32_t byte_hi, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
-                     size_t n_assemblies, double pairs_per_edge, sw_graph** out, sw_stage_times* t)
+                     size_t n_assemblies, double pairs_per_edge, const uint64_t* byte_off, sw_graph** out, sw_stage_times* t)
 {
     return guarded([&] {
         init_device_once();
         if (byte_lo > byte_hi || byte_hi > 256) fail_value("hash range must be 0 <= byte_lo <= byte_hi <= 256");
+        if (byte_off && (byte_off[0] != 0 || byte_off[byte_hi - byte_lo] != n)) fail_value("byte_off must run from 0 to n");
         if (n_offsets == 0 || record_offsets[0] != 0) fail_value("record_offsets must start with 0");
         for (size_t i = 0; i + 1 < n_offsets; ++i)
             if (record_offsets[i + 1] < record_offsets[i]) fail_value("record_offsets must be nondecreasing");
@@ -976,7 +1097,7 @@ int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const
         const NbrBuffers in{const_cast<uint64_t*>(static_cast<const uint64_t*>(keys)), const_cast<uint64_t*>(static_cast<const uint64_t*>(vals)),
                             const_cast<uint64_t*>(static_cast<const uint64_t*>(prev)), const_cast<uint64_t*>(static_cast<const uint64_t*>(next))};
         GraphTimes gt;
-        aggregate_range(in, n, byte_lo, byte_hi, d_ra.p, s, g->dev, &gt, score ? &score->args : nullptr, pairs_per_edge);
+        aggregate_range(in, n, byte_lo, byte_hi, d_ra.p, s, g->dev, &gt, score ? &score->args : nullptr, pairs_per_edge, byte_off);
         cudaEventRecord(e1, s);
         SW_CUDA(cudaStreamSynchronize(s));
         g->on_device = true;

@@ -1090,7 +1090,8 @@ void route_stream(SketchStream& st, cudaStream_t s, RoutedStream& out)
 }
 
 void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_t byte_hi, const uint32_t* d_rec_asm,
-                     cudaStream_t s, DevGraph& g, GraphTimes* times, const ScoreArgs* score, double pairs_per_edge)
+                     cudaStream_t s, DevGraph& g, GraphTimes* times, const ScoreArgs* score, double pairs_per_edge,
+                     const uint64_t* byte_off)
 {
     using namespace agg;
     GraphTimes tm;
@@ -1124,8 +1125,25 @@ void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_
     DevBuf<unsigned long long> tot(4, s, true);
     SW_CUDA(cudaMemsetAsync(tot.p, 0, 4 * sizeof(unsigned long long), s));
     const NbrBuffers* R = nullptr;
-    tm.launches += 1 + radix_partition_nbr(nullptr, nullptr, &in, n, key_bits, P - 8 + top_bits, A, B, s, &R, nullptr,
-                                           (uint64_t)byte_lo << 56);
+    if (byte_off) {
+        // partitioned on the top byte already: the lower bucket bits, one top-byte segment after the other (every
+        // segment takes the same number of passes, so all of them end up in the same set)
+        R = &in;
+        for (uint32_t b = 0; b < width; ++b) {
+            const uint64_t o = byte_off[b], nb_items = byte_off[b + 1] - o;
+            if (nb_items == 0) continue;
+            const NbrBuffers inV{in.keys + o, in.vals + o, in.prev + o, in.next + o};
+            const NbrBuffers AV{A.keys + o, A.vals + o, A.prev + o, A.next + o}, BV{B.keys + o, B.vals + o, B.prev + o, B.next + o};
+            const NbrBuffers* Rv = nullptr;
+            tm.launches += radix_partition_nbr(nullptr, nullptr, &inV, nb_items, key_bits, P - 8, AV, BV, s, &Rv, nullptr);
+            R = Rv == &inV ? &in : (Rv == &AV ? &A : &B);
+        }
+    } else {
+        // the bits below the top byte and the top byte itself, taken relative to the range's first value so that it
+        // needs no more digits than the range is wide
+        tm.launches += 1 + radix_partition_nbr(nullptr, nullptr, &in, n, key_bits, P - 8 + top_bits, A, B, s, &R, nullptr,
+                                               (uint64_t)byte_lo << 56);
+    }
     const NbrBuffers* Dd = R == &A ? &B : &A;
     if (R == &in) Dd = &A;   // no pass ran (one bucket): the input is the result, any set is free
     SliceJob J{};

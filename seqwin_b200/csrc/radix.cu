@@ -120,6 +120,10 @@ struct NbrArrays {
     uint64_t key_bias = 0;           // subtracted from a key before its digit is taken
     uint64_t n_total = 0;            // gen: items of the whole stream (neighbours across tile borders)
     unsigned int* zero_key = nullptr;   // gen: set when a key is 0 (the "not owned" marker would be ambiguous)
+    // Routed scatter (multi-GPU): the four output arrays of digit d start at route[a * 256 + d] (a = 0..3: keys, vals,
+    // prev, next) -- memory of the GPU that owns the digit's hash range, mapped over NVLink -- and `goff` holds the
+    // position of this shard's first item of every digit inside those arrays.  null: the ordinary outputs.
+    uint64_t* const* route = nullptr;
 };
 
 template <int NT, int ITEMS, bool FULL, typename V, int NBR>   // NBR: 0 = pairs only, 1 = carry the neighbour arrays, 2 = generate them
@@ -246,7 +250,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
             const uint64_t k2 = s_buf[p];
             const uint32_t d = (uint32_t)((k2 - nb.key_bias) >> shift) & dmask;
             dig[i >> 2] |= d << (8 * (i & 3));
-            kout[sm.dbase[d] + p] = k2;
+            (nb.route ? nb.route[d] : kout)[sm.dbase[d] + p] = k2;
         }
     }
     __pipeline_wait_prior(0);
@@ -260,7 +264,10 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const uint32_t p = (uint32_t)i * NT + tid;
-        if (FULL || p < n_valid) vout[sm.dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_val[p];
+        if (FULL || p < n_valid) {
+            const uint32_t d = (dig[i >> 2] >> (8 * (i & 3))) & 255u;
+            (nb.route ? reinterpret_cast<V*>(nb.route[256 + d]) : vout)[sm.dbase[d] + p] = s_val[p];
+        }
     }
     if (NBR != 0) {
         // the two neighbour arrays take the same route, one after the other; their loads are issued together
@@ -296,7 +303,10 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<NT, ITEMS>& sm, uint6
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const uint32_t p = (uint32_t)i * NT + tid;
-                if (FULL || p < n_valid) dst[sm.dbase[(dig[i >> 2] >> (8 * (i & 3))) & 255u] + p] = s_buf[p];
+                if (FULL || p < n_valid) {
+                    const uint32_t d = (dig[i >> 2] >> (8 * (i & 3))) & 255u;
+                    (nb.route ? nb.route[(2 + a) * 256 + d] : dst)[sm.dbase[d] + p] = s_buf[p];
+                }
             }
         }
     }
@@ -500,6 +510,45 @@ uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const N
     }
     *out = src;
     return launches;
+}
+
+// The routing pass of the fused multi-GPU build: ONE generating pass over the stream on the top byte of h1 whose
+// scatter writes go straight to the owners of the hash ranges.  byte_counts_out (device, 256 words): items per top
+// byte, filled by route_histogram; d_base (device, 256 words): where this shard's items of every byte start in the
+// owner's arrays; d_route (device, 4 * 256 pointers): see NbrArrays.
+void route_histogram(const uint64_t* keys, uint64_t n, unsigned long long* byte_counts_out, cudaStream_t s)
+{
+    RadixPasses ps{};
+    ps.n = 1;
+    ps.shift[0] = 56;
+    ps.bits[0] = 8;
+    SW_CUDA(cudaMemsetAsync(byte_counts_out, 0, kRadix * sizeof(unsigned long long), s));
+    if (n == 0) return;
+    const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
+    radix_hist_kernel<<<hist_grid, 256, 0, s>>>(keys, n, ps, byte_counts_out);
+    SW_CUDA(cudaGetLastError());
+}
+
+void route_scatter(const uint64_t* keys, const uint64_t* vals, uint64_t n, const unsigned long long* d_base,
+                   uint64_t* const* d_route, unsigned int* d_zero_key, cudaStream_t s)
+{
+    using V = unsigned long long;
+    if (n == 0) return;
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    DevBuf<unsigned long long> status(n_tiles * kRadix, s, true);
+    DevBuf<unsigned int> ticket(1, s, true);
+    constexpr size_t kSortSmem = (size_t)kSortTile * (8 + sizeof(V));
+    SW_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kSortThreads, kSortItems, V, 2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    SW_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), s));
+    SW_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), s));
+    NbrArrays nb;
+    nb.n_total = n;
+    nb.zero_key = d_zero_key;
+    nb.route = d_route;
+    radix_onesweep_kernel<kSortThreads, kSortItems, V, 2><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
+        keys, nullptr, reinterpret_cast<const V*>(vals), nullptr, n, 56, 255u, d_base, status.p, ticket.p, nb);
+    SW_CUDA(cudaGetLastError());
 }
 
 template uint32_t radix_partition_top<uint32_t>(const uint64_t*, const uint32_t*, uint64_t, int, uint64_t*, uint32_t*, uint64_t*,

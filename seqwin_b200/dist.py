@@ -192,6 +192,7 @@ class RoutedContext:
     record_offsets: np.ndarray          # [A_total + 1] uint32, global record indices
     is_targets: np.ndarray | None       # [A_total] bool
     bounds: np.ndarray                  # [world + 1] top-byte boundaries
+    peer: object = None                 # PeerBuffers of the fused build, allocated on first use
 
 
 def routed_context(record_offsets_local: np.ndarray, is_targets_local, group=None) -> RoutedContext:
@@ -230,6 +231,105 @@ def dist_build_routed(stages, dev_batch, k: int, w: int, ctx: RoutedContext, gro
     n = int(counts[0].sum())
     g = stages.aggregate(recv, n, int(ctx.bounds[rank]), int(ctx.bounds[rank + 1]), ctx.record_offsets, ctx.is_targets,
                          routed.pairs_per_edge)
+    if inspect is not None:
+        inspect(None, g)
+    if timed:
+        ev[3].record()
+        stages.phase_events = [ev[0], ev[1], ev[3]]
+        stages._merge_events = (ev[2], ev[3])
+    return g
+
+
+@dataclass
+class PeerBuffers:
+    """Receive arrays of the fused routing: every rank owns 4 x capacity words (keys | vals | prev | next) of plain
+    device memory that the other ranks have mapped through CUDA IPC (peer access over NVLink)."""
+    capacity: int
+    bases: list        # bases[r] = rank r's buffer as seen from this process (bases[rank] is this rank's own)
+
+
+def ensure_peer_buffers(stages, ctx: "RoutedContext", need_items: int, group=None) -> PeerBuffers:
+    """Collective: (re)allocate the receive arrays when the largest hash range of this step does not fit."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    pb = ctx.peer
+    if pb is not None and pb.capacity >= need_items:
+        return pb
+    if pb is not None:
+        for r, b in enumerate(pb.bases):
+            if r != rank:
+                stages.peer_close(b)
+        dist.barrier(group)            # nobody has this rank's memory mapped any more
+        stages.peer_free(pb.bases[rank])
+    cap = int(need_items * 1.25) + 4096
+    mine, handle = stages.peer_alloc(4 * cap * 8)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    bases = [mine if r == rank else stages.peer_open(handles[r]) for r in range(world)]
+    ctx.peer = PeerBuffers(cap, bases)
+    return ctx.peer
+
+
+def release_peer_buffers(stages, ctx: "RoutedContext", group=None) -> None:
+    """Collective: unmap and free the receive arrays of a context."""
+    pb, rank = ctx.peer, dist.get_rank(group)
+    if pb is None:
+        return
+    for r, b in enumerate(pb.bases):
+        if r != rank:
+            stages.peer_close(b)
+    dist.barrier(group)
+    stages.peer_free(pb.bases[rank])
+    ctx.peer = None
+
+
+def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", group=None, host_batch=None, inspect=None):
+    """The routed build with the exchange fused into the routing pass: no data-path collective at all.  The ranks
+    all-gather 256 counts each, derive where every shard's records of every top byte go in the owner's arrays --
+    (top byte, source rank) order: global stream order inside a byte --, and the pass that generates the owned
+    neighbour hashes scatters its output straight into those arrays over NVLink (csrc/radix.cu route_scatter)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    timed = torch.device(stages.device).type == "cuda"
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+    if timed:
+        ev[0].record()
+    routed, counts = stages.sketch_hist(dev_batch, k, w, ctx.rec_base, host_batch=host_batch)
+    if timed:
+        ev[1].record()
+    try:
+        if dist.get_backend(group) == "nccl":
+            mine_t = torch.from_numpy(counts.astype(np.int64)).to(stages.device)
+            every_t = torch.empty(world * 256, dtype=torch.int64, device=stages.device)
+            dist.all_gather_into_tensor(every_t, mine_t, group=group)
+            mat = every_t.cpu().numpy().reshape(world, 256)
+        else:
+            every = [None] * world
+            dist.all_gather_object(every, counts.astype(np.int64), group=group)
+            mat = np.stack(every)
+        bounds = ctx.bounds
+        owner = np.repeat(np.arange(world), np.diff(bounds))                 # [256] owner of every top byte
+        per_byte = mat.sum(axis=0)                                            # records of every top byte, all shards
+        n_owner = np.array([int(per_byte[bounds[o]:bounds[o + 1]].sum()) for o in range(world)])
+        pb = ensure_peer_buffers(stages, ctx, int(n_owner.max()), group)
+        # inside an owner's arrays: top bytes ascending, sources ascending inside a byte
+        byte_start = np.zeros(256, dtype=np.int64)
+        for o in range(world):
+            lo, hi = int(bounds[o]), int(bounds[o + 1])
+            byte_start[lo:hi] = np.concatenate([[0], np.cumsum(per_byte[lo:hi])[:-1]])
+        byte_base = np.ascontiguousarray(byte_start + mat[:rank].sum(axis=0), dtype=np.uint64)
+        route_ptrs = np.zeros(4 * 256, dtype=np.uint64)
+        for a in range(4):
+            route_ptrs[a * 256:(a + 1) * 256] = [pb.bases[int(owner[b])] + a * pb.capacity * 8 for b in range(256)]
+        stages.routed_scatter(routed, route_ptrs, byte_base)     # returns when this shard's records have left
+    finally:
+        stages.free_routed(routed)
+    dist.barrier(group)                                           # ... and now everybody's have arrived
+    if timed:
+        ev[2].record()
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    seg = np.ascontiguousarray(np.concatenate([[0], np.cumsum(per_byte[lo:hi])]), dtype=np.uint64)
+    mine = pb.bases[rank]
+    g = stages.aggregate([mine + a * pb.capacity * 8 for a in range(4)], int(n_owner[rank]), lo, hi, ctx.record_offsets,
+                         ctx.is_targets, routed.pairs_per_edge, byte_off=seg)
     if inspect is not None:
         inspect(None, g)
     if timed:
@@ -355,6 +455,55 @@ class CudaStages:
         self.merge_launches = 0
         return Routed(arrays, off, float(stats[1]), handle=r, dev_batch=own)
 
+    def sketch_hist(self, dev_batch, k: int, w: int, rec_base: int, host_batch=None):
+        """Fused routing, first half: sketch the shard, count its records per top byte of h1 (sw_dev_sketch_hist).
+        Returns (Routed without arrays, counts[256])."""
+        L, lb = self.L, self._lib
+        own = None
+        if dev_batch is None:
+            own = C.c_void_p()
+            lb.check(L.sw_dev_upload(host_batch, C.byref(own)))
+            dev_batch = own
+        r = C.c_void_p()
+        self.times = lb.StageTimes()
+        counts = np.zeros(256, dtype=np.uint64)
+        try:
+            lb.check(L.sw_dev_sketch_hist(dev_batch, k, w, rec_base, C.byref(r), counts.ctypes.data, C.byref(self.times)))
+        except BaseException:
+            if own is not None:
+                L.sw_dev_batch_free(own)
+            raise
+        stats = np.zeros(2, dtype=np.float64)
+        lb.check(L.sw_routed_info(r, None, None, None, None, None, None, stats.ctypes.data))
+        self.merge_launches = 0
+        return Routed([], counts, float(stats[1]), handle=r, dev_batch=own), counts
+
+    def routed_scatter(self, routed: Routed, route_ptrs: np.ndarray, byte_base: np.ndarray) -> None:
+        """Fused routing, second half: the generating partition pass whose scatter writes go to the owners' arrays."""
+        ms = C.c_float()
+        self._lib.check(self.L.sw_routed_scatter(routed.handle, route_ptrs.ctypes.data, byte_base.ctypes.data, C.byref(ms)))
+        if self.times is not None:
+            self.times.sort_nodes_ms += ms.value
+            self.times.total_ms += ms.value
+            self.times.total_launches += 1
+
+    def peer_alloc(self, n_bytes: int):
+        p_, h = C.c_void_p(), (C.c_ubyte * 64)()
+        self._lib.check(self.L.sw_peer_alloc(n_bytes, C.byref(p_), h))
+        return p_.value, bytes(h)
+
+    def peer_open(self, handle: bytes) -> int:
+        p_ = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._lib.check(self.L.sw_peer_open(buf, C.byref(p_)))
+        return p_.value
+
+    def peer_close(self, ptr: int) -> None:
+        self._lib.check(self.L.sw_peer_close(C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int) -> None:
+        self._lib.check(self.L.sw_peer_free(C.c_void_p(ptr)))
+
     def free_routed(self, routed: Routed) -> None:
         if routed.handle:
             self.L.sw_routed_free(routed.handle)
@@ -363,7 +512,8 @@ class CudaStages:
             self.L.sw_dev_batch_free(routed.dev_batch)
             routed.dev_batch = None
 
-    def aggregate(self, recv, n: int, byte_lo: int, byte_hi: int, record_offsets, is_targets, pairs_per_edge: float):
+    def aggregate(self, recv, n: int, byte_lo: int, byte_hi: int, record_offsets, is_targets, pairs_per_edge: float,
+                  byte_off=None):
         """Graph of the records this rank owns (sw_dev_aggregate): the single-GPU bucket kernels on what arrived."""
         L, lb = self.L, self._lib
         torch.cuda.current_stream(self.device).synchronize()   # received records visible to the library stream
@@ -371,9 +521,11 @@ class CudaStages:
         agg = lb.StageTimes()
         t_ptr = is_targets.ctypes.data if is_targets is not None else None
         t_len = len(is_targets) if is_targets is not None else 0
-        lb.check(L.sw_dev_aggregate(C.c_void_p(recv[0].data_ptr()), C.c_void_p(recv[1].data_ptr()), C.c_void_p(recv[2].data_ptr()),
-                                    C.c_void_p(recv[3].data_ptr()), n, byte_lo, byte_hi, record_offsets.ctypes.data,
-                                    len(record_offsets), t_ptr, t_len, float(pairs_per_edge), C.byref(g), C.byref(agg)))
+        ptrs = [x if isinstance(x, int) else x.data_ptr() for x in recv]   # tensors, or raw device pointers (peer buffers)
+        lb.check(L.sw_dev_aggregate(C.c_void_p(ptrs[0]), C.c_void_p(ptrs[1]), C.c_void_p(ptrs[2]),
+                                    C.c_void_p(ptrs[3]), n, byte_lo, byte_hi, record_offsets.ctypes.data,
+                                    len(record_offsets), t_ptr, t_len, float(pairs_per_edge),
+                                    None if byte_off is None else byte_off.ctypes.data, C.byref(g), C.byref(agg)))
         if self.times is not None:    # one stage record per step: the routing pass counts as part of the sort stage
             self.times.sort_nodes_ms += agg.sort_nodes_ms
             self.times.nodes_ms, self.times.edges_ms = agg.nodes_ms, agg.edges_ms
@@ -417,9 +569,8 @@ class CudaStages:
 
 
 def dist_mode() -> str:
-    """SEQWIN_DIST: 'merge' (default: shard graphs merged by the range owners) or 'routed' (records exchanged
-    through NCCL before they are aggregated).  Measured on 8 B200 (15,000 genomes): merge 45 ms, routed 50 ms per
-    step -- the NCCL exchange of the 32-byte records is not hidden behind anything (profiles/)."""
+    """SEQWIN_DIST: 'merge' (shard graphs merged by the range owners), 'routed' (records exchanged through NCCL
+    before they are aggregated) or 'fused' (the routing pass writes the records into the owners' memory)."""
     return os.environ.get("SEQWIN_DIST", "merge")
 
 
@@ -434,6 +585,8 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
     inspect(local, merged_handle), if given, runs after the merge while the shard's own graph is still alive
     (verification hooks of bench.py)."""
     world = dist.get_world_size(group)
+    if ctx is not None and dist_mode() == "fused":
+        return dist_build_fused(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
     if ctx is not None and dist_mode() != "merge":
         return dist_build_routed(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
     if rec_base is None:
@@ -760,6 +913,7 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     n_bases_total, n_k, n_n, n_e = (int(x) for x in tot)
     for d in stage_dicts:
         d["n_kmers"], d["n_nodes"], d["n_edges"] = n_k, n_n, n_e
+    release_peer_buffers(stages, ctx)
     L.sw_set_stream(None)
     return {"stages": stage_dicts, "clocks": clocks, "e2e_runs": e2e, "n_bases_total": n_bases_total,
             "single_gpu": {"ms_per_step": float(sg), "gbp_s_per_gpu": n_bases_local / (float(sg) * 1e-3) / 1e9,
@@ -790,6 +944,7 @@ def bench_parity(L, parity_batch, ss, rank: int, world: int, per_gpu: int, per_r
     g = dist_build(stages, dev, n_records, k, w, is_targets=is_t_local, ctx=ctx)
     kmers, nodes, edges = export_graph(L, g)
     L.sw_graph_free(g)
+    release_peer_buffers(stages, ctx)
     L.sw_dev_batch_free(dev)
     L.sw_set_stream(None)
     counts = [None] * world

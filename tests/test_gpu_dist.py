@@ -1,5 +1,6 @@
-"""Multi-rank build on real hardware against the oracle, both ways seqwin_b200.dist knows: routed (records
-partitioned on the top byte of h1, sent to the owners of their hash ranges, aggregated there with the
+"""Multi-rank build on real hardware against the oracle, all three ways seqwin_b200.dist knows: fused (the routing
+pass scatters the records straight into the range owners' memory, mapped through CUDA IPC), routed (records
+partitioned on the top byte of h1, sent to the owners of their hash ranges through NCCL, aggregated there with the
 single-GPU bucket kernels) and merge-based (local build with a record base, hash-range split, merge kernels of
 csrc/dist.cu).  Uses NCCL when one GPU per rank is visible; on a single GPU the ranks share cuda:0 and exchange
 through gloo (the device kernels exercised are the same)."""
@@ -44,11 +45,17 @@ def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is
         _lib.check(L.sw_dev_upload(b, C.byref(d)))
         mine_t = None if is_targets is None else np.asarray(is_targets[rank * per:(rank + 1) * per], dtype=np.bool_)
         ctx = None
-        if mode == "routed":
+        if mode != "merge":
             ctx = swd.routed_context(swd.batch_record_offsets(L, b, len(mine)), mine_t)
         g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t, ctx=ctx)
         parts = swd.export_graph(L, g)
         L.sw_graph_free(g)
+        if mode == "fused":   # a second build reuses the mapped receive arrays
+            g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t, ctx=ctx)
+            again = swd.export_graph(L, g)
+            L.sw_graph_free(g)
+            assert all(np.array_equal(x, y) for x, y in zip(parts, again))
+            swd.release_peer_buffers(stages, ctx)
         L.sw_dev_batch_free(d)
         L.sw_batch_free(b)
         full = swd.gather_graph(parts)
@@ -67,7 +74,7 @@ def _backend(world: int) -> bool:
     return use_nccl
 
 
-@pytest.mark.parametrize("mode", ["routed", "merge"])
+@pytest.mark.parametrize("mode", ["fused", "routed", "merge"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("kw", [(21, 200), (17, 10)], ids=lambda kw: f"k{kw[0]}w{kw[1]}")
 def test_multi_rank_build_matches_oracle(synth_sets, tmp_path, kw, world, mode):
@@ -102,7 +109,7 @@ def test_multi_rank_build_without_overlap(synth_sets, tmp_path):
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, "2 ranks, no overlap")
 
 
-@pytest.mark.parametrize("mode", ["routed", "merge"])
+@pytest.mark.parametrize("mode", ["fused", "routed", "merge"])
 def test_more_ranks_than_assemblies(synth_sets, tmp_path, mode):
     """A rank with an empty shard (no records to route; in the merge-based build it never reaches the nodes-ready
     hook) must still join every collective."""
@@ -120,7 +127,7 @@ def test_more_ranks_than_assemblies(synth_sets, tmp_path, mode):
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"3 ranks, 2 assemblies, {mode}")
 
 
-@pytest.mark.parametrize("mode", ["routed", "merge"])
+@pytest.mark.parametrize("mode", ["fused", "routed", "merge"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_multi_rank_scored_build(synth_sets, tmp_path, world, mode):
     """Scoring across ranks.  Routed: the owner of a hash range scores the records of every shard with the global
