@@ -207,8 +207,10 @@ void sw_routed_free(sw_routed* r);
  * the reference graph. */
 int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const void* next, uint64_t n, uint32_t byte_lo,
                      uint32_t byte_hi, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
-                     size_t n_assemblies, double pairs_per_edge, const uint64_t* byte_off, sw_graph** out, sw_stage_times* t);
-/* byte_off != NULL (byte_hi - byte_lo + 1 entries from 0 to n): the records arrive stably partitioned on the top byte,
+                     size_t n_assemblies, double pairs_per_edge, const uint64_t* byte_off, uint32_t range_bits, sw_graph** out,
+                     sw_stage_times* t);
+/* range_bits (1..8): the hash space is cut into 2^range_bits bins and byte_lo / byte_hi are bin numbers (8: top bytes).
+ * byte_off != NULL (byte_hi - byte_lo + 1 entries from 0 to n): the records arrive stably partitioned on the bins,
  * byte_off[i] = first record of top byte byte_lo + i -- what the fused routing below delivers; the owner then skips
  * the partition pass on that byte.
  *
@@ -225,8 +227,8 @@ int sw_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle /* 64 bytes out
 int sw_peer_open(const void* ipc_handle, void** dev_ptr);
 int sw_peer_close(void* dev_ptr);
 int sw_peer_free(void* dev_ptr);
-int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_routed** out, uint64_t* byte_counts /* 256 */,
-                       sw_stage_times* t);
+int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, uint32_t route_bits, sw_routed** out,
+                       uint64_t* byte_counts /* 256, the first 2^route_bits used */, sw_stage_times* t);
 int sw_routed_scatter(sw_routed* r, const void* const* route_ptrs, const uint64_t* byte_base, float* kernel_ms);
 
 /* ---- first consumers of the graph, on the device-resident arrays ------------ */

@@ -68,13 +68,13 @@ PROTOTYPES = {
     "sw_dev_sketch_route": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), C.POINTER(StageTimes)]),
     "sw_routed_info": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), _P, _P]),
     "sw_routed_free": (None, [_P]),
-    "sw_dev_aggregate": (_I, [_P, _P, _P, _P, C.c_uint64, _U32, _U32, _P, _SZ, _P, _SZ, C.c_double, _P, C.POINTER(_P),
+    "sw_dev_aggregate": (_I, [_P, _P, _P, _P, C.c_uint64, _U32, _U32, _P, _SZ, _P, _SZ, C.c_double, _P, _U32, C.POINTER(_P),
                               C.POINTER(StageTimes)]),
     "sw_peer_alloc": (_I, [_SZ, C.POINTER(_P), _P]),
     "sw_peer_open": (_I, [_P, C.POINTER(_P)]),
     "sw_peer_close": (_I, [_P]),
     "sw_peer_free": (_I, [_P]),
-    "sw_dev_sketch_hist": (_I, [_P, _U32, _U32, _U32, C.POINTER(_P), _P, C.POINTER(StageTimes)]),
+    "sw_dev_sketch_hist": (_I, [_P, _U32, _U32, _U32, _U32, C.POINTER(_P), _P, C.POINTER(StageTimes)]),
     "sw_routed_scatter": (_I, [_P, _P, _P, C.POINTER(C.c_float)]),
     "sw_set_low_memory": (_I, [_I]),
     "sw_trim_memory": (_I, []),

@@ -876,6 +876,7 @@ int sw_dev_build_ex(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_
 struct sw_routed {
     sw::RoutedStream rs;
     sw::SketchStream st;       // fused build: the stream waits here (scratch arena) between the histogram and the scatter
+    int route_bits = 8;
     cudaStream_t stream = nullptr;
 };
 
@@ -967,16 +968,18 @@ int sw_peer_free(void* dev_ptr)
     });
 }
 
-int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, sw_routed** out, uint64_t* byte_counts,
-                       sw_stage_times* t)
+int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t rec_base, uint32_t route_bits, sw_routed** out,
+                       uint64_t* byte_counts, sw_stage_times* t)
 {
     return guarded([&] {
         init_device_once();
         check_kw(k, w);
+        if (route_bits < 1 || route_bits > 8) fail_value("route_bits must be 1..8");
         cudaStream_t s = d->stream;
         arena_reset();
         auto r = std::make_unique<sw_routed>();
         r->stream = s;
+        r->route_bits = (int)route_bits;
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
@@ -991,7 +994,7 @@ int sw_dev_sketch_hist(const sw_dev_batch* d, uint32_t k, uint32_t w, uint32_t r
         run_sketch(d->words.p, d->rec_word_off.p, plan, k, w, rec_base, s, r->st);
         if (r->st.n > 0xFFFFFFFFull) fail_runtime("more than 2^32-1 minimizers on one device");
         DevBuf<unsigned long long> counts(256, s, true);
-        route_histogram(r->st.keys.p, r->st.n, counts.p, s);
+        route_histogram(r->st.keys.p, r->st.n, (int)route_bits, counts.p, s);
         cudaEventRecord(e1, s);
         const unsigned long long* h = readback_u64(counts.p, 256, s);
         SW_CUDA(cudaStreamSynchronize(s));
@@ -1030,7 +1033,7 @@ int sw_routed_scatter(sw_routed* r, const void* const* route_ptrs, const uint64_
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
-        route_scatter(r->st.keys.p, r->st.vals.p, r->st.n, d_base.p, d_route.p, reinterpret_cast<unsigned int*>(flag.p), s);
+        route_scatter(r->st.keys.p, r->st.vals.p, r->st.n, r->route_bits, d_base.p, d_route.p, reinterpret_cast<unsigned int*>(flag.p), s);
         cudaEventRecord(e1, s);
         const unsigned long long* hz = readback_u64(flag.p, 1, s);
         SW_CUDA(cudaStreamSynchronize(s));
@@ -1070,11 +1073,13 @@ void sw_routed_free(sw_routed* r)
 
 int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const void* next, uint64_t n, uint32_t byte_lo,
                      uint32_t byte_hi, const uint32_t* record_offsets, size_t n_offsets, const uint8_t* is_targets,
-                     size_t n_assemblies, double pairs_per_edge, const uint64_t* byte_off, sw_graph** out, sw_stage_times* t)
+                     size_t n_assemblies, double pairs_per_edge, const uint64_t* byte_off, uint32_t range_bits, sw_graph** out,
+                     sw_stage_times* t)
 {
     return guarded([&] {
         init_device_once();
-        if (byte_lo > byte_hi || byte_hi > 256) fail_value("hash range must be 0 <= byte_lo <= byte_hi <= 256");
+        if (range_bits < 1 || range_bits > 8) fail_value("range_bits must be 1..8");
+        if (byte_lo > byte_hi || byte_hi > (1u << range_bits)) fail_value("hash range must be 0 <= lo <= hi <= 2^range_bits");
         if (byte_off && (byte_off[0] != 0 || byte_off[byte_hi - byte_lo] != n)) fail_value("byte_off must run from 0 to n");
         if (n_offsets == 0 || record_offsets[0] != 0) fail_value("record_offsets must start with 0");
         for (size_t i = 0; i + 1 < n_offsets; ++i)
@@ -1097,7 +1102,8 @@ int sw_dev_aggregate(const void* keys, const void* vals, const void* prev, const
         const NbrBuffers in{const_cast<uint64_t*>(static_cast<const uint64_t*>(keys)), const_cast<uint64_t*>(static_cast<const uint64_t*>(vals)),
                             const_cast<uint64_t*>(static_cast<const uint64_t*>(prev)), const_cast<uint64_t*>(static_cast<const uint64_t*>(next))};
         GraphTimes gt;
-        aggregate_range(in, n, byte_lo, byte_hi, d_ra.p, s, g->dev, &gt, score ? &score->args : nullptr, pairs_per_edge, byte_off);
+        aggregate_range(in, n, byte_lo, byte_hi, d_ra.p, s, g->dev, &gt, score ? &score->args : nullptr, pairs_per_edge, byte_off,
+                        (int)range_bits);
         cudaEventRecord(e1, s);
         SW_CUDA(cudaStreamSynchronize(s));
         g->on_device = true;

@@ -172,8 +172,8 @@ uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const N
 // Fused routing pass of the multi-GPU build (radix.cu): items per top byte of h1; then one generating pass whose
 // scatter writes land in the arrays of the hash-range owners (d_route: 4 * 256 device pointers -- keys, vals, prev,
 // next of the owner of every top byte, peer memory -- and d_base[256]: first position of this shard's items there).
-void route_histogram(const uint64_t* keys, uint64_t n, unsigned long long* byte_counts_out, cudaStream_t s);
-void route_scatter(const uint64_t* keys, const uint64_t* vals, uint64_t n, const unsigned long long* d_base,
+void route_histogram(const uint64_t* keys, uint64_t n, int route_bits, unsigned long long* byte_counts_out, cudaStream_t s);
+void route_scatter(const uint64_t* keys, const uint64_t* vals, uint64_t n, int route_bits, const unsigned long long* d_base,
                    uint64_t* const* d_route, unsigned int* d_zero_key, cudaStream_t s);
 
 // ---- graph stage ------------------------------------------------------------------------------
@@ -223,9 +223,10 @@ void route_stream(SketchStream& st, cudaStream_t s, RoutedStream& out);
 // byte_off (host, byte_hi - byte_lo + 1 entries, may be null): the items arrive stably partitioned on the top byte
 // (the fused routing pass delivers them so) and byte_off[i] is the first item of top byte byte_lo + i; the lower
 // bucket bits are then partitioned segment by segment and the pass on the top byte is saved.
+// range_bits: the hash space is cut into 2^range_bits bins (8: top bytes) and [byte_lo, byte_hi) are bin numbers.
 void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_t byte_hi, const uint32_t* d_rec_asm,
                      cudaStream_t s, DevGraph& g, GraphTimes* times, const ScoreArgs* score, double pairs_per_edge,
-                     const uint64_t* byte_off = nullptr);
+                     const uint64_t* byte_off = nullptr, int range_bits = 8);
 
 // ---- consumers of a device-resident graph (filter.cu), in place on g ---------------------------------
 // edges with weight > weight_th and the nodes that keep an edge (kmers.py:132-162); k-mers untouched

@@ -1091,7 +1091,7 @@ void route_stream(SketchStream& st, cudaStream_t s, RoutedStream& out)
 
 void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_t byte_hi, const uint32_t* d_rec_asm,
                      cudaStream_t s, DevGraph& g, GraphTimes* times, const ScoreArgs* score, double pairs_per_edge,
-                     const uint64_t* byte_off)
+                     const uint64_t* byte_off, int range_bits)
 {
     using namespace agg;
     GraphTimes tm;
@@ -1109,12 +1109,12 @@ void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_
     timer.start();
     DevBuf<unsigned long long> sample_set(1ull << kSampleSetBits, s, true), sample_out(2, s, true);
     const double per_node = estimate_items_per_key(in.keys, n, sample_set.p, sample_out.p, s);
-    // bucket bits as if the whole hash space were this dense; at least the 8 bits the range is cut on
+    // bucket bits as if the whole hash space were this dense; at least the bits the range is cut on
     const uint32_t width = byte_hi - byte_lo;
     const EdgeGeom* egp = nullptr;
-    int P = choose_bucket_bits((uint64_t)((double)n * 256.0 / (double)width), per_node, pairs_per_edge > 0 ? pairs_per_edge : 1.0, &egp);
-    if (const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0)) P = partition_bits((uint64_t)((double)n * 256.0 / (double)width), fixed_nb);
-    P = std::max(P, 8);
+    int P = choose_bucket_bits((uint64_t)((double)n * (double)(1u << range_bits) / (double)width), per_node, pairs_per_edge > 0 ? pairs_per_edge : 1.0, &egp);
+    if (const uint32_t fixed_nb = env_u32("SEQWIN_AGG_NODE_BUCKET", 0)) P = partition_bits((uint64_t)((double)n * (double)(1u << range_bits) / (double)width), fixed_nb);
+    P = std::max(P, range_bits);
     const int key_bits = 64 - P;
     int top_bits = 0;
     while ((1u << top_bits) < width) ++top_bits;
@@ -1135,14 +1135,14 @@ void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_
             const NbrBuffers inV{in.keys + o, in.vals + o, in.prev + o, in.next + o};
             const NbrBuffers AV{A.keys + o, A.vals + o, A.prev + o, A.next + o}, BV{B.keys + o, B.vals + o, B.prev + o, B.next + o};
             const NbrBuffers* Rv = nullptr;
-            tm.launches += radix_partition_nbr(nullptr, nullptr, &inV, nb_items, key_bits, P - 8, AV, BV, s, &Rv, nullptr);
+            tm.launches += radix_partition_nbr(nullptr, nullptr, &inV, nb_items, key_bits, P - range_bits, AV, BV, s, &Rv, nullptr);
             R = Rv == &inV ? &in : (Rv == &AV ? &A : &B);
         }
     } else {
         // the bits below the top byte and the top byte itself, taken relative to the range's first value so that it
         // needs no more digits than the range is wide
-        tm.launches += 1 + radix_partition_nbr(nullptr, nullptr, &in, n, key_bits, P - 8 + top_bits, A, B, s, &R, nullptr,
-                                               (uint64_t)byte_lo << 56);
+        tm.launches += 1 + radix_partition_nbr(nullptr, nullptr, &in, n, key_bits, P - range_bits + top_bits, A, B, s, &R, nullptr,
+                                               (uint64_t)byte_lo << (64 - range_bits));
     }
     const NbrBuffers* Dd = R == &A ? &B : &A;
     if (R == &in) Dd = &A;   // no pass ran (one bucket): the input is the result, any set is free
@@ -1150,8 +1150,8 @@ void aggregate_range(const NbrBuffers& in, uint64_t n, uint32_t byte_lo, uint32_
     J.R = R;
     J.Dd = Dd;
     J.n = n;
-    J.n_buckets = (uint64_t)width << (P - 8);
-    J.bucket0 = (uint64_t)byte_lo << (P - 8);
+    J.n_buckets = (uint64_t)width << (P - range_bits);
+    J.bucket0 = (uint64_t)byte_lo << (P - range_bits);
     J.key_bits = key_bits;
     J.exact = true;
     bool fallback = false;

@@ -512,16 +512,17 @@ uint32_t radix_partition_nbr(const uint64_t* keys, const uint64_t* vals, const N
     return launches;
 }
 
-// The routing pass of the fused multi-GPU build: ONE generating pass over the stream on the top byte of h1 whose
+// The routing pass of the fused multi-GPU build: ONE generating pass over the stream on the top route_bits (<= 8)
+// bits of h1 ("bins"; tables are sized for 256) whose
 // scatter writes go straight to the owners of the hash ranges.  byte_counts_out (device, 256 words): items per top
 // byte, filled by route_histogram; d_base (device, 256 words): where this shard's items of every byte start in the
 // owner's arrays; d_route (device, 4 * 256 pointers): see NbrArrays.
-void route_histogram(const uint64_t* keys, uint64_t n, unsigned long long* byte_counts_out, cudaStream_t s)
+void route_histogram(const uint64_t* keys, uint64_t n, int route_bits, unsigned long long* byte_counts_out, cudaStream_t s)
 {
     RadixPasses ps{};
     ps.n = 1;
-    ps.shift[0] = 56;
-    ps.bits[0] = 8;
+    ps.shift[0] = 64 - route_bits;
+    ps.bits[0] = route_bits;
     SW_CUDA(cudaMemsetAsync(byte_counts_out, 0, kRadix * sizeof(unsigned long long), s));
     if (n == 0) return;
     const uint32_t hist_grid = (uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)sm_count() * 8);
@@ -529,7 +530,7 @@ void route_histogram(const uint64_t* keys, uint64_t n, unsigned long long* byte_
     SW_CUDA(cudaGetLastError());
 }
 
-void route_scatter(const uint64_t* keys, const uint64_t* vals, uint64_t n, const unsigned long long* d_base,
+void route_scatter(const uint64_t* keys, const uint64_t* vals, uint64_t n, int route_bits, const unsigned long long* d_base,
                    uint64_t* const* d_route, unsigned int* d_zero_key, cudaStream_t s)
 {
     using V = unsigned long long;
@@ -547,7 +548,8 @@ void route_scatter(const uint64_t* keys, const uint64_t* vals, uint64_t n, const
     nb.zero_key = d_zero_key;
     nb.route = d_route;
     radix_onesweep_kernel<kSortThreads, kSortItems, V, 2><<<(uint32_t)n_tiles, kSortThreads, kSortSmem, s>>>(
-        keys, nullptr, reinterpret_cast<const V*>(vals), nullptr, n, 56, 255u, d_base, status.p, ticket.p, nb);
+        keys, nullptr, reinterpret_cast<const V*>(vals), nullptr, n, 64 - route_bits, (1u << route_bits) - 1u, d_base, status.p,
+        ticket.p, nb);
     SW_CUDA(cudaGetLastError());
 }
 

@@ -171,17 +171,28 @@ def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
 
 # ---- routed build -----------------------------------------------------------------------------------------
 
-def range_bounds(world: int) -> np.ndarray:
-    """Top-byte boundaries of the ranks' hash ranges, [world + 1] ascending from 0 to 256.  A range owner handles the
-    records of its range and the adjacent pairs they own; a pair belongs to the smaller hash, so low ranges own more
-    pairs (density 2 (1 - x)): the boundaries are the quantiles of records + pairs, (3 x - x^2) / 2 = i / world."""
-    if world > 256:
-        raise ValueError("at most 256 hash ranges")
-    b = [int(round(256.0 * (3.0 - np.sqrt(9.0 - 8.0 * i / world)) / 2.0)) for i in range(world + 1)]
-    b[0], b[-1] = 0, 256
+def range_bounds(world: int, bits: int = 8) -> np.ndarray:
+    """Boundaries of the ranks' hash ranges in units of 2^-bits of the hash space ("bins"; bits = 8: top bytes),
+    [world + 1] ascending from 0 to 2^bits.  A range owner handles the records of its range and the adjacent pairs
+    they own; a pair belongs to the smaller hash, so low ranges own more pairs (density 2 (1 - x)): the boundaries
+    are the quantiles of records + pairs, (3 x - x^2) / 2 = i / world."""
+    n_bins = 1 << bits
+    if world > n_bins:
+        raise ValueError(f"at most {n_bins} hash ranges")
+    b = [int(round(n_bins * (3.0 - np.sqrt(9.0 - 8.0 * i / world)) / 2.0)) for i in range(world + 1)]
+    b[0], b[-1] = 0, n_bins
     for i in range(1, world):          # strictly increasing, whatever the rounding did
-        b[i] = min(max(b[i], b[i - 1] + 1), 256 - (world - i))
+        b[i] = min(max(b[i], b[i - 1] + 1), n_bins - (world - i))
     return np.asarray(b, dtype=np.int64)
+
+
+def fused_route_bits(world: int) -> int:
+    """Bins of the fused routing pass: about four per rank -- enough to balance the ranges, few enough that the
+    owner's per-bin partition launches stay negligible."""
+    bits = 3
+    while bits < 8 and (1 << bits) < 4 * world:
+        bits += 1
+    return bits
 
 
 @dataclass
@@ -292,7 +303,9 @@ def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", gr
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
     if timed:
         ev[0].record()
-    routed, counts = stages.sketch_hist(dev_batch, k, w, ctx.rec_base, host_batch=host_batch)
+    rb = fused_route_bits(world)
+    n_bins = 1 << rb
+    routed, counts = stages.sketch_hist(dev_batch, k, w, ctx.rec_base, rb, host_batch=host_batch)
     if timed:
         ev[1].record()
     try:
@@ -305,20 +318,22 @@ def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", gr
             every = [None] * world
             dist.all_gather_object(every, counts.astype(np.int64), group=group)
             mat = np.stack(every)
-        bounds = ctx.bounds
-        owner = np.repeat(np.arange(world), np.diff(bounds))                 # [256] owner of every top byte
-        per_byte = mat.sum(axis=0)                                            # records of every top byte, all shards
+        mat = mat[:, :n_bins]
+        bounds = range_bounds(world, rb)
+        owner = np.repeat(np.arange(world), np.diff(bounds))                 # owner of every bin
+        per_byte = mat.sum(axis=0)                                            # records of every bin, all shards
         n_owner = np.array([int(per_byte[bounds[o]:bounds[o + 1]].sum()) for o in range(world)])
         pb = ensure_peer_buffers(stages, ctx, int(n_owner.max()), group)
         # inside an owner's arrays: top bytes ascending, sources ascending inside a byte
-        byte_start = np.zeros(256, dtype=np.int64)
+        byte_start = np.zeros(n_bins, dtype=np.int64)
         for o in range(world):
             lo, hi = int(bounds[o]), int(bounds[o + 1])
             byte_start[lo:hi] = np.concatenate([[0], np.cumsum(per_byte[lo:hi])[:-1]])
-        byte_base = np.ascontiguousarray(byte_start + mat[:rank].sum(axis=0), dtype=np.uint64)
+        byte_base = np.zeros(256, dtype=np.uint64)
+        byte_base[:n_bins] = byte_start + mat[:rank].sum(axis=0)
         route_ptrs = np.zeros(4 * 256, dtype=np.uint64)
         for a in range(4):
-            route_ptrs[a * 256:(a + 1) * 256] = [pb.bases[int(owner[b])] + a * pb.capacity * 8 for b in range(256)]
+            route_ptrs[a * 256:a * 256 + n_bins] = [pb.bases[int(owner[b])] + a * pb.capacity * 8 for b in range(n_bins)]
         stages.routed_scatter(routed, route_ptrs, byte_base)     # returns when this shard's records have left
     finally:
         stages.free_routed(routed)
@@ -329,7 +344,7 @@ def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", gr
     seg = np.ascontiguousarray(np.concatenate([[0], np.cumsum(per_byte[lo:hi])]), dtype=np.uint64)
     mine = pb.bases[rank]
     g = stages.aggregate([mine + a * pb.capacity * 8 for a in range(4)], int(n_owner[rank]), lo, hi, ctx.record_offsets,
-                         ctx.is_targets, routed.pairs_per_edge, byte_off=seg)
+                         ctx.is_targets, routed.pairs_per_edge, byte_off=seg, range_bits=rb)
     if inspect is not None:
         inspect(None, g)
     if timed:
@@ -455,7 +470,7 @@ class CudaStages:
         self.merge_launches = 0
         return Routed(arrays, off, float(stats[1]), handle=r, dev_batch=own)
 
-    def sketch_hist(self, dev_batch, k: int, w: int, rec_base: int, host_batch=None):
+    def sketch_hist(self, dev_batch, k: int, w: int, rec_base: int, route_bits: int, host_batch=None):
         """Fused routing, first half: sketch the shard, count its records per top byte of h1 (sw_dev_sketch_hist).
         Returns (Routed without arrays, counts[256])."""
         L, lb = self.L, self._lib
@@ -468,7 +483,7 @@ class CudaStages:
         self.times = lb.StageTimes()
         counts = np.zeros(256, dtype=np.uint64)
         try:
-            lb.check(L.sw_dev_sketch_hist(dev_batch, k, w, rec_base, C.byref(r), counts.ctypes.data, C.byref(self.times)))
+            lb.check(L.sw_dev_sketch_hist(dev_batch, k, w, rec_base, route_bits, C.byref(r), counts.ctypes.data, C.byref(self.times)))
         except BaseException:
             if own is not None:
                 L.sw_dev_batch_free(own)
@@ -513,7 +528,7 @@ class CudaStages:
             routed.dev_batch = None
 
     def aggregate(self, recv, n: int, byte_lo: int, byte_hi: int, record_offsets, is_targets, pairs_per_edge: float,
-                  byte_off=None):
+                  byte_off=None, range_bits: int = 8):
         """Graph of the records this rank owns (sw_dev_aggregate): the single-GPU bucket kernels on what arrived."""
         L, lb = self.L, self._lib
         torch.cuda.current_stream(self.device).synchronize()   # received records visible to the library stream
@@ -525,7 +540,7 @@ class CudaStages:
         lb.check(L.sw_dev_aggregate(C.c_void_p(ptrs[0]), C.c_void_p(ptrs[1]), C.c_void_p(ptrs[2]),
                                     C.c_void_p(ptrs[3]), n, byte_lo, byte_hi, record_offsets.ctypes.data,
                                     len(record_offsets), t_ptr, t_len, float(pairs_per_edge),
-                                    None if byte_off is None else byte_off.ctypes.data, C.byref(g), C.byref(agg)))
+                                    None if byte_off is None else byte_off.ctypes.data, range_bits, C.byref(g), C.byref(agg)))
         if self.times is not None:    # one stage record per step: the routing pass counts as part of the sort stage
             self.times.sort_nodes_ms += agg.sort_nodes_ms
             self.times.nodes_ms, self.times.edges_ms = agg.nodes_ms, agg.edges_ms
