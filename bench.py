@@ -496,6 +496,9 @@ def main():
         line["single_gpu_same_shard"] = result["single_gpu"]
     if "full_size_checks" in result:
         line["full_size_checks"] = result["full_size_checks"]
+    if "mode" in result:
+        line["config"]["multi_gpu_build"] = result["mode"]
+        line["last_step_ms_by_rank"] = result["last_step_ms_by_rank"]
     print(json.dumps(line))
     L.sw_batch_free(batch)
     if dist is not None:

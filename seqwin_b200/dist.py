@@ -171,15 +171,20 @@ def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
 
 # ---- routed build -----------------------------------------------------------------------------------------
 
-def range_bounds(world: int, bits: int = 8) -> np.ndarray:
+PAIR_WEIGHT = 0.75   # cost of an owned adjacent pair relative to a record, at the owner (partition + node kernels vs edge kernel)
+
+
+def range_bounds(world: int, bits: int = 8, pair_weight: float = PAIR_WEIGHT) -> np.ndarray:
     """Boundaries of the ranks' hash ranges in units of 2^-bits of the hash space ("bins"; bits = 8: top bytes),
     [world + 1] ascending from 0 to 2^bits.  A range owner handles the records of its range and the adjacent pairs
     they own; a pair belongs to the smaller hash, so low ranges own more pairs (density 2 (1 - x)): the boundaries
-    are the quantiles of records + pairs, (3 x - x^2) / 2 = i / world."""
+    are the quantiles of records + a * pairs, (x + a (2 x - x^2)) / (1 + a) = i / world."""
     n_bins = 1 << bits
     if world > n_bins:
         raise ValueError(f"at most {n_bins} hash ranges")
-    b = [int(round(n_bins * (3.0 - np.sqrt(9.0 - 8.0 * i / world)) / 2.0)) for i in range(world + 1)]
+    a = float(pair_weight)
+    b = [int(round(n_bins * ((1 + 2 * a) - np.sqrt((1 + 2 * a) ** 2 - 4 * a * (1 + a) * i / world)) / (2 * a)))
+         for i in range(world + 1)]
     b[0], b[-1] = 0, n_bins
     for i in range(1, world):          # strictly increasing, whatever the rounding did
         b[i] = min(max(b[i], b[i - 1] + 1), n_bins - (world - i))
@@ -187,10 +192,10 @@ def range_bounds(world: int, bits: int = 8) -> np.ndarray:
 
 
 def fused_route_bits(world: int) -> int:
-    """Bins of the fused routing pass: about four per rank -- enough to balance the ranges, few enough that the
+    """Bins of the fused routing pass: about eight per rank -- enough to balance the ranges, few enough that the
     owner's per-bin partition launches stay negligible."""
     bits = 3
-    while bits < 8 and (1 << bits) < 4 * world:
+    while bits < 8 and (1 << bits) < 8 * world:
         bits += 1
     return bits
 
@@ -923,6 +928,10 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
             d["fetch_ms"] = (t2 - t1) * 1e3
             e2e.append((float(t), d))
 
+    by_rank = [None] * world
+    last = stage_dicts[-1]
+    dist.all_gather_object(by_rank, [round(last[n], 2) for n in ("phase_local_ms", "phase_exchange_merge_ms", "phase_merge_ms",
+                                                                  "sort_nodes_ms", "nodes_ms", "edges_ms")])
     tot = torch.tensor([n_bases_local] + sizes, dtype=torch.int64, device=device)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     n_bases_total, n_k, n_n, n_e = (int(x) for x in tot)
@@ -933,7 +942,9 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     return {"stages": stage_dicts, "clocks": clocks, "e2e_runs": e2e, "n_bases_total": n_bases_total,
             "single_gpu": {"ms_per_step": float(sg), "gbp_s_per_gpu": n_bases_local / (float(sg) * 1e-3) / 1e9,
                            "what": "the same shard built and scored by one GPU without the exchange (slowest rank)"},
-            "full_size_checks": checks}
+            "full_size_checks": checks, "mode": dist_mode(),
+            "last_step_ms_by_rank": {"columns": ["local", "exchange_and_owner", "owner", "partition_passes", "nodes", "edges"],
+                                     "rows": by_rank}}
 
 
 def bench_parity(L, parity_batch, ss, rank: int, world: int, per_gpu: int, per_rank: int, k: int, w: int, bench) -> dict | None:
