@@ -1,12 +1,16 @@
 """Multi-GPU graph build: one process per GPU, genomes sharded, hash ranges owned.
 
-Routed build (the default):
-    rank r:  shard of assemblies --sketch--> minimizer records (h1, k-mer, owned neighbour hashes), stably
-             partitioned on the top byte of h1 (csrc/graph.cu route_stream)
-             all-to-all of the records by hash range (NCCL over NVLink; torch.distributed is only the plumbing)
-             the owner aggregates its range with the single-GPU bucket kernels (csrc/agg.cuh): nodes, k-mers,
-             the edges those nodes own, scoring -- nothing is left to merge
-Merge-based build (SEQWIN_DIST=merge; round 1): every rank builds the graph of its shard, the sorted node / k-mer /
+Fused build (the default):
+    rank r:  shard of assemblies --sketch--> minimizer stream; records per hash bin counted, the counts all-gathered
+             (the only collective: 64 numbers per rank at 8 ranks)
+             ONE partition pass derives every record's owned neighbour hashes and scatters (h1, k-mer, neighbours)
+             straight into the arrays of the GPU that owns the record's hash range -- peer memory mapped through
+             CUDA IPC, written over NVLink -- in (bin, source rank) order (csrc/radix.cu route_scatter)
+             after a barrier the owner aggregates its range with the single-GPU bucket kernels (csrc/agg.cuh): nodes,
+             k-mers, the edges those nodes own, scoring -- nothing is left to merge
+Routed build (SEQWIN_DIST=routed): the same with the records partitioned locally on the top byte of h1 and exchanged
+    by four NCCL all-to-alls (csrc/graph.cu route_stream).
+Merge-based build (SEQWIN_DIST=merge; round 1, and the fallback where peer memory cannot be mapped): every rank builds the graph of its shard, the sorted node / k-mer /
 edge arrays are cut at the hash boundaries, exchanged and merged by the owner (csrc/dist.cu, mirrors
 merge_thread_graphs, cpp/src/seqwin/build_internals.cpp:295-392).
 
@@ -171,7 +175,7 @@ def record_base(n_records_local: int, device, group=None) -> tuple[int, int]:
 
 # ---- routed build -----------------------------------------------------------------------------------------
 
-PAIR_WEIGHT = 0.75   # cost of an owned adjacent pair relative to a record, at the owner (partition + node kernels vs edge kernel)
+PAIR_WEIGHT = 0.6    # cost of an owned adjacent pair relative to a record, at the owner (partition + node kernels vs edge kernel)
 
 
 def range_bounds(world: int, bits: int = 8, pair_weight: float = PAIR_WEIGHT) -> np.ndarray:
@@ -209,6 +213,7 @@ class RoutedContext:
     is_targets: np.ndarray | None       # [A_total] bool
     bounds: np.ndarray                  # [world + 1] top-byte boundaries
     peer: object = None                 # PeerBuffers of the fused build, allocated on first use
+    peer_failed: bool = False           # peer memory could not be set up: the merge-based build is used instead
 
 
 def routed_context(record_offsets_local: np.ndarray, is_targets_local, group=None) -> RoutedContext:
@@ -264,8 +269,13 @@ class PeerBuffers:
     bases: list        # bases[r] = rank r's buffer as seen from this process (bases[rank] is this rank's own)
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """CUDA IPC / peer access could not be set up on some rank: the caller takes the merge-based build."""
+
+
 def ensure_peer_buffers(stages, ctx: "RoutedContext", need_items: int, group=None) -> PeerBuffers:
-    """Collective: (re)allocate the receive arrays when the largest hash range of this step does not fit."""
+    """Collective: (re)allocate the receive arrays when the largest hash range of this step does not fit.
+    Raises PeerMemoryUnavailable on EVERY rank if any rank cannot allocate or map them."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     pb = ctx.peer
     if pb is not None and pb.capacity >= need_items:
@@ -276,11 +286,31 @@ def ensure_peer_buffers(stages, ctx: "RoutedContext", need_items: int, group=Non
                 stages.peer_close(b)
         dist.barrier(group)            # nobody has this rank's memory mapped any more
         stages.peer_free(pb.bases[rank])
+        ctx.peer = None
     cap = int(need_items * 1.25) + 4096
-    mine, handle = stages.peer_alloc(4 * cap * 8)
+    mine, handle = None, None
+    try:
+        mine, handle = stages.peer_alloc(4 * cap * 8)
+    except RuntimeError:
+        pass
     handles = [None] * world
     dist.all_gather_object(handles, handle, group=group)
-    bases = [mine if r == rank else stages.peer_open(handles[r]) for r in range(world)]
+    bases, ok = [None] * world, all(h is not None for h in handles)
+    if ok:
+        try:
+            bases = [mine if r == rank else stages.peer_open(handles[r]) for r in range(world)]
+        except RuntimeError:
+            ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok, group=group)
+    if not all(oks):
+        for r, b in enumerate(bases):
+            if b is not None and r != rank:
+                stages.peer_close(b)
+        dist.barrier(group)
+        if mine is not None:
+            stages.peer_free(mine)
+        raise PeerMemoryUnavailable("CUDA IPC peer memory is not available on every rank")
     ctx.peer = PeerBuffers(cap, bases)
     return ctx.peer
 
@@ -589,25 +619,29 @@ class CudaStages:
 
 
 def dist_mode() -> str:
-    """SEQWIN_DIST: 'merge' (shard graphs merged by the range owners), 'routed' (records exchanged through NCCL
-    before they are aggregated) or 'fused' (the routing pass writes the records into the owners' memory)."""
-    return os.environ.get("SEQWIN_DIST", "merge")
+    """SEQWIN_DIST: 'fused' (default: the routing pass writes the records into the owners' memory; falls back to
+    'merge' where CUDA IPC peer memory is not available), 'routed' (records exchanged through NCCL before they are
+    aggregated) or 'merge' (shard graphs merged by the range owners)."""
+    return os.environ.get("SEQWIN_DIST", "fused")
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
                host_batch=None, overlap: bool = True, is_targets=None, class_totals=None, inspect=None, ctx=None):
     """Full multi-GPU build of this rank's hash range; returns the sw_graph handle.
-    With ctx (routed_context()) the records are routed to their range owners before they are aggregated
-    (dist_build_routed) unless SEQWIN_DIST=merge; without it the merge-based build below runs.
+    With ctx (routed_context()) the build SEQWIN_DIST names runs (dist_mode(): fused by default, which falls back to
+    the merge-based build below when peer memory cannot be set up); without ctx the merge-based build runs.
     With is_targets (bool array, the classes of THIS rank's assemblies) the graph comes back scored:
     every shard counts its own assemblies, the merge adds the counts, and the penalty is finished with
     class_totals = (targets, non-targets) over all ranks (all-reduced here when not given).
     inspect(local, merged_handle), if given, runs after the merge while the shard's own graph is still alive
     (verification hooks of bench.py)."""
     world = dist.get_world_size(group)
-    if ctx is not None and dist_mode() == "fused":
-        return dist_build_fused(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
-    if ctx is not None and dist_mode() != "merge":
+    if ctx is not None and dist_mode() == "fused" and not ctx.peer_failed:
+        try:
+            return dist_build_fused(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
+        except PeerMemoryUnavailable:      # raised on every rank alike: all of them go on with the merge-based build
+            ctx.peer_failed = True
+    elif ctx is not None and dist_mode() == "routed":
         return dist_build_routed(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
@@ -792,7 +826,7 @@ def full_size_checks(stages: "CudaStages", dev, n_records: int, k: int, w: int, 
         else:
             os.environ["SEQWIN_DIST"] = prev_mode
     L.sw_graph_free(g)
-    if ctx is not None and dist_mode() != "merge":
+    if ctx is not None and dist_mode() != "merge" and not ctx.peer_failed:
         g = dist_build(stages, dev, n_records, k, w, ctx=ctx)
         got["routed"] = sums_of(g)
         L.sw_graph_free(g)
