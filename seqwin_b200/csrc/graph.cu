@@ -897,6 +897,14 @@ uint32_t choose_slices(uint64_t M, double per_node, double per_edge, bool scored
         return cudaMemGetInfo(&f, &t) == cudaSuccess ? (double)t : 0.0;
     }();
     if (outputs + per_item * (double)M / (double)h <= 0.4 * device_bytes) return h;
+    // a large build: what the stream-ordered pool still caches from earlier (differently shaped) builds goes back to the
+    // driver first, so that the free memory reported is what this build can really have
+    {
+        cudaDeviceSynchronize();
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return h;
     const double avail = 0.9 * ((double)free_b + (double)arena_free_bytes());

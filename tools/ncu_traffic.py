@@ -44,10 +44,12 @@ def main():
         rows = list(csv.reader(out.splitlines()))
         hdr = rows[0]
         ix = {h: i for i, h in enumerate(hdr)}
+        units = dict(zip(rows[0], rows[1]))   # the unit row: every column has its own (Mbyte here, Gbyte there)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
         def val(r, key):
             try:
-                return float(r[ix[key]])
+                return float(r[ix[key]]) * scale.get(units.get(key, ""), 1.0)
             except (KeyError, ValueError):
                 return None
         for r in rows[2:]:
@@ -63,41 +65,40 @@ def main():
                 "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                 "lanes_per_instruction": val(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
             })
-    # units of the raw page: bytes come as Mbyte / Gbyte etc. depending on the column unit row -> read units
-    # (ncu prints the unit in the second header row; --page raw --csv uses base units "Mbyte" for these captures)
-    # The unit row is needed: re-read it from the first report.
-    out = subprocess.run(["ncu", "-i", a.reports[0], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    units = dict(zip(rows[0], rows[1]))
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    bscale = scale.get(units.get("dram__bytes_read.sum", "byte"), 1.0)
-    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units.get("gpu__time_duration.sum", "ms"), 1.0)
+    # one build = the launches from a first-pass sketch kernel up to the edge kernel; only the LAST complete build of the
+    # capture is summed (a capture window may start or end in the middle of one)
+    builds, cur = [], []
     for l in launches:
-        for k in ("dram_bytes_read", "dram_bytes_write"):
-            if l[k] is not None:
-                l[k] *= bscale
-        if l["duration_ms_under_ncu"] is not None:
-            l["duration_ms_under_ncu"] *= tscale
+        if l["kernel"].startswith(SKETCH) and cur and any(x["kernel"].startswith("bucket_edges_kernel") for x in cur):
+            builds.append(cur)
+            cur = []
+        cur.append(l)
+    if cur:
+        builds.append(cur)
+    complete = [b for b in builds if any(x["kernel"].startswith("reorder_kernel") for x in b)
+                and any(x["kernel"].startswith("bucket_edges_kernel") for x in b)
+                and sum(x["kernel"].startswith("sketch_sparse_kernel") for x in b) >= 2]
+    build = complete[-1] if complete else launches
 
     def group(names):
         by = OrderedDict()
-        for l in launches:
+        for l in build:
             if any(l["kernel"].startswith(n) for n in names):
                 by.setdefault(l["kernel"], []).append(l)
         tot_b = tot_ms = 0.0
         parts = {}
         for k, ls in by.items():
-            n = next((c for nm, c in per_build.items() if k.startswith(nm)), 1)
-            b = sum((x["dram_bytes_read"] or 0) + (x["dram_bytes_write"] or 0) for x in ls) / len(ls) * n
-            ms = sum(x["duration_ms_under_ncu"] or 0 for x in ls) / len(ls) * n
-            parts[k] = {"launches_per_build": n, "captured": len(ls), "dram_bytes": b, "ms_under_ncu": ms}
+            b = sum((x["dram_bytes_read"] or 0) + (x["dram_bytes_write"] or 0) for x in ls)
+            ms = sum(x["duration_ms_under_ncu"] or 0 for x in ls)
+            parts[k] = {"launches_per_build": len(ls), "dram_bytes": b, "ms_under_ncu": ms}
             tot_b += b
             tot_ms += ms
         return tot_b, tot_ms, parts
     N, M, U, E = a.n_bases, a.n_kmers, a.n_nodes, a.n_edges
     sk_b, sk_ms, sk_parts = group(SKETCH)
     ag_b, ag_ms, ag_parts = group(AGG)
-    sparse = next((l for l in launches if l["kernel"].startswith("sketch_sparse_kernel")), None)
+    sparse = max((l for l in build if l["kernel"].startswith("sketch_sparse_kernel")), key=lambda l: l["duration_ms_under_ncu"] or 0,
+                 default=None)
     res = {
         "capture": "ncu --set full --clock-control none over tools/sweep_kw.py --genomes 500 --kw 21:200 (the bench.py N=1 workload)",
         "workload": {"n_bases": N, "n_kmers": M, "n_nodes": U, "n_edges": E},
