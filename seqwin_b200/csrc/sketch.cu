@@ -223,13 +223,9 @@ __global__ void __launch_bounds__(NT) sketch_sparse_kernel(const __grid_constant
                 for (uint32_t gi = 0; gi < n_gaps; ++gi) {
                     sparseG_hash<NT>(tid, gi, s_gaps, P, T, S);
                     __syncthreads();
-                    sparseG_chunks<NT>(tid, gi, s_gaps, S);
-                    __syncthreads();
                     sparseG_windows<NT>(tid, gi, s_gaps, P, S);
                     __syncthreads();
-                    sparseG_count<NT>(tid, gi, s_gaps, P, T, S);
-                    __syncthreads();
-                    sparseG_emit<NT>(tid, gi, &s_gaps, P, T, S);
+                    if (tid == 0) sparseG_emit(gi, &s_gaps, P, T, S);
                     __syncthreads();
                 }
                 hand_over = (s_gaps.n & kGapOverflow) != 0;

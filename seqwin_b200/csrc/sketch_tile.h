@@ -661,13 +661,7 @@ struct GapList {
     uint16_t e0[kGapMax + 1];     // first entry of the stretch in the emit arrays
 };
 constexpr uint32_t kGapOverflow = 0x80000000u;
-constexpr uint32_t kGapChunk = 32;      // window minima of a stretch: prefix / suffix minima over chunks of this many k-mers
-constexpr uint32_t kGapThreadsMax = 256;
-// h | sel, pre, suf (16-bit each) | eh | ep | chunk minima | per-thread emit counts
-SW_HD constexpr size_t sparse_gap_ws_words()
-{
-    return kGapLenMax + 3 * (kGapLenMax / 4) + kGapEmitMax + kGapEmitMax / 4 + kGapLenMax / kGapChunk / 4 + kGapThreadsMax / 4;
-}
+SW_HD constexpr size_t sparse_gap_ws_words() { return kGapLenMax + kGapLenMax / 4 + kGapEmitMax + kGapEmitMax / 4; }
 SW_HD constexpr size_t sparse_list_words(uint32_t nt, uint32_t cap)
 {
     return (size_t)cap * nt > sparse_gap_ws_words() ? (size_t)cap * nt : sparse_gap_ws_words();
@@ -990,24 +984,16 @@ SW_HD void sparseD_write(int tid, uint32_t per, uint32_t flags, unsigned long lo
 struct GapWs {
     uint64_t* h;      // [kGapLenMax] h0 of the stretch's k-mers
     uint16_t* sel;    // [kGapLenMax] selection of every window of the stretch (index into h)
-    uint16_t* pre;    // [kGapLenMax] rightmost minimum of [chunk start, j]
-    uint16_t* suf;    // [kGapLenMax] rightmost minimum of [j, chunk end)
     uint64_t* eh;     // [kGapEmitMax] h0 of the minimizers to add
     uint16_t* ep;     // [kGapEmitMax] their tile-local k-mer index
-    uint16_t* cmin;   // [kGapLenMax / kGapChunk] rightmost minimum of every chunk
-    uint16_t* ecnt;   // [threads] minimizers every thread's block of windows adds
 };
 SW_HD GapWs gap_workspace(const SparseSmem& S)
 {
     GapWs g;
     g.h = S.list;
     g.sel = reinterpret_cast<uint16_t*>(S.list + kGapLenMax);
-    g.pre = g.sel + kGapLenMax;
-    g.suf = g.pre + kGapLenMax;
-    g.eh = S.list + kGapLenMax + 3 * (kGapLenMax / 4);
+    g.eh = S.list + kGapLenMax + kGapLenMax / 4;
     g.ep = reinterpret_cast<uint16_t*>(g.eh + kGapEmitMax);
-    g.cmin = g.ep + kGapEmitMax;
-    g.ecnt = g.cmin + kGapLenMax / kGapChunk;
     return g;
 }
 
@@ -1045,118 +1031,42 @@ SW_COLD void sparseG_hash(int tid, uint32_t gi, const GapList& G, const SketchPa
     }
 }
 
-// thread t: prefix / suffix minima (rightmost on ties, minimizer.cpp:75) inside chunk t of the stretch
-template <int NT>
-SW_COLD void sparseG_chunks(int tid, uint32_t gi, const GapList& G, const SparseSmem& S)
-{
-    const GapWs ws = gap_workspace(S);
-    const uint32_t g = (uint32_t)(G.b[gi] - G.a[gi] - 1);
-    for (uint32_t c = (uint32_t)tid; c * kGapChunk < g; c += NT) {
-        const uint32_t c0 = c * kGapChunk, c1 = c0 + kGapChunk < g ? c0 + kGapChunk : g;
-        uint32_t arg = c0;
-        uint64_t best = ws.h[c0];
-        ws.pre[c0] = (uint16_t)c0;
-        for (uint32_t j = c0 + 1; j < c1; ++j) {
-            const uint64_t h = ws.h[j];
-            if (h <= best) { best = h; arg = j; }
-            ws.pre[j] = (uint16_t)arg;
-        }
-        ws.cmin[c] = (uint16_t)arg;
-        arg = c1 - 1;
-        best = ws.h[arg];
-        ws.suf[arg] = (uint16_t)arg;
-        for (uint32_t j = c1 - 1; j-- > c0;) {
-            const uint64_t h = ws.h[j];
-            if (h < best) { best = h; arg = j; }
-            ws.suf[j] = (uint16_t)arg;
-        }
-    }
-}
-
-// thread t evaluates windows t, t + NT, ... of the stretch: rightmost minimum of w consecutive k-mers, from the
-// suffix minimum of the window's first chunk, the minima of the chunks it covers and the prefix minimum of its last
+// thread t evaluates windows t, t + NT, ... of the stretch: rightmost minimum of w consecutive k-mers
 template <int NT>
 SW_COLD void sparseG_windows(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const SparseSmem& S)
 {
     const GapWs ws = gap_workspace(S);
     const uint32_t g = (uint32_t)(G.b[gi] - G.a[gi] - 1), nw = g - P.w + 1;
     for (uint32_t i = (uint32_t)tid; i < nw; i += NT) {
-        const uint32_t last = i + P.w - 1, c_lo = i / kGapChunk, c_hi = last / kGapChunk;
-        uint32_t arg;
-        if (c_lo == c_hi) {   // the window lies inside one chunk: scan it
-            arg = i;
-            uint64_t best = ws.h[i];
-            for (uint32_t x = i + 1; x <= last; ++x) {
-                const uint64_t h = ws.h[x];
-                if (h <= best) { best = h; arg = x; }
-            }
-        } else {
-            arg = ws.suf[i];
-            uint64_t best = ws.h[arg];
-            for (uint32_t c = c_lo + 1; c < c_hi; ++c) {
-                const uint32_t a2 = ws.cmin[c];
-                const uint64_t h = ws.h[a2];
-                if (h <= best) { best = h; arg = a2; }
-            }
-            const uint32_t a3 = ws.pre[last];
-            if (ws.h[a3] <= best) arg = a3;
+        uint64_t best = ws.h[i];
+        uint32_t arg = i;
+        for (uint32_t x = 1; x < P.w; ++x) {
+            const uint64_t h = ws.h[i + x];
+            if (h <= best) { best = h; arg = i + x; }
         }
         ws.sel[i] = (uint16_t)arg;
     }
 }
 
-// does window i of the stretch add a minimizer?  (the selection changes, minimizer.cpp:41-47; the window before the
-// stretch's first one selected the candidate at a; window 0 of a tile that is not the record's first only provides
-// the previous selection; 2^64-1 is never emitted)
-SW_HD bool gap_window_emits(const GapWs& ws, uint32_t i, int32_t a, const Tile& T)
-{
-    const uint32_t sel = ws.sel[i];
-    const bool emit = i == 0 ? (a >= 0 || T.first != 0) : sel != ws.sel[i - 1];
-    return emit && ws.h[sel] != ~0ull;
-}
-
-// thread t owns the windows [t * per, (t + 1) * per) of the stretch: how many minimizers do they add?
-template <int NT>
-SW_COLD void sparseG_count(int tid, uint32_t gi, const GapList& G, const SketchParams& P, const Tile& T, const SparseSmem& S)
-{
-    static_assert(NT <= (int)kGapThreadsMax, "one emit count per thread");
-    const GapWs ws = gap_workspace(S);
-    const int32_t a = G.a[gi];
-    const uint32_t g = (uint32_t)(G.b[gi] - a - 1), nw = g - P.w + 1, per = (nw + NT - 1) / NT;
-    uint32_t c = 0;
-    for (uint32_t i = (uint32_t)tid * per; i < nw && i < ((uint32_t)tid + 1) * per; ++i) c += gap_window_emits(ws, i, a, T) ? 1u : 0u;
-    ws.ecnt[tid] = (uint16_t)c;
-}
-
-// ... and writes them, in window order, behind those of the threads before it (and of the stretches before this one)
-template <int NT>
-SW_COLD void sparseG_emit(int tid, uint32_t gi, GapList* G, const SketchParams& P, const Tile& T, const SparseSmem& S)
+// one thread: the windows' selections, each once, in position order (minimizer.cpp:41-47)
+SW_COLD void sparseG_emit(uint32_t gi, GapList* G, const SketchParams& P, const Tile& T, const SparseSmem& S)
 {
     const GapWs ws = gap_workspace(S);
     const int32_t a = G->a[gi];
-    const uint32_t g = (uint32_t)(G->b[gi] - a - 1), nw = g - P.w + 1, per = (nw + NT - 1) / NT;
-    uint32_t e = G->e0[gi], total = 0;
-    for (int t = 0; t < NT; ++t) {
-        const uint32_t c = ws.ecnt[t];
-        if (t < tid) e += c;
-        total += c;
-    }
-    const uint32_t end = (uint32_t)G->e0[gi] + total;
-    if (end > kGapEmitMax) {   // every thread sees the same totals
-        if (tid == 0) {
-            G->n |= kGapOverflow;
-            G->e0[gi + 1] = G->e0[gi];
-        }
-        return;
-    }
-    for (uint32_t i = (uint32_t)tid * per; i < nw && i < ((uint32_t)tid + 1) * per; ++i) {
-        if (!gap_window_emits(ws, i, a, T)) continue;
+    const uint32_t g = (uint32_t)(G->b[gi] - a - 1), nw = g - P.w + 1;
+    uint32_t e = G->e0[gi];
+    for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t sel = ws.sel[i];
+        // the window before the stretch's first one selected the candidate at a; window 0 of a tile that
+        // is not the record's first only provides the previous selection
+        const bool emit = i == 0 ? (a >= 0 || T.first != 0) : sel != ws.sel[i - 1];
+        if (!emit || ws.h[sel] == ~0ull) continue;
+        if (e >= kGapEmitMax) { G->n |= kGapOverflow; break; }
         ws.eh[e] = ws.h[sel];
         ws.ep[e] = (uint16_t)((uint32_t)(a + 1) + sel);
         ++e;
     }
-    if (tid == 0) G->e0[gi + 1] = (uint16_t)end;
+    G->e0[gi + 1] = (uint16_t)e;
 }
 
 // which thread writes the minimizers of stretch gi: the owner of the candidate after it

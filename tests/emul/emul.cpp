@@ -215,10 +215,8 @@ static void emulate_sparse(const sw_batch& b, uint32_t k, uint32_t w, double can
                 const uint32_t n_gaps = gaps.n;   // the emit phase may set the overflow bit in n
                 for (uint32_t gi = 0; gi < n_gaps; ++gi) {
                     for (int tid = 0; tid < NT; ++tid) sparseG_hash<NT>(tid, gi, gaps, P, T, S);
-                    for (int tid = 0; tid < NT; ++tid) sparseG_chunks<NT>(tid, gi, gaps, S);
                     for (int tid = 0; tid < NT; ++tid) sparseG_windows<NT>(tid, gi, gaps, P, S);
-                    for (int tid = 0; tid < NT; ++tid) sparseG_count<NT>(tid, gi, gaps, P, T, S);
-                    for (int tid = 0; tid < NT; ++tid) sparseG_emit<NT>(tid, gi, &gaps, P, T, S);
+                    sparseG_emit(gi, &gaps, P, T, S);
                 }
                 hand_over = (gaps.n & kGapOverflow) != 0;
                 if (!hand_over) ++n_gap_tiles;
