@@ -214,6 +214,7 @@ class RoutedContext:
     bounds: np.ndarray                  # [world + 1] top-byte boundaries
     peer: object = None                 # PeerBuffers of the fused build, allocated on first use
     peer_failed: bool = False           # peer memory could not be set up: the merge-based build is used instead
+    prefer_merge: bool = False          # auto mode found the set repetitive: the merge-based build is used from then on
 
 
 def routed_context(record_offsets_local: np.ndarray, is_targets_local, group=None) -> RoutedContext:
@@ -328,7 +329,8 @@ def release_peer_buffers(stages, ctx: "RoutedContext", group=None) -> None:
     ctx.peer = None
 
 
-def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", group=None, host_batch=None, inspect=None):
+def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", group=None, host_batch=None, inspect=None,
+                     auto: bool = False):
     """The routed build with the exchange fused into the routing pass: no data-path collective at all.  The ranks
     all-gather 256 counts each, derive where every shard's records of every top byte go in the owner's arrays --
     (top byte, source rank) order: global stream order inside a byte --, and the pass that generates the owned
@@ -344,15 +346,20 @@ def dist_build_fused(stages, dev_batch, k: int, w: int, ctx: "RoutedContext", gr
     if timed:
         ev[1].record()
     try:
+        # the counts, and (last column) this shard's sampled pairs per distinct pair in thousandths
+        mine_np = np.concatenate([counts.astype(np.int64), [int(round(1000.0 * routed.pairs_per_edge))]])
         if dist.get_backend(group) == "nccl":
-            mine_t = torch.from_numpy(counts.astype(np.int64)).to(stages.device)
-            every_t = torch.empty(world * 256, dtype=torch.int64, device=stages.device)
+            mine_t = torch.from_numpy(mine_np).to(stages.device)
+            every_t = torch.empty(world * 257, dtype=torch.int64, device=stages.device)
             dist.all_gather_into_tensor(every_t, mine_t, group=group)
-            mat = every_t.cpu().numpy().reshape(world, 256)
+            mat = every_t.cpu().numpy().reshape(world, 257)
         else:
             every = [None] * world
-            dist.all_gather_object(every, counts.astype(np.int64), group=group)
+            dist.all_gather_object(every, mine_np, group=group)
             mat = np.stack(every)
+        nonempty = mat[:, :256].sum(axis=1) > 0
+        if auto and nonempty.any() and float(mat[nonempty, 256].mean()) / 1000.0 >= AUTO_MERGE_PAIRS_PER_EDGE:
+            raise _PreferMerge()      # every rank sees the same numbers
         mat = mat[:, :n_bins]
         bounds = range_bounds(world, rb)
         owner = np.repeat(np.arange(world), np.diff(bounds))                 # owner of every bin
@@ -618,11 +625,22 @@ class CudaStages:
         self._merge_events[1].record()
 
 
+AUTO_MERGE_PAIRS_PER_EDGE = 8.0
+
+
 def dist_mode() -> str:
-    """SEQWIN_DIST: 'fused' (default: the routing pass writes the records into the owners' memory; falls back to
-    'merge' where CUDA IPC peer memory is not available), 'routed' (records exchanged through NCCL before they are
-    aggregated) or 'merge' (shard graphs merged by the range owners)."""
-    return os.environ.get("SEQWIN_DIST", "fused")
+    """SEQWIN_DIST: 'auto' (default), 'fused' (the routing pass writes the records into the owners' memory; falls back
+    to 'merge' where CUDA IPC peer memory is not available), 'routed' (records exchanged through NCCL before they are
+    aggregated) or 'merge' (shard graphs merged by the range owners).
+    'auto' starts as 'fused' and looks at the shards' sampled adjacent pairs per distinct pair: highly repetitive
+    sets (>= 8, e.g. the near-clonal skew set: 12) collapse so much in a local build that shipping reduced graphs
+    beats shipping records -- measured on 8 B200: 62 vs 96 ms per step -- so those take 'merge' from then on;
+    ordinary sets (15,000 synthetic genomes: 5) stay 'fused' (44.4 vs 45.4 ms; 38.0 vs 42.4 ms on 2 GPUs)."""
+    return os.environ.get("SEQWIN_DIST", "auto")
+
+
+class _PreferMerge(Exception):
+    """auto mode, raised on every rank alike: the set is repetitive enough for the merge-based build."""
 
 
 def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: int, group=None, rec_base=None,
@@ -636,12 +654,16 @@ def dist_build(stages: CudaStages, dev_batch, n_records_local: int, k: int, w: i
     inspect(local, merged_handle), if given, runs after the merge while the shard's own graph is still alive
     (verification hooks of bench.py)."""
     world = dist.get_world_size(group)
-    if ctx is not None and dist_mode() == "fused" and not ctx.peer_failed:
+    mode = dist_mode()
+    if ctx is not None and mode in ("fused", "auto") and not ctx.peer_failed and not (mode == "auto" and ctx.prefer_merge):
         try:
-            return dist_build_fused(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
+            return dist_build_fused(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect,
+                                    auto=mode == "auto")
         except PeerMemoryUnavailable:      # raised on every rank alike: all of them go on with the merge-based build
             ctx.peer_failed = True
-    elif ctx is not None and dist_mode() == "routed":
+        except _PreferMerge:               # likewise
+            ctx.prefer_merge = True
+    elif ctx is not None and mode == "routed":
         return dist_build_routed(stages, dev_batch, k, w, ctx, group, host_batch=host_batch, inspect=inspect)
     if rec_base is None:
         rec_base, _ = record_base(n_records_local, stages.device, group)
@@ -826,7 +848,7 @@ def full_size_checks(stages: "CudaStages", dev, n_records: int, k: int, w: int, 
         else:
             os.environ["SEQWIN_DIST"] = prev_mode
     L.sw_graph_free(g)
-    if ctx is not None and dist_mode() != "merge" and not ctx.peer_failed:
+    if ctx is not None and dist_mode() != "merge" and not ctx.peer_failed and not ctx.prefer_merge:
         g = dist_build(stages, dev, n_records, k, w, ctx=ctx)
         got["routed"] = sums_of(g)
         L.sw_graph_free(g)
@@ -976,7 +998,10 @@ def bench_loop(L, batch, spec, rank: int, world: int, k: int, w: int, steps: int
     return {"stages": stage_dicts, "clocks": clocks, "e2e_runs": e2e, "n_bases_total": n_bases_total,
             "single_gpu": {"ms_per_step": float(sg), "gbp_s_per_gpu": n_bases_local / (float(sg) * 1e-3) / 1e9,
                            "what": "the same shard built and scored by one GPU without the exchange (slowest rank)"},
-            "full_size_checks": checks, "mode": dist_mode(),
+            "full_size_checks": checks,
+            "mode": dist_mode() + (" -> merge (peer memory unavailable)" if ctx.peer_failed else
+                                   " -> merge (repetitive set)" if ctx.prefer_merge else
+                                   " -> fused" if dist_mode() == "auto" else ""),
             "last_step_ms_by_rank": {"columns": ["local", "exchange_and_owner", "owner", "partition_passes", "nodes", "edges"],
                                      "rows": by_rank}}
 

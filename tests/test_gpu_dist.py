@@ -50,7 +50,7 @@ def _worker(rank, world, port, paths, k, w, out_path, use_nccl, overlap=True, is
         g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t, ctx=ctx)
         parts = swd.export_graph(L, g)
         L.sw_graph_free(g)
-        if mode == "fused":   # a second build reuses the mapped receive arrays
+        if mode in ("fused", "auto"):   # a second build reuses the mapped receive arrays (auto: or the choice it made)
             g = swd.dist_build(stages, d, L.sw_batch_n_records(b), k, w, overlap=overlap, is_targets=mine_t, ctx=ctx)
             again = swd.export_graph(L, g)
             L.sw_graph_free(g)
@@ -127,7 +127,7 @@ def test_more_ranks_than_assemblies(synth_sets, tmp_path, mode):
     assert_graph_equal((got["kmers"], got["nodes"], got["edges"], want[3]), want, f"3 ranks, 2 assemblies, {mode}")
 
 
-@pytest.mark.parametrize("mode", ["fused", "routed", "merge"])
+@pytest.mark.parametrize("mode", ["auto", "fused", "routed", "merge"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_multi_rank_scored_build(synth_sets, tmp_path, world, mode):
     """Scoring across ranks.  Routed: the owner of a hash range scores the records of every shard with the global
