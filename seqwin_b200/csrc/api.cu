@@ -152,9 +152,10 @@ struct Arena {
         size_t held = 0;
         for (auto& sl : slabs) held += sl.bytes;
         size_t free_b = 0, total_b = 0;
-        if (held > ((size_t)16 << 30) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && held > total_b / 4) {
-            // a build that needed a large part of the device: the next one may be shaped differently (outputs come
-            // from the stream-ordered pool), so the slabs go back to the driver instead of staying reserved
+        if (held > ((size_t)64 << 30) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && held > total_b / 5 * 3) {
+            // a build that needed most of the device: the next one may be shaped differently (outputs come from the
+            // stream-ordered pool), so the slabs go back to the driver instead of staying reserved.  (Re-allocating
+            // them costs tens of milliseconds per build, which is why smaller arenas are kept.)
             cudaDeviceSynchronize();
             trim();
             return;
